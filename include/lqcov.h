@@ -1,0 +1,133 @@
+/* lqcov.h -- C ABI of the B200-native minimap2-coverage / sdust path (liblqcov.so).
+ *
+ * The reference (yfukasawa/LongQC) has no library interface for this path: LongQC drives two
+ * executables, `minimap2-coverage` and `sdust`, through lq_exec.py:13-38 / lq_mask.py:17-23, and
+ * consumes their stdout.  The drop-in boundary is therefore argv + stdout bytes + exit status
+ * (lqcov_main / lqcov_sdust_main below are the two `main`s; longqc_b200/bin/ holds the thin
+ * executables).  The remaining entry points expose the same pipeline on HOST BUFFERS so that
+ * bindings (ctypes, cgo, JNI ...) and the parity tests can call it without going through files;
+ * each names the reference code it replaces.
+ *
+ * Plain C types only.  Every function returns 0 on success, non-zero on error (message on stderr)
+ * unless stated otherwise.  There is NO CPU implementation behind this ABI: lqcov_create() fails if
+ * no CUDA device is usable.
+ */
+#ifndef LQCOV_H
+#define LQCOV_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LQCOV_ABI_VERSION 1
+
+/* Options == what main() of the reference holds after argp + defaulting
+ * (minimap2-coverage.c:217-388, index.c:31-38, map.c:12-44). */
+typedef struct {
+    /* indexing */
+    int k;                    /* -k, default 12 */
+    int w;                    /* -w, default 5 */
+    int is_hpc;               /* -H */
+    uint64_t batch_size;      /* -I, default 4,000,000,000 bases per index part */
+    int mini_batch_size;      /* 50,000,000 (index.c:36): granularity of the part boundary */
+    /* mapping */
+    int no_self;              /* MM_F_NO_SELF: set by -X and -Y */
+    int ava;                  /* MM_F_AVA: -X only */
+    int max_gap;              /* -g 10000 */
+    int min_cnt;              /* -n 3 */
+    int min_chain_score;      /* -m 40 */
+    int min_score_med;        /* -p (default = -m) */
+    int min_score_good;       /* -q (default = -m) */
+    int max_chain_skip;       /* -s 25 */
+    int bw;                   /* 500 (map.c:21) */
+    float mid_occ_frac;       /* 2e-4f (map.c:16) */
+    /* filtering */
+    int max_overhang;         /* -a 2000 */
+    int min_ovlp;             /* -l 1000 (parsed, unused by the reference too) */
+    int min_coverage;         /* -c 3 */
+    double min_ratio;         /* -r 0.4 */
+    int filter;               /* -f / --filter */
+    /* execution */
+    int n_threads;            /* -t: host worker threads (parsing) */
+    int device;               /* CUDA device ordinal; -1 = current / CUDA_VISIBLE_DEVICES order 0 */
+    uint64_t seed_budget;     /* seeds per device batch (0 = default 400 M) */
+    int verbose;              /* 0..3, stderr progress lines like the reference's mm_verbose */
+} lqcov_opt_t;
+
+/* A read set in memory.  seq/qual: one blob, read i occupies [seq_off[i], seq_off[i+1]).
+ * names: one blob of n NUL-terminated names back to back is NOT required; name i occupies
+ * [name_off[i], name_off[i+1]) without terminator.  qual may be NULL (FASTA).
+ * seq_on_device != 0: `seq` is a CUDA device pointer (offsets and names stay on the host). */
+typedef struct {
+    uint32_t n;
+    const char *seq;
+    const uint64_t *seq_off;
+    const char *qual;
+    const char *names;
+    const uint64_t *name_off;
+    int seq_on_device;
+} lqcov_reads_t;
+
+typedef struct lqcov_ctx lqcov_ctx;
+
+/* per-run counters (diagnostics, bench.py) */
+typedef struct {
+    uint64_t target_bases, query_bases, target_minimizers, query_minimizers;
+    uint64_t seeds, groups, chains, overlaps, batches, walk_buckets;
+    int32_t mid_occ; int32_t n_parts;
+    double t_upload_ms, t_sketch_ms, t_index_ms, t_map_ms, t_post_ms; /* host-clock phase times, informational */
+} lqcov_stats_t;
+
+int  lqcov_abi_version(void);
+void lqcov_opt_init(lqcov_opt_t *o);                       /* the defaults listed above, with -Y semantics */
+
+/* minimap2-coverage.c:217-621 as a library ---------------------------------------------------- */
+lqcov_ctx *lqcov_create(const lqcov_opt_t *o);              /* NULL on error (no usable GPU, bad options) */
+void lqcov_destroy(lqcov_ctx *c);
+/* query pre-pass: sketch every query once, allocate the per-query accumulators (minimap2-coverage.c:406-444) */
+int  lqcov_set_queries(lqcov_ctx *c, const lqcov_reads_t *queries);
+/* one index part: mm_idx_gen (index.c:311-330) + mm_mapopt_update (map.c:46-54, mid_occ frozen from the
+ * first part) + lq_map_file for every query (lqmap.c:851-855) */
+int  lqcov_add_part(lqcov_ctx *c, const lqcov_reads_t *part);
+/* whole target set in memory: cut into parts exactly as index.c:238-330 does (mini-batch rule) and add each */
+int  lqcov_add_targets(lqcov_ctx *c, const lqcov_reads_t *targets);
+/* the stdout table of minimap2-coverage.c:545-617, one row per query; *buf is malloc'ed (lqcov_free) */
+int  lqcov_table(lqcov_ctx *c, char **buf, size_t *len);
+int  lqcov_get_stats(const lqcov_ctx *c, lqcov_stats_t *s);
+void lqcov_free(void *p);
+
+/* sdust.c:187-223 as a library: the stdout table of `sdust <reads>` */
+int  lqcov_sdust_table(const lqcov_opt_t *o, const lqcov_reads_t *reads, int W, int T, char **buf, size_t *len);
+
+/* stage-level entry points (parity tests against the oracle) --------------------------------- */
+/* mm_sketch (sketch.c:76-142) of every read; records in (read, position) order.  x[i] = hash<<8|span,
+ * y[i] = rid<<32|lastPos<<1|strand, rid = rid_base + read index.  *x,*y malloc'ed. */
+int  lqcov_sketch(const lqcov_opt_t *o, const lqcov_reads_t *reads, uint32_t rid_base, uint64_t **x, uint64_t **y, uint64_t *n);
+/* seeds of query q against the CURRENT part, before and after the reference-exact sort (lqmap.c:237-238):
+ * x/y as the reference lays mm128_t seeds out (y without the tandem flag).  Arrays malloc'ed, n each. */
+int  lqcov_debug_seeds(lqcov_ctx *c, uint32_t q, uint64_t **ux, uint64_t **uy, uint64_t **sx, uint64_t **sy, uint64_t *n);
+/* index one part WITHOUT mapping (used with lqcov_debug_seeds) */
+int  lqcov_index_part(lqcov_ctx *c, const lqcov_reads_t *part);
+
+/* host helpers shared with the executables -------------------------------------------------- */
+/* FASTA/FASTQ(.gz) reader with kseq.h:185-224 + bseq.c:56-66 semantics.  Reads records until the
+ * accumulated sequence length reaches `chunk` (chunk <= 0: whole file).  The returned set lives until
+ * the next call or lqcov_reader_close.  Returns 1 = records returned, 0 = end of file, <0 = error. */
+typedef struct lqcov_reader lqcov_reader;
+lqcov_reader *lqcov_reader_open(const char *path);          /* "-" = stdin */
+int  lqcov_reader_next(lqcov_reader *r, int64_t chunk, lqcov_reads_t *out);
+/* index.c:238-290: one index PART = mini-batches until sum_len > batch_size */
+int  lqcov_reader_next_part(lqcov_reader *r, uint64_t batch_size, int mini_batch_size, lqcov_reads_t *out);
+void lqcov_reader_close(lqcov_reader *r);
+
+/* the two executables */
+int  lqcov_main(int argc, char **argv);                     /* minimap2-coverage.c:199 main */
+int  lqcov_sdust_main(int argc, char **argv);               /* sdust.c:187 main */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,86 @@
+/* lq_afsort_core.h -- the reference's seed sort, reproduced exactly.
+ *
+ * lq_map_frag_mod() sorts the seeds of a query with radix_sort_128x (reference lqmap.c:238,
+ * misc.c:125-126, ksort.h:84-134): an IN-PLACE, UNSTABLE MSD radix sort (8-bit digits from bit 56
+ * down, insertion sort for buckets of <= 64).  Seeds with equal keys end in an order that depends on
+ * the whole array, and mm_chain_dp is sensitive to it, so the permutation itself must
+ * be reproduced, not just "sorted by x".
+ *
+ * One level of that sort, seen from above.  The array is cut into 256 destination regions R_0..R_255
+ * (sizes = digit histogram).  ksort.h:109-122 repeatedly takes the element at the head of the current
+ * region; the element's digit d says which region it belongs to; it is dropped at the head of R_d and the
+ * element that was there is picked up in turn.  Hence:
+ *   * elements are picked up from every region strictly in the region's original order;
+ *   * after picking an element with digit d the next pick is from the head of R_d; if R_d is exhausted
+ *     (only possible for the region k of the outer loop) the walk moves to the next non-exhausted region;
+ *   * an element lands in R_d at slot (number of digit-d elements picked before it).
+ * So the level is: "pick-up order = a deterministic walk over 256 queues", result = stable partition of
+ * the pick-up order by digit.  lq_af_walk() runs that walk on the DIGITS ALONE (1 byte per element) and
+ * returns each element's destination; the payload is then permuted in parallel.  With only two non-empty
+ * regions the walk has a closed form (lq_af_two_dest(), prefix sums only).
+ * Buckets of <= 64 elements are finished by insertion sort, which is stable, so their final order is
+ * "by key, ties by position on entry".
+ */
+#ifndef LQ_AFSORT_CORE_H
+#define LQ_AFSORT_CORE_H
+
+#include "lq_common.h"
+
+#define LQ_RS_MIN 64
+
+/* dest[p] (0-based inside the bucket) for p in [0,n).  cnt/start: digit histogram and its exclusive
+ * scan; head[256] scratch (zeroed here). */
+LQ_HD void lq_af_walk(const uint8_t *dig, uint32_t n, const uint32_t *cnt, const uint32_t *start, uint32_t *head, uint32_t *dest)
+{
+    uint32_t k = 0, c, step, arrived_k = 0; /* arrivals into the outer-loop region lag its pick-ups by the open hole */
+    for (c = 0; c < 256; ++c) head[c] = 0;
+    while (k < 256 && cnt[k] == 0) ++k;
+    c = k;
+    for (step = 0; step < n; ++step) {
+        const uint32_t p = start[c] + head[c];
+        const uint32_t d = dig[p];
+        ++head[c];
+        /* slot = number of digit-d elements that arrived before: for d != k that is head[d] (every arrival
+         * also picked one up); for d == k it is the separate arrival counter */
+        if (d == k) dest[p] = start[k] + arrived_k++;
+        else dest[p] = start[d] + head[d];
+        c = d;
+        if (c == k && head[k] == cnt[k]) { /* region k complete: open the next non-exhausted region */
+            do { ++k; } while (k < 256 && head[k] == cnt[k]);
+            if (k < 256) { c = k; arrived_k = head[k]; }
+        }
+    }
+}
+
+/* Closed form for exactly two non-empty digits d0 < d1 (regions [0,n0) and [n0,n)).
+ * fr[p]  = 1 if p is "foreign" (p < n0 with digit d1, or p >= n0 with digit d0)
+ * rk[p]  = number of foreign positions before p within p's own region (exclusive rank)
+ * P[i]/Z[i] = i-th foreign position of region 0 / region 1.
+ *   native of region 0            -> stays
+ *   P[i]                          -> Z[i-1] + 1   (Z[-1] = n0 - 1)
+ *   Z[i]                          -> P[i]
+ *   native q of region 1          -> q + 1 if some Z lies after q, else q */
+LQ_HD uint32_t lq_af_two_dest(uint32_t p, uint32_t n0, int foreign, uint32_t rk, uint32_t n_for, const uint32_t *P, const uint32_t *Z)
+{
+    if (p < n0) {
+        if (!foreign) return p;
+        return rk == 0 ? n0 : Z[rk - 1] + 1;
+    }
+    if (foreign) return P[rk];
+    return rk < n_for ? p + 1 : p;
+}
+
+/* stable insertion sort of idx[0..n) by key[idx] (ksort.h:88-98) */
+LQ_HD void lq_af_insertion(uint32_t *idx, uint32_t n, const uint64_t *key)
+{
+    for (uint32_t i = 1; i < n; ++i) {
+        const uint32_t t = idx[i]; const uint64_t kt = key[t];
+        if (kt < key[idx[i - 1]]) {
+            uint32_t j = i;
+            while (j > 0 && kt < key[idx[j - 1]]) { idx[j] = idx[j - 1]; --j; }
+            idx[j] = t;
+        }
+    }
+}
+
+#endif

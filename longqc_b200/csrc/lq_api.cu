@@ -1,0 +1,309 @@
+/* lq_api.cu -- the C ABI of include/lqcov.h: context, part loop, host bookkeeping.
+ *
+ * Control flow mirrors main() of the reference (minimap2-coverage.c:199-621):
+ *   lqcov_set_queries  ~ :406-444   query pre-pass + accumulators
+ *   lqcov_add_part     ~ :450-458   mm_idx_reader_read + mm_mapopt_update + lq_map_file
+ *   lqcov_table        ~ :545-617   final pass
+ * All compute is on the device (lq_sketch.cu, lq_index.cu, lq_map.cu); the host keeps the per-query
+ * interval lists and formats the table (lq_table.c).
+ */
+#include <string>
+#include <vector>
+#include <unordered_map>
+#include <algorithm>
+#include <chrono>
+#include <string.h>
+#include "lq_cuda.cuh"
+#include "lq_device.h"
+#include "lq_index.h"
+#include "lq_map.h"
+#include "lq_host.h"
+#include "lqcov.h"
+
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct lqcov_ctx {
+    lqcov_opt_t opt;
+    cudaStream_t st;
+    /* queries, host side */
+    uint32_t nq;
+    std::vector<std::string> qname;
+    std::vector<int> qlen;
+    std::vector<char> qqual; std::vector<uint64_t> qqual_off; bool q_has_qual;
+    std::unordered_map<std::string, std::vector<uint32_t> > qname_map;
+    std::vector<uint64_t> qfirst;
+    std::vector<lqh_sub_v> ovlp;        /* ovlp_coords (minimap2-coverage.c:438-444) */
+    std::vector<float> avg_k;           /* avg_ks */
+    /* device */
+    LqQueryDev qd; LqIndexDev ix; LqMapScratch sc; LqReadsDev treads; LqMinimizers tmins; LqDevBuf ws;
+    /* current part */
+    std::vector<uint32_t> self_off, self_list, qrank, trank;
+    bool part_ready;
+    int32_t mid_occ;
+    lqcov_stats_t stats;
+};
+
+extern "C" int lqcov_abi_version(void) { return LQCOV_ABI_VERSION; }
+
+extern "C" void lqcov_opt_init(lqcov_opt_t *o)
+{
+    memset(o, 0, sizeof(*o));
+    o->k = 12; o->w = 5; o->is_hpc = 0; o->batch_size = 4000000000ULL; o->mini_batch_size = 50000000;
+    o->no_self = 1; o->ava = 0;
+    o->max_gap = 10000; o->min_cnt = 3; o->min_chain_score = 40; o->min_score_med = 40; o->min_score_good = 40;
+    o->max_chain_skip = 25; o->bw = 500; o->mid_occ_frac = 2e-4f;
+    o->max_overhang = 2000; o->min_ovlp = 1000; o->min_coverage = 3; o->min_ratio = 0.4; o->filter = 0;
+    o->n_threads = 1; o->device = -1; o->seed_budget = 0; o->verbose = 0;
+}
+
+extern "C" void lqcov_free(void *p) { free(p); }
+
+extern "C" lqcov_ctx *lqcov_create(const lqcov_opt_t *o)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "[lqcov] ERROR: no usable CUDA device (%s). This library has no CPU path.\n", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return 0;
+    }
+    if (o->device >= 0) { if (cudaSetDevice(o->device) != cudaSuccess) { fprintf(stderr, "[lqcov] ERROR: cannot select CUDA device %d\n", o->device); return 0; } }
+    if (o->w < 1 || o->w > LQ_MAX_W) { fprintf(stderr, "[lqcov] ERROR: -w %d outside 1..%d supported by the GPU path\n", o->w, LQ_MAX_W); return 0; }
+    if (o->k < 1 || o->k > LQ_MAX_K_DIRECT) { fprintf(stderr, "[lqcov] ERROR: -k %d outside 1..%d supported by the direct-address index of this build\n", o->k, LQ_MAX_K_DIRECT); return 0; }
+    lqcov_ctx *c = new lqcov_ctx();
+    c->opt = *o; c->nq = 0; c->q_has_qual = false; c->part_ready = false; c->mid_occ = 0;
+    memset(&c->stats, 0, sizeof(c->stats));
+    if (cudaStreamCreate(&c->st) != cudaSuccess) { fprintf(stderr, "[lqcov] ERROR: cudaStreamCreate failed\n"); delete c; return 0; }
+    return c;
+}
+
+extern "C" void lqcov_destroy(lqcov_ctx *c)
+{
+    if (!c) return;
+    cudaStreamSynchronize(c->st);
+    for (size_t i = 0; i < c->ovlp.size(); ++i) free(c->ovlp[i].a);
+    c->qd.release(); c->ix.release(); c->sc.release(); c->treads.release(); c->tmins.release(); c->ws.release();
+    cudaStreamDestroy(c->st);
+    delete c;
+}
+
+static std::string name_of(const lqcov_reads_t *r, uint32_t i) { return std::string(r->names + r->name_off[i], (size_t)(r->name_off[i + 1] - r->name_off[i])); }
+
+extern "C" int lqcov_set_queries(lqcov_ctx *c, const lqcov_reads_t *q)
+{
+    const double t0 = now_ms();
+    c->nq = q->n;
+    c->qname.resize(q->n); c->qlen.resize(q->n); c->qname_map.clear();
+    for (uint32_t i = 0; i < q->n; ++i) {
+        c->qname[i] = name_of(q, i);
+        c->qlen[i] = (int)(q->seq_off[i + 1] - q->seq_off[i]);
+        c->qname_map[c->qname[i]].push_back(i);
+    }
+    c->q_has_qual = q->qual != 0;
+    c->qqual_off.assign(q->seq_off, q->seq_off + q->n + 1);
+    if (q->qual && q->n) c->qqual.assign(q->qual + q->seq_off[0], q->qual + q->seq_off[q->n]); else c->qqual.clear();
+    for (size_t i = 0; i < c->ovlp.size(); ++i) free(c->ovlp[i].a);
+    c->ovlp.assign(q->n, lqh_sub_v());
+    for (uint32_t i = 0; i < q->n; ++i) { c->ovlp[i].n = c->ovlp[i].m = 0; c->ovlp[i].a = 0; }
+    c->avg_k.assign(q->n, 0.f);
+    LqQueryDev *qd = &c->qd;
+    qd->nq = q->n;
+    LQ_TRY(lq_reads_upload(&qd->reads, (const uint8_t*)q->seq, q->seq_off, q->n, q->seq_on_device, 0, c->st));
+    LQ_TRY(lq_sketch_run(&qd->reads, c->opt.w, c->opt.k, c->opt.is_hpc, 0, &qd->mins, c->ws, c->st));
+    qd->n_min = qd->mins.n;
+    LQ_TRY(lq_read_first(&qd->mins, 0, q->n, qd->first, c->st));
+    c->qfirst.resize((size_t)q->n + 1);
+    LQ_CUDA_OK(cudaMemcpyAsync(c->qfirst.data(), qd->first.p, ((size_t)q->n + 1) * 8, cudaMemcpyDeviceToHost, c->st));
+    LQ_TRY(qd->lambda.ensure(((size_t)q->n + 1) * 8)); LQ_TRY(qd->lambda2.ensure(((size_t)q->n + 1) * 8));
+    LQ_TRY(qd->mcnt.ensure((qd->n_min + 1) * 4));
+    LQ_CUDA_OK(cudaMemsetAsync(qd->lambda.p, 0, ((size_t)q->n + 1) * 8, c->st));
+    LQ_CUDA_OK(cudaMemsetAsync(qd->lambda2.p, 0, ((size_t)q->n + 1) * 8, c->st));
+    LQ_CUDA_OK(cudaMemsetAsync(qd->mcnt.p, 0, (qd->n_min + 1) * 4, c->st));
+    LQ_CUDA_OK(cudaStreamSynchronize(c->st));
+    for (uint32_t i = 0; i < q->n; ++i)
+        if (c->qfirst[i + 1] - c->qfirst[i] >= (1u << 24)) { fprintf(stderr, "[lqcov] ERROR: query %u has >= 2^24 minimizers\n", i); return -1; }
+    c->stats.query_bases = qd->reads.n_bases; c->stats.query_minimizers = qd->n_min;
+    c->stats.t_sketch_ms += now_ms() - t0;
+    if (c->opt.verbose >= 3) fprintf(stderr, "[M::lqcov] loaded %u query sequence(s). Total m_cnt: %llu\n", q->n, (unsigned long long)qd->n_min);
+    return 0;
+}
+
+extern "C" int lqcov_index_part(lqcov_ctx *c, const lqcov_reads_t *part)
+{
+    double t0 = now_ms();
+    LqIndexDev *ix = &c->ix;
+    LQ_TRY(lq_reads_upload(&c->treads, (const uint8_t*)part->seq, part->seq_off, part->n, part->seq_on_device, 0, c->st));
+    LQ_CUDA_OK(cudaStreamSynchronize(c->st));
+    c->stats.t_upload_ms += now_ms() - t0; t0 = now_ms();
+    LQ_TRY(lq_sketch_run(&c->treads, c->opt.w, c->opt.k, c->opt.is_hpc, 0, &ix->rec, c->ws, c->st)); /* rid restarts at 0 in every part (index.c:287) */
+    LQ_CUDA_OK(cudaStreamSynchronize(c->st));
+    c->stats.t_sketch_ms += now_ms() - t0; t0 = now_ms();
+    LQ_TRY(lq_index_alloc(ix, c->opt.k, c->st));
+    LQ_TRY(lq_index_count(ix, &ix->rec, c->st));
+    /* (several GPUs: the counts table is all-reduced and the records all-gathered here -- see longqc_b200/dist.py) */
+    LQ_TRY(lq_index_finish(ix, &ix->rec, c->ws, c->st));
+    ix->n_seq = part->n;
+    LQ_TRY(ix->tlen.ensure(((size_t)part->n + 1) * 4));
+    if (part->n) LQ_CUDA_OK(cudaMemcpyAsync(ix->tlen.p, c->treads.h_len.data(), (size_t)part->n * 4, cudaMemcpyHostToDevice, c->st));
+    if (c->mid_occ <= 0) { /* map.c:50-51: only while still unset, i.e. from the first part */
+        uint64_t nd = 0;
+        LQ_TRY(lq_index_mid_occ(ix, c->opt.mid_occ_frac, &c->mid_occ, &nd, c->ws, c->st));
+        if (c->opt.verbose >= 3) fprintf(stderr, "[M::lqcov] mid_occ = %d (distinct minimizers: %llu)\n", c->mid_occ, (unsigned long long)nd);
+    }
+    LQ_CUDA_OK(cudaStreamSynchronize(c->st));
+    c->stats.t_index_ms += now_ms() - t0;
+    /* name tables for the self-diagonal / dual-mapping skips (lqmap.c:180-189) */
+    const uint32_t nq = c->nq;
+    std::vector<std::vector<uint32_t> > lists(nq);
+    bool any = false;
+    if (c->opt.no_self || c->opt.ava)
+        for (uint32_t t = 0; t < part->n; ++t) {
+            std::unordered_map<std::string, std::vector<uint32_t> >::const_iterator it = c->qname_map.find(name_of(part, t));
+            if (it != c->qname_map.end()) { any = true; for (size_t j = 0; j < it->second.size(); ++j) lists[it->second[j]].push_back(t); }
+        }
+    c->self_off.assign((size_t)nq + 1, 0); c->self_list.clear();
+    for (uint32_t q = 0; q < nq; ++q) { c->self_off[q] = (uint32_t)c->self_list.size(); if (any) c->self_list.insert(c->self_list.end(), lists[q].begin(), lists[q].end()); }
+    c->self_off[nq] = (uint32_t)c->self_list.size();
+    c->qrank.clear(); c->trank.clear();
+    if (c->opt.ava) { /* strcmp order of names == rank among the sorted distinct names of queries and targets */
+        std::vector<std::string> all; all.reserve((size_t)nq + part->n);
+        for (uint32_t q = 0; q < nq; ++q) all.push_back(c->qname[q]);
+        for (uint32_t t = 0; t < part->n; ++t) all.push_back(name_of(part, t));
+        std::vector<std::string> uniq(all);
+        std::sort(uniq.begin(), uniq.end());
+        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+        c->qrank.resize(nq); c->trank.resize(part->n);
+        for (uint32_t q = 0; q < nq; ++q) c->qrank[q] = (uint32_t)(std::lower_bound(uniq.begin(), uniq.end(), all[q]) - uniq.begin());
+        for (uint32_t t = 0; t < part->n; ++t) c->trank[t] = (uint32_t)(std::lower_bound(uniq.begin(), uniq.end(), all[nq + t]) - uniq.begin());
+    }
+    c->part_ready = true;
+    c->stats.target_bases += c->treads.n_bases; c->stats.target_minimizers += ix->n_rec;
+    c->stats.n_parts += 1; c->stats.mid_occ = c->mid_occ;
+    if (c->opt.verbose >= 3) fprintf(stderr, "[M::lqcov] loaded/built the index for %u target sequence(s)\n", part->n);
+    return 0;
+}
+
+static void map_opt_of(const lqcov_opt_t *o, LqMapOpt *m)
+{
+    m->no_self = o->no_self; m->ava = o->ava;
+    m->max_dist = o->max_gap; m->bw = o->bw; m->max_skip = o->max_chain_skip; m->min_cnt = o->min_cnt; m->min_sc = o->min_chain_score;
+    m->min_sc_med = o->min_score_med; m->min_sc_good = o->min_score_good;
+    m->max_overhang = o->max_overhang; m->min_ratio = o->min_ratio; m->covt = 150;
+}
+
+static bool ovl_by_q(const LqOvl &a, const LqOvl &b) { return a.q < b.q; }
+
+extern "C" int lqcov_add_part(lqcov_ctx *c, const lqcov_reads_t *part)
+{
+    LQ_TRY(lqcov_index_part(c, part));
+    if (c->nq == 0) return 0;
+    double t0 = now_ms();
+    LqMapOpt mo; map_opt_of(&c->opt, &mo);
+    std::vector<LqOvl> ovl; std::vector<LqQStat> hs; LqMapStats ms; memset(&ms, 0, sizeof(ms));
+    const uint64_t cap = c->opt.seed_budget ? c->opt.seed_budget : 400000000ULL;
+    LQ_TRY(lq_map_part(&c->qd, &c->ix, &mo, c->mid_occ, c->self_off.data(), c->self_list.data(), c->qrank.data(), c->trank.data(), cap, &c->sc, &ovl, &hs, &ms, c->st));
+    c->stats.t_map_ms += now_ms() - t0; t0 = now_ms();
+    /* esterr.c:93-97: the mean k-mer span is fixed by the first part in which the query keeps a minimizer */
+    for (uint32_t q = 0; q < c->nq; ++q)
+        if (hs[q].n_kept > 0 && !hs[q].gate_closed && c->avg_k[q] == 0.f) c->avg_k[q] = (float)(uint64_t)hs[q].sum_span_kept / (int32_t)hs[q].n_kept;
+    /* lqmap.c:287: fold this part's overlaps into every query's persistent interval list */
+    std::stable_sort(ovl.begin(), ovl.end(), ovl_by_q);
+    std::vector<lqh_sub> cv;
+    for (size_t i = 0; i < ovl.size(); ) {
+        size_t j = i; cv.clear();
+        while (j < ovl.size() && ovl[j].q == ovl[i].q) { lqh_sub s; s.start = ovl[j].start; s.end = ovl[j].end; cv.push_back(s); ++j; }
+        lqh_filter_redundant(&c->ovlp[ovl[i].q], cv.data(), cv.size(), (uint32_t)c->opt.min_coverage);
+        i = j;
+    }
+    c->stats.seeds += ms.n_seeds; c->stats.groups += ms.n_groups; c->stats.chains += ms.n_chains; c->stats.overlaps += ms.n_ovl;
+    c->stats.batches += ms.n_batches; c->stats.walk_buckets += ms.n_walk_buckets;
+    c->stats.t_post_ms += now_ms() - t0;
+    if (c->opt.verbose >= 3) fprintf(stderr, "[M::lqcov] mapped %u sequences (%llu seeds, %llu chains, %llu overlaps)\n", c->nq,
+                                    (unsigned long long)ms.n_seeds, (unsigned long long)ms.n_chains, (unsigned long long)ms.n_ovl);
+    return 0;
+}
+
+extern "C" int lqcov_add_targets(lqcov_ctx *c, const lqcov_reads_t *t)
+{
+    /* index.c:238-246,316 + bseq.c:82-87: a part is a run of mini-batches, opened while sum_len <= batch_size */
+    const uint64_t mini = (uint64_t)c->opt.mini_batch_size < c->opt.batch_size ? (uint64_t)c->opt.mini_batch_size : c->opt.batch_size;
+    uint32_t t0 = 0;
+    while (t0 < t->n) {
+        uint64_t sum_len = 0; uint32_t t1 = t0;
+        while (t1 < t->n && !(sum_len > c->opt.batch_size)) {
+            uint64_t sz = 0;
+            while (t1 < t->n) { const uint64_t L = t->seq_off[t1 + 1] - t->seq_off[t1]; sz += L; sum_len += L; ++t1; if (sz >= mini) break; }
+        }
+        lqcov_reads_t part = *t;
+        part.n = t1 - t0; part.seq_off = t->seq_off + t0; part.name_off = t->name_off + t0;
+        LQ_TRY(lqcov_add_part(c, &part));
+        t0 = t1;
+    }
+    return 0;
+}
+
+extern "C" int lqcov_table(lqcov_ctx *c, char **buf, size_t *len)
+{
+    const double t0 = now_ms();
+    std::vector<uint32_t> n_match; std::vector<uint64_t> lam(c->nq), lam2(c->nq);
+    LQ_TRY(lq_map_nmatch(&c->qd, &n_match, c->st));
+    if (c->nq) {
+        LQ_CUDA_OK(cudaMemcpyAsync(lam.data(), c->qd.lambda.p, (size_t)c->nq * 8, cudaMemcpyDeviceToHost, c->st));
+        LQ_CUDA_OK(cudaMemcpyAsync(lam2.data(), c->qd.lambda2.p, (size_t)c->nq * 8, cudaMemcpyDeviceToHost, c->st));
+        LQ_CUDA_OK(cudaStreamSynchronize(c->st));
+    }
+    lqh_str out; out.l = out.m = 0; out.s = 0;
+    for (uint32_t q = 0; q < c->nq; ++q) {
+        const uint32_t n_mini = (uint32_t)(c->qfirst[q + 1] - c->qfirst[q]);
+        if (n_mini == 0) { /* the reference divides by zero here (minimap2-coverage.c:558, SIGFPE) */
+            fprintf(stderr, "[lqcov] ERROR: query '%s' yields no minimizer; the reference binary crashes on such input\n", c->qname[q].c_str());
+            free(out.s); return -1;
+        }
+        const char *qual = c->q_has_qual ? c->qqual.data() + (c->qqual_off[q] - c->qqual_off[0]) : 0;
+        lqh_format_row(&out, c->qname[q].data(), c->qname[q].size(), c->qlen[q], qual, lam[q], lam2[q], n_mini, n_match[q], c->avg_k[q],
+                       &c->ovlp[q], c->opt.min_coverage, c->opt.filter);
+    }
+    if (!out.s) { out.s = (char*)malloc(1); out.s[0] = 0; }
+    *buf = out.s; *len = out.l;
+    c->stats.t_post_ms += now_ms() - t0;
+    return 0;
+}
+
+extern "C" int lqcov_get_stats(const lqcov_ctx *c, lqcov_stats_t *s) { *s = c->stats; return 0; }
+
+extern "C" int lqcov_sketch(const lqcov_opt_t *o, const lqcov_reads_t *reads, uint32_t rid_base, uint64_t **x, uint64_t **y, uint64_t *n)
+{
+    LqReadsDev rd; LqMinimizers m; LqDevBuf ws; cudaStream_t st = 0;
+    int rc = -1;
+    *x = *y = 0; *n = 0;
+    if (o->device >= 0 && cudaSetDevice(o->device) != cudaSuccess) { fprintf(stderr, "[lqcov] ERROR: cannot select CUDA device %d\n", o->device); return -1; }
+    if (lq_reads_upload(&rd, (const uint8_t*)reads->seq, reads->seq_off, reads->n, reads->seq_on_device, 0, st) == 0 &&
+        lq_sketch_run(&rd, o->w, o->k, o->is_hpc, rid_base, &m, ws, st) == 0) {
+        std::vector<uint32_t> key(m.n); std::vector<uint8_t> sp(m.n);
+        uint64_t *hy = (uint64_t*)malloc((m.n + 1) * 8), *hx = (uint64_t*)malloc((m.n + 1) * 8);
+        bool ok = true;
+        if (m.n) {
+            ok = cudaMemcpy(key.data(), m.key.p, m.n * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                 cudaMemcpy(hy, m.y.p, m.n * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+            if (ok && m.has_span) ok = cudaMemcpy(sp.data(), m.span.p, m.n, cudaMemcpyDeviceToHost) == cudaSuccess;
+        }
+        if (ok && cudaDeviceSynchronize() == cudaSuccess) {
+            for (uint64_t i = 0; i < m.n; ++i) hx[i] = (uint64_t)key[i] << 8 | (uint64_t)(m.has_span ? sp[i] : o->k);
+            *x = hx; *y = hy; *n = m.n; rc = 0;
+        } else { fprintf(stderr, "[lqcov] CUDA error in lqcov_sketch: %s\n", cudaGetErrorString(cudaGetLastError())); free(hx); free(hy); }
+    }
+    rd.release(); m.release(); ws.release();
+    return rc;
+}
+
+extern "C" int lqcov_debug_seeds(lqcov_ctx *c, uint32_t q, uint64_t **ux, uint64_t **uy, uint64_t **sx, uint64_t **sy, uint64_t *n)
+{
+    if (!c->part_ready || q >= c->nq) return -1;
+    LqMapOpt mo; map_opt_of(&c->opt, &mo);
+    std::vector<lq_mm128> u, s;
+    LQ_TRY(lq_map_debug_sorted_seeds(&c->qd, &c->ix, &mo, c->mid_occ, q, c->self_off.data(), c->self_list.data(), c->qrank.data(), c->trank.data(), &c->sc, &u, &s, c->st));
+    *n = u.size();
+    *ux = (uint64_t*)malloc((u.size() + 1) * 8); *uy = (uint64_t*)malloc((u.size() + 1) * 8);
+    *sx = (uint64_t*)malloc((u.size() + 1) * 8); *sy = (uint64_t*)malloc((u.size() + 1) * 8);
+    for (size_t i = 0; i < u.size(); ++i) { (*ux)[i] = u[i].x; (*uy)[i] = u[i].y; (*sx)[i] = s[i].x; (*sy)[i] = s[i].y; }
+    return 0;
+}

@@ -1,0 +1,195 @@
+// lq_hostcheck.cpp -- TEST-ONLY host build of the host/device core headers.
+// Lets the CPU-only test tier (-m "not gpu") execute the exact functions the CUDA kernels are
+// built from (position-parallel sketch, sort-order walk, chain chunk resolution) against the
+// oracle.  Built as liblqcov_hostcheck.so; NEVER linked into liblqcov.so and never a fallback:
+// the product path has no CPU implementation.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "lq_common.h"
+#include "lq_sketch_core.h"
+
+namespace {
+struct VecSink {
+    std::vector<lq_mm128> *v;
+    void operator()(uint64_t x, uint64_t y) { lq_mm128 e; e.x = x; e.y = y; v->push_back(e); }
+};
+void pack_read(const char *seq, int len, int sdust_tbl, std::vector<uint32_t> &b2, std::vector<uint32_t> &nm)
+{
+    int nslot = (len + LQ_SLOT - 1) / LQ_SLOT;
+    if (nslot == 0) nslot = 1;
+    b2.assign((size_t)nslot * LQ_SLOT_W2 + 4, 0u);  // +4: the 3-word k-mer gather may touch one word past the end
+    nm.assign((size_t)nslot * LQ_SLOT_WN + 2, 0xffffffffu);
+    for (int i = 0; i < len; ++i) {
+        uint32_t c = lq_nt4((unsigned char)seq[i], sdust_tbl);
+        if (c < 4) { b2[i >> 4] |= c << ((i & 15) * 2); nm[i >> 5] &= ~(1u << (i & 31)); }
+    }
+}
+}
+
+extern "C" {
+
+// position-parallel sketch of one read (every position evaluated independently, then concatenated)
+int lqhc_sketch_parallel(const char *seq, int len, int w, int k, uint32_t rid, lq_mm128 *out, int cap)
+{
+    std::vector<uint32_t> b2, nm; std::vector<lq_mm128> v; VecSink s; s.v = &v;
+    pack_read(seq, len, 0, b2, nm);
+    for (int i = 0; i < len; ++i) lq_sketch_at(b2.data(), nm.data(), 0, len, w, k, rid, i, s);
+    int n = (int)v.size();
+    for (int i = 0; i < n && i < cap; ++i) out[i] = v[i];
+    return n;
+}
+
+// the restartable state machine run from the start of the read (HPC allowed)
+int lqhc_sketch_replay(const char *seq, int len, int w, int k, uint32_t rid, int is_hpc, lq_mm128 *out, int cap)
+{
+    std::vector<uint32_t> b2, nm; std::vector<lq_mm128> v; VecSink s; s.v = &v;
+    pack_read(seq, len, 0, b2, nm);
+    lq_sketch_replay(b2.data(), nm.data(), 0, len, w, k, rid, is_hpc, 0, 1, len - 1, 0, len, (int*)0, s);
+    int n = (int)v.size();
+    for (int i = 0; i < n && i < cap; ++i) out[i] = v[i];
+    return n;
+}
+
+// only the slow path at every position (stress of the bounded restart)
+int lqhc_sketch_slow_everywhere(const char *seq, int len, int w, int k, uint32_t rid, lq_mm128 *out, int cap)
+{
+    std::vector<uint32_t> b2, nm; std::vector<lq_mm128> v; VecSink s; s.v = &v;
+    pack_read(seq, len, 0, b2, nm);
+    for (int i = 0; i < len; ++i) lq_sketch_slow_at(b2.data(), nm.data(), 0, len, w, k, rid, i, s);
+    int n = (int)v.size();
+    for (int i = 0; i < n && i < cap; ++i) out[i] = v[i];
+    return n;
+}
+
+uint32_t lqhc_hash32(uint32_t key, uint32_t mask) { return lq_hash32(key, mask); }
+uint64_t lqhc_hash64(uint64_t key, uint64_t mask) { return lq_hash64(key, mask); }
+
+} // extern "C"
+
+// ---------------------------------------------------------------- seed sort (lq_afsort_core.h)
+#include "lq_afsort_core.h"
+namespace {
+struct Bkt { uint32_t beg, end; };
+// same orchestration as the device: level by level, buckets > 64 keep going, 2..64 get the stable insertion sort
+void afsort_levels(const uint64_t *key, uint32_t n, uint32_t *idx, int use_two)
+{
+    for (uint32_t i = 0; i < n; ++i) idx[i] = i;
+    if (n <= LQ_RS_MIN) { lq_af_insertion(idx, n, key); return; }
+    std::vector<Bkt> cur, nxt; Bkt b0 = {0, n}; cur.push_back(b0);
+    std::vector<uint8_t> dig(n); std::vector<uint32_t> dest(n), tmp(n), P, Z, rk(n); std::vector<uint8_t> fr(n);
+    for (int s = 56; s >= 0 && !cur.empty(); s -= 8) {
+        nxt.clear();
+        for (size_t bi = 0; bi < cur.size(); ++bi) {
+            const uint32_t beg = cur[bi].beg, m = cur[bi].end - cur[bi].beg;
+            uint32_t cnt[256], start[256], head[256], nb = 0, acc = 0;
+            memset(cnt, 0, sizeof(cnt));
+            for (uint32_t p = 0; p < m; ++p) { dig[beg + p] = (uint8_t)(key[idx[beg + p]] >> s); ++cnt[dig[beg + p]]; }
+            for (int d = 0; d < 256; ++d) { start[d] = acc; acc += cnt[d]; nb += cnt[d] != 0; }
+            if (nb > 1) {
+                if (nb == 2 && use_two) {
+                    int d0 = -1, d1 = -1;
+                    for (int d = 0; d < 256; ++d) if (cnt[d]) { if (d0 < 0) d0 = d; else d1 = d; }
+                    const uint32_t n0 = cnt[d0];
+                    P.clear(); Z.clear();
+                    for (uint32_t p = 0; p < m; ++p) {
+                        int f = p < n0 ? dig[beg + p] == d1 : dig[beg + p] == d0;
+                        fr[p] = (uint8_t)f;
+                        if (p < n0) { rk[p] = (uint32_t)P.size(); if (f) P.push_back(p); }
+                        else { rk[p] = (uint32_t)Z.size(); if (f) Z.push_back(p); }
+                    }
+                    for (uint32_t p = 0; p < m; ++p)
+                        dest[beg + p] = lq_af_two_dest(p, n0, fr[p], rk[p], (uint32_t)P.size(), P.data(), Z.data());
+                } else lq_af_walk(dig.data() + beg, m, cnt, start, head, dest.data() + beg);
+                for (uint32_t p = 0; p < m; ++p) tmp[beg + dest[beg + p]] = idx[beg + p];
+                memcpy(idx + beg, tmp.data() + beg, (size_t)m * 4);
+            }
+            if (s > 0) {
+                for (int d = 0; d < 256; ++d) {
+                    if (cnt[d] > LQ_RS_MIN) { Bkt b = {beg + start[d], beg + start[d] + cnt[d]}; nxt.push_back(b); }
+                    else if (cnt[d] > 1) lq_af_insertion(idx + beg + start[d], cnt[d], key);
+                }
+            }
+        }
+        cur.swap(nxt);
+    }
+}
+}
+
+extern "C" int lqhc_afsort(const uint64_t *key, uint32_t n, uint32_t *idx, int use_two) { afsort_levels(key, n, idx, use_two); return 0; }
+
+// ---------------------------------------------------------------- chaining DP: chunked (warp-shaped) vs sequential
+#include "lq_chain_core.h"
+extern "C" {
+// plain restatement of chain.c:41-80 on (rpos, qpos, span) of one (strand, target) group
+void lqhc_chain_seq(const uint32_t *rpos, const int32_t *qpos, const uint8_t *span, int n, int max_dist, int bw, int max_skip, float avg_span,
+                    int32_t *f, int32_t *p, int32_t *v)
+{
+    std::vector<int32_t> t(n, -1);
+    int st = 0;
+    for (int i = 0; i < n; ++i) {
+        int32_t best = span[i], best_j = -1, n_skip = 0;
+        while (st < i && (uint64_t)rpos[i] - rpos[st] > (uint64_t)max_dist) ++st;
+        for (int j = i - 1; j >= st; --j) {
+            int32_t sc;
+            if (!lq_chain_gain((int64_t)rpos[i] - rpos[j], qpos[i] - qpos[j], span[i], max_dist, max_dist, bw, avg_span, &sc)) continue;
+            sc += f[j];
+            if (sc > best) { best = sc; best_j = j; if (n_skip > 0) --n_skip; }
+            else if (t[j] == i) { if (++n_skip > max_skip) break; }
+            if (p[j] >= 0) t[p[j]] = i;
+        }
+        f[i] = best; p[i] = best_j;
+        v[i] = best_j >= 0 && v[best_j] > best ? v[best_j] : best;
+    }
+}
+// the kernel's shape: 32 predecessors at a time, speculative stamping, prefix-max, event replay
+void lqhc_chain_chunked(const uint32_t *rpos, const int32_t *qpos, const uint8_t *span, int n, int max_dist, int bw, int max_skip, float avg_span,
+                        int32_t *f, int32_t *p, int32_t *v)
+{
+    std::vector<int32_t> t(n, -1);
+    int st = 0;
+    for (int i = 0; i < n; ++i) {
+        int32_t best = span[i], best_j = -1, n_skip = 0;
+        bool stop = false;
+        while (st < i && (uint64_t)rpos[i] - rpos[st] > (uint64_t)max_dist) ++st;
+        for (int jb = i - 1; jb >= st && !stop; jb -= 32) {
+            bool valid[32]; int32_t sc[32]; bool tf[32];
+            for (int l = 0; l < 32; ++l) {
+                int j = jb - l; valid[l] = false; sc[l] = 0;
+                if (j < st) continue;
+                int32_t g;
+                if (!lq_chain_gain((int64_t)rpos[i] - rpos[j], qpos[i] - qpos[j], span[i], max_dist, max_dist, bw, avg_span, &g)) continue;
+                valid[l] = true; sc[l] = g + f[j];
+            }
+            for (int l = 0; l < 32; ++l) { int j = jb - l; if (valid[l] && p[j] >= 0) t[p[j]] = i; } // speculative, all lanes
+            for (int l = 0; l < 32; ++l) { int j = jb - l; tf[l] = valid[l] && t[j] == i; }
+            int32_t run = best; uint32_t newmask = 0, incmask = 0;
+            for (int l = 0; l < 32; ++l) { // exclusive prefix max seeded with `best`
+                if (valid[l] && sc[l] > run) { newmask |= 1u << l; run = sc[l]; }
+                else if (tf[l]) incmask |= 1u << l;
+            }
+            uint32_t ev = newmask | incmask; int stop_lane = 32;
+            while (ev) {
+                int l = __builtin_ctz(ev); ev &= ev - 1;
+                if (newmask >> l & 1) { if (n_skip > 0) --n_skip; }
+                else if (++n_skip > max_skip) { stop_lane = l; break; }
+            }
+            uint32_t nm = stop_lane < 32 ? newmask & ((1u << stop_lane) - 1) : newmask;
+            if (nm) { int l = 31 - __builtin_clz(nm); best = sc[l]; best_j = jb - l; }
+            if (stop_lane < 32) stop = true;
+        }
+        f[i] = best; p[i] = best_j;
+        v[i] = best_j >= 0 && v[best_j] > best ? v[best_j] : best;
+    }
+}
+}
+
+// ---------------------------------------------------------------- sdust core
+#include "lq_sdust_core.h"
+extern "C" long lqhc_sdust_masked(const char *seq, int len, int T, int W)
+{
+    int ov = 0;
+    std::vector<int> pbuf(4 * (size_t)LQ_SD_PCAP(W));
+    long m = (long)lq_sdust_masked((const uint8_t*)seq, len, T, W, pbuf.data(), LQ_SD_PCAP(W), &ov);
+    return ov ? -1 : m;
+}

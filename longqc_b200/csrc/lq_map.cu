@@ -1,0 +1,716 @@
+/* lq_map.cu -- K4..K7: seed lookup, exact seed sort, chaining, coverage accounting for a batch of queries.
+ *
+ * Replaces, per query and index part, lq_map_frag_mod() of the reference (lqmap.c:207-326):
+ *   collect_seed_hits   lqmap.c:140-205   -> lq_lookup_k, lq_qstat_k, lq_fill_k
+ *   radix_sort_128x     ksort.h:84-134    -> lq_af_* (exact permutation, see lq_afsort_core.h)
+ *   mm_chain_dp         chain.c:22-157    -> lq_chain_k (one warp per (query, strand, target) group)
+ *   mm_gen_regs         hit.c:23-88       -> region coordinates inside lq_chain_k
+ *   lq_cnt_match        esterr.c:72-140   -> overlap filter, lambda/lambda2, per-minimizer counters
+ * Queries are processed in batches bounded by a seed budget; all per-seed arrays live in two arenas.
+ */
+#include <vector>
+#include <algorithm>
+#include "lq_cuda.cuh"
+#include "lq_map.h"
+#include "lq_afsort_core.h"
+#include "lq_chain_core.h"
+
+void LqQueryDev::release()
+{
+    reads.release(); mins.release(); first.release(); lambda.release(); lambda2.release(); mcnt.release();
+    keep.release(); neff.release(); krank.release(); soff.release(); qstat.release();
+    self_off.release(); self_list.release(); qrank.release(); trank.release();
+}
+
+struct MapTables {
+    int no_self, ava;
+    const uint32_t *self_off, *self_list, *qrank, *trank;
+};
+
+/* lqmap.c:180-189: the exact self-diagonal / dual-mapping skips */
+__device__ __forceinline__ bool lq_seed_skipped(const MapTables &t, uint64_t r, uint32_t qpos, uint32_t q)
+{
+    const uint32_t rid = (uint32_t)(r >> 32), rpos = (uint32_t)r >> 1;
+    if (t.no_self && rpos == qpos)
+        for (uint32_t s = t.self_off[q]; s < t.self_off[q + 1]; ++s) if (t.self_list[s] == rid) return true;
+    if (t.ava && t.qrank[q] > t.trank[rid]) return true;
+    return false;
+}
+
+/* ------------------------------------------------------------------ K4a: lookup (one thread per query minimizer) */
+
+__global__ void lq_lookup_k(const uint32_t *__restrict__ qkey, const uint64_t *__restrict__ qy, uint64_t n_min,
+                            const uint32_t *__restrict__ counts, const uint64_t *__restrict__ offs, const uint64_t *__restrict__ pos,
+                            int mid_occ, MapTables t, const uint64_t *__restrict__ lambda, const uint32_t *__restrict__ qlen, int covt,
+                            uint32_t *__restrict__ keep, uint32_t *__restrict__ neff)
+{
+    const uint64_t mi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (mi >= n_min) return;
+    const uint64_t y = qy[mi];
+    const uint32_t q = (uint32_t)(y >> 32), key = qkey[mi];
+    const bool gate = lambda[q] / (uint64_t)qlen[q] > (uint64_t)covt; /* esterr.c:87: nothing of this query is counted in this part */
+    const uint32_t c = counts[key];
+    const bool kept = !gate && (int64_t)c < (int64_t)mid_occ;          /* lqmap.c:159,166 */
+    uint32_t n = kept ? c : 0;
+    if (n && (t.ava || (t.no_self && t.self_off[q + 1] > t.self_off[q]))) {
+        const uint64_t o = offs[key];
+        const uint32_t qpos = (uint32_t)y >> 1;
+        uint32_t skipped = 0;
+        for (uint32_t j = 0; j < c; ++j) skipped += lq_seed_skipped(t, pos[o + j], qpos, q);
+        n -= skipped;
+    }
+    keep[mi] = kept; neff[mi] = n;
+}
+
+/* ------------------------------------------------------------------ K4b: per-query statistics (one warp per query) */
+
+__global__ void lq_qstat_k(uint32_t nq, const uint64_t *__restrict__ first, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ neff,
+                           const uint8_t *__restrict__ span, int k, const uint64_t *__restrict__ lambda, const uint32_t *__restrict__ qlen, int covt,
+                           LqQStat *__restrict__ out)
+{
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    uint32_t nk = 0, ssk = 0; uint64_t ns = 0, sss = 0;
+    for (uint64_t mi = first[q] + lane; mi < first[q + 1]; mi += 32) {
+        const uint32_t sp = span ? span[mi] : (uint32_t)k;
+        if (keep[mi]) { ++nk; ssk += sp; }
+        ns += neff[mi]; sss += (uint64_t)neff[mi] * sp;
+    }
+    nk = lq_warp_sum(nk); ssk = lq_warp_sum(ssk); ns = lq_warp_sum(ns); sss = lq_warp_sum(sss);
+    if (lane == 0) {
+        LqQStat s;
+        s.n_kept = nk; s.sum_span_kept = ssk; s.n_seeds = ns; s.sum_span_seeds = sss;
+        s.gate_closed = qlen[q] ? lambda[q] / (uint64_t)qlen[q] > (uint64_t)covt : 0;
+        s.avg_span = ns ? __fdiv_rn(__ull2float_rn(sss), __ll2float_rn((long long)ns)) : 0.f; /* chain.c:38 */
+        out[q] = s;
+    }
+}
+
+/* ------------------------------------------------------------------ K4c: seed fill (one warp per kept query minimizer of the batch) */
+
+struct SeedArrays { uint64_t *sx; uint32_t *sq, *sm; };
+
+__global__ void lq_fill_k(uint64_t mi0, uint64_t mi1, const uint32_t *__restrict__ qkey, const uint64_t *__restrict__ qy, const uint8_t *__restrict__ qspan, int k,
+                          const uint64_t *__restrict__ first, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ neff,
+                          const uint32_t *__restrict__ krank, const uint64_t *__restrict__ soff, uint64_t seed_base,
+                          const uint32_t *__restrict__ counts, const uint64_t *__restrict__ offs, const uint64_t *__restrict__ pos,
+                          MapTables t, const uint32_t *__restrict__ qlen, SeedArrays s)
+{
+    const uint64_t mi = mi0 + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (mi >= mi1 || !keep[mi] || neff[mi] == 0) return;
+    const uint64_t y = qy[mi];
+    const uint32_t q = (uint32_t)(y >> 32), key = qkey[mi], c = counts[key];
+    const uint32_t qpos = (uint32_t)y >> 1, qstrand = (uint32_t)y & 1, span = qspan ? qspan[mi] : (uint32_t)k;
+    const uint32_t rank = krank[mi] - krank[first[q]];       /* index into the query's mini_pos (lqmap.c:174) */
+    const bool filt = t.ava || (t.no_self && t.self_off[q + 1] > t.self_off[q]);
+    const uint64_t o = offs[key];
+    uint64_t out = soff[mi] - seed_base;
+    const int32_t ql = (int32_t)qlen[q];
+    for (uint32_t j0 = 0; j0 < c; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        uint64_t r = 0; bool ok = j < c;
+        if (ok) { r = pos[o + j]; if (filt && lq_seed_skipped(t, r, qpos, q)) ok = false; }
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const uint64_t at = out + __popc(m & ((1u << lane) - 1));
+            const uint32_t rpos = (uint32_t)r >> 1;
+            if (((uint32_t)r & 1) == qstrand) { /* lqmap.c:191-193 */
+                s.sx[at] = (r & 0xffffffff00000000ULL) | rpos;
+                s.sq[at] = qpos;
+            } else {                             /* lqmap.c:194-197 */
+                s.sx[at] = 1ULL << 63 | (r & 0xffffffff00000000ULL) | rpos;
+                s.sq[at] = (uint32_t)(ql - ((int32_t)qpos + 1 - (int32_t)span) - 1);
+            }
+            s.sm[at] = span << 24 | rank;
+        }
+        out += __popc(m);
+    }
+}
+
+/* ------------------------------------------------------------------ K5: exact seed sort */
+
+struct AfBkt { uint32_t beg, end; };
+struct AfArgs {
+    const uint64_t *sx; uint32_t *idx, *idx2, *dest; uint8_t *dig;
+    const AfBkt *cur; const uint32_t *n_cur; AfBkt *nxt; uint32_t *n_nxt; uint32_t *cursor; uint32_t *n_walk;
+    int shift;
+};
+
+__global__ void lq_af_init_k(uint32_t nqb, const uint64_t *__restrict__ qoff /* nqb+1 seed offsets in the batch */, const uint64_t *__restrict__ sx,
+                             uint32_t *__restrict__ idx, AfBkt *__restrict__ bkt, uint32_t *__restrict__ n_bkt)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nqb) return;
+    const uint32_t beg = (uint32_t)qoff[q], end = (uint32_t)qoff[q + 1], n = end - beg;
+    if (n > LQ_RS_MIN) { const uint32_t at = atomicAdd(n_bkt, 1u); bkt[at].beg = beg; bkt[at].end = end; }
+    else if (n > 1) lq_af_insertion(idx + beg, n, sx); /* ksort.h:132 */
+}
+
+__global__ void lq_iota_k(uint32_t *idx, uint64_t n)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = (uint32_t)i;
+}
+
+#define AF_WARPS 4
+__global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
+{
+    __shared__ uint32_t s_cnt[AF_WARPS][256], s_start[AF_WARPS][256], s_head[AF_WARPS][256];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lt = (1u << lane) - 1;
+    uint32_t *cnt = s_cnt[wid], *start = s_start[wid], *head = s_head[wid];
+    const uint32_t nb_total = *a.n_cur;
+    for (;;) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(a.cursor, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= nb_total) break;
+        const uint32_t beg = a.cur[b].beg, n = a.cur[b].end - beg;
+        uint32_t *idx = a.idx + beg, *idx2 = a.idx2 + beg, *dest = a.dest + beg;
+        uint8_t *dig = a.dig + beg;
+        /* 1. digits + histogram */
+        for (uint32_t d = lane; d < 256; d += 32) cnt[d] = 0;
+        __syncwarp();
+        for (uint32_t p0 = 0; p0 < n; p0 += 32) {
+            const uint32_t p = p0 + lane; const bool ok = p < n;
+            const uint32_t act = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const uint32_t d = (uint32_t)(a.sx[idx[p]] >> a.shift) & 255u;
+                dig[p] = (uint8_t)d;
+                const uint32_t peers = __match_any_sync(act, d);
+                if ((peers & lt) == 0) cnt[d] += __popc(peers);
+            }
+            __syncwarp();
+        }
+        /* 2. region starts; lane owns digits 8*lane .. 8*lane+7 */
+        uint32_t loc = 0, ne = 0;
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) { const uint32_t c = cnt[8 * lane + j]; loc += c; if (c) ++ne; }
+        uint32_t inc = lq_warp_incl_scan(loc), run = inc - loc;
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) { start[8 * lane + j] = run; run += cnt[8 * lane + j]; }
+        const uint32_t nb = lq_warp_sum(ne);
+        __syncwarp();
+        if (nb == 2) {
+            /* closed form (lq_af_two_dest): d0 < d1 are the two non-empty digits */
+            uint32_t d0 = 256, d1 = 0;
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) if (cnt[8 * lane + j]) { d0 = min(d0, 8 * lane + j); d1 = max(d1, 8 * lane + j); }
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { d0 = min(d0, __shfl_xor_sync(0xffffffffu, d0, o)); d1 = max(d1, __shfl_xor_sync(0xffffffffu, d1, o)); }
+            const uint32_t n0 = cnt[d0];
+            uint32_t *P = idx2, *Z = idx2 + n0;
+            uint32_t runP = 0, runZ = 0;
+            for (uint32_t p0 = 0; p0 < n0; p0 += 32) {          /* region 0: foreign == digit d1 */
+                const uint32_t p = p0 + lane; const bool fr = p < n0 && dig[p] == d1;
+                const uint32_t m = __ballot_sync(0xffffffffu, fr), rk = runP + __popc(m & lt);
+                if (p < n0) dest[p] = rk;
+                if (fr) P[rk] = p;
+                runP += __popc(m);
+            }
+            for (uint32_t p0 = n0; p0 < n; p0 += 32) {          /* region 1: foreign == digit d0 */
+                const uint32_t p = p0 + lane; const bool fr = p < n && dig[p] == d0;
+                const uint32_t m = __ballot_sync(0xffffffffu, fr), rk = runZ + __popc(m & lt);
+                if (p < n) dest[p] = rk;
+                if (fr) Z[rk] = p;
+                runZ += __popc(m);
+            }
+            __syncwarp();
+            for (uint32_t p = lane; p < n; p += 32) {
+                const int fr = p < n0 ? dig[p] == d1 : dig[p] == d0;
+                dest[p] = lq_af_two_dest(p, n0, fr, dest[p], runP, P, Z);
+            }
+            __syncwarp();
+        } else if (nb > 2) {
+            if (lane == 0) { lq_af_walk(dig, n, cnt, start, head, dest); atomicAdd(a.n_walk, 1u); }
+            __syncwarp();
+        }
+        /* 4. permute the payload (indices into the seed arrays) */
+        if (nb > 1) {
+            for (uint32_t p = lane; p < n; p += 32) idx2[dest[p]] = idx[p];
+            __syncwarp();
+            for (uint32_t p = lane; p < n; p += 32) idx[p] = idx2[p];
+            __syncwarp();
+        }
+        /* 5. sub-buckets (ksort.h:124-133) */
+        if (a.shift > 0) {
+            for (uint32_t d = lane; d < 256; d += 32) {
+                const uint32_t c = cnt[d];
+                if (c > LQ_RS_MIN) { const uint32_t at = atomicAdd(a.n_nxt, 1u); a.nxt[at].beg = beg + start[d]; a.nxt[at].end = beg + start[d] + c; }
+                else if (c > 1) lq_af_insertion(idx + start[d], c, a.sx);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void lq_gather_k(uint64_t n, const uint32_t *__restrict__ idx, SeedArrays s, uint64_t *__restrict__ ax, uint32_t *__restrict__ aq, uint32_t *__restrict__ am)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = idx[i];
+    ax[i] = s.sx[j]; aq[i] = s.sq[j]; am[i] = s.sm[j];
+}
+
+/* ------------------------------------------------------------------ K6/K7: groups, chaining, accounting */
+
+/* head[i] = 1 when sorted seed i starts a (query, strand, target) run */
+__global__ void lq_heads_k(uint64_t n, const uint64_t *__restrict__ ax, uint32_t *__restrict__ head)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    head[i] = i == 0 || (ax[i] >> 32) != (ax[i - 1] >> 32);
+}
+/* ...and a query boundary is a head too */
+__global__ void lq_qheads_k(uint32_t nqb, const uint64_t *__restrict__ qoff, uint64_t n, uint32_t *__restrict__ head)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nqb && qoff[q] < n && qoff[q + 1] > qoff[q]) head[qoff[q]] = 1;
+}
+__global__ void lq_gstart_k(uint64_t n, const uint32_t *__restrict__ head, const uint32_t *__restrict__ gid, uint32_t *__restrict__ gstart)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && head[i]) gstart[gid[i]] = (uint32_t)i;
+    if (i == n) gstart[gid[n]] = (uint32_t)n; /* gid[n] = number of groups */
+}
+
+struct ChainArgs {
+    const uint64_t *ax; const uint32_t *aq, *am;
+    int32_t *f, *p, *v, *t; uint64_t *uend; uint32_t *vl, *s_lo, *s_hi;
+    const uint32_t *gstart; const uint32_t *n_groups; uint32_t *cursor;
+    uint32_t nqb, q0; const uint64_t *qoff;
+    const LqQStat *qstat; const uint32_t *qlen, *tlen; const uint64_t *first;
+    uint64_t *lambda, *lambda2; uint32_t *mcnt;
+    LqOvl *ovl; uint32_t *n_ovl; uint32_t ovl_cap; uint32_t *n_chains;
+    LqMapOpt o;
+};
+
+#define CH_WARPS 4
+__global__ void __launch_bounds__(CH_WARPS * 32) lq_chain_k(ChainArgs a)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ng = *a.n_groups;
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(a.cursor, 1u);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= ng) break;
+        const int32_t gb = (int32_t)a.gstart[g], ge = (int32_t)a.gstart[g + 1], n = ge - gb;
+        if (n < a.o.min_cnt) continue; /* a chain needs min_cnt anchors of one (strand, target) run (chain.c:116-119) */
+        /* owning query */
+        uint32_t lo = 0, hi = a.nqb;
+        while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (a.qoff[mid] <= (uint64_t)gb) lo = mid; else hi = mid; }
+        const uint32_t q = a.q0 + lo;
+        const float avg_span = a.qstat[q].avg_span;
+
+        /* ---- DP (chain.c:41-80), 32 predecessors per step ---- */
+        int32_t st = gb;
+        for (int32_t i = gb; i < ge; ++i) {
+            const uint32_t ri = (uint32_t)a.ax[i];
+            const int32_t qi = (int32_t)a.aq[i], span = (int32_t)(a.am[i] >> 24);
+            int32_t best = span, best_j = -1, n_skip = 0;
+            while (st < i) { /* advance the window start (uniform) */
+                const int32_t j = st + (int32_t)lane;
+                const bool far = j < i && (uint64_t)ri - (uint64_t)(uint32_t)a.ax[j] > (uint64_t)a.o.max_dist;
+                const uint32_t m = __ballot_sync(0xffffffffu, far);
+                const int adv = m == 0xffffffffu ? 32 : __ffs(~m) - 1; /* rpos ascending: `far` is a prefix */
+                st += adv;
+                if (adv < 32) break;
+            }
+            bool stop = false;
+            for (int32_t jb = i - 1; jb >= st && !stop; jb -= 32) {
+                const int32_t j = jb - (int32_t)lane;
+                bool valid = false; int32_t sc = INT32_MIN, pj = -1;
+                if (j >= st) {
+                    int32_t gain;
+                    if (lq_chain_gain((int64_t)ri - (int64_t)(uint32_t)a.ax[j], qi - (int32_t)a.aq[j], span, a.o.max_dist, a.o.max_dist, a.o.bw, avg_span, &gain)) {
+                        valid = true; sc = gain + a.f[j]; pj = a.p[j];
+                    }
+                }
+                if (valid && pj >= 0) a.t[pj] = i;   /* chain.c:77, for every lane: stamps past a break are never read */
+                __syncwarp();
+                const bool tflag = valid && a.t[j] == i;
+                /* exclusive prefix max over lanes, seeded with `best` */
+                int32_t pm = sc;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int32_t o = __shfl_up_sync(0xffffffffu, pm, d); if (lane >= (uint32_t)d) pm = max(pm, o); }
+                int32_t ex = __shfl_up_sync(0xffffffffu, pm, 1);
+                if (lane == 0) ex = INT32_MIN;
+                ex = max(ex, best);
+                const bool is_new = valid && sc > ex;
+                const uint32_t newmask = __ballot_sync(0xffffffffu, is_new);
+                const uint32_t incmask = __ballot_sync(0xffffffffu, valid && !is_new && tflag);
+                uint32_t ev = newmask | incmask; int stop_lane = 32;
+                while (ev) { /* replay chain.c:70-76 on the event stream (uniform across the warp) */
+                    const int l = __ffs(ev) - 1; ev &= ev - 1;
+                    if (newmask >> l & 1) { if (n_skip > 0) --n_skip; }
+                    else if (++n_skip > a.o.max_skip) { stop_lane = l; break; }
+                }
+                const uint32_t nm = stop_lane < 32 ? newmask & ((1u << stop_lane) - 1) : newmask;
+                if (nm) { const int l = 31 - __clz(nm); best = __shfl_sync(0xffffffffu, sc, l); best_j = jb - l; }
+                if (stop_lane < 32) stop = true;
+            }
+            if (lane == 0) {
+                a.f[i] = best; a.p[i] = best_j;
+                a.v[i] = best_j >= 0 && a.v[best_j] > best ? a.v[best_j] : best;
+            }
+            __syncwarp();
+        }
+
+        /* ---- chain ends (chain.c:82-101) ---- */
+        for (int32_t i = gb + lane; i < ge; i += 32) a.t[i] = 0;
+        __syncwarp();
+        for (int32_t i = gb + lane; i < ge; i += 32) if (a.p[i] >= 0) a.t[a.p[i]] = 1;
+        __syncwarp();
+        uint32_t n_end = 0;
+        for (int32_t i0 = gb; i0 < ge; i0 += 32) {
+            const int32_t i = i0 + (int32_t)lane;
+            bool is_end = i < ge && a.t[i] == 0 && a.v[i] >= a.o.min_sc;
+            uint64_t u = 0;
+            if (is_end) {
+                int32_t j = i;
+                while (j >= 0 && a.f[j] < a.v[j]) j = a.p[j];
+                if (j < 0) j = i;
+                u = (uint64_t)(uint32_t)a.f[j] << 32 | (uint32_t)j;
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, is_end);
+            if (is_end) a.uend[gb + n_end + __popc(m & ((1u << lane) - 1))] = u;
+            n_end += __popc(m);
+        }
+        __syncwarp();
+        if (n_end == 0) continue;
+        /* ---- order by (score, index) descending (chain.c:102-106; keys are distinct): rank sort, staged through
+         *      the group's slices of the head/gid arrays (dead once the group list exists) ---- */
+        uint64_t *ue = a.uend + gb;
+        if (n_end > 1) {
+            uint32_t *s_lo = a.s_lo + gb, *s_hi = a.s_hi + gb;
+            for (uint32_t e = lane; e < n_end; e += 32) {
+                const uint64_t k = ue[e]; uint32_t r = 0;
+                for (uint32_t o = 0; o < n_end; ++o) r += ue[o] > k;
+                s_lo[r] = (uint32_t)k; s_hi[r] = (uint32_t)(k >> 32);
+            }
+            __syncwarp();
+            for (uint32_t e = lane; e < n_end; e += 32) ue[e] = (uint64_t)s_hi[e] << 32 | s_lo[e];
+            __syncwarp();
+        }
+        /* ---- backtrack (chain.c:108-125) + regions (hit.c:23-38) + accounting (esterr.c:99-139) ---- */
+        for (int32_t i = gb + lane; i < ge; i += 32) a.t[i] = 0;
+        __syncwarp();
+        const int32_t qlen = (int32_t)a.qlen[q];
+        int32_t n_v = 0;
+        for (uint32_t e = 0; e < n_end; ++e) {
+            int32_t cnt = 0, score = 0, keepc = 0;
+            if (lane == 0) {
+                const int32_t n_v0 = n_v;
+                int32_t j = (int32_t)(uint32_t)ue[e];
+                do { a.vl[gb + n_v++] = (uint32_t)j; a.t[j] = 1; j = a.p[j]; } while (j >= 0 && a.t[j] == 0);
+                cnt = n_v - n_v0;
+                if (j < 0) { score = (int32_t)(ue[e] >> 32); keepc = cnt >= a.o.min_cnt; }
+                else if ((int32_t)(ue[e] >> 32) - a.f[j] >= a.o.min_sc) { score = (int32_t)(ue[e] >> 32) - a.f[j]; keepc = cnt >= a.o.min_cnt; }
+                if (!keepc) n_v = n_v0;
+            }
+            keepc = __shfl_sync(0xffffffffu, keepc, 0);
+            if (!keepc) continue;
+            cnt = __shfl_sync(0xffffffffu, cnt, 0); score = __shfl_sync(0xffffffffu, score, 0);
+            n_v = __shfl_sync(0xffffffffu, n_v, 0);
+            __syncwarp();
+            const uint32_t *anch = a.vl + gb + (n_v - cnt);      /* descending index: anch[cnt-1] is the first anchor */
+            const uint32_t i_first = anch[cnt - 1], i_last = anch[0];
+            const uint64_t x0 = a.ax[i_first];
+            const int32_t span0 = (int32_t)(a.am[i_first] >> 24), rev = (int32_t)(x0 >> 63), rid = (int32_t)(x0 << 1 >> 33);
+            const int32_t rs = (int32_t)(uint32_t)x0 + 1 > span0 ? (int32_t)(uint32_t)x0 + 1 - span0 : 0;
+            const int32_t re = (int32_t)(uint32_t)a.ax[i_last] + 1;
+            int32_t qs, qe;
+            if (!rev) { qs = (int32_t)a.aq[i_first] + 1 - span0; qe = (int32_t)a.aq[i_last] + 1; }
+            else { qs = qlen - ((int32_t)a.aq[i_last] + 1); qe = qlen - ((int32_t)a.aq[i_first] + 1 - span0); }
+            if (lane == 0) atomicAdd(a.n_chains, 1u);
+            /* esterr.c:112-119 (unsigned arithmetic, double compare) */
+            const uint32_t uqs = (uint32_t)qs, uqe = (uint32_t)qe, urs = (uint32_t)rs, ure = (uint32_t)re, rl = a.tlen[rid];
+            const uint32_t h5 = uqs < urs ? uqs : urs;
+            const uint32_t h3 = (uint32_t)qlen - uqe < rl - ure ? (uint32_t)qlen - uqe : rl - ure;
+            if ((double)(uqe - uqs) < (double)(uqe - uqs + h5 + h3) * a.o.min_ratio || h5 > (uint32_t)a.o.max_overhang || h3 > (uint32_t)a.o.max_overhang)
+                continue;
+            const uint32_t flag = score >= (int32_t)(uint16_t)a.o.min_sc_med ? 2u : 0u;
+            if (lane == 0) {
+                atomicAdd((unsigned long long*)&a.lambda[q], (unsigned long long)(uqe - uqs + 1));
+                const uint32_t at = atomicAdd(a.n_ovl, 1u);
+                if (at < a.ovl_cap) { a.ovl[at].q = q; a.ovl[at].start = uqs << 3 | flag; a.ovl[at].end = uqe << 3 | flag | 1u; }
+            }
+            if (score < (int32_t)(uint16_t)a.o.min_sc_good) continue;
+            if (lane == 0) atomicAdd((unsigned long long*)&a.lambda2[q], (unsigned long long)(uqe - uqs + 1));
+            /* esterr.c:130-137: every anchor of the chain is a kept minimizer of the query */
+            uint32_t *mc = a.mcnt + a.first[q];
+            for (int32_t c = lane; c < cnt; c += 32) atomicAdd(&mc[a.am[anch[c]] & 0xffffffu], 1u);
+        }
+        __syncwarp();
+    }
+}
+
+/* minimap2-coverage.c:552-562 */
+__global__ void lq_nmatch_k(uint32_t nq, const uint64_t *__restrict__ first, const uint32_t *__restrict__ mcnt, uint32_t *__restrict__ n_match, uint32_t *__restrict__ sat)
+{
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const uint64_t b = first[q], e = first[q + 1];
+    uint32_t sum = 0, big = 0;
+    for (uint64_t i = b + lane; i < e; i += 32) { sum += mcnt[i]; big |= mcnt[i] >= 65535u; }
+    sum = lq_warp_sum(sum); big = __any_sync(0xffffffffu, big);
+    uint32_t nm = 0;
+    if (e > b) {
+        const uint32_t mean = sum / (uint32_t)(e - b);
+        for (uint64_t i = b + lane; i < e; i += 32) nm += mcnt[i] > mean;
+        nm = lq_warp_sum(nm);
+    }
+    if (lane == 0) { n_match[q] = nm; if (big) atomicAdd(sat, 1u); }
+}
+
+/* ------------------------------------------------------------------ host orchestration */
+
+static int upload_u32(LqDevBuf &b, const uint32_t *h, size_t n, cudaStream_t st)
+{
+    LQ_TRY(b.ensure((n + 1) * 4));
+    if (n) LQ_CUDA_OK(cudaMemcpyAsync(b.p, h, n * 4, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+struct BatchPtrs {
+    SeedArrays s; uint32_t *idx, *idx2, *dest; uint8_t *dig;   /* arena1, sort phase */
+    int32_t *f, *p, *v, *t; uint64_t *uend; uint32_t *vl, *head, *gid;  /* arena1, chain phase (aliases) */
+    uint64_t *ax; uint32_t *aq, *am;                           /* arena2 */
+};
+
+static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int carve(LqMapScratch *sc, uint64_t nb, BatchPtrs *b)
+{
+    const size_t n = (size_t)nb + 64;
+    /* sort phase: sx 8, sq 4, sm 4, idx 4, idx2 4, dest 4, dig 1 */
+    const size_t sort_bytes = al(n * 8) + 5 * al(n * 4) + al(n);
+    /* chain phase: f,p,v,t 4 each, uend 8, vl 4, head 4, gid 4 */
+    const size_t chain_bytes = 7 * al(n * 4) + al(n * 8) + 256;
+    LQ_TRY(sc->arena1.ensure(std::max(sort_bytes, chain_bytes)));
+    LQ_TRY(sc->arena2.ensure(al(n * 8) + 2 * al(n * 4)));
+    char *p = (char*)sc->arena1.p;
+    b->s.sx = (uint64_t*)p; p += al(n * 8);
+    b->s.sq = (uint32_t*)p; p += al(n * 4);
+    b->s.sm = (uint32_t*)p; p += al(n * 4);
+    b->idx = (uint32_t*)p; p += al(n * 4);
+    b->idx2 = (uint32_t*)p; p += al(n * 4);
+    b->dest = (uint32_t*)p; p += al(n * 4);
+    b->dig = (uint8_t*)p;
+    p = (char*)sc->arena1.p;
+    b->uend = (uint64_t*)p; p += al(n * 8);
+    b->f = (int32_t*)p; p += al(n * 4);
+    b->p = (int32_t*)p; p += al(n * 4);
+    b->v = (int32_t*)p; p += al(n * 4);
+    b->t = (int32_t*)p; p += al(n * 4);
+    b->vl = (uint32_t*)p; p += al(n * 4);
+    b->head = (uint32_t*)p; p += al(n * 4);
+    b->gid = (uint32_t*)p;
+    p = (char*)sc->arena2.p;
+    b->ax = (uint64_t*)p; p += al(n * 8);
+    b->aq = (uint32_t*)p; p += al(n * 4);
+    b->am = (uint32_t*)p;
+    return 0;
+}
+
+/* seeds of queries [q0,q1) -> sorted arrays in arena2.  h_qoff: nqb+1 batch-relative seed offsets. */
+static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &mt, uint32_t q0, uint32_t q1, const std::vector<uint64_t> &h_first,
+                         uint64_t seed_base, uint64_t nb, const std::vector<uint64_t> &h_qoff, LqMapScratch *sc, BatchPtrs *b, uint64_t **d_qoff_out,
+                         LqMapStats *stats, cudaStream_t st)
+{
+    const uint32_t nqb = q1 - q0;
+    LQ_TRY(carve(sc, nb, b));
+    /* misc: qoff (nqb+1 u64) | counters (16 u32) */
+    LQ_TRY(sc->misc.ensure(al((size_t)(nqb + 2) * 8) + 256));
+    uint64_t *d_qoff = sc->misc.as<uint64_t>();
+    uint32_t *ctr = (uint32_t*)((char*)sc->misc.p + al((size_t)(nqb + 2) * 8));
+    LQ_CUDA_OK(cudaMemcpyAsync(d_qoff, h_qoff.data(), (size_t)(nqb + 1) * 8, cudaMemcpyHostToDevice, st));
+    LQ_CUDA_OK(cudaMemsetAsync(ctr, 0, 64, st));
+    *d_qoff_out = d_qoff;
+    if (nb == 0) return 0;
+    const uint64_t mi0 = h_first[q0], mi1 = h_first[q1];
+    if (mi1 > mi0) {
+        lq_fill_k<<<lq_grid((mi1 - mi0) * 32, 256), 256, 0, st>>>(mi0, mi1, qd->mins.key.as<uint32_t>(), qd->mins.y.as<uint64_t>(),
+            qd->mins.has_span ? qd->mins.span.as<uint8_t>() : 0, ix->k, qd->first.as<uint64_t>(), qd->keep.as<uint32_t>(), qd->neff.as<uint32_t>(),
+            qd->krank.as<uint32_t>(), qd->soff.as<uint64_t>(), seed_base, ix->counts.as<uint32_t>(), ix->offs.as<uint64_t>(), ix->rec.y.as<uint64_t>(),
+            mt, qd->reads.len.as<uint32_t>(), b->s);
+        LQ_CUDA_OK(cudaGetLastError());
+    }
+    /* bucket lists: at most nb/65 + nqb live buckets per level */
+    const size_t bcap = (size_t)(nb / (LQ_RS_MIN + 1)) + nqb + 16;
+    LQ_TRY(sc->bkt.ensure(2 * bcap * sizeof(AfBkt)));
+    AfBkt *bk[2] = { sc->bkt.as<AfBkt>(), sc->bkt.as<AfBkt>() + bcap };
+    /* counters: ctr[0],ctr[1] = bucket counts of the two lists, ctr[2] = cursor, ctr[3] = walks */
+    lq_iota_k<<<lq_grid(nb, 256), 256, 0, st>>>(b->idx, nb);
+    lq_af_init_k<<<lq_grid(nqb, 128), 128, 0, st>>>(nqb, d_qoff, b->s.sx, b->idx, bk[0], ctr + 0);
+    LQ_CUDA_OK(cudaGetLastError());
+    int cur = 0;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        AfArgs a;
+        a.sx = b->s.sx; a.idx = b->idx; a.idx2 = b->idx2; a.dest = b->dest; a.dig = b->dig;
+        a.cur = bk[cur]; a.n_cur = ctr + cur; a.nxt = bk[cur ^ 1]; a.n_nxt = ctr + (cur ^ 1); a.cursor = ctr + 2; a.n_walk = ctr + 3; a.shift = shift;
+        LQ_CUDA_OK(cudaMemsetAsync(ctr + (cur ^ 1), 0, 4, st));
+        LQ_CUDA_OK(cudaMemsetAsync(ctr + 2, 0, 4, st));
+        lq_af_level_k<<<148 * 8, AF_WARPS * 32, 0, st>>>(a);
+        LQ_CUDA_OK(cudaGetLastError());
+        cur ^= 1;
+    }
+    lq_gather_k<<<lq_grid(nb, 256), 256, 0, st>>>(nb, b->idx, b->s, b->ax, b->aq, b->am);
+    LQ_CUDA_OK(cudaGetLastError());
+    if (stats) {
+        uint32_t w = 0;
+        LQ_CUDA_OK(cudaMemcpyAsync(&w, ctr + 3, 4, cudaMemcpyDeviceToHost, st));
+        LQ_CUDA_OK(cudaStreamSynchronize(st));
+        stats->n_walk_buckets += w;
+    }
+    return 0;
+}
+
+static int run_lookup(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int mid_occ, MapTables *mt,
+                      const uint32_t *h_self_off, const uint32_t *h_self_list, const uint32_t *h_qrank, const uint32_t *h_trank,
+                      LqMapScratch *sc, std::vector<LqQStat> *h_stat, cudaStream_t st)
+{
+    const uint32_t nq = qd->nq; const uint64_t nm = qd->n_min;
+    LQ_TRY(upload_u32(qd->self_off, h_self_off, (size_t)nq + 1, st));
+    LQ_TRY(upload_u32(qd->self_list, h_self_list, h_self_off[nq], st));
+    if (opt->ava) { LQ_TRY(upload_u32(qd->qrank, h_qrank, nq, st)); LQ_TRY(upload_u32(qd->trank, h_trank, ix->n_seq, st)); }
+    mt->no_self = opt->no_self; mt->ava = opt->ava;
+    mt->self_off = qd->self_off.as<uint32_t>(); mt->self_list = qd->self_list.as<uint32_t>();
+    mt->qrank = qd->qrank.as<uint32_t>(); mt->trank = qd->trank.as<uint32_t>();
+    LQ_TRY(qd->keep.ensure((nm + 1) * 4)); LQ_TRY(qd->neff.ensure((nm + 1) * 4));
+    LQ_TRY(qd->krank.ensure((nm + 2) * 4)); LQ_TRY(qd->soff.ensure((nm + 2) * 8));
+    LQ_TRY(qd->qstat.ensure(((size_t)nq + 1) * sizeof(LqQStat)));
+    h_stat->resize(nq);
+    if (nm == 0) { for (uint32_t q = 0; q < nq; ++q) memset(&(*h_stat)[q], 0, sizeof(LqQStat)); return 0; }
+    lq_lookup_k<<<lq_grid(nm, 256), 256, 0, st>>>(qd->mins.key.as<uint32_t>(), qd->mins.y.as<uint64_t>(), nm, ix->counts.as<uint32_t>(), ix->offs.as<uint64_t>(),
+        ix->rec.y.as<uint64_t>(), mid_occ, *mt, qd->lambda.as<uint64_t>(), qd->reads.len.as<uint32_t>(), opt->covt, qd->keep.as<uint32_t>(), qd->neff.as<uint32_t>());
+    LQ_CUDA_OK(cudaGetLastError());
+    LQ_TRY((lq_exclusive_scan<uint32_t, uint32_t>(qd->keep.as<uint32_t>(), qd->krank.as<uint32_t>(), nm, 1, sc->ws, st)));
+    LQ_TRY((lq_exclusive_scan<uint32_t, uint64_t>(qd->neff.as<uint32_t>(), qd->soff.as<uint64_t>(), nm, 1, sc->ws, st)));
+    lq_qstat_k<<<lq_grid((size_t)nq * 32, 256), 256, 0, st>>>(nq, qd->first.as<uint64_t>(), qd->keep.as<uint32_t>(), qd->neff.as<uint32_t>(),
+        qd->mins.has_span ? qd->mins.span.as<uint8_t>() : 0, ix->k, qd->lambda.as<uint64_t>(), qd->reads.len.as<uint32_t>(), opt->covt, qd->qstat.as<LqQStat>());
+    LQ_CUDA_OK(cudaGetLastError());
+    LQ_CUDA_OK(cudaMemcpyAsync(h_stat->data(), qd->qstat.p, (size_t)nq * sizeof(LqQStat), cudaMemcpyDeviceToHost, st));
+    LQ_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int mid_occ,
+                const uint32_t *h_self_off, const uint32_t *h_self_list, const uint32_t *h_qrank, const uint32_t *h_trank,
+                uint64_t seed_cap, LqMapScratch *sc, std::vector<LqOvl> *ovl_out, std::vector<LqQStat> *h_stat,
+                LqMapStats *stats, cudaStream_t st)
+{
+    const uint32_t nq = qd->nq;
+    MapTables mt;
+    if (nq == 0) return 0;
+    LQ_TRY(run_lookup(qd, ix, opt, mid_occ, &mt, h_self_off, h_self_list, h_qrank, h_trank, sc, h_stat, st));
+    std::vector<uint64_t> h_first((size_t)nq + 1);
+    LQ_CUDA_OK(cudaMemcpyAsync(h_first.data(), qd->first.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st));
+    LQ_CUDA_OK(cudaStreamSynchronize(st));
+    if (seed_cap > 0x70000000ULL) seed_cap = 0x70000000ULL; /* 32-bit seed indices inside a batch */
+    uint64_t seed_base = 0;
+    for (uint32_t q0 = 0; q0 < nq; ) {
+        /* batch = consecutive queries whose seeds fit the budget */
+        uint32_t q1 = q0; uint64_t nb = 0;
+        std::vector<uint64_t> h_qoff; h_qoff.push_back(0);
+        while (q1 < nq && (q1 == q0 || nb + (*h_stat)[q1].n_seeds <= seed_cap)) { nb += (*h_stat)[q1].n_seeds; h_qoff.push_back(nb); ++q1; }
+        if (nb > 0x7fffff00ULL) { fprintf(stderr, "[lqcov] query %u alone has %llu seeds in one part: beyond the 2^31 batch limit\n", q0, (unsigned long long)nb); return -1; }
+        const uint32_t nqb = q1 - q0;
+        BatchPtrs b; uint64_t *d_qoff = 0;
+        LQ_TRY(seed_and_sort(qd, ix, mt, q0, q1, h_first, seed_base, nb, h_qoff, sc, &b, &d_qoff, stats, st));
+        if (nb > 0) {
+            uint32_t *ctr = (uint32_t*)((char*)sc->misc.p + al((size_t)(nqb + 2) * 8));
+            /* groups */
+            lq_heads_k<<<lq_grid(nb, 256), 256, 0, st>>>(nb, b.ax, b.head);
+            lq_qheads_k<<<lq_grid(nqb, 256), 256, 0, st>>>(nqb, d_qoff, nb, b.head);
+            LQ_CUDA_OK(cudaGetLastError());
+            LQ_TRY((lq_exclusive_scan<uint32_t, uint32_t>(b.head, b.gid, nb, 1, sc->ws, st)));
+            uint32_t ng = 0;
+            LQ_CUDA_OK(cudaMemcpyAsync(&ng, b.gid + nb, 4, cudaMemcpyDeviceToHost, st));
+            LQ_CUDA_OK(cudaStreamSynchronize(st));
+            LQ_TRY(sc->grp.ensure(((size_t)ng + 2) * 4));
+            lq_gstart_k<<<lq_grid(nb + 1, 256), 256, 0, st>>>(nb, b.head, b.gid, sc->grp.as<uint32_t>());
+            LQ_CUDA_OK(cudaGetLastError());
+            /* ctr[4] = n_groups, ctr[5] = cursor, ctr[6] = n_ovl, ctr[7] = n_chains */
+            const uint32_t ovl_cap = (uint32_t)std::min<uint64_t>(nb / (uint64_t)std::max(opt->min_cnt, 1) + 1024, 0x7fffffffULL);
+            LQ_TRY(sc->ovl.ensure((size_t)ovl_cap * sizeof(LqOvl)));
+            LQ_CUDA_OK(cudaMemsetAsync(ctr + 4, 0, 16, st));
+            LQ_CUDA_OK(cudaMemcpyAsync(ctr + 4, &ng, 4, cudaMemcpyHostToDevice, st));
+            ChainArgs a;
+            a.ax = b.ax; a.aq = b.aq; a.am = b.am; a.f = b.f; a.p = b.p; a.v = b.v; a.t = b.t; a.uend = b.uend; a.vl = b.vl; a.s_lo = b.head; a.s_hi = b.gid;
+            a.gstart = sc->grp.as<uint32_t>(); a.n_groups = ctr + 4; a.cursor = ctr + 5;
+            a.nqb = nqb; a.q0 = q0; a.qoff = d_qoff; a.qstat = qd->qstat.as<LqQStat>(); a.qlen = qd->reads.len.as<uint32_t>(); a.tlen = ix->tlen.as<uint32_t>();
+            a.first = qd->first.as<uint64_t>(); a.lambda = qd->lambda.as<uint64_t>(); a.lambda2 = qd->lambda2.as<uint64_t>(); a.mcnt = qd->mcnt.as<uint32_t>();
+            a.ovl = sc->ovl.as<LqOvl>(); a.n_ovl = ctr + 6; a.ovl_cap = ovl_cap; a.n_chains = ctr + 7; a.o = *opt;
+            /* the DP reads t[] before writing it only through `t[j] == i` with i a seed index of this batch: clear it */
+            LQ_CUDA_OK(cudaMemsetAsync(b.t, 0xff, (size_t)nb * 4, st));
+            lq_chain_k<<<148 * 8, CH_WARPS * 32, 0, st>>>(a);
+            LQ_CUDA_OK(cudaGetLastError());
+            uint32_t h_ctr[4];
+            LQ_CUDA_OK(cudaMemcpyAsync(h_ctr, ctr + 4, 16, cudaMemcpyDeviceToHost, st));
+            LQ_CUDA_OK(cudaStreamSynchronize(st));
+            const uint32_t n_ovl = h_ctr[2];
+            if (n_ovl > ovl_cap) { fprintf(stderr, "[lqcov] overlap list overflow (%u > %u)\n", n_ovl, ovl_cap); return -1; }
+            const size_t old = ovl_out->size();
+            ovl_out->resize(old + n_ovl);
+            if (n_ovl) LQ_CUDA_OK(cudaMemcpyAsync(ovl_out->data() + old, sc->ovl.p, (size_t)n_ovl * sizeof(LqOvl), cudaMemcpyDeviceToHost, st));
+            LQ_CUDA_OK(cudaStreamSynchronize(st));
+            if (stats) { stats->n_seeds += nb; stats->n_groups += ng; stats->n_chains += h_ctr[3]; stats->n_ovl += n_ovl; stats->n_batches += 1; }
+        }
+        seed_base += nb;
+        q0 = q1;
+    }
+    return 0;
+}
+
+int lq_map_nmatch(LqQueryDev *qd, std::vector<uint32_t> *n_match, cudaStream_t st)
+{
+    const uint32_t nq = qd->nq;
+    n_match->assign(nq, 0);
+    if (nq == 0) return 0;
+    LqDevBuf out; LQ_TRY(out.ensure(((size_t)nq + 2) * 4));
+    LQ_CUDA_OK(cudaMemsetAsync(out.p, 0, ((size_t)nq + 2) * 4, st));
+    lq_nmatch_k<<<lq_grid((size_t)nq * 32, 256), 256, 0, st>>>(nq, qd->first.as<uint64_t>(), qd->mcnt.as<uint32_t>(), out.as<uint32_t>(), out.as<uint32_t>() + nq);
+    LQ_CUDA_OK(cudaGetLastError());
+    uint32_t sat = 0;
+    LQ_CUDA_OK(cudaMemcpyAsync(n_match->data(), out.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    LQ_CUDA_OK(cudaMemcpyAsync(&sat, out.as<uint32_t>() + nq, 4, cudaMemcpyDeviceToHost, st));
+    LQ_CUDA_OK(cudaStreamSynchronize(st));
+    out.release();
+    if (sat) fprintf(stderr, "[lqcov] WARNING: %u queries have a minimizer matched >= 65535 times: the reference's uint16 counters saturate "
+                             "in an order-dependent way there (esterr.c:130-137); column 8 of those rows is outside the parity domain\n", sat);
+    return 0;
+}
+
+int lq_map_debug_sorted_seeds(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int mid_occ, uint32_t q,
+                              const uint32_t *h_self_off, const uint32_t *h_self_list, const uint32_t *h_qrank, const uint32_t *h_trank,
+                              LqMapScratch *sc, std::vector<lq_mm128> *unsorted, std::vector<lq_mm128> *sorted, cudaStream_t st)
+{
+    MapTables mt; std::vector<LqQStat> hs;
+    LQ_TRY(run_lookup(qd, ix, opt, mid_occ, &mt, h_self_off, h_self_list, h_qrank, h_trank, sc, &hs, st));
+    std::vector<uint64_t> h_first((size_t)qd->nq + 1);
+    LQ_CUDA_OK(cudaMemcpyAsync(h_first.data(), qd->first.p, ((size_t)qd->nq + 1) * 8, cudaMemcpyDeviceToHost, st));
+    LQ_CUDA_OK(cudaStreamSynchronize(st));
+    uint64_t base = 0; for (uint32_t i = 0; i < q; ++i) base += hs[i].n_seeds;
+    const uint64_t nb = hs[q].n_seeds;
+    std::vector<uint64_t> h_qoff(2); h_qoff[0] = 0; h_qoff[1] = nb;
+    BatchPtrs b; uint64_t *d_qoff = 0;
+    LQ_TRY(seed_and_sort(qd, ix, mt, q, q + 1, h_first, base, nb, h_qoff, sc, &b, &d_qoff, 0, st));
+    std::vector<uint64_t> x(nb), x2(nb); std::vector<uint32_t> sq(nb), sm(nb), aq(nb), am(nb);
+    if (nb) {
+        LQ_CUDA_OK(cudaMemcpyAsync(x.data(), b.s.sx, nb * 8, cudaMemcpyDeviceToHost, st));
+        LQ_CUDA_OK(cudaMemcpyAsync(sq.data(), b.s.sq, nb * 4, cudaMemcpyDeviceToHost, st));
+        LQ_CUDA_OK(cudaMemcpyAsync(sm.data(), b.s.sm, nb * 4, cudaMemcpyDeviceToHost, st));
+        LQ_CUDA_OK(cudaMemcpyAsync(x2.data(), b.ax, nb * 8, cudaMemcpyDeviceToHost, st));
+        LQ_CUDA_OK(cudaMemcpyAsync(aq.data(), b.aq, nb * 4, cudaMemcpyDeviceToHost, st));
+        LQ_CUDA_OK(cudaMemcpyAsync(am.data(), b.am, nb * 4, cudaMemcpyDeviceToHost, st));
+        LQ_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    unsorted->resize(nb); sorted->resize(nb);
+    for (uint64_t i = 0; i < nb; ++i) {
+        (*unsorted)[i].x = x[i]; (*unsorted)[i].y = (uint64_t)(sm[i] >> 24) << 32 | sq[i];
+        (*sorted)[i].x = x2[i];  (*sorted)[i].y = (uint64_t)(am[i] >> 24) << 32 | aq[i];
+    }
+    return 0;
+}

@@ -1,0 +1,345 @@
+/* lq_sketch.cu -- K0 (ASCII -> 2-bit + ambiguity planes) and K1 (position-parallel (w,k)-minimizer sketch).
+ *
+ * Replaces, on the device, mm_sketch() as called for every target read (reference index.c:291-302)
+ * and every query read (minimap2-coverage.c:419, lqmap.c:131).  See lq_sketch_core.h for why the
+ * position-parallel form is exact.
+ *
+ * K1 launch shape: one CTA per tile of 1024 bases (8 slots), 256 threads, 4 bases per thread.
+ *   stage 0  the tile's 2-bit words (+256-base halo) and ambiguity words go to shared memory
+ *   stage A  every base of tile+128-base halo gets its candidate: 2k-bit hash of min(fw,rv), strand bit,
+ *            and an "ok" bit (pushes into the reference's ring: unambiguous and not palindromic)
+ *   stage B  every base of the tile evaluates what the reference scan pushes while processing it:
+ *            closed form over the candidates at i-w..i when the last w+k bases are all ok (fast path),
+ *            else a bounded replay of the reference state machine (lq_sketch_slow_at)
+ *   output   records are written in base order: block scan of the per-thread record counts + the CTA's
+ *            base offset (from the count pass, see lq_sketch_run()).
+ * Output is therefore globally ordered by (read, position) == ascending y, which the index build needs.
+ */
+#include "lq_cuda.cuh"
+#include "lq_sketch_core.h"
+#include "lq_device.h"
+
+#define SK_THREADS 256
+#define SK_PER_THREAD 4
+#define SK_TILE (SK_THREADS * SK_PER_THREAD)   /* 1024 bases */
+#define SK_HALO 128                            /* candidates kept before the tile */
+#define SK_HALO_W 256                          /* packed words kept before the tile */
+#define SK_NPOS (SK_TILE + SK_HALO)
+#define SK_BUF 8                               /* records a thread buffers between count and write */
+
+/* ------------------------------------------------------------------ K0: pack */
+
+__global__ void lq_pack_k(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ seq_off, const uint64_t *__restrict__ slot0,
+                          const uint32_t *__restrict__ len, uint32_t n_reads, uint64_t n_slots, int sdust_tbl,
+                          uint32_t *__restrict__ b2, uint32_t *__restrict__ nm, uint32_t *__restrict__ slot_read)
+{
+    /* one thread per 32 bases: two 2-bit words and one ambiguity word */
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t slot = t >> 2;
+    if (slot >= n_slots) return;
+    /* owner read of the slot: last r with slot0[r] <= slot */
+    uint32_t lo = 0, hi = n_reads;
+    while (hi - lo > 1) { uint32_t mid = lo + ((hi - lo) >> 1); if (slot0[mid] <= slot) lo = mid; else hi = mid; }
+    const uint32_t rd = lo;
+    if ((t & 3) == 0) slot_read[slot] = rd;
+    const uint64_t i0 = (slot - slot0[rd]) * LQ_SLOT + (t & 3) * 32;
+    const uint64_t L = len[rd];
+    const uint8_t *s = seq + seq_off[rd];
+    uint32_t w0 = 0, w1 = 0, m = 0;
+    #pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+        uint32_t c = 4;
+        if (i0 + j < L) c = lq_nt4(s[i0 + j], sdust_tbl);
+        if (c < 4) { if (j < 16) w0 |= c << (2 * j); else w1 |= c << (2 * (j - 16)); }
+        else m |= 1u << j;
+    }
+    b2[t * 2] = w0; b2[t * 2 + 1] = w1; nm[t] = m;
+}
+
+/* ------------------------------------------------------------------ K1: sketch */
+
+struct SkCount { int n; __device__ __forceinline__ void operator()(uint64_t, uint64_t) { ++n; } };
+struct SkBuf {
+    uint64_t x[SK_BUF], y[SK_BUF]; int n;
+    __device__ __forceinline__ void operator()(uint64_t x_, uint64_t y_) { if (n < SK_BUF) { x[n] = x_; y[n] = y_; } ++n; }
+};
+struct SkWrite {
+    uint32_t *key; uint64_t *yy; uint64_t at;
+    __device__ __forceinline__ void operator()(uint64_t x_, uint64_t y_) { key[at] = (uint32_t)(x_ >> 8); yy[at] = y_; ++at; }
+};
+
+struct SkArgs {
+    const uint32_t *b2, *nm, *slot_read, *len;
+    const uint64_t *slot0;
+    uint64_t n_slots;
+    int w, k;
+    uint32_t rid_base;
+    uint32_t *blk_count;        /* count pass: records per CTA */
+    const uint64_t *blk_base;   /* write pass: exclusive prefix of blk_count */
+    uint32_t *out_key; uint64_t *out_y;
+};
+
+template <class Sink>
+__device__ __forceinline__ void sk_eval(const SkArgs &a, const uint32_t *s_b2, const uint32_t *cand, const uint32_t *okb, const uint32_t *zb,
+                                        int idx /* index into cand[] */, uint64_t g, Sink &sink)
+{
+    const uint64_t slot = g >> 7;
+    if (slot >= a.n_slots) return;
+    const uint32_t rd = a.slot_read[slot];
+    const uint64_t s0 = a.slot0[rd];
+    const int L = (int)a.len[rd];
+    const int i = (int)((slot - s0) * LQ_SLOT + (g & 127));
+    if (i >= L) return;
+    const int need = a.w + a.k - 1;
+    bool fast = i >= need;
+    if (fast) {
+        /* ok bits of idx-need..idx, all must be set; need+1 <= 60 */
+        const int lo = idx - need;
+        const uint32_t wi = (uint32_t)lo >> 5, sh = (uint32_t)lo & 31;
+        uint64_t bits = ((uint64_t)okb[wi] | (uint64_t)okb[wi + 1] << 32) >> sh;
+        if (sh) bits |= (uint64_t)okb[wi + 2] << (64 - sh);
+        const uint64_t want = (need + 1 >= 64) ? ~0ULL : ((1ULL << (need + 1)) - 1);
+        fast = (bits & want) == want;
+    }
+    if (fast) {
+        uint64_t cx[LQ_MAX_W + 1]; uint32_t cz[LQ_MAX_W + 1];
+        const int w = a.w;
+        #pragma unroll 1
+        for (int j = 0; j <= w; ++j) {
+            const int p = idx - w + j;
+            cx[j] = (uint64_t)cand[p] << 8 | (uint64_t)a.k;
+            cz[j] = (zb[p >> 5] >> (p & 31)) & 1u;
+        }
+        lq_sketch_fast_at(cx, w, a.rid_base + rd, i, cz, i == L - 1, sink);
+    } else {
+        lq_sketch_slow_at(a.b2, a.nm, s0 * LQ_SLOT, L, a.w, a.k, a.rid_base + rd, i, sink);
+    }
+}
+
+template <int WRITE>
+__global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
+{
+    __shared__ uint32_t s_b2[(SK_TILE + SK_HALO_W) / 16 + 4];
+    __shared__ uint32_t s_nm[(SK_TILE + SK_HALO_W) / 32 + 2];
+    __shared__ uint32_t cand[SK_NPOS];
+    __shared__ uint32_t okb[SK_NPOS / 32 + 2], zb[SK_NPOS / 32 + 2];
+    __shared__ uint64_t scan_sm[33];
+
+    const int tid = threadIdx.x;
+    const int64_t T0 = (int64_t)blockIdx.x * SK_TILE;   /* first base of the tile (global base index) */
+    const int64_t W0 = T0 - SK_HALO_W;                    /* first base held in shared memory */
+    const int64_t n_bases = (int64_t)a.n_slots * LQ_SLOT;
+
+    /* stage 0 */
+    for (int j = tid; j < (SK_TILE + SK_HALO_W) / 16 + 4; j += SK_THREADS) {
+        int64_t wi = W0 / 16 + j;
+        s_b2[j] = (wi >= 0 && wi < n_bases / 16) ? a.b2[wi] : 0u;
+    }
+    for (int j = tid; j < (SK_TILE + SK_HALO_W) / 32 + 2; j += SK_THREADS) {
+        int64_t wi = W0 / 32 + j;
+        s_nm[j] = (wi >= 0 && wi < n_bases / 32) ? a.nm[wi] : 0xffffffffu;
+    }
+    if (tid < 2) { okb[SK_NPOS / 32 + tid] = 0; zb[SK_NPOS / 32 + tid] = 0; }
+    __syncthreads();
+
+    /* stage A: candidates for bases T0-128 .. T0+1023 (idx 0..1151); warps cover 32 consecutive idx */
+    for (int idx = tid; idx < SK_NPOS; idx += SK_THREADS) {
+        const int64_t g = T0 - SK_HALO + idx;
+        uint32_t ok = 0, z = 0, h32 = 0;
+        if (g >= 0 && (g >> 7) < (int64_t)a.n_slots) {
+            const uint64_t slot = (uint64_t)g >> 7;
+            const uint32_t rd = a.slot_read[slot];
+            const uint64_t s0 = a.slot0[rd];
+            const int L = (int)a.len[rd];
+            const int i = (int)((slot - s0) * LQ_SLOT + ((uint64_t)g & 127));
+            const uint64_t sg = (uint64_t)(g - W0);          /* index relative to the shared copies */
+            if (i < L && !lq_amb_at(s_nm, sg)) {
+                if (i >= a.k - 1 && !lq_amb_any(s_nm, sg - (uint64_t)(a.k - 1), sg)) {
+                    uint64_t h = 0;
+                    ok = (uint32_t)lq_cand_clean(s_b2, sg, a.k, &h, &z);
+                    h32 = (uint32_t)h;
+                } else { /* k-mer registers carry bits from before an ambiguous base / the read start */
+                    uint64_t fw, rv;
+                    lq_regs_at(a.b2, a.nm, s0 * LQ_SLOT, i, a.k, &fw, &rv);
+                    ok = fw != rv;
+                }
+            }
+        }
+        cand[idx] = h32;
+        const uint32_t okm = __ballot_sync(0xffffffffu, ok), zm = __ballot_sync(0xffffffffu, z);
+        if ((tid & 31) == 0) { okb[idx >> 5] = okm; zb[idx >> 5] = zm; }
+    }
+    __syncthreads();
+
+    /* stage B: rows r = 0..3, base = T0 + r*256 + tid */
+    if (!WRITE) {
+        SkCount c; c.n = 0;
+        #pragma unroll 1
+        for (int r = 0; r < SK_PER_THREAD; ++r)
+            sk_eval(a, s_b2, cand, okb, zb, SK_HALO + r * SK_THREADS + tid, (uint64_t)(T0 + r * SK_THREADS + tid), c);
+        uint64_t tot, v = (uint64_t)c.n;
+        lq_block_excl_scan(v, scan_sm, &tot);
+        if (tid == 0) a.blk_count[blockIdx.x] = (uint32_t)tot;
+    } else {
+        SkBuf b; b.n = 0;
+        int cnt[SK_PER_THREAD];
+        #pragma unroll 1
+        for (int r = 0; r < SK_PER_THREAD; ++r) {
+            const int before = b.n;
+            sk_eval(a, s_b2, cand, okb, zb, SK_HALO + r * SK_THREADS + tid, (uint64_t)(T0 + r * SK_THREADS + tid), b);
+            cnt[r] = b.n - before;
+        }
+        /* one block scan for the four rows: 16 bits per row (<= 256*(2w+2) < 65536 records per row) */
+        uint64_t packed = (uint64_t)cnt[0] | (uint64_t)cnt[1] << 16 | (uint64_t)cnt[2] << 32 | (uint64_t)cnt[3] << 48, tot;
+        const uint64_t ex = lq_block_excl_scan(packed, scan_sm, &tot);
+        uint64_t base = a.blk_base[blockIdx.x];
+        SkWrite wr; wr.key = a.out_key; wr.yy = a.out_y;
+        int used = 0;
+        #pragma unroll 1
+        for (int r = 0; r < SK_PER_THREAD; ++r) {
+            wr.at = base + ((ex >> (16 * r)) & 0xffff);
+            if (b.n <= SK_BUF) {
+                for (int j = 0; j < cnt[r]; ++j) wr(b.x[used + j], b.y[used + j]);
+                used += cnt[r];
+            } else { /* buffer overflowed (low-complexity sequence): evaluate again, writing directly */
+                sk_eval(a, s_b2, cand, okb, zb, SK_HALO + r * SK_THREADS + tid, (uint64_t)(T0 + r * SK_THREADS + tid), wr);
+            }
+            base += (tot >> (16 * r)) & 0xffff;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ HPC sketch: one thread per read (spike-in run, reference sketch.c:93-104) */
+
+struct SkWriteSpan {
+    uint32_t *key; uint64_t *yy; uint8_t *span; uint64_t at;
+    __device__ __forceinline__ void operator()(uint64_t x_, uint64_t y_) { key[at] = (uint32_t)(x_ >> 8); yy[at] = y_; span[at] = (uint8_t)x_; ++at; }
+};
+
+template <int WRITE>
+__global__ void lq_sketch_seq_k(SkArgs a, uint32_t n_reads, int is_hpc, uint32_t *read_count, const uint64_t *read_base, uint8_t *out_span)
+{
+    const uint32_t rd = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rd >= n_reads) return;
+    const int L = (int)a.len[rd];
+    const uint64_t g0 = a.slot0[rd] * LQ_SLOT;
+    if (!WRITE) {
+        SkCount c; c.n = 0;
+        if (L > 0) lq_sketch_replay(a.b2, a.nm, g0, L, a.w, a.k, a.rid_base + rd, is_hpc, 0, 1, L - 1, 0, L, (int*)0, c);
+        read_count[rd] = (uint32_t)c.n;
+    } else {
+        SkWriteSpan wr; wr.key = a.out_key; wr.yy = a.out_y; wr.span = out_span; wr.at = read_base[rd];
+        if (L > 0) lq_sketch_replay(a.b2, a.nm, g0, L, a.w, a.k, a.rid_base + rd, is_hpc, 0, 1, L - 1, 0, L, (int*)0, wr);
+    }
+}
+
+/* per-read record ranges from the y stream (rid in the high word): first[r] = first record with rid >= r */
+__global__ void lq_read_first_k(const uint64_t *__restrict__ y, uint64_t n, uint32_t rid_base, uint32_t n_reads, uint64_t *__restrict__ first)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const int64_t prev = i == 0 ? -1 : (int64_t)((uint32_t)(y[i - 1] >> 32) - rid_base);
+    const int64_t cur = i == n ? (int64_t)n_reads : (int64_t)((uint32_t)(y[i] >> 32) - rid_base);
+    for (int64_t r = prev + 1; r <= cur; ++r) first[r] = i;
+}
+
+/* ------------------------------------------------------------------ host side */
+
+int lq_reads_upload(LqReadsDev *d, const uint8_t *h_seq, const uint64_t *h_off, uint32_t n_reads, int seq_on_device, int sdust_tbl, cudaStream_t st)
+{
+    /* h_off: n_reads+1 offsets into h_seq (host array always); h_seq host or device (seq_on_device) */
+    d->n_reads = n_reads;
+    d->n_bases = h_off[n_reads] - h_off[0];
+    d->h_len.resize(n_reads); d->h_slot0.resize((size_t)n_reads + 1);
+    uint64_t slots = 0;
+    for (uint32_t r = 0; r < n_reads; ++r) {
+        uint64_t L = h_off[r + 1] - h_off[r];
+        if (L > 0x7fffffffULL) { fprintf(stderr, "[lqcov] read %u longer than 2^31\n", r); return -1; }
+        d->h_len[r] = (uint32_t)L; d->h_slot0[r] = slots;
+        slots += (L + LQ_SLOT - 1) / LQ_SLOT;
+    }
+    d->h_slot0[n_reads] = slots;
+    d->n_slots = slots;
+    LQ_TRY(d->len.ensure((size_t)(n_reads + 1) * 4));
+    LQ_TRY(d->slot0.ensure((size_t)(n_reads + 1) * 8));
+    LQ_TRY(d->off.ensure((size_t)(n_reads + 1) * 8));
+    LQ_TRY(d->b2.ensure((size_t)(slots * LQ_SLOT_W2 + 16) * 4));
+    LQ_TRY(d->nm.ensure((size_t)(slots * LQ_SLOT_WN + 16) * 4));
+    LQ_TRY(d->slot_read.ensure((size_t)(slots + 1) * 4));
+    if (n_reads == 0) return 0;
+    LQ_CUDA_OK(cudaMemcpyAsync(d->len.p, d->h_len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
+    LQ_CUDA_OK(cudaMemcpyAsync(d->slot0.p, d->h_slot0.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    LQ_CUDA_OK(cudaMemcpyAsync(d->off.p, h_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    const uint8_t *d_seq;
+    if (seq_on_device) d_seq = h_seq;
+    else {
+        LQ_TRY(d->ascii.ensure((size_t)d->n_bases + 16));
+        LQ_CUDA_OK(cudaMemcpyAsync(d->ascii.p, h_seq + h_off[0], (size_t)d->n_bases, cudaMemcpyHostToDevice, st));
+        d_seq = d->ascii.as<uint8_t>() - h_off[0];
+    }
+    /* pad words past the last slot (the 3-word k-mer gather may read one word past a read's last slot) */
+    LQ_CUDA_OK(cudaMemsetAsync(d->b2.as<uint32_t>() + slots * LQ_SLOT_W2, 0, 16 * 4, st));
+    LQ_CUDA_OK(cudaMemsetAsync(d->nm.as<uint32_t>() + slots * LQ_SLOT_WN, 0xff, 16 * 4, st));
+    if (slots) {
+        lq_pack_k<<<lq_grid(slots * 4, 256), 256, 0, st>>>(d_seq, d->off.as<uint64_t>(), d->slot0.as<uint64_t>(), d->len.as<uint32_t>(),
+                                                           n_reads, slots, sdust_tbl, d->b2.as<uint32_t>(), d->nm.as<uint32_t>(), d->slot_read.as<uint32_t>());
+        LQ_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
+int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_base, LqMinimizers *out, LqDevBuf &ws, cudaStream_t st)
+{
+    out->n = 0; out->has_span = is_hpc;
+    if (w < 1 || w > LQ_MAX_W) { fprintf(stderr, "[lqcov] window size %d not supported on the GPU path (1..%d)\n", w, LQ_MAX_W); return -1; }
+    if (k < 1 || k > 16) { fprintf(stderr, "[lqcov] k-mer size %d not supported on the GPU path (1..16 sketch, <=%d indexed)\n", k, LQ_MAX_K_DIRECT); return -1; }
+    if (rd->n_reads == 0 || rd->n_slots == 0) return 0;
+    SkArgs a;
+    a.b2 = rd->b2.as<uint32_t>(); a.nm = rd->nm.as<uint32_t>(); a.slot_read = rd->slot_read.as<uint32_t>(); a.len = rd->len.as<uint32_t>();
+    a.slot0 = rd->slot0.as<uint64_t>(); a.n_slots = rd->n_slots; a.w = w; a.k = k; a.rid_base = rid_base;
+    a.blk_count = 0; a.blk_base = 0; a.out_key = 0; a.out_y = 0;
+    uint64_t total = 0;
+    if (!is_hpc) {
+        const unsigned nblk = (unsigned)((rd->n_slots * LQ_SLOT + SK_TILE - 1) / SK_TILE);
+        LQ_TRY(out->blk.ensure((size_t)(nblk + 1) * 4 + (size_t)(nblk + 2) * 8));
+        uint32_t *cnt = out->blk.as<uint32_t>();
+        uint64_t *base = (uint64_t*)((char*)out->blk.p + (((size_t)(nblk + 1) * 4 + 7) & ~(size_t)7));
+        a.blk_count = cnt;
+        lq_sketch_k<0><<<nblk, SK_THREADS, 0, st>>>(a);
+        LQ_CUDA_OK(cudaGetLastError());
+        LQ_TRY((lq_exclusive_scan<uint32_t, uint64_t>(cnt, base, nblk, 1, ws, st)));
+        LQ_CUDA_OK(cudaMemcpyAsync(&total, base + nblk, 8, cudaMemcpyDeviceToHost, st));
+        LQ_CUDA_OK(cudaStreamSynchronize(st));
+        LQ_TRY(out->key.ensure((size_t)(total + 1) * 4));
+        LQ_TRY(out->y.ensure((size_t)(total + 1) * 8));
+        a.blk_base = base; a.out_key = out->key.as<uint32_t>(); a.out_y = out->y.as<uint64_t>();
+        lq_sketch_k<1><<<nblk, SK_THREADS, 0, st>>>(a);
+        LQ_CUDA_OK(cudaGetLastError());
+    } else {
+        const uint32_t n = rd->n_reads;
+        LQ_TRY(out->blk.ensure((size_t)(n + 1) * 4 + (size_t)(n + 2) * 8));
+        uint32_t *cnt = out->blk.as<uint32_t>();
+        uint64_t *base = (uint64_t*)((char*)out->blk.p + (((size_t)(n + 1) * 4 + 7) & ~(size_t)7));
+        lq_sketch_seq_k<0><<<lq_grid(n, 64), 64, 0, st>>>(a, n, 1, cnt, 0, 0);
+        LQ_CUDA_OK(cudaGetLastError());
+        LQ_TRY((lq_exclusive_scan<uint32_t, uint64_t>(cnt, base, n, 1, ws, st)));
+        LQ_CUDA_OK(cudaMemcpyAsync(&total, base + n, 8, cudaMemcpyDeviceToHost, st));
+        LQ_CUDA_OK(cudaStreamSynchronize(st));
+        LQ_TRY(out->key.ensure((size_t)(total + 1) * 4));
+        LQ_TRY(out->y.ensure((size_t)(total + 1) * 8));
+        LQ_TRY(out->span.ensure((size_t)(total + 1)));
+        a.out_key = out->key.as<uint32_t>(); a.out_y = out->y.as<uint64_t>();
+        lq_sketch_seq_k<1><<<lq_grid(n, 64), 64, 0, st>>>(a, n, 1, 0, base, out->span.as<uint8_t>());
+        LQ_CUDA_OK(cudaGetLastError());
+    }
+    out->n = total;
+    return 0;
+}
+
+int lq_read_first(const LqMinimizers *m, uint32_t rid_base, uint32_t n_reads, LqDevBuf &first, cudaStream_t st)
+{
+    LQ_TRY(first.ensure((size_t)(n_reads + 2) * 8));
+    lq_read_first_k<<<lq_grid(m->n + 1, 256), 256, 0, st>>>(m->y.as<uint64_t>(), m->n, rid_base, n_reads, first.as<uint64_t>());
+    LQ_CUDA_OK(cudaGetLastError());
+    return 0;
+}
