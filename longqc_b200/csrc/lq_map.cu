@@ -379,14 +379,14 @@ __global__ void __launch_bounds__(CH_WARPS * 32) lq_chain_k(ChainArgs a)
         }
         __syncwarp();
         if (n_end == 0) continue;
-        /* ---- order by (score, index) descending (chain.c:102-106; keys are distinct): rank sort, staged through
+        /* ---- order by (score, index) descending (chain.c:102-106): rank sort, staged through
          *      the group's slices of the head/gid arrays (dead once the group list exists) ---- */
         uint64_t *ue = a.uend + gb;
         if (n_end > 1) {
             uint32_t *s_lo = a.s_lo + gb, *s_hi = a.s_hi + gb;
             for (uint32_t e = lane; e < n_end; e += 32) {
                 const uint64_t k = ue[e]; uint32_t r = 0;
-                for (uint32_t o = 0; o < n_end; ++o) r += ue[o] > k;
+                for (uint32_t o = 0; o < n_end; ++o) r += ue[o] > k || (ue[o] == k && o < e); /* two ends may share a peak: equal keys */
                 s_lo[r] = (uint32_t)k; s_hi[r] = (uint32_t)(k >> 32);
             }
             __syncwarp();
