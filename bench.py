@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: read Gbases/s through minimap2-coverage on B200 vs host CPU.
+
+One "step" = one complete all-vs-subsample coverage job on the synthetic workload (sketch every
+target read, build the minimizer index, map the sampled queries, emit the table):
+    Gbases/s = (target bases indexed + query bases mapped) / step time.
+
+  value  whole-job throughput with the reads' ASCII bases already resident in HBM
+  e2e    the same job through the C ABI with HOST (pinned) buffers: H2D of every base and D2H of the
+         per-query results are inside the timed region
+  roofline      the dominant kernel of the step, timed with CUDA events on the library's stream
+  cpu_baseline  the reference CPU binary (oracle/_ref) on a bounded sample of the same workload
+  --impl reference   the reference's own CPU implementation as the measured arm (bounded sample per step)
+
+N > 1: launched under torchrun; see longqc_b200/dist.py for the sharding (targets sharded for sketching,
+minimizer counts all-reduced, index replicated, queries sharded).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLAGS = "-Y -l 0 -q 160 -k 12 -w 5 -I 4G -p 160"   # longQC.py:171-231 for -x ont-ligation
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=100_000)       # BASELINE.json configs[1]
+    ap.add_argument("--read-len", type=int, default=8_000)
+    ap.add_argument("--err", type=float, default=0.15)
+    ap.add_argument("--queries", type=int, default=5_000)
+    ap.add_argument("--seed", type=int, default=20260925)
+    ap.add_argument("--cpu-sample-reads", type=int, default=12_000)
+    ap.add_argument("--cpu-sample-queries", type=int, default=600)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "%dk synthetic ONT %d kb reads (%.0f%% error), -x ont-ligation (%s), %d sampled queries" % (
+        a.reads // 1000, a.read_len // 1000, a.err * 100, FLAGS, a.queries)
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, nm in enumerate(names):
+                if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- data
+def make_data(a, n_reads, n_query, rank=0):
+    from longqc_b200 import synth
+    return synth.standard_set(n_reads, a.read_len, a.err, seed=a.seed + 1000 * rank, n_query=n_query)
+
+
+def cpu_reference_run(a, targets, queries, threads):
+    """Time the unmodified reference binary (oracle/_ref) -- or the oracle port when it was not built --
+    on (targets, queries).  Returns (Gbases/s, seconds, kind, cores)."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "minimap2-coverage")
+    port = os.path.join(ROOT, "oracle", "lq_oracle_cli")
+    d = tempfile.mkdtemp(prefix="lqbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    tf, qf = os.path.join(d, "t.fq"), os.path.join(d, "q.fq")
+    targets.write_fastx(tf)
+    queries.write_fastx(qf)
+    if os.path.exists(ref):
+        cmd, kind, cores = [ref] + FLAGS.split() + ["-t", str(threads), tf, qf], "reference", threads
+    else:
+        cmd, kind, cores = [port, "cov"] + FLAGS.split() + [tf, qf], "port", 1
+    t0 = time.perf_counter()
+    with open(os.path.join(d, "out.tsv"), "wb") as out:
+        subprocess.run(cmd, stdout=out, stderr=subprocess.DEVNULL, check=True)
+    dt = time.perf_counter() - t0
+    for f in (tf, qf, os.path.join(d, "out.tsv")):
+        os.unlink(f)
+    os.rmdir(d)
+    return (targets.n_bases + queries.n_bases) / dt / 1e9, dt, kind, cores
+
+
+def host_threads():
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return max(1, min(n, 64))
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    targets, queries = make_data(a, a.cpu_sample_reads, a.cpu_sample_queries)
+    thr = host_threads()
+    for _ in range(a.warmup):
+        cpu_reference_run(a, targets, queries, thr)
+    vals, secs, kind, cores = [], [], None, None
+    for _ in range(a.steps):
+        v, dt, kind, cores = cpu_reference_run(a, targets, queries, thr)
+        vals.append(v)
+        secs.append(dt)
+    v = sum(vals) / len(vals)
+    sample = "%d target reads x %d b + %d queries of the same generator (bounded sample of the workload)" % (targets.n, a.read_len, queries.n)
+    line = {"impl": "reference", "metric": "read Gbases/s through minimap2-coverage (target bases indexed + query bases mapped per second)",
+            "value": v, "unit": "Gbases/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic", "config": {"workload": workload_name(a), "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "Gbases/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profile_json(L):
+    lib = L.load()
+    lib.lqcov_profile_json.restype = C.c_size_t
+    lib.lqcov_profile_json.argtypes = [C.c_char_p, C.c_size_t]
+    n = lib.lqcov_profile_json(None, 0)
+    buf = C.create_string_buffer(n + 16)
+    lib.lqcov_profile_json(buf, n + 16)
+    return json.loads(buf.value.decode())
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import longqc_b200 as L
+    from longqc_b200 import _lib
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == a.gpus, "launch with torchrun --nproc-per-node %d for --gpus %d" % (a.gpus, a.gpus)
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from longqc_b200 import dist as lqdist
+
+    opt = L.Opt(min_score_med=160, min_score_good=160, device=local)
+    runner = lqdist.Runner(a, opt, rank, world, local)
+    targets, queries = runner.make_inputs()        # this rank's shard of the workload (weak scaling)
+    n_bases_job = runner.job_bases()                # all ranks together
+
+    lib = L.load()
+    lib.lqcov_profile_enable(0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ----
+    for _ in range(a.warmup):
+        runner.step(resident=True)
+    lib.lqcov_profile_enable(1)
+    lib.lqcov_profile_reset()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            runner.step(resident=True)
+        barrier()
+        ev1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    prof = profile_json(L)
+    lib.lqcov_profile_enable(0)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / a.steps
+    value = n_bases_job / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: host buffers, copies inside the timed region ----
+    runner.step(resident=False)
+    lib.lqcov_profile_reset()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        runner.step(resident=False)
+    barrier()
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / a.steps
+    prof_e2e = profile_json(L)
+    e2e = {"value": n_bases_job / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s",
+           "h2d_bytes_per_step": int(prof_e2e["h2d_bytes"] // a.steps * world), "d2h_bytes_per_step": int(prof_e2e["d2h_bytes"] // a.steps * world),
+           "ms_per_step": e2e_ms}
+
+    # ---- parity spot-check of the benchmarked configuration (not timed) ----
+    parity = runner.parity_note()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (device time from CUDA events on the library's stream) ----
+    peak, peak_src = load_peaks()
+    kernels = sorted(prof["kernels"], key=lambda k: -k["ms"])
+    ktot = sum(k["ms"] for k in kernels) or 1.0
+    klist = []
+    for k in kernels:
+        ach = (k["bytes"] / (k["ms"] * 1e-3) / 1e9) if k["ms"] > 0 else 0.0
+        klist.append({"name": k["name"], "ms_per_step": k["ms"] / a.steps, "launches_per_step": k["launches"] / a.steps,
+                      "share": k["ms"] / ktot, "achieved_gbs": ach, "frac": ach / peak})
+    top = kernels[0] if kernels else None
+    roof = None
+    if top:
+        ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9 if top["ms"] > 0 else 0.0
+        roof = {"kernel": top["name"], "bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "ms_per_launch_group": top["ms"] / max(1, a.steps),
+                "note": "algorithmic bytes / CUDA-event time on the launching stream; see DESIGN.md for the bytes per unit"}
+    sk = [k for k in klist if k["name"] == "sketch_write"]
+    cpu = None
+    if not a.no_cpu_baseline and world == 1:
+        ct, cq = make_data(a, a.cpu_sample_reads, a.cpu_sample_queries)
+        v, dt, kind, cores = cpu_reference_run(a, ct, cq, host_threads())
+        cpu = {"value": v, "unit": "Gbases/s", "cores": cores, "kind": kind, "seconds": dt,
+               "sample": "%d target reads x %d b + %d queries of the same generator (bounded sample)" % (ct.n, a.read_len, cq.n)}
+    line = {"metric": "read Gbases/s through minimap2-coverage (target bases indexed + query bases mapped per second)",
+            "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "target_bases": int(runner.target_bases_all), "query_bases": int(runner.query_bases_all),
+                       "parallelism": runner.parallelism(), "l2": "inputs (>= %.1f GB per rank) larger than the 126 MB L2" % (targets.n_bases / 1e9),
+                       "host_wall_ms_per_step": 1e3 * wall / a.steps},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(prof["launches"] // a.steps),
+            "roofline": roof, "sketch_kernel": sk[0] if sk else None, "kernels": klist, "cpu_baseline": cpu, "parity": parity,
+            "stats": runner.last_stats}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference_arm(a)
+    return run_ours(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -87,11 +87,25 @@ void lqcov_opt_init(lqcov_opt_t *o);                       /* the defaults liste
 /* minimap2-coverage.c:217-621 as a library ---------------------------------------------------- */
 lqcov_ctx *lqcov_create(const lqcov_opt_t *o);              /* NULL on error (no usable GPU, bad options) */
 void lqcov_destroy(lqcov_ctx *c);
+int  lqcov_reset(lqcov_ctx *c);                               /* start a new job in the same context (buffers are kept) */
 /* query pre-pass: sketch every query once, allocate the per-query accumulators (minimap2-coverage.c:406-444) */
 int  lqcov_set_queries(lqcov_ctx *c, const lqcov_reads_t *queries);
 /* one index part: mm_idx_gen (index.c:311-330) + mm_mapopt_update (map.c:46-54, mid_occ frozen from the
  * first part) + lq_map_file for every query (lqmap.c:851-855) */
 int  lqcov_add_part(lqcov_ctx *c, const lqcov_reads_t *part);
+/* the same in phases, so that several GPUs can share one part (one process per GPU; the collectives between
+ * the phases are issued by the caller, see longqc_b200/dist.py and INTEGRATION.md):
+ *   lqcov_part_sketch        sketch THIS rank's contiguous shard of the part's reads (rid = rid_base + i), count minimizers
+ *   lqcov_part_device_views  device pointers of the count table (u32[4^k]: all-reduce SUM) and of the local records
+ *   lqcov_part_gather_buffers device buffers for the records of ALL ranks, concatenated in rank order (all-gather target)
+ *   lqcov_part_finish        offsets + stable sort + mid_occ + name tables; `part` describes the WHOLE part
+ *                            (n, seq_off for the lengths, names; seq may be NULL)
+ *   lqcov_map_part           map this context's queries against the finished part */
+int  lqcov_part_sketch(lqcov_ctx *c, const lqcov_reads_t *shard, uint32_t rid_base);
+int  lqcov_part_device_views(lqcov_ctx *c, void **counts, uint64_t *n_counts, void **key, void **y, uint64_t *n_rec);
+int  lqcov_part_gather_buffers(lqcov_ctx *c, uint64_t n_total, void **key, void **y);
+int  lqcov_part_finish(lqcov_ctx *c, const lqcov_reads_t *part);
+int  lqcov_map_part(lqcov_ctx *c);
 /* whole target set in memory: cut into parts exactly as index.c:238-330 does (mini-batch rule) and add each */
 int  lqcov_add_targets(lqcov_ctx *c, const lqcov_reads_t *targets);
 /* the stdout table of minimap2-coverage.c:545-617, one row per query; *buf is malloc'ed (lqcov_free) */
@@ -111,6 +125,11 @@ int  lqcov_sketch(const lqcov_opt_t *o, const lqcov_reads_t *reads, uint32_t rid
 int  lqcov_debug_seeds(lqcov_ctx *c, uint32_t q, uint64_t **ux, uint64_t **uy, uint64_t **sx, uint64_t **sy, uint64_t *n);
 /* index one part WITHOUT mapping (used with lqcov_debug_seeds) */
 int  lqcov_index_part(lqcov_ctx *c, const lqcov_reads_t *part);
+
+/* per-kernel device timing (CUDA events on the library's stream), launch and transfer counters: bench.py */
+void   lqcov_profile_enable(int on);
+void   lqcov_profile_reset(void);
+size_t lqcov_profile_json(char *buf, size_t cap);            /* returns the length needed (incl. NUL) */
 
 /* host helpers shared with the executables -------------------------------------------------- */
 /* FASTA/FASTQ(.gz) reader with kseq.h:185-224 + bseq.c:56-66 semantics.  Reads records until the

@@ -19,6 +19,7 @@
 #include "lq_map.h"
 #include "lq_host.h"
 #include "lqcov.h"
+#include "lq_prof.h"
 
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -35,7 +36,7 @@ struct lqcov_ctx {
     std::vector<lqh_sub_v> ovlp;        /* ovlp_coords (minimap2-coverage.c:438-444) */
     std::vector<float> avg_k;           /* avg_ks */
     /* device */
-    LqQueryDev qd; LqIndexDev ix; LqMapScratch sc; LqReadsDev treads; LqMinimizers tmins; LqDevBuf ws;
+    LqQueryDev qd; LqIndexDev ix; LqMapScratch sc; LqReadsDev treads; LqMinimizers tmins, full; LqDevBuf ws; bool use_full;
     /* current part */
     std::vector<uint32_t> self_off, self_list, qrank, trank;
     bool part_ready;
@@ -70,10 +71,19 @@ extern "C" lqcov_ctx *lqcov_create(const lqcov_opt_t *o)
     if (o->w < 1 || o->w > LQ_MAX_W) { fprintf(stderr, "[lqcov] ERROR: -w %d outside 1..%d supported by the GPU path\n", o->w, LQ_MAX_W); return 0; }
     if (o->k < 1 || o->k > LQ_MAX_K_DIRECT) { fprintf(stderr, "[lqcov] ERROR: -k %d outside 1..%d supported by the direct-address index of this build\n", o->k, LQ_MAX_K_DIRECT); return 0; }
     lqcov_ctx *c = new lqcov_ctx();
-    c->opt = *o; c->nq = 0; c->q_has_qual = false; c->part_ready = false; c->mid_occ = 0;
+    c->opt = *o; c->nq = 0; c->q_has_qual = false; c->part_ready = false; c->use_full = false; c->mid_occ = 0;
     memset(&c->stats, 0, sizeof(c->stats));
     if (cudaStreamCreate(&c->st) != cudaSuccess) { fprintf(stderr, "[lqcov] ERROR: cudaStreamCreate failed\n"); delete c; return 0; }
     return c;
+}
+
+/* forget everything learnt from previous parts (mid_occ, accumulators); buffers stay allocated */
+extern "C" int lqcov_reset(lqcov_ctx *c)
+{
+    c->mid_occ = 0; c->part_ready = false; c->use_full = false;
+    memset(&c->stats, 0, sizeof(c->stats));
+    for (size_t i = 0; i < c->ovlp.size(); ++i) { free(c->ovlp[i].a); c->ovlp[i].a = 0; c->ovlp[i].n = c->ovlp[i].m = 0; }
+    return 0;
 }
 
 extern "C" void lqcov_destroy(lqcov_ctx *c)
@@ -81,7 +91,7 @@ extern "C" void lqcov_destroy(lqcov_ctx *c)
     if (!c) return;
     cudaStreamSynchronize(c->st);
     for (size_t i = 0; i < c->ovlp.size(); ++i) free(c->ovlp[i].a);
-    c->qd.release(); c->ix.release(); c->sc.release(); c->treads.release(); c->tmins.release(); c->ws.release();
+    c->qd.release(); c->ix.release(); c->sc.release(); c->treads.release(); c->tmins.release(); c->full.release(); c->ws.release();
     cudaStreamDestroy(c->st);
     delete c;
 }
@@ -127,23 +137,61 @@ extern "C" int lqcov_set_queries(lqcov_ctx *c, const lqcov_reads_t *q)
     return 0;
 }
 
-extern "C" int lqcov_index_part(lqcov_ctx *c, const lqcov_reads_t *part)
+/* ---- one index part in three phases, so that several GPUs can share it:
+ *   lqcov_part_sketch   every rank: pack + sketch ITS shard of the part's reads (rid = rid_base + i) and count minimizers
+ *   (collective)        all-reduce of the count table, all-gather of the (key, y) records in rank order  [longqc_b200/dist.py]
+ *   lqcov_part_finish   every rank: offsets, stable sort by key, mid_occ, name tables  -> replicated index
+ * lqcov_index_part() is the single-GPU composition. */
+extern "C" int lqcov_part_sketch(lqcov_ctx *c, const lqcov_reads_t *shard, uint32_t rid_base)
 {
     double t0 = now_ms();
     LqIndexDev *ix = &c->ix;
-    LQ_TRY(lq_reads_upload(&c->treads, (const uint8_t*)part->seq, part->seq_off, part->n, part->seq_on_device, 0, c->st));
+    c->part_ready = false; c->use_full = false;
+    LQ_TRY(lq_reads_upload(&c->treads, (const uint8_t*)shard->seq, shard->seq_off, shard->n, shard->seq_on_device, 0, c->st));
     LQ_CUDA_OK(cudaStreamSynchronize(c->st));
     c->stats.t_upload_ms += now_ms() - t0; t0 = now_ms();
-    LQ_TRY(lq_sketch_run(&c->treads, c->opt.w, c->opt.k, c->opt.is_hpc, 0, &ix->rec, c->ws, c->st)); /* rid restarts at 0 in every part (index.c:287) */
+    LQ_TRY(lq_sketch_run(&c->treads, c->opt.w, c->opt.k, c->opt.is_hpc, rid_base, &ix->rec, c->ws, c->st)); /* rid restarts at 0 in every part (index.c:287) */
     LQ_CUDA_OK(cudaStreamSynchronize(c->st));
     c->stats.t_sketch_ms += now_ms() - t0; t0 = now_ms();
     LQ_TRY(lq_index_alloc(ix, c->opt.k, c->st));
     LQ_TRY(lq_index_count(ix, &ix->rec, c->st));
-    /* (several GPUs: the counts table is all-reduced and the records all-gathered here -- see longqc_b200/dist.py) */
+    LQ_CUDA_OK(cudaStreamSynchronize(c->st));
+    c->stats.t_index_ms += now_ms() - t0;
+    c->stats.target_bases += c->treads.n_bases;
+    return 0;
+}
+
+extern "C" int lqcov_part_device_views(lqcov_ctx *c, void **counts, uint64_t *n_counts, void **key, void **y, uint64_t *n_rec)
+{
+    *counts = c->ix.counts.p; *n_counts = c->ix.n_keyspace;
+    *key = c->ix.rec.key.p; *y = c->ix.rec.y.p; *n_rec = c->ix.rec.n;
+    return 0;
+}
+
+extern "C" int lqcov_part_gather_buffers(lqcov_ctx *c, uint64_t n_total, void **key, void **y)
+{
+    if (c->opt.is_hpc) { fprintf(stderr, "[lqcov] ERROR: HPC sketches are not supported on the multi-GPU path\n"); return -1; }
+    LQ_TRY(c->full.key.ensure((size_t)(n_total + 1) * 4)); LQ_TRY(c->full.y.ensure((size_t)(n_total + 1) * 8));
+    c->full.n = n_total; c->full.has_span = 0; c->use_full = true;
+    *key = c->full.key.p; *y = c->full.y.p;
+    return 0;
+}
+
+extern "C" int lqcov_part_finish(lqcov_ctx *c, const lqcov_reads_t *part)
+{
+    double t0 = now_ms();
+    LqIndexDev *ix = &c->ix;
+    if (c->use_full) { std::swap(ix->rec.key, c->full.key); std::swap(ix->rec.y, c->full.y); ix->rec.n = c->full.n; ix->rec.has_span = 0; c->use_full = false; }
     LQ_TRY(lq_index_finish(ix, &ix->rec, c->ws, c->st));
     ix->n_seq = part->n;
     LQ_TRY(ix->tlen.ensure(((size_t)part->n + 1) * 4));
-    if (part->n) LQ_CUDA_OK(cudaMemcpyAsync(ix->tlen.p, c->treads.h_len.data(), (size_t)part->n * 4, cudaMemcpyHostToDevice, c->st));
+    {
+        std::vector<uint32_t> tl(part->n);
+        for (uint32_t i = 0; i < part->n; ++i) tl[i] = (uint32_t)(part->seq_off[i + 1] - part->seq_off[i]);
+        if (part->n) LQ_CUDA_OK(cudaMemcpyAsync(ix->tlen.p, tl.data(), (size_t)part->n * 4, cudaMemcpyHostToDevice, c->st));
+        LQ_CUDA_OK(cudaStreamSynchronize(c->st));
+        lq_prof_h2d((uint64_t)part->n * 4);
+    }
     if (c->mid_occ <= 0) { /* map.c:50-51: only while still unset, i.e. from the first part */
         uint64_t nd = 0;
         LQ_TRY(lq_index_mid_occ(ix, c->opt.mid_occ_frac, &c->mid_occ, &nd, c->ws, c->st));
@@ -176,10 +224,17 @@ extern "C" int lqcov_index_part(lqcov_ctx *c, const lqcov_reads_t *part)
         for (uint32_t t = 0; t < part->n; ++t) c->trank[t] = (uint32_t)(std::lower_bound(uniq.begin(), uniq.end(), all[nq + t]) - uniq.begin());
     }
     c->part_ready = true;
-    c->stats.target_bases += c->treads.n_bases; c->stats.target_minimizers += ix->n_rec;
+    c->stats.target_minimizers += ix->n_rec;
     c->stats.n_parts += 1; c->stats.mid_occ = c->mid_occ;
+    c->stats.t_post_ms += now_ms() - t0 - 0.0;
     if (c->opt.verbose >= 3) fprintf(stderr, "[M::lqcov] loaded/built the index for %u target sequence(s)\n", part->n);
     return 0;
+}
+
+extern "C" int lqcov_index_part(lqcov_ctx *c, const lqcov_reads_t *part)
+{
+    LQ_TRY(lqcov_part_sketch(c, part, 0));
+    return lqcov_part_finish(c, part);
 }
 
 static void map_opt_of(const lqcov_opt_t *o, LqMapOpt *m)
@@ -192,15 +247,16 @@ static void map_opt_of(const lqcov_opt_t *o, LqMapOpt *m)
 
 static bool ovl_by_q(const LqOvl &a, const LqOvl &b) { return a.q < b.q; }
 
-extern "C" int lqcov_add_part(lqcov_ctx *c, const lqcov_reads_t *part)
+extern "C" int lqcov_map_part(lqcov_ctx *c)
 {
-    LQ_TRY(lqcov_index_part(c, part));
+    if (!c->part_ready) { fprintf(stderr, "[lqcov] ERROR: lqcov_map_part without an index part\n"); return -1; }
     if (c->nq == 0) return 0;
     double t0 = now_ms();
     LqMapOpt mo; map_opt_of(&c->opt, &mo);
     std::vector<LqOvl> ovl; std::vector<LqQStat> hs; LqMapStats ms; memset(&ms, 0, sizeof(ms));
     const uint64_t cap = c->opt.seed_budget ? c->opt.seed_budget : 400000000ULL;
     LQ_TRY(lq_map_part(&c->qd, &c->ix, &mo, c->mid_occ, c->self_off.data(), c->self_list.data(), c->qrank.data(), c->trank.data(), cap, &c->sc, &ovl, &hs, &ms, c->st));
+    lq_prof_collect();
     c->stats.t_map_ms += now_ms() - t0; t0 = now_ms();
     /* esterr.c:93-97: the mean k-mer span is fixed by the first part in which the query keeps a minimizer */
     for (uint32_t q = 0; q < c->nq; ++q)
@@ -220,6 +276,12 @@ extern "C" int lqcov_add_part(lqcov_ctx *c, const lqcov_reads_t *part)
     if (c->opt.verbose >= 3) fprintf(stderr, "[M::lqcov] mapped %u sequences (%llu seeds, %llu chains, %llu overlaps)\n", c->nq,
                                     (unsigned long long)ms.n_seeds, (unsigned long long)ms.n_chains, (unsigned long long)ms.n_ovl);
     return 0;
+}
+
+extern "C" int lqcov_add_part(lqcov_ctx *c, const lqcov_reads_t *part)
+{
+    LQ_TRY(lqcov_index_part(c, part));
+    return lqcov_map_part(c);
 }
 
 extern "C" int lqcov_add_targets(lqcov_ctx *c, const lqcov_reads_t *t)
@@ -251,6 +313,7 @@ extern "C" int lqcov_table(lqcov_ctx *c, char **buf, size_t *len)
         LQ_CUDA_OK(cudaMemcpyAsync(lam2.data(), c->qd.lambda2.p, (size_t)c->nq * 8, cudaMemcpyDeviceToHost, c->st));
         LQ_CUDA_OK(cudaStreamSynchronize(c->st));
     }
+    lq_prof_d2h((uint64_t)c->nq * 16); lq_prof_collect();
     lqh_str out; out.l = out.m = 0; out.s = 0;
     for (uint32_t q = 0; q < c->nq; ++q) {
         const uint32_t n_mini = (uint32_t)(c->qfirst[q + 1] - c->qfirst[q]);

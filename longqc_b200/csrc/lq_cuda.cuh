@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <stdint.h>
 #include "lq_common.h"
+#include "lq_prof.h"
 
 #define LQ_CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     fprintf(stderr, "[lqcov] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
@@ -118,6 +119,7 @@ static int lq_exclusive_scan(const TI *in, TO *out, size_t n, int with_total, Lq
     }
     TO *bsum = (TO*)((char*)ws.p + ws_off);
     lq_scan_reduce_k<TI, TO><<<(unsigned)nb, LQ_SCAN_BLOCK, 0, st>>>(in, n, bsum);
+    lq_prof_count_launch(2);
     /* exclusive scan of the block sums, in place, total at bsum[nb] */
     if (nb == 1) {
         /* bsum[1] = bsum[0]; bsum[0] = 0 */

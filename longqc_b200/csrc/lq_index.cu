@@ -122,10 +122,12 @@ int lq_sort_by_key(LqMinimizers *m, int key_bits, LqDevBuf &tmp_key, LqDevBuf &t
     uint8_t *sin = m->has_span ? m->span.as<uint8_t>() : 0, *sout = m->has_span ? tmp_sp.as<uint8_t>() : 0;
     for (int p = 0; p < npass; ++p) {
         const int shift = 8 * p;
-        lq_rs_hist_k<<<nblk, RS_THREADS, 0, st>>>(kin, n, shift, nblk, gh);
+        { LqProfScope ps("radix_hist", st, 1, n * 4);
+          lq_rs_hist_k<<<nblk, RS_THREADS, 0, st>>>(kin, n, shift, nblk, gh); }
         LQ_CUDA_OK(cudaGetLastError());
         LQ_TRY((lq_exclusive_scan<uint32_t, uint64_t>(gh, gb, (size_t)256 * nblk, 0, ws, st)));
-        lq_rs_scatter_k<<<nblk, RS_THREADS, 0, st>>>(kin, yin, sin, n, shift, nblk, gb, p == npass - 1 ? (uint32_t*)0 : kout, yout, sout);
+        { LqProfScope ps("radix_scatter", st, 1, n * (12 + (p == npass - 1 ? 8 : 12)));
+          lq_rs_scatter_k<<<nblk, RS_THREADS, 0, st>>>(kin, yin, sin, n, shift, nblk, gb, p == npass - 1 ? (uint32_t*)0 : kout, yout, sout); }
         LQ_CUDA_OK(cudaGetLastError());
         { uint32_t *t = kin; kin = kout; kout = t; } { uint64_t *t = yin; yin = yout; yout = t; } { uint8_t *t = sin; sin = sout; sout = t; }
     }
@@ -177,6 +179,7 @@ int lq_index_mid_occ(const LqIndexDev *ix, float frac, int32_t *mid_occ, uint64_
     LQ_CUDA_OK(cudaMemsetAsync(ws.p, 0, (size_t)OCC_BINS * 4 + 16, st));
     const uint64_t nkeys = ix->n_keyspace;
     unsigned grid = lq_grid(nkeys, 256 * 16); if (grid > 148 * 16) grid = 148 * 16;
+    lq_prof_count_launch(1); lq_prof_d2h((uint64_t)OCC_BINS * 4);
     lq_occ_hist_k<<<grid, 256, 0, st>>>(ix->counts.as<uint32_t>(), nkeys, ws.as<uint32_t>());
     LQ_CUDA_OK(cudaGetLastError());
     LQ_CUDA_OK(cudaMemcpyAsync(h.data(), ws.p, (size_t)OCC_BINS * 4, cudaMemcpyDeviceToHost, st));
@@ -229,6 +232,7 @@ int lq_index_count(LqIndexDev *ix, const LqMinimizers *m, cudaStream_t st)
 {
     if (m->n == 0) return 0;
     unsigned grid = lq_grid(m->n, 256 * 8); if (grid > 148 * 32) grid = 148 * 32;
+    LqProfScope ps("idx_count", st, 1, m->n * 8);
     lq_count_k<<<grid, 256, 0, st>>>(m->key.as<uint32_t>(), m->n, ix->counts.as<uint32_t>());
     LQ_CUDA_OK(cudaGetLastError());
     return 0;
@@ -237,7 +241,8 @@ int lq_index_count(LqIndexDev *ix, const LqMinimizers *m, cudaStream_t st)
 int lq_index_finish(LqIndexDev *ix, LqMinimizers *m, LqDevBuf &ws, cudaStream_t st)
 {
     /* counts are final (all-reduced when several GPUs share the part); m holds ALL records of the part in y order */
-    LQ_TRY((lq_exclusive_scan<uint32_t, uint64_t>(ix->counts.as<uint32_t>(), ix->offs.as<uint64_t>(), (size_t)ix->n_keyspace, 1, ws, st)));
+    { LqProfScope ps("offs_scan", st, 0, ix->n_keyspace * 16);
+      LQ_TRY((lq_exclusive_scan<uint32_t, uint64_t>(ix->counts.as<uint32_t>(), ix->offs.as<uint64_t>(), (size_t)ix->n_keyspace, 1, ws, st))); }
     LQ_TRY(lq_sort_by_key(m, 2 * ix->k, ix->tmp_key, ix->tmp_y, ix->tmp_sp, ix->hist, ws, st));
     ix->n_rec = m->n;
     return 0;

@@ -531,6 +531,7 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     if (nb == 0) return 0;
     const uint64_t mi0 = h_first[q0], mi1 = h_first[q1];
     if (mi1 > mi0) {
+        LqProfScope ps("seed_fill", st, 1, (mi1 - mi0) * 32 + nb * 24);
         lq_fill_k<<<lq_grid((mi1 - mi0) * 32, 256), 256, 0, st>>>(mi0, mi1, qd->mins.key.as<uint32_t>(), qd->mins.y.as<uint64_t>(),
             qd->mins.has_span ? qd->mins.span.as<uint8_t>() : 0, ix->k, qd->first.as<uint64_t>(), qd->keep.as<uint32_t>(), qd->neff.as<uint32_t>(),
             qd->krank.as<uint32_t>(), qd->soff.as<uint64_t>(), seed_base, ix->counts.as<uint32_t>(), ix->offs.as<uint64_t>(), ix->rec.y.as<uint64_t>(),
@@ -542,6 +543,7 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     LQ_TRY(sc->bkt.ensure(2 * bcap * sizeof(AfBkt)));
     AfBkt *bk[2] = { sc->bkt.as<AfBkt>(), sc->bkt.as<AfBkt>() + bcap };
     /* counters: ctr[0],ctr[1] = bucket counts of the two lists, ctr[2] = cursor, ctr[3] = walks */
+    lq_prof_count_launch(2);
     lq_iota_k<<<lq_grid(nb, 256), 256, 0, st>>>(b->idx, nb);
     lq_af_init_k<<<lq_grid(nqb, 128), 128, 0, st>>>(nqb, d_qoff, b->s.sx, b->idx, bk[0], ctr + 0);
     LQ_CUDA_OK(cudaGetLastError());
@@ -552,10 +554,12 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         a.cur = bk[cur]; a.n_cur = ctr + cur; a.nxt = bk[cur ^ 1]; a.n_nxt = ctr + (cur ^ 1); a.cursor = ctr + 2; a.n_walk = ctr + 3; a.shift = shift;
         LQ_CUDA_OK(cudaMemsetAsync(ctr + (cur ^ 1), 0, 4, st));
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 2, 0, 4, st));
-        lq_af_level_k<<<148 * 8, AF_WARPS * 32, 0, st>>>(a);
+        { LqProfScope ps("seed_sort_level", st, 1, 0);
+          lq_af_level_k<<<148 * 8, AF_WARPS * 32, 0, st>>>(a); }
         LQ_CUDA_OK(cudaGetLastError());
         cur ^= 1;
     }
+    LqProfScope psg("seed_gather", st, 1, nb * 36);
     lq_gather_k<<<lq_grid(nb, 256), 256, 0, st>>>(nb, b->idx, b->s, b->ax, b->aq, b->am);
     LQ_CUDA_OK(cudaGetLastError());
     if (stats) {
@@ -583,6 +587,7 @@ static int run_lookup(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt,
     LQ_TRY(qd->qstat.ensure(((size_t)nq + 1) * sizeof(LqQStat)));
     h_stat->resize(nq);
     if (nm == 0) { for (uint32_t q = 0; q < nq; ++q) memset(&(*h_stat)[q], 0, sizeof(LqQStat)); return 0; }
+    lq_prof_count_launch(2); lq_prof_h2d(((uint64_t)nq + 1 + h_self_off[nq]) * 4); lq_prof_d2h((uint64_t)nq * sizeof(LqQStat));
     lq_lookup_k<<<lq_grid(nm, 256), 256, 0, st>>>(qd->mins.key.as<uint32_t>(), qd->mins.y.as<uint64_t>(), nm, ix->counts.as<uint32_t>(), ix->offs.as<uint64_t>(),
         ix->rec.y.as<uint64_t>(), mid_occ, *mt, qd->lambda.as<uint64_t>(), qd->reads.len.as<uint32_t>(), opt->covt, qd->keep.as<uint32_t>(), qd->neff.as<uint32_t>());
     LQ_CUDA_OK(cudaGetLastError());
@@ -622,6 +627,7 @@ int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int m
         if (nb > 0) {
             uint32_t *ctr = (uint32_t*)((char*)sc->misc.p + al((size_t)(nqb + 2) * 8));
             /* groups */
+            lq_prof_count_launch(3);
             lq_heads_k<<<lq_grid(nb, 256), 256, 0, st>>>(nb, b.ax, b.head);
             lq_qheads_k<<<lq_grid(nqb, 256), 256, 0, st>>>(nqb, d_qoff, nb, b.head);
             LQ_CUDA_OK(cudaGetLastError());
@@ -645,7 +651,8 @@ int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int m
             a.ovl = sc->ovl.as<LqOvl>(); a.n_ovl = ctr + 6; a.ovl_cap = ovl_cap; a.n_chains = ctr + 7; a.o = *opt;
             /* the DP reads t[] before writing it only through `t[j] == i` with i a seed index of this batch: clear it */
             LQ_CUDA_OK(cudaMemsetAsync(b.t, 0xff, (size_t)nb * 4, st));
-            lq_chain_k<<<148 * 8, CH_WARPS * 32, 0, st>>>(a);
+            { LqProfScope ps("chain", st, 1, nb * 32);
+              lq_chain_k<<<148 * 8, CH_WARPS * 32, 0, st>>>(a); }
             LQ_CUDA_OK(cudaGetLastError());
             uint32_t h_ctr[4];
             LQ_CUDA_OK(cudaMemcpyAsync(h_ctr, ctr + 4, 16, cudaMemcpyDeviceToHost, st));
@@ -655,6 +662,7 @@ int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int m
             const size_t old = ovl_out->size();
             ovl_out->resize(old + n_ovl);
             if (n_ovl) LQ_CUDA_OK(cudaMemcpyAsync(ovl_out->data() + old, sc->ovl.p, (size_t)n_ovl * sizeof(LqOvl), cudaMemcpyDeviceToHost, st));
+            lq_prof_d2h((uint64_t)n_ovl * sizeof(LqOvl) + 32); lq_prof_h2d((uint64_t)(nqb + 1) * 8);
             LQ_CUDA_OK(cudaStreamSynchronize(st));
             if (stats) { stats->n_seeds += nb; stats->n_groups += ng; stats->n_chains += h_ctr[3]; stats->n_ovl += n_ovl; stats->n_batches += 1; }
         }
@@ -671,6 +679,7 @@ int lq_map_nmatch(LqQueryDev *qd, std::vector<uint32_t> *n_match, cudaStream_t s
     if (nq == 0) return 0;
     LqDevBuf out; LQ_TRY(out.ensure(((size_t)nq + 2) * 4));
     LQ_CUDA_OK(cudaMemsetAsync(out.p, 0, ((size_t)nq + 2) * 4, st));
+    lq_prof_count_launch(1); lq_prof_d2h((uint64_t)nq * 4);
     lq_nmatch_k<<<lq_grid((size_t)nq * 32, 256), 256, 0, st>>>(nq, qd->first.as<uint64_t>(), qd->mcnt.as<uint32_t>(), out.as<uint32_t>(), out.as<uint32_t>() + nq);
     LQ_CUDA_OK(cudaGetLastError());
     uint32_t sat = 0;

@@ -280,7 +280,9 @@ int lq_reads_upload(LqReadsDev *d, const uint8_t *h_seq, const uint64_t *h_off, 
     /* pad words past the last slot (the 3-word k-mer gather may read one word past a read's last slot) */
     LQ_CUDA_OK(cudaMemsetAsync(d->b2.as<uint32_t>() + slots * LQ_SLOT_W2, 0, 16 * 4, st));
     LQ_CUDA_OK(cudaMemsetAsync(d->nm.as<uint32_t>() + slots * LQ_SLOT_WN, 0xff, 16 * 4, st));
+    lq_prof_h2d((uint64_t)(n_reads + 1) * 20 + (seq_on_device ? 0 : d->n_bases));
     if (slots) {
+        LqProfScope ps("pack", st, 1, d->n_bases + slots * (LQ_SLOT_W2 + LQ_SLOT_WN + 1) * 4);
         lq_pack_k<<<lq_grid(slots * 4, 256), 256, 0, st>>>(d_seq, d->off.as<uint64_t>(), d->slot0.as<uint64_t>(), d->len.as<uint32_t>(),
                                                            n_reads, slots, sdust_tbl, d->b2.as<uint32_t>(), d->nm.as<uint32_t>(), d->slot_read.as<uint32_t>());
         LQ_CUDA_OK(cudaGetLastError());
@@ -305,21 +307,24 @@ int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_b
         uint32_t *cnt = out->blk.as<uint32_t>();
         uint64_t *base = (uint64_t*)((char*)out->blk.p + (((size_t)(nblk + 1) * 4 + 7) & ~(size_t)7));
         a.blk_count = cnt;
-        lq_sketch_k<0><<<nblk, SK_THREADS, 0, st>>>(a);
+        { LqProfScope ps("sketch_count", st, 1, rd->n_slots * (LQ_SLOT_W2 + LQ_SLOT_WN) * 4);
+          lq_sketch_k<0><<<nblk, SK_THREADS, 0, st>>>(a); }
         LQ_CUDA_OK(cudaGetLastError());
         LQ_TRY((lq_exclusive_scan<uint32_t, uint64_t>(cnt, base, nblk, 1, ws, st)));
-        LQ_CUDA_OK(cudaMemcpyAsync(&total, base + nblk, 8, cudaMemcpyDeviceToHost, st));
+        LQ_CUDA_OK(cudaMemcpyAsync(&total, base + nblk, 8, cudaMemcpyDeviceToHost, st)); lq_prof_d2h(8);
         LQ_CUDA_OK(cudaStreamSynchronize(st));
         LQ_TRY(out->key.ensure((size_t)(total + 1) * 4));
         LQ_TRY(out->y.ensure((size_t)(total + 1) * 8));
         a.blk_base = base; a.out_key = out->key.as<uint32_t>(); a.out_y = out->y.as<uint64_t>();
-        lq_sketch_k<1><<<nblk, SK_THREADS, 0, st>>>(a);
+        { LqProfScope ps("sketch_write", st, 1, rd->n_slots * (LQ_SLOT_W2 + LQ_SLOT_WN) * 4 + total * 12);
+          lq_sketch_k<1><<<nblk, SK_THREADS, 0, st>>>(a); }
         LQ_CUDA_OK(cudaGetLastError());
     } else {
         const uint32_t n = rd->n_reads;
         LQ_TRY(out->blk.ensure((size_t)(n + 1) * 4 + (size_t)(n + 2) * 8));
         uint32_t *cnt = out->blk.as<uint32_t>();
         uint64_t *base = (uint64_t*)((char*)out->blk.p + (((size_t)(n + 1) * 4 + 7) & ~(size_t)7));
+        lq_prof_count_launch(2);
         lq_sketch_seq_k<0><<<lq_grid(n, 64), 64, 0, st>>>(a, n, 1, cnt, 0, 0);
         LQ_CUDA_OK(cudaGetLastError());
         LQ_TRY((lq_exclusive_scan<uint32_t, uint64_t>(cnt, base, n, 1, ws, st)));
@@ -339,6 +344,7 @@ int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_b
 int lq_read_first(const LqMinimizers *m, uint32_t rid_base, uint32_t n_reads, LqDevBuf &first, cudaStream_t st)
 {
     LQ_TRY(first.ensure((size_t)(n_reads + 2) * 8));
+    lq_prof_count_launch(1);
     lq_read_first_k<<<lq_grid(m->n + 1, 256), 256, 0, st>>>(m->y.as<uint64_t>(), m->n, rid_base, n_reads, first.as<uint64_t>());
     LQ_CUDA_OK(cudaGetLastError());
     return 0;

@@ -1,0 +1,232 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink) for the exchange step.
+
+How one index part is shared by N GPUs:
+  * the part's reads are owned by the ranks in contiguous, rank-ordered ranges, so rid == position in
+    the part and the concatenation of the ranks' minimizer records is already ordered by y;
+  * every rank packs + sketches its own reads and counts its minimizers (lqcov_part_sketch);
+  * ALL-REDUCE (sum) of the per-minimizer count table -- the one collective the method needs: the
+    counts decide mid_occ (index.c:123-144) and the high-frequency filter (lqmap.c:159,166);
+  * the (key, y) records are replicated in rank order (N broadcasts into one buffer = an all-gather
+    with uneven shards) and every rank builds the same index (lqcov_part_finish);
+  * the queries are split across the ranks, each rank maps its share against every part
+    (lqcov_map_part) and rank 0 concatenates the rows in query order.
+Parts follow the reference's mini-batch rule on the GLOBAL read list (index.c:238-246).
+
+Runner is also what bench.py drives at N=1 (no collective is issued then).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+from typing import List, Tuple
+
+import numpy as np
+
+from . import _lib
+from . import synth
+
+
+def part_boundaries(lengths: np.ndarray, batch_size: int, mini_batch_size: int = 50_000_000) -> List[Tuple[int, int]]:
+    """[start, end) read ranges of the index parts: a part keeps taking mini-batches (each = reads until
+    its own size >= min(mini_batch_size, batch_size)) while the part's sum of lengths is <= batch_size
+    (reference index.c:244,316; bseq.c:82-87)."""
+    mini = min(int(mini_batch_size), int(batch_size))
+    out, n, t0 = [], len(lengths), 0
+    while t0 < n:
+        sum_len, t1 = 0, t0
+        while t1 < n and not (sum_len > batch_size):
+            sz = 0
+            while t1 < n:
+                sz += int(lengths[t1]); sum_len += int(lengths[t1]); t1 += 1
+                if sz >= mini:
+                    break
+        out.append((t0, t1))
+        t0 = t1
+    return out
+
+
+def split_even(n: int, world: int) -> List[Tuple[int, int]]:
+    """contiguous, rank-ordered shares of n items"""
+    base, rem = divmod(n, world)
+    out, s = [], 0
+    for r in range(world):
+        e = s + base + (1 if r < rem else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+class _DevArr:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def _view(ptr, n, typestr):
+    import torch
+    return torch.as_tensor(_DevArr(ptr, n, typestr), device="cuda")
+
+
+def _meta_struct(names: List[bytes], lengths: np.ndarray):
+    """lqcov_reads_t describing a whole part (lengths + names, no bases)"""
+    off = np.zeros(len(lengths) + 1, dtype=np.uint64)
+    np.cumsum(lengths.astype(np.uint64), out=off[1:])
+    blob = b"".join(names)
+    nlen = np.fromiter((len(x) for x in names), dtype=np.uint64, count=len(names))
+    noff = np.zeros(len(names) + 1, dtype=np.uint64)
+    np.cumsum(nlen, out=noff[1:])
+    nbuf = np.frombuffer(blob if blob else b"\0", dtype=np.uint8)
+    st = _lib.ReadsStruct()
+    st.n = len(lengths); st.seq = None; st.seq_off = off.ctypes.data; st.qual = None
+    st.names = nbuf.ctypes.data; st.name_off = noff.ctypes.data; st.seq_on_device = 0
+    return _lib._Keep(st, (off, nbuf, noff))
+
+
+def _sub_struct(keep, a: int, b: int, seq_ptr, on_device: int):
+    """reads [a, b) of a reads_struct(), with the bases taken from `seq_ptr` (same offsets)"""
+    st = _lib.ReadsStruct()
+    st.n = b - a
+    st.seq = seq_ptr
+    st.seq_off = keep.st.seq_off + 8 * a
+    st.qual = None
+    st.names = keep.st.names
+    st.name_off = keep.st.name_off + 8 * a
+    st.seq_on_device = on_device
+    return st
+
+
+class Runner:
+    """One rank of the (possibly multi-GPU) coverage job on the synthetic workload of bench.py."""
+
+    def __init__(self, a, opt, rank: int, world: int, local: int):
+        self.a, self.opt, self.rank, self.world, self.local = a, opt, rank, world, local
+        self.cov = None
+        self.last_stats = {}
+        self.tables = []
+
+    # -- inputs: every rank owns `reads` target reads of ONE genome shared by all ranks (30x overall) and
+    #    maps `queries/world` of its own reads
+    def make_inputs(self):
+        import torch
+        a, world, rank = self.a, self.world, self.rank
+        rng_g = np.random.default_rng(a.seed)
+        G = max(int(a.reads * world * a.read_len / 30.0), 2 * a.read_len)
+        genome = synth.make_genome(G, rng_g)
+        rng = np.random.default_rng(a.seed + 7919 * (rank + 1))
+        my_lo = rank * a.reads
+        self.targets = synth.simulate_reads(genome, a.reads, a.read_len, a.err, rng, name_start=my_lo)
+        nq_lo, nq_hi = split_even(a.queries, world)[rank]
+        qidx = np.sort(rng.choice(a.reads, size=min(nq_hi - nq_lo, a.reads), replace=False))
+        self.queries = self.targets.subset(qidx)
+        del genome
+        # global read list = rank-major: lengths and names of every rank's reads
+        lens = self.targets.lengths().astype(np.int64)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.from_numpy(lens).cuda()
+            allt = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            self.all_lens = np.concatenate([x.cpu().numpy() for x in allt])
+            qb = torch.tensor([self.queries.n_bases], dtype=torch.int64, device="cuda")
+            dist.all_reduce(qb)
+            self.query_bases_all = int(qb.item())
+        else:
+            self.all_lens = lens
+            self.query_bases_all = self.queries.n_bases
+        self.target_bases_all = int(self.all_lens.sum())
+        self.all_names = [b"r" + str(i).encode() for i in range(a.reads * world)]
+        self.parts = part_boundaries(self.all_lens, int(self.opt.batch_size), int(self.opt.mini_batch_size))
+        self.part_meta = [_meta_struct(self.all_names[s:e], self.all_lens[s:e]) for s, e in self.parts]
+        # host (pinned) and device copies of the bases
+        self.t_keep = _lib.reads_struct(self.targets)
+        self.q_keep = _lib.reads_struct(self.queries)
+        self.t_pin = torch.from_numpy(self.targets.seq).pin_memory()
+        self.q_pin = torch.from_numpy(self.queries.seq).pin_memory()
+        self.t_dev = self.t_pin.cuda()
+        self.q_dev = self.q_pin.cuda()
+        torch.cuda.synchronize()
+        self.cov = _lib.Coverage(self.opt)
+        return self.targets, self.queries
+
+    def job_bases(self):
+        return self.target_bases_all + self.query_bases_all
+
+    def parallelism(self):
+        if self.world == 1:
+            return "1 GPU"
+        return "%d GPUs: targets sharded for sketch+count, NCCL all-reduce of the 4^k count table, index replicated (records broadcast in rank order), queries sharded" % self.world
+
+    def _exchange(self, lib, h):
+        import torch
+        import torch.distributed as dist
+        counts, nc, key, y, n = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_void_p(), C.c_uint64()
+        lib.lqcov_part_device_views(h, C.byref(counts), C.byref(nc), C.byref(key), C.byref(y), C.byref(n))
+        tc = _view(counts.value, nc.value, "<i4")
+        dist.all_reduce(tc)                                   # the minimizer-count all-reduce
+        sizes = torch.zeros(self.world, dtype=torch.int64, device="cuda")
+        sizes[self.rank] = n.value
+        dist.all_reduce(sizes)
+        sizes = sizes.tolist()
+        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        fk, fy = C.c_void_p(), C.c_void_p()
+        if lib.lqcov_part_gather_buffers(h, int(offs[-1]), C.byref(fk), C.byref(fy)) != 0:
+            raise _lib.LqcovError("lqcov_part_gather_buffers failed")
+        full_k = _view(fk.value, max(int(offs[-1]), 1), "<i4")
+        full_y = _view(fy.value, max(int(offs[-1]), 1), "<i8")
+        if n.value:
+            full_k[offs[self.rank]:offs[self.rank + 1]].copy_(_view(key.value, n.value, "<i4"))
+            full_y[offs[self.rank]:offs[self.rank + 1]].copy_(_view(y.value, n.value, "<i8"))
+        for r in range(self.world):                           # index replication: rank-ordered all-gather
+            if sizes[r]:
+                dist.broadcast(full_k[offs[r]:offs[r + 1]], src=r)
+                dist.broadcast(full_y[offs[r]:offs[r + 1]], src=r)
+        torch.cuda.synchronize()
+
+    def step(self, resident: bool):
+        lib = _lib.load()
+        lib.lqcov_part_sketch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        lib.lqcov_part_finish.argtypes = [C.c_void_p, C.c_void_p]
+        lib.lqcov_map_part.argtypes = [C.c_void_p]
+        lib.lqcov_reset.argtypes = [C.c_void_p]
+        lib.lqcov_part_device_views.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        lib.lqcov_part_gather_buffers.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        h = self.cov._h
+        lib.lqcov_reset(h)
+        tptr = self.t_dev.data_ptr() if resident else self.t_pin.data_ptr()
+        qptr = self.q_dev.data_ptr() if resident else self.q_pin.data_ptr()
+        qs = _sub_struct(self.q_keep, 0, self.queries.n, qptr, 1 if resident else 0)
+        qs.qual = self.q_keep.st.qual
+        if lib.lqcov_set_queries(h, C.byref(qs)) != 0:
+            raise _lib.LqcovError("lqcov_set_queries failed")
+        my_lo = self.rank * self.a.reads
+        my_hi = my_lo + self.targets.n
+        for (s, e), meta in zip(self.parts, self.part_meta):
+            a, b = max(s, my_lo), min(e, my_hi)                # my reads inside this part
+            if b < a:
+                a = b = max(min(s, my_hi), my_lo)
+            sub = _sub_struct(self.t_keep, a - my_lo, b - my_lo, tptr, 1 if resident else 0)
+            if lib.lqcov_part_sketch(h, C.byref(sub), a - s if b > a else 0) != 0:
+                raise _lib.LqcovError("lqcov_part_sketch failed")
+            if self.world > 1:
+                self._exchange(lib, h)
+            if lib.lqcov_part_finish(h, C.byref(meta.st)) != 0:
+                raise _lib.LqcovError("lqcov_part_finish failed")
+            if lib.lqcov_map_part(h) != 0:
+                raise _lib.LqcovError("lqcov_map_part failed")
+        table = self.cov.table()
+        if self.world > 1:
+            import torch.distributed as dist
+            rows = [None] * self.world if self.rank == 0 else None
+            dist.gather_object(table, rows, dst=0)
+            if self.rank == 0:
+                table = b"".join(rows)
+        self.last_stats = self.cov.stats()
+        self.last_table = table
+        return table
+
+    def parity_note(self):
+        """md5 / row count of the benchmarked table (rank 0) -- the exact check lives in tests/ (oracle at small sizes)."""
+        if self.rank != 0:
+            return None
+        t = self.last_table
+        return {"rows": t.count(b"\n"), "md5": hashlib.md5(t).hexdigest(),
+                "nonsense_frac": sum(1 for ln in t.split(b"\n") if ln and ln.split(b"\t")[4] == b"0") / max(1, t.count(b"\n"))}
