@@ -121,6 +121,7 @@ extern "C" int lqcov_set_queries(lqcov_ctx *c, const lqcov_reads_t *q)
     LQ_TRY(lq_sketch_run(&qd->reads, c->opt.w, c->opt.k, c->opt.is_hpc, 0, &qd->mins, c->ws, c->st));
     qd->n_min = qd->mins.n;
     LQ_TRY(lq_read_first(&qd->mins, 0, q->n, qd->first, c->st));
+    LQ_TRY(lq_map_flag_dups(qd, 2 * c->opt.k, c->ws, c->st));
     c->qfirst.resize((size_t)q->n + 1);
     LQ_CUDA_OK(cudaMemcpyAsync(c->qfirst.data(), qd->first.p, ((size_t)q->n + 1) * 8, cudaMemcpyDeviceToHost, c->st));
     LQ_TRY(qd->lambda.ensure(((size_t)q->n + 1) * 8)); LQ_TRY(qd->lambda2.ensure(((size_t)q->n + 1) * 8));

@@ -105,9 +105,9 @@ __global__ void __launch_bounds__(RS_THREADS) lq_rs_scatter_k(const uint32_t *__
     }
 }
 
-int lq_sort_by_key(LqMinimizers *m, int key_bits, LqDevBuf &tmp_key, LqDevBuf &tmp_y, LqDevBuf &tmp_sp, LqDevBuf &hist, LqDevBuf &ws, cudaStream_t st)
+int lq_sort_by_key(LqMinimizers *m, int key_bits, LqDevBuf &tmp_key, LqDevBuf &tmp_y, LqDevBuf &tmp_sp, LqDevBuf &hist, LqDevBuf &ws, cudaStream_t st, int keep_keys)
 {
-    /* on return m->y (and m->span) are stable-sorted by key; m->key is left in an unspecified order */
+    /* on return m->y (and m->span) are stable-sorted by key; m->key is sorted too when keep_keys, else unspecified */
     const uint64_t n = m->n;
     if (n == 0) return 0;
     const int npass = (key_bits + 7) / 8;
@@ -126,8 +126,8 @@ int lq_sort_by_key(LqMinimizers *m, int key_bits, LqDevBuf &tmp_key, LqDevBuf &t
           lq_rs_hist_k<<<nblk, RS_THREADS, 0, st>>>(kin, n, shift, nblk, gh); }
         LQ_CUDA_OK(cudaGetLastError());
         LQ_TRY((lq_exclusive_scan<uint32_t, uint64_t>(gh, gb, (size_t)256 * nblk, 0, ws, st)));
-        { LqProfScope ps("radix_scatter", st, 1, n * (12 + (p == npass - 1 ? 8 : 12)));
-          lq_rs_scatter_k<<<nblk, RS_THREADS, 0, st>>>(kin, yin, sin, n, shift, nblk, gb, p == npass - 1 ? (uint32_t*)0 : kout, yout, sout); }
+        { LqProfScope ps("radix_scatter", st, 1, n * (12 + ((p == npass - 1 && !keep_keys) ? 8 : 12)));
+          lq_rs_scatter_k<<<nblk, RS_THREADS, 0, st>>>(kin, yin, sin, n, shift, nblk, gb, (p == npass - 1 && !keep_keys) ? (uint32_t*)0 : kout, yout, sout); }
         LQ_CUDA_OK(cudaGetLastError());
         { uint32_t *t = kin; kin = kout; kout = t; } { uint64_t *t = yin; yin = yout; yout = t; } { uint8_t *t = sin; sin = sout; sout = t; }
     }
@@ -243,7 +243,7 @@ int lq_index_finish(LqIndexDev *ix, LqMinimizers *m, LqDevBuf &ws, cudaStream_t 
     /* counts are final (all-reduced when several GPUs share the part); m holds ALL records of the part in y order */
     { LqProfScope ps("offs_scan", st, 0, ix->n_keyspace * 16);
       LQ_TRY((lq_exclusive_scan<uint32_t, uint64_t>(ix->counts.as<uint32_t>(), ix->offs.as<uint64_t>(), (size_t)ix->n_keyspace, 1, ws, st))); }
-    LQ_TRY(lq_sort_by_key(m, 2 * ix->k, ix->tmp_key, ix->tmp_y, ix->tmp_sp, ix->hist, ws, st));
+    LQ_TRY(lq_sort_by_key(m, 2 * ix->k, ix->tmp_key, ix->tmp_y, ix->tmp_sp, ix->hist, ws, st, 0));
     ix->n_rec = m->n;
     return 0;
 }

@@ -21,5 +21,5 @@ int lq_index_alloc(LqIndexDev *ix, int k, cudaStream_t st);
 int lq_index_count(LqIndexDev *ix, const LqMinimizers *m, cudaStream_t st);
 int lq_index_finish(LqIndexDev *ix, LqMinimizers *m, LqDevBuf &ws, cudaStream_t st);
 int lq_index_mid_occ(const LqIndexDev *ix, float frac, int32_t *mid_occ, uint64_t *n_distinct, LqDevBuf &ws, cudaStream_t st);
-int lq_sort_by_key(LqMinimizers *m, int key_bits, LqDevBuf &tmp_key, LqDevBuf &tmp_y, LqDevBuf &tmp_sp, LqDevBuf &hist, LqDevBuf &ws, cudaStream_t st);
+int lq_sort_by_key(LqMinimizers *m, int key_bits, LqDevBuf &tmp_key, LqDevBuf &tmp_y, LqDevBuf &tmp_sp, LqDevBuf &hist, LqDevBuf &ws, cudaStream_t st, int keep_keys);
 #endif

@@ -17,7 +17,7 @@
 
 void LqQueryDev::release()
 {
-    reads.release(); mins.release(); first.release(); lambda.release(); lambda2.release(); mcnt.release();
+    reads.release(); mins.release(); first.release(); dup.release(); lambda.release(); lambda2.release(); mcnt.release();
     keep.release(); neff.release(); krank.release(); soff.release(); qstat.release();
     self_off.release(); self_list.release(); qrank.release(); trank.release();
 }
@@ -94,7 +94,7 @@ __global__ void lq_fill_k(uint64_t mi0, uint64_t mi1, const uint32_t *__restrict
                           const uint64_t *__restrict__ first, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ neff,
                           const uint32_t *__restrict__ krank, const uint64_t *__restrict__ soff, uint64_t seed_base,
                           const uint32_t *__restrict__ counts, const uint64_t *__restrict__ offs, const uint64_t *__restrict__ pos,
-                          MapTables t, const uint32_t *__restrict__ qlen, SeedArrays s)
+                          MapTables t, const uint32_t *__restrict__ qlen, const uint8_t *__restrict__ dup, SeedArrays s)
 {
     const uint64_t mi = mi0 + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const uint32_t lane = threadIdx.x & 31;
@@ -107,6 +107,7 @@ __global__ void lq_fill_k(uint64_t mi0, uint64_t mi1, const uint32_t *__restrict
     const uint64_t o = offs[key];
     uint64_t out = soff[mi] - seed_base;
     const int32_t ql = (int32_t)qlen[q];
+    const uint32_t tie = dup[mi] ? 0x80000000u : 0u;       /* carried through the sort only (bit 31 of sq) */
     for (uint32_t j0 = 0; j0 < c; j0 += 32) {
         const uint32_t j = j0 + lane;
         uint64_t r = 0; bool ok = j < c;
@@ -117,10 +118,10 @@ __global__ void lq_fill_k(uint64_t mi0, uint64_t mi1, const uint32_t *__restrict
             const uint32_t rpos = (uint32_t)r >> 1;
             if (((uint32_t)r & 1) == qstrand) { /* lqmap.c:191-193 */
                 s.sx[at] = (r & 0xffffffff00000000ULL) | rpos;
-                s.sq[at] = qpos;
+                s.sq[at] = qpos | tie;
             } else {                             /* lqmap.c:194-197 */
                 s.sx[at] = 1ULL << 63 | (r & 0xffffffff00000000ULL) | rpos;
-                s.sq[at] = (uint32_t)(ql - ((int32_t)qpos + 1 - (int32_t)span) - 1);
+                s.sq[at] = (uint32_t)(ql - ((int32_t)qpos + 1 - (int32_t)span) - 1) | tie;
             }
             s.sm[at] = span << 24 | rank;
         }
@@ -132,7 +133,7 @@ __global__ void lq_fill_k(uint64_t mi0, uint64_t mi1, const uint32_t *__restrict
 
 struct AfBkt { uint32_t beg, end; };
 struct AfArgs {
-    const uint64_t *sx; uint32_t *idx, *idx2, *dest; uint8_t *dig;
+    const uint64_t *sx; const uint32_t *sq; uint32_t *idx, *idx2, *dest; uint8_t *dig;
     const AfBkt *cur; const uint32_t *n_cur; AfBkt *nxt; uint32_t *n_nxt; uint32_t *cursor; uint32_t *n_walk;
     int shift;
 };
@@ -171,11 +172,14 @@ __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
         /* 1. digits + histogram */
         for (uint32_t d = lane; d < 256; d += 32) cnt[d] = 0;
         __syncwarp();
+        uint32_t tied = 0;
         for (uint32_t p0 = 0; p0 < n; p0 += 32) {
             const uint32_t p = p0 + lane; const bool ok = p < n;
             const uint32_t act = __ballot_sync(0xffffffffu, ok);
             if (ok) {
-                const uint32_t d = (uint32_t)(a.sx[idx[p]] >> a.shift) & 255u;
+                const uint32_t e = idx[p];
+                const uint32_t d = (uint32_t)(a.sx[e] >> a.shift) & 255u;
+                tied |= a.sq[e] >> 31;
                 dig[p] = (uint8_t)d;
                 const uint32_t peers = __match_any_sync(act, d);
                 if ((peers & lt) == 0) cnt[d] += __popc(peers);
@@ -190,8 +194,23 @@ __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
         #pragma unroll
         for (int j = 0; j < 8; ++j) { start[8 * lane + j] = run; run += cnt[8 * lane + j]; }
         const uint32_t nb = lq_warp_sum(ne);
+        tied = __any_sync(0xffffffffu, tied);
         __syncwarp();
-        if (nb == 2) {
+        if (nb > 1 && !tied) {
+            /* no two keys of this bucket are equal, so the sorted result does not depend on how the reference permutes:
+             * stable counting partition, rows of 32 in order (head[] = running count per digit) */
+            for (uint32_t d = lane; d < 256; d += 32) head[d] = 0;
+            __syncwarp();
+            for (uint32_t p0 = 0; p0 < n; p0 += 32) {
+                const uint32_t p = p0 + lane; const bool ok = p < n;
+                const uint32_t act = __ballot_sync(0xffffffffu, ok);
+                uint32_t d = 0, peers = 0;
+                if (ok) { d = dig[p]; peers = __match_any_sync(act, d); dest[p] = start[d] + head[d] + __popc(peers & lt); }
+                __syncwarp();
+                if (ok && (peers & lt) == 0) head[d] += __popc(peers);
+                __syncwarp();
+            }
+        } else if (nb == 2) {
             /* closed form (lq_af_two_dest): d0 < d1 are the two non-empty digits */
             uint32_t d0 = 256, d1 = 0;
             #pragma unroll
@@ -249,7 +268,7 @@ __global__ void lq_gather_k(uint64_t n, const uint32_t *__restrict__ idx, SeedAr
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t j = idx[i];
-    ax[i] = s.sx[j]; aq[i] = s.sq[j]; am[i] = s.sm[j];
+    ax[i] = s.sx[j]; aq[i] = s.sq[j] & 0x7fffffffu; am[i] = s.sm[j];
 }
 
 /* ------------------------------------------------------------------ K6/K7: groups, chaining, accounting */
@@ -274,10 +293,22 @@ __global__ void lq_gstart_k(uint64_t n, const uint32_t *__restrict__ head, const
     if (i == n) gstart[gid[n]] = (uint32_t)n; /* gid[n] = number of groups */
 }
 
+/* groups that can hold a chain (>= min_cnt anchors, chain.c:116-119): compacted so that a warp is only spent on those */
+__global__ void lq_biggroups_k(uint32_t ng, const uint32_t *__restrict__ gstart, uint32_t min_cnt, uint32_t *__restrict__ big, uint32_t *__restrict__ n_big)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = g < ng && gstart[g + 1] - gstart[g] >= min_cnt;
+    const uint32_t m = __ballot_sync(0xffffffffu, ok), lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0 && m) base = atomicAdd(n_big, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (ok) big[base + __popc(m & ((1u << lane) - 1))] = g;
+}
+
 struct ChainArgs {
     const uint64_t *ax; const uint32_t *aq, *am;
     int32_t *f, *p, *v, *t; uint64_t *uend; uint32_t *vl, *s_lo, *s_hi;
-    const uint32_t *gstart; const uint32_t *n_groups; uint32_t *cursor;
+    const uint32_t *gstart; const uint32_t *big; const uint32_t *n_groups; uint32_t *cursor;
     uint32_t nqb, q0; const uint64_t *qoff;
     const LqQStat *qstat; const uint32_t *qlen, *tlen; const uint64_t *first;
     uint64_t *lambda, *lambda2; uint32_t *mcnt;
@@ -295,6 +326,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32) lq_chain_k(ChainArgs a)
         if (lane == 0) g = atomicAdd(a.cursor, 1u);
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= ng) break;
+        g = a.big[g];
         const int32_t gb = (int32_t)a.gstart[g], ge = (int32_t)a.gstart[g + 1], n = ge - gb;
         if (n < a.o.min_cnt) continue; /* a chain needs min_cnt anchors of one (strand, target) run (chain.c:116-119) */
         /* owning query */
@@ -446,6 +478,20 @@ __global__ void __launch_bounds__(CH_WARPS * 32) lq_chain_k(ChainArgs a)
     }
 }
 
+/* sorted by key (stable, so equal keys of one query are adjacent): flag (key, query, strand) groups of size > 1 */
+__global__ void lq_dupflag_k(uint64_t n, const uint32_t *__restrict__ skey, const uint64_t *__restrict__ smi, const uint64_t *__restrict__ qy, uint8_t *__restrict__ dup)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t key = skey[j]; const uint64_t mi = smi[j], y = qy[mi];
+    const uint32_t q = (uint32_t)(y >> 32), strand = (uint32_t)y & 1;
+    bool d = false;
+    for (uint64_t o = j; o-- > 0 && skey[o] == key; ) { const uint64_t yo = qy[smi[o]]; if ((uint32_t)(yo >> 32) != q) break; if (((uint32_t)yo & 1) == strand) { d = true; break; } }
+    for (uint64_t o = j + 1; !d && o < n && skey[o] == key; ++o) { const uint64_t yo = qy[smi[o]]; if ((uint32_t)(yo >> 32) != q) break; if (((uint32_t)yo & 1) == strand) d = true; }
+    dup[mi] = d;
+}
+__global__ void lq_iota64_k(uint64_t *a, uint64_t n) { const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }
+
 /* minimap2-coverage.c:552-562 */
 __global__ void lq_nmatch_k(uint32_t nq, const uint64_t *__restrict__ first, const uint32_t *__restrict__ mcnt, uint32_t *__restrict__ n_match, uint32_t *__restrict__ sat)
 {
@@ -535,7 +581,7 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         lq_fill_k<<<lq_grid((mi1 - mi0) * 32, 256), 256, 0, st>>>(mi0, mi1, qd->mins.key.as<uint32_t>(), qd->mins.y.as<uint64_t>(),
             qd->mins.has_span ? qd->mins.span.as<uint8_t>() : 0, ix->k, qd->first.as<uint64_t>(), qd->keep.as<uint32_t>(), qd->neff.as<uint32_t>(),
             qd->krank.as<uint32_t>(), qd->soff.as<uint64_t>(), seed_base, ix->counts.as<uint32_t>(), ix->offs.as<uint64_t>(), ix->rec.y.as<uint64_t>(),
-            mt, qd->reads.len.as<uint32_t>(), b->s);
+            mt, qd->reads.len.as<uint32_t>(), qd->dup.as<uint8_t>(), b->s);
         LQ_CUDA_OK(cudaGetLastError());
     }
     /* bucket lists: at most nb/65 + nqb live buckets per level */
@@ -550,12 +596,12 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     int cur = 0;
     for (int shift = 56; shift >= 0; shift -= 8) {
         AfArgs a;
-        a.sx = b->s.sx; a.idx = b->idx; a.idx2 = b->idx2; a.dest = b->dest; a.dig = b->dig;
+        a.sx = b->s.sx; a.sq = b->s.sq; a.idx = b->idx; a.idx2 = b->idx2; a.dest = b->dest; a.dig = b->dig;
         a.cur = bk[cur]; a.n_cur = ctr + cur; a.nxt = bk[cur ^ 1]; a.n_nxt = ctr + (cur ^ 1); a.cursor = ctr + 2; a.n_walk = ctr + 3; a.shift = shift;
         LQ_CUDA_OK(cudaMemsetAsync(ctr + (cur ^ 1), 0, 4, st));
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 2, 0, 4, st));
         { LqProfScope ps("seed_sort_level", st, 1, 0);
-          lq_af_level_k<<<148 * 8, AF_WARPS * 32, 0, st>>>(a); }
+          lq_af_level_k<<<148 * 16, AF_WARPS * 32, 0, st>>>(a); }
         LQ_CUDA_OK(cudaGetLastError());
         cur ^= 1;
     }
@@ -635,17 +681,20 @@ int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int m
             uint32_t ng = 0;
             LQ_CUDA_OK(cudaMemcpyAsync(&ng, b.gid + nb, 4, cudaMemcpyDeviceToHost, st));
             LQ_CUDA_OK(cudaStreamSynchronize(st));
-            LQ_TRY(sc->grp.ensure(((size_t)ng + 2) * 4));
+            const size_t big_cap = (size_t)(nb / (uint64_t)std::max(opt->min_cnt, 1)) + 64;
+            LQ_TRY(sc->grp.ensure(((size_t)ng + 2) * 4 + big_cap * 4));
+            uint32_t *d_big = sc->grp.as<uint32_t>() + ng + 2;
             lq_gstart_k<<<lq_grid(nb + 1, 256), 256, 0, st>>>(nb, b.head, b.gid, sc->grp.as<uint32_t>());
             LQ_CUDA_OK(cudaGetLastError());
             /* ctr[4] = n_groups, ctr[5] = cursor, ctr[6] = n_ovl, ctr[7] = n_chains */
             const uint32_t ovl_cap = (uint32_t)std::min<uint64_t>(nb / (uint64_t)std::max(opt->min_cnt, 1) + 1024, 0x7fffffffULL);
             LQ_TRY(sc->ovl.ensure((size_t)ovl_cap * sizeof(LqOvl)));
             LQ_CUDA_OK(cudaMemsetAsync(ctr + 4, 0, 16, st));
-            LQ_CUDA_OK(cudaMemcpyAsync(ctr + 4, &ng, 4, cudaMemcpyHostToDevice, st));
+            lq_prof_count_launch(1);
+            lq_biggroups_k<<<lq_grid(ng, 256), 256, 0, st>>>(ng, sc->grp.as<uint32_t>(), (uint32_t)std::max(opt->min_cnt, 1), d_big, ctr + 4); /* ctr[4] = chainable groups */
             ChainArgs a;
             a.ax = b.ax; a.aq = b.aq; a.am = b.am; a.f = b.f; a.p = b.p; a.v = b.v; a.t = b.t; a.uend = b.uend; a.vl = b.vl; a.s_lo = b.head; a.s_hi = b.gid;
-            a.gstart = sc->grp.as<uint32_t>(); a.n_groups = ctr + 4; a.cursor = ctr + 5;
+            a.gstart = sc->grp.as<uint32_t>(); a.big = d_big; a.n_groups = ctr + 4; a.cursor = ctr + 5;
             a.nqb = nqb; a.q0 = q0; a.qoff = d_qoff; a.qstat = qd->qstat.as<LqQStat>(); a.qlen = qd->reads.len.as<uint32_t>(); a.tlen = ix->tlen.as<uint32_t>();
             a.first = qd->first.as<uint64_t>(); a.lambda = qd->lambda.as<uint64_t>(); a.lambda2 = qd->lambda2.as<uint64_t>(); a.mcnt = qd->mcnt.as<uint32_t>();
             a.ovl = sc->ovl.as<LqOvl>(); a.n_ovl = ctr + 6; a.ovl_cap = ovl_cap; a.n_chains = ctr + 7; a.o = *opt;
@@ -670,6 +719,28 @@ int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int m
         q0 = q1;
     }
     return 0;
+}
+
+int lq_map_flag_dups(LqQueryDev *qd, int key_bits, LqDevBuf &ws, cudaStream_t st)
+{
+    const uint64_t n = qd->n_min;
+    LQ_TRY(qd->dup.ensure(n + 16));
+    if (n == 0) return 0;
+    LqMinimizers tmp; LqDevBuf tk, ty, ts, hist;
+    int rc = -1;
+    if (tmp.key.ensure(n * 4) == 0 && tmp.y.ensure(n * 8) == 0) {
+        tmp.n = n; tmp.has_span = 0;
+        cudaMemcpyAsync(tmp.key.p, qd->mins.key.p, n * 4, cudaMemcpyDeviceToDevice, st);
+        lq_iota64_k<<<lq_grid(n, 256), 256, 0, st>>>(tmp.y.as<uint64_t>(), n);
+        if (lq_sort_by_key(&tmp, key_bits, tk, ty, ts, hist, ws, st, 1) == 0) {
+            const uint32_t *skey = tmp.key.as<uint32_t>();
+            lq_dupflag_k<<<lq_grid(n, 256), 256, 0, st>>>(n, skey, tmp.y.as<uint64_t>(), qd->mins.y.as<uint64_t>(), qd->dup.as<uint8_t>());
+            lq_prof_count_launch(2);
+            rc = cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess ? 0 : -1;
+        }
+    }
+    tmp.release(); tk.release(); ty.release(); ts.release(); hist.release();
+    return rc;
 }
 
 int lq_map_nmatch(LqQueryDev *qd, std::vector<uint32_t> *n_match, cudaStream_t st)

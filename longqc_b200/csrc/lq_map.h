@@ -22,6 +22,7 @@ struct LqQueryDev {
     LqMinimizers mins;                /* key, y (rid = query index), span */
     LqDevBuf first;                   /* u64[nq+1] minimizer range per query */
     LqDevBuf lambda, lambda2;         /* u64[nq]  esterr.c:120,128 */
+    LqDevBuf dup;                     /* u8[n_min]: another minimizer of the same query has the same (key, strand) => its seeds tie (lq_afsort_core.h) */
     LqDevBuf mcnt;                    /* u32[n_min] per-minimizer match counters, indexed first[q] + rank among KEPT minimizers (esterr.c:130-137) */
     /* per part */
     LqDevBuf keep, neff, krank, soff; /* u32[n_min], u32[n_min], u32[n_min+1], u64[n_min+1] */
@@ -50,6 +51,9 @@ int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int m
 
 /* final per-query reduction of the match counters (minimap2-coverage.c:552-562): n_match[q] */
 int lq_map_nmatch(LqQueryDev *qd, std::vector<uint32_t> *n_match, cudaStream_t st);
+
+/* once per query set: flag the minimizers whose (key, strand) occurs more than once in their query */
+int lq_map_flag_dups(LqQueryDev *qd, int key_bits, LqDevBuf &ws, cudaStream_t st);
 
 /* test hooks: run seeding+sort for queries [q0,q1) and return the sorted seeds (x, y as the reference lays them out) */
 int lq_map_debug_sorted_seeds(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int mid_occ, uint32_t q,
