@@ -53,7 +53,7 @@ typedef struct {
     /* execution */
     int n_threads;            /* -t: host worker threads (parsing) */
     int device;               /* CUDA device ordinal; -1 = current / CUDA_VISIBLE_DEVICES order 0 */
-    uint64_t seed_budget;     /* seeds per device batch (0 = default 400 M) */
+    uint64_t seed_budget;     /* seeds per device batch (0 = default 1000 M, ~45 bytes of HBM each) */
     int verbose;              /* 0..3, stderr progress lines like the reference's mm_verbose */
 } lqcov_opt_t;
 

@@ -62,7 +62,7 @@ class Stats(C.Structure):
 
 _lib = None
 
-SYMBOLS = ["lqcov_abi_version", "lqcov_opt_init", "lqcov_create", "lqcov_destroy", "lqcov_set_queries", "lqcov_add_part",
+SYMBOLS = ["lqcov_abi_version", "lqcov_opt_init", "lqcov_create", "lqcov_destroy", "lqcov_reset", "lqcov_part_sketch", "lqcov_part_device_views", "lqcov_part_gather_buffers", "lqcov_part_finish", "lqcov_map_part", "lqcov_profile_enable", "lqcov_profile_reset", "lqcov_profile_json", "lqcov_set_queries", "lqcov_add_part",
            "lqcov_add_targets", "lqcov_table", "lqcov_get_stats", "lqcov_free", "lqcov_sdust_table", "lqcov_sketch",
            "lqcov_debug_seeds", "lqcov_index_part", "lqcov_reader_open", "lqcov_reader_next", "lqcov_reader_next_part",
            "lqcov_reader_close", "lqcov_main", "lqcov_sdust_main"]
@@ -82,6 +82,7 @@ def load() -> C.CDLL:
     lib.lqcov_create.argtypes = [C.c_void_p]
     lib.lqcov_create.restype = C.c_void_p
     lib.lqcov_destroy.argtypes = [C.c_void_p]
+    lib.lqcov_reset.argtypes = [C.c_void_p]
     for f in ("lqcov_set_queries", "lqcov_add_part", "lqcov_add_targets", "lqcov_index_part"):
         getattr(lib, f).argtypes = [C.c_void_p, C.c_void_p]
         getattr(lib, f).restype = C.c_int

@@ -255,7 +255,7 @@ extern "C" int lqcov_map_part(lqcov_ctx *c)
     double t0 = now_ms();
     LqMapOpt mo; map_opt_of(&c->opt, &mo);
     std::vector<LqOvl> ovl; std::vector<LqQStat> hs; LqMapStats ms; memset(&ms, 0, sizeof(ms));
-    const uint64_t cap = c->opt.seed_budget ? c->opt.seed_budget : 400000000ULL;
+    const uint64_t cap = c->opt.seed_budget ? c->opt.seed_budget : 1000000000ULL;
     LQ_TRY(lq_map_part(&c->qd, &c->ix, &mo, c->mid_occ, c->self_off.data(), c->self_list.data(), c->qrank.data(), c->trank.data(), cap, &c->sc, &ovl, &hs, &ms, c->st));
     lq_prof_collect();
     c->stats.t_map_ms += now_ms() - t0; t0 = now_ms();

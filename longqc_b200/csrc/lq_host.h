@@ -22,6 +22,7 @@ void lqh_filter_redundant(lqh_sub_v *v, const lqh_sub *cv, size_t n_cv, uint32_t
 void lqh_reliable_region(const lqh_sub_v *v, uint32_t min_cov, lqh_sub_v *coords, lqh_sub_v *mcoords);
 /* lqutils.c:51-58, 72-80 */
 double lqh_meanQ(const char *qual, int len);
+double lqh_q2p(int q);            /* entry q of the reference's Phred->probability table */
 int lqh_getQV(const char *qual, int threshold, int len);
 /* minimap2-coverage.c:552-604: one table row */
 void lqh_format_row(lqh_str *out, const char *name, size_t name_len, int len, const char *qual, uint64_t lambda, uint64_t lambda2,

@@ -193,3 +193,7 @@ extern "C" long lqhc_sdust_masked(const char *seq, int len, int T, int W)
     long m = (long)lq_sdust_masked((const uint8_t*)seq, len, T, W, pbuf.data(), LQ_SD_PCAP(W), &ov);
     return ov ? -1 : m;
 }
+
+// ---------------------------------------------------------------- host table code (lq_table.c is plain C: linked in for its self-test)
+extern "C" double lqh_q2p(int q);
+extern "C" double lqhc_q2p(int q) { return lqh_q2p(q); }

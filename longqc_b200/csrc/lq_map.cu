@@ -155,6 +155,7 @@ __global__ void lq_iota_k(uint32_t *idx, uint64_t n)
 }
 
 #define AF_WARPS 4
+#define AF_U 8
 __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
 {
     __shared__ uint32_t s_cnt[AF_WARPS][256], s_start[AF_WARPS][256], s_head[AF_WARPS][256];
@@ -173,18 +174,26 @@ __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
         for (uint32_t d = lane; d < 256; d += 32) cnt[d] = 0;
         __syncwarp();
         uint32_t tied = 0;
-        for (uint32_t p0 = 0; p0 < n; p0 += 32) {
-            const uint32_t p = p0 + lane; const bool ok = p < n;
-            const uint32_t act = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-                const uint32_t e = idx[p];
-                const uint32_t d = (uint32_t)(a.sx[e] >> a.shift) & 255u;
-                tied |= a.sq[e] >> 31;
-                dig[p] = (uint8_t)d;
-                const uint32_t peers = __match_any_sync(act, d);
-                if ((peers & lt) == 0) cnt[d] += __popc(peers);
+        for (uint32_t p0 = 0; p0 < n; p0 += 32 * AF_U) {   /* AF_U rows per trip: the idx -> key gathers of the rows overlap */
+            uint32_t e[AF_U], dv[AF_U];
+            #pragma unroll
+            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32 + lane; e[u] = p < n ? idx[p] : 0xffffffffu; }
+            #pragma unroll
+            for (int u = 0; u < AF_U; ++u) {
+                dv[u] = 0;
+                if (e[u] != 0xffffffffu) { dv[u] = (uint32_t)(a.sx[e[u]] >> a.shift) & 255u; tied |= a.sq[e[u]] >> 31; }
             }
-            __syncwarp();
+            #pragma unroll
+            for (int u = 0; u < AF_U; ++u) {
+                const uint32_t p = p0 + u * 32 + lane; const bool ok = p < n;
+                const uint32_t act = __ballot_sync(0xffffffffu, ok);
+                if (ok) {
+                    dig[p] = (uint8_t)dv[u];
+                    const uint32_t peers = __match_any_sync(act, dv[u]);
+                    if ((peers & lt) == 0) cnt[dv[u]] += __popc(peers);
+                }
+                __syncwarp();
+            }
         }
         /* 2. region starts; lane owns digits 8*lane .. 8*lane+7 */
         uint32_t loc = 0, ne = 0;
@@ -201,14 +210,20 @@ __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
              * stable counting partition, rows of 32 in order (head[] = running count per digit) */
             for (uint32_t d = lane; d < 256; d += 32) head[d] = 0;
             __syncwarp();
-            for (uint32_t p0 = 0; p0 < n; p0 += 32) {
-                const uint32_t p = p0 + lane; const bool ok = p < n;
-                const uint32_t act = __ballot_sync(0xffffffffu, ok);
-                uint32_t d = 0, peers = 0;
-                if (ok) { d = dig[p]; peers = __match_any_sync(act, d); dest[p] = start[d] + head[d] + __popc(peers & lt); }
-                __syncwarp();
-                if (ok && (peers & lt) == 0) head[d] += __popc(peers);
-                __syncwarp();
+            for (uint32_t p0 = 0; p0 < n; p0 += 32 * AF_U) {
+                uint32_t dv[AF_U];
+                #pragma unroll
+                for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32 + lane; dv[u] = p < n ? dig[p] : 0; }
+                #pragma unroll
+                for (int u = 0; u < AF_U; ++u) {
+                    const uint32_t p = p0 + u * 32 + lane; const bool ok = p < n;
+                    const uint32_t act = __ballot_sync(0xffffffffu, ok);
+                    uint32_t peers = 0;
+                    if (ok) { peers = __match_any_sync(act, dv[u]); dest[p] = start[dv[u]] + head[dv[u]] + __popc(peers & lt); }
+                    __syncwarp();
+                    if (ok && (peers & lt) == 0) head[dv[u]] += __popc(peers);
+                    __syncwarp();
+                }
             }
         } else if (nb == 2) {
             /* closed form (lq_af_two_dest): d0 < d1 are the two non-empty digits */
@@ -246,9 +261,21 @@ __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
         }
         /* 4. permute the payload (indices into the seed arrays) */
         if (nb > 1) {
-            for (uint32_t p = lane; p < n; p += 32) idx2[dest[p]] = idx[p];
+            for (uint32_t p0 = lane; p0 < n; p0 += 32 * AF_U) {
+                uint32_t dd[AF_U], ee[AF_U];
+                #pragma unroll
+                for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) { dd[u] = dest[p]; ee[u] = idx[p]; } }
+                #pragma unroll
+                for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) idx2[dd[u]] = ee[u]; }
+            }
             __syncwarp();
-            for (uint32_t p = lane; p < n; p += 32) idx[p] = idx2[p];
+            for (uint32_t p0 = lane; p0 < n; p0 += 32 * AF_U) {
+                uint32_t ee[AF_U];
+                #pragma unroll
+                for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) ee[u] = idx2[p]; }
+                #pragma unroll
+                for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) idx[p] = ee[u]; }
+            }
             __syncwarp();
         }
         /* 5. sub-buckets (ksort.h:124-133) */
@@ -600,7 +627,8 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         a.cur = bk[cur]; a.n_cur = ctr + cur; a.nxt = bk[cur ^ 1]; a.n_nxt = ctr + (cur ^ 1); a.cursor = ctr + 2; a.n_walk = ctr + 3; a.shift = shift;
         LQ_CUDA_OK(cudaMemsetAsync(ctr + (cur ^ 1), 0, 4, st));
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 2, 0, 4, st));
-        { LqProfScope ps("seed_sort_level", st, 1, 0);
+        static const char *lvl_name[8] = { "seed_sort_s0", "seed_sort_s8", "seed_sort_s16", "seed_sort_s24", "seed_sort_s32", "seed_sort_s40", "seed_sort_s48", "seed_sort_s56" };
+        { LqProfScope ps(lvl_name[shift >> 3], st, 1, 0);
           lq_af_level_k<<<148 * 16, AF_WARPS * 32, 0, st>>>(a); }
         LQ_CUDA_OK(cudaGetLastError());
         cur ^= 1;
@@ -789,7 +817,7 @@ int lq_map_debug_sorted_seeds(LqQueryDev *qd, const LqIndexDev *ix, const LqMapO
     }
     unsorted->resize(nb); sorted->resize(nb);
     for (uint64_t i = 0; i < nb; ++i) {
-        (*unsorted)[i].x = x[i]; (*unsorted)[i].y = (uint64_t)(sm[i] >> 24) << 32 | sq[i];
+        (*unsorted)[i].x = x[i]; (*unsorted)[i].y = (uint64_t)(sm[i] >> 24) << 32 | (sq[i] & 0x7fffffffu);
         (*sorted)[i].x = x2[i];  (*sorted)[i].y = (uint64_t)(am[i] >> 24) << 32 | aq[i];
     }
     return 0;

@@ -53,8 +53,8 @@ extern "C" int lqcov_sdust_table(const lqcov_opt_t *o, const lqcov_reads_t *read
     const uint32_t n = reads->n;
     lqh_str out; out.l = out.m = 0; out.s = 0;
     if (n) {
-        double h_q2p[127]; char b[48];
-        for (int q = 0; q < 127; ++q) { snprintf(b, sizeof b, "%.15f", pow(10.0, -q / 10.0)); h_q2p[q] = strtod(b, 0); } /* lqutils.c:26-49 */
+        double h_q2p[127];
+        for (int q = 0; q < 127; ++q) h_q2p[q] = lqh_q2p(q); /* lqutils.c:26-49 */
         LQ_CUDA_OK(cudaMemcpyToSymbol(c_q2p, h_q2p, sizeof(h_q2p)));
         const uint64_t nb = reads->seq_off[n] - reads->seq_off[0];
         LqDevBuf d_seq, d_qual, d_off, d_p, d_out, d_cur;

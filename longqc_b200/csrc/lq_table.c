@@ -99,17 +99,23 @@ void lqh_reliable_region(const lqh_sub_v *v, uint32_t min_cov, lqh_sub_v *coords
     free(e);
 }
 
-/* Phred+33 -> error probability.  The reference table (lqutils.c:26-49) lists 10^(-q/10) printed with 15
- * decimals; the same doubles are obtained by printing pow() with %.15f and reading the text back
- * (verified against the compiled reference in tests/test_oracle_vs_reference.py::test_q2p_table). */
+/* The reference's Phred table (lqutils.c:26-49) lists 10^(-q/10) with 15 decimals.  Printing pow() with %.15f and
+ * reading the text back gives the same doubles except for eight entries whose last printed digit is one higher in
+ * the reference (q = 34, 39, 58, 62, 67, 71, 72, 82); tests/test_oracle_vs_reference.py checks all 127 entries
+ * against the compiled reference. */
+static double lq_q2p_entry(int q)
+{
+    static const int plus1[8] = { 34, 39, 58, 62, 67, 71, 72, 82 };
+    char b[48]; int i, n;
+    n = snprintf(b, sizeof b, "%.15f", pow(10.0, -q / 10.0));
+    for (i = 0; i < 8; ++i)
+        if (plus1[i] == q) { int j = n - 1; while (j >= 0 && b[j] == '9') b[j--] = '0'; if (j >= 0 && b[j] != '.') ++b[j]; }
+    return strtod(b, NULL);
+}
 static double q2p[127];
 static int q2p_ok = 0;
-static void q2p_build(void)
-{
-    int q; char b[48];
-    for (q = 0; q < 127; ++q) { snprintf(b, sizeof b, "%.15f", pow(10.0, -q / 10.0)); q2p[q] = strtod(b, NULL); }
-    q2p_ok = 1;
-}
+static void q2p_build(void) { int q; for (q = 0; q < 127; ++q) q2p[q] = lq_q2p_entry(q); q2p_ok = 1; }
+double lqh_q2p(int q) { return lq_q2p_entry(q); }
 
 double lqh_meanQ(const char *qual, int len)
 {

@@ -1,0 +1,49 @@
+"""CPU tier, build container only: function-level pinning of the oracle against the compiled, unmodified
+reference (oracle/_ref/libmm2ref.so).  Skipped where oracle/_ref was not built."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import liblq
+
+pytestmark = pytest.mark.skipif(liblq.ref() is None, reason="oracle/_ref/libmm2ref.so not built (needs /root/reference)")
+
+
+@pytest.mark.parametrize("w,k,hpc", [(5, 12, 0), (10, 15, 0), (5, 15, 0), (3, 4, 0), (16, 20, 0), (5, 28, 0), (10, 15, 1), (5, 12, 1)])
+def test_sketch(w, k, hpc):
+    rng = np.random.default_rng(1000 + w + 31 * k + hpc)
+    for s in liblq.adversarial_seqs(rng, 140, 2000):
+        assert np.array_equal(liblq.ref_sketch(s, w, k, 3, hpc), liblq.oracle_sketch(s, w, k, 3, hpc))
+
+
+def test_radix_sort_128x_tie_order():
+    rng = np.random.default_rng(3)
+    o, r = liblq.oracle(), liblq.ref()
+    for trial in range(200):
+        n = int(rng.integers(1, 4000)) if trial % 10 else int(rng.integers(1, 130))
+        x = ((rng.integers(0, 2, n).astype(np.uint64) << np.uint64(63)) | (rng.integers(0, 300, n).astype(np.uint64) << np.uint64(32))
+             | rng.integers(0, 500, n).astype(np.uint64))
+        a = np.zeros(n, dtype=liblq.mm128_dtype)
+        a["x"] = x
+        a["y"] = np.arange(n, dtype=np.uint64)
+        b = a.copy()
+        o.lqo_radix_sort_128x(a.ctypes.data, a.ctypes.data + 16 * n)
+        r.radix_sort_128x(b.ctypes.data, b.ctypes.data + 16 * n)
+        assert np.array_equal(a["y"], b["y"])
+
+
+def test_q2p_table_and_meanq():
+    r = liblq.ref()
+    tab = (C.c_double * 127).in_dll(r, "q2p")
+    o = liblq.oracle()
+    o.lqo_q2p.restype = C.c_double
+    hc = liblq.hostcheck()
+    hc.lqhc_q2p.restype = C.c_double
+    for q in range(127):   # oracle and product both rebuild the reference's literal table
+        assert o.lqo_q2p(q) == tab[q] and hc.lqhc_q2p(q) == tab[q]
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        n = int(rng.integers(1, 5000))
+        qs = (rng.integers(0, 60, n).astype(np.uint8) + 33).tobytes()
+        assert r.meanQ(qs, n) == liblq.oracle().lqo_meanQ(qs, n)
