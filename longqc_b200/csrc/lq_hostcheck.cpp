@@ -40,6 +40,17 @@ int lqhc_sketch_parallel(const char *seq, int len, int w, int k, uint32_t rid, l
     return n;
 }
 
+// the windowed fast path (closed form around palindromes / ambiguous bases) at every position
+int lqhc_sketch_parallel_win(const char *seq, int len, int w, int k, uint32_t rid, lq_mm128 *out, int cap)
+{
+    std::vector<uint32_t> b2, nm; std::vector<lq_mm128> v; VecSink s; s.v = &v;
+    pack_read(seq, len, 0, b2, nm);
+    for (int i = 0; i < len; ++i) lq_sketch_at_win(b2.data(), nm.data(), 0, len, w, k, rid, i, s);
+    int n = (int)v.size();
+    for (int i = 0; i < n && i < cap; ++i) out[i] = v[i];
+    return n;
+}
+
 // the restartable state machine run from the start of the read (HPC allowed)
 int lqhc_sketch_replay(const char *seq, int len, int w, int k, uint32_t rid, int is_hpc, lq_mm128 *out, int cap)
 {

@@ -25,7 +25,6 @@
 #define SK_HALO 128                            /* candidates kept before the tile */
 #define SK_HALO_W 256                          /* packed words kept before the tile */
 #define SK_NPOS (SK_TILE + SK_HALO)
-#define SK_BUF 8                               /* records a thread buffers between count and write */
 
 /* ------------------------------------------------------------------ K0: pack */
 
@@ -59,10 +58,6 @@ __global__ void lq_pack_k(const uint8_t *__restrict__ seq, const uint64_t *__res
 /* ------------------------------------------------------------------ K1: sketch */
 
 struct SkCount { int n; __device__ __forceinline__ void operator()(uint64_t, uint64_t) { ++n; } };
-struct SkBuf {
-    uint64_t x[SK_BUF], y[SK_BUF]; int n;
-    __device__ __forceinline__ void operator()(uint64_t x_, uint64_t y_) { if (n < SK_BUF) { x[n] = x_; y[n] = y_; } ++n; }
-};
 struct SkWrite {
     uint32_t *key; uint64_t *yy; uint64_t at;
     __device__ __forceinline__ void operator()(uint64_t x_, uint64_t y_) { key[at] = (uint32_t)(x_ >> 8); yy[at] = y_; ++at; }
@@ -74,14 +69,32 @@ struct SkArgs {
     uint64_t n_slots;
     int w, k;
     uint32_t rid_base;
-    uint32_t *blk_count;        /* count pass: records per CTA */
-    const uint64_t *blk_base;   /* write pass: exclusive prefix of blk_count */
+    /* single-pass ordering of the output (decoupled look-back over the tiles) */
+    uint32_t *ticket;            /* dynamic tile id: tiles are numbered in the order their CTAs start */
+    unsigned long long *state;   /* per tile: flag<<62 | count; flag 1 = tile total, 2 = inclusive prefix */
+    uint64_t cap;                /* capacity of out_key / out_y in records */
+    uint32_t *err;               /* bit 0: look-back timed out */
     uint32_t *out_key; uint64_t *out_y;
 };
 
-template <class Sink>
-__device__ __forceinline__ void sk_eval(const SkArgs &a, const uint32_t *s_b2, const uint32_t *cand, const uint32_t *okb, const uint32_t *zb,
-                                        int idx /* index into cand[] */, uint64_t g, Sink &sink)
+/* candidate of smem position p (hash of min(fw,rv), strand) */
+struct SkFetch {
+    const uint32_t *cand, *zb; int idx;
+    __device__ __forceinline__ void operator()(int d, uint32_t *h, uint32_t *z) const { const int p = idx - d; *h = cand[p]; *z = (zb[p >> 5] >> (p & 31)) & 1u; }
+};
+
+__device__ __forceinline__ uint64_t sk_bits64(const uint32_t *w, int lo) /* bits lo..lo+63 of a bit array (lo >= 0) */
+{
+    const uint32_t wi = (uint32_t)lo >> 5, sh = (uint32_t)lo & 31;
+    uint64_t v = ((uint64_t)w[wi] | (uint64_t)w[wi + 1] << 32) >> sh;
+    if (sh) v |= (uint64_t)w[wi + 2] << (64 - sh);
+    return v;
+}
+
+/* what the reference pushes while processing base g (tile-relative candidate index idx) */
+template <int WT, class Sink>
+__device__ __forceinline__ void sk_eval(const SkArgs &a, const uint32_t *cand, const uint32_t *okb, const uint32_t *zb, const uint32_t *s_nm,
+                                        int idx, uint64_t g, int64_t W0, Sink &sink)
 {
     const uint64_t slot = g >> 7;
     if (slot >= a.n_slots) return;
@@ -90,33 +103,32 @@ __device__ __forceinline__ void sk_eval(const SkArgs &a, const uint32_t *s_b2, c
     const int L = (int)a.len[rd];
     const int i = (int)((slot - s0) * LQ_SLOT + (g & 127));
     if (i >= L) return;
-    const int need = a.w + a.k - 1;
-    bool fast = i >= need;
-    if (fast) {
-        /* ok bits of idx-need..idx, all must be set; need+1 <= 60 */
-        const int lo = idx - need;
-        const uint32_t wi = (uint32_t)lo >> 5, sh = (uint32_t)lo & 31;
-        uint64_t bits = ((uint64_t)okb[wi] | (uint64_t)okb[wi + 1] << 32) >> sh;
-        if (sh) bits |= (uint64_t)okb[wi + 2] << (64 - sh);
-        const uint64_t want = (need + 1 >= 64) ? ~0ULL : ((1ULL << (need + 1)) - 1);
-        fast = (bits & want) == want;
-    }
-    if (fast) {
-        uint64_t cx[LQ_MAX_W + 1]; uint32_t cz[LQ_MAX_W + 1];
-        const int w = a.w;
-        #pragma unroll 1
-        for (int j = 0; j <= w; ++j) {
-            const int p = idx - w + j;
-            cx[j] = (uint64_t)cand[p] << 8 | (uint64_t)a.k;
-            cz[j] = (zb[p >> 5] >> (p & 31)) & 1u;
-        }
-        lq_sketch_fast_at(cx, w, a.rid_base + rd, i, cz, i == L - 1, sink);
-    } else {
+    uint64_t okw = sk_bits64(okb, idx - 63);
+    uint64_t ambw = sk_bits64(s_nm, (int)((int64_t)g - W0) - 63);
+    if (i < 63) { const uint64_t keep = ~0ULL << (63 - i); okw &= keep; ambw &= keep; }   /* nothing before the read start */
+    SkFetch f; f.cand = cand; f.zb = zb; f.idx = idx;
+    if (!lq_sketch_fast_win<WT>(okw, ambw, a.w, a.k, a.rid_base + rd, i, i == L - 1, f, sink))
         lq_sketch_slow_at(a.b2, a.nm, s0 * LQ_SLOT, L, a.w, a.k, a.rid_base + rd, i, sink);
-    }
 }
 
-template <int WRITE>
+/* 32-bit k-mer / hash math for k <= 16 (the common case: LongQC uses 12 and 15) */
+__device__ __forceinline__ int sk_cand32(const uint32_t *b2, uint64_t g, int k, uint32_t *hash, uint32_t *strand)
+{
+    const uint64_t first = g - (uint64_t)(k - 1);
+    const uint32_t wi = (uint32_t)(first >> 4), sh = (uint32_t)(first & 15) * 2;
+    const uint32_t mask = k == 16 ? 0xffffffffu : ((1u << 2 * k) - 1);
+    const uint32_t le = __funnelshift_r(b2[wi], b2[wi + 1], sh) & mask;     /* oldest base in the low bits */
+    const uint32_t rv = ~le & mask;                                         /* sketch.c:106 */
+    uint32_t v = __brev(le);                                                /* reverse the 2-bit groups: bit reversal, then swap within pairs */
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    const uint32_t fw = v >> (32 - 2 * k);                                  /* sketch.c:105 */
+    if (fw == rv) return 0;
+    *strand = fw < rv ? 0u : 1u;
+    *hash = lq_hash32(fw < rv ? fw : rv, mask);
+    return 1;
+}
+
+template <int WT>
 __global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
 {
     __shared__ uint32_t s_b2[(SK_TILE + SK_HALO_W) / 16 + 4];
@@ -124,9 +136,14 @@ __global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
     __shared__ uint32_t cand[SK_NPOS];
     __shared__ uint32_t okb[SK_NPOS / 32 + 2], zb[SK_NPOS / 32 + 2];
     __shared__ uint64_t scan_sm[33];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_base;
 
     const int tid = threadIdx.x;
-    const int64_t T0 = (int64_t)blockIdx.x * SK_TILE;   /* first base of the tile (global base index) */
+    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t T0 = (int64_t)tile * SK_TILE;          /* first base of the tile (global base index) */
     const int64_t W0 = T0 - SK_HALO_W;                    /* first base held in shared memory */
     const int64_t n_bases = (int64_t)a.n_slots * LQ_SLOT;
 
@@ -155,9 +172,7 @@ __global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
             const uint64_t sg = (uint64_t)(g - W0);          /* index relative to the shared copies */
             if (i < L && !lq_amb_at(s_nm, sg)) {
                 if (i >= a.k - 1 && !lq_amb_any(s_nm, sg - (uint64_t)(a.k - 1), sg)) {
-                    uint64_t h = 0;
-                    ok = (uint32_t)lq_cand_clean(s_b2, sg, a.k, &h, &z);
-                    h32 = (uint32_t)h;
+                    ok = (uint32_t)sk_cand32(s_b2, sg, a.k, &h32, &z);
                 } else { /* k-mer registers carry bits from before an ambiguous base / the read start */
                     uint64_t fw, rv;
                     lq_regs_at(a.b2, a.nm, s0 * LQ_SLOT, i, a.k, &fw, &rv);
@@ -171,41 +186,52 @@ __global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
     }
     __syncthreads();
 
-    /* stage B: rows r = 0..3, base = T0 + r*256 + tid */
-    if (!WRITE) {
+    /* stage B, pass 1: record counts; rows r = 0..3, base = T0 + r*256 + tid */
+    int cnt[SK_PER_THREAD];
+    #pragma unroll
+    for (int r = 0; r < SK_PER_THREAD; ++r) {
         SkCount c; c.n = 0;
-        #pragma unroll 1
-        for (int r = 0; r < SK_PER_THREAD; ++r)
-            sk_eval(a, s_b2, cand, okb, zb, SK_HALO + r * SK_THREADS + tid, (uint64_t)(T0 + r * SK_THREADS + tid), c);
-        uint64_t tot, v = (uint64_t)c.n;
-        lq_block_excl_scan(v, scan_sm, &tot);
-        if (tid == 0) a.blk_count[blockIdx.x] = (uint32_t)tot;
-    } else {
-        SkBuf b; b.n = 0;
-        int cnt[SK_PER_THREAD];
-        #pragma unroll 1
-        for (int r = 0; r < SK_PER_THREAD; ++r) {
-            const int before = b.n;
-            sk_eval(a, s_b2, cand, okb, zb, SK_HALO + r * SK_THREADS + tid, (uint64_t)(T0 + r * SK_THREADS + tid), b);
-            cnt[r] = b.n - before;
-        }
-        /* one block scan for the four rows: 16 bits per row (<= 256*(2w+2) < 65536 records per row) */
-        uint64_t packed = (uint64_t)cnt[0] | (uint64_t)cnt[1] << 16 | (uint64_t)cnt[2] << 32 | (uint64_t)cnt[3] << 48, tot;
-        const uint64_t ex = lq_block_excl_scan(packed, scan_sm, &tot);
-        uint64_t base = a.blk_base[blockIdx.x];
-        SkWrite wr; wr.key = a.out_key; wr.yy = a.out_y;
-        int used = 0;
-        #pragma unroll 1
-        for (int r = 0; r < SK_PER_THREAD; ++r) {
-            wr.at = base + ((ex >> (16 * r)) & 0xffff);
-            if (b.n <= SK_BUF) {
-                for (int j = 0; j < cnt[r]; ++j) wr(b.x[used + j], b.y[used + j]);
-                used += cnt[r];
-            } else { /* buffer overflowed (low-complexity sequence): evaluate again, writing directly */
-                sk_eval(a, s_b2, cand, okb, zb, SK_HALO + r * SK_THREADS + tid, (uint64_t)(T0 + r * SK_THREADS + tid), wr);
+        sk_eval<WT>(a, cand, okb, zb, s_nm, SK_HALO + r * SK_THREADS + tid, (uint64_t)(T0 + r * SK_THREADS + tid), W0, c);
+        cnt[r] = c.n;
+    }
+    /* one block scan for the four rows: 16 bits per row (<= 256*(2w+2) < 65536 records per row) */
+    const uint64_t packed = (uint64_t)cnt[0] | (uint64_t)cnt[1] << 16 | (uint64_t)cnt[2] << 32 | (uint64_t)cnt[3] << 48;
+    uint64_t tot;
+    const uint64_t ex = lq_block_excl_scan(packed, scan_sm, &tot);
+    const uint64_t tile_total = (tot & 0xffff) + ((tot >> 16) & 0xffff) + ((tot >> 32) & 0xffff) + (tot >> 48);
+
+    /* decoupled look-back: exclusive prefix of the tile totals, tiles in ticket order */
+    if (tid == 0) {
+        const unsigned long long FLAG_AGG = 1ULL << 62, FLAG_PRE = 2ULL << 62, VMASK = (1ULL << 62) - 1;
+        uint64_t base = 0;
+        if (tile == 0) atomicExch(&a.state[0], FLAG_PRE | tile_total);
+        else {
+            atomicExch(&a.state[tile], FLAG_AGG | tile_total);
+            int64_t j = (int64_t)tile - 1; uint32_t spins = 0;
+            for (;;) {
+                const unsigned long long s = *(volatile unsigned long long*)&a.state[j];
+                if ((s >> 62) == 0) { if (++spins > (1u << 27)) { atomicOr(a.err, 1u); break; } continue; }
+                base += s & VMASK;
+                if ((s >> 62) == 2) break;
+                --j;
             }
-            base += (tot >> (16 * r)) & 0xffff;
+            atomicExch(&a.state[tile], FLAG_PRE | (base + tile_total));
         }
+        s_base = base;
+    }
+    __syncthreads();
+    uint64_t base = s_base;
+    if (base + tile_total > a.cap) return;     /* output buffer too small: the host re-runs with the exact size */
+
+    /* stage B, pass 2: evaluate again, writing in base order */
+    SkWrite wr; wr.key = a.out_key; wr.yy = a.out_y;
+    #pragma unroll
+    for (int r = 0; r < SK_PER_THREAD; ++r) {
+        if (cnt[r]) {
+            wr.at = base + ((ex >> (16 * r)) & 0xffff);
+            sk_eval<WT>(a, cand, okb, zb, s_nm, SK_HALO + r * SK_THREADS + tid, (uint64_t)(T0 + r * SK_THREADS + tid), W0, wr);
+        }
+        base += (tot >> (16 * r)) & 0xffff;
     }
 }
 
@@ -299,26 +325,39 @@ int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_b
     SkArgs a;
     a.b2 = rd->b2.as<uint32_t>(); a.nm = rd->nm.as<uint32_t>(); a.slot_read = rd->slot_read.as<uint32_t>(); a.len = rd->len.as<uint32_t>();
     a.slot0 = rd->slot0.as<uint64_t>(); a.n_slots = rd->n_slots; a.w = w; a.k = k; a.rid_base = rid_base;
-    a.blk_count = 0; a.blk_base = 0; a.out_key = 0; a.out_y = 0;
+    a.ticket = 0; a.state = 0; a.cap = 0; a.err = 0; a.out_key = 0; a.out_y = 0;
     uint64_t total = 0;
     if (!is_hpc) {
         const unsigned nblk = (unsigned)((rd->n_slots * LQ_SLOT + SK_TILE - 1) / SK_TILE);
-        LQ_TRY(out->blk.ensure((size_t)(nblk + 1) * 4 + (size_t)(nblk + 2) * 8));
-        uint32_t *cnt = out->blk.as<uint32_t>();
-        uint64_t *base = (uint64_t*)((char*)out->blk.p + (((size_t)(nblk + 1) * 4 + 7) & ~(size_t)7));
-        a.blk_count = cnt;
-        { LqProfScope ps("sketch_count", st, 1, rd->n_slots * (LQ_SLOT_W2 + LQ_SLOT_WN) * 4);
-          lq_sketch_k<0><<<nblk, SK_THREADS, 0, st>>>(a); }
-        LQ_CUDA_OK(cudaGetLastError());
-        LQ_TRY((lq_exclusive_scan<uint32_t, uint64_t>(cnt, base, nblk, 1, ws, st)));
-        LQ_CUDA_OK(cudaMemcpyAsync(&total, base + nblk, 8, cudaMemcpyDeviceToHost, st)); lq_prof_d2h(8);
-        LQ_CUDA_OK(cudaStreamSynchronize(st));
-        LQ_TRY(out->key.ensure((size_t)(total + 1) * 4));
-        LQ_TRY(out->y.ensure((size_t)(total + 1) * 8));
-        a.blk_base = base; a.out_key = out->key.as<uint32_t>(); a.out_y = out->y.as<uint64_t>();
-        { LqProfScope ps("sketch_write", st, 1, rd->n_slots * (LQ_SLOT_W2 + LQ_SLOT_WN) * 4 + total * 12);
-          lq_sketch_k<1><<<nblk, SK_THREADS, 0, st>>>(a); }
-        LQ_CUDA_OK(cudaGetLastError());
+        LQ_TRY(out->blk.ensure((size_t)(nblk + 2) * 8 + 64));
+        unsigned long long *state = out->blk.as<unsigned long long>();
+        uint32_t *ticket = (uint32_t*)(state + nblk + 1), *err = ticket + 1;
+        /* expected density 2/(w+1) records per base; the exact total is known after the pass, which is repeated only
+         * if the guess was too small (low-complexity input) */
+        uint64_t cap = (uint64_t)((double)rd->n_bases * 2.6 / (w + 1)) + 4096;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            LQ_TRY(out->key.ensure((size_t)(cap + 1) * 4));
+            LQ_TRY(out->y.ensure((size_t)(cap + 1) * 8));
+            LQ_CUDA_OK(cudaMemsetAsync(state, 0, (size_t)(nblk + 2) * 8 + 16, st));
+            a.ticket = ticket; a.state = state; a.cap = cap; a.err = err;
+            a.out_key = out->key.as<uint32_t>(); a.out_y = out->y.as<uint64_t>();
+            {
+                LqProfScope ps("sketch", st, 1, rd->n_slots * (LQ_SLOT_W2 + LQ_SLOT_WN) * 4 + (uint64_t)((double)rd->n_bases * 2.0 / (w + 1)) * 12);
+                if (w <= 5) lq_sketch_k<5><<<nblk, SK_THREADS, 0, st>>>(a);
+                else if (w <= 10) lq_sketch_k<10><<<nblk, SK_THREADS, 0, st>>>(a);
+                else lq_sketch_k<LQ_MAX_W><<<nblk, SK_THREADS, 0, st>>>(a);
+            }
+            LQ_CUDA_OK(cudaGetLastError());
+            unsigned long long last = 0; uint32_t h_err = 0;
+            LQ_CUDA_OK(cudaMemcpyAsync(&last, state + (nblk - 1), 8, cudaMemcpyDeviceToHost, st));
+            LQ_CUDA_OK(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, st)); lq_prof_d2h(12);
+            LQ_CUDA_OK(cudaStreamSynchronize(st));
+            if (h_err) { fprintf(stderr, "[lqcov] sketch: look-back timed out\n"); return -1; }
+            total = last & ((1ULL << 62) - 1);
+            if (total <= cap) break;
+            if (attempt == 1) { fprintf(stderr, "[lqcov] sketch: output overflow after resize\n"); return -1; }
+            cap = total;
+        }
     } else {
         const uint32_t n = rd->n_reads;
         LQ_TRY(out->blk.ensure((size_t)(n + 1) * 4 + (size_t)(n + 2) * 8));

@@ -289,6 +289,89 @@ LQ_HD void lq_sketch_at(const uint32_t *b2, const uint32_t *nm, uint64_t g0, int
     } else lq_sketch_slow_at(b2, nm, g0, len, w, k, rid, i, sink);
 }
 
+/* ---- windowed fast path: palindromic k-mers and ambiguous bases inside the look-back are handled in closed form ----
+ *
+ * okw / ambw describe the 64 bases ending at base i of the read: bit 63-d is set iff base i-d pushes a candidate
+ * (unambiguous and not palindromic) / is ambiguous; bits of bases before the read start are 0.
+ * Let l' = number of pushes after the last ambiguous base of the window (the read start counts as one).  The true run
+ * counter at i is >= l'.  If base i pushes and l' >= w+k then every gate of sketch.c:116-137 is open, the last w+1 ring
+ * pushes are exactly the last w+1 set bits of okw (all made with run >= k, i.e. valid, and none of them a MAX push of an
+ * ambiguous base), and the running minimum is the rightmost minimum of the w older ones: the closed form applies with
+ * NON-contiguous candidates.  Returns 0 when the bounded replay is needed instead (first w+k pushes of a run; the
+ * end-of-read record of a read whose last base does not push). */
+#ifdef __CUDA_ARCH__
+#define LQ_CLZ64(x) __clzll((long long)(x))
+#define LQ_POPC64(x) __popcll(x)
+#else
+#define LQ_CLZ64(x) __builtin_clzll(x)
+#define LQ_POPC64(x) __builtin_popcountll(x)
+#endif
+
+template <int WT, class Fetch, class Sink>
+LQ_HD int lq_sketch_fast_win(uint64_t okw, uint64_t ambw, int w, int k, uint32_t rid, int i, int last, Fetch &fetch, Sink &sink)
+{
+    if (!(okw >> 63)) return last ? 0 : 1;           /* base i pushes nothing valid and emits nothing (sketch.c:107 / :114 with l = 0) */
+    uint64_t m = okw;
+    if (ambw) { const int hb = 63 - LQ_CLZ64(ambw); m &= ~((2ULL << hb) - 1ULL); }  /* pushes after the last ambiguous base */
+    if (LQ_POPC64(m) < w + k) return 0;
+    /* the w+1 most recent pushes, newest first while scanning, stored oldest first */
+    uint32_t cx[WT + 1], cz[WT + 1]; int cd[WT + 1];
+    #pragma unroll
+    for (int j = 0; j <= WT; ++j) {
+        if (j <= w) {
+            const int b = 63 - LQ_CLZ64(m);          /* highest set bit */
+            m &= ~(1ULL << b);
+            const int d = 63 - b;                    /* distance back from i */
+            uint32_t h, z; fetch(d, &h, &z);
+            cx[w - j] = h; cz[w - j] = z; cd[w - j] = d;
+        }
+    }
+    #define LQ_EMIT(j_) sink((uint64_t)cx[j_] << 8 | (uint64_t)k, (uint64_t)rid << 32 | (uint64_t)((uint32_t)(i - cd[j_]) << 1) | (uint64_t)cz[j_])
+    int mi = 0;
+    #pragma unroll
+    for (int j = 1; j < WT; ++j) if (j < w && cx[j] <= cx[mi]) mi = j;      /* rightmost minimum of the old window cx[0..w-1] */
+    if (cx[w] <= cx[mi]) {
+        #pragma unroll
+        for (int j = 0; j < WT; ++j) if (j == mi) LQ_EMIT(j);
+        if (last) LQ_EMIT(w);
+    } else if (mi == 0) {
+        int m2 = 1;
+        LQ_EMIT(0);
+        #pragma unroll
+        for (int j = 2; j <= WT; ++j) if (j <= w && cx[j] <= cx[m2]) m2 = j;
+        #pragma unroll
+        for (int j = 1; j <= WT; ++j) if (j <= w && j != m2 && cx[j] == cx[m2]) LQ_EMIT(j);
+        if (last) {
+            #pragma unroll
+            for (int j = 1; j <= WT; ++j) if (j == m2) LQ_EMIT(j);
+        }
+    } else if (last) {
+        #pragma unroll
+        for (int j = 1; j < WT; ++j) if (j == mi) LQ_EMIT(j);
+    }
+    #undef LQ_EMIT
+    return 1;
+}
+
+/* host/test form of the same rule: windows and candidates recomputed from the packed read */
+struct lq_fetch_packed {
+    const uint32_t *b2; uint64_t g; int k;
+    LQ_HD void operator()(int d, uint32_t *h, uint32_t *z) const { uint64_t hh = 0; lq_cand_clean(b2, g - (uint64_t)d, k, &hh, z); *h = (uint32_t)hh; }
+};
+
+template <class Sink>
+LQ_HD void lq_sketch_at_win(const uint32_t *b2, const uint32_t *nm, uint64_t g0, int len, int w, int k, uint32_t rid, int i, Sink &sink)
+{
+    uint64_t okw = 0, ambw = 0;
+    for (int d = 0; d < 64 && d <= i; ++d) {
+        if (lq_amb_at(nm, g0 + (uint64_t)(i - d))) ambw |= 1ULL << (63 - d);
+        else if (lq_pos_ok(b2, nm, g0, i - d, k)) okw |= 1ULL << (63 - d);
+    }
+    lq_fetch_packed f; f.b2 = b2; f.g = g0 + (uint64_t)i; f.k = k;
+    if (k <= 16 && w <= LQ_MAX_W && lq_sketch_fast_win<LQ_MAX_W>(okw, ambw, w, k, rid, i, i == len - 1, f, sink)) return;
+    lq_sketch_slow_at(b2, nm, g0, len, w, k, rid, i, sink);
+}
+
 /* ASCII -> reference base code (sketch.c:8-25; sdust.c:26-43 when sdust_tbl: U is not a base there) */
 LQ_HD uint32_t lq_nt4(uint32_t c, int sdust_tbl)
 {
