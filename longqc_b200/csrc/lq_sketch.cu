@@ -58,6 +58,14 @@ __global__ void lq_pack_k(const uint8_t *__restrict__ seq, const uint64_t *__res
 /* ------------------------------------------------------------------ K1: sketch */
 
 struct SkCount { int n; __device__ __forceinline__ void operator()(uint64_t, uint64_t) { ++n; } };
+/* counts, and keeps the first two records of a base in registers (more than two is rare: that base is evaluated again) */
+struct SkHold {
+    uint32_t k0, p0, k1, p1; int n;
+    __device__ __forceinline__ void operator()(uint64_t x_, uint64_t y_) {
+        if (n == 0) { k0 = (uint32_t)(x_ >> 8); p0 = (uint32_t)y_; } else if (n == 1) { k1 = (uint32_t)(x_ >> 8); p1 = (uint32_t)y_; }
+        ++n;
+    }
+};
 struct SkWrite {
     uint32_t *key; uint64_t *yy; uint64_t at;
     __device__ __forceinline__ void operator()(uint64_t x_, uint64_t y_) { key[at] = (uint32_t)(x_ >> 8); yy[at] = y_; ++at; }
@@ -91,24 +99,35 @@ __device__ __forceinline__ uint64_t sk_bits64(const uint32_t *w, int lo) /* bits
     return v;
 }
 
-/* what the reference pushes while processing base g (tile-relative candidate index idx) */
-template <int WT, class Sink>
-__device__ __forceinline__ void sk_eval(const SkArgs &a, const uint32_t *cand, const uint32_t *okb, const uint32_t *zb, const uint32_t *s_nm,
-                                        int idx, uint64_t g, int64_t W0, Sink &sink)
+/* the bounded replay, out of line: it is rare, and inlining it four times per thread costs registers on the common path */
+__device__ __noinline__ void sk_slow(const uint32_t *b2, const uint32_t *nm, uint64_t g0, int L, int w, int k, uint32_t rid, int i, lq_sk_buf *buf)
+{
+    buf->n = 0;
+    lq_sketch_slow_at(b2, nm, g0, L, w, k, rid, i, *buf);
+}
+
+/* what the reference pushes while processing base g (tile-relative candidate index idx); returns the read's rid */
+template <int WT, int WC, class Sink>
+__device__ __forceinline__ uint32_t sk_eval(const SkArgs &a, const uint32_t *cand, const uint32_t *okb, const uint32_t *zb, const uint32_t *s_nm,
+                                            int idx, uint64_t g, Sink &sink)
 {
     const uint64_t slot = g >> 7;
-    if (slot >= a.n_slots) return;
+    if (slot >= a.n_slots) return 0;
     const uint32_t rd = a.slot_read[slot];
     const uint64_t s0 = a.slot0[rd];
     const int L = (int)a.len[rd];
-    const int i = (int)((slot - s0) * LQ_SLOT + (g & 127));
-    if (i >= L) return;
+    const int i = (int)(slot - s0) * LQ_SLOT + (int)(g & 127);
+    if (i >= L) return 0;
     uint64_t okw = sk_bits64(okb, idx - 63);
-    uint64_t ambw = sk_bits64(s_nm, (int)((int64_t)g - W0) - 63);
+    uint64_t ambw = sk_bits64(s_nm, idx + (SK_HALO_W - SK_HALO) - 63);   /* s_nm is indexed from W0 = T0 - SK_HALO_W, cand/okb from T0 - SK_HALO */
     if (i < 63) { const uint64_t keep = ~0ULL << (63 - i); okw &= keep; ambw &= keep; }   /* nothing before the read start */
     SkFetch f; f.cand = cand; f.zb = zb; f.idx = idx;
-    if (!lq_sketch_fast_win<WT>(okw, ambw, a.w, a.k, a.rid_base + rd, i, i == L - 1, f, sink))
-        lq_sketch_slow_at(a.b2, a.nm, s0 * LQ_SLOT, L, a.w, a.k, a.rid_base + rd, i, sink);
+    if (!lq_sketch_fast_win<WT, WC>(okw, ambw, a.w, a.k, a.rid_base + rd, i, i == L - 1, f, sink)) {
+        lq_sk_buf buf;
+        sk_slow(a.b2, a.nm, s0 * LQ_SLOT, L, a.w, a.k, a.rid_base + rd, i, &buf);
+        for (int j = 0; j < buf.n; ++j) sink(buf.x[j], buf.y[j]);
+    }
+    return a.rid_base + rd;
 }
 
 /* 32-bit k-mer / hash math for k <= 16 (the common case: LongQC uses 12 and 15) */
@@ -128,7 +147,7 @@ __device__ __forceinline__ int sk_cand32(const uint32_t *b2, uint64_t g, int k, 
     return 1;
 }
 
-template <int WT>
+template <int WT, int WC>
 __global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
 {
     __shared__ uint32_t s_b2[(SK_TILE + SK_HALO_W) / 16 + 4];
@@ -159,7 +178,8 @@ __global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
     if (tid < 2) { okb[SK_NPOS / 32 + tid] = 0; zb[SK_NPOS / 32 + tid] = 0; }
     __syncthreads();
 
-    /* stage A: candidates for bases T0-128 .. T0+1023 (idx 0..1151); warps cover 32 consecutive idx */
+    /* stage A: candidates for bases T0-128 .. T0+1023 (idx 0..1151); a warp covers 32 consecutive idx = one quarter of a slot,
+     * so the owning read is looked up once per warp */
     for (int idx = tid; idx < SK_NPOS; idx += SK_THREADS) {
         const int64_t g = T0 - SK_HALO + idx;
         uint32_t ok = 0, z = 0, h32 = 0;
@@ -168,10 +188,13 @@ __global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
             const uint32_t rd = a.slot_read[slot];
             const uint64_t s0 = a.slot0[rd];
             const int L = (int)a.len[rd];
-            const int i = (int)((slot - s0) * LQ_SLOT + ((uint64_t)g & 127));
-            const uint64_t sg = (uint64_t)(g - W0);          /* index relative to the shared copies */
-            if (i < L && !lq_amb_at(s_nm, sg)) {
-                if (i >= a.k - 1 && !lq_amb_any(s_nm, sg - (uint64_t)(a.k - 1), sg)) {
+            const int i = (int)(slot - s0) * LQ_SLOT + (int)((uint32_t)g & 127);
+            const uint32_t sg = (uint32_t)(idx + (SK_HALO_W - SK_HALO));          /* index relative to the shared copies */
+            if (i < L && !((s_nm[sg >> 5] >> (sg & 31)) & 1u)) {
+                /* ambiguity bits of the k-1 bases before: bits sg-k+1 .. sg-1 */
+                const uint32_t lo = sg - (uint32_t)(a.k - 1);
+                const uint32_t wv = __funnelshift_r(s_nm[lo >> 5], s_nm[(lo >> 5) + 1], lo & 31) & ((1u << (a.k - 1)) - 1);
+                if (i >= a.k - 1 && wv == 0) {
                     ok = (uint32_t)sk_cand32(s_b2, sg, a.k, &h32, &z);
                 } else { /* k-mer registers carry bits from before an ambiguous base / the read start */
                     uint64_t fw, rv;
@@ -186,50 +209,62 @@ __global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
     }
     __syncthreads();
 
-    /* stage B, pass 1: record counts; rows r = 0..3, base = T0 + r*256 + tid */
-    int cnt[SK_PER_THREAD];
+    /* stage B: evaluate every base of the tile once; rows r = 0..3, base = T0 + r*256 + tid */
+    SkHold hold[SK_PER_THREAD]; uint32_t rid[SK_PER_THREAD];
     #pragma unroll
     for (int r = 0; r < SK_PER_THREAD; ++r) {
-        SkCount c; c.n = 0;
-        sk_eval<WT>(a, cand, okb, zb, s_nm, SK_HALO + r * SK_THREADS + tid, (uint64_t)(T0 + r * SK_THREADS + tid), W0, c);
-        cnt[r] = c.n;
+        hold[r].n = 0;
+        rid[r] = sk_eval<WT, WC>(a, cand, okb, zb, s_nm, SK_HALO + r * SK_THREADS + tid, (uint64_t)(T0 + r * SK_THREADS + tid), hold[r]);
     }
     /* one block scan for the four rows: 16 bits per row (<= 256*(2w+2) < 65536 records per row) */
-    const uint64_t packed = (uint64_t)cnt[0] | (uint64_t)cnt[1] << 16 | (uint64_t)cnt[2] << 32 | (uint64_t)cnt[3] << 48;
+    const uint64_t packed = (uint64_t)hold[0].n | (uint64_t)hold[1].n << 16 | (uint64_t)hold[2].n << 32 | (uint64_t)hold[3].n << 48;
     uint64_t tot;
     const uint64_t ex = lq_block_excl_scan(packed, scan_sm, &tot);
     const uint64_t tile_total = (tot & 0xffff) + ((tot >> 16) & 0xffff) + ((tot >> 32) & 0xffff) + (tot >> 48);
 
-    /* decoupled look-back: exclusive prefix of the tile totals, tiles in ticket order */
-    if (tid == 0) {
+    /* decoupled look-back (warp 0): exclusive prefix of the tile totals, tiles in ticket order */
+    if (tid < 32) {
         const unsigned long long FLAG_AGG = 1ULL << 62, FLAG_PRE = 2ULL << 62, VMASK = (1ULL << 62) - 1;
         uint64_t base = 0;
-        if (tile == 0) atomicExch(&a.state[0], FLAG_PRE | tile_total);
+        if (tile == 0) { if (tid == 0) atomicExch(&a.state[0], FLAG_PRE | tile_total); }
         else {
-            atomicExch(&a.state[tile], FLAG_AGG | tile_total);
-            int64_t j = (int64_t)tile - 1; uint32_t spins = 0;
-            for (;;) {
-                const unsigned long long s = *(volatile unsigned long long*)&a.state[j];
-                if ((s >> 62) == 0) { if (++spins > (1u << 27)) { atomicOr(a.err, 1u); break; } continue; }
-                base += s & VMASK;
-                if ((s >> 62) == 2) break;
-                --j;
+            if (tid == 0) atomicExch(&a.state[tile], FLAG_AGG | tile_total);
+            int64_t hi = (int64_t)tile - 1; uint32_t spins = 0;
+            for (;;) {   /* lanes look at tiles hi, hi-1, ..., hi-31 */
+                const int64_t j = hi - tid;
+                unsigned long long sv = FLAG_PRE;                     /* tiles before the first one: an empty prefix */
+                if (j >= 0) sv = *(volatile unsigned long long*)&a.state[j];
+                const uint32_t ready = __ballot_sync(0xffffffffu, (sv >> 62) != 0);
+                const uint32_t pre = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+                /* usable lanes: 0 .. first PREFIX lane, all of which must be ready */
+                const int stop = pre ? __ffs(pre) - 1 : 31;
+                const uint32_t need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1);
+                if ((ready & need) != need) { if (++spins > (1u << 24)) { if (tid == 0) atomicOr(a.err, 1u); break; } continue; }
+                uint64_t v = (tid <= stop) ? (sv & VMASK) : 0;
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                base += v;
+                if (pre) break;
+                hi -= 32;
             }
-            atomicExch(&a.state[tile], FLAG_PRE | (base + tile_total));
+            if (tid == 0) atomicExch(&a.state[tile], FLAG_PRE | (base + tile_total));
         }
-        s_base = base;
+        if (tid == 0) s_base = base;
     }
     __syncthreads();
     uint64_t base = s_base;
     if (base + tile_total > a.cap) return;     /* output buffer too small: the host re-runs with the exact size */
 
-    /* stage B, pass 2: evaluate again, writing in base order */
-    SkWrite wr; wr.key = a.out_key; wr.yy = a.out_y;
+    /* write in base order */
     #pragma unroll
     for (int r = 0; r < SK_PER_THREAD; ++r) {
-        if (cnt[r]) {
-            wr.at = base + ((ex >> (16 * r)) & 0xffff);
-            sk_eval<WT>(a, cand, okb, zb, s_nm, SK_HALO + r * SK_THREADS + tid, (uint64_t)(T0 + r * SK_THREADS + tid), W0, wr);
+        const uint64_t at = base + ((ex >> (16 * r)) & 0xffff);
+        if (hold[r].n > 2) {   /* rare (equal minimizers inside one window): evaluate again, writing directly */
+            SkWrite wr; wr.key = a.out_key; wr.yy = a.out_y; wr.at = at;
+            sk_eval<WT, WC>(a, cand, okb, zb, s_nm, SK_HALO + r * SK_THREADS + tid, (uint64_t)(T0 + r * SK_THREADS + tid), wr);
+        } else if (hold[r].n > 0) {
+            a.out_key[at] = hold[r].k0; a.out_y[at] = (uint64_t)rid[r] << 32 | hold[r].p0;
+            if (hold[r].n > 1) { a.out_key[at + 1] = hold[r].k1; a.out_y[at + 1] = (uint64_t)rid[r] << 32 | hold[r].p1; }
         }
         base += (tot >> (16 * r)) & 0xffff;
     }
@@ -343,9 +378,9 @@ int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_b
             a.out_key = out->key.as<uint32_t>(); a.out_y = out->y.as<uint64_t>();
             {
                 LqProfScope ps("sketch", st, 1, rd->n_slots * (LQ_SLOT_W2 + LQ_SLOT_WN) * 4 + (uint64_t)((double)rd->n_bases * 2.0 / (w + 1)) * 12);
-                if (w <= 5) lq_sketch_k<5><<<nblk, SK_THREADS, 0, st>>>(a);
-                else if (w <= 10) lq_sketch_k<10><<<nblk, SK_THREADS, 0, st>>>(a);
-                else lq_sketch_k<LQ_MAX_W><<<nblk, SK_THREADS, 0, st>>>(a);
+                if (w == 5) lq_sketch_k<5, 5><<<nblk, SK_THREADS, 0, st>>>(a);              /* LongQC's overlap runs */
+                else if (w == 10) lq_sketch_k<10, 10><<<nblk, SK_THREADS, 0, st>>>(a);      /* LongQC's spike-in run */
+                else lq_sketch_k<LQ_MAX_W, 0><<<nblk, SK_THREADS, 0, st>>>(a);
             }
             LQ_CUDA_OK(cudaGetLastError());
             unsigned long long last = 0; uint32_t h_err = 0;

@@ -307,9 +307,11 @@ LQ_HD void lq_sketch_at(const uint32_t *b2, const uint32_t *nm, uint64_t g0, int
 #define LQ_POPC64(x) __builtin_popcountll(x)
 #endif
 
-template <int WT, class Fetch, class Sink>
-LQ_HD int lq_sketch_fast_win(uint64_t okw, uint64_t ambw, int w, int k, uint32_t rid, int i, int last, Fetch &fetch, Sink &sink)
+/* WC > 0: w is the compile-time constant WC (== WT), so the candidate arrays stay in registers */
+template <int WT, int WC, class Fetch, class Sink>
+LQ_HD int lq_sketch_fast_win(uint64_t okw, uint64_t ambw, int w_rt, int k, uint32_t rid, int i, int last, Fetch &fetch, Sink &sink)
 {
+    const int w = WC ? WC : w_rt;
     if (!(okw >> 63)) return last ? 0 : 1;           /* base i pushes nothing valid and emits nothing (sketch.c:107 / :114 with l = 0) */
     uint64_t m = okw;
     if (ambw) { const int hb = 63 - LQ_CLZ64(ambw); m &= ~((2ULL << hb) - 1ULL); }  /* pushes after the last ambiguous base */
@@ -368,7 +370,7 @@ LQ_HD void lq_sketch_at_win(const uint32_t *b2, const uint32_t *nm, uint64_t g0,
         else if (lq_pos_ok(b2, nm, g0, i - d, k)) okw |= 1ULL << (63 - d);
     }
     lq_fetch_packed f; f.b2 = b2; f.g = g0 + (uint64_t)i; f.k = k;
-    if (k <= 16 && w <= LQ_MAX_W && lq_sketch_fast_win<LQ_MAX_W>(okw, ambw, w, k, rid, i, i == len - 1, f, sink)) return;
+    if (k <= 16 && w <= LQ_MAX_W && lq_sketch_fast_win<LQ_MAX_W, 0>(okw, ambw, w, k, rid, i, i == len - 1, f, sink)) return;
     lq_sketch_slow_at(b2, nm, g0, len, w, k, rid, i, sink);
 }
 
