@@ -156,6 +156,8 @@ __global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
     __shared__ uint32_t okb[SK_NPOS / 32 + 2], zb[SK_NPOS / 32 + 2];
     __shared__ uint64_t scan_sm[33];
     __shared__ uint32_t s_tile;
+    __shared__ uint4 s_hold[SK_PER_THREAD][SK_THREADS];
+    __shared__ uint32_t s_rid[SK_PER_THREAD][SK_THREADS];
     __shared__ uint64_t s_base;
 
     const int tid = threadIdx.x;
@@ -209,15 +211,19 @@ __global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
     }
     __syncthreads();
 
-    /* stage B: evaluate every base of the tile once; rows r = 0..3, base = T0 + r*256 + tid */
-    SkHold hold[SK_PER_THREAD]; uint32_t rid[SK_PER_THREAD];
+    /* stage B: evaluate every base of the tile once; rows r = 0..3, base = T0 + r*256 + tid.  The (at most two) records of
+     * a base wait in shared memory until the tile's output offset is known. */
+    int cnt[SK_PER_THREAD];
     #pragma unroll
     for (int r = 0; r < SK_PER_THREAD; ++r) {
-        hold[r].n = 0;
-        rid[r] = sk_eval<WT, WC>(a, cand, okb, zb, s_nm, SK_HALO + r * SK_THREADS + tid, (uint64_t)(T0 + r * SK_THREADS + tid), hold[r]);
+        SkHold h; h.n = 0; h.k0 = h.p0 = h.k1 = h.p1 = 0;
+        const uint32_t rid = sk_eval<WT, WC>(a, cand, okb, zb, s_nm, SK_HALO + r * SK_THREADS + tid, (uint64_t)(T0 + r * SK_THREADS + tid), h);
+        cnt[r] = h.n;
+        s_hold[r][tid] = make_uint4(h.k0, h.p0, h.k1, h.p1);
+        s_rid[r][tid] = rid;
     }
     /* one block scan for the four rows: 16 bits per row (<= 256*(2w+2) < 65536 records per row) */
-    const uint64_t packed = (uint64_t)hold[0].n | (uint64_t)hold[1].n << 16 | (uint64_t)hold[2].n << 32 | (uint64_t)hold[3].n << 48;
+    const uint64_t packed = (uint64_t)cnt[0] | (uint64_t)cnt[1] << 16 | (uint64_t)cnt[2] << 32 | (uint64_t)cnt[3] << 48;
     uint64_t tot;
     const uint64_t ex = lq_block_excl_scan(packed, scan_sm, &tot);
     const uint64_t tile_total = (tot & 0xffff) + ((tot >> 16) & 0xffff) + ((tot >> 32) & 0xffff) + (tot >> 48);
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
                 /* usable lanes: 0 .. first PREFIX lane, all of which must be ready */
                 const int stop = pre ? __ffs(pre) - 1 : 31;
                 const uint32_t need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1);
-                if ((ready & need) != need) { if (++spins > (1u << 24)) { if (tid == 0) atomicOr(a.err, 1u); break; } continue; }
+                if ((ready & need) != need) { __nanosleep(64); if (++spins > (1u << 24)) { if (tid == 0) atomicOr(a.err, 1u); break; } continue; }
                 uint64_t v = (tid <= stop) ? (sv & VMASK) : 0;
                 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -259,12 +265,13 @@ __global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
     #pragma unroll
     for (int r = 0; r < SK_PER_THREAD; ++r) {
         const uint64_t at = base + ((ex >> (16 * r)) & 0xffff);
-        if (hold[r].n > 2) {   /* rare (equal minimizers inside one window): evaluate again, writing directly */
+        if (cnt[r] > 2) {   /* rare (equal minimizers inside one window): evaluate again, writing directly */
             SkWrite wr; wr.key = a.out_key; wr.yy = a.out_y; wr.at = at;
             sk_eval<WT, WC>(a, cand, okb, zb, s_nm, SK_HALO + r * SK_THREADS + tid, (uint64_t)(T0 + r * SK_THREADS + tid), wr);
-        } else if (hold[r].n > 0) {
-            a.out_key[at] = hold[r].k0; a.out_y[at] = (uint64_t)rid[r] << 32 | hold[r].p0;
-            if (hold[r].n > 1) { a.out_key[at + 1] = hold[r].k1; a.out_y[at + 1] = (uint64_t)rid[r] << 32 | hold[r].p1; }
+        } else if (cnt[r] > 0) {
+            const uint4 h = s_hold[r][tid]; const uint64_t hi = (uint64_t)s_rid[r][tid] << 32;
+            a.out_key[at] = h.x; a.out_y[at] = hi | h.y;
+            if (cnt[r] > 1) { a.out_key[at + 1] = h.z; a.out_y[at + 1] = hi | h.w; }
         }
         base += (tot >> (16 * r)) & 0xffff;
     }

@@ -329,27 +329,34 @@ LQ_HD int lq_sketch_fast_win(uint64_t okw, uint64_t ambw, int w_rt, int k, uint3
         }
     }
     #define LQ_EMIT(j_) sink((uint64_t)cx[j_] << 8 | (uint64_t)k, (uint64_t)rid << 32 | (uint64_t)((uint32_t)(i - cd[j_]) << 1) | (uint64_t)cz[j_])
-    int mi = 0;
+    /* rightmost minimum of the old window cx[0..w-1] and of the new one cx[1..w] */
+    int mi = 0, m2 = 1;
     #pragma unroll
-    for (int j = 1; j < WT; ++j) if (j < w && cx[j] <= cx[mi]) mi = j;      /* rightmost minimum of the old window cx[0..w-1] */
-    if (cx[w] <= cx[mi]) {
+    for (int j = 1; j < WT; ++j) if (j < w && cx[j] <= cx[mi]) mi = j;
+    #pragma unroll
+    for (int j = 2; j <= WT; ++j) if (j <= w && cx[j] <= cx[m2]) m2 = j;
+    const bool c1 = cx[w] <= cx[mi];            /* sketch.c:122: the newcomer takes over, the old minimum is written */
+    const bool c2 = !c1 && mi == 0;             /* sketch.c:125: the minimum was the oldest candidate and leaves the window */
+    if (c1 | c2) {                              /* one record, selected without a divergent branch per case */
+        const int sel = c1 ? mi : 0;
+        uint32_t ex = cx[0], ez = cz[0]; int ed = cd[0];
         #pragma unroll
-        for (int j = 0; j < WT; ++j) if (j == mi) LQ_EMIT(j);
-        if (last) LQ_EMIT(w);
-    } else if (mi == 0) {
-        int m2 = 1;
-        LQ_EMIT(0);
+        for (int j = 1; j < WT; ++j) if (j < w && j == sel) { ex = cx[j]; ez = cz[j]; ed = cd[j]; }
+        sink((uint64_t)ex << 8 | (uint64_t)k, (uint64_t)rid << 32 | (uint64_t)((uint32_t)(i - ed) << 1) | (uint64_t)ez);
+    }
+    if (c2) {                                   /* twins of the new minimum (sketch.c:131-136): equal hashes inside one window, rare */
+        bool any = false;
         #pragma unroll
-        for (int j = 2; j <= WT; ++j) if (j <= w && cx[j] <= cx[m2]) m2 = j;
-        #pragma unroll
-        for (int j = 1; j <= WT; ++j) if (j <= w && j != m2 && cx[j] == cx[m2]) LQ_EMIT(j);
-        if (last) {
+        for (int j = 1; j <= WT; ++j) if (j <= w && j != m2 && cx[j] == cx[m2]) any = true;
+        if (any) {
             #pragma unroll
-            for (int j = 1; j <= WT; ++j) if (j == m2) LQ_EMIT(j);
+            for (int j = 1; j <= WT; ++j) if (j <= w && j != m2 && cx[j] == cx[m2]) LQ_EMIT(j);
         }
-    } else if (last) {
+    }
+    if (last) {                                 /* sketch.c:140-141: the minimum of the final window */
+        const int fin = c1 ? w : (c2 ? m2 : mi);
         #pragma unroll
-        for (int j = 1; j < WT; ++j) if (j == mi) LQ_EMIT(j);
+        for (int j = 0; j <= WT; ++j) if (j <= w && j == fin) LQ_EMIT(j);
     }
     #undef LQ_EMIT
     return 1;

@@ -90,7 +90,7 @@ def hostcheck():
     global _hc
     if _hc is None:
         lib = C.CDLL(HOSTCHECK_SO)
-        for name in ("lqhc_sketch_parallel", "lqhc_sketch_slow_everywhere"):
+        for name in ("lqhc_sketch_parallel", "lqhc_sketch_parallel_win", "lqhc_sketch_slow_everywhere"):
             f = getattr(lib, name)
             f.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_int]
             f.restype = C.c_int

@@ -16,6 +16,8 @@ def test_position_parallel_sketch(w, k):
         want = liblq.oracle_sketch(s, w, k, 3)
         assert np.array_equal(liblq.hc_sketch("lqhc_sketch_parallel", s, w, k, 3), want)
         assert np.array_equal(liblq.hc_sketch("lqhc_sketch_replay", s, w, k, 3, 0), want)
+        if k <= 16:   # the kernel's windowed closed form (palindromes / N inside the look-back handled without replay)
+            assert np.array_equal(liblq.hc_sketch("lqhc_sketch_parallel_win", s, w, k, 3), want)
 
 
 @pytest.mark.parametrize("w,k", [(5, 12), (10, 15), (3, 4)])
