@@ -31,7 +31,8 @@ struct lqcov_ctx {
     std::vector<std::string> qname;
     std::vector<int> qlen;
     std::vector<char> qqual; std::vector<uint64_t> qqual_off; bool q_has_qual;
-    std::unordered_map<std::string, std::vector<uint32_t> > qname_map;
+    /* query names -> query indices: open-address table over (pointer, length) keys, chained for duplicate names */
+    std::vector<int32_t> qn_slot, qn_next; uint32_t qn_mask;
     std::vector<uint64_t> qfirst;
     std::vector<lqh_sub_v> ovlp;        /* ovlp_coords (minimap2-coverage.c:438-444) */
     std::vector<float> avg_k;           /* avg_ks */
@@ -98,16 +99,42 @@ extern "C" void lqcov_destroy(lqcov_ctx *c)
 
 static std::string name_of(const lqcov_reads_t *r, uint32_t i) { return std::string(r->names + r->name_off[i], (size_t)(r->name_off[i + 1] - r->name_off[i])); }
 
+static inline uint64_t name_hash(const char *s, size_t n) { uint64_t h = 1469598103934665603ULL; for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)s[i]; h *= 1099511628211ULL; } return h ^ (h >> 29); }
+
+static void qnames_build(lqcov_ctx *c)
+{
+    uint32_t cap = 16; while (cap < 4 * c->nq + 16) cap <<= 1;
+    c->qn_mask = cap - 1; c->qn_slot.assign(cap, -1); c->qn_next.assign(c->nq, -1);
+    for (uint32_t q = c->nq; q-- > 0; ) { /* reverse, so that chains list the queries in ascending order */
+        const std::string &nm = c->qname[q];
+        uint32_t h = (uint32_t)name_hash(nm.data(), nm.size()) & c->qn_mask;
+        for (;; h = (h + 1) & c->qn_mask) {
+            const int32_t s = c->qn_slot[h];
+            if (s < 0) { c->qn_slot[h] = (int32_t)q; break; }
+            if (c->qname[s] == nm) { c->qn_next[q] = s; c->qn_slot[h] = (int32_t)q; break; }
+        }
+    }
+}
+/* first query with this name (or -1); further ones through qn_next */
+static inline int32_t qnames_find(const lqcov_ctx *c, const char *s, size_t n)
+{
+    for (uint32_t h = (uint32_t)name_hash(s, n) & c->qn_mask;; h = (h + 1) & c->qn_mask) {
+        const int32_t q = c->qn_slot[h];
+        if (q < 0) return -1;
+        if (c->qname[q].size() == n && memcmp(c->qname[q].data(), s, n) == 0) return q;
+    }
+}
+
 extern "C" int lqcov_set_queries(lqcov_ctx *c, const lqcov_reads_t *q)
 {
     const double t0 = now_ms();
     c->nq = q->n;
-    c->qname.resize(q->n); c->qlen.resize(q->n); c->qname_map.clear();
+    c->qname.resize(q->n); c->qlen.resize(q->n);
     for (uint32_t i = 0; i < q->n; ++i) {
         c->qname[i] = name_of(q, i);
         c->qlen[i] = (int)(q->seq_off[i + 1] - q->seq_off[i]);
-        c->qname_map[c->qname[i]].push_back(i);
     }
+    qnames_build(c);
     c->q_has_qual = q->qual != 0;
     c->qqual_off.assign(q->seq_off, q->seq_off + q->n + 1);
     if (q->qual && q->n) c->qqual.assign(q->qual + q->seq_off[0], q->qual + q->seq_off[q->n]); else c->qqual.clear();
@@ -202,16 +229,19 @@ extern "C" int lqcov_part_finish(lqcov_ctx *c, const lqcov_reads_t *part)
     c->stats.t_index_ms += now_ms() - t0;
     /* name tables for the self-diagonal / dual-mapping skips (lqmap.c:180-189) */
     const uint32_t nq = c->nq;
-    std::vector<std::vector<uint32_t> > lists(nq);
-    bool any = false;
+    /* (query, target) pairs with equal names, then CSR by query with ascending target ids */
+    std::vector<std::pair<uint32_t, uint32_t> > hits;
     if (c->opt.no_self || c->opt.ava)
-        for (uint32_t t = 0; t < part->n; ++t) {
-            std::unordered_map<std::string, std::vector<uint32_t> >::const_iterator it = c->qname_map.find(name_of(part, t));
-            if (it != c->qname_map.end()) { any = true; for (size_t j = 0; j < it->second.size(); ++j) lists[it->second[j]].push_back(t); }
-        }
-    c->self_off.assign((size_t)nq + 1, 0); c->self_list.clear();
-    for (uint32_t q = 0; q < nq; ++q) { c->self_off[q] = (uint32_t)c->self_list.size(); if (any) c->self_list.insert(c->self_list.end(), lists[q].begin(), lists[q].end()); }
-    c->self_off[nq] = (uint32_t)c->self_list.size();
+        for (uint32_t t = 0; t < part->n; ++t)
+            for (int32_t q = qnames_find(c, part->names + part->name_off[t], (size_t)(part->name_off[t + 1] - part->name_off[t])); q >= 0; q = c->qn_next[q])
+                hits.push_back(std::make_pair((uint32_t)q, t));
+    c->self_off.assign((size_t)nq + 1, 0); c->self_list.assign(hits.size(), 0);
+    for (size_t i = 0; i < hits.size(); ++i) ++c->self_off[hits[i].first + 1];
+    for (uint32_t q = 0; q < nq; ++q) c->self_off[q + 1] += c->self_off[q];
+    {
+        std::vector<uint32_t> fill(c->self_off.begin(), c->self_off.end() - 1);
+        for (size_t i = 0; i < hits.size(); ++i) c->self_list[fill[hits[i].first]++] = hits[i].second; /* t ascending within a query */
+    }
     c->qrank.clear(); c->trank.clear();
     if (c->opt.ava) { /* strcmp order of names == rank among the sorted distinct names of queries and targets */
         std::vector<std::string> all; all.reserve((size_t)nq + part->n);
@@ -246,7 +276,6 @@ static void map_opt_of(const lqcov_opt_t *o, LqMapOpt *m)
     m->max_overhang = o->max_overhang; m->min_ratio = o->min_ratio; m->covt = 150;
 }
 
-static bool ovl_by_q(const LqOvl &a, const LqOvl &b) { return a.q < b.q; }
 
 extern "C" int lqcov_map_part(lqcov_ctx *c)
 {
@@ -263,13 +292,15 @@ extern "C" int lqcov_map_part(lqcov_ctx *c)
     for (uint32_t q = 0; q < c->nq; ++q)
         if (hs[q].n_kept > 0 && !hs[q].gate_closed && c->avg_k[q] == 0.f) c->avg_k[q] = (float)(uint64_t)hs[q].sum_span_kept / (int32_t)hs[q].n_kept;
     /* lqmap.c:287: fold this part's overlaps into every query's persistent interval list */
-    std::stable_sort(ovl.begin(), ovl.end(), ovl_by_q);
-    std::vector<lqh_sub> cv;
-    for (size_t i = 0; i < ovl.size(); ) {
-        size_t j = i; cv.clear();
-        while (j < ovl.size() && ovl[j].q == ovl[i].q) { lqh_sub s; s.start = ovl[j].start; s.end = ovl[j].end; cv.push_back(s); ++j; }
-        lqh_filter_redundant(&c->ovlp[ovl[i].q], cv.data(), cv.size(), (uint32_t)c->opt.min_coverage);
-        i = j;
+    {
+        std::vector<uint32_t> off((size_t)c->nq + 1, 0);
+        for (size_t i = 0; i < ovl.size(); ++i) ++off[ovl[i].q + 1];
+        for (uint32_t q = 0; q < c->nq; ++q) off[q + 1] += off[q];
+        std::vector<lqh_sub> cv(ovl.size());
+        std::vector<uint32_t> at(off.begin(), off.end() - 1);
+        for (size_t i = 0; i < ovl.size(); ++i) { lqh_sub s; s.start = ovl[i].start; s.end = ovl[i].end; cv[at[ovl[i].q]++] = s; }
+        for (uint32_t q = 0; q < c->nq; ++q)
+            if (off[q + 1] > off[q]) lqh_filter_redundant(&c->ovlp[q], cv.data() + off[q], off[q + 1] - off[q], (uint32_t)c->opt.min_coverage);
     }
     c->stats.seeds += ms.n_seeds; c->stats.groups += ms.n_groups; c->stats.chains += ms.n_chains; c->stats.overlaps += ms.n_ovl;
     c->stats.batches += ms.n_batches; c->stats.walk_buckets += ms.n_walk_buckets;

@@ -17,7 +17,7 @@
 
 void LqQueryDev::release()
 {
-    reads.release(); mins.release(); first.release(); dup.release(); lambda.release(); lambda2.release(); mcnt.release();
+    reads.release(); mins.release(); first.release(); dup.release(); dup_tmp.release(); dup_tk.release(); dup_ty.release(); dup_ts.release(); dup_hist.release(); nmatch_buf.release(); lambda.release(); lambda2.release(); mcnt.release();
     keep.release(); neff.release(); krank.release(); soff.release(); qstat.release();
     self_off.release(); self_list.release(); qrank.release(); trank.release();
 }
@@ -321,21 +321,29 @@ __global__ void lq_gstart_k(uint64_t n, const uint32_t *__restrict__ head, const
 }
 
 /* groups that can hold a chain (>= min_cnt anchors, chain.c:116-119): compacted so that a warp is only spent on those */
-__global__ void lq_biggroups_k(uint32_t ng, const uint32_t *__restrict__ gstart, uint32_t min_cnt, uint32_t *__restrict__ big, uint32_t *__restrict__ n_big)
+/* A chain needs >= min_cnt anchors, and its score cannot exceed the sum of the anchors' spans (chain.c:58: each link adds at most
+ * q_span), so a run of n anchors with n*max_span < min_sc cannot produce a chain either.  Runs of <= CH_SMALL anchors go to the
+ * one-thread-per-run kernel (list grows from the front of `big`), longer ones to the warp kernel (list grows from the back). */
+#define CH_SMALL 16
+__global__ void lq_biggroups_k(uint32_t ng, const uint32_t *__restrict__ gstart, uint32_t min_cnt, uint32_t min_sc, uint32_t max_span,
+                               uint32_t *__restrict__ big, uint32_t cap, uint32_t *__restrict__ n_small, uint32_t *__restrict__ n_large)
 {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool ok = g < ng && gstart[g + 1] - gstart[g] >= min_cnt;
-    const uint32_t m = __ballot_sync(0xffffffffu, ok), lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if (lane == 0 && m) base = atomicAdd(n_big, (uint32_t)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (ok) big[base + __popc(m & ((1u << lane) - 1))] = g;
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const uint32_t n = g < ng ? gstart[g + 1] - gstart[g] : 0;
+    const bool ok = n >= min_cnt && (uint64_t)n * max_span >= min_sc;
+    const bool sm = ok && n <= CH_SMALL, lg = ok && n > CH_SMALL;
+    const uint32_t ms = __ballot_sync(0xffffffffu, sm), ml = __ballot_sync(0xffffffffu, lg);
+    uint32_t bs = 0, bl = 0;
+    if (lane == 0) { if (ms) bs = atomicAdd(n_small, (uint32_t)__popc(ms)); if (ml) bl = atomicAdd(n_large, (uint32_t)__popc(ml)); }
+    bs = __shfl_sync(0xffffffffu, bs, 0); bl = __shfl_sync(0xffffffffu, bl, 0);
+    if (sm) big[bs + __popc(ms & ((1u << lane) - 1))] = g;
+    if (lg) big[cap - 1 - (bl + __popc(ml & ((1u << lane) - 1)))] = g;
 }
 
 struct ChainArgs {
     const uint64_t *ax; const uint32_t *aq, *am;
     int32_t *f, *p, *v, *t; uint64_t *uend; uint32_t *vl, *s_lo, *s_hi;
-    const uint32_t *gstart; const uint32_t *big; const uint32_t *n_groups; uint32_t *cursor;
+    const uint32_t *gstart; const uint32_t *big; uint32_t big_cap; const uint32_t *n_small, *n_groups; uint32_t *cursor;
     uint32_t nqb, q0; const uint64_t *qoff;
     const LqQStat *qstat; const uint32_t *qlen, *tlen; const uint64_t *first;
     uint64_t *lambda, *lambda2; uint32_t *mcnt;
@@ -344,16 +352,20 @@ struct ChainArgs {
 };
 
 #define CH_WARPS 4
+#define CH_RING 128
 __global__ void __launch_bounds__(CH_WARPS * 32) lq_chain_k(ChainArgs a)
 {
-    const uint32_t lane = threadIdx.x & 31;
+    __shared__ uint32_t s_r[CH_WARPS][CH_RING];
+    __shared__ int32_t s_q[CH_WARPS][CH_RING], s_f[CH_WARPS][CH_RING], s_p[CH_WARPS][CH_RING], s_v[CH_WARPS][CH_RING], s_t[CH_WARPS][CH_RING];
+    const uint32_t lane = threadIdx.x & 31, wid_ = threadIdx.x >> 5;
+    uint32_t *ring_r = s_r[wid_]; int32_t *ring_q = s_q[wid_], *ring_f = s_f[wid_], *ring_p = s_p[wid_], *ring_v = s_v[wid_], *ring_t = s_t[wid_];
     const uint32_t ng = *a.n_groups;
     for (;;) {
         uint32_t g = 0;
         if (lane == 0) g = atomicAdd(a.cursor, 1u);
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= ng) break;
-        g = a.big[g];
+        g = a.big[a.big_cap - 1 - g];
         const int32_t gb = (int32_t)a.gstart[g], ge = (int32_t)a.gstart[g + 1], n = ge - gb;
         if (n < a.o.min_cnt) continue; /* a chain needs min_cnt anchors of one (strand, target) run (chain.c:116-119) */
         /* owning query */
@@ -362,15 +374,23 @@ __global__ void __launch_bounds__(CH_WARPS * 32) lq_chain_k(ChainArgs a)
         const uint32_t q = a.q0 + lo;
         const float avg_span = a.qstat[q].avg_span;
 
-        /* ---- DP (chain.c:41-80), 32 predecessors per step ---- */
+        /* ---- DP (chain.c:41-80), 32 predecessors per step.  The last CH_RING anchors (target pos, query pos, f, p, v and the
+         *      t[] stamps) live in a per-warp shared-memory ring, so the inner loop does not wait on global memory; anchors
+         *      further back than the ring (dense repeats) are read from global memory. ---- */
         int32_t st = gb;
+        for (int e = lane; e < CH_RING; e += 32) ring_t[e] = -1;
+        __syncwarp();
+        uint64_t nx = a.ax[gb]; uint32_t nq_ = a.aq[gb], nm_ = a.am[gb];     /* next anchor, fetched one iteration ahead */
         for (int32_t i = gb; i < ge; ++i) {
-            const uint32_t ri = (uint32_t)a.ax[i];
-            const int32_t qi = (int32_t)a.aq[i], span = (int32_t)(a.am[i] >> 24);
+            const uint32_t ri = (uint32_t)nx;
+            const int32_t qi = (int32_t)nq_, span = (int32_t)(nm_ >> 24);
+            if (i + 1 < ge) { nx = a.ax[i + 1]; nq_ = a.aq[i + 1]; nm_ = a.am[i + 1]; }
+            if (lane == 0) { ring_r[i & (CH_RING - 1)] = ri; ring_q[i & (CH_RING - 1)] = qi; }
             int32_t best = span, best_j = -1, n_skip = 0;
             while (st < i) { /* advance the window start (uniform) */
                 const int32_t j = st + (int32_t)lane;
-                const bool far = j < i && (uint64_t)ri - (uint64_t)(uint32_t)a.ax[j] > (uint64_t)a.o.max_dist;
+                bool far = false;
+                if (j < i) { const uint32_t rj = i - j < CH_RING ? ring_r[j & (CH_RING - 1)] : (uint32_t)a.ax[j]; far = (uint64_t)ri - (uint64_t)rj > (uint64_t)a.o.max_dist; }
                 const uint32_t m = __ballot_sync(0xffffffffu, far);
                 const int adv = m == 0xffffffffu ? 32 : __ffs(~m) - 1; /* rpos ascending: `far` is a prefix */
                 st += adv;
@@ -379,16 +399,20 @@ __global__ void __launch_bounds__(CH_WARPS * 32) lq_chain_k(ChainArgs a)
             bool stop = false;
             for (int32_t jb = i - 1; jb >= st && !stop; jb -= 32) {
                 const int32_t j = jb - (int32_t)lane;
+                const bool inr = i - j < CH_RING;                 /* anchor j still in the ring */
+                const int js = j & (CH_RING - 1);
                 bool valid = false; int32_t sc = INT32_MIN, pj = -1;
                 if (j >= st) {
+                    const uint32_t rj = inr ? ring_r[js] : (uint32_t)a.ax[j];
+                    const int32_t qj = inr ? ring_q[js] : (int32_t)a.aq[j];
                     int32_t gain;
-                    if (lq_chain_gain((int64_t)ri - (int64_t)(uint32_t)a.ax[j], qi - (int32_t)a.aq[j], span, a.o.max_dist, a.o.max_dist, a.o.bw, avg_span, &gain)) {
-                        valid = true; sc = gain + a.f[j]; pj = a.p[j];
+                    if (lq_chain_gain((int64_t)ri - (int64_t)rj, qi - qj, span, a.o.max_dist, a.o.max_dist, a.o.bw, avg_span, &gain)) {
+                        valid = true; sc = gain + (inr ? ring_f[js] : a.f[j]); pj = inr ? ring_p[js] : a.p[j];
                     }
                 }
-                if (valid && pj >= 0) a.t[pj] = i;   /* chain.c:77, for every lane: stamps past a break are never read */
+                if (valid && pj >= 0) { if (i - pj < CH_RING) ring_t[pj & (CH_RING - 1)] = i; else a.t[pj] = i; }   /* chain.c:77, every lane: stamps past a break are never read */
                 __syncwarp();
-                const bool tflag = valid && a.t[j] == i;
+                const bool tflag = valid && (inr ? ring_t[js] : a.t[j]) == i;
                 /* exclusive prefix max over lanes, seeded with `best` */
                 int32_t pm = sc;
                 #pragma unroll
@@ -410,8 +434,11 @@ __global__ void __launch_bounds__(CH_WARPS * 32) lq_chain_k(ChainArgs a)
                 if (stop_lane < 32) stop = true;
             }
             if (lane == 0) {
-                a.f[i] = best; a.p[i] = best_j;
-                a.v[i] = best_j >= 0 && a.v[best_j] > best ? a.v[best_j] : best;
+                int32_t vb = best;
+                if (best_j >= 0) { const int32_t vj = i - best_j < CH_RING ? ring_v[best_j & (CH_RING - 1)] : a.v[best_j]; if (vj > best) vb = vj; }
+                a.f[i] = best; a.p[i] = best_j; a.v[i] = vb;
+                const int is_ = i & (CH_RING - 1);
+                ring_f[is_] = best; ring_p[is_] = best_j; ring_v[is_] = vb; ring_t[is_] = -1;
             }
             __syncwarp();
         }
@@ -502,6 +529,93 @@ __global__ void __launch_bounds__(CH_WARPS * 32) lq_chain_k(ChainArgs a)
             for (int32_t c = lane; c < cnt; c += 32) atomicAdd(&mc[a.am[anch[c]] & 0xffffffu], 1u);
         }
         __syncwarp();
+    }
+}
+
+
+/* ---- runs of <= CH_SMALL anchors: one thread per run, the reference's loops as they are (chain.c:41-125), then the same
+ *      region/accounting code as the warp kernel.  Most of these runs are chance hits that end without a chain. ---- */
+__global__ void __launch_bounds__(128) lq_chain_small_k(ChainArgs a)
+{
+    const uint32_t ns = *a.n_small;
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < ns; b += gridDim.x * blockDim.x) {
+        const uint32_t g = a.big[b];
+        const int32_t gb = (int32_t)a.gstart[g], n = (int32_t)a.gstart[g + 1] - gb;
+        uint32_t lo = 0, hi = a.nqb;
+        while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (a.qoff[mid] <= (uint64_t)gb) lo = mid; else hi = mid; }
+        const uint32_t q = a.q0 + lo;
+        const float avg_span = a.qstat[q].avg_span;
+        uint32_t r[CH_SMALL]; int32_t qp[CH_SMALL], f[CH_SMALL], p[CH_SMALL], v[CH_SMALL], t[CH_SMALL]; uint32_t am[CH_SMALL];
+        for (int i = 0; i < n; ++i) { r[i] = (uint32_t)a.ax[gb + i]; qp[i] = (int32_t)a.aq[gb + i]; am[i] = a.am[gb + i]; t[i] = -1; }
+        int st = 0, peak = 0;
+        for (int i = 0; i < n; ++i) {
+            const int32_t span = (int32_t)(am[i] >> 24);
+            int32_t best = span, best_j = -1, n_skip = 0;
+            while (st < i && (uint64_t)r[i] - (uint64_t)r[st] > (uint64_t)a.o.max_dist) ++st;
+            for (int j = i - 1; j >= st; --j) {
+                int32_t sc;
+                if (!lq_chain_gain((int64_t)r[i] - (int64_t)r[j], qp[i] - qp[j], span, a.o.max_dist, a.o.max_dist, a.o.bw, avg_span, &sc)) continue;
+                sc += f[j];
+                if (sc > best) { best = sc; best_j = j; if (n_skip > 0) --n_skip; }
+                else if (t[j] == i) { if (++n_skip > a.o.max_skip) break; }
+                if (p[j] >= 0) t[p[j]] = i;
+            }
+            f[i] = best; p[i] = best_j;
+            v[i] = best_j >= 0 && v[best_j] > best ? v[best_j] : best;
+            if (v[i] > peak) peak = v[i];
+        }
+        if (peak < a.o.min_sc) continue;                      /* no chain end can qualify (chain.c:86) */
+        /* chain ends, best first (chain.c:82-106) */
+        for (int i = 0; i < n; ++i) t[i] = 0;
+        for (int i = 0; i < n; ++i) if (p[i] >= 0) t[p[i]] = 1;
+        uint64_t u[CH_SMALL]; int n_u = 0;
+        for (int i = 0; i < n; ++i)
+            if (t[i] == 0 && v[i] >= a.o.min_sc) {
+                int j = i;
+                while (j >= 0 && f[j] < v[j]) j = p[j];
+                if (j < 0) j = i;
+                const uint64_t key = (uint64_t)(uint32_t)f[j] << 32 | (uint32_t)j;
+                int e = n_u++;
+                while (e > 0 && u[e - 1] < key) { u[e] = u[e - 1]; --e; }   /* descending; equal keys (shared peak) stay adjacent */
+                u[e] = key;
+            }
+        /* backtrack (chain.c:108-125) and account */
+        for (int i = 0; i < n; ++i) t[i] = 0;
+        const int32_t qlen = (int32_t)a.qlen[q];
+        int32_t vl[CH_SMALL]; int n_v = 0;
+        for (int e = 0; e < n_u; ++e) {
+            const int n_v0 = n_v;
+            int j = (int)(uint32_t)u[e];
+            do { vl[n_v++] = j; t[j] = 1; j = p[j]; } while (j >= 0 && t[j] == 0);
+            const int cnt = n_v - n_v0;
+            int32_t score; bool keep;
+            if (j < 0) { score = (int32_t)(u[e] >> 32); keep = cnt >= a.o.min_cnt; }
+            else if ((int32_t)(u[e] >> 32) - f[j] >= a.o.min_sc) { score = (int32_t)(u[e] >> 32) - f[j]; keep = cnt >= a.o.min_cnt; }
+            else { score = 0; keep = false; }
+            if (!keep) { n_v = n_v0; continue; }
+            atomicAdd(a.n_chains, 1u);
+            const int i_first = vl[n_v - 1], i_last = vl[n_v0];
+            const uint64_t x0 = a.ax[gb + i_first];
+            const int32_t span0 = (int32_t)(am[i_first] >> 24), rev = (int32_t)(x0 >> 63), rid = (int32_t)(x0 << 1 >> 33);
+            const int32_t rs = (int32_t)r[i_first] + 1 > span0 ? (int32_t)r[i_first] + 1 - span0 : 0;
+            const int32_t re = (int32_t)r[i_last] + 1;
+            int32_t qs, qe;
+            if (!rev) { qs = qp[i_first] + 1 - span0; qe = qp[i_last] + 1; }
+            else { qs = qlen - (qp[i_last] + 1); qe = qlen - (qp[i_first] + 1 - span0); }
+            const uint32_t uqs = (uint32_t)qs, uqe = (uint32_t)qe, urs = (uint32_t)rs, ure = (uint32_t)re, rl = a.tlen[rid];
+            const uint32_t h5 = uqs < urs ? uqs : urs;
+            const uint32_t h3 = (uint32_t)qlen - uqe < rl - ure ? (uint32_t)qlen - uqe : rl - ure;
+            if ((double)(uqe - uqs) < (double)(uqe - uqs + h5 + h3) * a.o.min_ratio || h5 > (uint32_t)a.o.max_overhang || h3 > (uint32_t)a.o.max_overhang)
+                continue;
+            const uint32_t flag = score >= (int32_t)(uint16_t)a.o.min_sc_med ? 2u : 0u;
+            atomicAdd((unsigned long long*)&a.lambda[q], (unsigned long long)(uqe - uqs + 1));
+            const uint32_t at = atomicAdd(a.n_ovl, 1u);
+            if (at < a.ovl_cap) { a.ovl[at].q = q; a.ovl[at].start = uqs << 3 | flag; a.ovl[at].end = uqe << 3 | flag | 1u; }
+            if (score < (int32_t)(uint16_t)a.o.min_sc_good) continue;
+            atomicAdd((unsigned long long*)&a.lambda2[q], (unsigned long long)(uqe - uqs + 1));
+            uint32_t *mc = a.mcnt + a.first[q];
+            for (int c = n_v0; c < n_v; ++c) atomicAdd(&mc[am[vl[c]] & 0xffffffu], 1u);
+        }
     }
 }
 
@@ -719,17 +833,22 @@ int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int m
             LQ_TRY(sc->ovl.ensure((size_t)ovl_cap * sizeof(LqOvl)));
             LQ_CUDA_OK(cudaMemsetAsync(ctr + 4, 0, 16, st));
             lq_prof_count_launch(1);
-            lq_biggroups_k<<<lq_grid(ng, 256), 256, 0, st>>>(ng, sc->grp.as<uint32_t>(), (uint32_t)std::max(opt->min_cnt, 1), d_big, ctr + 4); /* ctr[4] = chainable groups */
+            /* ctr[4] = long runs (warp kernel), ctr[8] = short runs (thread kernel) */
+            LQ_CUDA_OK(cudaMemsetAsync(ctr + 8, 0, 4, st));
+            lq_biggroups_k<<<lq_grid(ng, 256), 256, 0, st>>>(ng, sc->grp.as<uint32_t>(), (uint32_t)std::max(opt->min_cnt, 1), (uint32_t)std::max(opt->min_sc, 0),
+                                                             qd->mins.has_span ? 255u : (uint32_t)ix->k, d_big, (uint32_t)big_cap, ctr + 8, ctr + 4);
             ChainArgs a;
             a.ax = b.ax; a.aq = b.aq; a.am = b.am; a.f = b.f; a.p = b.p; a.v = b.v; a.t = b.t; a.uend = b.uend; a.vl = b.vl; a.s_lo = b.head; a.s_hi = b.gid;
-            a.gstart = sc->grp.as<uint32_t>(); a.big = d_big; a.n_groups = ctr + 4; a.cursor = ctr + 5;
+            a.gstart = sc->grp.as<uint32_t>(); a.big = d_big; a.big_cap = (uint32_t)big_cap; a.n_small = ctr + 8; a.n_groups = ctr + 4; a.cursor = ctr + 5;
             a.nqb = nqb; a.q0 = q0; a.qoff = d_qoff; a.qstat = qd->qstat.as<LqQStat>(); a.qlen = qd->reads.len.as<uint32_t>(); a.tlen = ix->tlen.as<uint32_t>();
             a.first = qd->first.as<uint64_t>(); a.lambda = qd->lambda.as<uint64_t>(); a.lambda2 = qd->lambda2.as<uint64_t>(); a.mcnt = qd->mcnt.as<uint32_t>();
             a.ovl = sc->ovl.as<LqOvl>(); a.n_ovl = ctr + 6; a.ovl_cap = ovl_cap; a.n_chains = ctr + 7; a.o = *opt;
             /* the DP reads t[] before writing it only through `t[j] == i` with i a seed index of this batch: clear it */
             LQ_CUDA_OK(cudaMemsetAsync(b.t, 0xff, (size_t)nb * 4, st));
+            { LqProfScope ps("chain_small", st, 1, 0);
+              lq_chain_small_k<<<148 * 16, 128, 0, st>>>(a); }
             { LqProfScope ps("chain", st, 1, nb * 32);
-              lq_chain_k<<<148 * 8, CH_WARPS * 32, 0, st>>>(a); }
+              lq_chain_k<<<148 * 16, CH_WARPS * 32, 0, st>>>(a); }
             LQ_CUDA_OK(cudaGetLastError());
             uint32_t h_ctr[4];
             LQ_CUDA_OK(cudaMemcpyAsync(h_ctr, ctr + 4, 16, cudaMemcpyDeviceToHost, st));
@@ -754,7 +873,7 @@ int lq_map_flag_dups(LqQueryDev *qd, int key_bits, LqDevBuf &ws, cudaStream_t st
     const uint64_t n = qd->n_min;
     LQ_TRY(qd->dup.ensure(n + 16));
     if (n == 0) return 0;
-    LqMinimizers tmp; LqDevBuf tk, ty, ts, hist;
+    LqMinimizers &tmp = qd->dup_tmp; LqDevBuf &tk = qd->dup_tk, &ty = qd->dup_ty, &ts = qd->dup_ts, &hist = qd->dup_hist;
     int rc = -1;
     if (tmp.key.ensure(n * 4) == 0 && tmp.y.ensure(n * 8) == 0) {
         tmp.n = n; tmp.has_span = 0;
@@ -767,7 +886,6 @@ int lq_map_flag_dups(LqQueryDev *qd, int key_bits, LqDevBuf &ws, cudaStream_t st
             rc = cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess ? 0 : -1;
         }
     }
-    tmp.release(); tk.release(); ty.release(); ts.release(); hist.release();
     return rc;
 }
 
@@ -776,7 +894,7 @@ int lq_map_nmatch(LqQueryDev *qd, std::vector<uint32_t> *n_match, cudaStream_t s
     const uint32_t nq = qd->nq;
     n_match->assign(nq, 0);
     if (nq == 0) return 0;
-    LqDevBuf out; LQ_TRY(out.ensure(((size_t)nq + 2) * 4));
+    LqDevBuf &out = qd->nmatch_buf; LQ_TRY(out.ensure(((size_t)nq + 2) * 4));
     LQ_CUDA_OK(cudaMemsetAsync(out.p, 0, ((size_t)nq + 2) * 4, st));
     lq_prof_count_launch(1); lq_prof_d2h((uint64_t)nq * 4);
     lq_nmatch_k<<<lq_grid((size_t)nq * 32, 256), 256, 0, st>>>(nq, qd->first.as<uint64_t>(), qd->mcnt.as<uint32_t>(), out.as<uint32_t>(), out.as<uint32_t>() + nq);
@@ -785,7 +903,6 @@ int lq_map_nmatch(LqQueryDev *qd, std::vector<uint32_t> *n_match, cudaStream_t s
     LQ_CUDA_OK(cudaMemcpyAsync(n_match->data(), out.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     LQ_CUDA_OK(cudaMemcpyAsync(&sat, out.as<uint32_t>() + nq, 4, cudaMemcpyDeviceToHost, st));
     LQ_CUDA_OK(cudaStreamSynchronize(st));
-    out.release();
     if (sat) fprintf(stderr, "[lqcov] WARNING: %u queries have a minimizer matched >= 65535 times: the reference's uint16 counters saturate "
                              "in an order-dependent way there (esterr.c:130-137); column 8 of those rows is outside the parity domain\n", sat);
     return 0;

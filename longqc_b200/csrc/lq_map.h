@@ -28,6 +28,7 @@ struct LqQueryDev {
     LqDevBuf keep, neff, krank, soff; /* u32[n_min], u32[n_min], u32[n_min+1], u64[n_min+1] */
     LqDevBuf qstat;                   /* per query: LqQStat */
     LqDevBuf self_off, self_list, qrank, trank; /* self-hit tables (u32) */
+    LqMinimizers dup_tmp; LqDevBuf dup_tk, dup_ty, dup_ts, dup_hist, nmatch_buf; /* reusable scratch */
     LqQueryDev() : nq(0), n_min(0) {}
     void release();
 };

@@ -330,12 +330,12 @@ LQ_HD int lq_sketch_fast_win(uint64_t okw, uint64_t ambw, int w_rt, int k, uint3
     }
     #define LQ_EMIT(j_) sink((uint64_t)cx[j_] << 8 | (uint64_t)k, (uint64_t)rid << 32 | (uint64_t)((uint32_t)(i - cd[j_]) << 1) | (uint64_t)cz[j_])
     /* rightmost minimum of the old window cx[0..w-1] and of the new one cx[1..w] */
-    int mi = 0, m2 = 1;
+    int mi = 0, m2 = 1; uint32_t v1 = cx[0], v2 = cx[1];   /* values carried along: no dynamically indexed register array */
     #pragma unroll
-    for (int j = 1; j < WT; ++j) if (j < w && cx[j] <= cx[mi]) mi = j;
+    for (int j = 1; j < WT; ++j) if (j < w && cx[j] <= v1) { mi = j; v1 = cx[j]; }
     #pragma unroll
-    for (int j = 2; j <= WT; ++j) if (j <= w && cx[j] <= cx[m2]) m2 = j;
-    const bool c1 = cx[w] <= cx[mi];            /* sketch.c:122: the newcomer takes over, the old minimum is written */
+    for (int j = 2; j <= WT; ++j) if (j <= w && cx[j] <= v2) { m2 = j; v2 = cx[j]; }
+    const bool c1 = cx[w] <= v1;            /* sketch.c:122: the newcomer takes over, the old minimum is written */
     const bool c2 = !c1 && mi == 0;             /* sketch.c:125: the minimum was the oldest candidate and leaves the window */
     if (c1 | c2) {                              /* one record, selected without a divergent branch per case */
         const int sel = c1 ? mi : 0;
@@ -347,10 +347,10 @@ LQ_HD int lq_sketch_fast_win(uint64_t okw, uint64_t ambw, int w_rt, int k, uint3
     if (c2) {                                   /* twins of the new minimum (sketch.c:131-136): equal hashes inside one window, rare */
         bool any = false;
         #pragma unroll
-        for (int j = 1; j <= WT; ++j) if (j <= w && j != m2 && cx[j] == cx[m2]) any = true;
+        for (int j = 1; j <= WT; ++j) if (j <= w && j != m2 && cx[j] == v2) any = true;
         if (any) {
             #pragma unroll
-            for (int j = 1; j <= WT; ++j) if (j <= w && j != m2 && cx[j] == cx[m2]) LQ_EMIT(j);
+            for (int j = 1; j <= WT; ++j) if (j <= w && j != m2 && cx[j] == v2) LQ_EMIT(j);
         }
     }
     if (last) {                                 /* sketch.c:140-141: the minimum of the final window */
