@@ -135,6 +135,7 @@ struct AfBkt { uint32_t beg, end; };
 struct AfArgs {
     const uint64_t *sx; const uint32_t *sq; uint32_t *idx, *idx2, *dest; uint8_t *dig;
     const AfBkt *cur; const uint32_t *n_cur; AfBkt *nxt; uint32_t *n_nxt; uint32_t *cursor; uint32_t *n_walk;
+    AfBkt *wlist; uint32_t *n_wlist; uint32_t *wcursor;   /* tied buckets with > 2 digits: walked by lq_af_walk_k */
     int shift;
 };
 
@@ -156,6 +157,63 @@ __global__ void lq_iota_k(uint32_t *idx, uint64_t n)
 
 #define AF_WARPS 4
 #define AF_U 8
+
+/* stable sort of a sub-bucket of 9..64 elements by key, one warp: each lane holds two elements, rank = #smaller + #equal-before
+ * (== the order ksort.h's insertion sort leaves) */
+__device__ __forceinline__ void af_warp_ranksort(uint32_t *idx, uint32_t n, const uint64_t *__restrict__ key, uint32_t lane)
+{
+    const uint32_t e0 = lane < n ? idx[lane] : 0, e1 = lane + 32 < n ? idx[lane + 32] : 0;
+    const uint64_t k0 = lane < n ? key[e0] : ~0ULL, k1 = lane + 32 < n ? key[e1] : ~0ULL;
+    uint32_t r0 = 0, r1 = 0;
+    for (uint32_t j = 0; j < n; ++j) {
+        const uint64_t kj = __shfl_sync(0xffffffffu, j < 32 ? k0 : k1, j & 31);
+        r0 += kj < k0 || (kj == k0 && j < lane);
+        r1 += kj < k1 || (kj == k1 && j < lane + 32);
+    }
+    __syncwarp();
+    if (lane < n) idx[r0] = e0;
+    if (lane + 32 < n) idx[r1] = e1;
+    __syncwarp();
+}
+
+/* after dest[] is known: permute the payload, then hand the sub-buckets on (ksort.h:124-133) */
+__device__ __forceinline__ void af_finish_bucket(const AfArgs &a, uint32_t beg, uint32_t n, uint32_t nb, const uint32_t *cnt, const uint32_t *start,
+                                                 uint32_t *idx, uint32_t *idx2, const uint32_t *dest, uint32_t lane)
+{
+    if (nb > 1) {
+        for (uint32_t p0 = lane; p0 < n; p0 += 32 * AF_U) {
+            uint32_t dd[AF_U], ee[AF_U];
+            #pragma unroll
+            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) { dd[u] = dest[p]; ee[u] = idx[p]; } }
+            #pragma unroll
+            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) idx2[dd[u]] = ee[u]; }
+        }
+        __syncwarp();
+        for (uint32_t p0 = lane; p0 < n; p0 += 32 * AF_U) {
+            uint32_t ee[AF_U];
+            #pragma unroll
+            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) ee[u] = idx2[p]; }
+            #pragma unroll
+            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) idx[p] = ee[u]; }
+        }
+        __syncwarp();
+    }
+    if (a.shift > 0) {
+        uint32_t mid = 0;   /* digits (bit per owned digit) whose sub-bucket has 9..64 elements: sorted by the whole warp afterwards */
+        for (uint32_t d = lane; d < 256; d += 32) {
+            const uint32_t c = cnt[d];
+            if (c > LQ_RS_MIN) { const uint32_t at = atomicAdd(a.n_nxt, 1u); a.nxt[at].beg = beg + start[d]; a.nxt[at].end = beg + start[d] + c; }
+            else if (c > 8) mid |= 1u << (d >> 5);
+            else if (c > 1) lq_af_insertion(idx + start[d], c, a.sx);
+        }
+        __syncwarp();
+        for (uint32_t l = 0; l < 32; ++l) {
+            uint32_t m = __shfl_sync(0xffffffffu, mid, l);
+            while (m) { const uint32_t d = (uint32_t)(__ffs(m) - 1) * 32 + l; m &= m - 1; af_warp_ranksort(idx + start[d], cnt[d], a.sx, lane); }
+        }
+    }
+    __syncwarp();
+}
 __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
 {
     __shared__ uint32_t s_cnt[AF_WARPS][256], s_start[AF_WARPS][256], s_head[AF_WARPS][256];
@@ -256,37 +314,75 @@ __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
             }
             __syncwarp();
         } else if (nb > 2) {
-            if (lane == 0) { lq_af_walk(dig, n, cnt, start, head, dest); atomicAdd(a.n_walk, 1u); }
+            /* tied keys and more than two digits: the sequential walk, done by lq_af_walk_k with a digit cache */
+            if (lane == 0) { const uint32_t at = atomicAdd(a.n_wlist, 1u); a.wlist[at].beg = beg; a.wlist[at].end = beg + n; }
+            __syncwarp();
+            continue;
+        }
+        af_finish_bucket(a, beg, n, nb, cnt, start, idx, idx2, dest, lane);
+    }
+}
+
+/* The walk of lq_afsort_core.h with the digits streamed through shared memory: region c's next 16 digits sit in cache[c],
+ * refilled with one 16-byte load when exhausted, so a step costs shared-memory latency instead of a global byte load. */
+#define AFW_WARPS 2
+__global__ void __launch_bounds__(AFW_WARPS * 32) lq_af_walk_k(AfArgs a)
+{
+    __shared__ uint32_t s_cnt[AFW_WARPS][256], s_start[AFW_WARPS][256], s_head[AFW_WARPS][256], s_tag[AFW_WARPS][256];
+    __shared__ uint4 s_cache[AFW_WARPS][256];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lt = (1u << lane) - 1;
+    uint32_t *cnt = s_cnt[wid], *start = s_start[wid], *head = s_head[wid], *tag = s_tag[wid];
+    uint4 *cache = s_cache[wid];
+    const uint32_t nw = *a.n_wlist;
+    for (;;) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(a.wcursor, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= nw) break;
+        const uint32_t beg = a.wlist[b].beg, n = a.wlist[b].end - beg;
+        uint32_t *idx = a.idx + beg, *idx2 = a.idx2 + beg, *dest = a.dest + beg;
+        const uint8_t *dig = a.dig + beg;
+        /* histogram from the digits the level kernel stored */
+        for (uint32_t d = lane; d < 256; d += 32) { cnt[d] = 0; tag[d] = 0xffffffffu; head[d] = 0; }
+        __syncwarp();
+        for (uint32_t p0 = 0; p0 < n; p0 += 32) {
+            const uint32_t p = p0 + lane; const bool ok = p < n;
+            const uint32_t act = __ballot_sync(0xffffffffu, ok);
+            if (ok) { const uint32_t d = dig[p]; const uint32_t peers = __match_any_sync(act, d); if ((peers & lt) == 0) cnt[d] += __popc(peers); }
             __syncwarp();
         }
-        /* 4. permute the payload (indices into the seed arrays) */
-        if (nb > 1) {
-            for (uint32_t p0 = lane; p0 < n; p0 += 32 * AF_U) {
-                uint32_t dd[AF_U], ee[AF_U];
-                #pragma unroll
-                for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) { dd[u] = dest[p]; ee[u] = idx[p]; } }
-                #pragma unroll
-                for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) idx2[dd[u]] = ee[u]; }
+        uint32_t loc = 0, ne = 0;
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) { const uint32_t c = cnt[8 * lane + j]; loc += c; if (c) ++ne; }
+        uint32_t inc = lq_warp_incl_scan(loc), run = inc - loc;
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) { start[8 * lane + j] = run; run += cnt[8 * lane + j]; }
+        const uint32_t nb = lq_warp_sum(ne);
+        __syncwarp();
+        if (lane == 0) {
+            /* == lq_af_walk(), digit fetch through the cache */
+            const uint8_t *dbase = a.dig;                 /* 256-byte aligned arena pointer: 16-byte chunks of it are aligned */
+            uint32_t k = 0, c, arrived_k = 0;
+            while (k < 256 && cnt[k] == 0) ++k;
+            c = k;
+            for (uint32_t step = 0; step < n; ++step) {
+                const uint32_t p = start[c] + head[c];
+                const uint32_t ab = beg + p, ch = ab >> 4;
+                if (tag[c] != ch) { cache[c] = *(const uint4*)(dbase + ((size_t)ch << 4)); tag[c] = ch; }
+                const uint32_t d = ((const uint8_t*)&cache[c])[ab & 15];
+                ++head[c];
+                if (d == k) dest[p] = start[k] + arrived_k++;
+                else dest[p] = start[d] + head[d];
+                c = d;
+                if (c == k && head[k] == cnt[k]) {
+                    do { ++k; } while (k < 256 && head[k] == cnt[k]);
+                    if (k < 256) { c = k; arrived_k = head[k]; }
+                }
             }
-            __syncwarp();
-            for (uint32_t p0 = lane; p0 < n; p0 += 32 * AF_U) {
-                uint32_t ee[AF_U];
-                #pragma unroll
-                for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) ee[u] = idx2[p]; }
-                #pragma unroll
-                for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) idx[p] = ee[u]; }
-            }
-            __syncwarp();
-        }
-        /* 5. sub-buckets (ksort.h:124-133) */
-        if (a.shift > 0) {
-            for (uint32_t d = lane; d < 256; d += 32) {
-                const uint32_t c = cnt[d];
-                if (c > LQ_RS_MIN) { const uint32_t at = atomicAdd(a.n_nxt, 1u); a.nxt[at].beg = beg + start[d]; a.nxt[at].end = beg + start[d] + c; }
-                else if (c > 1) lq_af_insertion(idx + start[d], c, a.sx);
-            }
+            atomicAdd(a.n_walk, 1u);
         }
         __syncwarp();
+        af_finish_bucket(a, beg, n, nb, cnt, start, idx, idx2, dest, lane);
     }
 }
 
@@ -727,8 +823,9 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     }
     /* bucket lists: at most nb/65 + nqb live buckets per level */
     const size_t bcap = (size_t)(nb / (LQ_RS_MIN + 1)) + nqb + 16;
-    LQ_TRY(sc->bkt.ensure(2 * bcap * sizeof(AfBkt)));
+    LQ_TRY(sc->bkt.ensure(3 * bcap * sizeof(AfBkt)));
     AfBkt *bk[2] = { sc->bkt.as<AfBkt>(), sc->bkt.as<AfBkt>() + bcap };
+    AfBkt *wl = sc->bkt.as<AfBkt>() + 2 * bcap;
     /* counters: ctr[0],ctr[1] = bucket counts of the two lists, ctr[2] = cursor, ctr[3] = walks */
     lq_prof_count_launch(2);
     lq_iota_k<<<lq_grid(nb, 256), 256, 0, st>>>(b->idx, nb);
@@ -739,11 +836,16 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         AfArgs a;
         a.sx = b->s.sx; a.sq = b->s.sq; a.idx = b->idx; a.idx2 = b->idx2; a.dest = b->dest; a.dig = b->dig;
         a.cur = bk[cur]; a.n_cur = ctr + cur; a.nxt = bk[cur ^ 1]; a.n_nxt = ctr + (cur ^ 1); a.cursor = ctr + 2; a.n_walk = ctr + 3; a.shift = shift;
+        a.wlist = wl; a.n_wlist = ctr + 9; a.wcursor = ctr + 10;
         LQ_CUDA_OK(cudaMemsetAsync(ctr + (cur ^ 1), 0, 4, st));
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 2, 0, 4, st));
+        LQ_CUDA_OK(cudaMemsetAsync(ctr + 9, 0, 8, st));
         static const char *lvl_name[8] = { "seed_sort_s0", "seed_sort_s8", "seed_sort_s16", "seed_sort_s24", "seed_sort_s32", "seed_sort_s40", "seed_sort_s48", "seed_sort_s56" };
         { LqProfScope ps(lvl_name[shift >> 3], st, 1, 0);
           lq_af_level_k<<<148 * 16, AF_WARPS * 32, 0, st>>>(a); }
+        static const char *wlk_name[8] = { "seed_walk_s0", "seed_walk_s8", "seed_walk_s16", "seed_walk_s24", "seed_walk_s32", "seed_walk_s40", "seed_walk_s48", "seed_walk_s56" };
+        { LqProfScope ps(wlk_name[shift >> 3], st, 1, 0);
+          lq_af_walk_k<<<148 * 16, AFW_WARPS * 32, 0, st>>>(a); }
         LQ_CUDA_OK(cudaGetLastError());
         cur ^= 1;
     }
