@@ -21,6 +21,8 @@
 #include "lqcov.h"
 #include "lq_prof.h"
 
+int lq_qualsum_run(const uint8_t *d_qual, const uint64_t *d_off, uint32_t n_reads, double *d_sum, cudaStream_t st);
+
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct lqcov_ctx {
@@ -30,14 +32,14 @@ struct lqcov_ctx {
     uint32_t nq;
     std::vector<std::string> qname;
     std::vector<int> qlen;
-    std::vector<char> qqual; std::vector<uint64_t> qqual_off; bool q_has_qual;
+    std::vector<double> qsum_p; bool q_has_qual;   /* ordered error-probability sums of the query qualities (device) */
     /* query names -> query indices: open-address table over (pointer, length) keys, chained for duplicate names */
     std::vector<int32_t> qn_slot, qn_next; uint32_t qn_mask;
     std::vector<uint64_t> qfirst;
     std::vector<lqh_sub_v> ovlp;        /* ovlp_coords (minimap2-coverage.c:438-444) */
     std::vector<float> avg_k;           /* avg_ks */
     /* device */
-    LqQueryDev qd; LqIndexDev ix; LqMapScratch sc; LqReadsDev treads; LqMinimizers tmins, full; LqDevBuf ws; bool use_full;
+    LqQueryDev qd; LqIndexDev ix; LqMapScratch sc; LqReadsDev treads; LqMinimizers tmins, full; LqDevBuf ws, qual_dev, qsum_dev; bool use_full;
     /* current part */
     std::vector<uint32_t> self_off, self_list, qrank, trank;
     bool part_ready;
@@ -92,7 +94,7 @@ extern "C" void lqcov_destroy(lqcov_ctx *c)
     if (!c) return;
     cudaStreamSynchronize(c->st);
     for (size_t i = 0; i < c->ovlp.size(); ++i) free(c->ovlp[i].a);
-    c->qd.release(); c->ix.release(); c->sc.release(); c->treads.release(); c->tmins.release(); c->full.release(); c->ws.release();
+    c->qd.release(); c->ix.release(); c->sc.release(); c->treads.release(); c->tmins.release(); c->full.release(); c->ws.release(); c->qual_dev.release(); c->qsum_dev.release();
     cudaStreamDestroy(c->st);
     delete c;
 }
@@ -136,8 +138,7 @@ extern "C" int lqcov_set_queries(lqcov_ctx *c, const lqcov_reads_t *q)
     }
     qnames_build(c);
     c->q_has_qual = q->qual != 0;
-    c->qqual_off.assign(q->seq_off, q->seq_off + q->n + 1);
-    if (q->qual && q->n) c->qqual.assign(q->qual + q->seq_off[0], q->qual + q->seq_off[q->n]); else c->qqual.clear();
+    c->qsum_p.assign(q->n, 0.0);
     for (size_t i = 0; i < c->ovlp.size(); ++i) free(c->ovlp[i].a);
     c->ovlp.assign(q->n, lqh_sub_v());
     for (uint32_t i = 0; i < q->n; ++i) { c->ovlp[i].n = c->ovlp[i].m = 0; c->ovlp[i].a = 0; }
@@ -149,6 +150,14 @@ extern "C" int lqcov_set_queries(lqcov_ctx *c, const lqcov_reads_t *q)
     qd->n_min = qd->mins.n;
     LQ_TRY(lq_read_first(&qd->mins, 0, q->n, qd->first, c->st));
     LQ_TRY(lq_map_flag_dups(qd, 2 * c->opt.k, c->ws, c->st));
+    if (q->qual && q->n) { /* meanQ of the table rows (lqutils.c:51-58): the additions must happen in read order, one thread per read */
+        const uint64_t nbq = q->seq_off[q->n] - q->seq_off[0];
+        LQ_TRY(c->qual_dev.ensure(nbq + 16)); LQ_TRY(c->qsum_dev.ensure(((size_t)q->n + 1) * 8));
+        LQ_CUDA_OK(cudaMemcpyAsync(c->qual_dev.p, q->qual + q->seq_off[0], nbq, cudaMemcpyHostToDevice, c->st)); lq_prof_h2d(nbq);
+        /* qd->reads.off holds the absolute offsets; the copy starts at seq_off[0] */
+        LQ_TRY(lq_qualsum_run(c->qual_dev.as<uint8_t>() - q->seq_off[0], qd->reads.off.as<uint64_t>(), q->n, c->qsum_dev.as<double>(), c->st));
+        LQ_CUDA_OK(cudaMemcpyAsync(c->qsum_p.data(), c->qsum_dev.p, (size_t)q->n * 8, cudaMemcpyDeviceToHost, c->st)); lq_prof_d2h((uint64_t)q->n * 8);
+    }
     c->qfirst.resize((size_t)q->n + 1);
     LQ_CUDA_OK(cudaMemcpyAsync(c->qfirst.data(), qd->first.p, ((size_t)q->n + 1) * 8, cudaMemcpyDeviceToHost, c->st));
     LQ_TRY(qd->lambda.ensure(((size_t)q->n + 1) * 8)); LQ_TRY(qd->lambda2.ensure(((size_t)q->n + 1) * 8));
@@ -228,6 +237,7 @@ extern "C" int lqcov_part_finish(lqcov_ctx *c, const lqcov_reads_t *part)
     LQ_CUDA_OK(cudaStreamSynchronize(c->st));
     c->stats.t_index_ms += now_ms() - t0;
     /* name tables for the self-diagonal / dual-mapping skips (lqmap.c:180-189) */
+    const double t_names = now_ms();
     const uint32_t nq = c->nq;
     /* (query, target) pairs with equal names, then CSR by query with ascending target ids */
     std::vector<std::pair<uint32_t, uint32_t> > hits;
@@ -257,7 +267,7 @@ extern "C" int lqcov_part_finish(lqcov_ctx *c, const lqcov_reads_t *part)
     c->part_ready = true;
     c->stats.target_minimizers += ix->n_rec;
     c->stats.n_parts += 1; c->stats.mid_occ = c->mid_occ;
-    c->stats.t_post_ms += now_ms() - t0 - 0.0;
+    c->stats.t_post_ms += now_ms() - t_names;
     if (c->opt.verbose >= 3) fprintf(stderr, "[M::lqcov] loaded/built the index for %u target sequence(s)\n", part->n);
     return 0;
 }
@@ -353,8 +363,7 @@ extern "C" int lqcov_table(lqcov_ctx *c, char **buf, size_t *len)
             fprintf(stderr, "[lqcov] ERROR: query '%s' yields no minimizer; the reference binary crashes on such input\n", c->qname[q].c_str());
             free(out.s); return -1;
         }
-        const char *qual = c->q_has_qual ? c->qqual.data() + (c->qqual_off[q] - c->qqual_off[0]) : 0;
-        lqh_format_row(&out, c->qname[q].data(), c->qname[q].size(), c->qlen[q], qual, lam[q], lam2[q], n_mini, n_match[q], c->avg_k[q],
+        lqh_format_row(&out, c->qname[q].data(), c->qname[q].size(), c->qlen[q], c->q_has_qual, c->qsum_p[q], lam[q], lam2[q], n_mini, n_match[q], c->avg_k[q],
                        &c->ovlp[q], c->opt.min_coverage, c->opt.filter);
     }
     if (!out.s) { out.s = (char*)malloc(1); out.s[0] = 0; }

@@ -25,7 +25,8 @@ double lqh_meanQ(const char *qual, int len);
 double lqh_q2p(int q);            /* entry q of the reference's Phred->probability table */
 int lqh_getQV(const char *qual, int threshold, int len);
 /* minimap2-coverage.c:552-604: one table row */
-void lqh_format_row(lqh_str *out, const char *name, size_t name_len, int len, const char *qual, uint64_t lambda, uint64_t lambda2,
+/* has_qual: sum_p is the ordered sum of the read's error probabilities (computed on the device); else the row prints -nan */
+void lqh_format_row(lqh_str *out, const char *name, size_t name_len, int len, int has_qual, double sum_p, uint64_t lambda, uint64_t lambda2,
                     uint32_t n_mini, uint32_t n_match, float avg_k, const lqh_sub_v *ovlp, int min_cov, int filter);
 /* sdust.c:211-217 */
 void lqh_format_sdust_row(lqh_str *out, const char *name, size_t name_len, uint32_t masked, int len, const char *qual, double sum_p, int n_q7);

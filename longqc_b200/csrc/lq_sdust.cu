@@ -43,6 +43,27 @@ __global__ void lq_sdust_k(const uint8_t *__restrict__ seq, const uint8_t *__res
     }
 }
 
+/* per read: the ordered sum of error probabilities (lqutils.c:54-56) -- also used for the query rows of the coverage table */
+__global__ void lq_qualsum_k(const uint8_t *__restrict__ qual, const uint64_t *__restrict__ off, uint32_t n_reads, double *__restrict__ sum_p)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    double acc = 0.0;
+    for (uint64_t i = off[r]; i < off[r + 1]; ++i) { const int q = (int)(signed char)qual[i] - 33; acc += c_q2p[q < 0 ? 0 : q > 126 ? 126 : q]; }
+    sum_p[r] = acc;
+}
+
+int lq_qualsum_run(const uint8_t *d_qual, const uint64_t *d_off, uint32_t n_reads, double *d_sum, cudaStream_t st)
+{
+    double h_q2p[127];
+    for (int q = 0; q < 127; ++q) h_q2p[q] = lqh_q2p(q);
+    LQ_CUDA_OK(cudaMemcpyToSymbolAsync(c_q2p, h_q2p, sizeof(h_q2p), 0, cudaMemcpyHostToDevice, st));
+    if (n_reads) lq_qualsum_k<<<lq_grid(n_reads, 64), 64, 0, st>>>(d_qual, d_off, n_reads, d_sum);
+    LQ_CUDA_OK(cudaGetLastError());
+    lq_prof_count_launch(1);
+    return 0;
+}
+
 extern "C" int lqcov_sdust_table(const lqcov_opt_t *o, const lqcov_reads_t *reads, int W, int T, char **buf, size_t *len)
 {
     *buf = 0; *len = 0;

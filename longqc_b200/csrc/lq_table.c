@@ -138,13 +138,13 @@ static void put_regions(lqh_str *out, const lqh_sub_v *r)
     for (j = 0; j < r->n; ++j) lqh_str_printf(out, "%s%d-%d", j ? "," : "", r->a[j].start, r->a[j].end);
 }
 
-void lqh_format_row(lqh_str *out, const char *name, size_t name_len, int len, const char *qual, uint64_t lambda, uint64_t lambda2,
+void lqh_format_row(lqh_str *out, const char *name, size_t name_len, int len, int has_qual, double sum_p, uint64_t lambda, uint64_t lambda2,
                     uint32_t n_mini, uint32_t n_match, float avg_k, const lqh_sub_v *ovlp, int min_cov, int filter)
 {
     lqh_sub_v reg = { 0, 0, 0 }, mreg = { 0, 0, 0 };
     /* minimap2-coverage.c:563: float log of a float ratio, divided by the float mean k-mer span */
     const double div = n_match > 0 ? logf((float)n_mini / n_match) / avg_k : 1.0;
-    const double mq = lqh_meanQ(qual, qual ? len : 0);
+    const double mq = has_qual ? -10 * log10(sum_p / len) : lqh_meanQ(NULL, 0);   /* lqutils.c:57; FASTA: 0/0 -> -nan */
     uint32_t tot = 0; size_t j;
     lqh_reliable_region(ovlp, (uint32_t)min_cov, &reg, &mreg);
     for (j = 0; j < reg.n; ++j) tot += reg.a[j].end - reg.a[j].start;

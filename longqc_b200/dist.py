@@ -94,6 +94,73 @@ def _sub_struct(keep, a: int, b: int, seq_ptr, on_device: int):
     return st
 
 
+def run_job(cov, t_keep, n_my_targets, my_lo, parts, part_meta, q_keep, n_my_queries, tptr, qptr, on_device, rank, world, exchange=None):
+    """One coverage job of this rank: its queries against every index part; targets [my_lo, my_lo+n_my_targets) of the global
+    read list are this rank's to sketch.  Returns the table (all ranks' rows on rank 0 when world > 1)."""
+    lib = _lib.load()
+    lib.lqcov_part_sketch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.lqcov_part_finish.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lqcov_map_part.argtypes = [C.c_void_p]
+    lib.lqcov_part_device_views.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    lib.lqcov_part_gather_buffers.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    h = cov._h
+    lib.lqcov_reset(h)
+    qs = _sub_struct(q_keep, 0, n_my_queries, qptr, on_device)
+    qs.qual = q_keep.st.qual
+    if lib.lqcov_set_queries(h, C.byref(qs)) != 0:
+        raise _lib.LqcovError("lqcov_set_queries failed")
+    my_hi = my_lo + n_my_targets
+    for (s, e), meta in zip(parts, part_meta):
+        a, b = max(s, my_lo), min(e, my_hi)                # my reads inside this part
+        if b < a:
+            a = b = max(min(s, my_hi), my_lo)
+        sub = _sub_struct(t_keep, a - my_lo, b - my_lo, tptr, on_device)
+        if lib.lqcov_part_sketch(h, C.byref(sub), a - s if b > a else 0) != 0:
+            raise _lib.LqcovError("lqcov_part_sketch failed")
+        if world > 1:
+            exchange(lib, h)
+        if lib.lqcov_part_finish(h, C.byref(meta.st)) != 0:
+            raise _lib.LqcovError("lqcov_part_finish failed")
+        if lib.lqcov_map_part(h) != 0:
+            raise _lib.LqcovError("lqcov_map_part failed")
+    table = cov.table()
+    if world > 1:
+        import torch.distributed as dist
+        rows = [None] * world if rank == 0 else None
+        dist.gather_object(table, rows, dst=0)
+        if rank == 0:
+            table = b"".join(rows)
+    return table
+
+
+def exchange_part(lib, h, rank, world):
+    """all-reduce of the minimizer counts + rank-ordered replication of the records (see module docstring)"""
+    import torch
+    import torch.distributed as dist
+    counts, nc, key, y, n = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_void_p(), C.c_uint64()
+    lib.lqcov_part_device_views(h, C.byref(counts), C.byref(nc), C.byref(key), C.byref(y), C.byref(n))
+    tc = _view(counts.value, nc.value, "<i4")
+    dist.all_reduce(tc)                                   # the minimizer-count all-reduce
+    sizes = torch.zeros(world, dtype=torch.int64, device="cuda")
+    sizes[rank] = n.value
+    dist.all_reduce(sizes)
+    sizes = sizes.tolist()
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    fk, fy = C.c_void_p(), C.c_void_p()
+    if lib.lqcov_part_gather_buffers(h, int(offs[-1]), C.byref(fk), C.byref(fy)) != 0:
+        raise _lib.LqcovError("lqcov_part_gather_buffers failed")
+    full_k = _view(fk.value, max(int(offs[-1]), 1), "<i4")
+    full_y = _view(fy.value, max(int(offs[-1]), 1), "<i8")
+    if n.value:
+        full_k[offs[rank]:offs[rank + 1]].copy_(_view(key.value, n.value, "<i4"))
+        full_y[offs[rank]:offs[rank + 1]].copy_(_view(y.value, n.value, "<i8"))
+    for r in range(world):                                # index replication: rank-ordered all-gather
+        if sizes[r]:
+            dist.broadcast(full_k[offs[r]:offs[r + 1]], src=r)
+            dist.broadcast(full_y[offs[r]:offs[r + 1]], src=r)
+    torch.cuda.synchronize()
+
+
 class Runner:
     """One rank of the (possibly multi-GPU) coverage job on the synthetic workload of bench.py."""
 
@@ -156,69 +223,13 @@ class Runner:
         return "%d GPUs: targets sharded for sketch+count, NCCL all-reduce of the 4^k count table, index replicated (records broadcast in rank order), queries sharded" % self.world
 
     def _exchange(self, lib, h):
-        import torch
-        import torch.distributed as dist
-        counts, nc, key, y, n = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_void_p(), C.c_uint64()
-        lib.lqcov_part_device_views(h, C.byref(counts), C.byref(nc), C.byref(key), C.byref(y), C.byref(n))
-        tc = _view(counts.value, nc.value, "<i4")
-        dist.all_reduce(tc)                                   # the minimizer-count all-reduce
-        sizes = torch.zeros(self.world, dtype=torch.int64, device="cuda")
-        sizes[self.rank] = n.value
-        dist.all_reduce(sizes)
-        sizes = sizes.tolist()
-        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-        fk, fy = C.c_void_p(), C.c_void_p()
-        if lib.lqcov_part_gather_buffers(h, int(offs[-1]), C.byref(fk), C.byref(fy)) != 0:
-            raise _lib.LqcovError("lqcov_part_gather_buffers failed")
-        full_k = _view(fk.value, max(int(offs[-1]), 1), "<i4")
-        full_y = _view(fy.value, max(int(offs[-1]), 1), "<i8")
-        if n.value:
-            full_k[offs[self.rank]:offs[self.rank + 1]].copy_(_view(key.value, n.value, "<i4"))
-            full_y[offs[self.rank]:offs[self.rank + 1]].copy_(_view(y.value, n.value, "<i8"))
-        for r in range(self.world):                           # index replication: rank-ordered all-gather
-            if sizes[r]:
-                dist.broadcast(full_k[offs[r]:offs[r + 1]], src=r)
-                dist.broadcast(full_y[offs[r]:offs[r + 1]], src=r)
-        torch.cuda.synchronize()
+        exchange_part(lib, h, self.rank, self.world)
 
     def step(self, resident: bool):
-        lib = _lib.load()
-        lib.lqcov_part_sketch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
-        lib.lqcov_part_finish.argtypes = [C.c_void_p, C.c_void_p]
-        lib.lqcov_map_part.argtypes = [C.c_void_p]
-        lib.lqcov_reset.argtypes = [C.c_void_p]
-        lib.lqcov_part_device_views.argtypes = [C.c_void_p] + [C.c_void_p] * 5
-        lib.lqcov_part_gather_buffers.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
-        h = self.cov._h
-        lib.lqcov_reset(h)
         tptr = self.t_dev.data_ptr() if resident else self.t_pin.data_ptr()
         qptr = self.q_dev.data_ptr() if resident else self.q_pin.data_ptr()
-        qs = _sub_struct(self.q_keep, 0, self.queries.n, qptr, 1 if resident else 0)
-        qs.qual = self.q_keep.st.qual
-        if lib.lqcov_set_queries(h, C.byref(qs)) != 0:
-            raise _lib.LqcovError("lqcov_set_queries failed")
-        my_lo = self.rank * self.a.reads
-        my_hi = my_lo + self.targets.n
-        for (s, e), meta in zip(self.parts, self.part_meta):
-            a, b = max(s, my_lo), min(e, my_hi)                # my reads inside this part
-            if b < a:
-                a = b = max(min(s, my_hi), my_lo)
-            sub = _sub_struct(self.t_keep, a - my_lo, b - my_lo, tptr, 1 if resident else 0)
-            if lib.lqcov_part_sketch(h, C.byref(sub), a - s if b > a else 0) != 0:
-                raise _lib.LqcovError("lqcov_part_sketch failed")
-            if self.world > 1:
-                self._exchange(lib, h)
-            if lib.lqcov_part_finish(h, C.byref(meta.st)) != 0:
-                raise _lib.LqcovError("lqcov_part_finish failed")
-            if lib.lqcov_map_part(h) != 0:
-                raise _lib.LqcovError("lqcov_map_part failed")
-        table = self.cov.table()
-        if self.world > 1:
-            import torch.distributed as dist
-            rows = [None] * self.world if self.rank == 0 else None
-            dist.gather_object(table, rows, dst=0)
-            if self.rank == 0:
-                table = b"".join(rows)
+        table = run_job(self.cov, self.t_keep, self.targets.n, self.rank * self.a.reads, self.parts, self.part_meta, self.q_keep, self.queries.n,
+                        tptr, qptr, 1 if resident else 0, self.rank, self.world, exchange=self._exchange)
         self.last_stats = self.cov.stats()
         self.last_table = table
         return table
