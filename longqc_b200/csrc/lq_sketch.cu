@@ -277,6 +277,174 @@ __global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
     }
 }
 
+
+/* ------------------------------------------------------------------ K1, rolling form (w = 5 or 10, k <= 15: LongQC's settings)
+ *
+ * One thread owns RK_SEG = 64 consecutive bases of a read and runs the reference scan itself, with the k-mer registers
+ * rolled base by base and the ring of the last W candidates held in registers as a shift register (oldest first).
+ * It starts RK_WU = 32 bases early with an empty state and emits nothing until its state is CERTIFIED equal to the
+ * reference's:
+ *   - a segment that starts within RK_WU bases of the read start begins at base 0 in the true initial state;
+ *   - otherwise `good` counts the ring pushes made since the registers became exact (k unambiguous bases consumed) and
+ *     since the last ambiguous base: once good >= w+k the true run counter is >= w+k (all gates of sketch.c:116-137 open),
+ *     the ring holds only pushes made in that stretch, all valid -- the state the reference has (lq_sketch_core.h, fact 1);
+ *   - an ambiguous base met with exact registers resets the run counter to 0 in both, which is exact from then on.
+ * Bases of the segment reached before certification (a palindromic k-mer or an N inside the warm-up: rare) take the
+ * bounded replay (sk_slow).  Records wait in shared memory (transposed, conflict-free) until the CTA's output offset is
+ * known from the look-back; a thread that emits more than RK_CAP records makes the CTA re-run the scan writing directly. */
+#define RK_SEG 64
+#define RK_WU 32
+#define RK_THREADS 128
+#define RK_CAP 32
+#define RK_TILE (RK_SEG * RK_THREADS)
+
+template <int W, int MODE /* 0: buffer in smem, 1: write directly at `wat` */>
+__device__ __forceinline__ int rk_scan(const SkArgs &a, uint32_t rd, uint64_t g0, int L, int i0, int i1 /* segment [i0,i1) */,
+                                       uint2 *s_rec, int tid, uint64_t wat)
+{
+    const int w = W, k = a.k;
+    const uint32_t mask = (1u << 2 * k) - 1, top = 2 * (k - 1);
+    const uint32_t MAXH = 0xffffffffu;
+    const uint32_t rid = a.rid_base + rd;
+    uint32_t wx[W], wp[W];                 /* ring as a shift register: [0] oldest ... [W-1] newest; wp = pos<<1|strand */
+    #pragma unroll
+    for (int j = 0; j < W; ++j) { wx[j] = MAXH; wp[j] = MAXH; }
+    uint32_t mx = MAXH, mp = MAXH; int mi = 0;   /* running minimum (copy) and its index in the shift register */
+    uint32_t fw = 0, rv = 0;
+    const int p0 = i0 - RK_WU > 0 ? i0 - RK_WU : 0;
+    int run = 0;                           /* the reference's l when exact, else a lower bound */
+    int nb = p0 == 0 ? 1 << 20 : 0;        /* unambiguous bases consumed (registers exact once nb >= k) */
+    int good = p0 == 0 ? 1 << 20 : 0;
+    bool cert = p0 == 0, lexact = p0 == 0;
+    int n = 0;
+    bool last_slow = false;
+    lq_sk_buf sbuf;
+    #define RK_EMIT(H_, P_) do { if (MODE == 0) { if (n < RK_CAP) s_rec[n * RK_THREADS + tid] = make_uint2((H_), (P_)); } \
+                                 else { a.out_key[wat + n] = (H_); a.out_y[wat + n] = (uint64_t)rid << 32 | (P_); } ++n; } while (0)
+    uint32_t wb = 0, wn = 0;               /* current packed words */
+    for (int i = p0; i < i1; ++i) {
+        const uint64_t g = g0 + (uint64_t)i;
+        if ((i & 15) == 0 || i == p0) wb = a.b2[g >> 4];
+        if ((i & 31) == 0 || i == p0) wn = a.nm[g >> 5];
+        const uint32_t c = (wb >> ((i & 15) * 2)) & 3u;
+        const bool amb = (wn >> (i & 31)) & 1u;
+        const bool out = i >= i0;
+        const bool use_slow = out && !cert;
+        if (i == i1 - 1) last_slow = use_slow;
+        if (use_slow) {                    /* not certified yet: this base's records come from the bounded replay */
+            sk_slow(a.b2, a.nm, g0, L, w, k, rid, i, &sbuf);
+            for (int j = 0; j < sbuf.n; ++j) RK_EMIT((uint32_t)(sbuf.x[j] >> 8), (uint32_t)sbuf.y[j]);
+        }
+        uint32_t cx = MAXH, cp = MAXH;
+        if (!amb) {
+            fw = (fw << 2 | c) & mask;
+            rv = rv >> 2 | (3u ^ c) << top;
+            ++nb;
+            if (fw == rv) continue;                    /* sketch.c:107 */
+            const uint32_t z = fw < rv ? 0u : 1u;
+            ++run;
+            if (nb >= k) ++good; else good = 0;
+            if (run >= k) { cx = lq_hash32(z ? rv : fw, mask); cp = (uint32_t)i << 1 | z; }
+        } else {
+            if (nb >= k) { cert = true; lexact = true; }   /* registers exact: the reset is exact */
+            run = 0; good = 0;
+        }
+        if (!lexact && good >= w + k) { cert = true; }
+        const int l = (lexact || !cert) ? run : (run > w + k ? run : w + k);   /* certified by `good`: every gate is open */
+        const bool em = out && !use_slow;      /* certified at the top of this step */
+        /* the slot being overwritten is wx[0]; (A) first full window, sketch.c:116-121: entries older than the newcomer */
+        if (l == w + k - 1 && mx != MAXH) {
+            #pragma unroll
+            for (int j = 1; j < W; ++j) if (wx[j] == mx && wp[j] != mp && em) RK_EMIT(wx[j], wp[j]);
+        }
+        if (cx <= mx) {                                 /* sketch.c:122-124 */
+            if (l >= w + k && mx != MAXH && em) RK_EMIT(mx, mp);
+            mx = cx; mp = cp; mi = W;                   /* index after the shift below: W-1 */
+        } else if (mi == 0) {                           /* sketch.c:125-137: the minimum's slot is overwritten */
+            if (l >= w + k - 1 && mx != MAXH && em) RK_EMIT(mx, mp);
+            mx = MAXH; mp = MAXH; mi = 1;
+            #pragma unroll
+            for (int j = 1; j < W; ++j) if (mx >= wx[j]) { mx = wx[j]; mp = wp[j]; mi = j; }
+            if (mx >= cx) { mx = cx; mp = cp; mi = W; }
+            if (l >= w + k - 1 && mx != MAXH) {
+                #pragma unroll
+                for (int j = 1; j < W; ++j) if (wx[j] == mx && wp[j] != mp && em) RK_EMIT(wx[j], wp[j]);
+                if (cx == mx && cp != mp && em) RK_EMIT(cx, cp);
+            }
+        }
+        #pragma unroll
+        for (int j = 0; j + 1 < W; ++j) { wx[j] = wx[j + 1]; wp[j] = wp[j + 1]; }
+        wx[W - 1] = cx; wp[W - 1] = cp;
+        --mi;
+    }
+    if (i1 == L && !last_slow) {           /* sketch.c:140-141; a last base that took the replay already got this record from it */
+        if (mx != MAXH) RK_EMIT(mx, mp);
+    }
+    #undef RK_EMIT
+    return n;
+}
+
+template <int W>
+__global__ void __launch_bounds__(RK_THREADS) lq_sketch_roll_k(SkArgs a)
+{
+    __shared__ uint2 s_rec[RK_CAP * RK_THREADS];       /* 32 KB */
+    __shared__ uint64_t scan_sm[33];
+    __shared__ uint32_t s_tile; __shared__ uint64_t s_base; __shared__ int s_over;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_tile = atomicAdd(a.ticket, 1u); s_over = 0; }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t g = ((uint64_t)tile * RK_THREADS + tid) * RK_SEG;   /* global base index of the segment */
+    const uint64_t slot = g >> 7;
+    uint32_t rd = 0; uint64_t g0 = 0; int L = 0, i0 = 0, i1 = 0;
+    if (slot < a.n_slots) {
+        rd = a.slot_read[slot];
+        const uint64_t s0 = a.slot0[rd];
+        L = (int)a.len[rd]; g0 = s0 * LQ_SLOT;
+        i0 = (int)(slot - s0) * LQ_SLOT + (int)(g & 127);
+        i1 = i0 + RK_SEG < L ? i0 + RK_SEG : L;
+    }
+    int n = 0;
+    if (i0 < i1) n = rk_scan<W, 0>(a, rd, g0, L, i0, i1, s_rec, tid, 0);
+    if (n > RK_CAP) s_over = 1;
+    uint64_t tot;
+    const uint64_t ex = lq_block_excl_scan((uint64_t)n, scan_sm, &tot);
+    /* decoupled look-back (warp 0) */
+    if (tid < 32) {
+        const unsigned long long FLAG_AGG = 1ULL << 62, FLAG_PRE = 2ULL << 62, VMASK = (1ULL << 62) - 1;
+        uint64_t base = 0;
+        if (tile == 0) { if (tid == 0) atomicExch(&a.state[0], FLAG_PRE | tot); }
+        else {
+            if (tid == 0) atomicExch(&a.state[tile], FLAG_AGG | tot);
+            int64_t hi = (int64_t)tile - 1; uint32_t spins = 0;
+            for (;;) {
+                const int64_t j = hi - tid;
+                unsigned long long sv = FLAG_PRE;
+                if (j >= 0) sv = *(volatile unsigned long long*)&a.state[j];
+                const uint32_t ready = __ballot_sync(0xffffffffu, (sv >> 62) != 0);
+                const uint32_t pre = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+                const int stop = pre ? __ffs(pre) - 1 : 31;
+                const uint32_t need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1);
+                if ((ready & need) != need) { __nanosleep(64); if (++spins > (1u << 24)) { if (tid == 0) atomicOr(a.err, 1u); break; } continue; }
+                uint64_t v = (tid <= stop) ? (sv & VMASK) : 0;
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                base += v;
+                if (pre) break;
+                hi -= 32;
+            }
+            if (tid == 0) atomicExch(&a.state[tile], FLAG_PRE | (base + tot));
+        }
+        if (tid == 0) s_base = base;
+    }
+    __syncthreads();
+    const uint64_t at = s_base + ex;
+    if (s_base + tot > a.cap || n == 0) return;
+    if (!s_over) {
+        for (int j = 0; j < n; ++j) { const uint2 r = s_rec[j * RK_THREADS + tid]; a.out_key[at + j] = r.x; a.out_y[at + j] = (uint64_t)(a.rid_base + rd) << 32 | r.y; }
+    } else rk_scan<W, 1>(a, rd, g0, L, i0, i1, s_rec, tid, at);   /* low-complexity tile: scan again, writing in place */
+}
+
 /* ------------------------------------------------------------------ HPC sketch: one thread per read (spike-in run, reference sketch.c:93-104) */
 
 struct SkWriteSpan {
@@ -312,6 +480,10 @@ __global__ void lq_read_first_k(const uint64_t *__restrict__ y, uint64_t n, uint
 }
 
 /* ------------------------------------------------------------------ host side */
+
+/* test switch: force the tiled position-parallel kernel even where the rolling kernel applies (LQCOV_SKETCH_TILED=1) */
+static int g_sketch_tiled = getenv("LQCOV_SKETCH_TILED") ? atoi(getenv("LQCOV_SKETCH_TILED")) : 0;
+extern "C" void lqcov_debug_sketch_tiled(int on) { g_sketch_tiled = on; }
 
 int lq_reads_upload(LqReadsDev *d, const uint8_t *h_seq, const uint64_t *h_off, uint32_t n_reads, int seq_on_device, int sdust_tbl, cudaStream_t st)
 {
@@ -370,7 +542,8 @@ int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_b
     a.ticket = 0; a.state = 0; a.cap = 0; a.err = 0; a.out_key = 0; a.out_y = 0;
     uint64_t total = 0;
     if (!is_hpc) {
-        const unsigned nblk = (unsigned)((rd->n_slots * LQ_SLOT + SK_TILE - 1) / SK_TILE);
+        const bool roll = (w == 5 || w == 10) && k <= 15 && !g_sketch_tiled;
+        const unsigned nblk = roll ? (unsigned)((rd->n_slots * LQ_SLOT + RK_TILE - 1) / RK_TILE) : (unsigned)((rd->n_slots * LQ_SLOT + SK_TILE - 1) / SK_TILE);
         LQ_TRY(out->blk.ensure((size_t)(nblk + 2) * 8 + 64));
         unsigned long long *state = out->blk.as<unsigned long long>();
         uint32_t *ticket = (uint32_t*)(state + nblk + 1), *err = ticket + 1;
@@ -385,8 +558,10 @@ int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_b
             a.out_key = out->key.as<uint32_t>(); a.out_y = out->y.as<uint64_t>();
             {
                 LqProfScope ps("sketch", st, 1, rd->n_slots * (LQ_SLOT_W2 + LQ_SLOT_WN) * 4 + (uint64_t)((double)rd->n_bases * 2.0 / (w + 1)) * 12);
-                if (w == 5) lq_sketch_k<5, 5><<<nblk, SK_THREADS, 0, st>>>(a);              /* LongQC's overlap runs */
-                else if (w == 10) lq_sketch_k<10, 10><<<nblk, SK_THREADS, 0, st>>>(a);      /* LongQC's spike-in run */
+                if (w == 5 && k <= 15 && !g_sketch_tiled) lq_sketch_roll_k<5><<<nblk, RK_THREADS, 0, st>>>(a);        /* LongQC's overlap runs */
+                else if (w == 10 && k <= 15 && !g_sketch_tiled) lq_sketch_roll_k<10><<<nblk, RK_THREADS, 0, st>>>(a); /* LongQC's spike-in run */
+                else if (w == 5) lq_sketch_k<5, 5><<<nblk, SK_THREADS, 0, st>>>(a);
+                else if (w == 10) lq_sketch_k<10, 10><<<nblk, SK_THREADS, 0, st>>>(a);
                 else lq_sketch_k<LQ_MAX_W, 0><<<nblk, SK_THREADS, 0, st>>>(a);
             }
             LQ_CUDA_OK(cudaGetLastError());

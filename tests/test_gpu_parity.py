@@ -26,6 +26,21 @@ def test_sketch_adversarial(w, k):
     assert np.array_equal(x, want["x"]) and np.array_equal(y, want["y"])
 
 
+@pytest.mark.parametrize("w,k", [(5, 12), (10, 15)])
+def test_sketch_tiled_kernel_where_rolling_is_default(w, k):
+    """both exact formulations exist for LongQC's (w,k): the tiled closed form must agree too"""
+    L = _L()
+    rng = np.random.default_rng(77)
+    rs = liblq.reads_from_seqs(liblq.adversarial_seqs(rng, 140, 2500))
+    L.load().lqcov_debug_sketch_tiled(1)
+    try:
+        x, y = L.sketch(rs, L.Opt(w=w, k=k))
+    finally:
+        L.load().lqcov_debug_sketch_tiled(0)
+    want = liblq.oracle_sketch_set(rs, w, k, 0)
+    assert np.array_equal(x, want["x"]) and np.array_equal(y, want["y"])
+
+
 def test_sketch_hpc():
     L = _L()
     rng = np.random.default_rng(5)
