@@ -50,58 +50,86 @@ __global__ void __launch_bounds__(RS_THREADS) lq_rs_hist_k(const uint32_t *__res
     ghist[(uint64_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
 }
 
-/* Stable scatter.  Warp w of the CTA owns records [base + w*512, base + (w+1)*512) and walks them in
- * rows of 32, so "CTA order" == "warp, row, lane" order == input order. */
+/* Stable scatter.  Warp w of the CTA owns records [base + w*512, base + (w+1)*512) and walks them in rows of 32, so
+ * "CTA order" == "warp, row, lane" order == input order.  The CTA's 4096 records are first ordered by digit in shared
+ * memory (stable), then written out run by run, so that consecutive threads store to consecutive addresses. */
+#define RS_SMEM_BYTES (RS_CHUNK * (4 + 8 + 1) + RS_WARPS * 256 * 4 + 256 * 4 + 256 * 8 + 33 * 4 + 64)
 __global__ void __launch_bounds__(RS_THREADS) lq_rs_scatter_k(const uint32_t *__restrict__ key_in, const uint64_t *__restrict__ y_in, const uint8_t *__restrict__ sp_in,
                                                                uint64_t n, int shift, uint32_t nblk, const uint64_t *__restrict__ gbase,
                                                                uint32_t *__restrict__ key_out, uint64_t *__restrict__ y_out, uint8_t *__restrict__ sp_out)
 {
-    __shared__ uint64_t wbase[RS_WARPS][256];
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    uint64_t *s_y = (uint64_t*)rs_smem;                                   /* RS_CHUNK */
+    uint64_t *s_gb = s_y + RS_CHUNK;                                      /* 256: global base of the digit minus its start inside the CTA */
+    uint32_t *s_key = (uint32_t*)(s_gb + 256);                            /* RS_CHUNK */
+    uint32_t (*wbase)[256] = (uint32_t (*)[256])(s_key + RS_CHUNK);       /* RS_WARPS x 256 */
+    uint32_t *s_dstart = (uint32_t*)(wbase + RS_WARPS);                   /* 256 */
+    uint32_t *s_scan = s_dstart + 256;                                    /* 33 */
+    uint8_t *s_sp = (uint8_t*)(s_scan + 36);                              /* RS_CHUNK */
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint64_t base = (uint64_t)blockIdx.x * RS_CHUNK + (uint64_t)wid * (RS_ROWS * 32);
+    const uint64_t blk0 = (uint64_t)blockIdx.x * RS_CHUNK;
+    const uint64_t base = blk0 + (uint64_t)wid * (RS_ROWS * 32);
+    const uint32_t nblkrec = (uint32_t)(n - blk0 < RS_CHUNK ? n - blk0 : RS_CHUNK);
     const uint32_t lt = (1u << lane) - 1;
     for (int d = lane; d < 256; d += 32) wbase[wid][d] = 0;
     __syncwarp();
     /* 1. per-warp digit counts */
+    uint32_t kv[RS_ROWS];
+    #pragma unroll
+    for (int r = 0; r < RS_ROWS; ++r) { const uint64_t i = base + (uint64_t)r * 32 + lane; kv[r] = i < n ? key_in[i] : 0; }
+    #pragma unroll
     for (int r = 0; r < RS_ROWS; ++r) {
         const uint64_t i = base + (uint64_t)r * 32 + lane;
         const bool ok = i < n;
         const uint32_t act = __ballot_sync(0xffffffffu, ok);
         if (ok) {
-            const uint32_t d = (key_in[i] >> shift) & 255u;
+            const uint32_t d = (kv[r] >> shift) & 255u;
             const uint32_t peers = __match_any_sync(act, d);
-            if ((peers & lt) == 0) wbase[wid][d] += (uint64_t)__popc(peers);
+            if ((peers & lt) == 0) wbase[wid][d] += __popc(peers);
         }
         __syncwarp();
     }
     __syncthreads();
-    /* 2. digit d: global base of this CTA, then exclusive prefix over the warps */
+    /* 2. digit d: exclusive prefix over the warps, CTA-wide start of the digit's run, global base */
     {
         const uint32_t d = threadIdx.x;
-        uint64_t run = gbase[(uint64_t)d * nblk + blockIdx.x];
+        uint32_t run = 0;
         #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) { uint64_t t = wbase[w][d]; wbase[w][d] = run; run += t; }
+        for (int w = 0; w < RS_WARPS; ++w) { const uint32_t t = wbase[w][d]; wbase[w][d] = run; run += t; }
+        uint32_t tot;
+        const uint32_t ds = lq_block_excl_scan(run, s_scan, &tot);
+        s_dstart[d] = ds;
+        s_gb[d] = gbase[(uint64_t)d * nblk + blockIdx.x] - ds;
     }
     __syncthreads();
-    /* 3. scatter, rows in order */
+    /* 3. order the CTA's records by digit in shared memory, rows in order */
+    #pragma unroll
     for (int r = 0; r < RS_ROWS; ++r) {
         const uint64_t i = base + (uint64_t)r * 32 + lane;
         const bool ok = i < n;
         const uint32_t act = __ballot_sync(0xffffffffu, ok);
-        uint32_t kv = 0, d = 0, peers = 0; uint64_t dst = 0;
+        uint32_t d = 0, peers = 0, dst = 0;
         if (ok) {
-            kv = key_in[i]; d = (kv >> shift) & 255u;
+            d = (kv[r] >> shift) & 255u;
             peers = __match_any_sync(act, d);
-            dst = wbase[wid][d] + (uint64_t)__popc(peers & lt);
+            dst = s_dstart[d] + wbase[wid][d] + __popc(peers & lt);
         }
         __syncwarp();
         if (ok) {
-            if ((peers & lt) == 0) wbase[wid][d] += (uint64_t)__popc(peers);
-            if (key_out) key_out[dst] = kv;
-            y_out[dst] = y_in[i];
-            if (sp_in) sp_out[dst] = sp_in[i];
+            if ((peers & lt) == 0) wbase[wid][d] += __popc(peers);
+            s_key[dst] = kv[r]; s_y[dst] = y_in[i];
+            if (sp_in) s_sp[dst] = sp_in[i];
         }
         __syncwarp();
+    }
+    __syncthreads();
+    /* 4. write out: record j of the CTA goes to (global base of its digit) + j */
+    for (uint32_t j = threadIdx.x; j < nblkrec; j += RS_THREADS) {
+        const uint32_t k = s_key[j];
+        const uint64_t dst = s_gb[(k >> shift) & 255u] + j;
+        if (key_out) key_out[dst] = k;
+        y_out[dst] = s_y[j];
+        if (sp_in) sp_out[dst] = s_sp[j];
     }
 }
 
@@ -120,6 +148,7 @@ int lq_sort_by_key(LqMinimizers *m, int key_bits, LqDevBuf &tmp_key, LqDevBuf &t
     uint32_t *kin = m->key.as<uint32_t>(), *kout = tmp_key.as<uint32_t>();
     uint64_t *yin = m->y.as<uint64_t>(), *yout = tmp_y.as<uint64_t>();
     uint8_t *sin = m->has_span ? m->span.as<uint8_t>() : 0, *sout = m->has_span ? tmp_sp.as<uint8_t>() : 0;
+    LQ_CUDA_OK(cudaFuncSetAttribute(lq_rs_scatter_k, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES));
     for (int p = 0; p < npass; ++p) {
         const int shift = 8 * p;
         { LqProfScope ps("radix_hist", st, 1, n * 4);
@@ -127,7 +156,7 @@ int lq_sort_by_key(LqMinimizers *m, int key_bits, LqDevBuf &tmp_key, LqDevBuf &t
         LQ_CUDA_OK(cudaGetLastError());
         LQ_TRY((lq_exclusive_scan<uint32_t, uint64_t>(gh, gb, (size_t)256 * nblk, 0, ws, st)));
         { LqProfScope ps("radix_scatter", st, 1, n * (12 + ((p == npass - 1 && !keep_keys) ? 8 : 12)));
-          lq_rs_scatter_k<<<nblk, RS_THREADS, 0, st>>>(kin, yin, sin, n, shift, nblk, gb, (p == npass - 1 && !keep_keys) ? (uint32_t*)0 : kout, yout, sout); }
+          lq_rs_scatter_k<<<nblk, RS_THREADS, RS_SMEM_BYTES, st>>>(kin, yin, sin, n, shift, nblk, gb, (p == npass - 1 && !keep_keys) ? (uint32_t*)0 : kout, yout, sout); }
         LQ_CUDA_OK(cudaGetLastError());
         { uint32_t *t = kin; kin = kout; kout = t; } { uint64_t *t = yin; yin = yout; yout = t; } { uint8_t *t = sin; sin = sout; sout = t; }
     }

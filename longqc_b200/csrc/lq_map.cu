@@ -293,24 +293,42 @@ __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
             const uint32_t n0 = cnt[d0];
             uint32_t *P = idx2, *Z = idx2 + n0;
             uint32_t runP = 0, runZ = 0;
-            for (uint32_t p0 = 0; p0 < n0; p0 += 32) {          /* region 0: foreign == digit d1 */
-                const uint32_t p = p0 + lane; const bool fr = p < n0 && dig[p] == d1;
-                const uint32_t m = __ballot_sync(0xffffffffu, fr), rk = runP + __popc(m & lt);
-                if (p < n0) dest[p] = rk;
-                if (fr) P[rk] = p;
-                runP += __popc(m);
+            for (uint32_t p0 = 0; p0 < n0; p0 += 32 * AF_U) {   /* region 0: foreign == digit d1 */
+                uint32_t dv[AF_U];
+                #pragma unroll
+                for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32 + lane; dv[u] = p < n0 ? dig[p] : 256u; }
+                #pragma unroll
+                for (int u = 0; u < AF_U; ++u) {
+                    const uint32_t p = p0 + u * 32 + lane; const bool fr = dv[u] == d1;
+                    const uint32_t m = __ballot_sync(0xffffffffu, fr), rk = runP + __popc(m & lt);
+                    if (p < n0) dest[p] = rk;
+                    if (fr) P[rk] = p;
+                    runP += __popc(m);
+                }
             }
-            for (uint32_t p0 = n0; p0 < n; p0 += 32) {          /* region 1: foreign == digit d0 */
-                const uint32_t p = p0 + lane; const bool fr = p < n && dig[p] == d0;
-                const uint32_t m = __ballot_sync(0xffffffffu, fr), rk = runZ + __popc(m & lt);
-                if (p < n) dest[p] = rk;
-                if (fr) Z[rk] = p;
-                runZ += __popc(m);
+            for (uint32_t p0 = n0; p0 < n; p0 += 32 * AF_U) {   /* region 1: foreign == digit d0 */
+                uint32_t dv[AF_U];
+                #pragma unroll
+                for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32 + lane; dv[u] = p < n ? dig[p] : 256u; }
+                #pragma unroll
+                for (int u = 0; u < AF_U; ++u) {
+                    const uint32_t p = p0 + u * 32 + lane; const bool fr = dv[u] == d0;
+                    const uint32_t m = __ballot_sync(0xffffffffu, fr), rk = runZ + __popc(m & lt);
+                    if (p < n) dest[p] = rk;
+                    if (fr) Z[rk] = p;
+                    runZ += __popc(m);
+                }
             }
             __syncwarp();
-            for (uint32_t p = lane; p < n; p += 32) {
-                const int fr = p < n0 ? dig[p] == d1 : dig[p] == d0;
-                dest[p] = lq_af_two_dest(p, n0, fr, dest[p], runP, P, Z);
+            for (uint32_t p0 = lane; p0 < n; p0 += 32 * AF_U) {
+                uint32_t dv[AF_U], rk[AF_U];
+                #pragma unroll
+                for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) { dv[u] = dig[p]; rk[u] = dest[p]; } }
+                #pragma unroll
+                for (int u = 0; u < AF_U; ++u) {
+                    const uint32_t p = p0 + u * 32;
+                    if (p < n) { const int fr = p < n0 ? dv[u] == d1 : dv[u] == d0; dest[p] = lq_af_two_dest(p, n0, fr, rk[u], runP, P, Z); }
+                }
             }
             __syncwarp();
         } else if (nb > 2) {
@@ -345,11 +363,17 @@ __global__ void __launch_bounds__(AFW_WARPS * 32) lq_af_walk_k(AfArgs a)
         /* histogram from the digits the level kernel stored */
         for (uint32_t d = lane; d < 256; d += 32) { cnt[d] = 0; tag[d] = 0xffffffffu; head[d] = 0; }
         __syncwarp();
-        for (uint32_t p0 = 0; p0 < n; p0 += 32) {
-            const uint32_t p = p0 + lane; const bool ok = p < n;
-            const uint32_t act = __ballot_sync(0xffffffffu, ok);
-            if (ok) { const uint32_t d = dig[p]; const uint32_t peers = __match_any_sync(act, d); if ((peers & lt) == 0) cnt[d] += __popc(peers); }
-            __syncwarp();
+        for (uint32_t p0 = 0; p0 < n; p0 += 32 * AF_U) {
+            uint32_t dv[AF_U];
+            #pragma unroll
+            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32 + lane; dv[u] = p < n ? dig[p] : 0; }
+            #pragma unroll
+            for (int u = 0; u < AF_U; ++u) {
+                const uint32_t p = p0 + u * 32 + lane; const bool ok = p < n;
+                const uint32_t act = __ballot_sync(0xffffffffu, ok);
+                if (ok) { const uint32_t peers = __match_any_sync(act, dv[u]); if ((peers & lt) == 0) cnt[dv[u]] += __popc(peers); }
+                __syncwarp();
+            }
         }
         uint32_t loc = 0, ne = 0;
         #pragma unroll

@@ -322,10 +322,53 @@ __device__ __forceinline__ int rk_scan(const SkArgs &a, uint32_t rd, uint64_t g0
     #define RK_EMIT(H_, P_) do { if (MODE == 0) { if (n < RK_CAP) s_rec[n * RK_THREADS + tid] = make_uint2((H_), (P_)); } \
                                  else { a.out_key[wat + n] = (H_); a.out_y[wat + n] = (uint64_t)rid << 32 | (P_); } ++n; } while (0)
     uint32_t wb = 0, wn = 0;               /* current packed words */
-    for (int i = p0; i < i1; ++i) {
+    int i = p0;
+    if (i < i1) { wb = a.b2[(g0 + (uint64_t)i) >> 4]; wn = a.nm[(g0 + (uint64_t)i) >> 5]; }
+    while (i < i1) {
+        /* ---- steady state: certified, every gate open, no ambiguous base: the common case, kept lean ---- */
+        if (cert && (lexact ? run >= w + k : good >= w + k)) {
+            while (i < i1) {
+                if ((i & 15) == 0) wb = a.b2[(g0 + (uint64_t)i) >> 4];
+                if ((i & 31) == 0) wn = a.nm[(g0 + (uint64_t)i) >> 5];
+                if ((wn >> (i & 31)) & 1u) break;                       /* ambiguous base: back to the general step */
+                const uint32_t c = (wb >> ((i & 15) * 2)) & 3u;
+                fw = (fw << 2 | c) & mask;
+                rv = rv >> 2 | (3u ^ c) << top;
+                if (fw != rv) {                                          /* else sketch.c:107: no push */
+                    const uint32_t z = fw < rv ? 0u : 1u;
+                    const uint32_t cx = lq_hash32(z ? rv : fw, mask), cp = (uint32_t)i << 1 | z;
+                    const bool em = i >= i0;
+                    if (cx <= mx) {
+                        if (em) RK_EMIT(mx, mp);
+                        mx = cx; mp = cp; mi = W;
+                    } else if (mi == 0) {
+                        if (em) RK_EMIT(mx, mp);
+                        mx = MAXH; mp = MAXH;
+                        #pragma unroll
+                        for (int j = 1; j < W; ++j) if (mx >= wx[j]) { mx = wx[j]; mp = wp[j]; mi = j; }
+                        if (mx >= cx) { mx = cx; mp = cp; mi = W; }
+                        bool twin = cx == mx && cp != mp;
+                        #pragma unroll
+                        for (int j = 1; j < W; ++j) twin |= wx[j] == mx && wp[j] != mp;
+                        if (twin && em) {
+                            #pragma unroll
+                            for (int j = 1; j < W; ++j) if (wx[j] == mx && wp[j] != mp) RK_EMIT(wx[j], wp[j]);
+                            if (cx == mx && cp != mp) RK_EMIT(cx, cp);
+                        }
+                    }
+                    #pragma unroll
+                    for (int j = 0; j + 1 < W; ++j) { wx[j] = wx[j + 1]; wp[j] = wp[j + 1]; }
+                    wx[W - 1] = cx; wp[W - 1] = cp;
+                    --mi; ++run; ++good;
+                }
+                ++nb; ++i;
+            }
+            if (i >= i1) break;
+        }
+        /* ---- general step (warm-up, first windows of a run, ambiguous bases) ---- */
         const uint64_t g = g0 + (uint64_t)i;
-        if ((i & 15) == 0 || i == p0) wb = a.b2[g >> 4];
-        if ((i & 31) == 0 || i == p0) wn = a.nm[g >> 5];
+        if ((i & 15) == 0) wb = a.b2[g >> 4];
+        if ((i & 31) == 0) wn = a.nm[g >> 5];
         const uint32_t c = (wb >> ((i & 15) * 2)) & 3u;
         const bool amb = (wn >> (i & 31)) & 1u;
         const bool out = i >= i0;
@@ -336,46 +379,52 @@ __device__ __forceinline__ int rk_scan(const SkArgs &a, uint32_t rd, uint64_t g0
             for (int j = 0; j < sbuf.n; ++j) RK_EMIT((uint32_t)(sbuf.x[j] >> 8), (uint32_t)sbuf.y[j]);
         }
         uint32_t cx = MAXH, cp = MAXH;
+        bool push = true;
         if (!amb) {
             fw = (fw << 2 | c) & mask;
             rv = rv >> 2 | (3u ^ c) << top;
             ++nb;
-            if (fw == rv) continue;                    /* sketch.c:107 */
-            const uint32_t z = fw < rv ? 0u : 1u;
-            ++run;
-            if (nb >= k) ++good; else good = 0;
-            if (run >= k) { cx = lq_hash32(z ? rv : fw, mask); cp = (uint32_t)i << 1 | z; }
+            if (fw == rv) push = false;                /* sketch.c:107 */
+            else {
+                const uint32_t z = fw < rv ? 0u : 1u;
+                ++run;
+                if (nb >= k) ++good; else good = 0;
+                if (run >= k) { cx = lq_hash32(z ? rv : fw, mask); cp = (uint32_t)i << 1 | z; }
+            }
         } else {
             if (nb >= k) { cert = true; lexact = true; }   /* registers exact: the reset is exact */
             run = 0; good = 0;
         }
-        if (!lexact && good >= w + k) { cert = true; }
-        const int l = (lexact || !cert) ? run : (run > w + k ? run : w + k);   /* certified by `good`: every gate is open */
-        const bool em = out && !use_slow;      /* certified at the top of this step */
-        /* the slot being overwritten is wx[0]; (A) first full window, sketch.c:116-121: entries older than the newcomer */
-        if (l == w + k - 1 && mx != MAXH) {
-            #pragma unroll
-            for (int j = 1; j < W; ++j) if (wx[j] == mx && wp[j] != mp && em) RK_EMIT(wx[j], wp[j]);
-        }
-        if (cx <= mx) {                                 /* sketch.c:122-124 */
-            if (l >= w + k && mx != MAXH && em) RK_EMIT(mx, mp);
-            mx = cx; mp = cp; mi = W;                   /* index after the shift below: W-1 */
-        } else if (mi == 0) {                           /* sketch.c:125-137: the minimum's slot is overwritten */
-            if (l >= w + k - 1 && mx != MAXH && em) RK_EMIT(mx, mp);
-            mx = MAXH; mp = MAXH; mi = 1;
-            #pragma unroll
-            for (int j = 1; j < W; ++j) if (mx >= wx[j]) { mx = wx[j]; mp = wp[j]; mi = j; }
-            if (mx >= cx) { mx = cx; mp = cp; mi = W; }
-            if (l >= w + k - 1 && mx != MAXH) {
+        if (push) {
+            if (!lexact && good >= w + k) cert = true;
+            const int l = (lexact || !cert) ? run : (run > w + k ? run : w + k);   /* certified by `good`: every gate is open */
+            const bool em = out && !use_slow;      /* certified at the top of this step */
+            /* the slot being overwritten is wx[0]; (A) first full window, sketch.c:116-121: entries older than the newcomer */
+            if (l == w + k - 1 && mx != MAXH) {
                 #pragma unroll
                 for (int j = 1; j < W; ++j) if (wx[j] == mx && wp[j] != mp && em) RK_EMIT(wx[j], wp[j]);
-                if (cx == mx && cp != mp && em) RK_EMIT(cx, cp);
             }
+            if (cx <= mx) {                                 /* sketch.c:122-124 */
+                if (l >= w + k && mx != MAXH && em) RK_EMIT(mx, mp);
+                mx = cx; mp = cp; mi = W;                   /* index after the shift below: W-1 */
+            } else if (mi == 0) {                           /* sketch.c:125-137: the minimum's slot is overwritten */
+                if (l >= w + k - 1 && mx != MAXH && em) RK_EMIT(mx, mp);
+                mx = MAXH; mp = MAXH; mi = 1;
+                #pragma unroll
+                for (int j = 1; j < W; ++j) if (mx >= wx[j]) { mx = wx[j]; mp = wp[j]; mi = j; }
+                if (mx >= cx) { mx = cx; mp = cp; mi = W; }
+                if (l >= w + k - 1 && mx != MAXH) {
+                    #pragma unroll
+                    for (int j = 1; j < W; ++j) if (wx[j] == mx && wp[j] != mp && em) RK_EMIT(wx[j], wp[j]);
+                    if (cx == mx && cp != mp && em) RK_EMIT(cx, cp);
+                }
+            }
+            #pragma unroll
+            for (int j = 0; j + 1 < W; ++j) { wx[j] = wx[j + 1]; wp[j] = wp[j + 1]; }
+            wx[W - 1] = cx; wp[W - 1] = cp;
+            --mi;
         }
-        #pragma unroll
-        for (int j = 0; j + 1 < W; ++j) { wx[j] = wx[j + 1]; wp[j] = wp[j + 1]; }
-        wx[W - 1] = cx; wp[W - 1] = cp;
-        --mi;
+        ++i;
     }
     if (i1 == L && !last_slow) {           /* sketch.c:140-141; a last base that took the replay already got this record from it */
         if (mx != MAXH) RK_EMIT(mx, mp);
