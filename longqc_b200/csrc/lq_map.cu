@@ -158,6 +158,17 @@ __global__ void lq_iota_k(uint32_t *idx, uint64_t n)
 #define AF_WARPS 4
 #define AF_U 8
 
+/* append a sub-bucket to the next level's list: one atomic per warp (the lanes that append are counted with a ballot) */
+__device__ __forceinline__ void af_append(const AfArgs &a, uint32_t beg, uint32_t c, bool doit)
+{
+    const uint32_t m = __ballot_sync(0xffffffffu, doit), lane = threadIdx.x & 31;
+    if (m == 0) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(a.n_nxt, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (doit) { const uint32_t at = base + __popc(m & ((1u << lane) - 1)); a.nxt[at].beg = beg; a.nxt[at].end = beg + c; }
+}
+
 /* stable sort of a sub-bucket of 9..64 elements by key, one warp: each lane holds two elements, rank = #smaller + #equal-before
  * (== the order ksort.h's insertion sort leaves) */
 __device__ __forceinline__ void af_warp_ranksort(uint32_t *idx, uint32_t n, const uint64_t *__restrict__ key, uint32_t lane)
@@ -177,8 +188,9 @@ __device__ __forceinline__ void af_warp_ranksort(uint32_t *idx, uint32_t n, cons
 }
 
 /* after dest[] is known: permute the payload, then hand the sub-buckets on (ksort.h:124-133) */
+#define AF_SN 320
 __device__ __forceinline__ void af_finish_bucket(const AfArgs &a, uint32_t beg, uint32_t n, uint32_t nb, const uint32_t *cnt, const uint32_t *start,
-                                                 uint32_t *idx, uint32_t *idx2, const uint32_t *dest, uint32_t lane)
+                                                 uint32_t *idx, uint32_t *idx2, const uint32_t *dest, uint32_t lane, uint64_t *s_k, uint32_t *s_i)
 {
     if (nb > 1) {
         for (uint32_t p0 = lane; p0 < n; p0 += 32 * AF_U) {
@@ -199,17 +211,44 @@ __device__ __forceinline__ void af_finish_bucket(const AfArgs &a, uint32_t beg, 
         __syncwarp();
     }
     if (a.shift > 0) {
-        uint32_t mid = 0;   /* digits (bit per owned digit) whose sub-bucket has 9..64 elements: sorted by the whole warp afterwards */
-        for (uint32_t d = lane; d < 256; d += 32) {
-            const uint32_t c = cnt[d];
-            if (c > LQ_RS_MIN) { const uint32_t at = atomicAdd(a.n_nxt, 1u); a.nxt[at].beg = beg + start[d]; a.nxt[at].end = beg + start[d] + c; }
-            else if (c > 8) mid |= 1u << (d >> 5);
-            else if (c > 1) lq_af_insertion(idx + start[d], c, a.sx);
-        }
-        __syncwarp();
-        for (uint32_t l = 0; l < 32; ++l) {
-            uint32_t m = __shfl_sync(0xffffffffu, mid, l);
-            while (m) { const uint32_t d = (uint32_t)(__ffs(m) - 1) * 32 + l; m &= m - 1; af_warp_ranksort(idx + start[d], cnt[d], a.sx, lane); }
+        if (n <= AF_SN) {
+            /* small bucket: stage (key, index) in shared memory once, so that the insertion sorts of its sub-buckets run at
+             * shared-memory latency instead of two dependent global loads per comparison */
+            for (uint32_t p = lane; p < n; p += 32) { const uint32_t e = idx[p]; s_i[p] = e; s_k[p] = a.sx[e]; }
+            __syncwarp();
+            for (uint32_t d = lane; d < 256; d += 32) {
+                const uint32_t c = cnt[d];
+                const bool big_ = c > LQ_RS_MIN;
+                af_append(a, beg + start[d], c, big_);
+                if (!big_ && c > 1) { /* ksort.h:88-98 on the staged copy */
+                    uint64_t *kk = s_k + start[d]; uint32_t *ii = s_i + start[d];
+                    for (uint32_t x = 1; x < c; ++x) {
+                        const uint64_t kt = kk[x]; const uint32_t it = ii[x];
+                        if (kt < kk[x - 1]) {
+                            uint32_t j = x;
+                            while (j > 0 && kt < kk[j - 1]) { kk[j] = kk[j - 1]; ii[j] = ii[j - 1]; --j; }
+                            kk[j] = kt; ii[j] = it;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            for (uint32_t p = lane; p < n; p += 32) idx[p] = s_i[p];
+        } else {
+            uint32_t mid = 0;   /* digits (bit per owned digit) whose sub-bucket has 9..64 elements: sorted by the whole warp afterwards */
+            for (uint32_t d = lane; d < 256; d += 32) {
+                const uint32_t c = cnt[d];
+                const bool big_ = c > LQ_RS_MIN;
+                af_append(a, beg + start[d], c, big_);
+                if (big_) {}
+                else if (c > 8) mid |= 1u << (d >> 5);
+                else if (c > 1) lq_af_insertion(idx + start[d], c, a.sx);
+            }
+            __syncwarp();
+            for (uint32_t l = 0; l < 32; ++l) {
+                uint32_t m = __shfl_sync(0xffffffffu, mid, l);
+                while (m) { const uint32_t d = (uint32_t)(__ffs(m) - 1) * 32 + l; m &= m - 1; af_warp_ranksort(idx + start[d], cnt[d], a.sx, lane); }
+            }
         }
     }
     __syncwarp();
@@ -217,15 +256,21 @@ __device__ __forceinline__ void af_finish_bucket(const AfArgs &a, uint32_t beg, 
 __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
 {
     __shared__ uint32_t s_cnt[AF_WARPS][256], s_start[AF_WARPS][256], s_head[AF_WARPS][256];
+    __shared__ uint64_t s_sk[AF_WARPS][AF_SN]; __shared__ uint32_t s_si[AF_WARPS][AF_SN];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lt = (1u << lane) - 1;
     uint32_t *cnt = s_cnt[wid], *start = s_start[wid], *head = s_head[wid];
     const uint32_t nb_total = *a.n_cur;
+    const uint32_t grab = nb_total > 200000u ? 16u : 1u;   /* many small buckets: fetch them 16 at a time (one same-address atomic per fetch) */
+    uint32_t b = 0, b_end = 0;
     for (;;) {
-        uint32_t b = 0;
-        if (lane == 0) b = atomicAdd(a.cursor, 1u);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= nb_total) break;
-        const uint32_t beg = a.cur[b].beg, n = a.cur[b].end - beg;
+        if (b >= b_end) {
+            if (lane == 0) b = atomicAdd(a.cursor, grab);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            b_end = b + grab < nb_total ? b + grab : nb_total;
+            if (b >= nb_total) break;
+        }
+        const uint32_t bcur = b++;
+        const uint32_t beg = a.cur[bcur].beg, n = a.cur[bcur].end - beg;
         uint32_t *idx = a.idx + beg, *idx2 = a.idx2 + beg, *dest = a.dest + beg;
         uint8_t *dig = a.dig + beg;
         /* 1. digits + histogram */
@@ -337,7 +382,7 @@ __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
             __syncwarp();
             continue;
         }
-        af_finish_bucket(a, beg, n, nb, cnt, start, idx, idx2, dest, lane);
+        af_finish_bucket(a, beg, n, nb, cnt, start, idx, idx2, dest, lane, s_sk[wid], s_si[wid]);
     }
 }
 
@@ -348,6 +393,7 @@ __global__ void __launch_bounds__(AFW_WARPS * 32) lq_af_walk_k(AfArgs a)
 {
     __shared__ uint32_t s_cnt[AFW_WARPS][256], s_start[AFW_WARPS][256], s_head[AFW_WARPS][256], s_tag[AFW_WARPS][256];
     __shared__ uint4 s_cache[AFW_WARPS][256];
+    __shared__ uint64_t s_sk[AFW_WARPS][AF_SN]; __shared__ uint32_t s_si[AFW_WARPS][AF_SN];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lt = (1u << lane) - 1;
     uint32_t *cnt = s_cnt[wid], *start = s_start[wid], *head = s_head[wid], *tag = s_tag[wid];
     uint4 *cache = s_cache[wid];
@@ -406,7 +452,7 @@ __global__ void __launch_bounds__(AFW_WARPS * 32) lq_af_walk_k(AfArgs a)
             atomicAdd(a.n_walk, 1u);
         }
         __syncwarp();
-        af_finish_bucket(a, beg, n, nb, cnt, start, idx, idx2, dest, lane);
+        af_finish_bucket(a, beg, n, nb, cnt, start, idx, idx2, dest, lane, s_sk[wid], s_si[wid]);
     }
 }
 
