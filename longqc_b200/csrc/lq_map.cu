@@ -17,7 +17,7 @@
 
 void LqQueryDev::release()
 {
-    reads.release(); mins.release(); first.release(); dup.release(); dup_tmp.release(); dup_tk.release(); dup_ty.release(); dup_ts.release(); dup_hist.release(); nmatch_buf.release(); lambda.release(); lambda2.release(); mcnt.release();
+    reads.release(); mins.release(); first.release(); qtied.release(); dup.release(); dup_tmp.release(); dup_tk.release(); dup_ty.release(); dup_ts.release(); dup_hist.release(); nmatch_buf.release(); lambda.release(); lambda2.release(); mcnt.release();
     keep.release(); neff.release(); krank.release(); soff.release(); qstat.release();
     self_off.release(); self_list.release(); qrank.release(); trank.release();
 }
@@ -94,13 +94,14 @@ __global__ void lq_fill_k(uint64_t mi0, uint64_t mi1, const uint32_t *__restrict
                           const uint64_t *__restrict__ first, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ neff,
                           const uint32_t *__restrict__ krank, const uint64_t *__restrict__ soff, uint64_t seed_base,
                           const uint32_t *__restrict__ counts, const uint64_t *__restrict__ offs, const uint64_t *__restrict__ pos,
-                          MapTables t, const uint32_t *__restrict__ qlen, const uint8_t *__restrict__ dup, SeedArrays s)
+                          MapTables t, const uint32_t *__restrict__ qlen, const uint8_t *__restrict__ dup, const uint8_t *__restrict__ qtied /* null: every query */, SeedArrays s)
 {
     const uint64_t mi = mi0 + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const uint32_t lane = threadIdx.x & 31;
     if (mi >= mi1 || !keep[mi] || neff[mi] == 0) return;
     const uint64_t y = qy[mi];
     const uint32_t q = (uint32_t)(y >> 32), key = qkey[mi], c = counts[key];
+    if (qtied && !qtied[q]) return;                       /* queries without tied keys are written by lq_fill_filtered_k */
     const uint32_t qpos = (uint32_t)y >> 1, qstrand = (uint32_t)y & 1, span = qspan ? qspan[mi] : (uint32_t)k;
     const uint32_t rank = krank[mi] - krank[first[q]];       /* index into the query's mini_pos (lqmap.c:174) */
     const bool filt = t.ava || (t.no_self && t.self_off[q + 1] > t.self_off[q]);
@@ -127,6 +128,164 @@ __global__ void lq_fill_k(uint64_t mi0, uint64_t mi1, const uint32_t *__restrict
         }
         out += __popc(m);
     }
+}
+
+
+/* ------------------------------------------------------------------ seed pre-filter for queries without tied keys
+ *
+ * A (strand, target) run of fewer than T = max(min_cnt, ceil(min_sc / max_span)) anchors cannot hold a chain (chain.c:116-119, and a
+ * chain's score is at most the sum of its anchors' spans), so its seeds influence nothing that is printed -- EXCEPT through the
+ * reference's unstable sort, whose permutation of tied keys depends on every element.  For a query none of whose minimizers
+ * repeats (no tied keys, lq_map_flag_dups) the sorted order is unique, so the seeds of short runs can be dropped before they
+ * are ever written.  The run lengths are bounded from above with 4-bit saturating counters over a hash of (strand, target) in
+ * shared memory (collisions only make a run look longer); ~93 % of the seeds of a typical query are chance hits and go away.
+ * Queries with tied keys keep every seed. */
+#define FL_THREADS 1024
+#define FL_ILP 8
+#define FL_BINS_LOG 18
+#define FL_WORDS (1u << (FL_BINS_LOG - 3))      /* 4-bit counters, 8 per word: 128 KiB */
+
+__device__ __forceinline__ uint32_t fl_hash(uint64_t r, uint32_t qstrand)
+{
+    const uint32_t v = (uint32_t)(r >> 32) << 1 | ((((uint32_t)r & 1u) != qstrand) ? 1u : 0u);
+    return (v * 0x9E3779B1u) >> (32 - FL_BINS_LOG);
+}
+__device__ __forceinline__ void fl_inc(uint32_t *bins, uint32_t h)
+{
+    const uint32_t w = h >> 3, sh = (h & 7u) * 4;
+    uint32_t old = bins[w];
+    while (((old >> sh) & 15u) < 15u) { const uint32_t as = old; old = atomicCAS(&bins[w], as, as + (1u << sh)); if (old == as) break; }
+}
+__device__ __forceinline__ uint32_t fl_get(const uint32_t *bins, uint32_t h) { return (bins[h >> 3] >> ((h & 7u) * 4)) & 15u; }
+
+struct FlArgs {
+    const uint32_t *qkey; const uint64_t *qy; const uint8_t *qspan; int k;
+    const uint64_t *first; const uint32_t *keep; uint32_t *neff; const uint8_t *qtied;
+    const uint32_t *counts; const uint64_t *offs, *pos;
+    MapTables t; const uint32_t *qlen;
+    uint32_t thr;                 /* T */
+    /* fill only */
+    const uint32_t *krank; const uint64_t *soff; uint64_t seed_base; SeedArrays s;
+    uint32_t q0, q1;
+};
+
+/* Both kernels walk the query's occurrence lists one THREAD per minimizer (a list is ~70 consecutive 8-byte entries: each thread
+ * streams its own list, and the 16..32 resident warps hide the latency); the fill then writes each minimizer's survivors to its own
+ * contiguous output range, which preserves the reference's order by construction. */
+
+/* pass 1 of both kernels: run-length bounds of query q into bins[] */
+__device__ __forceinline__ void fl_count_runs(const FlArgs &a, uint32_t q, uint32_t *bins)
+{
+    for (uint32_t j = threadIdx.x; j < FL_WORDS; j += blockDim.x) bins[j] = 0;
+    __syncthreads();
+    const bool filt = a.t.ava || (a.t.no_self && a.t.self_off[q + 1] > a.t.self_off[q]);
+    for (uint64_t mi = a.first[q] + threadIdx.x; mi < a.first[q + 1]; mi += blockDim.x) {
+        if (!a.keep[mi] || a.neff[mi] == 0) continue;
+        const uint64_t y = a.qy[mi];
+        const uint32_t key = a.qkey[mi], c = a.counts[key], qpos = (uint32_t)y >> 1, qstrand = (uint32_t)y & 1;
+        const uint64_t *pp = a.pos + a.offs[key];
+        for (uint32_t j0 = 0; j0 < c; j0 += FL_ILP) {   /* FL_ILP loads in flight per thread */
+            uint64_t rr[FL_ILP];
+            #pragma unroll
+            for (int u = 0; u < FL_ILP; ++u) rr[u] = j0 + u < c ? pp[j0 + u] : 0;
+            #pragma unroll
+            for (int u = 0; u < FL_ILP; ++u) {
+                if (j0 + u >= c) break;
+                if (filt && lq_seed_skipped(a.t, rr[u], qpos, q)) continue;
+                fl_inc(bins, fl_hash(rr[u], qstrand));
+            }
+        }
+    }
+    __syncthreads();
+}
+
+extern __shared__ uint32_t fl_bins[];
+
+/* survivors per minimizer -> neff (queries without tied keys only) */
+__global__ void __launch_bounds__(FL_THREADS) lq_filter_count_k(FlArgs a)
+{
+    for (uint32_t q = a.q0 + blockIdx.x; q < a.q1; q += gridDim.x) {
+        if (a.qtied[q]) continue;
+        __syncthreads();
+        fl_count_runs(a, q, fl_bins);
+        const bool filt = a.t.ava || (a.t.no_self && a.t.self_off[q + 1] > a.t.self_off[q]);
+        for (uint64_t mi = a.first[q] + threadIdx.x; mi < a.first[q + 1]; mi += blockDim.x) {
+            if (!a.keep[mi] || a.neff[mi] == 0) continue;
+            const uint64_t y = a.qy[mi];
+            const uint32_t key = a.qkey[mi], c = a.counts[key], qpos = (uint32_t)y >> 1, qstrand = (uint32_t)y & 1;
+            const uint64_t *pp = a.pos + a.offs[key];
+            uint32_t n = 0;
+            for (uint32_t j0 = 0; j0 < c; j0 += FL_ILP) {
+                uint64_t rr[FL_ILP];
+                #pragma unroll
+                for (int u = 0; u < FL_ILP; ++u) rr[u] = j0 + u < c ? pp[j0 + u] : 0;
+                #pragma unroll
+                for (int u = 0; u < FL_ILP; ++u) {
+                    if (j0 + u >= c) break;
+                    if (filt && lq_seed_skipped(a.t, rr[u], qpos, q)) continue;
+                    n += fl_get(fl_bins, fl_hash(rr[u], qstrand)) >= a.thr;
+                }
+            }
+            a.neff[mi] = n;
+        }
+    }
+}
+
+/* the seeds that survive, in the reference's order (minimizer order x ascending target position) */
+__global__ void __launch_bounds__(FL_THREADS) lq_fill_filtered_k(FlArgs a)
+{
+    for (uint32_t q = a.q0 + blockIdx.x; q < a.q1; q += gridDim.x) {
+        if (a.qtied[q]) continue;
+        __syncthreads();
+        fl_count_runs(a, q, fl_bins);
+        const bool filt = a.t.ava || (a.t.no_self && a.t.self_off[q + 1] > a.t.self_off[q]);
+        const int32_t ql = (int32_t)a.qlen[q];
+        const uint32_t kr0 = a.krank[a.first[q]];
+        for (uint64_t mi = a.first[q] + threadIdx.x; mi < a.first[q + 1]; mi += blockDim.x) {
+            if (!a.keep[mi] || a.neff[mi] == 0) continue;
+            const uint64_t y = a.qy[mi];
+            const uint32_t key = a.qkey[mi], c = a.counts[key], qpos = (uint32_t)y >> 1, qstrand = (uint32_t)y & 1;
+            const uint32_t span = a.qspan ? a.qspan[mi] : (uint32_t)a.k;
+            const uint32_t sm = span << 24 | (a.krank[mi] - kr0);
+            const uint32_t sq_rev = (uint32_t)(ql - ((int32_t)qpos + 1 - (int32_t)span) - 1);
+            const uint64_t *pp = a.pos + a.offs[key];
+            uint64_t at = a.soff[mi] - a.seed_base;
+            for (uint32_t j0 = 0; j0 < c; j0 += FL_ILP) {
+              uint64_t rr[FL_ILP];
+              #pragma unroll
+              for (int u = 0; u < FL_ILP; ++u) rr[u] = j0 + u < c ? pp[j0 + u] : 0;
+              #pragma unroll
+              for (int u = 0; u < FL_ILP; ++u) {
+                if (j0 + u >= c) break;
+                const uint64_t r = rr[u];
+                if (filt && lq_seed_skipped(a.t, r, qpos, q)) continue;
+                if (fl_get(fl_bins, fl_hash(r, qstrand)) < a.thr) continue;
+                const uint32_t rpos = (uint32_t)r >> 1;
+                if (((uint32_t)r & 1) == qstrand) { a.s.sx[at] = (r & 0xffffffff00000000ULL) | rpos; a.s.sq[at] = qpos; }
+                else { a.s.sx[at] = 1ULL << 63 | (r & 0xffffffff00000000ULL) | rpos; a.s.sq[at] = sq_rev; }
+                a.s.sm[at] = sm;
+                ++at;
+              }
+            }
+        }
+    }
+}
+
+/* per query: does any of its minimizers repeat (=> tied sort keys)? */
+__global__ void lq_qtied_k(uint32_t nq, const uint64_t *__restrict__ first, const uint8_t *__restrict__ dup, uint8_t *__restrict__ qtied)
+{
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    uint32_t t = 0;
+    for (uint64_t mi = first[q] + lane; mi < first[q + 1]; mi += 32) t |= dup[mi];
+    t = __any_sync(0xffffffffu, t);
+    if (lane == 0) qtied[q] = (uint8_t)t;
+}
+/* seeds of each query after filtering */
+__global__ void lq_qseeds_k(uint32_t nq, const uint64_t *__restrict__ first, const uint64_t *__restrict__ soff, LqQStat *__restrict__ qs)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) qs[q].n_sorted = soff[first[q + 1]] - soff[first[q]];
 }
 
 /* ------------------------------------------------------------------ K5: exact seed sort */
@@ -867,8 +1026,10 @@ static int carve(LqMapScratch *sc, uint64_t nb, BatchPtrs *b)
     return 0;
 }
 
+static void fill_flargs(FlArgs *fa, LqQueryDev *qd, const LqIndexDev *ix, const MapTables &mt, uint32_t thr, uint32_t q0, uint32_t q1);
+
 /* seeds of queries [q0,q1) -> sorted arrays in arena2.  h_qoff: nqb+1 batch-relative seed offsets. */
-static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &mt, uint32_t q0, uint32_t q1, const std::vector<uint64_t> &h_first,
+static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &mt, uint32_t filter_thr, uint32_t q0, uint32_t q1, const std::vector<uint64_t> &h_first,
                          uint64_t seed_base, uint64_t nb, const std::vector<uint64_t> &h_qoff, LqMapScratch *sc, BatchPtrs *b, uint64_t **d_qoff_out,
                          LqMapStats *stats, cudaStream_t st)
 {
@@ -888,7 +1049,16 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         lq_fill_k<<<lq_grid((mi1 - mi0) * 32, 256), 256, 0, st>>>(mi0, mi1, qd->mins.key.as<uint32_t>(), qd->mins.y.as<uint64_t>(),
             qd->mins.has_span ? qd->mins.span.as<uint8_t>() : 0, ix->k, qd->first.as<uint64_t>(), qd->keep.as<uint32_t>(), qd->neff.as<uint32_t>(),
             qd->krank.as<uint32_t>(), qd->soff.as<uint64_t>(), seed_base, ix->counts.as<uint32_t>(), ix->offs.as<uint64_t>(), ix->rec.y.as<uint64_t>(),
-            mt, qd->reads.len.as<uint32_t>(), qd->dup.as<uint8_t>(), b->s);
+            mt, qd->reads.len.as<uint32_t>(), qd->dup.as<uint8_t>(), filter_thr ? qd->qtied.as<uint8_t>() : (const uint8_t*)0, b->s);
+        LQ_CUDA_OK(cudaGetLastError());
+    }
+    if (mi1 > mi0 && filter_thr) {
+        FlArgs fa;
+        fill_flargs(&fa, qd, ix, mt, filter_thr, q0, q1);
+        fa.seed_base = seed_base; fa.s = b->s;
+        LQ_CUDA_OK(cudaFuncSetAttribute(lq_fill_filtered_k, cudaFuncAttributeMaxDynamicSharedMemorySize, FL_WORDS * 4));
+        LqProfScope ps("seed_fill_filtered", st, 1, 0);
+        lq_fill_filtered_k<<<nqb < 148 ? nqb : 148, FL_THREADS, FL_WORDS * 4, st>>>(fa);
         LQ_CUDA_OK(cudaGetLastError());
     }
     /* bucket lists: at most nb/65 + nqb live buckets per level */
@@ -931,7 +1101,28 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     return 0;
 }
 
-static int run_lookup(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int mid_occ, MapTables *mt,
+static void fill_flargs(FlArgs *fa, LqQueryDev *qd, const LqIndexDev *ix, const MapTables &mt, uint32_t thr, uint32_t q0, uint32_t q1)
+{
+    fa->qkey = qd->mins.key.as<uint32_t>(); fa->qy = qd->mins.y.as<uint64_t>(); fa->qspan = qd->mins.has_span ? qd->mins.span.as<uint8_t>() : 0; fa->k = ix->k;
+    fa->first = qd->first.as<uint64_t>(); fa->keep = qd->keep.as<uint32_t>(); fa->neff = qd->neff.as<uint32_t>(); fa->qtied = qd->qtied.as<uint8_t>();
+    fa->counts = ix->counts.as<uint32_t>(); fa->offs = ix->offs.as<uint64_t>(); fa->pos = ix->rec.y.as<uint64_t>();
+    fa->t = mt; fa->qlen = qd->reads.len.as<uint32_t>(); fa->thr = thr;
+    fa->krank = qd->krank.as<uint32_t>(); fa->soff = qd->soff.as<uint64_t>(); fa->seed_base = 0; fa->s.sx = 0; fa->s.sq = 0; fa->s.sm = 0;
+    fa->q0 = q0; fa->q1 = q1;
+}
+
+/* T of the pre-filter, 0 = off (debug hook, thresholds beyond the 4-bit counters, LQCOV_NO_SEED_FILTER=1) */
+static uint32_t filter_threshold(const LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt)
+{
+    static const int off = getenv("LQCOV_NO_SEED_FILTER") ? atoi(getenv("LQCOV_NO_SEED_FILTER")) : 0;
+    if (off) return 0;
+    const int max_span = qd->mins.has_span ? 255 : ix->k;
+    const int by_score = (std::max(opt->min_sc, 0) + max_span - 1) / max_span;
+    const int thr = std::max(std::max(opt->min_cnt, by_score), 1);
+    return thr >= 2 && thr <= 15 ? (uint32_t)thr : 0;
+}
+
+static int run_lookup(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int mid_occ, MapTables *mt, uint32_t filter_thr,
                       const uint32_t *h_self_off, const uint32_t *h_self_list, const uint32_t *h_qrank, const uint32_t *h_trank,
                       LqMapScratch *sc, std::vector<LqQStat> *h_stat, cudaStream_t st)
 {
@@ -952,9 +1143,20 @@ static int run_lookup(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt,
         ix->rec.y.as<uint64_t>(), mid_occ, *mt, qd->lambda.as<uint64_t>(), qd->reads.len.as<uint32_t>(), opt->covt, qd->keep.as<uint32_t>(), qd->neff.as<uint32_t>());
     LQ_CUDA_OK(cudaGetLastError());
     LQ_TRY((lq_exclusive_scan<uint32_t, uint32_t>(qd->keep.as<uint32_t>(), qd->krank.as<uint32_t>(), nm, 1, sc->ws, st)));
-    LQ_TRY((lq_exclusive_scan<uint32_t, uint64_t>(qd->neff.as<uint32_t>(), qd->soff.as<uint64_t>(), nm, 1, sc->ws, st)));
     lq_qstat_k<<<lq_grid((size_t)nq * 32, 256), 256, 0, st>>>(nq, qd->first.as<uint64_t>(), qd->keep.as<uint32_t>(), qd->neff.as<uint32_t>(),
         qd->mins.has_span ? qd->mins.span.as<uint8_t>() : 0, ix->k, qd->lambda.as<uint64_t>(), qd->reads.len.as<uint32_t>(), opt->covt, qd->qstat.as<LqQStat>());
+    LQ_CUDA_OK(cudaGetLastError());
+    if (filter_thr) { /* seeds of runs too short to chain are not written for queries without tied keys */
+        FlArgs fa;
+        fill_flargs(&fa, qd, ix, *mt, filter_thr, 0, nq);
+        LQ_CUDA_OK(cudaFuncSetAttribute(lq_filter_count_k, cudaFuncAttributeMaxDynamicSharedMemorySize, FL_WORDS * 4));
+        LqProfScope ps("seed_filter", st, 1, 0);
+        lq_filter_count_k<<<nq < 148 * 1 ? nq : 148, FL_THREADS, FL_WORDS * 4, st>>>(fa);
+    }
+    LQ_CUDA_OK(cudaGetLastError());
+    LQ_TRY((lq_exclusive_scan<uint32_t, uint64_t>(qd->neff.as<uint32_t>(), qd->soff.as<uint64_t>(), nm, 1, sc->ws, st)));
+    lq_qseeds_k<<<lq_grid(nq, 256), 256, 0, st>>>(nq, qd->first.as<uint64_t>(), qd->soff.as<uint64_t>(), qd->qstat.as<LqQStat>());
+    lq_prof_count_launch(1);
     LQ_CUDA_OK(cudaGetLastError());
     LQ_CUDA_OK(cudaMemcpyAsync(h_stat->data(), qd->qstat.p, (size_t)nq * sizeof(LqQStat), cudaMemcpyDeviceToHost, st));
     LQ_CUDA_OK(cudaStreamSynchronize(st));
@@ -969,7 +1171,8 @@ int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int m
     const uint32_t nq = qd->nq;
     MapTables mt;
     if (nq == 0) return 0;
-    LQ_TRY(run_lookup(qd, ix, opt, mid_occ, &mt, h_self_off, h_self_list, h_qrank, h_trank, sc, h_stat, st));
+    const uint32_t filter_thr = filter_threshold(qd, ix, opt);
+    LQ_TRY(run_lookup(qd, ix, opt, mid_occ, &mt, filter_thr, h_self_off, h_self_list, h_qrank, h_trank, sc, h_stat, st));
     std::vector<uint64_t> h_first((size_t)nq + 1);
     LQ_CUDA_OK(cudaMemcpyAsync(h_first.data(), qd->first.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st));
     LQ_CUDA_OK(cudaStreamSynchronize(st));
@@ -979,11 +1182,11 @@ int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int m
         /* batch = consecutive queries whose seeds fit the budget */
         uint32_t q1 = q0; uint64_t nb = 0;
         std::vector<uint64_t> h_qoff; h_qoff.push_back(0);
-        while (q1 < nq && (q1 == q0 || nb + (*h_stat)[q1].n_seeds <= seed_cap)) { nb += (*h_stat)[q1].n_seeds; h_qoff.push_back(nb); ++q1; }
+        while (q1 < nq && (q1 == q0 || nb + (*h_stat)[q1].n_sorted <= seed_cap)) { nb += (*h_stat)[q1].n_sorted; h_qoff.push_back(nb); ++q1; }
         if (nb > 0x7fffff00ULL) { fprintf(stderr, "[lqcov] query %u alone has %llu seeds in one part: beyond the 2^31 batch limit\n", q0, (unsigned long long)nb); return -1; }
         const uint32_t nqb = q1 - q0;
         BatchPtrs b; uint64_t *d_qoff = 0;
-        LQ_TRY(seed_and_sort(qd, ix, mt, q0, q1, h_first, seed_base, nb, h_qoff, sc, &b, &d_qoff, stats, st));
+        LQ_TRY(seed_and_sort(qd, ix, mt, filter_thr, q0, q1, h_first, seed_base, nb, h_qoff, sc, &b, &d_qoff, stats, st));
         if (nb > 0) {
             uint32_t *ctr = (uint32_t*)((char*)sc->misc.p + al((size_t)(nqb + 2) * 8));
             /* groups */
@@ -1043,7 +1246,8 @@ int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int m
 int lq_map_flag_dups(LqQueryDev *qd, int key_bits, LqDevBuf &ws, cudaStream_t st)
 {
     const uint64_t n = qd->n_min;
-    LQ_TRY(qd->dup.ensure(n + 16));
+    LQ_TRY(qd->dup.ensure(n + 16)); LQ_TRY(qd->qtied.ensure((size_t)qd->nq + 16));
+    LQ_CUDA_OK(cudaMemsetAsync(qd->qtied.p, 0, (size_t)qd->nq + 16, st));
     if (n == 0) return 0;
     LqMinimizers &tmp = qd->dup_tmp; LqDevBuf &tk = qd->dup_tk, &ty = qd->dup_ty, &ts = qd->dup_ts, &hist = qd->dup_hist;
     int rc = -1;
@@ -1054,7 +1258,8 @@ int lq_map_flag_dups(LqQueryDev *qd, int key_bits, LqDevBuf &ws, cudaStream_t st
         if (lq_sort_by_key(&tmp, key_bits, tk, ty, ts, hist, ws, st, 1) == 0) {
             const uint32_t *skey = tmp.key.as<uint32_t>();
             lq_dupflag_k<<<lq_grid(n, 256), 256, 0, st>>>(n, skey, tmp.y.as<uint64_t>(), qd->mins.y.as<uint64_t>(), qd->dup.as<uint8_t>());
-            lq_prof_count_launch(2);
+            lq_qtied_k<<<lq_grid((size_t)qd->nq * 32, 256), 256, 0, st>>>(qd->nq, qd->first.as<uint64_t>(), qd->dup.as<uint8_t>(), qd->qtied.as<uint8_t>());
+            lq_prof_count_launch(3);
             rc = cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess ? 0 : -1;
         }
     }
@@ -1085,15 +1290,15 @@ int lq_map_debug_sorted_seeds(LqQueryDev *qd, const LqIndexDev *ix, const LqMapO
                               LqMapScratch *sc, std::vector<lq_mm128> *unsorted, std::vector<lq_mm128> *sorted, cudaStream_t st)
 {
     MapTables mt; std::vector<LqQStat> hs;
-    LQ_TRY(run_lookup(qd, ix, opt, mid_occ, &mt, h_self_off, h_self_list, h_qrank, h_trank, sc, &hs, st));
+    LQ_TRY(run_lookup(qd, ix, opt, mid_occ, &mt, 0, h_self_off, h_self_list, h_qrank, h_trank, sc, &hs, st));
     std::vector<uint64_t> h_first((size_t)qd->nq + 1);
     LQ_CUDA_OK(cudaMemcpyAsync(h_first.data(), qd->first.p, ((size_t)qd->nq + 1) * 8, cudaMemcpyDeviceToHost, st));
     LQ_CUDA_OK(cudaStreamSynchronize(st));
-    uint64_t base = 0; for (uint32_t i = 0; i < q; ++i) base += hs[i].n_seeds;
-    const uint64_t nb = hs[q].n_seeds;
+    uint64_t base = 0; for (uint32_t i = 0; i < q; ++i) base += hs[i].n_sorted;
+    const uint64_t nb = hs[q].n_sorted;
     std::vector<uint64_t> h_qoff(2); h_qoff[0] = 0; h_qoff[1] = nb;
     BatchPtrs b; uint64_t *d_qoff = 0;
-    LQ_TRY(seed_and_sort(qd, ix, mt, q, q + 1, h_first, base, nb, h_qoff, sc, &b, &d_qoff, 0, st));
+    LQ_TRY(seed_and_sort(qd, ix, mt, 0, q, q + 1, h_first, base, nb, h_qoff, sc, &b, &d_qoff, 0, st));
     std::vector<uint64_t> x(nb), x2(nb); std::vector<uint32_t> sq(nb), sm(nb), aq(nb), am(nb);
     if (nb) {
         LQ_CUDA_OK(cudaMemcpyAsync(x.data(), b.s.sx, nb * 8, cudaMemcpyDeviceToHost, st));

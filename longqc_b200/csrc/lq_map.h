@@ -22,6 +22,7 @@ struct LqQueryDev {
     LqMinimizers mins;                /* key, y (rid = query index), span */
     LqDevBuf first;                   /* u64[nq+1] minimizer range per query */
     LqDevBuf lambda, lambda2;         /* u64[nq]  esterr.c:120,128 */
+    LqDevBuf qtied;                   /* u8[nq]: the query has such a minimizer (its seeds are never pre-filtered) */
     LqDevBuf dup;                     /* u8[n_min]: another minimizer of the same query has the same (key, strand) => its seeds tie (lq_afsort_core.h) */
     LqDevBuf mcnt;                    /* u32[n_min] per-minimizer match counters, indexed first[q] + rank among KEPT minimizers (esterr.c:130-137) */
     /* per part */
@@ -33,14 +34,15 @@ struct LqQueryDev {
     void release();
 };
 
-struct LqQStat { uint32_t n_kept; uint32_t sum_span_kept; uint64_t n_seeds; uint64_t sum_span_seeds; uint32_t gate_closed; float avg_span; };
+/* n_seeds: seeds the reference would sort (collect_seed_hits); n_sorted: seeds this part actually writes and sorts (after the pre-filter) */
+struct LqQStat { uint32_t n_kept; uint32_t sum_span_kept; uint64_t n_seeds; uint64_t sum_span_seeds; uint32_t gate_closed; float avg_span; uint64_t n_sorted; };
 
 struct LqMapScratch {
     LqDevBuf arena1, arena2, bkt, grp, misc, ovl, ws;
     void release() { arena1.release(); arena2.release(); bkt.release(); grp.release(); misc.release(); ovl.release(); ws.release(); }
 };
 
-struct LqMapStats { uint64_t n_seeds, n_groups, n_chains, n_ovl, n_batches, n_walk_buckets; };
+struct LqMapStats { uint64_t n_seeds, n_groups, n_chains, n_ovl, n_batches, n_walk_buckets, n_seeds_all; };
 
 /* Map every query against the part `ix`.  h_self_off/h_self_list: per query, target rids of this part
  * with the same name (CSR); h_qrank/h_trank: name ranks (only used with ava).  Appends accepted overlaps
