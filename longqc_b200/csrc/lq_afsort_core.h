@@ -52,6 +52,69 @@ LQ_HD void lq_af_walk(const uint8_t *dig, uint32_t n, const uint32_t *cnt, const
     }
 }
 
+/* ---- the same walk with the per-region state packed for a short dependent chain (what the device runs) ----
+ * The walk is one thread chasing a pointer through 256 queues, so its speed is the latency of one step.  State per region c:
+ *   pb[c]    = { pos, base }: next unread position of region c (bucket-relative), and the position cache[c][0] holds
+ *   cache[c] = the digits of positions base .. base+15
+ * One step = one 8-byte load (pb[c]) and one byte load (the digit); the digit's own pb[] entry is both this element's
+ * destination and the next step's position.  lq_afw_run() walks until every element is placed or a region runs out of cached
+ * digits; the caller then refills every region's cache (on the device: the whole warp, in parallel) and calls it again. */
+typedef struct
+#ifdef __CUDACC__
+__align__(8)
+#endif
+{ uint32_t x, y; } lq_afw_pb;
+typedef struct { uint32_t k, c, arrived, step; } lq_afw_state;
+#define LQ_AFW_CACHE 16
+
+/* start[0..256]: region starts, start[256] = n.  Sets the state to the first non-empty region and marks every cache empty. */
+LQ_HD void lq_afw_init_state(lq_afw_state *s, const uint32_t *start)
+{
+    uint32_t k = 0;
+    while (k < 256 && start[k + 1] == start[k]) ++k;
+    s->k = k; s->c = k; s->arrived = 0; s->step = 0;
+}
+
+/* returns 1 when all n elements are placed, 0 when region s->c needs a refill */
+LQ_HD int lq_afw_run(lq_afw_state *s, uint32_t n, const uint32_t *start, lq_afw_pb *pb, const uint8_t *cache, uint32_t *dest)
+{
+    uint32_t k = s->k, c = s->c, arrived = s->arrived, step = s->step;
+    uint32_t start_k = k < 256 ? start[k] : 0, end_k = k < 256 ? start[k + 1] : 0;
+    lq_afw_pb cur = pb[c];
+    int done = 1;
+    while (step < n) {
+        const uint32_t j = cur.x - cur.y;
+        if (j >= LQ_AFW_CACHE) { done = 0; break; }
+        const uint32_t d = cache[c * LQ_AFW_CACHE + j], p = cur.x;
+        pb[c].x = p + 1;
+        ++step;
+        if (d != k) { cur = pb[d]; dest[p] = cur.x; c = d; }   /* slot = number of digit-d elements picked before = the next pick of region d */
+        else {
+            dest[p] = start_k + arrived++;                     /* arrivals into the outer-loop region lag its pick-ups by the open hole */
+            c = k;
+            if (pb[k].x == end_k) {                            /* region k complete: open the next non-exhausted region */
+                do { ++k; } while (k < 256 && pb[k].x == start[k + 1]);
+                if (k < 256) { c = k; start_k = start[k]; end_k = start[k + 1]; arrived = pb[k].x - start_k; }
+                else c = 0;
+            }
+            cur = pb[c];
+        }
+    }
+    s->k = k; s->c = c; s->arrived = arrived; s->step = step;
+    return done;
+}
+
+/* host form of the refill (the device does it with two aligned 16-byte loads per region) */
+LQ_HD void lq_afw_refill_host(const uint8_t *dig, uint32_t n, const uint32_t *start, lq_afw_pb *pb, uint8_t *cache)
+{
+    for (uint32_t r = 0; r < 256; ++r) {
+        const uint32_t p = pb[r].x;
+        if (p >= start[r + 1] || p == pb[r].y) continue;
+        for (uint32_t j = 0; j < LQ_AFW_CACHE; ++j) cache[r * LQ_AFW_CACHE + j] = p + j < n ? dig[p + j] : 0;
+        pb[r].y = p;
+    }
+}
+
 /* Closed form for exactly two non-empty digits d0 < d1 (regions [0,n0) and [n0,n)).
  * fr[p]  = 1 if p is "foreign" (p < n0 with digit d1, or p >= n0 with digit d0)
  * rk[p]  = number of foreign positions before p within p's own region (exclusive rank)

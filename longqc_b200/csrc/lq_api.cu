@@ -12,6 +12,8 @@
 #include <unordered_map>
 #include <algorithm>
 #include <chrono>
+#include <thread>
+#include <future>
 #include <string.h>
 #include "lq_cuda.cuh"
 #include "lq_device.h"
@@ -22,6 +24,31 @@
 #include "lq_prof.h"
 
 int lq_qualsum_run(const uint8_t *d_qual, const uint64_t *d_off, uint32_t n_reads, double *d_sum, cudaStream_t st);
+
+/* host worker threads for the per-query bookkeeping (interval folding, table rows): LQCOV_HOST_THREADS, else the cores we may use, <= 16 */
+static unsigned host_threads()
+{
+    static unsigned n = 0;
+    if (n == 0) {
+        const char *e = getenv("LQCOV_HOST_THREADS");
+        n = e ? (unsigned)atoi(e) : std::thread::hardware_concurrency();
+        if (n < 1) n = 1;
+        if (n > 16) n = 16;
+    }
+    return n;
+}
+/* fn(lo, hi, chunk index) over [0, n) cut into contiguous chunks, one thread each */
+template <class F> static void parallel_chunks(uint32_t n, unsigned n_chunks, F fn)
+{
+    if (n_chunks > n) n_chunks = n ? n : 1;
+    if (n_chunks <= 1) { fn(0u, n, 0u); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < n_chunks; ++t) {
+        const uint32_t lo = (uint32_t)((uint64_t)n * t / n_chunks), hi = (uint32_t)((uint64_t)n * (t + 1) / n_chunks);
+        th.emplace_back([=]() { fn(lo, hi, t); });
+    }
+    for (size_t t = 0; t < th.size(); ++t) th[t].join();
+}
 
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -214,30 +241,9 @@ extern "C" int lqcov_part_gather_buffers(lqcov_ctx *c, uint64_t n_total, void **
     return 0;
 }
 
-extern "C" int lqcov_part_finish(lqcov_ctx *c, const lqcov_reads_t *part)
+/* name tables for the self-diagonal / dual-mapping skips (lqmap.c:180-189): host-only work */
+static void build_name_tables(lqcov_ctx *c, const lqcov_reads_t *part)
 {
-    double t0 = now_ms();
-    LqIndexDev *ix = &c->ix;
-    if (c->use_full) { std::swap(ix->rec.key, c->full.key); std::swap(ix->rec.y, c->full.y); ix->rec.n = c->full.n; ix->rec.has_span = 0; c->use_full = false; }
-    LQ_TRY(lq_index_finish(ix, &ix->rec, c->ws, c->st));
-    ix->n_seq = part->n;
-    LQ_TRY(ix->tlen.ensure(((size_t)part->n + 1) * 4));
-    {
-        std::vector<uint32_t> tl(part->n);
-        for (uint32_t i = 0; i < part->n; ++i) tl[i] = (uint32_t)(part->seq_off[i + 1] - part->seq_off[i]);
-        if (part->n) LQ_CUDA_OK(cudaMemcpyAsync(ix->tlen.p, tl.data(), (size_t)part->n * 4, cudaMemcpyHostToDevice, c->st));
-        LQ_CUDA_OK(cudaStreamSynchronize(c->st));
-        lq_prof_h2d((uint64_t)part->n * 4);
-    }
-    if (c->mid_occ <= 0) { /* map.c:50-51: only while still unset, i.e. from the first part */
-        uint64_t nd = 0;
-        LQ_TRY(lq_index_mid_occ(ix, c->opt.mid_occ_frac, &c->mid_occ, &nd, c->ws, c->st));
-        if (c->opt.verbose >= 3) fprintf(stderr, "[M::lqcov] mid_occ = %d (distinct minimizers: %llu)\n", c->mid_occ, (unsigned long long)nd);
-    }
-    LQ_CUDA_OK(cudaStreamSynchronize(c->st));
-    c->stats.t_index_ms += now_ms() - t0;
-    /* name tables for the self-diagonal / dual-mapping skips (lqmap.c:180-189) */
-    const double t_names = now_ms();
     const uint32_t nq = c->nq;
     /* (query, target) pairs with equal names, then CSR by query with ascending target ids */
     std::vector<std::pair<uint32_t, uint32_t> > hits;
@@ -264,10 +270,45 @@ extern "C" int lqcov_part_finish(lqcov_ctx *c, const lqcov_reads_t *part)
         for (uint32_t q = 0; q < nq; ++q) c->qrank[q] = (uint32_t)(std::lower_bound(uniq.begin(), uniq.end(), all[q]) - uniq.begin());
         for (uint32_t t = 0; t < part->n; ++t) c->trank[t] = (uint32_t)(std::lower_bound(uniq.begin(), uniq.end(), all[nq + t]) - uniq.begin());
     }
+}
+
+static int part_finish_device(lqcov_ctx *c, const lqcov_reads_t *part)
+{
+    LqIndexDev *ix = &c->ix;
+    if (c->use_full) { std::swap(ix->rec.key, c->full.key); std::swap(ix->rec.y, c->full.y); ix->rec.n = c->full.n; ix->rec.has_span = 0; c->use_full = false; }
+    LQ_TRY(lq_index_finish(ix, &ix->rec, c->ws, c->st));
+    ix->n_seq = part->n;
+    LQ_TRY(ix->tlen.ensure(((size_t)part->n + 1) * 4));
+    {
+        std::vector<uint32_t> tl(part->n);
+        for (uint32_t i = 0; i < part->n; ++i) tl[i] = (uint32_t)(part->seq_off[i + 1] - part->seq_off[i]);
+        if (part->n) LQ_CUDA_OK(cudaMemcpyAsync(ix->tlen.p, tl.data(), (size_t)part->n * 4, cudaMemcpyHostToDevice, c->st));
+        LQ_CUDA_OK(cudaStreamSynchronize(c->st));
+        lq_prof_h2d((uint64_t)part->n * 4);
+    }
+    if (c->mid_occ <= 0) { /* map.c:50-51: only while still unset, i.e. from the first part */
+        uint64_t nd = 0;
+        LQ_TRY(lq_index_mid_occ(ix, c->opt.mid_occ_frac, &c->mid_occ, &nd, c->ws, c->st));
+        if (c->opt.verbose >= 3) fprintf(stderr, "[M::lqcov] mid_occ = %d (distinct minimizers: %llu)\n", c->mid_occ, (unsigned long long)nd);
+    }
+    LQ_CUDA_OK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int lqcov_part_finish(lqcov_ctx *c, const lqcov_reads_t *part)
+{
+    const double t0 = now_ms();
+    /* the name tables are host-only work: built on a second thread while the device sorts the records */
+    std::future<void> names = std::async(std::launch::async, build_name_tables, c, part);
+    const int rc = part_finish_device(c, part);
+    c->stats.t_index_ms += now_ms() - t0;
+    const double t1 = now_ms();
+    names.get();
+    c->stats.t_post_ms += now_ms() - t1;
+    if (rc != 0) return rc;
     c->part_ready = true;
-    c->stats.target_minimizers += ix->n_rec;
+    c->stats.target_minimizers += c->ix.n_rec;
     c->stats.n_parts += 1; c->stats.mid_occ = c->mid_occ;
-    c->stats.t_post_ms += now_ms() - t_names;
     if (c->opt.verbose >= 3) fprintf(stderr, "[M::lqcov] loaded/built the index for %u target sequence(s)\n", part->n);
     return 0;
 }
@@ -309,8 +350,11 @@ extern "C" int lqcov_map_part(lqcov_ctx *c)
         std::vector<lqh_sub> cv(ovl.size());
         std::vector<uint32_t> at(off.begin(), off.end() - 1);
         for (size_t i = 0; i < ovl.size(); ++i) { lqh_sub s; s.start = ovl[i].start; s.end = ovl[i].end; cv[at[ovl[i].q]++] = s; }
-        for (uint32_t q = 0; q < c->nq; ++q)
-            if (off[q + 1] > off[q]) lqh_filter_redundant(&c->ovlp[q], cv.data() + off[q], off[q + 1] - off[q], (uint32_t)c->opt.min_coverage);
+        const uint32_t min_cov = (uint32_t)c->opt.min_coverage;
+        parallel_chunks(c->nq, host_threads(), [&](uint32_t lo, uint32_t hi, unsigned) {   /* queries are independent */
+            for (uint32_t q = lo; q < hi; ++q)
+                if (off[q + 1] > off[q]) lqh_filter_redundant(&c->ovlp[q], cv.data() + off[q], off[q + 1] - off[q], min_cov);
+        });
     }
     c->stats.seeds += ms.n_seeds; c->stats.groups += ms.n_groups; c->stats.chains += ms.n_chains; c->stats.overlaps += ms.n_ovl;
     c->stats.batches += ms.n_batches; c->stats.walk_buckets += ms.n_walk_buckets;
@@ -356,17 +400,27 @@ extern "C" int lqcov_table(lqcov_ctx *c, char **buf, size_t *len)
         LQ_CUDA_OK(cudaStreamSynchronize(c->st));
     }
     lq_prof_d2h((uint64_t)c->nq * 16); lq_prof_collect();
-    lqh_str out; out.l = out.m = 0; out.s = 0;
-    for (uint32_t q = 0; q < c->nq; ++q) {
-        const uint32_t n_mini = (uint32_t)(c->qfirst[q + 1] - c->qfirst[q]);
-        if (n_mini == 0) { /* the reference divides by zero here (minimap2-coverage.c:558, SIGFPE) */
+    for (uint32_t q = 0; q < c->nq; ++q)
+        if (c->qfirst[q + 1] == c->qfirst[q]) { /* the reference divides by zero here (minimap2-coverage.c:558, SIGFPE) */
             fprintf(stderr, "[lqcov] ERROR: query '%s' yields no minimizer; the reference binary crashes on such input\n", c->qname[q].c_str());
-            free(out.s); return -1;
+            return -1;
         }
-        lqh_format_row(&out, c->qname[q].data(), c->qname[q].size(), c->qlen[q], c->q_has_qual, c->qsum_p[q], lam[q], lam2[q], n_mini, n_match[q], c->avg_k[q],
-                       &c->ovlp[q], c->opt.min_coverage, c->opt.filter);
-    }
-    if (!out.s) { out.s = (char*)malloc(1); out.s[0] = 0; }
+    /* rows are independent: contiguous query ranges are formatted by the host threads and concatenated in order */
+    (void)lqh_meanQ(NULL, 0);   /* builds the Phred table once, before the threads read it */
+    const unsigned nt = host_threads();
+    std::vector<lqh_str> piece(nt);
+    for (unsigned t = 0; t < nt; ++t) { piece[t].l = piece[t].m = 0; piece[t].s = 0; }
+    parallel_chunks(c->nq, nt, [&](uint32_t lo, uint32_t hi, unsigned t) {
+        for (uint32_t q = lo; q < hi; ++q)
+            lqh_format_row(&piece[t], c->qname[q].data(), c->qname[q].size(), c->qlen[q], c->q_has_qual, c->qsum_p[q], lam[q], lam2[q],
+                           (uint32_t)(c->qfirst[q + 1] - c->qfirst[q]), n_match[q], c->avg_k[q], &c->ovlp[q], c->opt.min_coverage, c->opt.filter);
+    });
+    lqh_str out; out.l = 0; out.m = 1; out.s = 0;
+    for (unsigned t = 0; t < nt; ++t) out.m += piece[t].l;
+    out.s = (char*)malloc(out.m);
+    if (!out.s) { fprintf(stderr, "[lqcov] out of host memory\n"); return -1; }
+    for (unsigned t = 0; t < nt; ++t) { if (piece[t].l) memcpy(out.s + out.l, piece[t].s, piece[t].l); out.l += piece[t].l; free(piece[t].s); }
+    out.s[out.l] = 0;
     *buf = out.s; *len = out.l;
     c->stats.t_post_ms += now_ms() - t0;
     return 0;

@@ -98,7 +98,7 @@ void afsort_levels(const uint64_t *key, uint32_t n, uint32_t *idx, int use_two)
             for (uint32_t p = 0; p < m; ++p) { dig[beg + p] = (uint8_t)(key[idx[beg + p]] >> s); ++cnt[dig[beg + p]]; }
             for (int d = 0; d < 256; ++d) { start[d] = acc; acc += cnt[d]; nb += cnt[d] != 0; }
             if (nb > 1) {
-                if (nb == 2 && use_two) {
+                if (nb == 2 && (use_two & 1)) {
                     int d0 = -1, d1 = -1;
                     for (int d = 0; d < 256; ++d) if (cnt[d]) { if (d0 < 0) d0 = d; else d1 = d; }
                     const uint32_t n0 = cnt[d0];
@@ -111,6 +111,15 @@ void afsort_levels(const uint64_t *key, uint32_t n, uint32_t *idx, int use_two)
                     }
                     for (uint32_t p = 0; p < m; ++p)
                         dest[beg + p] = lq_af_two_dest(p, n0, fr[p], rk[p], (uint32_t)P.size(), P.data(), Z.data());
+                } else if (use_two & 2) { // the device's form of the walk: packed per-region state, cached digits, refill rounds
+                    uint32_t st257[257]; lq_afw_pb pb[256]; uint8_t cache[256 * LQ_AFW_CACHE]; lq_afw_state ws;
+                    for (int d = 0; d < 256; ++d) { st257[d] = start[d]; pb[d].x = start[d]; pb[d].y = start[d] - LQ_AFW_CACHE; }
+                    st257[256] = m;
+                    lq_afw_init_state(&ws, st257);
+                    for (;;) {
+                        lq_afw_refill_host(dig.data() + beg, m, st257, pb, cache);
+                        if (lq_afw_run(&ws, m, st257, pb, cache, dest.data() + beg)) break;
+                    }
                 } else lq_af_walk(dig.data() + beg, m, cnt, start, head, dest.data() + beg);
                 for (uint32_t p = 0; p < m; ++p) tmp[beg + dest[beg + p]] = idx[beg + p];
                 memcpy(idx + beg, tmp.data() + beg, (size_t)m * 4);

@@ -18,7 +18,7 @@
 void LqQueryDev::release()
 {
     reads.release(); mins.release(); first.release(); qtied.release(); dup.release(); dup_tmp.release(); dup_tk.release(); dup_ty.release(); dup_ts.release(); dup_hist.release(); nmatch_buf.release(); lambda.release(); lambda2.release(); mcnt.release();
-    keep.release(); neff.release(); krank.release(); soff.release(); qstat.release();
+    keep.release(); neff.release(); krank.release(); soff.release(); qstat.release(); fmask.release();
     self_off.release(); self_list.release(); qrank.release(); trank.release();
 }
 
@@ -52,12 +52,23 @@ __global__ void lq_lookup_k(const uint32_t *__restrict__ qkey, const uint64_t *_
     const uint32_t c = counts[key];
     const bool kept = !gate && (int64_t)c < (int64_t)mid_occ;          /* lqmap.c:159,166 */
     uint32_t n = kept ? c : 0;
-    if (n && (t.ava || (t.no_self && t.self_off[q + 1] > t.self_off[q]))) {
+    if (n && t.ava) {
         const uint64_t o = offs[key];
         const uint32_t qpos = (uint32_t)y >> 1;
         uint32_t skipped = 0;
         for (uint32_t j = 0; j < c; ++j) skipped += lq_seed_skipped(t, pos[o + j], qpos, q);
         n -= skipped;
+    } else if (n && t.no_self) {
+        /* only the self-diagonal skip: occurrences (rid, rpos == qpos) of a target named like the query, either strand.  The
+         * occurrence list ascends in y = rid<<32 | rpos<<1 | strand, so they are found by binary search. */
+        const uint64_t *pp = pos + offs[key];
+        const uint32_t qpos = (uint32_t)y >> 1;
+        for (uint32_t s = t.self_off[q]; s < t.self_off[q + 1]; ++s) {
+            const uint64_t lo_y = (uint64_t)t.self_list[s] << 32 | (uint64_t)qpos << 1;
+            uint32_t lo = 0, hi = c;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (pp[mid] < lo_y) lo = mid + 1; else hi = mid; }
+            while (lo < c && pp[lo] <= (lo_y | 1ULL)) { --n; ++lo; }
+        }
     }
     keep[mi] = kept; neff[mi] = n;
 }
@@ -164,6 +175,7 @@ struct FlArgs {
     const uint32_t *counts; const uint64_t *offs, *pos;
     MapTables t; const uint32_t *qlen;
     uint32_t thr;                 /* T */
+    uint32_t *mask; uint32_t mstride;   /* survivor bits per occurrence: mstride words per minimizer (lq_filter_count_k -> lq_fill_masked_k) */
     /* fill only */
     const uint32_t *krank; const uint64_t *soff; uint64_t seed_base; SeedArrays s;
     uint32_t q0, q1;
@@ -214,7 +226,8 @@ __global__ void __launch_bounds__(FL_THREADS) lq_filter_count_k(FlArgs a)
             const uint64_t y = a.qy[mi];
             const uint32_t key = a.qkey[mi], c = a.counts[key], qpos = (uint32_t)y >> 1, qstrand = (uint32_t)y & 1;
             const uint64_t *pp = a.pos + a.offs[key];
-            uint32_t n = 0;
+            uint32_t n = 0, mword = 0;
+            uint32_t *mw = a.mask + mi * a.mstride;
             for (uint32_t j0 = 0; j0 < c; j0 += FL_ILP) {
                 uint64_t rr[FL_ILP];
                 #pragma unroll
@@ -223,50 +236,42 @@ __global__ void __launch_bounds__(FL_THREADS) lq_filter_count_k(FlArgs a)
                 for (int u = 0; u < FL_ILP; ++u) {
                     if (j0 + u >= c) break;
                     if (filt && lq_seed_skipped(a.t, rr[u], qpos, q)) continue;
-                    n += fl_get(fl_bins, fl_hash(rr[u], qstrand)) >= a.thr;
+                    const uint32_t live = fl_get(fl_bins, fl_hash(rr[u], qstrand)) >= a.thr;
+                    n += live; mword |= live << ((j0 + u) & 31);
                 }
+                if (((j0 + FL_ILP) & 31) == 0 || j0 + FL_ILP >= c) { mw[j0 >> 5] = mword; mword = 0; }   /* FL_ILP divides 32 */
             }
             a.neff[mi] = n;
         }
     }
 }
 
-/* the seeds that survive, in the reference's order (minimizer order x ascending target position) */
-__global__ void __launch_bounds__(FL_THREADS) lq_fill_filtered_k(FlArgs a)
+/* the seeds that survive, in the reference's order (minimizer order x ascending target position): one thread per minimizer walks
+ * the survivor bits lq_filter_count_k left and writes its own contiguous output range */
+__global__ void lq_fill_masked_k(FlArgs a, uint64_t mi0, uint64_t mi1)
 {
-    for (uint32_t q = a.q0 + blockIdx.x; q < a.q1; q += gridDim.x) {
-        if (a.qtied[q]) continue;
-        __syncthreads();
-        fl_count_runs(a, q, fl_bins);
-        const bool filt = a.t.ava || (a.t.no_self && a.t.self_off[q + 1] > a.t.self_off[q]);
-        const int32_t ql = (int32_t)a.qlen[q];
-        const uint32_t kr0 = a.krank[a.first[q]];
-        for (uint64_t mi = a.first[q] + threadIdx.x; mi < a.first[q + 1]; mi += blockDim.x) {
-            if (!a.keep[mi] || a.neff[mi] == 0) continue;
-            const uint64_t y = a.qy[mi];
-            const uint32_t key = a.qkey[mi], c = a.counts[key], qpos = (uint32_t)y >> 1, qstrand = (uint32_t)y & 1;
-            const uint32_t span = a.qspan ? a.qspan[mi] : (uint32_t)a.k;
-            const uint32_t sm = span << 24 | (a.krank[mi] - kr0);
-            const uint32_t sq_rev = (uint32_t)(ql - ((int32_t)qpos + 1 - (int32_t)span) - 1);
-            const uint64_t *pp = a.pos + a.offs[key];
-            uint64_t at = a.soff[mi] - a.seed_base;
-            for (uint32_t j0 = 0; j0 < c; j0 += FL_ILP) {
-              uint64_t rr[FL_ILP];
-              #pragma unroll
-              for (int u = 0; u < FL_ILP; ++u) rr[u] = j0 + u < c ? pp[j0 + u] : 0;
-              #pragma unroll
-              for (int u = 0; u < FL_ILP; ++u) {
-                if (j0 + u >= c) break;
-                const uint64_t r = rr[u];
-                if (filt && lq_seed_skipped(a.t, r, qpos, q)) continue;
-                if (fl_get(fl_bins, fl_hash(r, qstrand)) < a.thr) continue;
-                const uint32_t rpos = (uint32_t)r >> 1;
-                if (((uint32_t)r & 1) == qstrand) { a.s.sx[at] = (r & 0xffffffff00000000ULL) | rpos; a.s.sq[at] = qpos; }
-                else { a.s.sx[at] = 1ULL << 63 | (r & 0xffffffff00000000ULL) | rpos; a.s.sq[at] = sq_rev; }
-                a.s.sm[at] = sm;
-                ++at;
-              }
-            }
+    const uint64_t mi = mi0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (mi >= mi1 || !a.keep[mi] || a.neff[mi] == 0) return;
+    const uint64_t y = a.qy[mi];
+    const uint32_t q = (uint32_t)(y >> 32);
+    if (a.qtied[q]) return;                                /* written by lq_fill_k */
+    const uint32_t key = a.qkey[mi], c = a.counts[key], qpos = (uint32_t)y >> 1, qstrand = (uint32_t)y & 1;
+    const uint32_t span = a.qspan ? a.qspan[mi] : (uint32_t)a.k;
+    const uint32_t sm = span << 24 | (a.krank[mi] - a.krank[a.first[q]]);
+    const uint32_t sq_rev = (uint32_t)((int32_t)a.qlen[q] - ((int32_t)qpos + 1 - (int32_t)span) - 1);
+    const uint64_t *pp = a.pos + a.offs[key];
+    const uint32_t *mw = a.mask + mi * a.mstride;
+    uint64_t at = a.soff[mi] - a.seed_base;
+    for (uint32_t w0 = 0; w0 * 32 < c; ++w0) {
+        uint32_t m = mw[w0];
+        while (m) {
+            const uint32_t j = w0 * 32 + (uint32_t)(__ffs(m) - 1); m &= m - 1;
+            const uint64_t r = pp[j];
+            const uint32_t rpos = (uint32_t)r >> 1;
+            if (((uint32_t)r & 1) == qstrand) { a.s.sx[at] = (r & 0xffffffff00000000ULL) | rpos; a.s.sq[at] = qpos; }
+            else { a.s.sx[at] = 1ULL << 63 | (r & 0xffffffff00000000ULL) | rpos; a.s.sq[at] = sq_rev; }
+            a.s.sm[at] = sm;
+            ++at;
         }
     }
 }
@@ -295,6 +300,7 @@ struct AfArgs {
     const uint64_t *sx; const uint32_t *sq; uint32_t *idx, *idx2, *dest; uint8_t *dig;
     const AfBkt *cur; const uint32_t *n_cur; AfBkt *nxt; uint32_t *n_nxt; uint32_t *cursor; uint32_t *n_walk;
     AfBkt *wlist; uint32_t *n_wlist; uint32_t *wcursor;   /* tied buckets with > 2 digits: walked by lq_af_walk_k */
+    unsigned long long *n_elem;   /* elements this launch handled (profiling: algorithmic bytes of the launch) */
     int shift;
 };
 
@@ -432,6 +438,7 @@ __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
         const uint32_t beg = a.cur[bcur].beg, n = a.cur[bcur].end - beg;
         uint32_t *idx = a.idx + beg, *idx2 = a.idx2 + beg, *dest = a.dest + beg;
         uint8_t *dig = a.dig + beg;
+        if (lane == 0) atomicAdd(a.n_elem, (unsigned long long)n);
         /* 1. digits + histogram */
         for (uint32_t d = lane; d < 256; d += 32) cnt[d] = 0;
         __syncwarp();
@@ -545,17 +552,31 @@ __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
     }
 }
 
-/* The walk of lq_afsort_core.h with the digits streamed through shared memory: region c's next 16 digits sit in cache[c],
- * refilled with one 16-byte load when exhausted, so a step costs shared-memory latency instead of a global byte load. */
+/* The walk of lq_afsort_core.h (lq_afw_run): one lane chases the pointer, so what counts is the latency of one step and how
+ * many walks an SM holds.  Per walk 7 KB of shared memory: region starts, {pos, base} per region, 16 cached digits per region;
+ * a step is one 8-byte and one 1-byte shared-memory load.  When a region's cached digits run out the whole warp refills every
+ * region that moved (two aligned 16-byte loads each, shifted to the region's position) and the walk resumes. */
 #define AFW_WARPS 2
+struct AfwSmem { uint32_t start[260]; lq_afw_pb pb[256]; uint4 cache[256]; };
+
+__device__ __forceinline__ uint4 afw_load16(const uint8_t *addr)   /* 16 bytes from an arbitrary address (reads up to 31 bytes past it: the arena is padded) */
+{
+    const uintptr_t A = (uintptr_t)addr & ~(uintptr_t)15; const uint32_t o = (uint32_t)((uintptr_t)addr & 15), q = o >> 2, sh = (o & 3) * 8;
+    const uint4 lo = *(const uint4*)A, hi = *(const uint4*)(A + 16);
+    const uint32_t t0 = q == 0 ? lo.x : q == 1 ? lo.y : q == 2 ? lo.z : lo.w;
+    const uint32_t t1 = q == 0 ? lo.y : q == 1 ? lo.z : q == 2 ? lo.w : hi.x;
+    const uint32_t t2 = q == 0 ? lo.z : q == 1 ? lo.w : q == 2 ? hi.x : hi.y;
+    const uint32_t t3 = q == 0 ? lo.w : q == 1 ? hi.x : q == 2 ? hi.y : hi.z;
+    const uint32_t t4 = q == 0 ? hi.x : q == 1 ? hi.y : q == 2 ? hi.z : hi.w;
+    return make_uint4(__funnelshift_r(t0, t1, sh), __funnelshift_r(t1, t2, sh), __funnelshift_r(t2, t3, sh), __funnelshift_r(t3, t4, sh));
+}
+
 __global__ void __launch_bounds__(AFW_WARPS * 32) lq_af_walk_k(AfArgs a)
 {
-    __shared__ uint32_t s_cnt[AFW_WARPS][256], s_start[AFW_WARPS][256], s_head[AFW_WARPS][256], s_tag[AFW_WARPS][256];
-    __shared__ uint4 s_cache[AFW_WARPS][256];
-    __shared__ uint64_t s_sk[AFW_WARPS][AF_SN]; __shared__ uint32_t s_si[AFW_WARPS][AF_SN];
+    __shared__ __align__(16) AfwSmem s_w[AFW_WARPS];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lt = (1u << lane) - 1;
-    uint32_t *cnt = s_cnt[wid], *start = s_start[wid], *head = s_head[wid], *tag = s_tag[wid];
-    uint4 *cache = s_cache[wid];
+    AfwSmem &S = s_w[wid];
+    uint32_t *start = S.start, *cnt = (uint32_t*)S.pb;   /* cnt[] shares the pb[] storage: histogram before the walk, sizes after it */
     const uint32_t nw = *a.n_wlist;
     for (;;) {
         uint32_t b = 0;
@@ -566,7 +587,7 @@ __global__ void __launch_bounds__(AFW_WARPS * 32) lq_af_walk_k(AfArgs a)
         uint32_t *idx = a.idx + beg, *idx2 = a.idx2 + beg, *dest = a.dest + beg;
         const uint8_t *dig = a.dig + beg;
         /* histogram from the digits the level kernel stored */
-        for (uint32_t d = lane; d < 256; d += 32) { cnt[d] = 0; tag[d] = 0xffffffffu; head[d] = 0; }
+        for (uint32_t d = lane; d < 256; d += 32) cnt[d] = 0;
         __syncwarp();
         for (uint32_t p0 = 0; p0 < n; p0 += 32 * AF_U) {
             uint32_t dv[AF_U];
@@ -580,38 +601,37 @@ __global__ void __launch_bounds__(AFW_WARPS * 32) lq_af_walk_k(AfArgs a)
                 __syncwarp();
             }
         }
-        uint32_t loc = 0, ne = 0;
+        uint32_t loc = 0, ne = 0, cc[8];
         #pragma unroll
-        for (int j = 0; j < 8; ++j) { const uint32_t c = cnt[8 * lane + j]; loc += c; if (c) ++ne; }
+        for (int j = 0; j < 8; ++j) { cc[j] = cnt[8 * lane + j]; loc += cc[j]; if (cc[j]) ++ne; }
         uint32_t inc = lq_warp_incl_scan(loc), run = inc - loc;
         #pragma unroll
-        for (int j = 0; j < 8; ++j) { start[8 * lane + j] = run; run += cnt[8 * lane + j]; }
+        for (int j = 0; j < 8; ++j) { start[8 * lane + j] = run; run += cc[j]; }
+        if (lane == 31) start[256] = n;
         const uint32_t nb = lq_warp_sum(ne);
+        __syncwarp();                                    /* every lane has read its counts: pb[] may overwrite them */
+        for (uint32_t r = lane; r < 256; r += 32) { lq_afw_pb e; e.x = start[r]; e.y = start[r] - LQ_AFW_CACHE; S.pb[r] = e; }
         __syncwarp();
-        if (lane == 0) {
-            /* == lq_af_walk(), digit fetch through the cache */
-            const uint8_t *dbase = a.dig;                 /* 256-byte aligned arena pointer: 16-byte chunks of it are aligned */
-            uint32_t k = 0, c, arrived_k = 0;
-            while (k < 256 && cnt[k] == 0) ++k;
-            c = k;
-            for (uint32_t step = 0; step < n; ++step) {
-                const uint32_t p = start[c] + head[c];
-                const uint32_t ab = beg + p, ch = ab >> 4;
-                if (tag[c] != ch) { cache[c] = *(const uint4*)(dbase + ((size_t)ch << 4)); tag[c] = ch; }
-                const uint32_t d = ((const uint8_t*)&cache[c])[ab & 15];
-                ++head[c];
-                if (d == k) dest[p] = start[k] + arrived_k++;
-                else dest[p] = start[d] + head[d];
-                c = d;
-                if (c == k && head[k] == cnt[k]) {
-                    do { ++k; } while (k < 256 && head[k] == cnt[k]);
-                    if (k < 256) { c = k; arrived_k = head[k]; }
-                }
+        lq_afw_state ws;
+        lq_afw_init_state(&ws, start);
+        for (;;) {
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) {                /* refill every region that moved since its last refill */
+                const uint32_t r = lane + 32 * i;
+                const lq_afw_pb e = S.pb[r];
+                if (e.x < start[r + 1] && e.x != e.y) { S.cache[r] = afw_load16(dig + e.x); S.pb[r].y = e.x; }
             }
-            atomicAdd(a.n_walk, 1u);
+            __syncwarp();
+            int done = 0;
+            if (lane == 0) done = lq_afw_run(&ws, n, start, S.pb, (const uint8_t*)S.cache, dest);
+            done = __shfl_sync(0xffffffffu, done, 0);
+            if (done) break;
         }
+        if (lane == 0) { atomicAdd(a.n_walk, 1u); atomicAdd(a.n_elem, (unsigned long long)n); }
         __syncwarp();
-        af_finish_bucket(a, beg, n, nb, cnt, start, idx, idx2, dest, lane, s_sk[wid], s_si[wid]);
+        for (uint32_t d = lane; d < 256; d += 32) cnt[d] = start[d + 1] - start[d];
+        __syncwarp();
+        af_finish_bucket(a, beg, n, nb, cnt, start, idx, idx2, dest, lane, (uint64_t*)S.cache, (uint32_t*)S.cache + 2 * AF_SN);
     }
 }
 
@@ -1040,7 +1060,7 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     uint64_t *d_qoff = sc->misc.as<uint64_t>();
     uint32_t *ctr = (uint32_t*)((char*)sc->misc.p + al((size_t)(nqb + 2) * 8));
     LQ_CUDA_OK(cudaMemcpyAsync(d_qoff, h_qoff.data(), (size_t)(nqb + 1) * 8, cudaMemcpyHostToDevice, st));
-    LQ_CUDA_OK(cudaMemsetAsync(ctr, 0, 64, st));
+    LQ_CUDA_OK(cudaMemsetAsync(ctr, 0, 256, st));   /* ctr[0..15]: u32 counters; ctr[16..47]: 16 u64 element counters (8 levels, 8 walks) */
     *d_qoff_out = d_qoff;
     if (nb == 0) return 0;
     const uint64_t mi0 = h_first[q0], mi1 = h_first[q1];
@@ -1056,9 +1076,8 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         FlArgs fa;
         fill_flargs(&fa, qd, ix, mt, filter_thr, q0, q1);
         fa.seed_base = seed_base; fa.s = b->s;
-        LQ_CUDA_OK(cudaFuncSetAttribute(lq_fill_filtered_k, cudaFuncAttributeMaxDynamicSharedMemorySize, FL_WORDS * 4));
         LqProfScope ps("seed_fill_filtered", st, 1, 0);
-        lq_fill_filtered_k<<<nqb < 148 ? nqb : 148, FL_THREADS, FL_WORDS * 4, st>>>(fa);
+        lq_fill_masked_k<<<lq_grid(mi1 - mi0, 128), 128, 0, st>>>(fa, mi0, mi1);
         LQ_CUDA_OK(cudaGetLastError());
     }
     /* bucket lists: at most nb/65 + nqb live buckets per level */
@@ -1071,6 +1090,8 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     lq_iota_k<<<lq_grid(nb, 256), 256, 0, st>>>(b->idx, nb);
     lq_af_init_k<<<lq_grid(nqb, 128), 128, 0, st>>>(nqb, d_qoff, b->s.sx, b->idx, bk[0], ctr + 0);
     LQ_CUDA_OK(cudaGetLastError());
+    static const char *lvl_name[8] = { "seed_sort_s0", "seed_sort_s8", "seed_sort_s16", "seed_sort_s24", "seed_sort_s32", "seed_sort_s40", "seed_sort_s48", "seed_sort_s56" };
+    static const char *wlk_name[8] = { "seed_walk_s0", "seed_walk_s8", "seed_walk_s16", "seed_walk_s24", "seed_walk_s32", "seed_walk_s40", "seed_walk_s48", "seed_walk_s56" };
     int cur = 0;
     for (int shift = 56; shift >= 0; shift -= 8) {
         AfArgs a;
@@ -1080,10 +1101,11 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         LQ_CUDA_OK(cudaMemsetAsync(ctr + (cur ^ 1), 0, 4, st));
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 2, 0, 4, st));
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 9, 0, 8, st));
-        static const char *lvl_name[8] = { "seed_sort_s0", "seed_sort_s8", "seed_sort_s16", "seed_sort_s24", "seed_sort_s32", "seed_sort_s40", "seed_sort_s48", "seed_sort_s56" };
+        unsigned long long *n_elem = (unsigned long long*)(ctr + 16);
+        a.n_elem = n_elem + (shift >> 3);
         { LqProfScope ps(lvl_name[shift >> 3], st, 1, 0);
           lq_af_level_k<<<148 * 16, AF_WARPS * 32, 0, st>>>(a); }
-        static const char *wlk_name[8] = { "seed_walk_s0", "seed_walk_s8", "seed_walk_s16", "seed_walk_s24", "seed_walk_s32", "seed_walk_s40", "seed_walk_s48", "seed_walk_s56" };
+        a.n_elem = n_elem + 8 + (shift >> 3);
         { LqProfScope ps(wlk_name[shift >> 3], st, 1, 0);
           lq_af_walk_k<<<148 * 16, AFW_WARPS * 32, 0, st>>>(a); }
         LQ_CUDA_OK(cudaGetLastError());
@@ -1093,10 +1115,16 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     lq_gather_k<<<lq_grid(nb, 256), 256, 0, st>>>(nb, b->idx, b->s, b->ax, b->aq, b->am);
     LQ_CUDA_OK(cudaGetLastError());
     if (stats) {
-        uint32_t w = 0;
+        uint32_t w = 0; unsigned long long ne[16];
         LQ_CUDA_OK(cudaMemcpyAsync(&w, ctr + 3, 4, cudaMemcpyDeviceToHost, st));
+        LQ_CUDA_OK(cudaMemcpyAsync(ne, ctr + 16, sizeof ne, cudaMemcpyDeviceToHost, st));
         LQ_CUDA_OK(cudaStreamSynchronize(st));
         stats->n_walk_buckets += w;
+        if (lq_prof_on()) {
+            /* algorithmic bytes per element. level: idx 4 + key gather 8 + tie flag 4 + digit 1w+1r + dest 4w+4r + permute (4r 4w 4r 4w) = 42;
+             * walk: digit 1r (histogram) + 1r (walk) + dest 4w+4r + permute 16 = 26 */
+            for (int l = 0; l < 8; ++l) { lq_prof_add_bytes(lvl_name[l], ne[l] * 42ULL); lq_prof_add_bytes(wlk_name[l], ne[8 + l] * 26ULL); }
+        }
     }
     return 0;
 }
@@ -1109,11 +1137,14 @@ static void fill_flargs(FlArgs *fa, LqQueryDev *qd, const LqIndexDev *ix, const 
     fa->t = mt; fa->qlen = qd->reads.len.as<uint32_t>(); fa->thr = thr;
     fa->krank = qd->krank.as<uint32_t>(); fa->soff = qd->soff.as<uint64_t>(); fa->seed_base = 0; fa->s.sx = 0; fa->s.sq = 0; fa->s.sm = 0;
     fa->q0 = q0; fa->q1 = q1;
+    fa->mask = qd->fmask.as<uint32_t>(); fa->mstride = qd->fmask_stride;
 }
 
 /* T of the pre-filter, 0 = off (debug hook, thresholds beyond the 4-bit counters, LQCOV_NO_SEED_FILTER=1) */
-static uint32_t filter_threshold(const LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt)
+static uint32_t filter_threshold(const LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int mid_occ)
 {
+    /* the survivor bits take ceil(mid_occ/32) words per query minimizer: not worth it for absurd thresholds */
+    if (mid_occ <= 0 || (uint64_t)qd->n_min * (uint64_t)((mid_occ + 31) / 32) * 4 > (8ULL << 30)) return 0;
     static const int off = getenv("LQCOV_NO_SEED_FILTER") ? atoi(getenv("LQCOV_NO_SEED_FILTER")) : 0;
     if (off) return 0;
     const int max_span = qd->mins.has_span ? 255 : ix->k;
@@ -1138,9 +1169,10 @@ static int run_lookup(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt,
     LQ_TRY(qd->qstat.ensure(((size_t)nq + 1) * sizeof(LqQStat)));
     h_stat->resize(nq);
     if (nm == 0) { for (uint32_t q = 0; q < nq; ++q) memset(&(*h_stat)[q], 0, sizeof(LqQStat)); return 0; }
-    lq_prof_count_launch(2); lq_prof_h2d(((uint64_t)nq + 1 + h_self_off[nq]) * 4); lq_prof_d2h((uint64_t)nq * sizeof(LqQStat));
+    lq_prof_count_launch(1); lq_prof_h2d(((uint64_t)nq + 1 + h_self_off[nq]) * 4); lq_prof_d2h((uint64_t)nq * sizeof(LqQStat));
+    { LqProfScope ps("seed_lookup", st, 1, nm * (12 + 4 + 8 + 8 * 7 + 8));   /* minimizer 12 B, count 4, offset 8, ~7 probes of the self-hit search, 8 written */
     lq_lookup_k<<<lq_grid(nm, 256), 256, 0, st>>>(qd->mins.key.as<uint32_t>(), qd->mins.y.as<uint64_t>(), nm, ix->counts.as<uint32_t>(), ix->offs.as<uint64_t>(),
-        ix->rec.y.as<uint64_t>(), mid_occ, *mt, qd->lambda.as<uint64_t>(), qd->reads.len.as<uint32_t>(), opt->covt, qd->keep.as<uint32_t>(), qd->neff.as<uint32_t>());
+        ix->rec.y.as<uint64_t>(), mid_occ, *mt, qd->lambda.as<uint64_t>(), qd->reads.len.as<uint32_t>(), opt->covt, qd->keep.as<uint32_t>(), qd->neff.as<uint32_t>()); }
     LQ_CUDA_OK(cudaGetLastError());
     LQ_TRY((lq_exclusive_scan<uint32_t, uint32_t>(qd->keep.as<uint32_t>(), qd->krank.as<uint32_t>(), nm, 1, sc->ws, st)));
     lq_qstat_k<<<lq_grid((size_t)nq * 32, 256), 256, 0, st>>>(nq, qd->first.as<uint64_t>(), qd->keep.as<uint32_t>(), qd->neff.as<uint32_t>(),
@@ -1148,6 +1180,8 @@ static int run_lookup(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt,
     LQ_CUDA_OK(cudaGetLastError());
     if (filter_thr) { /* seeds of runs too short to chain are not written for queries without tied keys */
         FlArgs fa;
+        qd->fmask_stride = (uint32_t)((mid_occ + 31) / 32);   /* kept minimizers occur < mid_occ times */
+        LQ_TRY(qd->fmask.ensure((size_t)nm * qd->fmask_stride * 4 + 64));
         fill_flargs(&fa, qd, ix, *mt, filter_thr, 0, nq);
         LQ_CUDA_OK(cudaFuncSetAttribute(lq_filter_count_k, cudaFuncAttributeMaxDynamicSharedMemorySize, FL_WORDS * 4));
         LqProfScope ps("seed_filter", st, 1, 0);
@@ -1171,8 +1205,13 @@ int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int m
     const uint32_t nq = qd->nq;
     MapTables mt;
     if (nq == 0) return 0;
-    const uint32_t filter_thr = filter_threshold(qd, ix, opt);
+    const uint32_t filter_thr = filter_threshold(qd, ix, opt, mid_occ);
     LQ_TRY(run_lookup(qd, ix, opt, mid_occ, &mt, filter_thr, h_self_off, h_self_list, h_qrank, h_trank, sc, h_stat, st));
+    if (filter_thr && lq_prof_on()) {   /* algorithmic bytes of the pre-filter: both kernels stream the 8-byte occurrence lists of the filtered queries twice */
+        uint64_t occ = 0, kept = 0;
+        for (uint32_t q = 0; q < nq; ++q) if ((*h_stat)[q].n_sorted != (*h_stat)[q].n_seeds) { occ += (*h_stat)[q].n_seeds; kept += (*h_stat)[q].n_sorted; }
+        lq_prof_add_bytes("seed_filter", occ * 16); lq_prof_add_bytes("seed_fill_filtered", occ * 16 + kept * 16);
+    }
     std::vector<uint64_t> h_first((size_t)nq + 1);
     LQ_CUDA_OK(cudaMemcpyAsync(h_first.data(), qd->first.p, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, st));
     LQ_CUDA_OK(cudaStreamSynchronize(st));

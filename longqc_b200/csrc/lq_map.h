@@ -28,9 +28,10 @@ struct LqQueryDev {
     /* per part */
     LqDevBuf keep, neff, krank, soff; /* u32[n_min], u32[n_min], u32[n_min+1], u64[n_min+1] */
     LqDevBuf qstat;                   /* per query: LqQStat */
+    LqDevBuf fmask; uint32_t fmask_stride; /* pre-filter survivor bits: fmask_stride u32 words per query minimizer */
     LqDevBuf self_off, self_list, qrank, trank; /* self-hit tables (u32) */
     LqMinimizers dup_tmp; LqDevBuf dup_tk, dup_ty, dup_ts, dup_hist, nmatch_buf; /* reusable scratch */
-    LqQueryDev() : nq(0), n_min(0) {}
+    LqQueryDev() : nq(0), n_min(0), fmask_stride(0) {}
     void release();
 };
 

@@ -35,6 +35,7 @@ void lq_prof_end(cudaStream_t st, uint64_t launches, uint64_t bytes)
     g_pending.push_back(p); g_open = 0;
 }
 void lq_prof_count_launch(uint64_t n) { g_launches += n; }
+void lq_prof_add_bytes(const char *name, uint64_t bytes) { if (g_on && bytes) slot(name)->bytes += bytes; }
 void lq_prof_h2d(uint64_t b) { g_h2d += b; }
 void lq_prof_d2h(uint64_t b) { g_d2h += b; }
 void lq_prof_collect()

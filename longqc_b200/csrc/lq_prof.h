@@ -13,6 +13,7 @@ int  lq_prof_on();
 /* bracket a group of launches that make up one named kernel (name must be a string literal) */
 void lq_prof_begin(const char *name, cudaStream_t st);
 void lq_prof_end(cudaStream_t st, uint64_t launches, uint64_t algorithmic_bytes);
+void lq_prof_add_bytes(const char *name, uint64_t bytes);   /* bytes only known after the launch (device-side counters) */
 void lq_prof_count_launch(uint64_t n);           /* launches outside begin/end brackets */
 void lq_prof_h2d(uint64_t bytes);
 void lq_prof_d2h(uint64_t bytes);
