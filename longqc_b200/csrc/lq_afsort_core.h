@@ -115,6 +115,76 @@ LQ_HD void lq_afw_refill_host(const uint8_t *dig, uint32_t n, const uint32_t *st
     }
 }
 
+/* ---- packed form: position and upcoming digits of a region in ONE 16-byte word, so that a step is a single load ----
+ * st[c] = { x: next unread position of region c (bucket-relative),
+ *           y, z, w: the digits of positions x, x+1, ... (byte 0 of y first); top byte of w = how many of them are valid (<= 11) }
+ * The digit's own entry gives the element's destination AND is the next step's load, so the store of dest[p] is deferred by one
+ * step (pend).  This is what lq_af_walk_k runs with one LANE per bucket: the dependent chain of a step is load -> and -> address. */
+typedef struct
+#ifdef __CUDACC__
+__align__(16)
+#endif
+{ uint32_t x, y, z, w; } lq_afp_st;
+typedef struct { uint32_t k, c, arrived, step, start_k, end_k, pend_p; int pend; } lq_afp_walk;
+#define LQ_AFP_DIG 11
+#ifdef __CUDA_ARCH__
+#define LQ_FUNNEL_R8(lo_, hi_) __funnelshift_r((lo_), (hi_), 8)
+#else
+#define LQ_FUNNEL_R8(lo_, hi_) ((uint32_t)((((uint64_t)(hi_) << 32) | (uint64_t)(lo_)) >> 8))
+#endif
+
+LQ_HD void lq_afp_init(lq_afp_walk *s, const uint32_t *start)
+{
+    uint32_t k = 0;
+    while (k < 256 && start[k + 1] == start[k]) ++k;
+    s->k = k; s->c = k < 256 ? k : 0; s->arrived = 0; s->step = 0; s->pend = 0; s->pend_p = 0;
+    s->start_k = k < 256 ? start[k] : 0; s->end_k = k < 256 ? start[k + 1] : 0;
+}
+
+/* returns 1 when all n elements are placed, 0 when region s->c has no cached digit left (refill, then call again) */
+LQ_HD int lq_afp_run(lq_afp_walk *s, uint32_t n, const uint32_t *start, lq_afp_st *st, uint32_t *dest)
+{
+    uint32_t k = s->k, c = s->c, arrived = s->arrived, step = s->step, start_k = s->start_k, end_k = s->end_k, pend_p = s->pend_p;
+    int pend = s->pend, done = 1;
+    while (step < n) {
+        lq_afp_st S = st[c];
+        if (pend) { dest[pend_p] = S.x; pend = 0; }         /* the previous element lands on the next pick of its region */
+        const uint32_t left = S.w >> 24;
+        if (left == 0) { done = 0; break; }
+        const uint32_t d = S.y & 255u, p = S.x;
+        S.x = p + 1; S.y = LQ_FUNNEL_R8(S.y, S.z); S.z = LQ_FUNNEL_R8(S.z, S.w); S.w = ((S.w >> 8) & 0xffffu) | (left - 1) << 24;
+        st[c] = S;
+        ++step;
+        if (d != k) { pend = 1; pend_p = p; c = d; }
+        else {
+            dest[p] = start_k + arrived++;                     /* arrivals into the outer-loop region lag its pick-ups by the open hole */
+            c = k;
+            if (st[k].x == end_k) {                            /* region k complete: open the next non-exhausted region */
+                do { ++k; } while (k < 256 && st[k].x == start[k + 1]);
+                if (k < 256) { c = k; start_k = start[k]; end_k = start[k + 1]; arrived = st[k].x - start_k; }
+                else c = 0;
+            }
+        }
+    }
+    if (done && pend) { dest[pend_p] = st[c].x; pend = 0; }
+    s->k = k; s->c = c; s->arrived = arrived; s->step = step; s->start_k = start_k; s->end_k = end_k; s->pend_p = pend_p; s->pend = pend;
+    return done;
+}
+
+/* refill rule of one region (host form; the device loads the bytes with two aligned 16-byte loads) */
+LQ_HD void lq_afp_refill_host(const uint8_t *dig, const uint32_t *start, lq_afp_st *st, uint32_t r)
+{
+    lq_afp_st S = st[r];
+    const uint32_t avail = start[r + 1] - S.x, left = S.w >> 24, m = avail < LQ_AFP_DIG ? avail : LQ_AFP_DIG;
+    if (left >= m) return;
+    uint8_t b[12]; uint32_t j;
+    for (j = 0; j < 12; ++j) b[j] = j < m ? dig[S.x + j] : 0;
+    S.y = (uint32_t)b[0] | (uint32_t)b[1] << 8 | (uint32_t)b[2] << 16 | (uint32_t)b[3] << 24;
+    S.z = (uint32_t)b[4] | (uint32_t)b[5] << 8 | (uint32_t)b[6] << 16 | (uint32_t)b[7] << 24;
+    S.w = (uint32_t)b[8] | (uint32_t)b[9] << 8 | (uint32_t)b[10] << 16 | m << 24;
+    st[r] = S;
+}
+
 /* Closed form for exactly two non-empty digits d0 < d1 (regions [0,n0) and [n0,n)).
  * fr[p]  = 1 if p is "foreign" (p < n0 with digit d1, or p >= n0 with digit d0)
  * rk[p]  = number of foreign positions before p within p's own region (exclusive rank)

@@ -301,16 +301,20 @@ struct AfArgs {
     const AfBkt *cur; const uint32_t *n_cur; AfBkt *nxt; uint32_t *n_nxt; uint32_t *cursor; uint32_t *n_walk;
     AfBkt *wlist; uint32_t *n_wlist; uint32_t *wcursor;   /* tied buckets with > 2 digits: walked by lq_af_walk_k */
     unsigned long long *n_elem;   /* elements this launch handled (profiling: algorithmic bytes of the launch) */
+    const AfBkt *curb; const uint32_t *n_curb; AfBkt *nxtb; uint32_t *n_nxtb; uint32_t *cursorb;   /* buckets of >= AFB_MIN elements: a CTA each (lq_af_big_k) */
     int shift;
 };
 
+#define AFB_MIN 4096               /* buckets at least this long are sorted by a whole CTA (lq_af_big_k), shorter ones by a warp (lq_af_level_k) */
+
 __global__ void lq_af_init_k(uint32_t nqb, const uint64_t *__restrict__ qoff /* nqb+1 seed offsets in the batch */, const uint64_t *__restrict__ sx,
-                             uint32_t *__restrict__ idx, AfBkt *__restrict__ bkt, uint32_t *__restrict__ n_bkt)
+                             uint32_t *__restrict__ idx, AfBkt *__restrict__ bkt, uint32_t *__restrict__ n_bkt, AfBkt *__restrict__ bktb, uint32_t *__restrict__ n_bktb)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nqb) return;
     const uint32_t beg = (uint32_t)qoff[q], end = (uint32_t)qoff[q + 1], n = end - beg;
-    if (n > LQ_RS_MIN) { const uint32_t at = atomicAdd(n_bkt, 1u); bkt[at].beg = beg; bkt[at].end = end; }
+    if (n >= AFB_MIN) { const uint32_t at = atomicAdd(n_bktb, 1u); bktb[at].beg = beg; bktb[at].end = end; }
+    else if (n > LQ_RS_MIN) { const uint32_t at = atomicAdd(n_bkt, 1u); bkt[at].beg = beg; bkt[at].end = end; }
     else if (n > 1) lq_af_insertion(idx + beg, n, sx); /* ksort.h:132 */
 }
 
@@ -326,12 +330,15 @@ __global__ void lq_iota_k(uint32_t *idx, uint64_t n)
 /* append a sub-bucket to the next level's list: one atomic per warp (the lanes that append are counted with a ballot) */
 __device__ __forceinline__ void af_append(const AfArgs &a, uint32_t beg, uint32_t c, bool doit)
 {
-    const uint32_t m = __ballot_sync(0xffffffffu, doit), lane = threadIdx.x & 31;
-    if (m == 0) return;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(a.n_nxt, (uint32_t)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (doit) { const uint32_t at = base + __popc(m & ((1u << lane) - 1)); a.nxt[at].beg = beg; a.nxt[at].end = beg + c; }
+    const uint32_t lane = threadIdx.x & 31;
+    const bool big = doit && c >= AFB_MIN, small = doit && !big;
+    const uint32_t ms = __ballot_sync(0xffffffffu, small), mb = __ballot_sync(0xffffffffu, big);
+    if ((ms | mb) == 0) return;
+    uint32_t bs = 0, bb = 0;
+    if (lane == 0) { if (ms) bs = atomicAdd(a.n_nxt, (uint32_t)__popc(ms)); if (mb) bb = atomicAdd(a.n_nxtb, (uint32_t)__popc(mb)); }
+    bs = __shfl_sync(0xffffffffu, bs, 0); bb = __shfl_sync(0xffffffffu, bb, 0);
+    if (small) { const uint32_t at = bs + __popc(ms & ((1u << lane) - 1)); a.nxt[at].beg = beg; a.nxt[at].end = beg + c; }
+    if (big) { const uint32_t at = bb + __popc(mb & ((1u << lane) - 1)); a.nxtb[at].beg = beg; a.nxtb[at].end = beg + c; }
 }
 
 /* stable sort of a sub-bucket of 9..64 elements by key, one warp: each lane holds two elements, rank = #smaller + #equal-before
@@ -354,6 +361,7 @@ __device__ __forceinline__ void af_warp_ranksort(uint32_t *idx, uint32_t n, cons
 
 /* after dest[] is known: permute the payload, then hand the sub-buckets on (ksort.h:124-133) */
 #define AF_SN 320
+template <int SN>
 __device__ __forceinline__ void af_finish_bucket(const AfArgs &a, uint32_t beg, uint32_t n, uint32_t nb, const uint32_t *cnt, const uint32_t *start,
                                                  uint32_t *idx, uint32_t *idx2, const uint32_t *dest, uint32_t lane, uint64_t *s_k, uint32_t *s_i)
 {
@@ -376,7 +384,7 @@ __device__ __forceinline__ void af_finish_bucket(const AfArgs &a, uint32_t beg, 
         __syncwarp();
     }
     if (a.shift > 0) {
-        if (n <= AF_SN) {
+        if (n <= SN) {
             /* small bucket: stage (key, index) in shared memory once, so that the insertion sorts of its sub-buckets run at
              * shared-memory latency instead of two dependent global loads per comparison */
             for (uint32_t p = lane; p < n; p += 32) { const uint32_t e = idx[p]; s_i[p] = e; s_k[p] = a.sx[e]; }
@@ -548,16 +556,171 @@ __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
             __syncwarp();
             continue;
         }
-        af_finish_bucket(a, beg, n, nb, cnt, start, idx, idx2, dest, lane, s_sk[wid], s_si[wid]);
+        af_finish_bucket<AF_SN>(a, beg, n, nb, cnt, start, idx, idx2, dest, lane, s_sk[wid], s_si[wid]);
     }
 }
 
-/* The walk of lq_afsort_core.h (lq_afw_run): one lane chases the pointer, so what counts is the latency of one step and how
- * many walks an SM holds.  Per walk 7 KB of shared memory: region starts, {pos, base} per region, 16 cached digits per region;
- * a step is one 8-byte and one 1-byte shared-memory load.  When a region's cached digits run out the whole warp refills every
- * region that moved (two aligned 16-byte loads each, shifted to the region's position) and the walk resumes. */
-#define AFW_WARPS 2
-struct AfwSmem { uint32_t start[260]; lq_afw_pb pb[256]; uint4 cache[256]; };
+/* ---- one level for a LONG bucket: a whole CTA.  Same rules as lq_af_level_k (digits, histogram, then the exact destination of
+ *      every element), with block-wide primitives so that a 300 k-element bucket is not one warp's serial loop:
+ *        no tied key in the bucket    any partition by digit gives the same final order (all keys distinct): counters per digit
+ *        tied keys, two digits        the closed form lq_af_two_dest(), its ranks from block scans over tiles taken in order
+ *        tied keys, more digits       handed to lq_af_walk_k (wlist), which also finishes the bucket ---- */
+#define AFB_THREADS 512
+#define AFB_V 4
+__global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
+{
+    __shared__ uint32_t s_cnt[256], s_start[257], s_head[256], scan_sm[33];
+    __shared__ uint32_t s_b, s_tied, s_nb, s_d0, s_d1;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, lt = (1u << lane) - 1;
+    const uint32_t nbig = *a.n_curb;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_b = atomicAdd(a.cursorb, 1u);
+        __syncthreads();
+        const uint32_t b = s_b;
+        if (b >= nbig) break;
+        const uint32_t beg = a.curb[b].beg, n = a.curb[b].end - beg;
+        uint32_t *idx = a.idx + beg, *idx2 = a.idx2 + beg, *dest = a.dest + beg;
+        uint8_t *dig = a.dig + beg;
+        if (tid < 256) { s_cnt[tid] = 0; s_head[tid] = 0; }
+        if (tid == 0) { s_tied = 0; atomicAdd(a.n_elem, (unsigned long long)n); }
+        __syncthreads();
+        /* 1. digits + histogram (warp-aggregated shared-memory atomics: a level may have only two digits) */
+        uint32_t tied = 0;
+        for (uint32_t r0 = 0; r0 < n; r0 += AFB_THREADS * AFB_V) {
+            uint32_t e[AFB_V], dv[AFB_V];
+            #pragma unroll
+            for (int u = 0; u < AFB_V; ++u) { const uint32_t p = r0 + u * AFB_THREADS + tid; e[u] = p < n ? idx[p] : 0xffffffffu; }
+            #pragma unroll
+            for (int u = 0; u < AFB_V; ++u) {
+                dv[u] = 0;
+                if (e[u] != 0xffffffffu) { dv[u] = (uint32_t)(a.sx[e[u]] >> a.shift) & 255u; tied |= a.sq[e[u]] >> 31; }
+            }
+            #pragma unroll
+            for (int u = 0; u < AFB_V; ++u) {
+                const uint32_t p = r0 + u * AFB_THREADS + tid; const bool ok = p < n;
+                const uint32_t act = __ballot_sync(0xffffffffu, ok);
+                if (ok) {
+                    dig[p] = (uint8_t)dv[u];
+                    const uint32_t peers = __match_any_sync(act, dv[u]);
+                    if ((peers & lt) == 0) atomicAdd(&s_cnt[dv[u]], (uint32_t)__popc(peers));
+                }
+            }
+        }
+        if (tied) s_tied = 1;
+        __syncthreads();
+        /* 2. region starts */
+        if (wid == 0) {
+            uint32_t loc = 0, ne = 0, d0 = 256, d1 = 0;
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) { const uint32_t c = s_cnt[8 * lane + j]; loc += c; if (c) { ++ne; d0 = min(d0, 8 * lane + j); d1 = max(d1, 8 * lane + j); } }
+            const uint32_t inc = lq_warp_incl_scan(loc);
+            uint32_t run = inc - loc;
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) { s_start[8 * lane + j] = run; run += s_cnt[8 * lane + j]; }
+            ne = lq_warp_sum(ne);
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { d0 = min(d0, __shfl_xor_sync(0xffffffffu, d0, o)); d1 = max(d1, __shfl_xor_sync(0xffffffffu, d1, o)); }
+            if (lane == 0) { s_start[256] = n; s_nb = ne; s_d0 = d0; s_d1 = d1; }
+        }
+        __syncthreads();
+        const uint32_t nb = s_nb; const bool tiedb = s_tied != 0;
+        if (nb > 2 && tiedb) {   /* the sequential walk */
+            if (tid == 0) { const uint32_t at = atomicAdd(a.n_wlist, 1u); a.wlist[at].beg = beg; a.wlist[at].end = beg + n; }
+            continue;
+        }
+        if (nb > 1) {
+            if (tiedb) {
+                /* 3a. two digits d0 < d1, tied keys: closed form.  rk = foreign positions before p in p's own region */
+                const uint32_t d0 = s_d0, d1 = s_d1, n0 = s_cnt[d0];
+                uint32_t *P = idx2, *Z = idx2 + n0;
+                uint32_t runP = 0, runZ = 0;
+                for (uint32_t t0 = 0; t0 < n; t0 += AFB_THREADS * AFB_V) {
+                    const uint32_t pb = t0 + tid * AFB_V;
+                    uint32_t fr[AFB_V], f0 = 0, f1 = 0;
+                    #pragma unroll
+                    for (int j = 0; j < AFB_V; ++j) {
+                        const uint32_t p = pb + j;
+                        fr[j] = 0;
+                        if (p < n) { const uint32_t d = dig[p]; fr[j] = p < n0 ? d == d1 : d == d0; if (p < n0) f0 += fr[j]; else f1 += fr[j]; }
+                    }
+                    uint32_t tot;
+                    const uint32_t ex = lq_block_excl_scan<uint32_t>(f0 | f1 << 16, scan_sm, &tot);
+                    uint32_t r0 = runP + (ex & 0xffffu), r1 = runZ + (ex >> 16);
+                    #pragma unroll
+                    for (int j = 0; j < AFB_V; ++j) {
+                        const uint32_t p = pb + j;
+                        if (p < n) {
+                            if (p < n0) { dest[p] = r0; if (fr[j]) P[r0++] = p; }
+                            else { dest[p] = r1; if (fr[j]) Z[r1++] = p; }
+                        }
+                    }
+                    runP += tot & 0xffffu; runZ += tot >> 16;
+                }
+                __syncthreads();
+                for (uint32_t p = tid; p < n; p += AFB_THREADS) {
+                    const uint32_t d = dig[p], rk = dest[p];
+                    const int f = p < n0 ? d == d1 : d == d0;
+                    dest[p] = lq_af_two_dest(p, n0, f, rk, runP, P, Z);
+                }
+                __syncthreads();
+            } else {
+                /* 3b. no tied key: any partition by digit */
+                for (uint32_t r0 = 0; r0 < n; r0 += AFB_THREADS * AFB_V) {
+                    uint32_t dv[AFB_V];
+                    #pragma unroll
+                    for (int u = 0; u < AFB_V; ++u) { const uint32_t p = r0 + u * AFB_THREADS + tid; dv[u] = p < n ? dig[p] : 0; }
+                    #pragma unroll
+                    for (int u = 0; u < AFB_V; ++u) {
+                        const uint32_t p = r0 + u * AFB_THREADS + tid; const bool ok = p < n;
+                        const uint32_t act = __ballot_sync(0xffffffffu, ok);
+                        if (ok) {
+                            const uint32_t peers = __match_any_sync(act, dv[u]);
+                            const int leader = __ffs(peers) - 1;
+                            uint32_t b0 = 0;
+                            if ((int)lane == leader) b0 = atomicAdd(&s_head[dv[u]], (uint32_t)__popc(peers));
+                            b0 = __shfl_sync(peers, b0, leader);
+                            dest[p] = s_start[dv[u]] + b0 + __popc(peers & lt);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            /* 4. permute the payload */
+            #pragma unroll 4
+            for (uint32_t p = tid; p < n; p += AFB_THREADS) idx2[dest[p]] = idx[p];
+            __syncthreads();
+            #pragma unroll 4
+            for (uint32_t p = tid; p < n; p += AFB_THREADS) idx[p] = idx2[p];
+            __syncthreads();
+        }
+        /* 5. sub-buckets (ksort.h:124-133) */
+        if (a.shift > 0 && tid < 256) {
+            const uint32_t c = s_cnt[tid];
+            const bool big_ = c > LQ_RS_MIN;
+            af_append(a, beg + s_start[tid], c, big_);
+            if (!big_ && c > 1) lq_af_insertion(idx + s_start[tid], c, a.sx);
+        }
+    }
+}
+
+/* The walk of lq_afsort_core.h, one LANE per bucket (lq_afp_run): a single thread chases a pointer through 256 queues, so a warp
+ * with one active lane wastes 31/32 of its issue slots and the SM ends up issue-bound.  Here a CTA takes up to AFS_WALKERS buckets at
+ * a time ("generation"):
+ *   setup   the whole CTA builds the digit histograms (shared-memory atomics), then a warp per bucket turns them into region starts
+ *           (kept in a global scratch row) and empty per-region states
+ *   rounds  all threads refill the 16-byte region states (position + next 11 digits) of every bucket, then the walker warps walk,
+ *           lane = bucket, until every lane is done or out of digits somewhere; one step = one LDS.128, an AND and the next address
+ *   finish  the whole CTA permutes the payload, then a warp per bucket hands the sub-buckets on (af_finish_bucket)
+ * 4 KB of shared memory per bucket (256 states), reused for the histogram before and for start/cnt/staging after the walk. */
+#define AFS_WPW 28                 /* walker lanes per walker warp */
+#define AFS_WW 2                   /* walker warps: they interleave on the SM, hiding each other's load latency */
+#define AFS_WALKERS (AFS_WPW * AFS_WW)
+#define AFS_THREADS 512
+#define AFS_SN 160                 /* staging capacity in the finish phase: start 1040 + cnt 1024 + keys 1280 + indices 640 < 4096 */
+#define AFS_GRID 148               /* one CTA per SM (224 KB of shared memory each) */
+#define AFS_ROW 260                /* u32 per bucket in the global scratch: 257 region starts */
+struct AfsMeta { uint32_t beg, n, nb; };
 
 __device__ __forceinline__ uint4 afw_load16(const uint8_t *addr)   /* 16 bytes from an arbitrary address (reads up to 31 bytes past it: the arena is padded) */
 {
@@ -571,67 +734,129 @@ __device__ __forceinline__ uint4 afw_load16(const uint8_t *addr)   /* 16 bytes f
     return make_uint4(__funnelshift_r(t0, t1, sh), __funnelshift_r(t1, t2, sh), __funnelshift_r(t2, t3, sh), __funnelshift_r(t3, t4, sh));
 }
 
-__global__ void __launch_bounds__(AFW_WARPS * 32) lq_af_walk_k(AfArgs a)
+extern __shared__ __align__(16) uint8_t afs_smem[];
+
+__global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk_k(AfArgs a, uint32_t *gstart /* gridDim.x * AFS_WALKERS * AFS_ROW */)
 {
-    __shared__ __align__(16) AfwSmem s_w[AFW_WARPS];
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lt = (1u << lane) - 1;
-    AfwSmem &S = s_w[wid];
-    uint32_t *start = S.start, *cnt = (uint32_t*)S.pb;   /* cnt[] shares the pb[] storage: histogram before the walk, sizes after it */
+    lq_afp_st *state = (lq_afp_st*)afs_smem;                      /* [AFS_WALKERS][256] */
+    __shared__ AfsMeta meta[AFS_WALKERS];
+    __shared__ uint32_t s_base, s_alive[AFS_WW];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t nw = *a.n_wlist;
+    uint32_t gsize = (nw + gridDim.x - 1) / gridDim.x;            /* buckets per generation: all CTAs busy, at most AFS_WALKERS */
+    gsize = gsize < 1 ? 1 : gsize > AFS_WALKERS ? AFS_WALKERS : gsize;
+    uint32_t *gs = gstart + (size_t)blockIdx.x * AFS_WALKERS * AFS_ROW;
     for (;;) {
-        uint32_t b = 0;
-        if (lane == 0) b = atomicAdd(a.wcursor, 1u);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= nw) break;
-        const uint32_t beg = a.wlist[b].beg, n = a.wlist[b].end - beg;
-        uint32_t *idx = a.idx + beg, *idx2 = a.idx2 + beg, *dest = a.dest + beg;
-        const uint8_t *dig = a.dig + beg;
-        /* histogram from the digits the level kernel stored */
-        for (uint32_t d = lane; d < 256; d += 32) cnt[d] = 0;
-        __syncwarp();
-        for (uint32_t p0 = 0; p0 < n; p0 += 32 * AF_U) {
-            uint32_t dv[AF_U];
-            #pragma unroll
-            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32 + lane; dv[u] = p < n ? dig[p] : 0; }
-            #pragma unroll
-            for (int u = 0; u < AF_U; ++u) {
-                const uint32_t p = p0 + u * 32 + lane; const bool ok = p < n;
-                const uint32_t act = __ballot_sync(0xffffffffu, ok);
-                if (ok) { const uint32_t peers = __match_any_sync(act, dv[u]); if ((peers & lt) == 0) cnt[dv[u]] += __popc(peers); }
-                __syncwarp();
+        __syncthreads();
+        if (tid == 0) s_base = atomicAdd(a.wcursor, gsize);
+        __syncthreads();
+        const uint32_t base = s_base;
+        if (base >= nw) break;
+        const uint32_t nbk = nw - base < gsize ? nw - base : gsize;
+        /* ---- setup: histograms by the whole CTA ---- */
+        for (uint32_t w = tid; w < nbk; w += AFS_THREADS) { const AfBkt b = a.wlist[base + w]; meta[w].beg = b.beg; meta[w].n = b.end - b.beg; }
+        for (uint32_t e = tid; e < nbk * 256; e += AFS_THREADS) ((uint32_t*)(state + (e >> 8) * 256))[e & 255] = 0;   /* cnt = first 1 KB of a bucket's area */
+        __syncthreads();
+        for (uint32_t w = 0; w < nbk; ++w) {
+            const uint32_t n = meta[w].n;
+            const uint8_t *dig = a.dig + meta[w].beg;
+            uint32_t *cnt = (uint32_t*)(state + w * 256);
+            uint32_t head = (uint32_t)((16 - ((uintptr_t)dig & 15)) & 15);
+            if (head > n) head = n;
+            const uint32_t nch = (n - head) >> 4, tail0 = head + (nch << 4);
+            if (tid < head) atomicAdd(&cnt[dig[tid]], 1u);
+            if (tail0 + tid < n) atomicAdd(&cnt[dig[tail0 + tid]], 1u);
+            const uint4 *body = (const uint4*)(dig + head);
+            #pragma unroll 2
+            for (uint32_t ch = tid; ch < nch; ch += AFS_THREADS) {
+                const uint4 v = body[ch];
+                const uint32_t ww[4] = { v.x, v.y, v.z, v.w };
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    atomicAdd(&cnt[ww[j] & 255u], 1u); atomicAdd(&cnt[(ww[j] >> 8) & 255u], 1u);
+                    atomicAdd(&cnt[(ww[j] >> 16) & 255u], 1u); atomicAdd(&cnt[ww[j] >> 24], 1u);
+                }
             }
         }
-        uint32_t loc = 0, ne = 0, cc[8];
-        #pragma unroll
-        for (int j = 0; j < 8; ++j) { cc[j] = cnt[8 * lane + j]; loc += cc[j]; if (cc[j]) ++ne; }
-        uint32_t inc = lq_warp_incl_scan(loc), run = inc - loc;
-        #pragma unroll
-        for (int j = 0; j < 8; ++j) { start[8 * lane + j] = run; run += cc[j]; }
-        if (lane == 31) start[256] = n;
-        const uint32_t nb = lq_warp_sum(ne);
-        __syncwarp();                                    /* every lane has read its counts: pb[] may overwrite them */
-        for (uint32_t r = lane; r < 256; r += 32) { lq_afw_pb e; e.x = start[r]; e.y = start[r] - LQ_AFW_CACHE; S.pb[r] = e; }
-        __syncwarp();
-        lq_afw_state ws;
-        lq_afw_init_state(&ws, start);
+        __syncthreads();
+        /* ---- setup: region starts and empty states, a warp per bucket ---- */
+        for (uint32_t w = wid; w < nbk; w += AFS_THREADS / 32) {
+            const uint32_t *cnt = (const uint32_t*)(state + w * 256);
+            uint32_t loc = 0, ne = 0, cc[8];
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) { cc[j] = cnt[8 * lane + j]; loc += cc[j]; if (cc[j]) ++ne; }
+            const uint32_t inc = lq_warp_incl_scan(loc);
+            uint32_t run = inc - loc;
+            const uint32_t nb = lq_warp_sum(ne);
+            __syncwarp();                                          /* every lane holds its counts: the states may overwrite them */
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t r = 8 * lane + j;
+                gs[w * AFS_ROW + r] = run;
+                lq_afp_st e; e.x = run; e.y = e.z = e.w = 0;
+                state[w * 256 + r] = e;
+                run += cc[j];
+            }
+            if (lane == 31) gs[w * AFS_ROW + 256] = meta[w].n;
+            if (lane == 0) meta[w].nb = nb;
+        }
+        __syncthreads();
+        /* ---- rounds ---- */
+        const uint32_t wl = wid * AFS_WPW + lane;                 /* this thread's bucket when it is a walker lane */
+        const bool walker = wid < AFS_WW && lane < AFS_WPW && wl < nbk;
+        lq_afp_walk ws; bool fin = true; uint32_t my_n = 0; uint32_t *my_dest = 0; const uint32_t *my_start = gs;
+        if (walker) { my_start = gs + wl * AFS_ROW; lq_afp_init(&ws, my_start); fin = false; my_n = meta[wl].n; my_dest = a.dest + meta[wl].beg; }
         for (;;) {
-            #pragma unroll
-            for (int i = 0; i < 8; ++i) {                /* refill every region that moved since its last refill */
-                const uint32_t r = lane + 32 * i;
-                const lq_afw_pb e = S.pb[r];
-                if (e.x < start[r + 1] && e.x != e.y) { S.cache[r] = afw_load16(dig + e.x); S.pb[r].y = e.x; }
+            for (uint32_t e = tid; e < nbk * 256; e += AFS_THREADS) {   /* refill: consecutive threads, consecutive regions of a bucket */
+                const uint32_t w = e >> 8, r = e & 255;
+                lq_afp_st S = state[e];
+                const uint32_t avail = gs[w * AFS_ROW + r + 1] - S.x, left = S.w >> 24, m = avail < LQ_AFP_DIG ? avail : LQ_AFP_DIG;
+                if (left < m) {
+                    const uint4 v = afw_load16(a.dig + meta[w].beg + S.x);
+                    S.y = v.x; S.z = v.y; S.w = (v.z & 0x00ffffffu) | m << 24;
+                    state[e] = S;
+                }
             }
-            __syncwarp();
-            int done = 0;
-            if (lane == 0) done = lq_afw_run(&ws, n, start, S.pb, (const uint8_t*)S.cache, dest);
-            done = __shfl_sync(0xffffffffu, done, 0);
-            if (done) break;
+            __syncthreads();
+            if (wid < AFS_WW) {
+                if (!fin) fin = lq_afp_run(&ws, my_n, my_start, state + wl * 256, my_dest) != 0;
+                const uint32_t alive = __ballot_sync(0xffffffffu, !fin);
+                if (lane == 0) s_alive[wid] = alive;
+            }
+            __syncthreads();
+            uint32_t alive = 0;
+            #pragma unroll
+            for (int j = 0; j < AFS_WW; ++j) alive |= s_alive[j];
+            if (!alive) break;
         }
-        if (lane == 0) { atomicAdd(a.n_walk, 1u); atomicAdd(a.n_elem, (unsigned long long)n); }
-        __syncwarp();
-        for (uint32_t d = lane; d < 256; d += 32) cnt[d] = start[d + 1] - start[d];
-        __syncwarp();
-        af_finish_bucket(a, beg, n, nb, cnt, start, idx, idx2, dest, lane, (uint64_t*)S.cache, (uint32_t*)S.cache + 2 * AF_SN);
+        if (tid == 0) {
+            unsigned long long tot = 0;
+            for (uint32_t w = 0; w < nbk; ++w) tot += meta[w].n;
+            atomicAdd(a.n_walk, nbk); atomicAdd(a.n_elem, tot);
+        }
+        /* ---- finish: permute the payload (whole CTA), then the sub-buckets (a warp per bucket) ---- */
+        for (uint32_t w = 0; w < nbk; ++w) {
+            const uint32_t n = meta[w].n; const uint32_t *idx = a.idx + meta[w].beg, *dest = a.dest + meta[w].beg; uint32_t *idx2 = a.idx2 + meta[w].beg;
+            #pragma unroll 4
+            for (uint32_t p = tid; p < n; p += AFS_THREADS) idx2[dest[p]] = idx[p];
+        }
+        __syncthreads();
+        for (uint32_t w = 0; w < nbk; ++w) {
+            const uint32_t n = meta[w].n; uint32_t *idx = a.idx + meta[w].beg; const uint32_t *idx2 = a.idx2 + meta[w].beg;
+            #pragma unroll 4
+            for (uint32_t p = tid; p < n; p += AFS_THREADS) idx[p] = idx2[p];
+        }
+        __syncthreads();
+        for (uint32_t w = wid; w < nbk; w += AFS_THREADS / 32) {
+            const uint32_t beg = meta[w].beg, n = meta[w].n;
+            uint32_t *start = (uint32_t*)(state + w * 256), *cnt = start + AFS_ROW;
+            uint64_t *s_k = (uint64_t*)(cnt + 256); uint32_t *s_i = (uint32_t*)(s_k + AFS_SN);
+            for (uint32_t d = lane; d < 257; d += 32) start[d] = gs[w * AFS_ROW + d];
+            __syncwarp();
+            for (uint32_t d = lane; d < 256; d += 32) cnt[d] = start[d + 1] - start[d];
+            __syncwarp();
+            af_finish_bucket<AFS_SN>(a, beg, n, 1 /* already permuted */, cnt, start, a.idx + beg, a.idx2 + beg, a.dest + beg, lane, s_k, s_i);
+        }
     }
 }
 
@@ -1081,14 +1306,17 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         LQ_CUDA_OK(cudaGetLastError());
     }
     /* bucket lists: at most nb/65 + nqb live buckets per level */
-    const size_t bcap = (size_t)(nb / (LQ_RS_MIN + 1)) + nqb + 16;
-    LQ_TRY(sc->bkt.ensure(3 * bcap * sizeof(AfBkt)));
+    const size_t bcap = (size_t)(nb / (LQ_RS_MIN + 1)) + nqb + 16, bcapb = (size_t)(nb / AFB_MIN) + nqb + 16;
+    LQ_TRY(sc->bkt.ensure((3 * bcap + 2 * bcapb) * sizeof(AfBkt)));
+    LQ_TRY(sc->wst.ensure((size_t)AFS_GRID * AFS_WALKERS * AFS_ROW * 4));
+    LQ_CUDA_OK(cudaFuncSetAttribute(lq_af_walk_k, cudaFuncAttributeMaxDynamicSharedMemorySize, AFS_WALKERS * 4096));
     AfBkt *bk[2] = { sc->bkt.as<AfBkt>(), sc->bkt.as<AfBkt>() + bcap };
     AfBkt *wl = sc->bkt.as<AfBkt>() + 2 * bcap;
+    AfBkt *bkb[2] = { sc->bkt.as<AfBkt>() + 3 * bcap, sc->bkt.as<AfBkt>() + 3 * bcap + bcapb };   /* long buckets: ctr[11], ctr[12] = counts, ctr[13] = cursor */
     /* counters: ctr[0],ctr[1] = bucket counts of the two lists, ctr[2] = cursor, ctr[3] = walks */
     lq_prof_count_launch(2);
     lq_iota_k<<<lq_grid(nb, 256), 256, 0, st>>>(b->idx, nb);
-    lq_af_init_k<<<lq_grid(nqb, 128), 128, 0, st>>>(nqb, d_qoff, b->s.sx, b->idx, bk[0], ctr + 0);
+    lq_af_init_k<<<lq_grid(nqb, 128), 128, 0, st>>>(nqb, d_qoff, b->s.sx, b->idx, bk[0], ctr + 0, bkb[0], ctr + 11);
     LQ_CUDA_OK(cudaGetLastError());
     static const char *lvl_name[8] = { "seed_sort_s0", "seed_sort_s8", "seed_sort_s16", "seed_sort_s24", "seed_sort_s32", "seed_sort_s40", "seed_sort_s48", "seed_sort_s56" };
     static const char *wlk_name[8] = { "seed_walk_s0", "seed_walk_s8", "seed_walk_s16", "seed_walk_s24", "seed_walk_s32", "seed_walk_s40", "seed_walk_s48", "seed_walk_s56" };
@@ -1098,16 +1326,20 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         a.sx = b->s.sx; a.sq = b->s.sq; a.idx = b->idx; a.idx2 = b->idx2; a.dest = b->dest; a.dig = b->dig;
         a.cur = bk[cur]; a.n_cur = ctr + cur; a.nxt = bk[cur ^ 1]; a.n_nxt = ctr + (cur ^ 1); a.cursor = ctr + 2; a.n_walk = ctr + 3; a.shift = shift;
         a.wlist = wl; a.n_wlist = ctr + 9; a.wcursor = ctr + 10;
+        a.curb = bkb[cur]; a.n_curb = ctr + 11 + cur; a.nxtb = bkb[cur ^ 1]; a.n_nxtb = ctr + 11 + (cur ^ 1); a.cursorb = ctr + 13;
+        LQ_CUDA_OK(cudaMemsetAsync(ctr + 11 + (cur ^ 1), 0, 4, st));
+        LQ_CUDA_OK(cudaMemsetAsync(ctr + 13, 0, 4, st));
         LQ_CUDA_OK(cudaMemsetAsync(ctr + (cur ^ 1), 0, 4, st));
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 2, 0, 4, st));
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 9, 0, 8, st));
         unsigned long long *n_elem = (unsigned long long*)(ctr + 16);
         a.n_elem = n_elem + (shift >> 3);
-        { LqProfScope ps(lvl_name[shift >> 3], st, 1, 0);
+        { LqProfScope ps(lvl_name[shift >> 3], st, 2, 0);
+          lq_af_big_k<<<148 * 4, AFB_THREADS, 0, st>>>(a);
           lq_af_level_k<<<148 * 16, AF_WARPS * 32, 0, st>>>(a); }
         a.n_elem = n_elem + 8 + (shift >> 3);
         { LqProfScope ps(wlk_name[shift >> 3], st, 1, 0);
-          lq_af_walk_k<<<148 * 16, AFW_WARPS * 32, 0, st>>>(a); }
+          lq_af_walk_k<<<AFS_GRID, AFS_THREADS, AFS_WALKERS * 4096, st>>>(a, sc->wst.as<uint32_t>()); }
         LQ_CUDA_OK(cudaGetLastError());
         cur ^= 1;
     }
