@@ -141,47 +141,61 @@ LQ_HD void lq_afp_init(lq_afp_walk *s, const uint32_t *start)
     s->start_k = k < 256 ? start[k] : 0; s->end_k = k < 256 ? start[k + 1] : 0;
 }
 
-/* returns 1 when all n elements are placed, 0 when region s->c has no cached digit left (refill, then call again) */
+/* returns 1 when all n elements are placed, 0 when region s->c has no cached digit left (refill, then call again).
+ * The state of the digit's region is loaded as soon as the digit is known (Sn), before this step's bookkeeping: the dependent chain
+ * of a step is load -> and -> address -> load, everything else sits in the shadow of the load.  Sn is stale only when the digit
+ * names the region just read (d == c); the updated copy in registers is used then. */
 LQ_HD int lq_afp_run(lq_afp_walk *s, uint32_t n, const uint32_t *start, lq_afp_st *st, uint32_t *dest)
 {
     uint32_t k = s->k, c = s->c, arrived = s->arrived, step = s->step, start_k = s->start_k, end_k = s->end_k, pend_p = s->pend_p;
     int pend = s->pend, done = 1;
-    while (step < n) {
+    if (step < n) {
         lq_afp_st S = st[c];
-        if (pend) { dest[pend_p] = S.x; pend = 0; }         /* the previous element lands on the next pick of its region */
-        const uint32_t left = S.w >> 24;
-        if (left == 0) { done = 0; break; }
-        const uint32_t d = S.y & 255u, p = S.x;
-        S.x = p + 1; S.y = LQ_FUNNEL_R8(S.y, S.z); S.z = LQ_FUNNEL_R8(S.z, S.w); S.w = ((S.w >> 8) & 0xffffu) | (left - 1) << 24;
-        st[c] = S;
-        ++step;
-        if (d != k) { pend = 1; pend_p = p; c = d; }
-        else {
-            dest[p] = start_k + arrived++;                     /* arrivals into the outer-loop region lag its pick-ups by the open hole */
-            c = k;
-            if (st[k].x == end_k) {                            /* region k complete: open the next non-exhausted region */
-                do { ++k; } while (k < 256 && st[k].x == start[k + 1]);
-                if (k < 256) { c = k; start_k = start[k]; end_k = start[k + 1]; arrived = st[k].x - start_k; }
-                else c = 0;
+        for (;;) {
+            if (pend) { dest[pend_p] = S.x; pend = 0; }         /* the previous element lands on the next pick of its region */
+            const uint32_t left = S.w >> 24;
+            if (left == 0) { done = 0; break; }
+            const uint32_t d = S.y & 255u, p = S.x;
+            const lq_afp_st Sn = st[d];
+            S.x = p + 1; S.y = LQ_FUNNEL_R8(S.y, S.z); S.z = LQ_FUNNEL_R8(S.z, S.w); S.w = ((S.w >> 8) & 0xffffu) | (left - 1) << 24;
+            st[c] = S;
+            ++step;
+            if (d != k) {
+                pend = 1; pend_p = p;
+                if (d != c) S = Sn;
+                c = d;
+            } else {
+                dest[p] = start_k + arrived++;                     /* arrivals into the outer-loop region lag its pick-ups by the open hole */
+                if (c != k) S = Sn;
+                c = k;
+                if (S.x == end_k) {                                /* region k complete: open the next non-exhausted region */
+                    do { ++k; } while (k < 256 && st[k].x == start[k + 1]);
+                    if (k < 256) { c = k; start_k = start[k]; end_k = start[k + 1]; arrived = st[k].x - start_k; }
+                    else c = 0;
+                    S = st[c];
+                }
             }
+            if (step >= n) break;
         }
+        if (done && pend) { dest[pend_p] = S.x; pend = 0; }
     }
-    if (done && pend) { dest[pend_p] = st[c].x; pend = 0; }
     s->k = k; s->c = c; s->arrived = arrived; s->step = step; s->start_k = start_k; s->end_k = end_k; s->pend_p = pend_p; s->pend = pend;
     return done;
 }
 
-/* refill rule of one region (host form; the device loads the bytes with two aligned 16-byte loads) */
+/* refill rule of one region (host form; the device loads the bytes with two aligned 16-byte loads): a region that moved since its
+ * last refill gets the LQ_AFP_DIG digits from its position on.  Digits past the region's end are cached too (the next region's, or
+ * padding): the walk never reads them, because a region is picked from exactly as often as it has elements. */
 LQ_HD void lq_afp_refill_host(const uint8_t *dig, const uint32_t *start, lq_afp_st *st, uint32_t r)
 {
     lq_afp_st S = st[r];
-    const uint32_t avail = start[r + 1] - S.x, left = S.w >> 24, m = avail < LQ_AFP_DIG ? avail : LQ_AFP_DIG;
-    if (left >= m) return;
+    const uint32_t n = start[256];
+    if ((S.w >> 24) >= LQ_AFP_DIG) return;
     uint8_t b[12]; uint32_t j;
-    for (j = 0; j < 12; ++j) b[j] = j < m ? dig[S.x + j] : 0;
+    for (j = 0; j < 12; ++j) b[j] = j < LQ_AFP_DIG && S.x + j < n ? dig[S.x + j] : 0;
     S.y = (uint32_t)b[0] | (uint32_t)b[1] << 8 | (uint32_t)b[2] << 16 | (uint32_t)b[3] << 24;
     S.z = (uint32_t)b[4] | (uint32_t)b[5] << 8 | (uint32_t)b[6] << 16 | (uint32_t)b[7] << 24;
-    S.w = (uint32_t)b[8] | (uint32_t)b[9] << 8 | (uint32_t)b[10] << 16 | m << 24;
+    S.w = (uint32_t)b[8] | (uint32_t)b[9] << 8 | (uint32_t)b[10] << 16 | (uint32_t)LQ_AFP_DIG << 24;
     st[r] = S;
 }
 
@@ -212,6 +226,19 @@ LQ_HD void lq_af_insertion(uint32_t *idx, uint32_t n, const uint64_t *key)
             uint32_t j = i;
             while (j > 0 && kt < key[idx[j - 1]]) { idx[j] = idx[j - 1]; --j; }
             idx[j] = t;
+        }
+    }
+}
+
+/* the same on (key, value) pairs held in place: what the device runs once the keys travel with the elements */
+LQ_HD void lq_af_insertion_kv(uint64_t *key, uint32_t *val, uint32_t n)
+{
+    for (uint32_t i = 1; i < n; ++i) {
+        const uint64_t kt = key[i]; const uint32_t vt = val[i];
+        if (kt < key[i - 1]) {
+            uint32_t j = i;
+            while (j > 0 && kt < key[j - 1]) { key[j] = key[j - 1]; val[j] = val[j - 1]; --j; }
+            key[j] = kt; val[j] = vt;
         }
     }
 }

@@ -296,18 +296,22 @@ __global__ void lq_qseeds_k(uint32_t nq, const uint64_t *__restrict__ first, con
 /* ------------------------------------------------------------------ K5: exact seed sort */
 
 struct AfBkt { uint32_t beg, end; };
+/* The sort moves (key, idx) pairs: kx[p] = sort key of the element now at p, idx[p] = its seed number (bit 31: the seed belongs to a
+ * repeated query minimizer, so its key may be tied).  Nothing is gathered through idx until the very end (lq_gather_k). */
 struct AfArgs {
-    const uint64_t *sx; const uint32_t *sq; uint32_t *idx, *idx2, *dest; uint8_t *dig;
+    uint64_t *kx, *kx2; uint32_t *idx, *idx2, *dest; uint8_t *dig;
     const AfBkt *cur; const uint32_t *n_cur; AfBkt *nxt; uint32_t *n_nxt; uint32_t *cursor; uint32_t *n_walk;
-    AfBkt *wlist; uint32_t *n_wlist; uint32_t *wcursor;   /* tied buckets with > 2 digits: walked by lq_af_walk_k */
+    AfBkt *wlist; uint32_t *n_wlist; uint32_t *wcursor, *wcursor_f;   /* tied buckets with > 2 digits: walked by lq_af_walk_k (>= AFW_SMALL elements) ... */
+    AfBkt *wlist_s; uint32_t *n_wlist_s; uint32_t *wcursor_s;   /* ... or by lq_af_walk_small_k (a warp per bucket) */
     unsigned long long *n_elem;   /* elements this launch handled (profiling: algorithmic bytes of the launch) */
     const AfBkt *curb; const uint32_t *n_curb; AfBkt *nxtb; uint32_t *n_nxtb; uint32_t *cursorb;   /* buckets of >= AFB_MIN elements: a CTA each (lq_af_big_k) */
     int shift;
 };
 
 #define AFB_MIN 4096               /* buckets at least this long are sorted by a whole CTA (lq_af_big_k), shorter ones by a warp (lq_af_level_k) */
+#define AFW_SMALL 2048             /* walks shorter than this: a warp per bucket (lq_af_walk_small_k); longer: a lane per bucket (lq_af_walk_k) */
 
-__global__ void lq_af_init_k(uint32_t nqb, const uint64_t *__restrict__ qoff /* nqb+1 seed offsets in the batch */, const uint64_t *__restrict__ sx,
+__global__ void lq_af_init_k(uint32_t nqb, const uint64_t *__restrict__ qoff /* nqb+1 seed offsets in the batch */, uint64_t *__restrict__ kx,
                              uint32_t *__restrict__ idx, AfBkt *__restrict__ bkt, uint32_t *__restrict__ n_bkt, AfBkt *__restrict__ bktb, uint32_t *__restrict__ n_bktb)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,13 +319,13 @@ __global__ void lq_af_init_k(uint32_t nqb, const uint64_t *__restrict__ qoff /* 
     const uint32_t beg = (uint32_t)qoff[q], end = (uint32_t)qoff[q + 1], n = end - beg;
     if (n >= AFB_MIN) { const uint32_t at = atomicAdd(n_bktb, 1u); bktb[at].beg = beg; bktb[at].end = end; }
     else if (n > LQ_RS_MIN) { const uint32_t at = atomicAdd(n_bkt, 1u); bkt[at].beg = beg; bkt[at].end = end; }
-    else if (n > 1) lq_af_insertion(idx + beg, n, sx); /* ksort.h:132 */
+    else if (n > 1) lq_af_insertion_kv(kx + beg, idx + beg, n); /* ksort.h:132 */
 }
 
-__global__ void lq_iota_k(uint32_t *idx, uint64_t n)
+__global__ void lq_iota_k(uint32_t *__restrict__ idx, const uint32_t *__restrict__ sq, uint64_t n)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) idx[i] = (uint32_t)i;
+    if (i < n) idx[i] = (uint32_t)i | (sq[i] & 0x80000000u);   /* the tie mark of lq_fill_k travels with the element */
 }
 
 #define AF_WARPS 4
@@ -341,12 +345,19 @@ __device__ __forceinline__ void af_append(const AfArgs &a, uint32_t beg, uint32_
     if (big) { const uint32_t at = bb + __popc(mb & ((1u << lane) - 1)); a.nxtb[at].beg = beg; a.nxtb[at].end = beg + c; }
 }
 
+/* a tied bucket with more than two digits goes to one of the two walk kernels (called by one thread) */
+__device__ __forceinline__ void af_push_walk(const AfArgs &a, uint32_t beg, uint32_t n)
+{
+    if (n < AFW_SMALL) { const uint32_t at = atomicAdd(a.n_wlist_s, 1u); a.wlist_s[at].beg = beg; a.wlist_s[at].end = beg + n; }
+    else { const uint32_t at = atomicAdd(a.n_wlist, 1u); a.wlist[at].beg = beg; a.wlist[at].end = beg + n; }
+}
+
 /* stable sort of a sub-bucket of 9..64 elements by key, one warp: each lane holds two elements, rank = #smaller + #equal-before
  * (== the order ksort.h's insertion sort leaves) */
-__device__ __forceinline__ void af_warp_ranksort(uint32_t *idx, uint32_t n, const uint64_t *__restrict__ key, uint32_t lane)
+__device__ __forceinline__ void af_warp_ranksort(uint64_t *key, uint32_t *idx, uint32_t n, uint32_t lane)
 {
     const uint32_t e0 = lane < n ? idx[lane] : 0, e1 = lane + 32 < n ? idx[lane + 32] : 0;
-    const uint64_t k0 = lane < n ? key[e0] : ~0ULL, k1 = lane + 32 < n ? key[e1] : ~0ULL;
+    const uint64_t k0 = lane < n ? key[lane] : ~0ULL, k1 = lane + 32 < n ? key[lane + 32] : ~0ULL;
     uint32_t r0 = 0, r1 = 0;
     for (uint32_t j = 0; j < n; ++j) {
         const uint64_t kj = __shfl_sync(0xffffffffu, j < 32 ? k0 : k1, j & 31);
@@ -354,32 +365,33 @@ __device__ __forceinline__ void af_warp_ranksort(uint32_t *idx, uint32_t n, cons
         r1 += kj < k1 || (kj == k1 && j < lane + 32);
     }
     __syncwarp();
-    if (lane < n) idx[r0] = e0;
-    if (lane + 32 < n) idx[r1] = e1;
+    if (lane < n) { idx[r0] = e0; key[r0] = k0; }
+    if (lane + 32 < n) { idx[r1] = e1; key[r1] = k1; }
     __syncwarp();
 }
 
 /* after dest[] is known: permute the payload, then hand the sub-buckets on (ksort.h:124-133) */
-#define AF_SN 320
+#define AF_SN 512
 template <int SN>
 __device__ __forceinline__ void af_finish_bucket(const AfArgs &a, uint32_t beg, uint32_t n, uint32_t nb, const uint32_t *cnt, const uint32_t *start,
-                                                 uint32_t *idx, uint32_t *idx2, const uint32_t *dest, uint32_t lane, uint64_t *s_k, uint32_t *s_i)
+                                                 const uint32_t *dest, uint32_t lane, uint64_t *s_k, uint32_t *s_i)
 {
+    uint64_t *kx = a.kx + beg, *kx2 = a.kx2 + beg; uint32_t *idx = a.idx + beg, *idx2 = a.idx2 + beg;
     if (nb > 1) {
         for (uint32_t p0 = lane; p0 < n; p0 += 32 * AF_U) {
-            uint32_t dd[AF_U], ee[AF_U];
+            uint32_t dd[AF_U], ee[AF_U]; uint64_t kk[AF_U];
             #pragma unroll
-            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) { dd[u] = dest[p]; ee[u] = idx[p]; } }
+            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) { dd[u] = dest[p]; ee[u] = idx[p]; kk[u] = kx[p]; } }
             #pragma unroll
-            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) idx2[dd[u]] = ee[u]; }
+            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) { idx2[dd[u]] = ee[u]; kx2[dd[u]] = kk[u]; } }
         }
         __syncwarp();
         for (uint32_t p0 = lane; p0 < n; p0 += 32 * AF_U) {
-            uint32_t ee[AF_U];
+            uint32_t ee[AF_U]; uint64_t kk[AF_U];
             #pragma unroll
-            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) ee[u] = idx2[p]; }
+            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) { ee[u] = idx2[p]; kk[u] = kx2[p]; } }
             #pragma unroll
-            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) idx[p] = ee[u]; }
+            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) { idx[p] = ee[u]; kx[p] = kk[u]; } }
         }
         __syncwarp();
     }
@@ -387,7 +399,7 @@ __device__ __forceinline__ void af_finish_bucket(const AfArgs &a, uint32_t beg, 
         if (n <= SN) {
             /* small bucket: stage (key, index) in shared memory once, so that the insertion sorts of its sub-buckets run at
              * shared-memory latency instead of two dependent global loads per comparison */
-            for (uint32_t p = lane; p < n; p += 32) { const uint32_t e = idx[p]; s_i[p] = e; s_k[p] = a.sx[e]; }
+            for (uint32_t p = lane; p < n; p += 32) { s_i[p] = idx[p]; s_k[p] = kx[p]; }
             __syncwarp();
             for (uint32_t d = lane; d < 256; d += 32) {
                 const uint32_t c = cnt[d];
@@ -406,7 +418,7 @@ __device__ __forceinline__ void af_finish_bucket(const AfArgs &a, uint32_t beg, 
                 }
             }
             __syncwarp();
-            for (uint32_t p = lane; p < n; p += 32) idx[p] = s_i[p];
+            for (uint32_t p = lane; p < n; p += 32) { idx[p] = s_i[p]; kx[p] = s_k[p]; }
         } else {
             uint32_t mid = 0;   /* digits (bit per owned digit) whose sub-bucket has 9..64 elements: sorted by the whole warp afterwards */
             for (uint32_t d = lane; d < 256; d += 32) {
@@ -415,17 +427,64 @@ __device__ __forceinline__ void af_finish_bucket(const AfArgs &a, uint32_t beg, 
                 af_append(a, beg + start[d], c, big_);
                 if (big_) {}
                 else if (c > 8) mid |= 1u << (d >> 5);
-                else if (c > 1) lq_af_insertion(idx + start[d], c, a.sx);
+                else if (c > 1) lq_af_insertion_kv(kx + start[d], idx + start[d], c);
             }
             __syncwarp();
             for (uint32_t l = 0; l < 32; ++l) {
                 uint32_t m = __shfl_sync(0xffffffffu, mid, l);
-                while (m) { const uint32_t d = (uint32_t)(__ffs(m) - 1) * 32 + l; m &= m - 1; af_warp_ranksort(idx + start[d], cnt[d], a.sx, lane); }
+                while (m) { const uint32_t d = (uint32_t)(__ffs(m) - 1) * 32 + l; m &= m - 1; af_warp_ranksort(kx + start[d], idx + start[d], cnt[d], lane); }
             }
         }
     }
     __syncwarp();
 }
+/* A bucket of at most AF_SN elements none of which can tie: its keys are all distinct, so the order the reference leaves is simply
+ * "sorted by key" whatever its permutations did, and any partition by digit will do.  One warp, one pass over the bucket: histogram
+ * and scatter with shared-memory atomics (the arrival order inside a digit does not matter), then every digit group is sorted by
+ * key in shared memory (<= 8: a lane each; 9..64: the warp's rank sort) and the bucket is written back once.  Groups of more than
+ * 64 go on to the next level as usual.  Returns false (nothing written) when the bucket holds a tie mark. */
+__device__ __forceinline__ bool af_small_untied(const AfArgs &a, uint32_t beg, uint32_t n, uint32_t lane, uint64_t *s_k, uint32_t *s_i,
+                                                uint32_t *cnt, uint32_t *start, uint32_t *head)
+{
+    uint64_t *kx = a.kx + beg; uint32_t *idx = a.idx + beg;
+    for (uint32_t d = lane; d < 256; d += 32) cnt[d] = 0;
+    __syncwarp();
+    uint32_t tied = 0;
+    for (uint32_t p = lane; p < n; p += 32) { tied |= idx[p] >> 31; atomicAdd(&cnt[(uint32_t)(kx[p] >> a.shift) & 255u], 1u); }
+    if (__any_sync(0xffffffffu, tied)) return false;
+    __syncwarp();
+    uint32_t loc = 0, cc[8];
+    #pragma unroll
+    for (int j = 0; j < 8; ++j) { cc[j] = cnt[8 * lane + j]; loc += cc[j]; }
+    uint32_t run = lq_warp_incl_scan(loc) - loc;
+    #pragma unroll
+    for (int j = 0; j < 8; ++j) { start[8 * lane + j] = run; head[8 * lane + j] = run; run += cc[j]; }
+    __syncwarp();
+    for (uint32_t p = lane; p < n; p += 32) {
+        const uint64_t k = kx[p];
+        const uint32_t slot = atomicAdd(&head[(uint32_t)(k >> a.shift) & 255u], 1u);
+        s_k[slot] = k; s_i[slot] = idx[p];
+    }
+    __syncwarp();
+    uint32_t mid = 0;
+    for (uint32_t d = lane; d < 256; d += 32) {
+        const uint32_t c = cnt[d];
+        const bool big_ = c > LQ_RS_MIN && a.shift > 0;
+        af_append(a, beg + start[d], c, big_);
+        if (big_ || c < 2) {}
+        else if (c > 8 && c <= LQ_RS_MIN) mid |= 1u << (d >> 5);
+        else lq_af_insertion_kv(s_k + start[d], s_i + start[d], c);
+    }
+    __syncwarp();
+    for (uint32_t l = 0; l < 32; ++l) {
+        uint32_t m = __shfl_sync(0xffffffffu, mid, l);
+        while (m) { const uint32_t d = (uint32_t)(__ffs(m) - 1) * 32 + l; m &= m - 1; af_warp_ranksort(s_k + start[d], s_i + start[d], cnt[d], lane); }
+    }
+    for (uint32_t p = lane; p < n; p += 32) { kx[p] = s_k[p]; idx[p] = s_i[p]; }
+    __syncwarp();
+    return true;
+}
+
 __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
 {
     __shared__ uint32_t s_cnt[AF_WARPS][256], s_start[AF_WARPS][256], s_head[AF_WARPS][256];
@@ -445,21 +504,20 @@ __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
         const uint32_t bcur = b++;
         const uint32_t beg = a.cur[bcur].beg, n = a.cur[bcur].end - beg;
         uint32_t *idx = a.idx + beg, *idx2 = a.idx2 + beg, *dest = a.dest + beg;
+        uint64_t *kx = a.kx + beg;
         uint8_t *dig = a.dig + beg;
         if (lane == 0) atomicAdd(a.n_elem, (unsigned long long)n);
+        if (n <= AF_SN && af_small_untied(a, beg, n, lane, s_sk[wid], s_si[wid], cnt, start, head)) continue;
         /* 1. digits + histogram */
         for (uint32_t d = lane; d < 256; d += 32) cnt[d] = 0;
         __syncwarp();
         uint32_t tied = 0;
         for (uint32_t p0 = 0; p0 < n; p0 += 32 * AF_U) {   /* AF_U rows per trip: the idx -> key gathers of the rows overlap */
-            uint32_t e[AF_U], dv[AF_U];
+            uint32_t dv[AF_U]; uint64_t kk[AF_U];
             #pragma unroll
-            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32 + lane; e[u] = p < n ? idx[p] : 0xffffffffu; }
+            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32 + lane; kk[u] = p < n ? kx[p] : 0; if (p < n) tied |= idx[p] >> 31; }
             #pragma unroll
-            for (int u = 0; u < AF_U; ++u) {
-                dv[u] = 0;
-                if (e[u] != 0xffffffffu) { dv[u] = (uint32_t)(a.sx[e[u]] >> a.shift) & 255u; tied |= a.sq[e[u]] >> 31; }
-            }
+            for (int u = 0; u < AF_U; ++u) dv[u] = (uint32_t)(kk[u] >> a.shift) & 255u;
             #pragma unroll
             for (int u = 0; u < AF_U; ++u) {
                 const uint32_t p = p0 + u * 32 + lane; const bool ok = p < n;
@@ -552,11 +610,11 @@ __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
             __syncwarp();
         } else if (nb > 2) {
             /* tied keys and more than two digits: the sequential walk, done by lq_af_walk_k with a digit cache */
-            if (lane == 0) { const uint32_t at = atomicAdd(a.n_wlist, 1u); a.wlist[at].beg = beg; a.wlist[at].end = beg + n; }
+            if (lane == 0) af_push_walk(a, beg, n);
             __syncwarp();
             continue;
         }
-        af_finish_bucket<AF_SN>(a, beg, n, nb, cnt, start, idx, idx2, dest, lane, s_sk[wid], s_si[wid]);
+        af_finish_bucket<AF_SN>(a, beg, n, nb, cnt, start, dest, lane, s_sk[wid], s_si[wid]);
     }
 }
 
@@ -567,35 +625,48 @@ __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
  *        tied keys, more digits       handed to lq_af_walk_k (wlist), which also finishes the bucket ---- */
 #define AFB_THREADS 512
 #define AFB_V 4
+template <bool WALKED>   /* WALKED: the buckets of the long-walk list, whose dest[] lq_af_walk_k has just computed: permute + sub-buckets only */
 __global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
 {
     __shared__ uint32_t s_cnt[256], s_start[257], s_head[256], scan_sm[33];
     __shared__ uint32_t s_b, s_tied, s_nb, s_d0, s_d1;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, lt = (1u << lane) - 1;
-    const uint32_t nbig = *a.n_curb;
+    const uint32_t nbig = WALKED ? *a.n_wlist : *a.n_curb;
+    const AfBkt *list = WALKED ? a.wlist : a.curb;
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_b = atomicAdd(a.cursorb, 1u);
+        if (tid == 0) s_b = atomicAdd(WALKED ? a.wcursor_f : a.cursorb, 1u);
         __syncthreads();
         const uint32_t b = s_b;
         if (b >= nbig) break;
-        const uint32_t beg = a.curb[b].beg, n = a.curb[b].end - beg;
+        const uint32_t beg = list[b].beg, n = list[b].end - beg;
         uint32_t *idx = a.idx + beg, *idx2 = a.idx2 + beg, *dest = a.dest + beg;
+        uint64_t *kx = a.kx + beg, *kx2 = a.kx2 + beg;
         uint8_t *dig = a.dig + beg;
         if (tid < 256) { s_cnt[tid] = 0; s_head[tid] = 0; }
-        if (tid == 0) { s_tied = 0; atomicAdd(a.n_elem, (unsigned long long)n); }
+        if (tid == 0) { s_tied = 0; if (!WALKED) atomicAdd(a.n_elem, (unsigned long long)n); }
         __syncthreads();
         /* 1. digits + histogram (warp-aggregated shared-memory atomics: a level may have only two digits) */
         uint32_t tied = 0;
-        for (uint32_t r0 = 0; r0 < n; r0 += AFB_THREADS * AFB_V) {
-            uint32_t e[AFB_V], dv[AFB_V];
-            #pragma unroll
-            for (int u = 0; u < AFB_V; ++u) { const uint32_t p = r0 + u * AFB_THREADS + tid; e[u] = p < n ? idx[p] : 0xffffffffu; }
-            #pragma unroll
-            for (int u = 0; u < AFB_V; ++u) {
-                dv[u] = 0;
-                if (e[u] != 0xffffffffu) { dv[u] = (uint32_t)(a.sx[e[u]] >> a.shift) & 255u; tied |= a.sq[e[u]] >> 31; }
+        if (WALKED) {   /* the digits are there already */
+            for (uint32_t r0 = 0; r0 < n; r0 += AFB_THREADS * AFB_V) {
+                uint32_t dv[AFB_V];
+                #pragma unroll
+                for (int u = 0; u < AFB_V; ++u) { const uint32_t p = r0 + u * AFB_THREADS + tid; dv[u] = p < n ? dig[p] : 0; }
+                #pragma unroll
+                for (int u = 0; u < AFB_V; ++u) {
+                    const uint32_t p = r0 + u * AFB_THREADS + tid; const bool ok = p < n;
+                    const uint32_t act = __ballot_sync(0xffffffffu, ok);
+                    if (ok) { const uint32_t peers = __match_any_sync(act, dv[u]); if ((peers & lt) == 0) atomicAdd(&s_cnt[dv[u]], (uint32_t)__popc(peers)); }
+                }
             }
+        } else
+        for (uint32_t r0 = 0; r0 < n; r0 += AFB_THREADS * AFB_V) {
+            uint32_t dv[AFB_V]; uint64_t kk[AFB_V];
+            #pragma unroll
+            for (int u = 0; u < AFB_V; ++u) { const uint32_t p = r0 + u * AFB_THREADS + tid; kk[u] = p < n ? kx[p] : 0; if (p < n) tied |= idx[p] >> 31; }
+            #pragma unroll
+            for (int u = 0; u < AFB_V; ++u) dv[u] = (uint32_t)(kk[u] >> a.shift) & 255u;
             #pragma unroll
             for (int u = 0; u < AFB_V; ++u) {
                 const uint32_t p = r0 + u * AFB_THREADS + tid; const bool ok = p < n;
@@ -625,12 +696,13 @@ __global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
         }
         __syncthreads();
         const uint32_t nb = s_nb; const bool tiedb = s_tied != 0;
-        if (nb > 2 && tiedb) {   /* the sequential walk */
-            if (tid == 0) { const uint32_t at = atomicAdd(a.n_wlist, 1u); a.wlist[at].beg = beg; a.wlist[at].end = beg + n; }
+        if (!WALKED && nb > 2 && tiedb) {   /* the sequential walk */
+            if (tid == 0) af_push_walk(a, beg, n);
             continue;
         }
         if (nb > 1) {
-            if (tiedb) {
+            if (WALKED) {
+            } else if (tiedb) {
                 /* 3a. two digits d0 < d1, tied keys: closed form.  rk = foreign positions before p in p's own region */
                 const uint32_t d0 = s_d0, d1 = s_d1, n0 = s_cnt[d0];
                 uint32_t *P = idx2, *Z = idx2 + n0;
@@ -688,18 +760,24 @@ __global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
             }
             /* 4. permute the payload */
             #pragma unroll 4
-            for (uint32_t p = tid; p < n; p += AFB_THREADS) idx2[dest[p]] = idx[p];
+            for (uint32_t p = tid; p < n; p += AFB_THREADS) { const uint32_t d = dest[p]; idx2[d] = idx[p]; kx2[d] = kx[p]; }
             __syncthreads();
             #pragma unroll 4
-            for (uint32_t p = tid; p < n; p += AFB_THREADS) idx[p] = idx2[p];
+            for (uint32_t p = tid; p < n; p += AFB_THREADS) { idx[p] = idx2[p]; kx[p] = kx2[p]; }
             __syncthreads();
         }
         /* 5. sub-buckets (ksort.h:124-133) */
-        if (a.shift > 0 && tid < 256) {
-            const uint32_t c = s_cnt[tid];
-            const bool big_ = c > LQ_RS_MIN;
-            af_append(a, beg + s_start[tid], c, big_);
-            if (!big_ && c > 1) lq_af_insertion(idx + s_start[tid], c, a.sx);
+        if (a.shift > 0) {
+            if (tid < 256) {
+                const uint32_t c = s_cnt[tid];
+                const bool big_ = c > LQ_RS_MIN;
+                af_append(a, beg + s_start[tid], c, big_);
+                if (c > 1 && c <= 8) lq_af_insertion_kv(kx + s_start[tid], idx + s_start[tid], c);
+            }
+            for (uint32_t d = wid; d < 256; d += AFB_THREADS / 32) {   /* 9..64: a warp each, so that no thread sorts alone while 511 wait */
+                const uint32_t c = s_cnt[d];
+                if (c > 8 && c <= LQ_RS_MIN) af_warp_ranksort(kx + s_start[d], idx + s_start[d], c, lane);
+            }
         }
     }
 }
@@ -807,14 +885,20 @@ __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk_k(AfArgs a, uint32_
         lq_afp_walk ws; bool fin = true; uint32_t my_n = 0; uint32_t *my_dest = 0; const uint32_t *my_start = gs;
         if (walker) { my_start = gs + wl * AFS_ROW; lq_afp_init(&ws, my_start); fin = false; my_n = meta[wl].n; my_dest = a.dest + meta[wl].beg; }
         for (;;) {
-            for (uint32_t e = tid; e < nbk * 256; e += AFS_THREADS) {   /* refill: consecutive threads, consecutive regions of a bucket */
-                const uint32_t w = e >> 8, r = e & 255;
-                lq_afp_st S = state[e];
-                const uint32_t avail = gs[w * AFS_ROW + r + 1] - S.x, left = S.w >> 24, m = avail < LQ_AFP_DIG ? avail : LQ_AFP_DIG;
-                if (left < m) {
-                    const uint4 v = afw_load16(a.dig + meta[w].beg + S.x);
-                    S.y = v.x; S.z = v.y; S.w = (v.z & 0x00ffffffu) | m << 24;
-                    state[e] = S;
+            for (uint32_t e0 = tid; e0 < nbk * 256; e0 += 4 * AFS_THREADS) {   /* refill: consecutive threads, consecutive regions of a bucket; 4 loads in flight */
+                lq_afp_st S[4]; bool need[4]; uint4 v[4];
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t e = e0 + u * AFS_THREADS;
+                    need[u] = false;
+                    if (e < nbk * 256) { S[u] = state[e]; need[u] = (S[u].w >> 24) < LQ_AFP_DIG; }   /* the region moved since its last refill */
+                }
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) if (need[u]) v[u] = afw_load16(a.dig + meta[(e0 + u * AFS_THREADS) >> 8].beg + S[u].x);
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) if (need[u]) {
+                    S[u].y = v[u].x; S[u].z = v[u].y; S[u].w = (v[u].z & 0x00ffffffu) | (uint32_t)LQ_AFP_DIG << 24;
+                    state[e0 + u * AFS_THREADS] = S[u];
                 }
             }
             __syncthreads();
@@ -834,38 +918,87 @@ __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk_k(AfArgs a, uint32_
             for (uint32_t w = 0; w < nbk; ++w) tot += meta[w].n;
             atomicAdd(a.n_walk, nbk); atomicAdd(a.n_elem, tot);
         }
-        /* ---- finish: permute the payload (whole CTA), then the sub-buckets (a warp per bucket) ---- */
-        for (uint32_t w = 0; w < nbk; ++w) {
-            const uint32_t n = meta[w].n; const uint32_t *idx = a.idx + meta[w].beg, *dest = a.dest + meta[w].beg; uint32_t *idx2 = a.idx2 + meta[w].beg;
-            #pragma unroll 4
-            for (uint32_t p = tid; p < n; p += AFS_THREADS) idx2[dest[p]] = idx[p];
-        }
-        __syncthreads();
-        for (uint32_t w = 0; w < nbk; ++w) {
-            const uint32_t n = meta[w].n; uint32_t *idx = a.idx + meta[w].beg; const uint32_t *idx2 = a.idx2 + meta[w].beg;
-            #pragma unroll 4
-            for (uint32_t p = tid; p < n; p += AFS_THREADS) idx[p] = idx2[p];
-        }
-        __syncthreads();
-        for (uint32_t w = wid; w < nbk; w += AFS_THREADS / 32) {
-            const uint32_t beg = meta[w].beg, n = meta[w].n;
-            uint32_t *start = (uint32_t*)(state + w * 256), *cnt = start + AFS_ROW;
-            uint64_t *s_k = (uint64_t*)(cnt + 256); uint32_t *s_i = (uint32_t*)(s_k + AFS_SN);
-            for (uint32_t d = lane; d < 257; d += 32) start[d] = gs[w * AFS_ROW + d];
-            __syncwarp();
-            for (uint32_t d = lane; d < 256; d += 32) cnt[d] = start[d + 1] - start[d];
-            __syncwarp();
-            af_finish_bucket<AFS_SN>(a, beg, n, 1 /* already permuted */, cnt, start, a.idx + beg, a.idx2 + beg, a.dest + beg, lane, s_k, s_i);
-        }
+        /* the payload is permuted and the sub-buckets handed on by lq_af_big_k<true> (full occupancy, a CTA per bucket) */
     }
 }
 
-__global__ void lq_gather_k(uint64_t n, const uint32_t *__restrict__ idx, SeedArrays s, uint64_t *__restrict__ ax, uint32_t *__restrict__ aq, uint32_t *__restrict__ am)
+/* Short walks (the tied sub-buckets of the lower levels: ~10^2 elements, ~10^5 of them): a warp per bucket, lane 0 chases the pointer
+ * (lq_afw_run).  Per walk 7 KB of shared memory: region starts, {pos, base} per region, 16 cached digits per region; a step is one
+ * 8-byte and one 1-byte shared-memory load; when a region's cached digits run out the whole warp refills every region that moved. */
+#define AFW_WARPS 2
+#define AFW_SN 320                 /* staging capacity of the finish phase inside the 4 KB digit cache: 320 keys + 320 indices */
+struct AfwSmem { uint32_t start[260]; lq_afw_pb pb[256]; uint4 cache[256]; };
+
+__global__ void __launch_bounds__(AFW_WARPS * 32) lq_af_walk_small_k(AfArgs a)
+{
+    __shared__ __align__(16) AfwSmem s_w[AFW_WARPS];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lt = (1u << lane) - 1;
+    AfwSmem &S = s_w[wid];
+    uint32_t *start = S.start, *cnt = (uint32_t*)S.pb;   /* cnt[] shares the pb[] storage: histogram before the walk, sizes after it */
+    const uint32_t nw = *a.n_wlist_s;
+    for (;;) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(a.wcursor_s, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= nw) break;
+        const uint32_t beg = a.wlist_s[b].beg, n = a.wlist_s[b].end - beg;
+        uint32_t *dest = a.dest + beg;
+        const uint8_t *dig = a.dig + beg;
+        for (uint32_t d = lane; d < 256; d += 32) cnt[d] = 0;
+        __syncwarp();
+        for (uint32_t p0 = 0; p0 < n; p0 += 32 * AF_U) {   /* histogram from the digits the level kernel stored */
+            uint32_t dv[AF_U];
+            #pragma unroll
+            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32 + lane; dv[u] = p < n ? dig[p] : 0; }
+            #pragma unroll
+            for (int u = 0; u < AF_U; ++u) {
+                const uint32_t p = p0 + u * 32 + lane; const bool ok = p < n;
+                const uint32_t act = __ballot_sync(0xffffffffu, ok);
+                if (ok) { const uint32_t peers = __match_any_sync(act, dv[u]); if ((peers & lt) == 0) cnt[dv[u]] += __popc(peers); }
+                __syncwarp();
+            }
+        }
+        uint32_t loc = 0, ne = 0, cc[8];
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) { cc[j] = cnt[8 * lane + j]; loc += cc[j]; if (cc[j]) ++ne; }
+        uint32_t inc = lq_warp_incl_scan(loc), run = inc - loc;
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) { start[8 * lane + j] = run; run += cc[j]; }
+        if (lane == 31) start[256] = n;
+        const uint32_t nb = lq_warp_sum(ne);
+        __syncwarp();                                    /* every lane has read its counts: pb[] may overwrite them */
+        for (uint32_t r = lane; r < 256; r += 32) { lq_afw_pb e; e.x = start[r]; e.y = start[r] - LQ_AFW_CACHE; S.pb[r] = e; }
+        __syncwarp();
+        lq_afw_state ws;
+        lq_afw_init_state(&ws, start);
+        for (;;) {
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) {                /* refill every region that moved since its last refill */
+                const uint32_t r = lane + 32 * i;
+                const lq_afw_pb e = S.pb[r];
+                if (e.x < start[r + 1] && e.x != e.y) { S.cache[r] = afw_load16(dig + e.x); S.pb[r].y = e.x; }
+            }
+            __syncwarp();
+            int done = 0;
+            if (lane == 0) done = lq_afw_run(&ws, n, start, S.pb, (const uint8_t*)S.cache, dest);
+            done = __shfl_sync(0xffffffffu, done, 0);
+            if (done) break;
+        }
+        if (lane == 0) { atomicAdd(a.n_walk, 1u); atomicAdd(a.n_elem, (unsigned long long)n); }
+        __syncwarp();
+        for (uint32_t d = lane; d < 256; d += 32) cnt[d] = start[d + 1] - start[d];
+        __syncwarp();
+        af_finish_bucket<AFW_SN>(a, beg, n, nb, cnt, start, dest, lane, (uint64_t*)S.cache, (uint32_t*)S.cache + 2 * AFW_SN);
+    }
+}
+
+/* the keys are sorted in place (kx == ax); the rest of a seed follows through its number */
+__global__ void lq_gather_k(uint64_t n, const uint32_t *__restrict__ idx, SeedArrays s, uint32_t *__restrict__ aq, uint32_t *__restrict__ am)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t j = idx[i];
-    ax[i] = s.sx[j]; aq[i] = s.sq[j] & 0x7fffffffu; am[i] = s.sm[j];
+    const uint32_t j = idx[i] & 0x7fffffffu;
+    aq[i] = s.sq[j] & 0x7fffffffu; am[i] = s.sm[j];
 }
 
 /* ------------------------------------------------------------------ K6/K7: groups, chaining, accounting */
@@ -1231,7 +1364,7 @@ static int upload_u32(LqDevBuf &b, const uint32_t *h, size_t n, cudaStream_t st)
 }
 
 struct BatchPtrs {
-    SeedArrays s; uint32_t *idx, *idx2, *dest; uint8_t *dig;   /* arena1, sort phase */
+    SeedArrays s; uint64_t *kx2; uint32_t *idx, *idx2, *dest; uint8_t *dig;   /* arena1, sort phase (s.sx == ax: the keys are sorted in place in arena2) */
     int32_t *f, *p, *v, *t; uint64_t *uend; uint32_t *vl, *head, *gid;  /* arena1, chain phase (aliases) */
     uint64_t *ax; uint32_t *aq, *am;                           /* arena2 */
 };
@@ -1241,14 +1374,14 @@ static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 static int carve(LqMapScratch *sc, uint64_t nb, BatchPtrs *b)
 {
     const size_t n = (size_t)nb + 64;
-    /* sort phase: sx 8, sq 4, sm 4, idx 4, idx2 4, dest 4, dig 1 */
+    /* sort phase: kx2 8, sq 4, sm 4, idx 4, idx2 4, dest 4, dig 1 */
     const size_t sort_bytes = al(n * 8) + 5 * al(n * 4) + al(n);
     /* chain phase: f,p,v,t 4 each, uend 8, vl 4, head 4, gid 4 */
     const size_t chain_bytes = 7 * al(n * 4) + al(n * 8) + 256;
     LQ_TRY(sc->arena1.ensure(std::max(sort_bytes, chain_bytes)));
     LQ_TRY(sc->arena2.ensure(al(n * 8) + 2 * al(n * 4)));
     char *p = (char*)sc->arena1.p;
-    b->s.sx = (uint64_t*)p; p += al(n * 8);
+    b->kx2 = (uint64_t*)p; p += al(n * 8);
     b->s.sq = (uint32_t*)p; p += al(n * 4);
     b->s.sm = (uint32_t*)p; p += al(n * 4);
     b->idx = (uint32_t*)p; p += al(n * 4);
@@ -1268,6 +1401,7 @@ static int carve(LqMapScratch *sc, uint64_t nb, BatchPtrs *b)
     b->ax = (uint64_t*)p; p += al(n * 8);
     b->aq = (uint32_t*)p; p += al(n * 4);
     b->am = (uint32_t*)p;
+    b->s.sx = b->ax;
     return 0;
 }
 
@@ -1288,6 +1422,7 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     LQ_CUDA_OK(cudaMemsetAsync(ctr, 0, 256, st));   /* ctr[0..15]: u32 counters; ctr[16..47]: 16 u64 element counters (8 levels, 8 walks) */
     *d_qoff_out = d_qoff;
     if (nb == 0) return 0;
+    if (nb >= (1ULL << 31)) { fprintf(stderr, "[lqcov] a batch of %llu seeds exceeds the 31-bit seed numbers of the sort\n", (unsigned long long)nb); return -1; }
     const uint64_t mi0 = h_first[q0], mi1 = h_first[q1];
     if (mi1 > mi0) {
         LqProfScope ps("seed_fill", st, 1, (mi1 - mi0) * 32 + nb * 24);
@@ -1307,25 +1442,29 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     }
     /* bucket lists: at most nb/65 + nqb live buckets per level */
     const size_t bcap = (size_t)(nb / (LQ_RS_MIN + 1)) + nqb + 16, bcapb = (size_t)(nb / AFB_MIN) + nqb + 16;
-    LQ_TRY(sc->bkt.ensure((3 * bcap + 2 * bcapb) * sizeof(AfBkt)));
+    LQ_TRY(sc->bkt.ensure((4 * bcap + 2 * bcapb) * sizeof(AfBkt)));
     LQ_TRY(sc->wst.ensure((size_t)AFS_GRID * AFS_WALKERS * AFS_ROW * 4));
     LQ_CUDA_OK(cudaFuncSetAttribute(lq_af_walk_k, cudaFuncAttributeMaxDynamicSharedMemorySize, AFS_WALKERS * 4096));
     AfBkt *bk[2] = { sc->bkt.as<AfBkt>(), sc->bkt.as<AfBkt>() + bcap };
     AfBkt *wl = sc->bkt.as<AfBkt>() + 2 * bcap;
-    AfBkt *bkb[2] = { sc->bkt.as<AfBkt>() + 3 * bcap, sc->bkt.as<AfBkt>() + 3 * bcap + bcapb };   /* long buckets: ctr[11], ctr[12] = counts, ctr[13] = cursor */
+    AfBkt *wls = sc->bkt.as<AfBkt>() + 3 * bcap;                                                     /* short walks: ctr[14] = count, ctr[15] = cursor */
+    AfBkt *bkb[2] = { sc->bkt.as<AfBkt>() + 4 * bcap, sc->bkt.as<AfBkt>() + 4 * bcap + bcapb };   /* long buckets: ctr[11], ctr[12] = counts, ctr[13] = cursor */
     /* counters: ctr[0],ctr[1] = bucket counts of the two lists, ctr[2] = cursor, ctr[3] = walks */
     lq_prof_count_launch(2);
-    lq_iota_k<<<lq_grid(nb, 256), 256, 0, st>>>(b->idx, nb);
-    lq_af_init_k<<<lq_grid(nqb, 128), 128, 0, st>>>(nqb, d_qoff, b->s.sx, b->idx, bk[0], ctr + 0, bkb[0], ctr + 11);
+    lq_iota_k<<<lq_grid(nb, 256), 256, 0, st>>>(b->idx, b->s.sq, nb);
+    lq_af_init_k<<<lq_grid(nqb, 128), 128, 0, st>>>(nqb, d_qoff, b->ax, b->idx, bk[0], ctr + 0, bkb[0], ctr + 11);
     LQ_CUDA_OK(cudaGetLastError());
     static const char *lvl_name[8] = { "seed_sort_s0", "seed_sort_s8", "seed_sort_s16", "seed_sort_s24", "seed_sort_s32", "seed_sort_s40", "seed_sort_s48", "seed_sort_s56" };
     static const char *wlk_name[8] = { "seed_walk_s0", "seed_walk_s8", "seed_walk_s16", "seed_walk_s24", "seed_walk_s32", "seed_walk_s40", "seed_walk_s48", "seed_walk_s56" };
     int cur = 0;
     for (int shift = 56; shift >= 0; shift -= 8) {
         AfArgs a;
-        a.sx = b->s.sx; a.sq = b->s.sq; a.idx = b->idx; a.idx2 = b->idx2; a.dest = b->dest; a.dig = b->dig;
+        a.kx = b->ax; a.kx2 = b->kx2; a.idx = b->idx; a.idx2 = b->idx2; a.dest = b->dest; a.dig = b->dig;
         a.cur = bk[cur]; a.n_cur = ctr + cur; a.nxt = bk[cur ^ 1]; a.n_nxt = ctr + (cur ^ 1); a.cursor = ctr + 2; a.n_walk = ctr + 3; a.shift = shift;
         a.wlist = wl; a.n_wlist = ctr + 9; a.wcursor = ctr + 10;
+        a.wlist_s = wls; a.n_wlist_s = ctr + 14; a.wcursor_s = ctr + 15; a.wcursor_f = ctr + 48;
+        LQ_CUDA_OK(cudaMemsetAsync(ctr + 14, 0, 8, st));
+        LQ_CUDA_OK(cudaMemsetAsync(ctr + 48, 0, 4, st));
         a.curb = bkb[cur]; a.n_curb = ctr + 11 + cur; a.nxtb = bkb[cur ^ 1]; a.n_nxtb = ctr + 11 + (cur ^ 1); a.cursorb = ctr + 13;
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 11 + (cur ^ 1), 0, 4, st));
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 13, 0, 4, st));
@@ -1335,16 +1474,18 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         unsigned long long *n_elem = (unsigned long long*)(ctr + 16);
         a.n_elem = n_elem + (shift >> 3);
         { LqProfScope ps(lvl_name[shift >> 3], st, 2, 0);
-          lq_af_big_k<<<148 * 4, AFB_THREADS, 0, st>>>(a);
+          lq_af_big_k<false><<<148 * 4, AFB_THREADS, 0, st>>>(a);
           lq_af_level_k<<<148 * 16, AF_WARPS * 32, 0, st>>>(a); }
         a.n_elem = n_elem + 8 + (shift >> 3);
-        { LqProfScope ps(wlk_name[shift >> 3], st, 1, 0);
-          lq_af_walk_k<<<AFS_GRID, AFS_THREADS, AFS_WALKERS * 4096, st>>>(a, sc->wst.as<uint32_t>()); }
+        { LqProfScope ps(wlk_name[shift >> 3], st, 3, 0);
+          lq_af_walk_k<<<AFS_GRID, AFS_THREADS, AFS_WALKERS * 4096, st>>>(a, sc->wst.as<uint32_t>());
+          lq_af_big_k<true><<<148 * 4, AFB_THREADS, 0, st>>>(a);
+          lq_af_walk_small_k<<<148 * 16, AFW_WARPS * 32, 0, st>>>(a); }
         LQ_CUDA_OK(cudaGetLastError());
         cur ^= 1;
     }
-    LqProfScope psg("seed_gather", st, 1, nb * 36);
-    lq_gather_k<<<lq_grid(nb, 256), 256, 0, st>>>(nb, b->idx, b->s, b->ax, b->aq, b->am);
+    LqProfScope psg("seed_gather", st, 1, nb * 20);
+    lq_gather_k<<<lq_grid(nb, 256), 256, 0, st>>>(nb, b->idx, b->s, b->aq, b->am);
     LQ_CUDA_OK(cudaGetLastError());
     if (stats) {
         uint32_t w = 0; unsigned long long ne[16];
@@ -1570,9 +1711,9 @@ int lq_map_debug_sorted_seeds(LqQueryDev *qd, const LqIndexDev *ix, const LqMapO
     std::vector<uint64_t> h_qoff(2); h_qoff[0] = 0; h_qoff[1] = nb;
     BatchPtrs b; uint64_t *d_qoff = 0;
     LQ_TRY(seed_and_sort(qd, ix, mt, 0, q, q + 1, h_first, base, nb, h_qoff, sc, &b, &d_qoff, 0, st));
-    std::vector<uint64_t> x(nb), x2(nb); std::vector<uint32_t> sq(nb), sm(nb), aq(nb), am(nb);
+    std::vector<uint64_t> x(nb), x2(nb); std::vector<uint32_t> sq(nb), sm(nb), aq(nb), am(nb), pi(nb);
     if (nb) {
-        LQ_CUDA_OK(cudaMemcpyAsync(x.data(), b.s.sx, nb * 8, cudaMemcpyDeviceToHost, st));
+        LQ_CUDA_OK(cudaMemcpyAsync(pi.data(), b.idx, nb * 4, cudaMemcpyDeviceToHost, st));   /* sorted position -> seed number */
         LQ_CUDA_OK(cudaMemcpyAsync(sq.data(), b.s.sq, nb * 4, cudaMemcpyDeviceToHost, st));
         LQ_CUDA_OK(cudaMemcpyAsync(sm.data(), b.s.sm, nb * 4, cudaMemcpyDeviceToHost, st));
         LQ_CUDA_OK(cudaMemcpyAsync(x2.data(), b.ax, nb * 8, cudaMemcpyDeviceToHost, st));
@@ -1581,6 +1722,7 @@ int lq_map_debug_sorted_seeds(LqQueryDev *qd, const LqIndexDev *ix, const LqMapO
         LQ_CUDA_OK(cudaStreamSynchronize(st));
     }
     unsorted->resize(nb); sorted->resize(nb);
+    for (uint64_t i = 0; i < nb; ++i) x[pi[i] & 0x7fffffffu] = x2[i];   /* the keys were sorted in place */
     for (uint64_t i = 0; i < nb; ++i) {
         (*unsorted)[i].x = x[i]; (*unsorted)[i].y = (uint64_t)(sm[i] >> 24) << 32 | (sq[i] & 0x7fffffffu);
         (*sorted)[i].x = x2[i];  (*sorted)[i].y = (uint64_t)(am[i] >> 24) << 32 | aq[i];
