@@ -118,14 +118,14 @@ LQ_HD void lq_afw_refill_host(const uint8_t *dig, uint32_t n, const uint32_t *st
 /* ---- packed form: position and upcoming digits of a region in ONE 16-byte word, so that a step is a single load ----
  * st[c] = { x: next unread position of region c (bucket-relative),
  *           y, z, w: the digits of positions x, x+1, ... (byte 0 of y first); top byte of w = how many of them are valid (<= 11) }
- * The digit's own entry gives the element's destination AND is the next step's load, so the store of dest[p] is deferred by one
- * step (pend).  This is what lq_af_walk_k runs with one LANE per bucket: the dependent chain of a step is load -> and -> address. */
+ * The digit's own entry gives the element's destination AND is the next step's load.  This is what lq_af_walk_k runs with one LANE
+ * per bucket: the dependent chain of a step is load -> and -> address. */
 typedef struct
 #ifdef __CUDACC__
 __align__(16)
 #endif
 { uint32_t x, y, z, w; } lq_afp_st;
-typedef struct { uint32_t k, c, arrived, step, start_k, end_k, pend_p; int pend; } lq_afp_walk;
+typedef struct { uint32_t k, c, arrived, step, start_k, end_k; } lq_afp_walk;
 #define LQ_AFP_DIG 11
 #ifdef __CUDA_ARCH__
 #define LQ_FUNNEL_R8(lo_, hi_) __funnelshift_r((lo_), (hi_), 8)
@@ -137,35 +137,37 @@ LQ_HD void lq_afp_init(lq_afp_walk *s, const uint32_t *start)
 {
     uint32_t k = 0;
     while (k < 256 && start[k + 1] == start[k]) ++k;
-    s->k = k; s->c = k < 256 ? k : 0; s->arrived = 0; s->step = 0; s->pend = 0; s->pend_p = 0;
+    s->k = k; s->c = k < 256 ? k : 0; s->arrived = 0; s->step = 0;
     s->start_k = k < 256 ? start[k] : 0; s->end_k = k < 256 ? start[k + 1] : 0;
 }
 
 /* returns 1 when all n elements are placed, 0 when region s->c has no cached digit left (refill, then call again).
+ * Output is the walk itself: the t-th pick-up took position ord[t] and dropped it at slot[t].  Both streams are written in pick-up
+ * order, and in that order the reads and the writes of the payload permutation advance sequentially inside each of the 256
+ * regions -- which is what lets the permutation run at full sector efficiency afterwards (lq_af_big_k<true>).
  * The state of the digit's region is loaded as soon as the digit is known (Sn), before this step's bookkeeping: the dependent chain
  * of a step is load -> and -> address -> load, everything else sits in the shadow of the load.  Sn is stale only when the digit
  * names the region just read (d == c); the updated copy in registers is used then. */
-LQ_HD int lq_afp_run(lq_afp_walk *s, uint32_t n, const uint32_t *start, lq_afp_st *st, uint32_t *dest)
+LQ_HD int lq_afp_run(lq_afp_walk *s, uint32_t n, const uint32_t *start, lq_afp_st *st, uint32_t *ord, uint32_t *slot)
 {
-    uint32_t k = s->k, c = s->c, arrived = s->arrived, step = s->step, start_k = s->start_k, end_k = s->end_k, pend_p = s->pend_p;
-    int pend = s->pend, done = 1;
+    uint32_t k = s->k, c = s->c, arrived = s->arrived, step = s->step, start_k = s->start_k, end_k = s->end_k;
+    int done = 1;
     if (step < n) {
         lq_afp_st S = st[c];
         for (;;) {
-            if (pend) { dest[pend_p] = S.x; pend = 0; }         /* the previous element lands on the next pick of its region */
             const uint32_t left = S.w >> 24;
             if (left == 0) { done = 0; break; }
             const uint32_t d = S.y & 255u, p = S.x;
             const lq_afp_st Sn = st[d];
             S.x = p + 1; S.y = LQ_FUNNEL_R8(S.y, S.z); S.z = LQ_FUNNEL_R8(S.z, S.w); S.w = ((S.w >> 8) & 0xffffu) | (left - 1) << 24;
             st[c] = S;
-            ++step;
+            ord[step] = p;
             if (d != k) {
-                pend = 1; pend_p = p;
                 if (d != c) S = Sn;
+                slot[step] = S.x;                                  /* lands where its region's next pick-up is taken from */
                 c = d;
             } else {
-                dest[p] = start_k + arrived++;                     /* arrivals into the outer-loop region lag its pick-ups by the open hole */
+                slot[step] = start_k + arrived++;                  /* arrivals into the outer-loop region lag its pick-ups by the open hole */
                 if (c != k) S = Sn;
                 c = k;
                 if (S.x == end_k) {                                /* region k complete: open the next non-exhausted region */
@@ -175,11 +177,10 @@ LQ_HD int lq_afp_run(lq_afp_walk *s, uint32_t n, const uint32_t *start, lq_afp_s
                     S = st[c];
                 }
             }
-            if (step >= n) break;
+            if (++step >= n) break;
         }
-        if (done && pend) { dest[pend_p] = S.x; pend = 0; }
     }
-    s->k = k; s->c = c; s->arrived = arrived; s->step = step; s->start_k = start_k; s->end_k = end_k; s->pend_p = pend_p; s->pend = pend;
+    s->k = k; s->c = c; s->arrived = arrived; s->step = step; s->start_k = start_k; s->end_k = end_k;
     return done;
 }
 
@@ -197,6 +198,96 @@ LQ_HD void lq_afp_refill_host(const uint8_t *dig, const uint32_t *start, lq_afp_
     S.z = (uint32_t)b[4] | (uint32_t)b[5] << 8 | (uint32_t)b[6] << 16 | (uint32_t)b[7] << 24;
     S.w = (uint32_t)b[8] | (uint32_t)b[9] << 8 | (uint32_t)b[10] << 16 | (uint32_t)LQ_AFP_DIG << 24;
     st[r] = S;
+}
+
+/* ---- ring form: the walker never waits for a refill round ----
+ * st[c] = { x: next unread position of region c (bucket-relative); f: the digits of positions < f are in the ring;
+ *           r0, r1: ring of 8 digits, the digit of position q sits in byte (q & 7) }
+ * The walker writes x and nothing else; the refiller (on the device: the other warps of the CTA, running concurrently) rewrites
+ * the ring with the digits of positions x .. x+7 and THEN publishes f = x + 8.  Bytes of positions the walker may still read
+ * (x .. old f) are rewritten with the same values, so a stale x in the refiller or a stale ring in the walker is harmless; a
+ * walker that finds x == f re-reads until the refiller has been there.  One step = one 16-byte load, as in the packed form. */
+typedef struct
+#ifdef __CUDACC__
+__align__(16)
+#endif
+{ uint32_t x, f, r0, r1; } lq_afq_st;
+#define LQ_AFQ_RING 8
+#define LQ_AFQ_LOW 4          /* refill when at most this many cached digits are left */
+
+/* the refiller's rule for one region, given the 8 digits d8 from position x on (little-endian: digit of x in byte 0) */
+LQ_HD void lq_afq_ring_of(uint32_t x, uint64_t d8, uint32_t *r0, uint32_t *r1)
+{
+    const uint32_t sh = (x & 7u) * 8u;
+    const uint64_t r = sh ? (d8 << sh | d8 >> (64u - sh)) : d8;   /* digit of position q -> byte (q & 7) */
+    *r0 = (uint32_t)r; *r1 = (uint32_t)(r >> 32);
+}
+LQ_HD void lq_afq_refill_host(const uint8_t *dig, uint32_t n, lq_afq_st *st, uint32_t r)
+{
+    const uint32_t x = st[r].x;
+    uint64_t d8 = 0;
+    for (uint32_t j = 0; j < 8; ++j) if (x + j < n) d8 |= (uint64_t)dig[x + j] << (8 * j);
+    lq_afq_ring_of(x, d8, &st[r].r0, &st[r].r1);
+    st[r].f = x + LQ_AFQ_RING;
+}
+
+#ifdef __CUDA_ARCH__
+/* one volatile 16-byte shared-memory load (the states live in shared memory on the device) */
+#define LQ_AFQ_LOAD(dst_, ptr_) asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" \
+    : "=r"((dst_).x), "=r"((dst_).f), "=r"((dst_).r0), "=r"((dst_).r1) : "r"((uint32_t)__cvta_generic_to_shared(ptr_)) : "memory")
+#define LQ_AFQ_STORE_X(ptr_, v_) (*(volatile uint32_t*)&(ptr_)->x = (v_))
+#define LQ_AFQ_X(ptr_) (*(volatile const uint32_t*)&(ptr_)->x)
+#else
+#define LQ_AFQ_LOAD(dst_, ptr_) ((dst_) = *(ptr_))
+#define LQ_AFQ_STORE_X(ptr_, v_) ((ptr_)->x = (v_))
+#define LQ_AFQ_X(ptr_) ((ptr_)->x)
+#endif
+
+/* runs the whole walk.  host_dig: host builds pass the digits so that a starved region is refilled on the spot (and, to imitate
+ * the concurrent refiller, every region at or below the low-water mark is refilled every `host_sweep` steps). */
+LQ_HD void lq_afq_run(uint32_t n, const uint32_t *start, lq_afq_st *st, uint32_t *ord, uint32_t *slot, const uint8_t *host_dig, uint32_t host_sweep)
+{
+    uint32_t k = 0, c, arrived = 0, step = 0, start_k, end_k;
+    while (k < 256 && start[k + 1] == start[k]) ++k;
+    if (k >= 256 || n == 0) return;
+    c = k; start_k = start[k]; end_k = start[k + 1];
+    lq_afq_st S;
+    LQ_AFQ_LOAD(S, &st[c]);
+    for (;;) {
+        while (S.x == S.f) {                                   /* starved: the refiller has not been here yet */
+#ifndef __CUDA_ARCH__
+            lq_afq_refill_host(host_dig, n, st, c);
+#endif
+            LQ_AFQ_LOAD(S, &st[c]);
+        }
+#ifndef __CUDA_ARCH__
+        if (host_sweep && step % host_sweep == host_sweep - 1)
+            for (uint32_t r = 0; r < 256; ++r) if (st[r].f - st[r].x <= LQ_AFQ_LOW) { lq_afq_refill_host(host_dig, n, st, r); if (r == c) S = st[c]; }
+#endif
+        const uint32_t p = S.x, sh = (p & 7u) * 8u;
+        const uint32_t d = (uint32_t)((((uint64_t)S.r1 << 32) | S.r0) >> sh) & 255u;
+        lq_afq_st Sn;
+        LQ_AFQ_LOAD(Sn, &st[d]);                               /* stale only if d == c */
+        LQ_AFQ_STORE_X(&st[c], p + 1);
+        S.x = p + 1;
+        ord[step] = p;
+        if (d != k) {
+            if (d != c) S = Sn;
+            slot[step] = S.x;                                  /* lands where its region's next pick-up is taken from */
+            c = d;
+        } else {
+            slot[step] = start_k + arrived++;                  /* arrivals into the outer-loop region lag its pick-ups by the open hole */
+            if (c != k) S = Sn;
+            c = k;
+            if (S.x == end_k) {                                /* region k complete: open the next non-exhausted region */
+                do { ++k; } while (k < 256 && LQ_AFQ_X(&st[k]) == start[k + 1]);
+                if (k < 256) { c = k; start_k = start[k]; end_k = start[k + 1]; arrived = LQ_AFQ_X(&st[k]) - start_k; }
+                else c = 0;
+                LQ_AFQ_LOAD(S, &st[c]);
+            }
+        }
+        if (++step >= n) break;
+    }
 }
 
 /* Closed form for exactly two non-empty digits d0 < d1 (regions [0,n0) and [n0,n)).

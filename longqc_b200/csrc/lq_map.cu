@@ -299,7 +299,7 @@ struct AfBkt { uint32_t beg, end; };
 /* The sort moves (key, idx) pairs: kx[p] = sort key of the element now at p, idx[p] = its seed number (bit 31: the seed belongs to a
  * repeated query minimizer, so its key may be tied).  Nothing is gathered through idx until the very end (lq_gather_k). */
 struct AfArgs {
-    uint64_t *kx, *kx2; uint32_t *idx, *idx2, *dest; uint8_t *dig;
+    uint64_t *kx, *kx2; uint32_t *idx, *idx2, *dest, *ord; uint8_t *dig;   /* (ord, dest): pick-up order and slots of a walked bucket */
     const AfBkt *cur; const uint32_t *n_cur; AfBkt *nxt; uint32_t *n_nxt; uint32_t *cursor; uint32_t *n_walk;
     AfBkt *wlist; uint32_t *n_wlist; uint32_t *wcursor, *wcursor_f;   /* tied buckets with > 2 digits: walked by lq_af_walk_k (>= AFW_SMALL elements) ... */
     AfBkt *wlist_s; uint32_t *n_wlist_s; uint32_t *wcursor_s;   /* ... or by lq_af_walk_small_k (a warp per bucket) */
@@ -758,9 +758,16 @@ __global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
                 }
                 __syncthreads();
             }
-            /* 4. permute the payload */
-            #pragma unroll 4
-            for (uint32_t p = tid; p < n; p += AFB_THREADS) { const uint32_t d = dest[p]; idx2[d] = idx[p]; kx2[d] = kx[p]; }
+            /* 4. permute the payload.  A walked bucket comes as (ord[t], dest[t]) in pick-up order: consecutive t read and write
+             * consecutive positions inside each region, so the sectors of both sides are used whole. */
+            if (WALKED) {
+                const uint32_t *ord = a.ord + beg;
+                #pragma unroll 4
+                for (uint32_t t = tid; t < n; t += AFB_THREADS) { const uint32_t p = ord[t], d = dest[t]; idx2[d] = idx[p]; kx2[d] = kx[p]; }
+            } else {
+                #pragma unroll 4
+                for (uint32_t p = tid; p < n; p += AFB_THREADS) { const uint32_t d = dest[p]; idx2[d] = idx[p]; kx2[d] = kx[p]; }
+            }
             __syncthreads();
             #pragma unroll 4
             for (uint32_t p = tid; p < n; p += AFB_THREADS) { idx[p] = idx2[p]; kx[p] = kx2[p]; }
@@ -798,8 +805,6 @@ __global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
 #define AFS_SN 160                 /* staging capacity in the finish phase: start 1040 + cnt 1024 + keys 1280 + indices 640 < 4096 */
 #define AFS_GRID 148               /* one CTA per SM (224 KB of shared memory each) */
 #define AFS_ROW 260                /* u32 per bucket in the global scratch: 257 region starts */
-struct AfsMeta { uint32_t beg, n, nb; };
-
 __device__ __forceinline__ uint4 afw_load16(const uint8_t *addr)   /* 16 bytes from an arbitrary address (reads up to 31 bytes past it: the arena is padded) */
 {
     const uintptr_t A = (uintptr_t)addr & ~(uintptr_t)15; const uint32_t o = (uint32_t)((uintptr_t)addr & 15), q = o >> 2, sh = (o & 3) * 8;
@@ -812,13 +817,41 @@ __device__ __forceinline__ uint4 afw_load16(const uint8_t *addr)   /* 16 bytes f
     return make_uint4(__funnelshift_r(t0, t1, sh), __funnelshift_r(t1, t2, sh), __funnelshift_r(t2, t3, sh), __funnelshift_r(t3, t4, sh));
 }
 
+/* the refiller's step for four regions (entries e0, e0+stride, ...): a region with at most `low` cached digits left gets the
+ * 8 digits from its position on -- ring first, then (fence) the published bound (lq_afsort_core.h, ring form) */
+struct AfsMeta { uint32_t beg, n, nb; };
+__device__ __forceinline__ void afq_refill4(const uint8_t *dig, const AfsMeta *meta, lq_afq_st *state, uint32_t e0, uint32_t stride, uint32_t tot, uint32_t low)
+{
+    uint32_t x[4]; bool need[4]; uint4 v[4];
+    #pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const uint32_t e = e0 + u * stride;
+        need[u] = false; x[u] = 0;
+        if (e < tot) {
+            const unsigned long long xf = *(volatile const unsigned long long*)&state[e];
+            x[u] = (uint32_t)xf; need[u] = (uint32_t)(xf >> 32) - x[u] <= low;
+        }
+    }
+    #pragma unroll
+    for (int u = 0; u < 4; ++u) if (need[u]) v[u] = afw_load16(dig + meta[(e0 + u * stride) >> 8].beg + x[u]);
+    #pragma unroll
+    for (int u = 0; u < 4; ++u) if (need[u]) {
+        uint32_t r0, r1;
+        lq_afq_ring_of(x[u], (uint64_t)v[u].y << 32 | v[u].x, &r0, &r1);
+        lq_afq_st *e = &state[e0 + u * stride];
+        *(volatile unsigned long long*)&e->r0 = (unsigned long long)r1 << 32 | r0;
+        __threadfence_block();
+        *(volatile uint32_t*)&e->f = x[u] + LQ_AFQ_RING;
+    }
+}
+
 extern __shared__ __align__(16) uint8_t afs_smem[];
 
 __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk_k(AfArgs a, uint32_t *gstart /* gridDim.x * AFS_WALKERS * AFS_ROW */)
 {
-    lq_afp_st *state = (lq_afp_st*)afs_smem;                      /* [AFS_WALKERS][256] */
+    lq_afq_st *state = (lq_afq_st*)afs_smem;                      /* [AFS_WALKERS][256] */
     __shared__ AfsMeta meta[AFS_WALKERS];
-    __shared__ uint32_t s_base, s_alive[AFS_WW];
+    __shared__ uint32_t s_base; __shared__ volatile uint32_t s_live;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t nw = *a.n_wlist;
     uint32_t gsize = (nw + gridDim.x - 1) / gridDim.x;            /* buckets per generation: all CTAs busy, at most AFS_WALKERS */
@@ -871,7 +904,7 @@ __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk_k(AfArgs a, uint32_
             for (int j = 0; j < 8; ++j) {
                 const uint32_t r = 8 * lane + j;
                 gs[w * AFS_ROW + r] = run;
-                lq_afp_st e; e.x = run; e.y = e.z = e.w = 0;
+                lq_afq_st e; e.x = run; e.f = run; e.r0 = e.r1 = 0;      /* empty ring */
                 state[w * 256 + r] = e;
                 run += cc[j];
             }
@@ -879,40 +912,24 @@ __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk_k(AfArgs a, uint32_
             if (lane == 0) meta[w].nb = nb;
         }
         __syncthreads();
-        /* ---- rounds ---- */
+        /* ---- walk: warps 0..AFS_WW-1 walk (lane = bucket) while the other warps keep the digit rings filled (lq_afq_*) ---- */
         const uint32_t wl = wid * AFS_WPW + lane;                 /* this thread's bucket when it is a walker lane */
         const bool walker = wid < AFS_WW && lane < AFS_WPW && wl < nbk;
-        lq_afp_walk ws; bool fin = true; uint32_t my_n = 0; uint32_t *my_dest = 0; const uint32_t *my_start = gs;
-        if (walker) { my_start = gs + wl * AFS_ROW; lq_afp_init(&ws, my_start); fin = false; my_n = meta[wl].n; my_dest = a.dest + meta[wl].beg; }
-        for (;;) {
-            for (uint32_t e0 = tid; e0 < nbk * 256; e0 += 4 * AFS_THREADS) {   /* refill: consecutive threads, consecutive regions of a bucket; 4 loads in flight */
-                lq_afp_st S[4]; bool need[4]; uint4 v[4];
-                #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t e = e0 + u * AFS_THREADS;
-                    need[u] = false;
-                    if (e < nbk * 256) { S[u] = state[e]; need[u] = (S[u].w >> 24) < LQ_AFP_DIG; }   /* the region moved since its last refill */
-                }
-                #pragma unroll
-                for (int u = 0; u < 4; ++u) if (need[u]) v[u] = afw_load16(a.dig + meta[(e0 + u * AFS_THREADS) >> 8].beg + S[u].x);
-                #pragma unroll
-                for (int u = 0; u < 4; ++u) if (need[u]) {
-                    S[u].y = v[u].x; S[u].z = v[u].y; S[u].w = (v[u].z & 0x00ffffffu) | (uint32_t)LQ_AFP_DIG << 24;
-                    state[e0 + u * AFS_THREADS] = S[u];
-                }
+        if (tid == 0) s_live = AFS_WW;
+        for (uint32_t e0 = tid; e0 < nbk * 256; e0 += 4 * AFS_THREADS) afq_refill4(a.dig, meta, state, e0, AFS_THREADS, nbk * 256, 0xffffffffu);   /* every ring full */
+        __syncthreads();
+        if (wid < AFS_WW) {
+            if (walker) lq_afq_run(meta[wl].n, gs + wl * AFS_ROW, state + wl * 256, a.ord + meta[wl].beg, a.dest + meta[wl].beg, 0, 0);
+            __syncwarp();
+            if (lane == 0) atomicSub((uint32_t*)&s_live, 1u);
+        } else {
+            const uint32_t ht = tid - AFS_WW * 32, nh = AFS_THREADS - AFS_WW * 32;
+            while (s_live != 0) {
+                for (uint32_t e0 = ht; e0 < nbk * 256; e0 += 4 * nh) afq_refill4(a.dig, meta, state, e0, nh, nbk * 256, LQ_AFQ_LOW);
+                __nanosleep(100);
             }
-            __syncthreads();
-            if (wid < AFS_WW) {
-                if (!fin) fin = lq_afp_run(&ws, my_n, my_start, state + wl * 256, my_dest) != 0;
-                const uint32_t alive = __ballot_sync(0xffffffffu, !fin);
-                if (lane == 0) s_alive[wid] = alive;
-            }
-            __syncthreads();
-            uint32_t alive = 0;
-            #pragma unroll
-            for (int j = 0; j < AFS_WW; ++j) alive |= s_alive[j];
-            if (!alive) break;
         }
+        __syncthreads();
         if (tid == 0) {
             unsigned long long tot = 0;
             for (uint32_t w = 0; w < nbk; ++w) tot += meta[w].n;
@@ -1364,7 +1381,7 @@ static int upload_u32(LqDevBuf &b, const uint32_t *h, size_t n, cudaStream_t st)
 }
 
 struct BatchPtrs {
-    SeedArrays s; uint64_t *kx2; uint32_t *idx, *idx2, *dest; uint8_t *dig;   /* arena1, sort phase (s.sx == ax: the keys are sorted in place in arena2) */
+    SeedArrays s; uint64_t *kx2; uint32_t *idx, *idx2, *dest, *ord; uint8_t *dig;   /* arena1, sort phase (s.sx == ax: the keys are sorted in place in arena2) */
     int32_t *f, *p, *v, *t; uint64_t *uend; uint32_t *vl, *head, *gid;  /* arena1, chain phase (aliases) */
     uint64_t *ax; uint32_t *aq, *am;                           /* arena2 */
 };
@@ -1374,8 +1391,8 @@ static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 static int carve(LqMapScratch *sc, uint64_t nb, BatchPtrs *b)
 {
     const size_t n = (size_t)nb + 64;
-    /* sort phase: kx2 8, sq 4, sm 4, idx 4, idx2 4, dest 4, dig 1 */
-    const size_t sort_bytes = al(n * 8) + 5 * al(n * 4) + al(n);
+    /* sort phase: kx2 8, sq 4, sm 4, idx 4, idx2 4, dest 4, ord 4, dig 1 */
+    const size_t sort_bytes = al(n * 8) + 6 * al(n * 4) + al(n);
     /* chain phase: f,p,v,t 4 each, uend 8, vl 4, head 4, gid 4 */
     const size_t chain_bytes = 7 * al(n * 4) + al(n * 8) + 256;
     LQ_TRY(sc->arena1.ensure(std::max(sort_bytes, chain_bytes)));
@@ -1387,6 +1404,7 @@ static int carve(LqMapScratch *sc, uint64_t nb, BatchPtrs *b)
     b->idx = (uint32_t*)p; p += al(n * 4);
     b->idx2 = (uint32_t*)p; p += al(n * 4);
     b->dest = (uint32_t*)p; p += al(n * 4);
+    b->ord = (uint32_t*)p; p += al(n * 4);
     b->dig = (uint8_t*)p;
     p = (char*)sc->arena1.p;
     b->uend = (uint64_t*)p; p += al(n * 8);
@@ -1459,7 +1477,7 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     int cur = 0;
     for (int shift = 56; shift >= 0; shift -= 8) {
         AfArgs a;
-        a.kx = b->ax; a.kx2 = b->kx2; a.idx = b->idx; a.idx2 = b->idx2; a.dest = b->dest; a.dig = b->dig;
+        a.kx = b->ax; a.kx2 = b->kx2; a.idx = b->idx; a.idx2 = b->idx2; a.dest = b->dest; a.ord = b->ord; a.dig = b->dig;
         a.cur = bk[cur]; a.n_cur = ctr + cur; a.nxt = bk[cur ^ 1]; a.n_nxt = ctr + (cur ^ 1); a.cursor = ctr + 2; a.n_walk = ctr + 3; a.shift = shift;
         a.wlist = wl; a.n_wlist = ctr + 9; a.wcursor = ctr + 10;
         a.wlist_s = wls; a.n_wlist_s = ctr + 14; a.wcursor_s = ctr + 15; a.wcursor_f = ctr + 48;
