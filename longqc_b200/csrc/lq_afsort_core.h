@@ -200,96 +200,6 @@ LQ_HD void lq_afp_refill_host(const uint8_t *dig, const uint32_t *start, lq_afp_
     st[r] = S;
 }
 
-/* ---- ring form: the walker never waits for a refill round ----
- * st[c] = { x: next unread position of region c (bucket-relative); f: the digits of positions < f are in the ring;
- *           r0, r1: ring of 8 digits, the digit of position q sits in byte (q & 7) }
- * The walker writes x and nothing else; the refiller (on the device: the other warps of the CTA, running concurrently) rewrites
- * the ring with the digits of positions x .. x+7 and THEN publishes f = x + 8.  Bytes of positions the walker may still read
- * (x .. old f) are rewritten with the same values, so a stale x in the refiller or a stale ring in the walker is harmless; a
- * walker that finds x == f re-reads until the refiller has been there.  One step = one 16-byte load, as in the packed form. */
-typedef struct
-#ifdef __CUDACC__
-__align__(16)
-#endif
-{ uint32_t x, f, r0, r1; } lq_afq_st;
-#define LQ_AFQ_RING 8
-#define LQ_AFQ_LOW 4          /* refill when at most this many cached digits are left */
-
-/* the refiller's rule for one region, given the 8 digits d8 from position x on (little-endian: digit of x in byte 0) */
-LQ_HD void lq_afq_ring_of(uint32_t x, uint64_t d8, uint32_t *r0, uint32_t *r1)
-{
-    const uint32_t sh = (x & 7u) * 8u;
-    const uint64_t r = sh ? (d8 << sh | d8 >> (64u - sh)) : d8;   /* digit of position q -> byte (q & 7) */
-    *r0 = (uint32_t)r; *r1 = (uint32_t)(r >> 32);
-}
-LQ_HD void lq_afq_refill_host(const uint8_t *dig, uint32_t n, lq_afq_st *st, uint32_t r)
-{
-    const uint32_t x = st[r].x;
-    uint64_t d8 = 0;
-    for (uint32_t j = 0; j < 8; ++j) if (x + j < n) d8 |= (uint64_t)dig[x + j] << (8 * j);
-    lq_afq_ring_of(x, d8, &st[r].r0, &st[r].r1);
-    st[r].f = x + LQ_AFQ_RING;
-}
-
-#ifdef __CUDA_ARCH__
-/* one volatile 16-byte shared-memory load (the states live in shared memory on the device) */
-#define LQ_AFQ_LOAD(dst_, ptr_) asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" \
-    : "=r"((dst_).x), "=r"((dst_).f), "=r"((dst_).r0), "=r"((dst_).r1) : "r"((uint32_t)__cvta_generic_to_shared(ptr_)) : "memory")
-#define LQ_AFQ_STORE_X(ptr_, v_) (*(volatile uint32_t*)&(ptr_)->x = (v_))
-#define LQ_AFQ_X(ptr_) (*(volatile const uint32_t*)&(ptr_)->x)
-#else
-#define LQ_AFQ_LOAD(dst_, ptr_) ((dst_) = *(ptr_))
-#define LQ_AFQ_STORE_X(ptr_, v_) ((ptr_)->x = (v_))
-#define LQ_AFQ_X(ptr_) ((ptr_)->x)
-#endif
-
-/* runs the whole walk.  host_dig: host builds pass the digits so that a starved region is refilled on the spot (and, to imitate
- * the concurrent refiller, every region at or below the low-water mark is refilled every `host_sweep` steps). */
-LQ_HD void lq_afq_run(uint32_t n, const uint32_t *start, lq_afq_st *st, uint32_t *ord, uint32_t *slot, const uint8_t *host_dig, uint32_t host_sweep)
-{
-    uint32_t k = 0, c, arrived = 0, step = 0, start_k, end_k;
-    while (k < 256 && start[k + 1] == start[k]) ++k;
-    if (k >= 256 || n == 0) return;
-    c = k; start_k = start[k]; end_k = start[k + 1];
-    lq_afq_st S;
-    LQ_AFQ_LOAD(S, &st[c]);
-    for (;;) {
-        while (S.x == S.f) {                                   /* starved: the refiller has not been here yet */
-#ifndef __CUDA_ARCH__
-            lq_afq_refill_host(host_dig, n, st, c);
-#endif
-            LQ_AFQ_LOAD(S, &st[c]);
-        }
-#ifndef __CUDA_ARCH__
-        if (host_sweep && step % host_sweep == host_sweep - 1)
-            for (uint32_t r = 0; r < 256; ++r) if (st[r].f - st[r].x <= LQ_AFQ_LOW) { lq_afq_refill_host(host_dig, n, st, r); if (r == c) S = st[c]; }
-#endif
-        const uint32_t p = S.x, sh = (p & 7u) * 8u;
-        const uint32_t d = (uint32_t)((((uint64_t)S.r1 << 32) | S.r0) >> sh) & 255u;
-        lq_afq_st Sn;
-        LQ_AFQ_LOAD(Sn, &st[d]);                               /* stale only if d == c */
-        LQ_AFQ_STORE_X(&st[c], p + 1);
-        S.x = p + 1;
-        ord[step] = p;
-        if (d != k) {
-            if (d != c) S = Sn;
-            slot[step] = S.x;                                  /* lands where its region's next pick-up is taken from */
-            c = d;
-        } else {
-            slot[step] = start_k + arrived++;                  /* arrivals into the outer-loop region lag its pick-ups by the open hole */
-            if (c != k) S = Sn;
-            c = k;
-            if (S.x == end_k) {                                /* region k complete: open the next non-exhausted region */
-                do { ++k; } while (k < 256 && LQ_AFQ_X(&st[k]) == start[k + 1]);
-                if (k < 256) { c = k; start_k = start[k]; end_k = start[k + 1]; arrived = LQ_AFQ_X(&st[k]) - start_k; }
-                else c = 0;
-                LQ_AFQ_LOAD(S, &st[c]);
-            }
-        }
-        if (++step >= n) break;
-    }
-}
-
 /* Closed form for exactly two non-empty digits d0 < d1 (regions [0,n0) and [n0,n)).
  * fr[p]  = 1 if p is "foreign" (p < n0 with digit d1, or p >= n0 with digit d0)
  * rk[p]  = number of foreign positions before p within p's own region (exclusive rank)

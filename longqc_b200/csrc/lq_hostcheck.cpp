@@ -111,13 +111,6 @@ void afsort_levels(const uint64_t *key, uint32_t n, uint32_t *idx, int use_two)
                     }
                     for (uint32_t p = 0; p < m; ++p)
                         dest[beg + p] = lq_af_two_dest(p, n0, fr[p], rk[p], (uint32_t)P.size(), P.data(), Z.data());
-                } else if (use_two & 8) { // the ring form (walker and refiller concurrent on the device; here: refill on starvation + periodic sweeps)
-                    uint32_t st257[257]; lq_afq_st qst[256];
-                    for (int d = 0; d < 256; ++d) { st257[d] = start[d]; qst[d].x = start[d]; qst[d].f = start[d]; qst[d].r0 = qst[d].r1 = 0; }
-                    st257[256] = m;
-                    std::vector<uint32_t> ord(m), slot(m);
-                    lq_afq_run(m, st257, qst, ord.data(), slot.data(), dig.data() + beg, (use_two & 16) ? 37 : 0);
-                    for (uint32_t t = 0; t < m; ++t) dest[beg + ord[t]] = slot[t];
                 } else if (use_two & 4) { // the packed one-load-per-step form (what the device runs, one lane per bucket)
                     uint32_t st257[257]; lq_afp_st pst[256]; lq_afp_walk ws;
                     for (int d = 0; d < 256; ++d) { st257[d] = start[d]; pst[d].x = start[d]; pst[d].y = pst[d].z = pst[d].w = 0; }

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(RS_THREADS) lq_rs_hist_k(const uint32_t *__res
  * "CTA order" == "warp, row, lane" order == input order.  The CTA's 4096 records are first ordered by digit in shared
  * memory (stable), then written out run by run, so that consecutive threads store to consecutive addresses. */
 #define RS_SMEM_BYTES (RS_CHUNK * (4 + 8 + 1) + RS_WARPS * 256 * 4 + 256 * 4 + 256 * 8 + 33 * 4 + 64)
-__global__ void __launch_bounds__(RS_THREADS) lq_rs_scatter_k(const uint32_t *__restrict__ key_in, const uint64_t *__restrict__ y_in, const uint8_t *__restrict__ sp_in,
+__global__ void __launch_bounds__(RS_THREADS, 3) lq_rs_scatter_k(const uint32_t *__restrict__ key_in, const uint64_t *__restrict__ y_in, const uint8_t *__restrict__ sp_in,
                                                                uint64_t n, int shift, uint32_t nblk, const uint64_t *__restrict__ gbase,
                                                                uint32_t *__restrict__ key_out, uint64_t *__restrict__ y_out, uint8_t *__restrict__ sp_out)
 {
@@ -74,9 +74,9 @@ __global__ void __launch_bounds__(RS_THREADS) lq_rs_scatter_k(const uint32_t *__
     for (int d = lane; d < 256; d += 32) wbase[wid][d] = 0;
     __syncwarp();
     /* 1. per-warp digit counts */
-    uint32_t kv[RS_ROWS];
+    uint32_t kv[RS_ROWS]; uint64_t yv[RS_ROWS];   /* the payload is fetched up front too: the ordering loop below is a chain of warp syncs, no load may wait inside it */
     #pragma unroll
-    for (int r = 0; r < RS_ROWS; ++r) { const uint64_t i = base + (uint64_t)r * 32 + lane; kv[r] = i < n ? key_in[i] : 0; }
+    for (int r = 0; r < RS_ROWS; ++r) { const uint64_t i = base + (uint64_t)r * 32 + lane; kv[r] = i < n ? key_in[i] : 0; yv[r] = i < n ? y_in[i] : 0; }
     #pragma unroll
     for (int r = 0; r < RS_ROWS; ++r) {
         const uint64_t i = base + (uint64_t)r * 32 + lane;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(RS_THREADS) lq_rs_scatter_k(const uint32_t *__
         __syncwarp();
         if (ok) {
             if ((peers & lt) == 0) wbase[wid][d] += __popc(peers);
-            s_key[dst] = kv[r]; s_y[dst] = y_in[i];
+            s_key[dst] = kv[r]; s_y[dst] = yv[r];
             if (sp_in) s_sp[dst] = sp_in[i];
         }
         __syncwarp();

@@ -99,7 +99,7 @@ __global__ void lq_qstat_k(uint32_t nq, const uint64_t *__restrict__ first, cons
 
 /* ------------------------------------------------------------------ K4c: seed fill (one warp per kept query minimizer of the batch) */
 
-struct SeedArrays { uint64_t *sx; uint32_t *sq, *sm; };
+struct SeedArrays { uint64_t *sx; uint32_t *sq, *sm, *idx; };   /* idx[at] = at | tie mark: the sort's (key, idx) pairs start out here */
 
 __global__ void lq_fill_k(uint64_t mi0, uint64_t mi1, const uint32_t *__restrict__ qkey, const uint64_t *__restrict__ qy, const uint8_t *__restrict__ qspan, int k,
                           const uint64_t *__restrict__ first, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ neff,
@@ -136,6 +136,7 @@ __global__ void lq_fill_k(uint64_t mi0, uint64_t mi1, const uint32_t *__restrict
                 s.sq[at] = (uint32_t)(ql - ((int32_t)qpos + 1 - (int32_t)span) - 1) | tie;
             }
             s.sm[at] = span << 24 | rank;
+            s.idx[at] = (uint32_t)at | tie;
         }
         out += __popc(m);
     }
@@ -271,6 +272,7 @@ __global__ void lq_fill_masked_k(FlArgs a, uint64_t mi0, uint64_t mi1)
             if (((uint32_t)r & 1) == qstrand) { a.s.sx[at] = (r & 0xffffffff00000000ULL) | rpos; a.s.sq[at] = qpos; }
             else { a.s.sx[at] = 1ULL << 63 | (r & 0xffffffff00000000ULL) | rpos; a.s.sq[at] = sq_rev; }
             a.s.sm[at] = sm;
+            a.s.idx[at] = (uint32_t)at;
             ++at;
         }
     }
@@ -322,11 +324,7 @@ __global__ void lq_af_init_k(uint32_t nqb, const uint64_t *__restrict__ qoff /* 
     else if (n > 1) lq_af_insertion_kv(kx + beg, idx + beg, n); /* ksort.h:132 */
 }
 
-__global__ void lq_iota_k(uint32_t *__restrict__ idx, const uint32_t *__restrict__ sq, uint64_t n)
-{
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) idx[i] = (uint32_t)i | (sq[i] & 0x80000000u);   /* the tie mark of lq_fill_k travels with the element */
-}
+
 
 #define AF_WARPS 4
 #define AF_U 8
@@ -817,41 +815,15 @@ __device__ __forceinline__ uint4 afw_load16(const uint8_t *addr)   /* 16 bytes f
     return make_uint4(__funnelshift_r(t0, t1, sh), __funnelshift_r(t1, t2, sh), __funnelshift_r(t2, t3, sh), __funnelshift_r(t3, t4, sh));
 }
 
-/* the refiller's step for four regions (entries e0, e0+stride, ...): a region with at most `low` cached digits left gets the
- * 8 digits from its position on -- ring first, then (fence) the published bound (lq_afsort_core.h, ring form) */
 struct AfsMeta { uint32_t beg, n, nb; };
-__device__ __forceinline__ void afq_refill4(const uint8_t *dig, const AfsMeta *meta, lq_afq_st *state, uint32_t e0, uint32_t stride, uint32_t tot, uint32_t low)
-{
-    uint32_t x[4]; bool need[4]; uint4 v[4];
-    #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const uint32_t e = e0 + u * stride;
-        need[u] = false; x[u] = 0;
-        if (e < tot) {
-            const unsigned long long xf = *(volatile const unsigned long long*)&state[e];
-            x[u] = (uint32_t)xf; need[u] = (uint32_t)(xf >> 32) - x[u] <= low;
-        }
-    }
-    #pragma unroll
-    for (int u = 0; u < 4; ++u) if (need[u]) v[u] = afw_load16(dig + meta[(e0 + u * stride) >> 8].beg + x[u]);
-    #pragma unroll
-    for (int u = 0; u < 4; ++u) if (need[u]) {
-        uint32_t r0, r1;
-        lq_afq_ring_of(x[u], (uint64_t)v[u].y << 32 | v[u].x, &r0, &r1);
-        lq_afq_st *e = &state[e0 + u * stride];
-        *(volatile unsigned long long*)&e->r0 = (unsigned long long)r1 << 32 | r0;
-        __threadfence_block();
-        *(volatile uint32_t*)&e->f = x[u] + LQ_AFQ_RING;
-    }
-}
 
 extern __shared__ __align__(16) uint8_t afs_smem[];
 
 __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk_k(AfArgs a, uint32_t *gstart /* gridDim.x * AFS_WALKERS * AFS_ROW */)
 {
-    lq_afq_st *state = (lq_afq_st*)afs_smem;                      /* [AFS_WALKERS][256] */
+    lq_afp_st *state = (lq_afp_st*)afs_smem;                      /* [AFS_WALKERS][256] */
     __shared__ AfsMeta meta[AFS_WALKERS];
-    __shared__ uint32_t s_base; __shared__ volatile uint32_t s_live;
+    __shared__ uint32_t s_base, s_alive[AFS_WW];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t nw = *a.n_wlist;
     uint32_t gsize = (nw + gridDim.x - 1) / gridDim.x;            /* buckets per generation: all CTAs busy, at most AFS_WALKERS */
@@ -904,7 +876,7 @@ __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk_k(AfArgs a, uint32_
             for (int j = 0; j < 8; ++j) {
                 const uint32_t r = 8 * lane + j;
                 gs[w * AFS_ROW + r] = run;
-                lq_afq_st e; e.x = run; e.f = run; e.r0 = e.r1 = 0;      /* empty ring */
+                lq_afp_st e; e.x = run; e.y = e.z = e.w = 0;
                 state[w * 256 + r] = e;
                 run += cc[j];
             }
@@ -912,24 +884,40 @@ __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk_k(AfArgs a, uint32_
             if (lane == 0) meta[w].nb = nb;
         }
         __syncthreads();
-        /* ---- walk: warps 0..AFS_WW-1 walk (lane = bucket) while the other warps keep the digit rings filled (lq_afq_*) ---- */
+        /* ---- rounds: everybody refills the regions that moved, then the walker warps walk until every lane is done or out of digits ---- */
         const uint32_t wl = wid * AFS_WPW + lane;                 /* this thread's bucket when it is a walker lane */
         const bool walker = wid < AFS_WW && lane < AFS_WPW && wl < nbk;
-        if (tid == 0) s_live = AFS_WW;
-        for (uint32_t e0 = tid; e0 < nbk * 256; e0 += 4 * AFS_THREADS) afq_refill4(a.dig, meta, state, e0, AFS_THREADS, nbk * 256, 0xffffffffu);   /* every ring full */
-        __syncthreads();
-        if (wid < AFS_WW) {
-            if (walker) lq_afq_run(meta[wl].n, gs + wl * AFS_ROW, state + wl * 256, a.ord + meta[wl].beg, a.dest + meta[wl].beg, 0, 0);
-            __syncwarp();
-            if (lane == 0) atomicSub((uint32_t*)&s_live, 1u);
-        } else {
-            const uint32_t ht = tid - AFS_WW * 32, nh = AFS_THREADS - AFS_WW * 32;
-            while (s_live != 0) {
-                for (uint32_t e0 = ht; e0 < nbk * 256; e0 += 4 * nh) afq_refill4(a.dig, meta, state, e0, nh, nbk * 256, LQ_AFQ_LOW);
-                __nanosleep(100);
+        lq_afp_walk ws; bool fin = true; uint32_t my_n = 0; uint32_t *my_dest = 0, *my_ord = 0; const uint32_t *my_start = gs;
+        if (walker) { my_start = gs + wl * AFS_ROW; lq_afp_init(&ws, my_start); fin = false; my_n = meta[wl].n; my_dest = a.dest + meta[wl].beg; my_ord = a.ord + meta[wl].beg; }
+        for (;;) {
+            for (uint32_t e0 = tid; e0 < nbk * 256; e0 += 4 * AFS_THREADS) {   /* refill: consecutive threads, consecutive regions of a bucket; 4 loads in flight */
+                lq_afp_st S[4]; bool need[4]; uint4 v[4];
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t e = e0 + u * AFS_THREADS;
+                    need[u] = false;
+                    if (e < nbk * 256) { S[u] = state[e]; need[u] = (S[u].w >> 24) < LQ_AFP_DIG; }   /* the region moved since its last refill */
+                }
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) if (need[u]) v[u] = afw_load16(a.dig + meta[(e0 + u * AFS_THREADS) >> 8].beg + S[u].x);
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) if (need[u]) {
+                    S[u].y = v[u].x; S[u].z = v[u].y; S[u].w = (v[u].z & 0x00ffffffu) | (uint32_t)LQ_AFP_DIG << 24;
+                    state[e0 + u * AFS_THREADS] = S[u];
+                }
             }
+            __syncthreads();
+            if (wid < AFS_WW) {
+                if (!fin) fin = lq_afp_run(&ws, my_n, my_start, state + wl * 256, my_ord, my_dest) != 0;
+                const uint32_t alive = __ballot_sync(0xffffffffu, !fin);
+                if (lane == 0) s_alive[wid] = alive;
+            }
+            __syncthreads();
+            uint32_t alive = 0;
+            #pragma unroll
+            for (int j = 0; j < AFS_WW; ++j) alive |= s_alive[j];
+            if (!alive) break;
         }
-        __syncthreads();
         if (tid == 0) {
             unsigned long long tot = 0;
             for (uint32_t w = 0; w < nbk; ++w) tot += meta[w].n;
@@ -1021,49 +1009,64 @@ __global__ void lq_gather_k(uint64_t n, const uint32_t *__restrict__ idx, SeedAr
 /* ------------------------------------------------------------------ K6/K7: groups, chaining, accounting */
 
 /* head[i] = 1 when sorted seed i starts a (query, strand, target) run */
-__global__ void lq_heads_k(uint64_t n, const uint64_t *__restrict__ ax, uint32_t *__restrict__ head)
+/* The runs that can hold a chain, straight from the sorted keys.  A run = maximal stretch of one query's seeds with the same
+ * (strand, target) = the high word of the key.  A chain needs >= min_cnt anchors (chain.c:116-119) and its score cannot exceed the
+ * sum of its anchors' spans (chain.c:58: each link adds at most q_span), so only runs of T = max(min_cnt, ceil(min_sc / max_span))
+ * or more anchors matter -- ~1 % of them; the others are never listed.  Thread i: is seed i the first of its run (key differs from
+ * seed i-1; a query's first seed is handled by lq_runs_q_k) and does the run reach i+T-1?  Only then the run's end is located
+ * (galloping + binary search, clipped to the query) and the run appended: runs of <= CH_SMALL anchors to the front of `runs` (one
+ * thread each, lq_chain_small_k), longer ones to the back (a warp each, lq_chain_k). */
+#define CH_SMALL 16
+struct RunArgs {
+    const uint64_t *ax; uint64_t n; const uint64_t *qoff; uint32_t nqb; uint32_t thr;
+    uint2 *runs; uint32_t cap; uint32_t *n_small, *n_large; unsigned long long *n_heads;
+};
+__device__ __forceinline__ uint32_t run_query_of(const RunArgs &a, uint64_t i)   /* batch-relative query owning seed i */
 {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    head[i] = i == 0 || (ax[i] >> 32) != (ax[i - 1] >> 32);
+    uint32_t lo = 0, hi = a.nqb;
+    while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (a.qoff[mid] <= i) lo = mid; else hi = mid; }
+    return lo;
 }
-/* ...and a query boundary is a head too */
-__global__ void lq_qheads_k(uint32_t nqb, const uint64_t *__restrict__ qoff, uint64_t n, uint32_t *__restrict__ head)
+__device__ __forceinline__ void run_emit(const RunArgs &a, uint64_t i, uint64_t lim /* end of the query */)
+{
+    const uint32_t key = (uint32_t)(a.ax[i] >> 32);
+    uint64_t lo = i + a.thr - 1, step = 1, hi;          /* lo: known inside the run */
+    for (;;) { hi = lo + step; if (hi >= lim) { hi = lim; break; } if ((uint32_t)(a.ax[hi] >> 32) != key) break; lo = hi; step <<= 1; }
+    while (hi - lo > 1) { const uint64_t mid = lo + ((hi - lo) >> 1); if ((uint32_t)(a.ax[mid] >> 32) == key) lo = mid; else hi = mid; }
+    const uint32_t len = (uint32_t)(hi - i);
+    if (len <= CH_SMALL) a.runs[atomicAdd(a.n_small, 1u)] = make_uint2((uint32_t)i, (uint32_t)hi);
+    else a.runs[a.cap - 1 - atomicAdd(a.n_large, 1u)] = make_uint2((uint32_t)i, (uint32_t)hi);
+}
+__global__ void __launch_bounds__(256) lq_runs_k(RunArgs a)
+{
+    uint32_t my_heads = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t key = (uint32_t)(a.ax[i] >> 32);
+        const bool head = i > 0 && (uint32_t)(a.ax[i - 1] >> 32) != key;
+        my_heads += head;
+        if (!head || i + a.thr - 1 >= a.n || (uint32_t)(a.ax[i + a.thr - 1] >> 32) != key) continue;
+        const uint32_t q = run_query_of(a, i);
+        if (a.qoff[q] == i) continue;                    /* a query's first seed: lq_runs_q_k */
+        if (i + a.thr - 1 < a.qoff[q + 1]) run_emit(a, i, a.qoff[q + 1]);
+    }
+    my_heads = lq_warp_sum(my_heads);                    /* one counter update per warp of the whole grid, not per 32 seeds */
+    if ((threadIdx.x & 31) == 0 && my_heads) atomicAdd(a.n_heads, (unsigned long long)my_heads);
+}
+/* the run that starts a query */
+__global__ void lq_runs_q_k(RunArgs a)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nqb && qoff[q] < n && qoff[q + 1] > qoff[q]) head[qoff[q]] = 1;
-}
-__global__ void lq_gstart_k(uint64_t n, const uint32_t *__restrict__ head, const uint32_t *__restrict__ gid, uint32_t *__restrict__ gstart)
-{
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && head[i]) gstart[gid[i]] = (uint32_t)i;
-    if (i == n) gstart[gid[n]] = (uint32_t)n; /* gid[n] = number of groups */
-}
-
-/* groups that can hold a chain (>= min_cnt anchors, chain.c:116-119): compacted so that a warp is only spent on those */
-/* A chain needs >= min_cnt anchors, and its score cannot exceed the sum of the anchors' spans (chain.c:58: each link adds at most
- * q_span), so a run of n anchors with n*max_span < min_sc cannot produce a chain either.  Runs of <= CH_SMALL anchors go to the
- * one-thread-per-run kernel (list grows from the front of `big`), longer ones to the warp kernel (list grows from the back). */
-#define CH_SMALL 16
-__global__ void lq_biggroups_k(uint32_t ng, const uint32_t *__restrict__ gstart, uint32_t min_cnt, uint32_t min_sc, uint32_t max_span,
-                               uint32_t *__restrict__ big, uint32_t cap, uint32_t *__restrict__ n_small, uint32_t *__restrict__ n_large)
-{
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
-    const uint32_t n = g < ng ? gstart[g + 1] - gstart[g] : 0;
-    const bool ok = n >= min_cnt && (uint64_t)n * max_span >= min_sc;
-    const bool sm = ok && n <= CH_SMALL, lg = ok && n > CH_SMALL;
-    const uint32_t ms = __ballot_sync(0xffffffffu, sm), ml = __ballot_sync(0xffffffffu, lg);
-    uint32_t bs = 0, bl = 0;
-    if (lane == 0) { if (ms) bs = atomicAdd(n_small, (uint32_t)__popc(ms)); if (ml) bl = atomicAdd(n_large, (uint32_t)__popc(ml)); }
-    bs = __shfl_sync(0xffffffffu, bs, 0); bl = __shfl_sync(0xffffffffu, bl, 0);
-    if (sm) big[bs + __popc(ms & ((1u << lane) - 1))] = g;
-    if (lg) big[cap - 1 - (bl + __popc(ml & ((1u << lane) - 1)))] = g;
+    if (q >= a.nqb) return;
+    const uint64_t i = a.qoff[q], lim = a.qoff[q + 1];
+    if (i >= lim) return;
+    if (i == 0 || (uint32_t)(a.ax[i - 1] >> 32) == (uint32_t)(a.ax[i] >> 32)) atomicAdd(a.n_heads, 1ULL);   /* not counted by lq_runs_k */
+    if (i + a.thr - 1 < lim && (uint32_t)(a.ax[i + a.thr - 1] >> 32) == (uint32_t)(a.ax[i] >> 32)) run_emit(a, i, lim);
 }
 
 struct ChainArgs {
     const uint64_t *ax; const uint32_t *aq, *am;
     int32_t *f, *p, *v, *t; uint64_t *uend; uint32_t *vl, *s_lo, *s_hi;
-    const uint32_t *gstart; const uint32_t *big; uint32_t big_cap; const uint32_t *n_small, *n_groups; uint32_t *cursor;
+    const uint2 *runs; uint32_t big_cap; const uint32_t *n_small, *n_groups; uint32_t *cursor;   /* lq_runs_k: short runs from the front, long ones from the back */
     uint32_t nqb, q0; const uint64_t *qoff;
     const LqQStat *qstat; const uint32_t *qlen, *tlen; const uint64_t *first;
     uint64_t *lambda, *lambda2; uint32_t *mcnt;
@@ -1085,8 +1088,8 @@ __global__ void __launch_bounds__(CH_WARPS * 32) lq_chain_k(ChainArgs a)
         if (lane == 0) g = atomicAdd(a.cursor, 1u);
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= ng) break;
-        g = a.big[a.big_cap - 1 - g];
-        const int32_t gb = (int32_t)a.gstart[g], ge = (int32_t)a.gstart[g + 1], n = ge - gb;
+        const uint2 run = a.runs[a.big_cap - 1 - g];
+        const int32_t gb = (int32_t)run.x, ge = (int32_t)run.y, n = ge - gb;
         if (n < a.o.min_cnt) continue; /* a chain needs min_cnt anchors of one (strand, target) run (chain.c:116-119) */
         /* owning query */
         uint32_t lo = 0, hi = a.nqb;
@@ -1259,8 +1262,8 @@ __global__ void __launch_bounds__(128) lq_chain_small_k(ChainArgs a)
 {
     const uint32_t ns = *a.n_small;
     for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < ns; b += gridDim.x * blockDim.x) {
-        const uint32_t g = a.big[b];
-        const int32_t gb = (int32_t)a.gstart[g], n = (int32_t)a.gstart[g + 1] - gb;
+        const uint2 run = a.runs[b];
+        const int32_t gb = (int32_t)run.x, n = (int32_t)run.y - gb;
         uint32_t lo = 0, hi = a.nqb;
         while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (a.qoff[mid] <= (uint64_t)gb) lo = mid; else hi = mid; }
         const uint32_t q = a.q0 + lo;
@@ -1419,7 +1422,7 @@ static int carve(LqMapScratch *sc, uint64_t nb, BatchPtrs *b)
     b->ax = (uint64_t*)p; p += al(n * 8);
     b->aq = (uint32_t*)p; p += al(n * 4);
     b->am = (uint32_t*)p;
-    b->s.sx = b->ax;
+    b->s.sx = b->ax; b->s.idx = b->idx;
     return 0;
 }
 
@@ -1468,8 +1471,7 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     AfBkt *wls = sc->bkt.as<AfBkt>() + 3 * bcap;                                                     /* short walks: ctr[14] = count, ctr[15] = cursor */
     AfBkt *bkb[2] = { sc->bkt.as<AfBkt>() + 4 * bcap, sc->bkt.as<AfBkt>() + 4 * bcap + bcapb };   /* long buckets: ctr[11], ctr[12] = counts, ctr[13] = cursor */
     /* counters: ctr[0],ctr[1] = bucket counts of the two lists, ctr[2] = cursor, ctr[3] = walks */
-    lq_prof_count_launch(2);
-    lq_iota_k<<<lq_grid(nb, 256), 256, 0, st>>>(b->idx, b->s.sq, nb);
+    lq_prof_count_launch(1);
     lq_af_init_k<<<lq_grid(nqb, 128), 128, 0, st>>>(nqb, d_qoff, b->ax, b->idx, bk[0], ctr + 0, bkb[0], ctr + 11);
     LQ_CUDA_OK(cudaGetLastError());
     static const char *lvl_name[8] = { "seed_sort_s0", "seed_sort_s8", "seed_sort_s16", "seed_sort_s24", "seed_sort_s32", "seed_sort_s40", "seed_sort_s48", "seed_sort_s56" };
@@ -1526,7 +1528,7 @@ static void fill_flargs(FlArgs *fa, LqQueryDev *qd, const LqIndexDev *ix, const 
     fa->first = qd->first.as<uint64_t>(); fa->keep = qd->keep.as<uint32_t>(); fa->neff = qd->neff.as<uint32_t>(); fa->qtied = qd->qtied.as<uint8_t>();
     fa->counts = ix->counts.as<uint32_t>(); fa->offs = ix->offs.as<uint64_t>(); fa->pos = ix->rec.y.as<uint64_t>();
     fa->t = mt; fa->qlen = qd->reads.len.as<uint32_t>(); fa->thr = thr;
-    fa->krank = qd->krank.as<uint32_t>(); fa->soff = qd->soff.as<uint64_t>(); fa->seed_base = 0; fa->s.sx = 0; fa->s.sq = 0; fa->s.sm = 0;
+    fa->krank = qd->krank.as<uint32_t>(); fa->soff = qd->soff.as<uint64_t>(); fa->seed_base = 0; fa->s.sx = 0; fa->s.sq = 0; fa->s.sm = 0; fa->s.idx = 0;
     fa->q0 = q0; fa->q1 = q1;
     fa->mask = qd->fmask.as<uint32_t>(); fa->mstride = qd->fmask_stride;
 }
@@ -1619,32 +1621,26 @@ int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int m
         LQ_TRY(seed_and_sort(qd, ix, mt, filter_thr, q0, q1, h_first, seed_base, nb, h_qoff, sc, &b, &d_qoff, stats, st));
         if (nb > 0) {
             uint32_t *ctr = (uint32_t*)((char*)sc->misc.p + al((size_t)(nqb + 2) * 8));
-            /* groups */
-            lq_prof_count_launch(3);
-            lq_heads_k<<<lq_grid(nb, 256), 256, 0, st>>>(nb, b.ax, b.head);
-            lq_qheads_k<<<lq_grid(nqb, 256), 256, 0, st>>>(nqb, d_qoff, nb, b.head);
-            LQ_CUDA_OK(cudaGetLastError());
-            LQ_TRY((lq_exclusive_scan<uint32_t, uint32_t>(b.head, b.gid, nb, 1, sc->ws, st)));
-            uint32_t ng = 0;
-            LQ_CUDA_OK(cudaMemcpyAsync(&ng, b.gid + nb, 4, cudaMemcpyDeviceToHost, st));
-            LQ_CUDA_OK(cudaStreamSynchronize(st));
-            const size_t big_cap = (size_t)(nb / (uint64_t)std::max(opt->min_cnt, 1)) + 64;
-            LQ_TRY(sc->grp.ensure(((size_t)ng + 2) * 4 + big_cap * 4));
-            uint32_t *d_big = sc->grp.as<uint32_t>() + ng + 2;
-            lq_gstart_k<<<lq_grid(nb + 1, 256), 256, 0, st>>>(nb, b.head, b.gid, sc->grp.as<uint32_t>());
-            LQ_CUDA_OK(cudaGetLastError());
-            /* ctr[4] = n_groups, ctr[5] = cursor, ctr[6] = n_ovl, ctr[7] = n_chains */
+            /* runs that can chain (ctr[4] = long runs, ctr[8] = short runs, ctr[5] = cursor, ctr[6] = n_ovl, ctr[7] = n_chains; ctr[50..51] = u64 number of runs) */
+            const int max_span = qd->mins.has_span ? 255 : ix->k;
+            const uint32_t run_thr = (uint32_t)std::max(std::max(opt->min_cnt, 1), (std::max(opt->min_sc, 0) + max_span - 1) / max_span);
+            const size_t big_cap = (size_t)(nb / run_thr) + 64;
+            LQ_TRY(sc->grp.ensure(big_cap * sizeof(uint2)));
             const uint32_t ovl_cap = (uint32_t)std::min<uint64_t>(nb / (uint64_t)std::max(opt->min_cnt, 1) + 1024, 0x7fffffffULL);
             LQ_TRY(sc->ovl.ensure((size_t)ovl_cap * sizeof(LqOvl)));
             LQ_CUDA_OK(cudaMemsetAsync(ctr + 4, 0, 16, st));
-            lq_prof_count_launch(1);
-            /* ctr[4] = long runs (warp kernel), ctr[8] = short runs (thread kernel) */
             LQ_CUDA_OK(cudaMemsetAsync(ctr + 8, 0, 4, st));
-            lq_biggroups_k<<<lq_grid(ng, 256), 256, 0, st>>>(ng, sc->grp.as<uint32_t>(), (uint32_t)std::max(opt->min_cnt, 1), (uint32_t)std::max(opt->min_sc, 0),
-                                                             qd->mins.has_span ? 255u : (uint32_t)ix->k, d_big, (uint32_t)big_cap, ctr + 8, ctr + 4);
+            LQ_CUDA_OK(cudaMemsetAsync(ctr + 50, 0, 8, st));
+            RunArgs ra;
+            ra.ax = b.ax; ra.n = nb; ra.qoff = d_qoff; ra.nqb = nqb; ra.thr = run_thr; ra.runs = sc->grp.as<uint2>(); ra.cap = (uint32_t)big_cap;
+            ra.n_small = ctr + 8; ra.n_large = ctr + 4; ra.n_heads = (unsigned long long*)(ctr + 50);
+            { LqProfScope ps("runs", st, 2, nb * 8);
+              lq_runs_k<<<148 * 8, 256, 0, st>>>(ra);
+              lq_runs_q_k<<<lq_grid(nqb, 128), 128, 0, st>>>(ra); }
+            LQ_CUDA_OK(cudaGetLastError());
             ChainArgs a;
             a.ax = b.ax; a.aq = b.aq; a.am = b.am; a.f = b.f; a.p = b.p; a.v = b.v; a.t = b.t; a.uend = b.uend; a.vl = b.vl; a.s_lo = b.head; a.s_hi = b.gid;
-            a.gstart = sc->grp.as<uint32_t>(); a.big = d_big; a.big_cap = (uint32_t)big_cap; a.n_small = ctr + 8; a.n_groups = ctr + 4; a.cursor = ctr + 5;
+            a.runs = sc->grp.as<uint2>(); a.big_cap = (uint32_t)big_cap; a.n_small = ctr + 8; a.n_groups = ctr + 4; a.cursor = ctr + 5;
             a.nqb = nqb; a.q0 = q0; a.qoff = d_qoff; a.qstat = qd->qstat.as<LqQStat>(); a.qlen = qd->reads.len.as<uint32_t>(); a.tlen = ix->tlen.as<uint32_t>();
             a.first = qd->first.as<uint64_t>(); a.lambda = qd->lambda.as<uint64_t>(); a.lambda2 = qd->lambda2.as<uint64_t>(); a.mcnt = qd->mcnt.as<uint32_t>();
             a.ovl = sc->ovl.as<LqOvl>(); a.n_ovl = ctr + 6; a.ovl_cap = ovl_cap; a.n_chains = ctr + 7; a.o = *opt;
@@ -1655,8 +1651,9 @@ int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int m
             { LqProfScope ps("chain", st, 1, nb * 32);
               lq_chain_k<<<148 * 16, CH_WARPS * 32, 0, st>>>(a); }
             LQ_CUDA_OK(cudaGetLastError());
-            uint32_t h_ctr[4];
+            uint32_t h_ctr[4]; unsigned long long ng = 0;
             LQ_CUDA_OK(cudaMemcpyAsync(h_ctr, ctr + 4, 16, cudaMemcpyDeviceToHost, st));
+            LQ_CUDA_OK(cudaMemcpyAsync(&ng, ctr + 50, 8, cudaMemcpyDeviceToHost, st));
             LQ_CUDA_OK(cudaStreamSynchronize(st));
             const uint32_t n_ovl = h_ctr[2];
             if (n_ovl > ovl_cap) { fprintf(stderr, "[lqcov] overlap list overflow (%u > %u)\n", n_ovl, ovl_cap); return -1; }

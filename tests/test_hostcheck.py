@@ -56,7 +56,7 @@ def _keys(rng, n, mode):
             | rng.integers(0, 70000, n).astype(u))
 
 
-@pytest.mark.parametrize("use_two", [0, 1, 2, 3, 4, 5, 8, 9, 24, 25])   # bit 0: two-region closed form, bit 1: cached-digit walk, bit 2: packed one-load-per-step walk, bit 3: ring walk (bit 4: with periodic refill sweeps)
+@pytest.mark.parametrize("use_two", [0, 1, 2, 3, 4, 5])   # bit 0: two-region closed form, bit 1: cached-digit walk, bit 2: packed one-load-per-step walk (device)
 def test_seed_sort_walk_and_closed_form(use_two):
     """the queue-walk formulation (and the two-region closed form) reproduce ksort.h's permutation, ties included"""
     hc, o = liblq.hostcheck(), liblq.oracle()
