@@ -169,6 +169,20 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(scope):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one profiling scope per job, from the committed ncu launch list of
+    this same command (profiles/*_traffic.json, written by tools/summarize_launches.py); None when no capture names the scope."""
+    import glob
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            d = json.load(open(f))
+            if scope in d:
+                return d[scope]["dram_bytes_per_job"], os.path.relpath(f, ROOT)
+        except Exception:
+            pass
+    return None, None
+
+
 def profile_json(L):
     lib = L.load()
     lib.lqcov_profile_json.restype = C.c_size_t
@@ -275,8 +289,10 @@ def run_ours(a):
     roof = None
     if top:
         ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9 if top["ms"] > 0 else 0.0
+        traffic, traffic_src = load_traffic(top["name"])
         roof = {"kernel": top["name"], "bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "ms_per_launch_group": top["ms"] / max(1, a.steps),
+                "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes": top["bytes"] / max(1, a.steps), "ms_per_launch_group": top["ms"] / max(1, a.steps),
                 "note": "algorithmic bytes / CUDA-event time on the launching stream; see DESIGN.md for the bytes per unit"}
     sk = [k for k in klist if k["name"] == "sketch"]
     cpu = None

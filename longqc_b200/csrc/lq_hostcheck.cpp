@@ -78,6 +78,59 @@ uint64_t lqhc_hash64(uint64_t key, uint64_t mask) { return lq_hash64(key, mask);
 
 } // extern "C"
 
+// the 16-bases-per-lane form (lq_sketch_lane_core.h): every segment that may start from a handed-over state does, the others
+// take the per-position path; *n_inj counts the segments that did
+#include "lq_sketch_lane_core.h"
+namespace {
+struct LaneSink {
+    std::vector<lq_mm128> *v; uint32_t rid; int k;
+    void operator()(uint32_t h, uint32_t p) { lq_mm128 e; e.x = (uint64_t)h << 8 | (uint64_t)k; e.y = (uint64_t)rid << 32 | p; v->push_back(e); }
+};
+template <int W>
+int sketch_lanes(const char *seq, int len, int k, uint32_t rid, lq_mm128 *out, int cap, int *n_inj)
+{
+    std::vector<uint32_t> b2, nm; std::vector<lq_mm128> v; VecSink s; s.v = &v; LaneSink ls; ls.v = &v; ls.rid = rid; ls.k = k;
+    pack_read(seq, len, 0, b2, nm);
+    const int nseg = (len + LQ_RL_SEG - 1) / LQ_RL_SEG;
+    int inj = 0;
+    for (int sg = 0; sg < nseg; ++sg) {
+        const int i0 = sg * LQ_RL_SEG, nb = len - i0 < LQ_RL_SEG ? len - i0 : LQ_RL_SEG;
+        uint32_t cx[3][LQ_RL_SEG], zm[3] = {0, 0, 0}, ok[3] = {0, 0, 0};
+        for (int b = 0; b < 3; ++b) {          // this segment and the two before it
+            const int t = sg - b;
+            if (t < 0 || k > 15) continue;
+            lq_rl_cands(t > 0 ? b2[t - 1] : 0u, b2[t], k, cx[b], &zm[b], &ok[b]);
+        }
+        if (nb < LQ_RL_SEG) ok[0] &= (1u << nb) - 1;
+        if (lq_rl_inject_ok(nm.data(), (uint64_t)i0, i0, nb, ok[1], ok[2], W, k)) {
+            uint32_t wx[W], wp[W];
+            lq_rl_tail<W>(cx[1], zm[1], ok[1], i0 - LQ_RL_SEG, wx, wp);
+            lq_rl_steady<W>(cx[0], 1, zm[0], ok[0], i0, wx, wp, i0 + nb == len, ls);
+            ++inj;
+        } else {
+            for (int i = i0; i < i0 + nb; ++i) lq_sketch_at(b2.data(), nm.data(), 0, len, W, k, rid, i, s);
+        }
+    }
+    if (n_inj) *n_inj = inj;
+    int n = (int)v.size();
+    for (int i = 0; i < n && i < cap; ++i) out[i] = v[i];
+    return n;
+}
+}
+extern "C" int lqhc_sketch_lanes(const char *seq, int len, int w, int k, uint32_t rid, int *n_inj, lq_mm128 *out, int cap)
+{
+    switch (w) {
+    case 1: return sketch_lanes<1>(seq, len, k, rid, out, cap, n_inj);
+    case 3: return sketch_lanes<3>(seq, len, k, rid, out, cap, n_inj);
+    case 5: return sketch_lanes<5>(seq, len, k, rid, out, cap, n_inj);
+    case 7: return sketch_lanes<7>(seq, len, k, rid, out, cap, n_inj);
+    case 10: return sketch_lanes<10>(seq, len, k, rid, out, cap, n_inj);
+    case 16: return sketch_lanes<16>(seq, len, k, rid, out, cap, n_inj);
+    }
+    return -1;
+}
+
+
 // ---------------------------------------------------------------- seed sort (lq_afsort_core.h)
 #include "lq_afsort_core.h"
 namespace {

@@ -299,9 +299,13 @@ __global__ void lq_qseeds_k(uint32_t nq, const uint64_t *__restrict__ first, con
 
 struct AfBkt { uint32_t beg, end; };
 /* The sort moves (key, idx) pairs: kx[p] = sort key of the element now at p, idx[p] = its seed number (bit 31: the seed belongs to a
- * repeated query minimizer, so its key may be tied).  Nothing is gathered through idx until the very end (lq_gather_k). */
+ * repeated query minimizer, so its key may be tied).  Nothing is gathered through idx until the very end (lq_gather_k).
+ * Two buffers, no copy-back: a level reads its buckets from (kx, idx) and leaves every element it handles in (kx2, idx2); the roles
+ * swap from level to level.  An element is FINISHED when its sub-bucket has <= 64 elements (sorted on the spot) -- it must then sit
+ * in the primary buffer (kxp, idxp), which is this level's destination on every other level and costs one extra copy otherwise. */
 struct AfArgs {
-    uint64_t *kx, *kx2; uint32_t *idx, *idx2, *dest, *ord; uint8_t *dig;   /* (ord, dest): pick-up order and slots of a walked bucket */
+    uint64_t *kx, *kx2, *kxp; uint32_t *idx, *idx2, *idxp, *dest, *ord; uint8_t *dig;   /* (ord, dest): pick-up order and slots of a walked bucket */
+    int dst_primary;              /* (kx2, idx2) == (kxp, idxp) */
     const AfBkt *cur; const uint32_t *n_cur; AfBkt *nxt; uint32_t *n_nxt; uint32_t *cursor; uint32_t *n_walk;
     AfBkt *wlist; uint32_t *n_wlist; uint32_t *wcursor, *wcursor_f;   /* tied buckets with > 2 digits: walked by lq_af_walk_k (>= AFW_SMALL elements) ... */
     AfBkt *wlist_s; uint32_t *n_wlist_s; uint32_t *wcursor_s;   /* ... or by lq_af_walk_small_k (a warp per bucket) */
@@ -352,7 +356,7 @@ __device__ __forceinline__ void af_push_walk(const AfArgs &a, uint32_t beg, uint
 
 /* stable sort of a sub-bucket of 9..64 elements by key, one warp: each lane holds two elements, rank = #smaller + #equal-before
  * (== the order ksort.h's insertion sort leaves) */
-__device__ __forceinline__ void af_warp_ranksort(uint64_t *key, uint32_t *idx, uint32_t n, uint32_t lane)
+__device__ __forceinline__ void af_warp_ranksort(uint64_t *key, uint32_t *idx, uint32_t n, uint32_t lane, uint64_t *key2 = 0, uint32_t *idx2 = 0)
 {
     const uint32_t e0 = lane < n ? idx[lane] : 0, e1 = lane + 32 < n ? idx[lane + 32] : 0;
     const uint64_t k0 = lane < n ? key[lane] : ~0ULL, k1 = lane + 32 < n ? key[lane + 32] : ~0ULL;
@@ -363,8 +367,8 @@ __device__ __forceinline__ void af_warp_ranksort(uint64_t *key, uint32_t *idx, u
         r1 += kj < k1 || (kj == k1 && j < lane + 32);
     }
     __syncwarp();
-    if (lane < n) { idx[r0] = e0; key[r0] = k0; }
-    if (lane + 32 < n) { idx[r1] = e1; key[r1] = k1; }
+    if (lane < n) { idx[r0] = e0; key[r0] = k0; if (key2) { idx2[r0] = e0; key2[r0] = k0; } }
+    if (lane + 32 < n) { idx[r1] = e1; key[r1] = k1; if (key2) { idx2[r1] = e1; key2[r1] = k1; } }
     __syncwarp();
 }
 
@@ -374,65 +378,62 @@ template <int SN>
 __device__ __forceinline__ void af_finish_bucket(const AfArgs &a, uint32_t beg, uint32_t n, uint32_t nb, const uint32_t *cnt, const uint32_t *start,
                                                  const uint32_t *dest, uint32_t lane, uint64_t *s_k, uint32_t *s_i)
 {
-    uint64_t *kx = a.kx + beg, *kx2 = a.kx2 + beg; uint32_t *idx = a.idx + beg, *idx2 = a.idx2 + beg;
+    const uint64_t *ks = a.kx + beg; const uint32_t *is = a.idx + beg;        /* where the bucket is */
+    uint64_t *kd = a.kx2 + beg; uint32_t *id = a.idx2 + beg;                  /* where this level leaves it */
+    uint64_t *kp = a.kxp + beg; uint32_t *ip = a.idxp + beg;                  /* where finished elements belong */
+    if (a.shift > 0 && n <= SN) {
+        /* small bucket: permuted straight into shared memory, so that the insertion sorts of its sub-buckets run at shared-memory
+         * latency, and written out once */
+        if (nb > 1) for (uint32_t p = lane; p < n; p += 32) { const uint32_t d = dest[p]; s_i[d] = is[p]; s_k[d] = ks[p]; }
+        else for (uint32_t p = lane; p < n; p += 32) { s_i[p] = is[p]; s_k[p] = ks[p]; }
+        __syncwarp();
+        for (uint32_t d = lane; d < 256; d += 32) {
+            const uint32_t c = cnt[d];
+            const bool big_ = c > LQ_RS_MIN;
+            af_append(a, beg + start[d], c, big_);
+            if (!big_ && c > 1) lq_af_insertion_kv(s_k + start[d], s_i + start[d], c); /* ksort.h:88-98 on the staged copy */
+        }
+        __syncwarp();
+        for (uint32_t p = lane; p < n; p += 32) { id[p] = s_i[p]; kd[p] = s_k[p]; }
+        if (!a.dst_primary) for (uint32_t p = lane; p < n; p += 32) { ip[p] = s_i[p]; kp[p] = s_k[p]; }
+        __syncwarp();
+        return;
+    }
     if (nb > 1) {
         for (uint32_t p0 = lane; p0 < n; p0 += 32 * AF_U) {
             uint32_t dd[AF_U], ee[AF_U]; uint64_t kk[AF_U];
             #pragma unroll
-            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) { dd[u] = dest[p]; ee[u] = idx[p]; kk[u] = kx[p]; } }
+            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) { dd[u] = dest[p]; ee[u] = is[p]; kk[u] = ks[p]; } }
             #pragma unroll
-            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) { idx2[dd[u]] = ee[u]; kx2[dd[u]] = kk[u]; } }
+            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) { id[dd[u]] = ee[u]; kd[dd[u]] = kk[u]; } }
         }
-        __syncwarp();
-        for (uint32_t p0 = lane; p0 < n; p0 += 32 * AF_U) {
-            uint32_t ee[AF_U]; uint64_t kk[AF_U];
-            #pragma unroll
-            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) { ee[u] = idx2[p]; kk[u] = kx2[p]; } }
-            #pragma unroll
-            for (int u = 0; u < AF_U; ++u) { const uint32_t p = p0 + u * 32; if (p < n) { idx[p] = ee[u]; kx[p] = kk[u]; } }
-        }
-        __syncwarp();
+    } else {
+        for (uint32_t p = lane; p < n; p += 32) { id[p] = is[p]; kd[p] = ks[p]; }
     }
+    __syncwarp();
     if (a.shift > 0) {
-        if (n <= SN) {
-            /* small bucket: stage (key, index) in shared memory once, so that the insertion sorts of its sub-buckets run at
-             * shared-memory latency instead of two dependent global loads per comparison */
-            for (uint32_t p = lane; p < n; p += 32) { s_i[p] = idx[p]; s_k[p] = kx[p]; }
-            __syncwarp();
-            for (uint32_t d = lane; d < 256; d += 32) {
-                const uint32_t c = cnt[d];
-                const bool big_ = c > LQ_RS_MIN;
-                af_append(a, beg + start[d], c, big_);
-                if (!big_ && c > 1) { /* ksort.h:88-98 on the staged copy */
-                    uint64_t *kk = s_k + start[d]; uint32_t *ii = s_i + start[d];
-                    for (uint32_t x = 1; x < c; ++x) {
-                        const uint64_t kt = kk[x]; const uint32_t it = ii[x];
-                        if (kt < kk[x - 1]) {
-                            uint32_t j = x;
-                            while (j > 0 && kt < kk[j - 1]) { kk[j] = kk[j - 1]; ii[j] = ii[j - 1]; --j; }
-                            kk[j] = kt; ii[j] = it;
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            for (uint32_t p = lane; p < n; p += 32) { idx[p] = s_i[p]; kx[p] = s_k[p]; }
-        } else {
-            uint32_t mid = 0;   /* digits (bit per owned digit) whose sub-bucket has 9..64 elements: sorted by the whole warp afterwards */
-            for (uint32_t d = lane; d < 256; d += 32) {
-                const uint32_t c = cnt[d];
-                const bool big_ = c > LQ_RS_MIN;
-                af_append(a, beg + start[d], c, big_);
-                if (big_) {}
-                else if (c > 8) mid |= 1u << (d >> 5);
-                else if (c > 1) lq_af_insertion_kv(kx + start[d], idx + start[d], c);
-            }
-            __syncwarp();
-            for (uint32_t l = 0; l < 32; ++l) {
-                uint32_t m = __shfl_sync(0xffffffffu, mid, l);
-                while (m) { const uint32_t d = (uint32_t)(__ffs(m) - 1) * 32 + l; m &= m - 1; af_warp_ranksort(kx + start[d], idx + start[d], cnt[d], lane); }
+        uint32_t mid = 0;   /* digits (bit per owned digit) whose sub-bucket has 9..64 elements: sorted by the whole warp afterwards */
+        for (uint32_t d = lane; d < 256; d += 32) {
+            const uint32_t c = cnt[d];
+            const bool big_ = c > LQ_RS_MIN;
+            af_append(a, beg + start[d], c, big_);
+            if (big_ || c == 0) {}
+            else if (c > 8) mid |= 1u << (d >> 5);
+            else {
+                if (c > 1) lq_af_insertion_kv(kd + start[d], id + start[d], c);
+                if (!a.dst_primary) for (uint32_t x = 0; x < c; ++x) { kp[start[d] + x] = kd[start[d] + x]; ip[start[d] + x] = id[start[d] + x]; }
             }
         }
+        __syncwarp();
+        for (uint32_t l = 0; l < 32; ++l) {
+            uint32_t m = __shfl_sync(0xffffffffu, mid, l);
+            while (m) {
+                const uint32_t d = (uint32_t)(__ffs(m) - 1) * 32 + l; m &= m - 1;
+                af_warp_ranksort(kd + start[d], id + start[d], cnt[d], lane, a.dst_primary ? (uint64_t*)0 : kp + start[d], a.dst_primary ? (uint32_t*)0 : ip + start[d]);
+            }
+        }
+    } else if (!a.dst_primary) {
+        for (uint32_t p = lane; p < n; p += 32) { ip[p] = id[p]; kp[p] = kd[p]; }
     }
     __syncwarp();
 }
@@ -444,7 +445,7 @@ __device__ __forceinline__ void af_finish_bucket(const AfArgs &a, uint32_t beg, 
 __device__ __forceinline__ bool af_small_untied(const AfArgs &a, uint32_t beg, uint32_t n, uint32_t lane, uint64_t *s_k, uint32_t *s_i,
                                                 uint32_t *cnt, uint32_t *start, uint32_t *head)
 {
-    uint64_t *kx = a.kx + beg; uint32_t *idx = a.idx + beg;
+    const uint64_t *kx = a.kx + beg; const uint32_t *idx = a.idx + beg;
     for (uint32_t d = lane; d < 256; d += 32) cnt[d] = 0;
     __syncwarp();
     uint32_t tied = 0;
@@ -478,7 +479,9 @@ __device__ __forceinline__ bool af_small_untied(const AfArgs &a, uint32_t beg, u
         uint32_t m = __shfl_sync(0xffffffffu, mid, l);
         while (m) { const uint32_t d = (uint32_t)(__ffs(m) - 1) * 32 + l; m &= m - 1; af_warp_ranksort(s_k + start[d], s_i + start[d], cnt[d], lane); }
     }
-    for (uint32_t p = lane; p < n; p += 32) { kx[p] = s_k[p]; idx[p] = s_i[p]; }
+    uint64_t *kd = a.kx2 + beg; uint32_t *id = a.idx2 + beg;
+    for (uint32_t p = lane; p < n; p += 32) { kd[p] = s_k[p]; id[p] = s_i[p]; }                 /* groups that go on are read from here */
+    if (!a.dst_primary) { uint64_t *kp = a.kxp + beg; uint32_t *ip = a.idxp + beg; for (uint32_t p = lane; p < n; p += 32) { kp[p] = s_k[p]; ip[p] = s_i[p]; } }
     __syncwarp();
     return true;
 }
@@ -767,22 +770,30 @@ __global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
                 for (uint32_t p = tid; p < n; p += AFB_THREADS) { const uint32_t d = dest[p]; idx2[d] = idx[p]; kx2[d] = kx[p]; }
             }
             __syncthreads();
+        } else {   /* one digit: nothing moves, but the bucket changes buffers like every other */
             #pragma unroll 4
-            for (uint32_t p = tid; p < n; p += AFB_THREADS) { idx[p] = idx2[p]; kx[p] = kx2[p]; }
+            for (uint32_t p = tid; p < n; p += AFB_THREADS) { idx2[p] = idx[p]; kx2[p] = kx[p]; }
             __syncthreads();
         }
-        /* 5. sub-buckets (ksort.h:124-133) */
+        /* 5. sub-buckets (ksort.h:124-133), in the destination buffer; what is finished here must end in the primary one */
+        uint64_t *kp = a.kxp + beg; uint32_t *ip = a.idxp + beg;
         if (a.shift > 0) {
             if (tid < 256) {
-                const uint32_t c = s_cnt[tid];
+                const uint32_t c = s_cnt[tid], s0 = s_start[tid];
                 const bool big_ = c > LQ_RS_MIN;
-                af_append(a, beg + s_start[tid], c, big_);
-                if (c > 1 && c <= 8) lq_af_insertion_kv(kx + s_start[tid], idx + s_start[tid], c);
+                af_append(a, beg + s0, c, big_);
+                if (c >= 1 && c <= 8) {
+                    if (c > 1) lq_af_insertion_kv(kx2 + s0, idx2 + s0, c);
+                    if (!a.dst_primary) for (uint32_t x = 0; x < c; ++x) { kp[s0 + x] = kx2[s0 + x]; ip[s0 + x] = idx2[s0 + x]; }
+                }
             }
             for (uint32_t d = wid; d < 256; d += AFB_THREADS / 32) {   /* 9..64: a warp each, so that no thread sorts alone while 511 wait */
-                const uint32_t c = s_cnt[d];
-                if (c > 8 && c <= LQ_RS_MIN) af_warp_ranksort(kx + s_start[d], idx + s_start[d], c, lane);
+                const uint32_t c = s_cnt[d], s0 = s_start[d];
+                if (c > 8 && c <= LQ_RS_MIN) af_warp_ranksort(kx2 + s0, idx2 + s0, c, lane, a.dst_primary ? (uint64_t*)0 : kp + s0, a.dst_primary ? (uint32_t*)0 : ip + s0);
             }
+        } else if (!a.dst_primary) {
+            #pragma unroll 4
+            for (uint32_t p = tid; p < n; p += AFB_THREADS) { ip[p] = idx2[p]; kp[p] = kx2[p]; }
         }
     }
 }
@@ -1020,6 +1031,7 @@ __global__ void lq_gather_k(uint64_t n, const uint32_t *__restrict__ idx, SeedAr
 struct RunArgs {
     const uint64_t *ax; uint64_t n; const uint64_t *qoff; uint32_t nqb; uint32_t thr;
     uint2 *runs; uint32_t cap; uint32_t *n_small, *n_large; unsigned long long *n_heads;
+    uint32_t *cand, *wcount; uint64_t chunk; uint32_t cand_stride;   /* run starts that reach the threshold, listed per scanning warp (lq_runs_k) */
 };
 __device__ __forceinline__ uint32_t run_query_of(const RunArgs &a, uint64_t i)   /* batch-relative query owning seed i */
 {
@@ -1027,40 +1039,84 @@ __device__ __forceinline__ uint32_t run_query_of(const RunArgs &a, uint64_t i)  
     while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (a.qoff[mid] <= i) lo = mid; else hi = mid; }
     return lo;
 }
-__device__ __forceinline__ void run_emit(const RunArgs &a, uint64_t i, uint64_t lim /* end of the query */)
+__device__ __forceinline__ uint64_t run_end(const RunArgs &a, uint64_t i, uint64_t lim /* end of the query */)
 {
     const uint32_t key = (uint32_t)(a.ax[i] >> 32);
     uint64_t lo = i + a.thr - 1, step = 1, hi;          /* lo: known inside the run */
     for (;;) { hi = lo + step; if (hi >= lim) { hi = lim; break; } if ((uint32_t)(a.ax[hi] >> 32) != key) break; lo = hi; step <<= 1; }
     while (hi - lo > 1) { const uint64_t mid = lo + ((hi - lo) >> 1); if ((uint32_t)(a.ax[mid] >> 32) == key) lo = mid; else hi = mid; }
-    const uint32_t len = (uint32_t)(hi - i);
-    if (len <= CH_SMALL) a.runs[atomicAdd(a.n_small, 1u)] = make_uint2((uint32_t)i, (uint32_t)hi);
-    else a.runs[a.cap - 1 - atomicAdd(a.n_large, 1u)] = make_uint2((uint32_t)i, (uint32_t)hi);
+    return hi;
 }
-__global__ void __launch_bounds__(256) lq_runs_k(RunArgs a)
+/* append the run [i, hi) (hi == 0: nothing); called by whole warps: one counter update per warp and list */
+__device__ __forceinline__ void run_append(const RunArgs &a, uint64_t i, uint64_t hi)
 {
-    uint32_t my_heads = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t key = (uint32_t)(a.ax[i] >> 32);
-        const bool head = i > 0 && (uint32_t)(a.ax[i - 1] >> 32) != key;
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
+    const bool sm = hi != 0 && hi - i <= CH_SMALL, lg = hi != 0 && hi - i > CH_SMALL;
+    const uint32_t ms = __ballot_sync(0xffffffffu, sm), ml = __ballot_sync(0xffffffffu, lg);
+    uint32_t bs = 0, bl = 0;
+    if (lane == 0) { if (ms) bs = atomicAdd(a.n_small, (uint32_t)__popc(ms)); if (ml) bl = atomicAdd(a.n_large, (uint32_t)__popc(ml)); }
+    bs = __shfl_sync(0xffffffffu, bs, 0); bl = __shfl_sync(0xffffffffu, bl, 0);
+    if (sm) a.runs[bs + __popc(ms & lt)] = make_uint2((uint32_t)i, (uint32_t)hi);
+    if (lg) a.runs[a.cap - 1 - (bl + __popc(ml & lt))] = make_uint2((uint32_t)i, (uint32_t)hi);
+}
+#define RUN_GRID (148 * 8)
+#define RUN_THREADS 256
+#define RUN_WARPS (RUN_GRID * RUN_THREADS / 32)
+/* warp gw scans the contiguous chunk [gw*chunk, (gw+1)*chunk) of the seeds and lists its candidates in its own stretch of `cand`
+ * (at most chunk/thr + 1 of them: candidate runs are disjoint and >= thr long), so that listing takes no atomic at all */
+__global__ void __launch_bounds__(RUN_THREADS) lq_runs_k(RunArgs a)
+{
+    const uint32_t lane = threadIdx.x & 31, gw = (blockIdx.x * RUN_THREADS + threadIdx.x) >> 5;
+    const uint64_t beg = (uint64_t)gw * a.chunk, end = beg + a.chunk < a.n ? beg + a.chunk : a.n;
+    uint32_t *mine = a.cand + (size_t)gw * a.cand_stride;
+    uint32_t my_heads = 0, cnt = 0;
+    for (uint64_t i0 = beg; i0 < end; i0 += 32) {       /* a.chunk is a multiple of 32 */
+        const uint64_t i = i0 + lane;
+        bool head = false, cand = false;
+        if (i < end) {
+            const uint32_t key = (uint32_t)(a.ax[i] >> 32);
+            head = i > 0 && (uint32_t)(a.ax[i - 1] >> 32) != key;
+            cand = head && i + a.thr - 1 < a.n && (uint32_t)(a.ax[i + a.thr - 1] >> 32) == key;
+        }
         my_heads += head;
-        if (!head || i + a.thr - 1 >= a.n || (uint32_t)(a.ax[i + a.thr - 1] >> 32) != key) continue;
-        const uint32_t q = run_query_of(a, i);
-        if (a.qoff[q] == i) continue;                    /* a query's first seed: lq_runs_q_k */
-        if (i + a.thr - 1 < a.qoff[q + 1]) run_emit(a, i, a.qoff[q + 1]);
+        const uint32_t m = __ballot_sync(0xffffffffu, cand);
+        if (cand) mine[cnt + __popc(m & ((1u << lane) - 1))] = (uint32_t)i;
+        cnt += __popc(m);
     }
+    if (lane == 0) a.wcount[gw] = cnt;
     my_heads = lq_warp_sum(my_heads);                    /* one counter update per warp of the whole grid, not per 32 seeds */
-    if ((threadIdx.x & 31) == 0 && my_heads) atomicAdd(a.n_heads, (unsigned long long)my_heads);
+    if (lane == 0 && my_heads) atomicAdd(a.n_heads, (unsigned long long)my_heads);
+}
+/* locating a run's end is serial pointer chasing: a thread per candidate, so that no lane waits on another's search */
+__global__ void __launch_bounds__(RUN_THREADS) lq_runs_emit_k(RunArgs a)
+{
+    const uint32_t lane = threadIdx.x & 31, gw = (blockIdx.x * RUN_THREADS + threadIdx.x) >> 5;
+    const uint32_t *mine = a.cand + (size_t)gw * a.cand_stride;
+    const uint32_t nc = a.wcount[gw];
+    for (uint32_t c0 = 0; c0 < nc; c0 += 32) {
+        uint64_t i = 0, hi = 0;
+        if (c0 + lane < nc) {
+            i = mine[c0 + lane];
+            const uint32_t q = run_query_of(a, i);
+            if (a.qoff[q] != i && i + a.thr - 1 < a.qoff[q + 1]) hi = run_end(a, i, a.qoff[q + 1]);   /* a query's first seed: lq_runs_q_k */
+        }
+        run_append(a, i, hi);
+    }
 }
 /* the run that starts a query */
 __global__ void lq_runs_q_k(RunArgs a)
 {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= a.nqb) return;
-    const uint64_t i = a.qoff[q], lim = a.qoff[q + 1];
-    if (i >= lim) return;
-    if (i == 0 || (uint32_t)(a.ax[i - 1] >> 32) == (uint32_t)(a.ax[i] >> 32)) atomicAdd(a.n_heads, 1ULL);   /* not counted by lq_runs_k */
-    if (i + a.thr - 1 < lim && (uint32_t)(a.ax[i + a.thr - 1] >> 32) == (uint32_t)(a.ax[i] >> 32)) run_emit(a, i, lim);
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;      /* the grid is a whole number of warps */
+    uint64_t i = 0, hi = 0;
+    if (q < a.nqb) {
+        i = a.qoff[q];
+        const uint64_t lim = a.qoff[q + 1];
+        if (i < lim) {
+            if (i == 0 || (uint32_t)(a.ax[i - 1] >> 32) == (uint32_t)(a.ax[i] >> 32)) atomicAdd(a.n_heads, 1ULL);   /* not counted by lq_runs_k */
+            if (i + a.thr - 1 < lim && (uint32_t)(a.ax[i + a.thr - 1] >> 32) == (uint32_t)(a.ax[i] >> 32)) hi = run_end(a, i, lim);
+        }
+    }
+    run_append(a, i, hi);
 }
 
 struct ChainArgs {
@@ -1479,7 +1535,10 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     int cur = 0;
     for (int shift = 56; shift >= 0; shift -= 8) {
         AfArgs a;
-        a.kx = b->ax; a.kx2 = b->kx2; a.idx = b->idx; a.idx2 = b->idx2; a.dest = b->dest; a.ord = b->ord; a.dig = b->dig;
+        const int odd = ((56 - shift) >> 3) & 1;           /* even levels read the primary buffer (ax, idx) and leave their buckets in (kx2, idx2); odd levels the other way */
+        a.kx = odd ? b->kx2 : b->ax; a.kx2 = odd ? b->ax : b->kx2; a.idx = odd ? b->idx2 : b->idx; a.idx2 = odd ? b->idx : b->idx2;
+        a.kxp = b->ax; a.idxp = b->idx; a.dst_primary = odd;
+        a.dest = b->dest; a.ord = b->ord; a.dig = b->dig;
         a.cur = bk[cur]; a.n_cur = ctr + cur; a.nxt = bk[cur ^ 1]; a.n_nxt = ctr + (cur ^ 1); a.cursor = ctr + 2; a.n_walk = ctr + 3; a.shift = shift;
         a.wlist = wl; a.n_wlist = ctr + 9; a.wcursor = ctr + 10;
         a.wlist_s = wls; a.n_wlist_s = ctr + 14; a.wcursor_s = ctr + 15; a.wcursor_f = ctr + 48;
@@ -1625,7 +1684,9 @@ int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int m
             const int max_span = qd->mins.has_span ? 255 : ix->k;
             const uint32_t run_thr = (uint32_t)std::max(std::max(opt->min_cnt, 1), (std::max(opt->min_sc, 0) + max_span - 1) / max_span);
             const size_t big_cap = (size_t)(nb / run_thr) + 64;
-            LQ_TRY(sc->grp.ensure(big_cap * sizeof(uint2)));
+            const uint64_t run_chunk = (((nb + RUN_WARPS - 1) / RUN_WARPS) + 31) & ~31ULL;
+            const uint32_t cand_stride = (uint32_t)(run_chunk / run_thr + 2);
+            LQ_TRY(sc->grp.ensure(big_cap * sizeof(uint2) + ((size_t)RUN_WARPS * cand_stride + RUN_WARPS + 16) * 4));
             const uint32_t ovl_cap = (uint32_t)std::min<uint64_t>(nb / (uint64_t)std::max(opt->min_cnt, 1) + 1024, 0x7fffffffULL);
             LQ_TRY(sc->ovl.ensure((size_t)ovl_cap * sizeof(LqOvl)));
             LQ_CUDA_OK(cudaMemsetAsync(ctr + 4, 0, 16, st));
@@ -1634,8 +1695,10 @@ int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int m
             RunArgs ra;
             ra.ax = b.ax; ra.n = nb; ra.qoff = d_qoff; ra.nqb = nqb; ra.thr = run_thr; ra.runs = sc->grp.as<uint2>(); ra.cap = (uint32_t)big_cap;
             ra.n_small = ctr + 8; ra.n_large = ctr + 4; ra.n_heads = (unsigned long long*)(ctr + 50);
-            { LqProfScope ps("runs", st, 2, nb * 8);
-              lq_runs_k<<<148 * 8, 256, 0, st>>>(ra);
+            ra.cand = (uint32_t*)(sc->grp.as<uint2>() + big_cap); ra.wcount = ra.cand + (size_t)RUN_WARPS * cand_stride; ra.chunk = run_chunk; ra.cand_stride = cand_stride;
+            { LqProfScope ps("runs", st, 3, nb * 8);
+              lq_runs_k<<<RUN_GRID, RUN_THREADS, 0, st>>>(ra);
+              lq_runs_emit_k<<<RUN_GRID, RUN_THREADS, 0, st>>>(ra);
               lq_runs_q_k<<<lq_grid(nqb, 128), 128, 0, st>>>(ra); }
             LQ_CUDA_OK(cudaGetLastError());
             ChainArgs a;

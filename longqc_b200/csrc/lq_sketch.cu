@@ -17,6 +17,7 @@
  */
 #include "lq_cuda.cuh"
 #include "lq_sketch_core.h"
+#include "lq_sketch_lane_core.h"
 #include "lq_device.h"
 
 #define SK_THREADS 256
@@ -30,7 +31,8 @@
 
 __global__ void lq_pack_k(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ seq_off, const uint64_t *__restrict__ slot0,
                           const uint32_t *__restrict__ len, uint32_t n_reads, uint64_t n_slots, int sdust_tbl,
-                          uint32_t *__restrict__ b2, uint32_t *__restrict__ nm, uint32_t *__restrict__ slot_read)
+                          uint32_t *__restrict__ b2, uint32_t *__restrict__ nm, uint32_t *__restrict__ slot_read,
+                          const uint8_t *seq_lo, const uint8_t *seq_hi /* the bases of all reads lie in [seq_lo, seq_hi) */)
 {
     /* one thread per 32 bases: two 2-bit words and one ambiguity word */
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -45,12 +47,36 @@ __global__ void lq_pack_k(const uint8_t *__restrict__ seq, const uint64_t *__res
     const uint64_t L = len[rd];
     const uint8_t *s = seq + seq_off[rd];
     uint32_t w0 = 0, w1 = 0, m = 0;
-    #pragma unroll 8
-    for (int j = 0; j < 32; ++j) {
-        uint32_t c = 4;
-        if (i0 + j < L) c = lq_nt4(s[i0 + j], sdust_tbl);
-        if (c < 4) { if (j < 16) w0 |= c << (2 * j); else w1 |= c << (2 * (j - 16)); }
-        else m |= 1u << j;
+    const uint8_t *A = s + i0;
+    const uintptr_t A16 = (uintptr_t)A & ~(uintptr_t)15;
+    if (i0 + 32 <= L && A16 >= (uintptr_t)seq_lo && A16 + 48 <= (uintptr_t)seq_hi) {
+        /* 32 whole bases: three aligned 16-byte loads cover them wherever the read starts; realigned with funnel shifts */
+        const uint4 *P = (const uint4*)A16;
+        const uint4 x0 = P[0], x1 = P[1], x2 = P[2];
+        const uint32_t o = (uint32_t)((uintptr_t)A & 15), q = o >> 2, sh = (o & 3) * 8;
+        const uint32_t w[12] = { x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w };
+        uint32_t sel[9];
+        #pragma unroll
+        for (int u = 0; u < 9; ++u) sel[u] = q == 0 ? w[u] : q == 1 ? w[u + 1] : q == 2 ? w[u + 2] : w[u + 3];
+        #pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t v = __funnelshift_r(sel[u], sel[u + 1], sh);
+            #pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = 4 * u + e;
+                const uint32_t c = lq_nt4((v >> (8 * e)) & 255u, sdust_tbl);
+                if (c < 4) { if (j < 16) w0 |= c << (2 * j); else w1 |= c << (2 * (j - 16)); }
+                else m |= 1u << j;
+            }
+        }
+    } else {
+        #pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            uint32_t c = 4;
+            if (i0 + j < L) c = lq_nt4(s[i0 + j], sdust_tbl);
+            if (c < 4) { if (j < 16) w0 |= c << (2 * j); else w1 |= c << (2 * (j - 16)); }
+            else m |= 1u << j;
+        }
     }
     b2[t * 2] = w0; b2[t * 2 + 1] = w1; nm[t] = m;
 }
@@ -298,7 +324,7 @@ __global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
 #define RK_CAP 32
 #define RK_TILE (RK_SEG * RK_THREADS)
 
-template <int W, int MODE /* 0: buffer in smem, 1: write directly at `wat` */>
+template <int W, int MODE /* 0: buffer in smem, 1: write directly at `wat` */, int THREADS = RK_THREADS, int CAP = RK_CAP /* staging geometry of the calling kernel */>
 __device__ __forceinline__ int rk_scan(const SkArgs &a, uint32_t rd, uint64_t g0, int L, int i0, int i1 /* segment [i0,i1) */,
                                        uint2 *s_rec, int tid, uint64_t wat)
 {
@@ -319,7 +345,7 @@ __device__ __forceinline__ int rk_scan(const SkArgs &a, uint32_t rd, uint64_t g0
     int n = 0;
     bool last_slow = false;
     lq_sk_buf sbuf;
-    #define RK_EMIT(H_, P_) do { if (MODE == 0) { if (n < RK_CAP) s_rec[n * RK_THREADS + tid] = make_uint2((H_), (P_)); } \
+    #define RK_EMIT(H_, P_) do { if (MODE == 0) { if (n < CAP) s_rec[n * THREADS + tid] = make_uint2((H_), (P_)); } \
                                  else { a.out_key[wat + n] = (H_); a.out_y[wat + n] = (uint64_t)rid << 32 | (P_); } ++n; } while (0)
     uint32_t wb = 0, wn = 0;               /* current packed words */
     int i = p0;
@@ -494,6 +520,126 @@ __global__ void __launch_bounds__(RK_THREADS) lq_sketch_roll_k(SkArgs a)
     } else rk_scan<W, 1>(a, rd, g0, L, i0, i1, s_rec, tid, at);   /* low-complexity tile: scan again, writing in place */
 }
 
+/* ------------------------------------------------------------------ K1, lane form (w = 5 or 10, k <= 15): 16 bases per thread
+ *
+ * lq_sketch_lane_core.h: a thread owns one packed word, computes the candidates of its 16 bases, hands the tail of them to the
+ * next lane by shuffle and starts the reference's steady state from the tail it receives -- no warm-up.  Lanes 0 and 1 of a warp
+ * are halo lanes (they redo the two segments before the warp's first one and emit nothing), so a warp emits 30 segments = 480
+ * bases and a CTA of 4 warps 1920.  A segment that may not start from a handed-over state (read start, ambiguous bases,
+ * palindromic runs) runs rk_scan with its certified warm-up.  Output staging, look-back and overflow handling as in
+ * lq_sketch_roll_k. */
+#define RL_THREADS 512             /* 16 warps: 7680 bases per tile, so that the look-back is paid once per ~2600 records */
+#define RL_CAP 16                  /* staged records per thread (16 bases emit ~5); more: the tile is scanned again writing in place */
+#define RL_SMEM (RL_CAP * RL_THREADS * 8 + LQ_RL_SEG * RL_THREADS * 4)
+#define RL_EMIT 30
+#define RL_TILE_SEGS (RL_EMIT * (RL_THREADS / 32))
+
+struct RlStage {
+    uint2 *rec; int tid; int n;
+    __device__ __forceinline__ void operator()(uint32_t h, uint32_t p) { if (n < RL_CAP) rec[n * RL_THREADS + tid] = make_uint2(h, p); ++n; }
+};
+struct RlWrite {
+    uint32_t *key; uint64_t *yy; uint64_t at; uint64_t ridhi;
+    __device__ __forceinline__ void operator()(uint32_t h, uint32_t p) { key[at] = h; yy[at] = ridhi | p; ++at; }
+};
+
+template <int W>
+__global__ void __launch_bounds__(RL_THREADS) lq_sketch_lane_k(SkArgs a)
+{
+    extern __shared__ __align__(16) uint8_t rl_smem[];
+    uint2 *s_rec = (uint2*)rl_smem;                                   /* RL_CAP x RL_THREADS staged records (64 KB) */
+    uint32_t *s_cx = (uint32_t*)(s_rec + RL_CAP * RL_THREADS);        /* candidate j of thread t at [j * RL_THREADS + t] (32 KB) */
+    __shared__ uint64_t scan_sm[33];
+    __shared__ uint32_t s_tile; __shared__ uint64_t s_base; __shared__ int s_over;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) { s_tile = atomicAdd(a.ticket, 1u); s_over = 0; }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    /* this lane's segment (index in units of 16 bases of the packed stream; negative: before the data) */
+    const int64_t seg = ((int64_t)tile * (RL_THREADS / 32) + wid) * RL_EMIT + (lane - 2);
+    const bool halo = lane < 2;
+    bool live = seg >= 0 && (uint64_t)(seg >> 3) < a.n_slots;
+    uint32_t rd = 0; uint64_t g0 = 0, g = 0; int L = 0, i0 = 0, i1 = 0;
+    if (live) {
+        g = (uint64_t)seg * LQ_RL_SEG;
+        const uint64_t slot = g >> 7;
+        rd = a.slot_read[slot];
+        const uint64_t s0 = a.slot0[rd];
+        L = (int)a.len[rd]; g0 = s0 * LQ_SLOT;
+        i0 = (int)(slot - s0) * LQ_SLOT + (int)(g & 127);
+        i1 = i0 + LQ_RL_SEG < L ? i0 + LQ_RL_SEG : L;
+        if (i0 >= L) live = false;                     /* padding after the read's last base */
+    }
+    /* candidates of the segment, the tail for the next lane, the tail of the previous one */
+    uint32_t cx[LQ_RL_SEG], zmask = 0, okmask = 0, tx[W], tp[W];
+    if (live) {
+        lq_rl_cands(seg > 0 ? a.b2[seg - 1] : 0u, a.b2[seg], a.k, cx, &zmask, &okmask);
+        if (i1 - i0 < LQ_RL_SEG) okmask &= (1u << (i1 - i0)) - 1;
+    } else {
+        #pragma unroll
+        for (int j = 0; j < LQ_RL_SEG; ++j) cx[j] = 0;
+    }
+    lq_rl_tail<W>(cx, zmask, okmask, i0, tx, tp);
+    #pragma unroll
+    for (int j = 0; j < LQ_RL_SEG; ++j) s_cx[j * RL_THREADS + tid] = cx[j];   /* read back by this thread only */
+    const uint32_t ok1 = __shfl_up_sync(0xffffffffu, okmask, 1), ok2 = __shfl_up_sync(0xffffffffu, okmask, 2);
+    uint32_t wx[W], wp[W];
+    #pragma unroll
+    for (int t = 0; t < W; ++t) { wx[t] = __shfl_up_sync(0xffffffffu, tx[t], 1); wp[t] = __shfl_up_sync(0xffffffffu, tp[t], 1); }
+    const bool emit = live && !halo;
+    const bool inj = emit && lq_rl_inject_ok(a.nm, g, i0, i1 - i0, ok1, ok2, W, a.k);
+    int n = 0;
+    if (inj) {
+        RlStage st; st.rec = s_rec; st.tid = tid; st.n = 0;
+        uint32_t rx[W], rp[W];                          /* the ring is consumed: keep the received tail for a possible second run */
+        #pragma unroll
+        for (int t = 0; t < W; ++t) { rx[t] = wx[t]; rp[t] = wp[t]; }
+        lq_rl_steady<W>(s_cx + tid, RL_THREADS, zmask, okmask, i0, rx, rp, i1 == L, st);
+        n = st.n;
+    } else if (emit) n = rk_scan<W, 0, RL_THREADS, RL_CAP>(a, rd, g0, L, i0, i1, s_rec, tid, 0);
+    if (n > RL_CAP) s_over = 1;
+    uint64_t tot;
+    const uint64_t ex = lq_block_excl_scan((uint64_t)n, scan_sm, &tot);
+    /* decoupled look-back (warp 0) */
+    if (tid < 32) {
+        const unsigned long long FLAG_AGG = 1ULL << 62, FLAG_PRE = 2ULL << 62, VMASK = (1ULL << 62) - 1;
+        uint64_t base = 0;
+        if (tile == 0) { if (tid == 0) atomicExch(&a.state[0], FLAG_PRE | tot); }
+        else {
+            if (tid == 0) atomicExch(&a.state[tile], FLAG_AGG | tot);
+            int64_t hi = (int64_t)tile - 1; uint32_t spins = 0;
+            for (;;) {
+                const int64_t j = hi - tid;
+                unsigned long long sv = FLAG_PRE;
+                if (j >= 0) sv = *(volatile unsigned long long*)&a.state[j];
+                const uint32_t ready = __ballot_sync(0xffffffffu, (sv >> 62) != 0);
+                const uint32_t pre = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+                const int stop = pre ? __ffs(pre) - 1 : 31;
+                const uint32_t need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1);
+                if ((ready & need) != need) { __nanosleep(64); if (++spins > (1u << 24)) { if (tid == 0) atomicOr(a.err, 1u); break; } continue; }
+                uint64_t v = (tid <= stop) ? (sv & VMASK) : 0;
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                base += v;
+                if (pre) break;
+                hi -= 32;
+            }
+            if (tid == 0) atomicExch(&a.state[tile], FLAG_PRE | (base + tot));
+        }
+        if (tid == 0) s_base = base;
+    }
+    __syncthreads();
+    const uint64_t at = s_base + ex;
+    if (s_base + tot > a.cap || n == 0) return;
+    const uint64_t ridhi = (uint64_t)(a.rid_base + rd) << 32;
+    if (!s_over) {
+        for (int j = 0; j < n; ++j) { const uint2 r = s_rec[j * RL_THREADS + tid]; a.out_key[at + j] = r.x; a.out_y[at + j] = ridhi | r.y; }
+    } else if (inj) {                                    /* low-complexity tile: scan again, writing in place */
+        RlWrite wr; wr.key = a.out_key; wr.yy = a.out_y; wr.at = at; wr.ridhi = ridhi;
+        lq_rl_steady<W>(s_cx + tid, RL_THREADS, zmask, okmask, i0, wx, wp, i1 == L, wr);
+    } else rk_scan<W, 1, RL_THREADS, RL_CAP>(a, rd, g0, L, i0, i1, s_rec, tid, at);
+}
+
 /* ------------------------------------------------------------------ HPC sketch: one thread per read (spike-in run, reference sketch.c:93-104) */
 
 struct SkWriteSpan {
@@ -532,7 +678,11 @@ __global__ void lq_read_first_k(const uint64_t *__restrict__ y, uint64_t n, uint
 
 /* test switch: force the tiled position-parallel kernel even where the rolling kernel applies (LQCOV_SKETCH_TILED=1) */
 static int g_sketch_tiled = getenv("LQCOV_SKETCH_TILED") ? atoi(getenv("LQCOV_SKETCH_TILED")) : 0;
-extern "C" void lqcov_debug_sketch_tiled(int on) { g_sketch_tiled = on; }
+/* on = 1: tiled kernel; on = 2: lane kernel (16 bases per thread, lq_sketch_lane_core.h); 0: the default (rolling kernel where it
+ * applies).  The lane kernel is exact and tested, but measured slower on B200 (14.9 ms vs 12.0 ms for 840 Mbases): with 16 bases
+ * per thread the dependent slot -> read -> length loads and the per-tile look-back are paid four times as often. */
+static int g_sketch_lanes = getenv("LQCOV_SKETCH_LANES") ? atoi(getenv("LQCOV_SKETCH_LANES")) : 0;
+extern "C" void lqcov_debug_sketch_tiled(int on) { g_sketch_tiled = on == 1; g_sketch_lanes = on == 2; }
 
 int lq_reads_upload(LqReadsDev *d, const uint8_t *h_seq, const uint64_t *h_off, uint32_t n_reads, int seq_on_device, int sdust_tbl, cudaStream_t st)
 {
@@ -573,7 +723,8 @@ int lq_reads_upload(LqReadsDev *d, const uint8_t *h_seq, const uint64_t *h_off, 
     if (slots) {
         LqProfScope ps("pack", st, 1, d->n_bases + slots * (LQ_SLOT_W2 + LQ_SLOT_WN + 1) * 4);
         lq_pack_k<<<lq_grid(slots * 4, 256), 256, 0, st>>>(d_seq, d->off.as<uint64_t>(), d->slot0.as<uint64_t>(), d->len.as<uint32_t>(),
-                                                           n_reads, slots, sdust_tbl, d->b2.as<uint32_t>(), d->nm.as<uint32_t>(), d->slot_read.as<uint32_t>());
+                                                           n_reads, slots, sdust_tbl, d->b2.as<uint32_t>(), d->nm.as<uint32_t>(), d->slot_read.as<uint32_t>(),
+                                                           d_seq + h_off[0], d_seq + h_off[n_reads]);
         LQ_CUDA_OK(cudaGetLastError());
     }
     return 0;
@@ -592,7 +743,9 @@ int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_b
     uint64_t total = 0;
     if (!is_hpc) {
         const bool roll = (w == 5 || w == 10) && k <= 15 && !g_sketch_tiled;
-        const unsigned nblk = roll ? (unsigned)((rd->n_slots * LQ_SLOT + RK_TILE - 1) / RK_TILE) : (unsigned)((rd->n_slots * LQ_SLOT + SK_TILE - 1) / SK_TILE);
+        const bool lanes = roll && g_sketch_lanes;
+        const unsigned nblk = lanes ? (unsigned)((rd->n_slots * (LQ_SLOT / LQ_RL_SEG) + RL_TILE_SEGS - 1) / RL_TILE_SEGS)
+                            : roll ? (unsigned)((rd->n_slots * LQ_SLOT + RK_TILE - 1) / RK_TILE) : (unsigned)((rd->n_slots * LQ_SLOT + SK_TILE - 1) / SK_TILE);
         LQ_TRY(out->blk.ensure((size_t)(nblk + 2) * 8 + 64));
         unsigned long long *state = out->blk.as<unsigned long long>();
         uint32_t *ticket = (uint32_t*)(state + nblk + 1), *err = ticket + 1;
@@ -605,9 +758,15 @@ int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_b
             LQ_CUDA_OK(cudaMemsetAsync(state, 0, (size_t)(nblk + 2) * 8 + 16, st));
             a.ticket = ticket; a.state = state; a.cap = cap; a.err = err;
             a.out_key = out->key.as<uint32_t>(); a.out_y = out->y.as<uint64_t>();
+            if (lanes) {
+                LQ_CUDA_OK(cudaFuncSetAttribute(lq_sketch_lane_k<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM));
+                LQ_CUDA_OK(cudaFuncSetAttribute(lq_sketch_lane_k<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM));
+            }
             {
                 LqProfScope ps("sketch", st, 1, rd->n_slots * (LQ_SLOT_W2 + LQ_SLOT_WN) * 4 + (uint64_t)((double)rd->n_bases * 2.0 / (w + 1)) * 12);
-                if (w == 5 && k <= 15 && !g_sketch_tiled) lq_sketch_roll_k<5><<<nblk, RK_THREADS, 0, st>>>(a);        /* LongQC's overlap runs */
+                if (lanes && w == 5) lq_sketch_lane_k<5><<<nblk, RL_THREADS, RL_SMEM, st>>>(a);                              /* LongQC's overlap runs */
+                else if (lanes && w == 10) lq_sketch_lane_k<10><<<nblk, RL_THREADS, RL_SMEM, st>>>(a);                       /* LongQC's spike-in run */
+                else if (w == 5 && k <= 15 && !g_sketch_tiled) lq_sketch_roll_k<5><<<nblk, RK_THREADS, 0, st>>>(a);
                 else if (w == 10 && k <= 15 && !g_sketch_tiled) lq_sketch_roll_k<10><<<nblk, RK_THREADS, 0, st>>>(a); /* LongQC's spike-in run */
                 else if (w == 5) lq_sketch_k<5, 5><<<nblk, SK_THREADS, 0, st>>>(a);
                 else if (w == 10) lq_sketch_k<10, 10><<<nblk, SK_THREADS, 0, st>>>(a);

@@ -41,6 +41,25 @@ def test_sketch_tiled_kernel_where_rolling_is_default(w, k):
     assert np.array_equal(x, want["x"]) and np.array_equal(y, want["y"])
 
 
+@pytest.mark.parametrize("w,k", [(5, 12), (10, 15), (5, 15)])
+def test_sketch_lane_kernel(w, k):
+    """the 16-bases-per-lane kernel (state handed over by warp shuffle, lq_sketch_lane_core.h) is exact as well; long clean reads
+    so that nearly every segment starts from a handed-over state, plus the adversarial set for the fall-backs"""
+    L = _L()
+    rng = np.random.default_rng(300 + w + k)
+    seqs = liblq.adversarial_seqs(rng, 120, 2500)
+    for _ in range(40):
+        seqs.append(bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(rng.integers(500, 20000))).tobytes()))
+    rs = liblq.reads_from_seqs(seqs)
+    L.load().lqcov_debug_sketch_tiled(2)
+    try:
+        x, y = L.sketch(rs, L.Opt(w=w, k=k), rid_base=3)
+    finally:
+        L.load().lqcov_debug_sketch_tiled(0)
+    want = liblq.oracle_sketch_set(rs, w, k, 0, rid_base=3)
+    assert np.array_equal(x, want["x"]) and np.array_equal(y, want["y"])
+
+
 def test_sketch_hpc():
     L = _L()
     rng = np.random.default_rng(5)
