@@ -211,10 +211,17 @@ extern "C" int lqcov_part_sketch(lqcov_ctx *c, const lqcov_reads_t *shard, uint3
     double t0 = now_ms();
     LqIndexDev *ix = &c->ix;
     c->part_ready = false; c->use_full = false;
-    LQ_TRY(lq_reads_upload(&c->treads, (const uint8_t*)shard->seq, shard->seq_off, shard->n, shard->seq_on_device, 0, c->st));
-    LQ_CUDA_OK(cudaStreamSynchronize(c->st));
-    c->stats.t_upload_ms += now_ms() - t0; t0 = now_ms();
-    LQ_TRY(lq_sketch_run(&c->treads, c->opt.w, c->opt.k, c->opt.is_hpc, rid_base, &ix->rec, c->ws, c->st)); /* rid restarts at 0 in every part (index.c:287) */
+    int piped = 1;
+    if (!shard->seq_on_device) {   /* host bases: copy, pack and sketch overlap chunk by chunk where the rolling kernel applies */
+        piped = lq_upload_sketch_pipelined(&c->treads, (const uint8_t*)shard->seq, shard->seq_off, shard->n, c->opt.w, c->opt.k, c->opt.is_hpc, rid_base, &ix->rec, c->ws, c->st);
+        if (piped < 0) return -1;
+    }
+    if (piped == 1) {
+        LQ_TRY(lq_reads_upload(&c->treads, (const uint8_t*)shard->seq, shard->seq_off, shard->n, shard->seq_on_device, 0, c->st));
+        LQ_CUDA_OK(cudaStreamSynchronize(c->st));
+        c->stats.t_upload_ms += now_ms() - t0; t0 = now_ms();
+        LQ_TRY(lq_sketch_run(&c->treads, c->opt.w, c->opt.k, c->opt.is_hpc, rid_base, &ix->rec, c->ws, c->st)); /* rid restarts at 0 in every part (index.c:287) */
+    }
     LQ_CUDA_OK(cudaStreamSynchronize(c->st));
     c->stats.t_sketch_ms += now_ms() - t0; t0 = now_ms();
     LQ_TRY(lq_index_alloc(ix, c->opt.k, c->st));

@@ -25,6 +25,9 @@ struct LqMinimizers {
 
 int lq_reads_upload(LqReadsDev *d, const uint8_t *h_seq, const uint64_t *h_off, uint32_t n_reads, int seq_on_device, int sdust_tbl, cudaStream_t st);
 int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_base, LqMinimizers *out, LqDevBuf &ws, cudaStream_t st);
+/* host buffers only: copy, pack and sketch in overlapped chunks; returns 1 when not applicable (use lq_reads_upload + lq_sketch_run) */
+int lq_upload_sketch_pipelined(LqReadsDev *d, const uint8_t *h_seq, const uint64_t *h_off, uint32_t n_reads, int w, int k, int is_hpc, uint32_t rid_base,
+                               LqMinimizers *out, LqDevBuf &ws, cudaStream_t st);
 int lq_read_first(const LqMinimizers *m, uint32_t rid_base, uint32_t n_reads, LqDevBuf &first, cudaStream_t st);
 
 #endif

@@ -32,10 +32,11 @@
 __global__ void lq_pack_k(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ seq_off, const uint64_t *__restrict__ slot0,
                           const uint32_t *__restrict__ len, uint32_t n_reads, uint64_t n_slots, int sdust_tbl,
                           uint32_t *__restrict__ b2, uint32_t *__restrict__ nm, uint32_t *__restrict__ slot_read,
-                          const uint8_t *seq_lo, const uint8_t *seq_hi /* the bases of all reads lie in [seq_lo, seq_hi) */)
+                          const uint8_t *seq_lo, const uint8_t *seq_hi /* the bases of all reads lie in [seq_lo, seq_hi) */,
+                          uint64_t slot_begin /* this launch packs slots [slot_begin, n_slots) */)
 {
     /* one thread per 32 bases: two 2-bit words and one ambiguity word */
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + slot_begin * 4;
     const uint64_t slot = t >> 2;
     if (slot >= n_slots) return;
     /* owner read of the slot: last r with slot0[r] <= slot */
@@ -109,6 +110,9 @@ struct SkArgs {
     uint64_t cap;                /* capacity of out_key / out_y in records */
     uint32_t *err;               /* bit 0: look-back timed out */
     uint32_t *out_key; uint64_t *out_y;
+    /* chunked launches (lq_upload_sketch_pipelined): this launch covers the packed bases from g_begin to slot n_slots; its records
+     * follow the *base_in of the launches before it, and its last tile leaves the running total in *base_out */
+    uint64_t g_begin; const unsigned long long *base_in; unsigned long long *base_out;
 };
 
 /* candidate of smem position p (hash of min(fw,rv), strand) */
@@ -469,7 +473,7 @@ __global__ void __launch_bounds__(RK_THREADS) lq_sketch_roll_k(SkArgs a)
     if (tid == 0) { s_tile = atomicAdd(a.ticket, 1u); s_over = 0; }
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint64_t g = ((uint64_t)tile * RK_THREADS + tid) * RK_SEG;   /* global base index of the segment */
+    const uint64_t g = a.g_begin + ((uint64_t)tile * RK_THREADS + tid) * RK_SEG;   /* global base index of the segment */
     const uint64_t slot = g >> 7;
     uint32_t rd = 0; uint64_t g0 = 0; int L = 0, i0 = 0, i1 = 0;
     if (slot < a.n_slots) {
@@ -510,7 +514,11 @@ __global__ void __launch_bounds__(RK_THREADS) lq_sketch_roll_k(SkArgs a)
             }
             if (tid == 0) atomicExch(&a.state[tile], FLAG_PRE | (base + tot));
         }
-        if (tid == 0) s_base = base;
+        if (tid == 0) {
+            const uint64_t cb = a.base_in ? *a.base_in : 0;                  /* records of the launches before this one */
+            s_base = cb + base;
+            if (a.base_out && tile == gridDim.x - 1) *a.base_out = cb + base + tot;
+        }
     }
     __syncthreads();
     const uint64_t at = s_base + ex;
@@ -724,9 +732,115 @@ int lq_reads_upload(LqReadsDev *d, const uint8_t *h_seq, const uint64_t *h_off, 
         LqProfScope ps("pack", st, 1, d->n_bases + slots * (LQ_SLOT_W2 + LQ_SLOT_WN + 1) * 4);
         lq_pack_k<<<lq_grid(slots * 4, 256), 256, 0, st>>>(d_seq, d->off.as<uint64_t>(), d->slot0.as<uint64_t>(), d->len.as<uint32_t>(),
                                                            n_reads, slots, sdust_tbl, d->b2.as<uint32_t>(), d->nm.as<uint32_t>(), d->slot_read.as<uint32_t>(),
-                                                           d_seq + h_off[0], d_seq + h_off[n_reads]);
+                                                           d_seq + h_off[0], d_seq + h_off[n_reads], 0);
         LQ_CUDA_OK(cudaGetLastError());
     }
+    return 0;
+}
+
+int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_base, LqMinimizers *out, LqDevBuf &ws, cudaStream_t st);
+
+/* ------------------------------------------------------------------ upload + pack + sketch, pipelined (host buffers)
+ *
+ * A part's bases come over PCIe (~15 ms for 0.8 GB) while nothing else runs.  Here the reads are cut into chunks of ~48 MB: chunk c+1
+ * is copied on a second stream while chunk c is packed and sketched (rolling kernel, launched over the chunk's slots; its records
+ * follow the running total the previous launch left in device memory, so the output is the same contiguous, ordered array).
+ * Returns 1 (nothing done) where the rolling kernel does not apply or the input is small: the caller takes the plain sequence. */
+static int g_pipeline = getenv("LQCOV_NO_PIPELINE") ? 0 : 1;
+#define PL_CHUNK (48ull << 20)
+
+int lq_upload_sketch_pipelined(LqReadsDev *d, const uint8_t *h_seq, const uint64_t *h_off, uint32_t n_reads, int w, int k, int is_hpc, uint32_t rid_base,
+                               LqMinimizers *out, LqDevBuf &ws, cudaStream_t st)
+{
+    const bool roll = !is_hpc && (w == 5 || w == 10) && k <= 15 && !g_sketch_tiled && !g_sketch_lanes;
+    if (!g_pipeline || !roll || n_reads == 0 || h_off[n_reads] - h_off[0] < 2 * PL_CHUNK) return 1;
+    static cudaStream_t st_copy = 0;
+    if (!st_copy) LQ_CUDA_OK(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
+    /* layout, as lq_reads_upload() */
+    d->n_reads = n_reads; d->n_bases = h_off[n_reads] - h_off[0];
+    d->h_len.resize(n_reads); d->h_slot0.resize((size_t)n_reads + 1);
+    uint64_t slots = 0;
+    for (uint32_t r = 0; r < n_reads; ++r) {
+        const uint64_t L = h_off[r + 1] - h_off[r];
+        if (L > 0x7fffffffULL) { fprintf(stderr, "[lqcov] read %u longer than 2^31\n", r); return -1; }
+        d->h_len[r] = (uint32_t)L; d->h_slot0[r] = slots;
+        slots += (L + LQ_SLOT - 1) / LQ_SLOT;
+    }
+    d->h_slot0[n_reads] = slots; d->n_slots = slots;
+    LQ_TRY(d->len.ensure((size_t)(n_reads + 1) * 4)); LQ_TRY(d->slot0.ensure((size_t)(n_reads + 1) * 8)); LQ_TRY(d->off.ensure((size_t)(n_reads + 1) * 8));
+    LQ_TRY(d->b2.ensure((size_t)(slots * LQ_SLOT_W2 + 16) * 4)); LQ_TRY(d->nm.ensure((size_t)(slots * LQ_SLOT_WN + 16) * 4));
+    LQ_TRY(d->slot_read.ensure((size_t)(slots + 1) * 4)); LQ_TRY(d->ascii.ensure((size_t)d->n_bases + 16));
+    LQ_CUDA_OK(cudaMemcpyAsync(d->len.p, d->h_len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
+    LQ_CUDA_OK(cudaMemcpyAsync(d->slot0.p, d->h_slot0.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    LQ_CUDA_OK(cudaMemcpyAsync(d->off.p, h_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    LQ_CUDA_OK(cudaMemsetAsync(d->b2.as<uint32_t>() + slots * LQ_SLOT_W2, 0, 16 * 4, st));
+    LQ_CUDA_OK(cudaMemsetAsync(d->nm.as<uint32_t>() + slots * LQ_SLOT_WN, 0xff, 16 * 4, st));
+    lq_prof_h2d((uint64_t)(n_reads + 1) * 20 + d->n_bases);
+    const uint8_t *d_seq = d->ascii.as<uint8_t>() - h_off[0];
+    /* chunks = read ranges of >= PL_CHUNK bases */
+    std::vector<uint32_t> cut; cut.push_back(0);
+    for (uint32_t r = 0; r < n_reads; ) {
+        uint64_t sz = 0;
+        while (r < n_reads && sz < PL_CHUNK) { sz += d->h_len[r]; ++r; }
+        cut.push_back(r);
+    }
+    const size_t nc = cut.size() - 1;
+    /* output + per-chunk look-back state + running totals */
+    out->n = 0; out->has_span = 0;
+    const uint64_t cap = (uint64_t)((double)d->n_bases * 2.6 / (w + 1)) + 4096;
+    LQ_TRY(out->key.ensure((size_t)(cap + 1) * 4)); LQ_TRY(out->y.ensure((size_t)(cap + 1) * 8));
+    std::vector<size_t> soff(nc + 1, 0);
+    for (size_t c = 0; c < nc; ++c) {
+        const uint64_t ns = d->h_slot0[cut[c + 1]] - d->h_slot0[cut[c]];
+        soff[c + 1] = soff[c] + (size_t)((ns * LQ_SLOT + RK_TILE - 1) / RK_TILE) + 2;       /* tiles + {ticket, err} */
+    }
+    LQ_TRY(out->blk.ensure((soff[nc] + nc + 4) * 8 + 64));
+    unsigned long long *state = out->blk.as<unsigned long long>(), *totals = state + soff[nc];
+    LQ_CUDA_OK(cudaMemsetAsync(state, 0, (soff[nc] + nc + 4) * 8, st));
+    std::vector<cudaEvent_t> ev(nc);
+    cudaEvent_t ev0;                                       /* the copies must not start before this call's place in the stream */
+    LQ_CUDA_OK(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
+    LQ_CUDA_OK(cudaEventRecord(ev0, st));
+    LQ_CUDA_OK(cudaStreamWaitEvent(st_copy, ev0, 0));
+    for (size_t c = 0; c < nc; ++c) {
+        LQ_CUDA_OK(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));
+        const uint64_t b0 = h_off[cut[c]], b1 = h_off[cut[c + 1]];
+        LQ_CUDA_OK(cudaMemcpyAsync(d->ascii.as<uint8_t>() + (b0 - h_off[0]), h_seq + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st_copy));
+        LQ_CUDA_OK(cudaEventRecord(ev[c], st_copy));
+    }
+    SkArgs a;
+    a.b2 = d->b2.as<uint32_t>(); a.nm = d->nm.as<uint32_t>(); a.slot_read = d->slot_read.as<uint32_t>(); a.len = d->len.as<uint32_t>();
+    a.slot0 = d->slot0.as<uint64_t>(); a.w = w; a.k = k; a.rid_base = rid_base; a.cap = cap;
+    a.out_key = out->key.as<uint32_t>(); a.out_y = out->y.as<uint64_t>();
+    for (size_t c = 0; c < nc; ++c) {
+        const uint64_t s0 = d->h_slot0[cut[c]], s1 = d->h_slot0[cut[c + 1]], bases = h_off[cut[c + 1]] - h_off[cut[c]];
+        LQ_CUDA_OK(cudaStreamWaitEvent(st, ev[c], 0));
+        if (s1 == s0) { LQ_CUDA_OK(cudaMemcpyAsync(totals + c + 1, totals + c, 8, cudaMemcpyDeviceToDevice, st)); continue; }
+        { LqProfScope ps("pack", st, 1, bases + (s1 - s0) * (LQ_SLOT_W2 + LQ_SLOT_WN + 1) * 4);
+          lq_pack_k<<<lq_grid((s1 - s0) * 4, 256), 256, 0, st>>>(d_seq, d->off.as<uint64_t>(), d->slot0.as<uint64_t>(), d->len.as<uint32_t>(), n_reads, s1, 0,
+                                                               d->b2.as<uint32_t>(), d->nm.as<uint32_t>(), d->slot_read.as<uint32_t>(), d_seq + h_off[0], d_seq + h_off[n_reads], s0); }
+        const unsigned nblk = (unsigned)(((s1 - s0) * LQ_SLOT + RK_TILE - 1) / RK_TILE);
+        a.n_slots = s1; a.g_begin = s0 * LQ_SLOT;
+        a.state = state + soff[c]; a.ticket = (uint32_t*)(a.state + nblk); a.err = a.ticket + 1;
+        a.base_in = totals + c; a.base_out = totals + c + 1;
+        { LqProfScope ps("sketch", st, 1, (s1 - s0) * (LQ_SLOT_W2 + LQ_SLOT_WN) * 4 + (uint64_t)((double)bases * 2.0 / (w + 1)) * 12);
+          if (w == 5) lq_sketch_roll_k<5><<<nblk, RK_THREADS, 0, st>>>(a); else lq_sketch_roll_k<10><<<nblk, RK_THREADS, 0, st>>>(a); }
+        LQ_CUDA_OK(cudaGetLastError());
+    }
+    unsigned long long total = 0;
+    std::vector<unsigned long long> h_state(soff[nc]);
+    LQ_CUDA_OK(cudaMemcpyAsync(&total, totals + nc, 8, cudaMemcpyDeviceToHost, st));
+    LQ_CUDA_OK(cudaMemcpyAsync(h_state.data(), state, soff[nc] * 8, cudaMemcpyDeviceToHost, st)); lq_prof_d2h(8 + soff[nc] * 8);
+    LQ_CUDA_OK(cudaStreamSynchronize(st));
+    for (size_t c = 0; c < nc; ++c) cudaEventDestroy(ev[c]);
+    cudaEventDestroy(ev0);
+    for (size_t c = 0; c < nc; ++c) {                      /* the err word of every chunk */
+        const uint64_t ns = d->h_slot0[cut[c + 1]] - d->h_slot0[cut[c]];
+        const size_t nblk = (size_t)((ns * LQ_SLOT + RK_TILE - 1) / RK_TILE);
+        if (((const uint32_t*)(h_state.data() + soff[c] + nblk))[1]) { fprintf(stderr, "[lqcov] sketch: look-back timed out\n"); return -1; }
+    }
+    if (total > cap) return lq_sketch_run(d, w, k, is_hpc, rid_base, out, ws, st);   /* low-complexity input: the bases are packed, sketch again with room */
+    out->n = total;
     return 0;
 }
 
@@ -739,7 +853,7 @@ int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_b
     SkArgs a;
     a.b2 = rd->b2.as<uint32_t>(); a.nm = rd->nm.as<uint32_t>(); a.slot_read = rd->slot_read.as<uint32_t>(); a.len = rd->len.as<uint32_t>();
     a.slot0 = rd->slot0.as<uint64_t>(); a.n_slots = rd->n_slots; a.w = w; a.k = k; a.rid_base = rid_base;
-    a.ticket = 0; a.state = 0; a.cap = 0; a.err = 0; a.out_key = 0; a.out_y = 0;
+    a.ticket = 0; a.state = 0; a.cap = 0; a.err = 0; a.out_key = 0; a.out_y = 0; a.g_begin = 0; a.base_in = 0; a.base_out = 0;
     uint64_t total = 0;
     if (!is_hpc) {
         const bool roll = (w == 5 || w == 10) && k <= 15 && !g_sketch_tiled;
