@@ -1,0 +1,53 @@
+"""BASELINE.json configs[0] (the reference's own CPU-runnable case) and the consumer of the table.
+
+CPU tier: the oracle port reproduces the reference's C1 tables (committed goldens made by oracle/make_consumer_golden.py); where
+/root/reference exists the UNMODIFIED lq_coverage.LqCoverage is run on them (tests/consumer_harness.py) and its fields must be
+the committed ones -- "bit-identical lq_coverage.py output" follows from a byte-identical table, this pins the numbers it means.
+GPU tier: the CUDA path reproduces the same tables."""
+import json
+import os
+
+import pytest
+
+import c1_cases
+import consumer_harness
+import liblq
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+
+
+def _golden(name):
+    return open(os.path.join(GOLD, name + ".tsv"), "rb").read()
+
+
+@pytest.mark.parametrize("name", c1_cases.NAMES)
+def test_oracle_reproduces_c1(name):
+    T, Q = c1_cases.make(name)
+    _, oopt = liblq.opt_pair(**c1_cases.OPTS)
+    got, mid_occ, parts = liblq.oracle_table(T, Q, oopt)
+    assert parts == 1
+    assert got == _golden(name)
+
+
+@pytest.mark.skipif(not consumer_harness.available(), reason="needs /root/reference (lq_coverage.py)")
+@pytest.mark.parametrize("name", c1_cases.NAMES)
+def test_consumer_fields(name):
+    want = json.load(open(os.path.join(GOLD, "consumer_c1.json")))[name]
+    got = consumer_harness.consumer_fields(os.path.join(GOLD, name + ".tsv"))
+    for k in ("unmapped_frac_trimmed", "unmapped_frac_untrimmed", "unmapped_frac_med", "high_div_frac", "low_coverage"):
+        assert got[k] == want[k], k                       # deterministic functions of the table
+    for k in ("mean", "sd"):                              # seeded GMM: same library, same seed
+        assert got[k] == pytest.approx(want[k], rel=1e-6), k
+    # the non-sense-read flag of north_star == column 4 is '0'
+    rows = [ln.split(b"\t") for ln in _golden(name).splitlines()]
+    assert got["unmapped_frac_med"] == pytest.approx(sum(1 for r in rows if r[4] == b"0") / len(rows))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", c1_cases.NAMES)
+def test_gpu_reproduces_c1(name):
+    import longqc_b200 as L
+    T, Q = c1_cases.make(name)
+    opt, _ = liblq.opt_pair(**c1_cases.OPTS)
+    assert L.coverage_table(T, Q, opt) == _golden(name)
