@@ -47,3 +47,35 @@ def test_q2p_table_and_meanq():
         n = int(rng.integers(1, 5000))
         qs = (rng.integers(0, 60, n).astype(np.uint8) + 33).tobytes()
         assert r.meanQ(qs, n) == liblq.oracle().lqo_meanQ(qs, n)
+
+
+def _ref_table(T, Q, flags):
+    import os
+    import subprocess
+    import tempfile
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "minimap2-coverage")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/minimap2-coverage not built")
+    with tempfile.TemporaryDirectory() as d:
+        tf, qf = os.path.join(d, "t.fq"), os.path.join(d, "q.fq")
+        T.write_fastx(tf)
+        Q.write_fastx(qf)
+        return subprocess.run([exe] + flags.split() + [tf, qf], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+
+
+def test_table_ultralong_reads():
+    """BASELINE configs[3] flavour (ONT ultra-long 50 kb reads, -x ont-rapid => -p 160): long chains, many anchors per target"""
+    from longqc_b200 import synth
+    T, Q = synth.standard_set(60, 50000, 0.15, seed=31, n_query=12)
+    want = _ref_table(T, Q, "-Y -l 0 -q 160 -k 12 -w 5 -I 4G -p 160 -t 4")
+    got, _, parts = liblq.oracle_table(T, Q, liblq.oracle_opt(min_score_med=160, min_score_good=160))
+    assert parts == 1 and got == want and got.count(b"\n") == 12
+
+
+def test_table_many_parts_with_covt_gate():
+    """a deep, tiny genome cut into many index parts: the COVT gate (esterr.c:87-91) closes for later parts"""
+    from longqc_b200 import synth
+    T, Q = synth.standard_set(600, 3000, 0.10, seed=32, coverage=300.0, n_query=25)   # ~300x of a 6 kb genome
+    want = _ref_table(T, Q, "-Y -l 0 -q 160 -k 12 -w 5 -I 150K -p 80 -t 2")
+    got, _, parts = liblq.oracle_table(T, Q, liblq.oracle_opt(min_score_med=80, min_score_good=160, batch_size=150000))
+    assert parts >= 6 and got == want
