@@ -49,9 +49,12 @@ def parse():
     return ap.parse_args()
 
 
-def workload_name(a):
-    return "%dk synthetic ONT %d kb reads (%.0f%% error), -x ont-ligation (%s), %d sampled queries" % (
+def workload_name(a, world=1):
+    s = "%dk synthetic ONT %d kb reads (%.0f%% error), -x ont-ligation (%s), %d sampled queries" % (
         a.reads // 1000, a.read_len // 1000, a.err * 100, FLAGS, a.queries)
+    if world > 1:   # weak scaling: every rank brings its own reads of one shared genome, the queries are split
+        s += "; x%d GPUs = %dk target reads in one replicated index, %d queries per GPU" % (world, a.reads * world // 1000, a.queries // world)
+    return s
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -310,7 +313,7 @@ def run_ours(a):
     line = {"metric": "read Gbases/s through minimap2-coverage (target bases indexed + query bases mapped per second)",
             "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "target_bases": int(runner.target_bases_all), "query_bases": int(runner.query_bases_all),
+            "config": {"workload": workload_name(a, world), "target_bases": int(runner.target_bases_all), "query_bases": int(runner.query_bases_all),
                        "parallelism": runner.parallelism(), "l2": "inputs (>= %.1f GB per rank) larger than the 126 MB L2" % (targets.n_bases / 1e9),
                        "host_wall_ms_per_step": 1e3 * wall / a.steps},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(prof["launches"] // a.steps),
