@@ -334,7 +334,7 @@ def run_ours(a):
     roof = None
     if top:
         ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9 if top["ms"] > 0 else 0.0
-        traffic, traffic_src = load_traffic(top["name"])
+        traffic, traffic_src = load_traffic(top["name"]) if world == 1 else (None, None)   # the committed capture is of the 1-GPU job
         roof = {"kernel": top["name"], "bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes": top["bytes"] / max(1, a.steps), "ms_per_launch_group": top["ms"] / max(1, a.steps),
