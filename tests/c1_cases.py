@@ -4,6 +4,9 @@ import numpy as np
 
 FLAGS = "-Y -l 0 -q 160 -k 12 -w 5 -I 4G -p 80 -t 4"
 NAMES = ("c1_sampleqc", "c1_junk")
+# more than 131 072 target reads in one index part: the rid>>16 digit of the seed key takes three values, so the s48 level of the exact
+# seed sort is a walk over few, large regions (the regime of the multi-GPU runs, where the replicated index holds N x 100 000 reads)
+EXTRA = ("many_targets",)
 OPTS = dict(min_score_med=80, min_score_good=160)
 
 
@@ -21,4 +24,10 @@ def make(name):
         adp = synth.with_adapters(synth.simulate_reads(g, 100, L, 0.13, rng), cases.ADP, cases.ADP, rng)
         T = synth.ReadSet.concat([good, junk, adp]).shuffled(rng).renamed()
         return T, T
+    if name == "many_targets":
+        rng = np.random.default_rng(77)
+        n, L = 140000, 1500
+        g = synth.add_tandem_repeats(synth.make_genome(n * L // 25, rng), rng, 300, unit_len=(2, 40), copies=(10, 150))
+        T = synth.simulate_reads(g, n, L, 0.08, rng)
+        return T, T.subset(np.sort(rng.choice(n, 60, replace=False)))
     raise KeyError(name)

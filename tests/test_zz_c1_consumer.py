@@ -44,6 +44,23 @@ def test_consumer_fields(name):
     assert got["unmapped_frac_med"] == pytest.approx(sum(1 for r in rows if r[4] == b"0") / len(rows))
 
 
+def test_oracle_reproduces_many_targets():
+    """> 131 072 target reads in one part (three values of rid>>16): the oracle's sort restatement against the reference table"""
+    T, Q = c1_cases.make("many_targets")
+    _, oopt = liblq.opt_pair(**c1_cases.OPTS)
+    got, _, parts = liblq.oracle_table(T, Q, oopt)
+    assert parts == 1 and got == _golden("many_targets")
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_many_targets():
+    """the few-region walk of the s48 sort level (tied queries with > 2048 seeds per strand against 140 000 targets)"""
+    import longqc_b200 as L
+    T, Q = c1_cases.make("many_targets")
+    opt, _ = liblq.opt_pair(**c1_cases.OPTS)
+    assert L.coverage_table(T, Q, opt) == _golden("many_targets")
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", c1_cases.NAMES)
 def test_gpu_reproduces_c1(name):
