@@ -25,6 +25,7 @@ typedef struct { size_t n, m; uint64_t *a; } offs_t;
 struct lqcov_reader {
     gzFile fp;
     unsigned char *buf; int beg, end, eof;
+    uint64_t total; int zero_read;   /* bytes delivered so far; kseq's 16 KB reader has already seen a zero-length read */
     int last_char;       /* header character already consumed (kseq.h last_char) */
     int failed;          /* a truncated/mismatched FASTQ record ends the stream, like kseq_read() < 0 */
     blob_t seq, qual, names;
@@ -42,6 +43,7 @@ static inline int rd_fill(lqcov_reader *r)
     r->beg = 0; r->end = gzread(r->fp, r->buf, RD_BUF);
     if (r->end < RD_BUF) r->eof = 1;
     if (r->end <= 0) { r->end = 0; return 0; }
+    r->total += (uint64_t)r->end;
     return 1;
 }
 static inline int rd_getc(lqcov_reader *r)
@@ -55,7 +57,13 @@ static int rd_line(lqcov_reader *r, blob_t *b, size_t line_start)
     int got = 0;
     for (;;) {
         unsigned char *p, *q;
-        if (r->beg >= r->end && !rd_fill(r)) break;
+        if (r->beg >= r->end && !rd_fill(r)) {
+            /* kseq.h:98 returns -1 before the '\r' trim only when its stream already KNOWS it is at end of file: its 16 KB reads have
+             * returned a short count, i.e. the file length is not a multiple of 16384, or a zero-length read has happened before */
+            if (!got && (r->total % 16384u != 0 || r->zero_read)) return -1;
+            r->zero_read = 1;
+            break;
+        }
         got = 1;
         p = r->buf + r->beg;
         q = (unsigned char*)memchr(p, '\n', (size_t)(r->end - r->beg));
@@ -66,7 +74,7 @@ static int rd_line(lqcov_reader *r, blob_t *b, size_t line_start)
         }
         if (q) break;
     }
-    /* ks_getuntil2 drops one trailing '\r' when the (accumulated) string is longer than one character */
+    /* ks_getuntil2 drops one trailing '\r' when the (accumulated) string is longer than one character (kseq.h:138) */
     if (b && b->n - line_start > 1 && b->a[b->n - 1] == '\r') --b->n;
     return got ? 0 : -1;
 }

@@ -88,7 +88,7 @@ extern "C" int lqcov_sdust_table(const lqcov_opt_t *o, const lqcov_reads_t *read
         LQ_TRY(d_off.ensure(((size_t)n + 1) * 8)); LQ_CUDA_OK(cudaMemcpy(d_off.p, rel.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice));
         const int capP = LQ_SD_PCAP(W);
         const unsigned threads = 64;
-        unsigned blocks = (n + threads - 1) / threads; if (blocks > 148 * 8) blocks = 148 * 8;
+        unsigned blocks = (n + threads - 1) / threads; if (blocks > 148 * 4) blocks = 148 * 4;   /* 64 threads x 61 KB of interval scratch each: 2.3 GB at most */
         LQ_TRY(d_p.ensure((size_t)blocks * threads * 4 * capP * sizeof(int)));
         LQ_TRY(d_out.ensure((size_t)n * sizeof(SdOut))); LQ_TRY(d_cur.ensure(64));
         LQ_CUDA_OK(cudaMemset(d_cur.p, 0, 64));

@@ -11,9 +11,13 @@
 #include "lq_common.h"
 #include "lq_sketch_core.h" /* lq_nt4 */
 
-/* perfect intervals alive in one window: observed < W*W/2 on adversarial low-complexity input; the caller
- * provides the storage (4 ints per entry) so that device threads can keep it in a global scratch slice */
-#define LQ_SD_PCAP(W) ((W) * (W) / 2 + 2 * (W))
+/* Perfect intervals alive at one time: at most (W-2)^2.  Proof: an entry is inserted by find_perfect with start' = ii + start,
+ * 0 <= ii <= W-3 (one entry per ii and call), and lives while start' >= the current `start`.  `start` is frozen for the first W-2 calls
+ * after a reset of l (sdust.c:149-151: l <= W) and then grows by one per call, so a call made d starts ago still owns at most W-2-d
+ * entries: the total peaks at (W-2)^2 when the frozen stretch ends.  The bound is reached in practice only after an N, when the
+ * deque keeps its stale words (sdust.c:158-162): 'A'*200 + 'N' + 'A'*200 needs 3596 of the 3844 entries at W = 64.
+ * The caller provides the storage (4 ints per entry) so that device threads can keep it in a global scratch slice. */
+#define LQ_SD_PCAP(W) (((W) - 2) * ((W) - 2) + 2)
 
 struct lq_sd_state {
     int win[64], w_front, w_n;

@@ -267,6 +267,23 @@ def reads_from_seqs(seqs, prefix=b"s", qual=False, rng=None):
     return ReadSet(seq, off, q, [prefix + str(i).encode() for i in range(len(seqs))])
 
 
+def sdust_stale_seqs(rng=None):
+    """low-complexity repeats interrupted by a non-ACGT base: sdust keeps its deque and counts across the N (sdust.c:158-162), so
+    find_perfect inserts up to W-2 stale intervals per base for ~W bases -- the worst case of the perfect-interval list"""
+    out = [b"A" * 200 + b"N" + b"A" * 200, b"AC" * 50 + b"N" + b"AC" * 50, b"ACG" * 40 + b"NN" + b"ACG" * 40 + b"N" + b"T" * 90,
+           b"T" * 70 + b"N" + b"T" * 3 + b"N" + b"T" * 64 + b"X" + b"AT" * 100, b"G" * 63 + b"N" + b"G" * 63 + b"N" + b"G" * 63,
+           b"A" * 64 + b"N" + b"C" * 64 + b"N" + b"AAC" * 30 + b"n" + b"AAC" * 30]
+    if rng is not None:
+        acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+        for _ in range(40):
+            parts = []
+            for _ in range(int(rng.integers(2, 6))):
+                u = acgt[rng.integers(0, 4, int(rng.integers(1, 4)))]
+                parts.append(np.tile(u, int(rng.integers(20, 120)))[: int(rng.integers(30, 260))].tobytes())
+            out.append(b"N".join(parts))
+    return out
+
+
 def oracle_sdust_table(rs, W=64, T=20):
     import tempfile
     lib = oracle()

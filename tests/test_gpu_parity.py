@@ -174,3 +174,5 @@ def test_sdust_table():
     assert got == want
     rs2 = liblq.reads_from_seqs(seqs[:50])
     assert L.sdust_table(rs2) == liblq.oracle_sdust_table(rs2)
+    rs3 = liblq.reads_from_seqs(liblq.sdust_stale_seqs(rng), qual=True, rng=rng)   # repeats interrupted by N: the interval list at its bound
+    assert L.sdust_table(rs3) == liblq.oracle_sdust_table(rs3)

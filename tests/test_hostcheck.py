@@ -135,7 +135,7 @@ def test_sdust_core():
     hc.lqhc_sdust_masked.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
     hc.lqhc_sdust_masked.restype = C.c_long
     rng = np.random.default_rng(21)
-    seqs = liblq.adversarial_seqs(rng, 210, 3000)
+    seqs = liblq.adversarial_seqs(rng, 210, 3000) + liblq.sdust_stale_seqs(rng)   # the latter fill the interval list to ~(W-2)^2
     rs = liblq.reads_from_seqs(seqs)
     want = [int(ln.split(b"\t")[1]) for ln in liblq.oracle_sdust_table(rs).strip().split(b"\n")]
     got = [hc.lqhc_sdust_masked(s, len(s), 20, 64) for s in seqs]

@@ -79,3 +79,17 @@ def test_table_many_parts_with_covt_gate():
     want = _ref_table(T, Q, "-Y -l 0 -q 160 -k 12 -w 5 -I 150K -p 80 -t 2")
     got, _, parts = liblq.oracle_table(T, Q, liblq.oracle_opt(min_score_med=80, min_score_good=160, batch_size=150000))
     assert parts >= 6 and got == want
+
+
+def test_sdust_stale_window_against_reference_binary(tmp_path):
+    """repeats interrupted by N (the interval list near (W-2)^2 entries): oracle table == `sdust` of the unmodified reference"""
+    import os
+    import subprocess
+    if not os.path.exists(liblq.REF_SDUST):
+        pytest.skip("oracle/_ref/sdust not built")
+    rng = np.random.default_rng(77)
+    rs = liblq.reads_from_seqs(liblq.sdust_stale_seqs(rng), qual=True, rng=rng)
+    fq = str(tmp_path / "s.fq")
+    rs.write_fastx(fq)
+    want = subprocess.run([liblq.REF_SDUST, fq], capture_output=True, check=True).stdout
+    assert liblq.oracle_sdust_table(rs) == want
