@@ -34,6 +34,10 @@ def main():
             os.unlink(f)
         os.rmdir(d)
     json.dump(out, open(os.path.join(ROOT, "tests", "golden", "consumer_c1.json"), "w"), indent=1, sort_keys=True)
+    # the reduced configs[4] case (tests/cases.py "c5_small": its table golden is made by make_golden.py)
+    c5 = consumer_harness.consumer_fields(os.path.join(ROOT, "tests", "golden", "c5_small.tsv"))
+    json.dump({"c5_small": c5}, open(os.path.join(ROOT, "tests", "golden", "consumer_c5.json"), "w"), indent=1, sort_keys=True)
+    print("c5_small", {k: v for k, v in c5.items() if not k.startswith("hist_")})
 
 
 if __name__ == "__main__":

@@ -17,6 +17,12 @@ CASES = {
     "spike_hpc_filter": (("spike", 108, 200, 5000), dict(is_hpc=1, k=15, w=10, min_coverage=1, filter=1), "-Y -Hk15 -w 10 -c 1 -l 0 --filter"),
     "ambiguous_fasta": (("nfasta", 109, 250, 5000, 30), dict(min_score_med=80, min_score_good=160), "-Y -l 0 -q 160 -k 12 -w 5 -p 80"),
     "junk_adapters": (("junk", 110, 250, 5000, 40), dict(min_score_med=80, min_score_good=160), "-Y -l 0 -q 160 -k 12 -w 5 -p 80"),
+    # ~300x of a 6 kb genome cut into >= 6 index parts: the COVT gate (esterr.c:87-91, lambda/len > 150) closes for the later parts
+    "covt_gate": (("deep", 600, 3000, 0.10, 32, 300.0, 25), dict(min_score_med=80, min_score_good=160, batch_size=150000), "-Y -l 0 -q 160 -k 12 -w 5 -I 150K -p 80"),
+    # BASELINE configs[3] flavour: ONT ultra-long 50 kb reads, -x ont-rapid (-p 160): long chains, thousands of anchors per target
+    "ultralong": (("std", 60, 50000, 0.15, 31, 12), dict(min_score_med=160, min_score_good=160), "-Y -l 0 -q 160 -k 12 -w 5 -I 4G -p 160"),
+    # BASELINE configs[4] reduced: mixed-GC genome, 10 % iid junk + 10 % adapter/low-complexity reads, several index parts, -x pb-sequel
+    "c5_small": (("junk", 111, 1500, 6000, 400), dict(min_score_med=80, min_score_good=160, batch_size=2000000), "-Y -l 0 -q 160 -k 12 -w 5 -I 2M -p 80"),
 }
 
 ADP = b"ATCTCTCTCAACAACAACAACGGAGGAGGAGGAAAAGAGAGAGAT"  # longQC.py:184 (pb-sequel preset)
@@ -30,6 +36,9 @@ def make_case(name):
     if kind == "std":
         _, n, L, err, seed, nq = spec
         return synth.standard_set(n, L, err, seed=seed, n_query=nq)
+    if kind == "deep":
+        _, n, L, err, seed, cov, nq = spec
+        return synth.standard_set(n, L, err, seed=seed, coverage=cov, n_query=nq)
     if kind == "tandem":
         _, seed, n, L, nq = spec
         rng = np.random.default_rng(seed)

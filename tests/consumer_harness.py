@@ -18,7 +18,7 @@ def available():
 
 
 def _stub_matplotlib():
-    if "matplotlib" in sys.modules and not getattr(sys.modules["matplotlib"], "_lq_stub", False):
+    if "matplotlib" in sys.modules:   # the real one, or our stub from an earlier call (lq_coverage keeps its reference to it)
         return
     mpl = types.ModuleType("matplotlib")
     mpl._lq_stub = True
@@ -27,6 +27,7 @@ def _stub_matplotlib():
 
     def hist(x, bins=10, density=False, **k):
         h, e = np.histogram(x, bins=bins, density=density)
+        plt._lq_last_hist = (np.asarray(h), np.asarray(e))   # lq_coverage.py:234-241: the coverage histogram behind is_low_coverage()
         return h, e, None
     plt.hist = hist
     for name in ("close", "figure", "grid", "axvline", "axhline", "xlabel", "ylabel", "legend", "savefig", "plot", "xlim", "ylim",
@@ -58,6 +59,8 @@ def consumer_fields(table_path, seed=12345):
         "unmapped_frac_untrimmed": float(c.unmapped_frac_untrimmed),  # share of rows with column 2 == 0     (:214)
         "unmapped_frac_med": float(c.unmapped_frac_med),              # non-sense reads: column 4 == '0'     (:216)
         "high_div_frac": float(c.high_div_frac),                      # (:220-224)
-        "mean": float(c.get_mean()), "sd": float(c.get_sd()),
+        "mean": float(c.get_mean()), "sd": float(c.get_sd()), "cov_main": float(c.cov_main),
+        "hist_density": [float(x) for x in sys.modules["matplotlib.pyplot"]._lq_last_hist[0]],
+        "hist_edges": [float(x) for x in sys.modules["matplotlib.pyplot"]._lq_last_hist[1]],
         "low_coverage": bool(c.is_low_coverage()) if c.is_low_coverage() is not None else None,
     }

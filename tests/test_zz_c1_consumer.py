@@ -68,3 +68,37 @@ def test_gpu_reproduces_c1(name):
     T, Q = c1_cases.make(name)
     opt, _ = liblq.opt_pair(**c1_cases.OPTS)
     assert L.coverage_table(T, Q, opt) == _golden(name)
+
+
+# ---- the consumer's deterministic core restated (longqc_b200/consumer.py) against the unmodified class's committed fields ----
+def _consumer_gold():
+    g = json.load(open(os.path.join(GOLD, "consumer_c1.json")))
+    g.update(json.load(open(os.path.join(GOLD, "consumer_c5.json"))))
+    return g
+
+
+def _check_consumer(table, want):
+    from longqc_b200 import consumer
+    got = consumer.zero_fractions(table)
+    for k in ("unmapped_frac_trimmed", "unmapped_frac_untrimmed", "unmapped_frac_med", "high_div_frac"):
+        assert got[k] == want[k], k
+    h, e = consumer.coverage_histogram(table, want["mean"], want["cov_main"])
+    assert [float(x) for x in e] == want["hist_edges"] and [float(x) for x in h] == want["hist_density"]
+
+
+@pytest.mark.parametrize("name", list(c1_cases.NAMES) + ["c5_small"])
+def test_consumer_restatement_matches_lq_coverage(name):
+    """zero-coverage fractions (non-sense reads) and histogram bins of lq_coverage.py:211-241, from the reference's table"""
+    _check_consumer(_golden(name), _consumer_gold()[name])
+
+
+@pytest.mark.gpu
+def test_gpu_c5_small_consumer_fields():
+    """BASELINE configs[4] reduced (mixed GC, junk + adapter reads, 5 index parts): every row identical AND the consumer's
+    unmapped_frac_med / histogram bins computed from OUR table equal what the unmodified lq_coverage.py got from the reference's"""
+    import cases
+    import longqc_b200 as L
+    T, Q = cases.make_case("c5_small")
+    got = L.coverage_table(T, Q, L.Opt(**cases.opts("c5_small")))
+    assert got == _golden("c5_small")
+    _check_consumer(got, _consumer_gold()["c5_small"])
