@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLAGS = "-Y -l 0 -q 160 -k 12 -w 5 -I 4G -p 160"   # longQC.py:171-231 for -x ont-ligation
+METRIC = "read Gbases/s through minimap2-coverage (target bases indexed + query bases mapped per second)"
 
 
 def parse():
@@ -46,6 +47,9 @@ def parse():
     ap.add_argument("--cpu-sample-queries", type=int, default=600)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", action="store_true", help="time the CPU reference on the bounded sample instead of the whole workload")
+    ap.add_argument("--ref-full", action="store_true", help="--impl reference at N > 1: time the whole N-GPU workload (N x 25 s per step)")
+    ap.add_argument("--no-cli", action="store_true", help="skip the drop-in executable's end-to-end run (cli_e2e)")
+    ap.add_argument("--no-sdust", action="store_true", help="skip the sdust line")
     return ap.parse_args()
 
 
@@ -148,28 +152,60 @@ def make_data(a, n_reads, n_query, rank=0):
     return synth.standard_set(n_reads, a.read_len, a.err, seed=a.seed + 1000 * rank, n_query=n_query)
 
 
-def cpu_reference_run(a, targets, queries, threads):
-    """Time the unmodified reference binary (oracle/_ref) -- or the oracle port when it was not built --
-    on (targets, queries).  Returns (Gbases/s, seconds, kind, cores, table bytes)."""
+def global_workload(a, world):
+    """(targets, queries) of the whole job exactly as our arm's ranks generate them (longqc_b200/dist.py rank_inputs), rank-major"""
+    from longqc_b200 import dist as lqdist, synth
+    parts = [lqdist.rank_inputs(a, r, world) for r in range(world)]
+    if world == 1:
+        return parts[0]
+    return synth.ReadSet.concat([p[0] for p in parts]), synth.ReadSet.concat([p[1] for p in parts])
+
+
+class FastqFiles:
+    """the workload as the FASTQ files LongQC hands the binaries, in /dev/shm (written once, outside every timed region)"""
+
+    def __init__(self, targets, queries):
+        self.d = tempfile.mkdtemp(prefix="lqbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        self.tf, self.qf, self.out = os.path.join(self.d, "t.fq"), os.path.join(self.d, "q.fq"), os.path.join(self.d, "out.tsv")
+        targets.write_fastx(self.tf)
+        queries.write_fastx(self.qf)
+        self.n_bases = targets.n_bases + queries.n_bases
+        self.bytes = os.path.getsize(self.tf) + os.path.getsize(self.qf)
+
+    def run(self, cmd, env=None):
+        """wall seconds of one invocation `cmd <targets> <queries> > out`, and the table it printed"""
+        t0 = time.perf_counter()
+        with open(self.out, "wb") as out:
+            subprocess.run(cmd + [self.tf, self.qf], stdout=out, stderr=subprocess.DEVNULL, check=True, env=env)
+        dt = time.perf_counter() - t0
+        return dt, open(self.out, "rb").read()
+
+    def close(self):
+        for f in (self.tf, self.qf, self.out):
+            if os.path.exists(f):
+                os.unlink(f)
+        os.rmdir(self.d)
+
+
+def reference_cmd(threads):
+    """the unmodified reference binary (oracle/_ref) -- or the oracle port when it was not built"""
     ref = os.path.join(ROOT, "oracle", "_ref", "minimap2-coverage")
     port = os.path.join(ROOT, "oracle", "lq_oracle_cli")
-    d = tempfile.mkdtemp(prefix="lqbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-    tf, qf = os.path.join(d, "t.fq"), os.path.join(d, "q.fq")
-    targets.write_fastx(tf)
-    queries.write_fastx(qf)
     if os.path.exists(ref):
-        cmd, kind, cores = [ref] + FLAGS.split() + ["-t", str(threads), tf, qf], "reference", threads
-    else:
-        cmd, kind, cores = [port, "cov"] + FLAGS.split() + [tf, qf], "port", 1
-    t0 = time.perf_counter()
-    with open(os.path.join(d, "out.tsv"), "wb") as out:
-        subprocess.run(cmd, stdout=out, stderr=subprocess.DEVNULL, check=True)
-    dt = time.perf_counter() - t0
-    table = open(os.path.join(d, "out.tsv"), "rb").read()
-    for f in (tf, qf, os.path.join(d, "out.tsv")):
-        os.unlink(f)
-    os.rmdir(d)
-    return (targets.n_bases + queries.n_bases) / dt / 1e9, dt, kind, cores, table
+        return [ref] + FLAGS.split() + ["-t", str(threads)], "reference", threads
+    return [port, "cov"] + FLAGS.split(), "port", 1
+
+
+def cpu_reference_run(a, targets, queries, threads, files=None):
+    """Time the reference CPU implementation on (targets, queries).  Returns (Gbases/s, seconds, kind, cores, table bytes)."""
+    own = files is None
+    if own:
+        files = FastqFiles(targets, queries)
+    cmd, kind, cores = reference_cmd(threads)
+    dt, table = files.run(cmd)
+    if own:
+        files.close()
+    return files.n_bases / dt / 1e9, dt, kind, cores, table
 
 
 def host_threads():
@@ -179,24 +215,40 @@ def host_threads():
 
 # ----------------------------------------------------------------------------------------------- reference arm
 def run_reference_arm(a):
+    """The unmodified reference binary (oracle/_ref/minimap2-coverage, all host threads) as the measured arm.
+    N=1: every timed step is the WHOLE benchmarked workload (same inputs as our arm: same generator, same seed), ~25 s per step;
+    the untimed warm-up steps run on a bounded sample (a CPU process has nothing to warm but the page cache).
+    N>1: our arm's workload is N x as large (one replicated index over all ranks' reads) and would take N x as long per step on the
+    CPU, so each step is a bounded sample of it unless --ref-full is given; `config.sample` says which."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    targets, queries = make_data(a, a.cpu_sample_reads, a.cpu_sample_queries)
     thr = host_threads()
+    full = a.gpus == 1 or a.ref_full
+    st, sq = make_data(a, a.cpu_sample_reads, a.cpu_sample_queries)
     for _ in range(a.warmup):
-        cpu_reference_run(a, targets, queries, thr)
+        cpu_reference_run(a, st, sq, thr)
+    if full:
+        targets, queries = global_workload(a, a.gpus)
+        sample = "the whole workload (%d target reads, %d queries): same inputs as the GPU arm; warm-up steps on %d reads + %d queries" % (
+            targets.n, queries.n, st.n, sq.n)
+    else:
+        targets, queries = st, sq
+        sample = "%d target reads x %d b + %d queries of the same generator (bounded sample of the %d-GPU workload)" % (st.n, a.read_len, sq.n, a.gpus)
     vals, secs, kind, cores = [], [], None, None
+    files = FastqFiles(targets, queries)
     for _ in range(a.steps):
-        v, dt, kind, cores, _ = cpu_reference_run(a, targets, queries, thr)
+        v, dt, kind, cores, _ = cpu_reference_run(a, targets, queries, thr, files)
         vals.append(v)
         secs.append(dt)
-    v = sum(vals) / len(vals)
-    sample = "%d target reads x %d b + %d queries of the same generator (bounded sample of the workload)" % (targets.n, a.read_len, queries.n)
-    line = {"impl": "reference", "metric": "read Gbases/s through minimap2-coverage (target bases indexed + query bases mapped per second)",
+    files.close()
+    v = (targets.n_bases + queries.n_bases) * len(secs) / sum(secs) / 1e9
+    line = {"impl": "reference", "metric": METRIC,
             "value": v, "unit": "Gbases/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic", "config": {"workload": workload_name(a), "sample": sample},
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(a, a.gpus), "target_bases": int(targets.n_bases), "query_bases": int(queries.n_bases),
+                       "sample": sample, "same_workload_as_gpu_arm": bool(full)},
             "cpu_baseline": {"value": v, "unit": "Gbases/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -236,6 +288,33 @@ def profile_json(L):
     buf = C.create_string_buffer(n + 16)
     lib.lqcov_profile_json(buf, n + 16)
     return json.loads(buf.value.decode())
+
+
+def sdust_line(a, L, reads):
+    """the second executable of the path: `sdust` over EVERY read of the input (lq_mask.py:17-23), through the C ABI with host buffers"""
+    import torch
+    t0 = time.perf_counter()
+    tab = L.sdust_table(reads)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    tab = L.sdust_table(reads)
+    dt = time.perf_counter() - t1
+    out = {"value": reads.n_bases / dt / 1e9, "unit": "Gbases/s", "seconds": dt, "first_call_seconds": t1 - t0, "reads": reads.n, "rows": tab.count(b"\n"),
+           "what": "lqcov_sdust_table on all target reads (host buffers in, table out)"}
+    ref = os.path.join(ROOT, "oracle", "_ref", "sdust")
+    if os.path.exists(ref):   # the reference's sdust on a bounded sample (one thread, as lq_mask.py runs it per chunk)
+        n = min(reads.n, 4000)
+        sub = reads.subset(range(n))
+        d = tempfile.mkdtemp(prefix="lqsd_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        fq = os.path.join(d, "s.fq")
+        sub.write_fastx(fq)
+        t2 = time.perf_counter()
+        want = subprocess.run([ref, fq], capture_output=True, check=True).stdout
+        dtc = time.perf_counter() - t2
+        os.unlink(fq); os.rmdir(d)
+        out["cpu_reference"] = {"value": sub.n_bases / dtc / 1e9, "unit": "Gbases/s", "cores": 1, "sample": "%d reads" % n}
+        out["parity"] = "identical on the sample" if L.sdust_table(sub) == want else "DIFFERS"
+    return out
 
 
 def run_ours(a):
@@ -340,26 +419,47 @@ def run_ours(a):
                 "algorithmic_bytes": top["bytes"] / max(1, a.steps), "ms_per_launch_group": top["ms"] / max(1, a.steps),
                 "note": "algorithmic bytes / CUDA-event time on the launching stream; see DESIGN.md for the bytes per unit"}
     sk = [k for k in klist if k["name"] == "sketch"]
-    cpu = None
-    if not a.no_cpu_baseline and world == 1:
-        if a.cpu_sample:
-            ct, cq = make_data(a, a.cpu_sample_reads, a.cpu_sample_queries)
-            what = "%d target reads x %d b + %d queries of the same generator (bounded sample)" % (ct.n, a.read_len, cq.n)
-        else:   # the whole benchmarked workload: ~20-30 s of CPU, and its table is the full-size parity check of ours
-            ct, cq = targets, queries
-            what = "the whole workload (%d target reads, %d queries): same inputs as the GPU arm" % (ct.n, cq.n)
-        v, dt, kind, cores, ref_table = cpu_reference_run(a, ct, cq, host_threads())
-        cpu = {"value": v, "unit": "Gbases/s", "cores": cores, "kind": kind, "seconds": dt, "sample": what}
-        if not a.cpu_sample:
-            parity["vs_cpu_%s_full_size" % kind] = "identical (%d rows, byte for byte)" % ref_table.count(b"\n") if ref_table == runner.last_table else "DIFFERS"
-    line = {"metric": "read Gbases/s through minimap2-coverage (target bases indexed + query bases mapped per second)",
+    cpu, cli, sd = None, None, None
+    if world == 1 and not (a.no_cpu_baseline and a.no_cli):
+        # the workload as the FASTQ files LongQC would hand the binaries (in /dev/shm): the reference binary and OUR drop-in executable
+        # run on the same files, wall clock of the whole process each (exec, CUDA context, parsing, compute, table on stdout)
+        files = FastqFiles(targets, queries)
+        if not a.no_cpu_baseline:
+            if a.cpu_sample:
+                ct, cq = make_data(a, a.cpu_sample_reads, a.cpu_sample_queries)
+                what = "%d target reads x %d b + %d queries of the same generator (bounded sample)" % (ct.n, a.read_len, cq.n)
+                v, dt, kind, cores, ref_table = cpu_reference_run(a, ct, cq, host_threads())
+            else:   # the whole benchmarked workload: ~20-30 s of CPU, and its table is the full-size parity check of ours
+                what = "the whole workload (%d target reads, %d queries): same inputs as the GPU arm" % (targets.n, queries.n)
+                v, dt, kind, cores, ref_table = cpu_reference_run(a, targets, queries, host_threads(), files)
+                parity["vs_cpu_%s_full_size" % kind] = "identical (%d rows, byte for byte)" % ref_table.count(b"\n") if ref_table == runner.last_table else "DIFFERS"
+            cpu = {"value": v, "unit": "Gbases/s", "cores": cores, "kind": kind, "seconds": dt, "sample": what}
+        if not a.no_cli:
+            exe = [L.bin_path("minimap2-coverage")] + FLAGS.split() + ["-t", str(host_threads())]
+            files.run(exe)                                   # warm-up: page cache, CUDA driver's module cache
+            secs, tab = [], b""
+            for _ in range(3):
+                dt, tab = files.run(exe)
+                secs.append(dt)
+            best = min(secs)
+            cli = {"value": files.n_bases / (sum(secs) / len(secs)) / 1e9, "unit": "Gbases/s", "seconds": sum(secs) / len(secs), "seconds_best": best,
+                   "runs": len(secs), "fastq_bytes": files.bytes, "fastq_gb_per_s": files.bytes / best / 1e9,
+                   "what": "wall clock of longqc_b200/bin/minimap2-coverage %s -t %d <targets.fq> <queries.fq> > table, files in /dev/shm: process start, "
+                           "CUDA context, FASTQ parsing, H2D, compute, table" % (FLAGS, host_threads()),
+                   "table": "identical to the resident-path table" if tab == runner.last_table else "DIFFERS"}
+            if cpu and not a.cpu_sample:
+                cli["speedup_vs_cpu_reference_same_files"] = cpu["seconds"] / cli["seconds"]
+        files.close()
+    if world == 1 and not a.no_sdust:
+        sd = sdust_line(a, L, targets)
+    line = {"metric": METRIC,
             "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name(a, world), "target_bases": int(runner.target_bases_all), "query_bases": int(runner.query_bases_all),
                        "parallelism": runner.parallelism(), "l2": "inputs (>= %.1f GB per rank) larger than the 126 MB L2" % (targets.n_bases / 1e9),
                        "host_wall_ms_per_step": 1e3 * wall / a.steps},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(prof["launches"] // a.steps),
-            "roofline": roof, "sketch_kernel": sk[0] if sk else None, "kernels": klist, "cpu_baseline": cpu, "parity": parity,
+            "roofline": roof, "sketch_kernel": sk[0] if sk else None, "kernels": klist, "cpu_baseline": cpu, "cli_e2e": cli, "sdust": sd, "parity": parity,
             "stats": runner.last_stats}
     print(json.dumps(line))
     if world > 1:

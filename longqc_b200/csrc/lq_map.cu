@@ -1575,9 +1575,9 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         LQ_CUDA_OK(cudaStreamSynchronize(st));
         stats->n_walk_buckets += w;
         if (lq_prof_on()) {
-            /* algorithmic bytes per element. level: idx 4 + key gather 8 + tie flag 4 + digit 1w+1r + dest 4w+4r + permute (4r 4w 4r 4w) = 42;
-             * walk: digit 1r (histogram) + 1r (walk) + dest 4w+4r + permute 16 = 26 */
-            for (int l = 0; l < 8; ++l) { lq_prof_add_bytes(lvl_name[l], ne[l] * 42ULL); lq_prof_add_bytes(wlk_name[l], ne[8 + l] * 26ULL); }
+            /* algorithmic bytes per element and level: the 12-byte (key, seed number) pair read once and written once.
+             * Digits, destinations and pick-up lists are this implementation's own traffic and are not counted. */
+            for (int l = 0; l < 8; ++l) { lq_prof_add_bytes(lvl_name[l], ne[l] * 24ULL); lq_prof_add_bytes(wlk_name[l], ne[8 + l] * 24ULL); }
         }
     }
     return 0;

@@ -161,6 +161,20 @@ def exchange_part(lib, h, rank, world):
     torch.cuda.synchronize()
 
 
+def rank_inputs(a, rank: int, world: int):
+    """(targets, queries) of one rank of bench.py's workload: every rank owns `a.reads` target reads of ONE genome shared by all
+    ranks (30x overall) and maps `a.queries / world` of its own reads.  Deterministic in (a.seed, rank, world), so any process can
+    regenerate any rank's share (bench.py --impl reference, the N > 1 table check)."""
+    rng_g = np.random.default_rng(a.seed)
+    G = max(int(a.reads * world * a.read_len / 30.0), 2 * a.read_len)
+    genome = synth.make_genome(G, rng_g)
+    rng = np.random.default_rng(a.seed + 7919 * (rank + 1))
+    targets = synth.simulate_reads(genome, a.reads, a.read_len, a.err, rng, name_start=rank * a.reads)
+    nq_lo, nq_hi = split_even(a.queries, world)[rank]
+    qidx = np.sort(rng.choice(a.reads, size=min(nq_hi - nq_lo, a.reads), replace=False))
+    return targets, targets.subset(qidx)
+
+
 class Runner:
     """One rank of the (possibly multi-GPU) coverage job on the synthetic workload of bench.py."""
 
@@ -175,16 +189,7 @@ class Runner:
     def make_inputs(self):
         import torch
         a, world, rank = self.a, self.world, self.rank
-        rng_g = np.random.default_rng(a.seed)
-        G = max(int(a.reads * world * a.read_len / 30.0), 2 * a.read_len)
-        genome = synth.make_genome(G, rng_g)
-        rng = np.random.default_rng(a.seed + 7919 * (rank + 1))
-        my_lo = rank * a.reads
-        self.targets = synth.simulate_reads(genome, a.reads, a.read_len, a.err, rng, name_start=my_lo)
-        nq_lo, nq_hi = split_even(a.queries, world)[rank]
-        qidx = np.sort(rng.choice(a.reads, size=min(nq_hi - nq_lo, a.reads), replace=False))
-        self.queries = self.targets.subset(qidx)
-        del genome
+        self.targets, self.queries = rank_inputs(a, rank, world)
         # global read list = rank-major: lengths and names of every rank's reads
         lens = self.targets.lengths().astype(np.int64)
         if world > 1:
