@@ -102,6 +102,20 @@ int  lqcov_add_part(lqcov_ctx *c, const lqcov_reads_t *part);
  *                            (n, seq_off for the lengths, names; seq may be NULL)
  *   lqcov_map_part           map this context's queries against the finished part */
 int  lqcov_part_sketch(lqcov_ctx *c, const lqcov_reads_t *shard, uint32_t rid_base);
+/* lqcov_part_sketch with the shard arriving in CHUNKS of consecutive reads (the executable's reader threads fill pinned staging
+ * buffers while the device copies, packs and sketches the chunk before; replaces the reference's 3-stage kt_pipeline of
+ * index.c:238-309 / kthread.c:96-158):
+ *   lqcov_part_begin   expect_bases: first sizing of the device arrays (0 = unknown; they grow); returns 1 when the configuration
+ *                      has no chunked form (-H): use lqcov_part_sketch
+ *   lqcov_stage        n pinned host buffers of `bytes` bytes each, owned by the context
+ *   lqcov_part_chunk   queue copy + pack + sketch of a chunk whose bases lie in staging buffer `stage_index` (-1: any host memory); returns at once
+ *   lqcov_stage_wait   block until staging buffer `stage_index` may be refilled
+ *   lqcov_part_end     all chunks are in: minimizers counted; go on with the collectives / lqcov_part_finish / lqcov_map_part */
+int  lqcov_part_begin(lqcov_ctx *c, uint64_t expect_bases, uint32_t rid_base);
+int  lqcov_stage(lqcov_ctx *c, int n, size_t bytes, char **bufs);
+int  lqcov_part_chunk(lqcov_ctx *c, const lqcov_reads_t *chunk, int stage_index);
+int  lqcov_stage_wait(lqcov_ctx *c, int stage_index);
+int  lqcov_part_end(lqcov_ctx *c);
 int  lqcov_part_device_views(lqcov_ctx *c, void **counts, uint64_t *n_counts, void **key, void **y, uint64_t *n_rec);
 int  lqcov_part_gather_buffers(lqcov_ctx *c, uint64_t n_total, void **key, void **y);
 int  lqcov_part_finish(lqcov_ctx *c, const lqcov_reads_t *part);
@@ -137,7 +151,11 @@ size_t lqcov_profile_json(char *buf, size_t cap);            /* returns the leng
 /* host helpers shared with the executables -------------------------------------------------- */
 /* FASTA/FASTQ(.gz) reader with kseq.h:185-224 + bseq.c:56-66 semantics.  Reads records until the
  * accumulated sequence length reaches `chunk` (chunk <= 0: whole file).  The returned set lives until
- * the next call or lqcov_reader_close.  Returns 1 = records returned, 0 = end of file, <0 = error. */
+ * the next call or lqcov_reader_close.  Returns 1 = records returned, 0 = end of input, 2 = an empty set (see below), <0 = error.
+ * A FASTQ record kseq_read() rejects (truncated or mismatched quality, kseq.h:216-222) is not delivered and ends what the reading
+ * loop of the reference would end there: with chunk <= 0 the whole input (one kseq_read loop: minimap2-coverage.c:418, sdust.c:198),
+ * with chunk > 0 the batch (bseq.c:76), for index parts the mini-batch -- and the part when that mini-batch is empty (index.c:246-247).
+ * Plain files are read by several threads (lq_ingest.c; LQCOV_READER_THREADS), anything else sequentially. */
 typedef struct lqcov_reader lqcov_reader;
 lqcov_reader *lqcov_reader_open(const char *path);          /* "-" = stdin */
 int  lqcov_reader_next(lqcov_reader *r, int64_t chunk, lqcov_reads_t *out);

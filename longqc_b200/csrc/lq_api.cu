@@ -67,6 +67,7 @@ struct lqcov_ctx {
     std::vector<float> avg_k;           /* avg_ks */
     /* device */
     LqQueryDev qd; LqIndexDev ix; LqMapScratch sc; LqReadsDev treads; LqMinimizers tmins, full; LqDevBuf ws, qual_dev, qsum_dev; bool use_full;
+    LqPartStream stream; std::vector<char*> stage; size_t stage_bytes; std::vector<cudaEvent_t> stage_ev; double t_part0;
     /* current part */
     std::vector<uint32_t> self_off, self_list, qrank, trank;
     bool part_ready;
@@ -101,7 +102,7 @@ extern "C" lqcov_ctx *lqcov_create(const lqcov_opt_t *o)
     if (o->w < 1 || o->w > LQ_MAX_W) { fprintf(stderr, "[lqcov] ERROR: -w %d outside 1..%d supported by the GPU path\n", o->w, LQ_MAX_W); return 0; }
     if (o->k < 1 || o->k > LQ_MAX_K_DIRECT) { fprintf(stderr, "[lqcov] ERROR: -k %d outside 1..%d supported by the direct-address index of this build\n", o->k, LQ_MAX_K_DIRECT); return 0; }
     lqcov_ctx *c = new lqcov_ctx();
-    c->opt = *o; c->nq = 0; c->q_has_qual = false; c->part_ready = false; c->use_full = false; c->mid_occ = 0;
+    c->opt = *o; c->stage_bytes = 0; c->nq = 0; c->q_has_qual = false; c->part_ready = false; c->use_full = false; c->mid_occ = 0;
     memset(&c->stats, 0, sizeof(c->stats));
     if (cudaStreamCreate(&c->st) != cudaSuccess) { fprintf(stderr, "[lqcov] ERROR: cudaStreamCreate failed\n"); delete c; return 0; }
     return c;
@@ -121,6 +122,7 @@ extern "C" void lqcov_destroy(lqcov_ctx *c)
     if (!c) return;
     cudaStreamSynchronize(c->st);
     for (size_t i = 0; i < c->ovlp.size(); ++i) free(c->ovlp[i].a);
+    c->stream.release(); for (size_t i = 0; i < c->stage.size(); ++i) cudaFreeHost(c->stage[i]);
     c->qd.release(); c->ix.release(); c->sc.release(); c->treads.release(); c->tmins.release(); c->full.release(); c->ws.release(); c->qual_dev.release(); c->qsum_dev.release();
     cudaStreamDestroy(c->st);
     delete c;
@@ -224,6 +226,58 @@ extern "C" int lqcov_part_sketch(lqcov_ctx *c, const lqcov_reads_t *shard, uint3
     }
     LQ_CUDA_OK(cudaStreamSynchronize(c->st));
     c->stats.t_sketch_ms += now_ms() - t0; t0 = now_ms();
+    LQ_TRY(lq_index_alloc(ix, c->opt.k, c->st));
+    LQ_TRY(lq_index_count(ix, &ix->rec, c->st));
+    LQ_CUDA_OK(cudaStreamSynchronize(c->st));
+    c->stats.t_index_ms += now_ms() - t0;
+    c->stats.target_bases += c->treads.n_bases;
+    return 0;
+}
+
+/* ---- the same, with the shard arriving in chunks from pinned staging buffers while the caller's reader threads parse the file ---- */
+extern "C" int lqcov_part_begin(lqcov_ctx *c, uint64_t expect_bases, uint32_t rid_base)
+{
+    if (!lq_stream_ok(c->opt.w, c->opt.k, c->opt.is_hpc)) return 1;   /* not applicable: hand the whole part to lqcov_part_sketch */
+    c->t_part0 = now_ms();
+    c->part_ready = false; c->use_full = false;
+    LQ_TRY(lq_stream_begin(&c->stream, &c->treads, &c->ix.rec, c->opt.w, c->opt.k, rid_base, expect_bases, c->st));
+    return 0;
+}
+
+extern "C" int lqcov_stage(lqcov_ctx *c, int n, size_t bytes, char **bufs)
+{
+    if ((int)c->stage.size() != n || c->stage_bytes != bytes) {
+        for (size_t i = 0; i < c->stage.size(); ++i) cudaFreeHost(c->stage[i]);
+        c->stage.assign((size_t)n, (char*)0); c->stage_ev.assign((size_t)n, (cudaEvent_t)0); c->stage_bytes = bytes;
+        for (int i = 0; i < n; ++i) LQ_CUDA_OK(cudaHostAlloc((void**)&c->stage[i], bytes, cudaHostAllocDefault));
+    }
+    for (int i = 0; i < n; ++i) { bufs[i] = c->stage[i]; c->stage_ev[i] = 0; }
+    return 0;
+}
+
+extern "C" int lqcov_part_chunk(lqcov_ctx *c, const lqcov_reads_t *chunk, int stage_index)
+{
+    cudaEvent_t ev = 0;
+    LQ_TRY(lq_stream_push(&c->stream, (const uint8_t*)chunk->seq, chunk->seq_off, chunk->n, &ev));
+    if (stage_index >= 0 && stage_index < (int)c->stage_ev.size()) c->stage_ev[stage_index] = ev;
+    return 0;
+}
+
+extern "C" int lqcov_stage_wait(lqcov_ctx *c, int stage_index)
+{
+    if (stage_index >= 0 && stage_index < (int)c->stage_ev.size() && c->stage_ev[stage_index]) {
+        LQ_CUDA_OK(cudaEventSynchronize(c->stage_ev[stage_index]));   /* the event may have been re-recorded by a later chunk: waiting longer is harmless */
+        c->stage_ev[stage_index] = 0;
+    }
+    return 0;
+}
+
+extern "C" int lqcov_part_end(lqcov_ctx *c)
+{
+    LqIndexDev *ix = &c->ix;
+    LQ_TRY(lq_stream_end(&c->stream, c->ws));
+    c->stats.t_sketch_ms += now_ms() - c->t_part0;
+    const double t0 = now_ms();
     LQ_TRY(lq_index_alloc(ix, c->opt.k, c->st));
     LQ_TRY(lq_index_count(ix, &ix->rec, c->st));
     LQ_CUDA_OK(cudaStreamSynchronize(c->st));

@@ -11,7 +11,9 @@
 #include <inttypes.h>
 #include <sys/time.h>
 #include <sys/resource.h>
+#include <pthread.h>
 #include "lqcov.h"
+#include "lq_ingest.h"
 
 const char *argp_program_version = "minimap2-coverage 0.3 (lqcov-b200; CLI of LongQC's fork of minimap2 2.6-r639)";
 const char *argp_program_bug_address = "<lqcov-b200 maintainers>";
@@ -108,6 +110,111 @@ static struct argp the_argp = { opts, on_opt, "reference reads",
 static double wall(void) { struct timeval t; gettimeofday(&t, 0); return t.tv_sec + t.tv_usec * 1e-6; }
 static double cpu(void) { struct rusage r; getrusage(RUSAGE_SELF, &r); return r.ru_utime.tv_sec + r.ru_stime.tv_sec + 1e-6 * (r.ru_utime.tv_usec + r.ru_stime.tv_usec); }
 
+/* ---- the part loop: index parts arrive in chunks of consecutive reads (lq_ingest.c), the device copies, packs and sketches chunk i
+ *      while the reader threads fill chunk i+1 (replaces kt_pipeline's read -> sketch -> dispatch stages, index.c:238-309) ---- */
+#define CLI_NSTAGE 4
+#define CLI_STAGE_BYTES ((size_t)32 << 20)
+
+struct init_job { const lqcov_opt_t *o; lqcov_ctx *c; char *stage[CLI_NSTAGE]; int rc; };
+static void *init_thread(void *p)
+{
+    struct init_job *j = (struct init_job*)p;
+    j->c = lqcov_create(j->o);
+    j->rc = j->c ? lqcov_stage(j->c, CLI_NSTAGE, CLI_STAGE_BYTES, j->stage) : -1;
+    return 0;
+}
+
+static int reader_threads(int t_opt)
+{
+    const char *e = getenv("LQCOV_READER_THREADS");
+    int n = e ? atoi(e) : t_opt;
+    if (n < 1) n = 1;
+    if (n > 64) n = 64;
+    return n;
+}
+
+typedef struct { uint64_t *seq_off, *name_off; char *names; size_t n, m, nn, nm; } part_meta;
+static void meta_add(part_meta *pm, const lqi_chunk *ch)
+{
+    if (pm->n + ch->n + 2 > pm->m) { pm->m = (pm->n + ch->n + 2) * 2; pm->seq_off = (uint64_t*)realloc(pm->seq_off, pm->m * 8); pm->name_off = (uint64_t*)realloc(pm->name_off, pm->m * 8); }
+    if (pm->nn + ch->name_off[ch->n] + 1 > pm->nm) { pm->nm = (pm->nn + ch->name_off[ch->n] + 1) * 2; pm->names = (char*)realloc(pm->names, pm->nm); }
+    if (pm->n == 0) { pm->seq_off[0] = 0; pm->name_off[0] = 0; }
+    for (uint32_t i = 0; i < ch->n; ++i) {
+        pm->seq_off[pm->n + i + 1] = pm->seq_off[pm->n] + ch->seq_off[i + 1];
+        pm->name_off[pm->n + i + 1] = pm->nn + ch->name_off[i + 1];
+    }
+    memcpy(pm->names + pm->nn, ch->names, ch->name_off[ch->n]);
+    pm->n += ch->n; pm->nn += ch->name_off[ch->n];
+}
+
+static int run_parts(lqcov_ctx *c, lqi_reader *tr, const lqcov_opt_t *o, char **stage, double t0)
+{
+    part_meta pm; memset(&pm, 0, sizeof pm);
+    int rc = 0, eof = 0;
+    lqi_part_rule(tr, o->batch_size, o->mini_batch_size);
+    while (rc == 0 && !eof) {
+        uint64_t expect = lqi_bases_left_bound(tr);           /* first sizing of the device arrays; they grow if the part turns out larger */
+        if (expect > o->batch_size + 2 * (uint64_t)o->mini_batch_size) expect = o->batch_size + 2 * (uint64_t)o->mini_batch_size;
+        const int streamed = lqcov_part_begin(c, expect, 0);  /* 1: no chunked form for this configuration (-H): whole part at once */
+        char *whole = 0; size_t whole_cap = 0, whole_n = 0;
+        int i = 0, part_end = 0;
+        if (streamed < 0) { rc = 1; break; }
+        pm.n = 0; pm.nn = 0;
+        while (rc == 0 && !part_end && !eof) {
+            lqi_chunk ch; int r;
+            char *dst; size_t cap;
+            if (streamed == 0) { lqcov_stage_wait(c, i % CLI_NSTAGE); dst = stage[i % CLI_NSTAGE]; cap = CLI_STAGE_BYTES; }
+            else {
+                if (whole_cap - whole_n < CLI_STAGE_BYTES) { whole_cap = whole_cap ? whole_cap * 2 : 4 * CLI_STAGE_BYTES; whole = (char*)realloc(whole, whole_cap); }
+                dst = whole + whole_n; cap = whole_cap - whole_n;
+            }
+            r = lqi_next_chunk(tr, cap, dst, 0, &ch);
+            if (r == -2) {                                    /* a read longer than a staging buffer */
+                if (streamed != 0) { whole_cap = whole_n + ch.need + CLI_STAGE_BYTES; whole = (char*)realloc(whole, whole_cap); continue; }
+                /* through pageable memory: cudaMemcpyAsync returns once a pageable source has been staged, so `big` can be freed at once */
+                char *big = (char*)malloc(ch.need + 1);
+                r = lqi_next_chunk(tr, ch.need, big, 0, &ch);
+                if (r == 1) {
+                    lqcov_reads_t cr; memset(&cr, 0, sizeof cr);
+                    cr.n = ch.n; cr.seq = big; cr.seq_off = ch.seq_off; cr.names = ch.names; cr.name_off = ch.name_off;
+                    meta_add(&pm, &ch);
+                    if (lqcov_part_chunk(c, &cr, -1) != 0) rc = 1;
+                }
+                free(big);
+                part_end = ch.part_end; eof = ch.eof;
+                continue;
+            }
+            part_end = ch.part_end; eof = ch.eof;
+            if (r <= 0) continue;
+            meta_add(&pm, &ch);
+            if (streamed == 0) {
+                lqcov_reads_t cr; memset(&cr, 0, sizeof cr);
+                cr.n = ch.n; cr.seq = dst; cr.seq_off = ch.seq_off; cr.names = ch.names; cr.name_off = ch.name_off;
+                if (lqcov_part_chunk(c, &cr, i % CLI_NSTAGE) != 0) rc = 1;
+                ++i;
+            } else whole_n += ch.n_bases;
+        }
+        if (rc == 0 && pm.n > 0) {
+            lqcov_reads_t part; memset(&part, 0, sizeof part);
+            part.n = (uint32_t)pm.n; part.seq_off = pm.seq_off; part.names = pm.names; part.name_off = pm.name_off;
+            if (streamed == 0) {
+                if (lqcov_part_end(c) != 0 || lqcov_part_finish(c, &part) != 0) rc = 1;
+                fprintf(stderr, "[M::%s::%.3f*%.2f] indexed %u target sequence(s)\n", __func__, wall() - t0, cpu() / (wall() - t0), part.n);
+                if (rc == 0 && lqcov_map_part(c) != 0) rc = 1;
+            } else {
+                part.seq = whole;
+                if (lqcov_add_part(c, &part) != 0) rc = 1;
+            }
+            fprintf(stderr, "[M::%s::%.3f*%.2f] mapped against part of %u sequence(s)\n", __func__, wall() - t0, cpu() / (wall() - t0), part.n);
+        } else if (rc == 0 && streamed == 0) {
+            if (lqcov_part_end(c) != 0) rc = 1;               /* an empty part (a rejected record closed it): nothing to map against */
+        }
+        free(whole);
+    }
+    free(pm.seq_off); free(pm.name_off); free(pm.names);
+    return rc;
+}
+
 int lqcov_main(int argc, char **argv)
 {
     struct cli a;
@@ -149,27 +256,32 @@ int lqcov_main(int argc, char **argv)
     fprintf(stderr, "max-overhang %d, min-overlaplen %d, min-overapratio %.2f\n", o.max_overhang, o.min_ovlp, o.min_ratio);
     fprintf(stderr, "num of threads %d, num of query seqs %d\n===\n", o.n_threads, a.n_subset);
 
-    lqcov_reader *tr = lqcov_reader_open(a.args[0]);
-    if (!tr) { fprintf(stderr, "ERROR: failed to open file '%s'\n", a.args[0]); return 1; }
-    lqcov_reader *qr = lqcov_reader_open(a.args[1]);
-    if (!qr) { fprintf(stderr, "ERROR: failed to open file '%s'\n", a.args[1]); lqcov_reader_close(tr); return 1; }
-    lqcov_ctx *c = lqcov_create(&o);
-    if (!c) { lqcov_reader_close(tr); lqcov_reader_close(qr); return 1; }
-    lqcov_reads_t q, part;
+    /* The CUDA context (a few hundred ms) is created on a second thread while the reader threads already parse the inputs. */
+    struct init_job ij; pthread_t ith;
+    memset(&ij, 0, sizeof ij); ij.o = &o;
+    pthread_create(&ith, 0, init_thread, &ij);
+    const int n_rd = reader_threads(o.n_threads);
+    lqi_reader *tr = lqi_open(a.args[0], n_rd);
+    lqcov_reader *qr = tr ? lqcov_reader_open(a.args[1]) : 0;
+    lqcov_reads_t q; memset(&q, 0, sizeof q);
+    if (qr) lqcov_reader_next(qr, 0, &q);                     /* one kseq_read loop over the query file (minimap2-coverage.c:418) */
+    pthread_join(ith, 0);
+    lqcov_ctx *c = ij.c;
+    if (!tr) fprintf(stderr, "ERROR: failed to open file '%s'\n", a.args[0]);
+    else if (!qr) fprintf(stderr, "ERROR: failed to open file '%s'\n", a.args[1]);
+    if (!tr || !qr || !c || ij.rc != 0) { if (tr) lqi_close(tr); if (qr) lqcov_reader_close(qr); if (c) lqcov_destroy(c); return 1; }
     int rc = 0;
-    lqcov_reader_next(qr, 0, &q);
     if (lqcov_set_queries(c, &q) != 0) rc = 1;
-    lqcov_reader_close(qr);
     fprintf(stderr, "[M::%s::%.3f*%.2f] loaded %u sequence(s).\n", __func__, wall() - t0, cpu() / (wall() - t0), q.n);
-    while (rc == 0 && lqcov_reader_next_part(tr, o.batch_size, o.mini_batch_size, &part) > 0)
-        if (lqcov_add_part(c, &part) != 0) rc = 1;
-    lqcov_reader_close(tr);
+    lqcov_reader_close(qr);
+    if (rc == 0) rc = run_parts(c, tr, &o, ij.stage, t0);
+    lqi_close(tr);
     if (rc == 0) {
         char *tab = 0; size_t len = 0;
         if (lqcov_table(c, &tab, &len) != 0) rc = 1;
         else { fwrite(tab, 1, len, stdout); fflush(stdout); lqcov_free(tab); }
     }
-    lqcov_destroy(c);
+    if (!getenv("LQCOV_FAST_EXIT")) lqcov_destroy(c);
     fprintf(stderr, "\n[M::%s] Real time: %.3f sec; CPU: %.3f sec\n", __func__, wall() - t0, cpu());
     return rc;
 }

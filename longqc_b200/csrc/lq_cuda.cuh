@@ -30,6 +30,16 @@ struct LqDevBuf {
         if (e != cudaSuccess) { fprintf(stderr, "[lqcov] cudaMalloc(%zu) failed: %s\n", want, cudaGetErrorString(e)); p = 0; return -1; }
         cap = want; return 0;
     }
+    /* grow, keeping the first `keep` bytes (work queued on `st` that touches the old block is waited for) */
+    int ensure_keep(size_t bytes, size_t keep, cudaStream_t st) {
+        if (bytes <= cap) return 0;
+        if (!p || keep == 0) return ensure(bytes);
+        void *q = 0; const size_t want = bytes + (bytes >> 1) + 256;
+        cudaError_t e = cudaMalloc(&q, want);
+        if (e != cudaSuccess) { fprintf(stderr, "[lqcov] cudaMalloc(%zu) failed: %s\n", want, cudaGetErrorString(e)); return -1; }
+        if (cudaMemcpyAsync(q, p, keep < cap ? keep : cap, cudaMemcpyDeviceToDevice, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(q); return -1; }
+        cudaFree(p); p = q; cap = want; return 0;
+    }
     void release() { if (p) cudaFree(p); p = 0; cap = 0; }
     template <class T> T *as() const { return (T*)p; }
 };

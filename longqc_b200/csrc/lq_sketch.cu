@@ -927,3 +927,155 @@ int lq_read_first(const LqMinimizers *m, uint32_t rid_base, uint32_t n_reads, Lq
     LQ_CUDA_OK(cudaGetLastError());
     return 0;
 }
+
+/* ------------------------------------------------------------------ a part arriving in chunks (host staging buffers -> records)
+ *
+ * The streaming form of lq_upload_sketch_pipelined(): the chunks are not cut from one big host blob but arrive one by one from the
+ * reader (lq_ingest.c fills pinned staging buffers while the GPU works on the chunk before), and the part's size is not known in
+ * advance -- the packed read store, the per-read arrays and the record arrays grow on demand (LqDevBuf::ensure_keep).  The ASCII
+ * bases only pass through a ring of two chunk-sized device buffers. */
+void LqPartStream::release()
+{
+    for (int i = 0; i < LQ_STREAM_RING; ++i) asc[i].release();
+    state.release(); totals.release();
+    if (ev_made) for (int i = 0; i < LQ_STREAM_RING; ++i) { cudaEventDestroy(ev_copied[i]); cudaEventDestroy(ev_packed[i]); }
+    ev_made = false;
+    if (st_copy) { cudaStreamDestroy(st_copy); st_copy = 0; }
+    for (int i = 0; i < LQ_STREAM_RING; ++i) { if (h_meta[i]) cudaFreeHost(h_meta[i]); h_meta[i] = 0; h_meta_cap[i] = 0; }
+}
+
+bool lq_stream_ok(int w, int k, int is_hpc) { return !is_hpc && (w == 5 || w == 10) && k <= 15 && !g_sketch_tiled && !g_sketch_lanes; }
+
+#define ST_MAX_CHUNKS 65536
+int lq_stream_begin(LqPartStream *s, LqReadsDev *d, LqMinimizers *out, int w, int k, uint32_t rid_base, uint64_t expect_bases, cudaStream_t st)
+{
+    s->d = d; s->out = out; s->w = w; s->k = k; s->rid_base = rid_base; s->st = st;
+    if (!s->st_copy) LQ_CUDA_OK(cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking));
+    if (!s->ev_made) {
+        for (int i = 0; i < LQ_STREAM_RING; ++i) {
+            LQ_CUDA_OK(cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming));
+            LQ_CUDA_OK(cudaEventCreateWithFlags(&s->ev_packed[i], cudaEventDisableTiming));
+        }
+        s->ev_made = true;
+    }
+    d->n_reads = 0; d->n_bases = 0; d->n_slots = 0; d->h_len.clear(); d->h_slot0.clear(); d->h_slot0.push_back(0);
+    out->n = 0; out->has_span = 0;
+    s->state_used = 0; s->n_chunks = 0; s->chunk_state_off.clear(); s->chunk_tiles.clear();
+    /* first sizes from the caller's expectation; everything grows when the part turns out larger */
+    const uint64_t eb = expect_bases ? expect_bases : (256ull << 20), er = eb / 2000 + 1024, es = eb / LQ_SLOT + er;
+    LQ_TRY(d->len.ensure((size_t)(er + 1) * 4)); LQ_TRY(d->slot0.ensure((size_t)(er + 1) * 8)); LQ_TRY(d->off.ensure((size_t)(er + 1) * 8));
+    LQ_TRY(d->b2.ensure((size_t)(es * LQ_SLOT_W2 + 16) * 4)); LQ_TRY(d->nm.ensure((size_t)(es * LQ_SLOT_WN + 16) * 4)); LQ_TRY(d->slot_read.ensure((size_t)(es + 1) * 4));
+    s->cap_rec = (uint64_t)((double)eb * 2.6 / (w + 1)) + 4096;
+    LQ_TRY(out->key.ensure((size_t)(s->cap_rec + 1) * 4)); LQ_TRY(out->y.ensure((size_t)(s->cap_rec + 1) * 8));
+    LQ_TRY(s->state.ensure((size_t)(es * LQ_SLOT / RK_TILE + 4096) * 8));
+    LQ_TRY(s->totals.ensure((size_t)(ST_MAX_CHUNKS + 2) * 8));
+    LQ_CUDA_OK(cudaMemsetAsync(s->totals.p, 0, 8, st));
+    s->open = true;
+    return 0;
+}
+
+int lq_stream_push(LqPartStream *s, const uint8_t *h_seq, const uint64_t *h_off, uint32_t n, cudaEvent_t *copied)
+{
+    LqReadsDev *d = s->d; LqMinimizers *out = s->out; cudaStream_t st = s->st;
+    if (copied) *copied = 0;
+    if (n == 0) return 0;
+    if (s->n_chunks >= ST_MAX_CHUNKS) { fprintf(stderr, "[lqcov] too many chunks in one index part\n"); return -1; }
+    const uint32_t r0 = d->n_reads; const uint64_t s0 = d->n_slots, bases = h_off[n] - h_off[0];
+    const int ring = (int)(s->n_chunks % LQ_STREAM_RING);
+    /* layout of the new reads; their per-read arrays travel through a pinned block of the ring slot (it was last used two chunks
+     * ago: the copy that read it is ordered before ev_packed of that chunk, which the host waits for here) */
+    uint64_t slots = s0;
+    const size_t meta_bytes = (size_t)n * 20 + 64;
+    if (s->n_chunks >= LQ_STREAM_RING) LQ_CUDA_OK(cudaEventSynchronize(s->ev_packed[ring]));
+    if (meta_bytes > s->h_meta_cap[ring]) {
+        if (s->h_meta[ring]) cudaFreeHost(s->h_meta[ring]);
+        s->h_meta[ring] = 0; s->h_meta_cap[ring] = 0;
+        LQ_CUDA_OK(cudaHostAlloc(&s->h_meta[ring], meta_bytes * 2, cudaHostAllocDefault));
+        s->h_meta_cap[ring] = meta_bytes * 2;
+    }
+    uint64_t *aoff = (uint64_t*)s->h_meta[ring], *pslot0 = aoff + n; uint32_t *plen = (uint32_t*)(pslot0 + n + 1);   /* offsets inside the ring buffer | slot0 | len */
+    d->h_len.resize((size_t)r0 + n); d->h_slot0.resize((size_t)r0 + n + 1);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t L = h_off[i + 1] - h_off[i];
+        if (L > 0x7fffffffULL) { fprintf(stderr, "[lqcov] read longer than 2^31\n"); return -1; }
+        d->h_len[r0 + i] = (uint32_t)L; d->h_slot0[r0 + i] = slots; aoff[i] = h_off[i] - h_off[0]; pslot0[i] = slots; plen[i] = (uint32_t)L;
+        slots += (L + LQ_SLOT - 1) / LQ_SLOT;
+    }
+    pslot0[n] = slots;
+    d->h_slot0[(size_t)r0 + n] = slots;
+    const uint32_t r1 = r0 + n; const uint64_t s1 = slots;
+    /* room (growth keeps what earlier chunks left; it waits for the stream, which is fine for a rare event) */
+    LQ_TRY(d->len.ensure_keep((size_t)(r1 + 1) * 4, (size_t)r0 * 4, st)); LQ_TRY(d->slot0.ensure_keep((size_t)(r1 + 1) * 8, (size_t)(r0 + 1) * 8, st));
+    LQ_TRY(d->off.ensure_keep((size_t)(r1 + 1) * 8, (size_t)r0 * 8, st));
+    LQ_TRY(d->b2.ensure_keep((size_t)(s1 * LQ_SLOT_W2 + 16) * 4, (size_t)s0 * LQ_SLOT_W2 * 4, st)); LQ_TRY(d->nm.ensure_keep((size_t)(s1 * LQ_SLOT_WN + 16) * 4, (size_t)s0 * LQ_SLOT_WN * 4, st));
+    LQ_TRY(d->slot_read.ensure_keep((size_t)(s1 + 1) * 4, (size_t)s0 * 4, st));
+    const uint64_t need_rec = (uint64_t)((double)(d->n_bases + bases) * 2.6 / (s->w + 1)) + 4096;
+    if (need_rec > s->cap_rec) {
+        /* the records written so far: the running total is on the device; keep the whole old capacity */
+        LQ_TRY(out->key.ensure_keep((size_t)(need_rec * 3 / 2 + 1) * 4, (size_t)s->cap_rec * 4, st)); LQ_TRY(out->y.ensure_keep((size_t)(need_rec * 3 / 2 + 1) * 8, (size_t)s->cap_rec * 8, st));
+        s->cap_rec = need_rec * 3 / 2;
+    }
+    const unsigned nblk = (unsigned)(((s1 - s0) * LQ_SLOT + RK_TILE - 1) / RK_TILE);
+    LQ_TRY(s->state.ensure_keep((s->state_used + nblk + 4) * 8, s->state_used * 8, st));
+    /* the ring buffer must have been packed (two chunks ago) before it is overwritten */
+    LQ_TRY(s->asc[ring].ensure((size_t)bases + 64));   /* ensure() frees only when too small: chunks have one size in practice */
+    if (s->n_chunks >= LQ_STREAM_RING) LQ_CUDA_OK(cudaStreamWaitEvent(s->st_copy, s->ev_packed[ring], 0));
+    else { cudaEvent_t e0; LQ_CUDA_OK(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming)); LQ_CUDA_OK(cudaEventRecord(e0, st)); LQ_CUDA_OK(cudaStreamWaitEvent(s->st_copy, e0, 0)); cudaEventDestroy(e0); }
+    LQ_CUDA_OK(cudaMemcpyAsync(s->asc[ring].p, h_seq + h_off[0], (size_t)bases, cudaMemcpyHostToDevice, s->st_copy));
+    LQ_CUDA_OK(cudaEventRecord(s->ev_copied[ring], s->st_copy));
+    if (copied) *copied = s->ev_copied[ring];
+    LQ_CUDA_OK(cudaMemcpyAsync(d->len.as<uint32_t>() + r0, plen, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    LQ_CUDA_OK(cudaMemcpyAsync(d->slot0.as<uint64_t>() + r0, pslot0, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    LQ_CUDA_OK(cudaMemcpyAsync(d->off.as<uint64_t>() + r0, aoff, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    lq_prof_h2d((uint64_t)n * 20 + bases);
+    LQ_CUDA_OK(cudaMemsetAsync(d->b2.as<uint32_t>() + s1 * LQ_SLOT_W2, 0, 16 * 4, st));
+    LQ_CUDA_OK(cudaMemsetAsync(d->nm.as<uint32_t>() + s1 * LQ_SLOT_WN, 0xff, 16 * 4, st));
+    LQ_CUDA_OK(cudaStreamWaitEvent(st, s->ev_copied[ring], 0));
+    const uint8_t *d_seq = s->asc[ring].as<uint8_t>();
+    if (s1 > s0) {
+        { LqProfScope ps("pack", st, 1, bases + (s1 - s0) * (LQ_SLOT_W2 + LQ_SLOT_WN + 1) * 4);
+          /* lq_pack_k finds a slot's read by binary search over slot0[0..n_reads): the reads of this chunk are [r0, r1) */
+          lq_pack_k<<<lq_grid((s1 - s0) * 4, 256), 256, 0, st>>>(d_seq, d->off.as<uint64_t>(), d->slot0.as<uint64_t>(), d->len.as<uint32_t>(), r1, s1, 0,
+                                                               d->b2.as<uint32_t>(), d->nm.as<uint32_t>(), d->slot_read.as<uint32_t>(), d_seq, d_seq + bases, s0); }
+        LQ_CUDA_OK(cudaEventRecord(s->ev_packed[ring], st));
+        unsigned long long *state = s->state.as<unsigned long long>() + s->state_used;
+        LQ_CUDA_OK(cudaMemsetAsync(state, 0, (size_t)(nblk + 2) * 8, st));
+        SkArgs a;
+        a.b2 = d->b2.as<uint32_t>(); a.nm = d->nm.as<uint32_t>(); a.slot_read = d->slot_read.as<uint32_t>(); a.len = d->len.as<uint32_t>();
+        a.slot0 = d->slot0.as<uint64_t>(); a.w = s->w; a.k = s->k; a.rid_base = s->rid_base; a.cap = s->cap_rec;
+        a.out_key = out->key.as<uint32_t>(); a.out_y = out->y.as<uint64_t>();
+        a.n_slots = s1; a.g_begin = s0 * LQ_SLOT;
+        a.state = state; a.ticket = (uint32_t*)(state + nblk); a.err = a.ticket + 1;
+        a.base_in = s->totals.as<unsigned long long>() + s->n_chunks; a.base_out = s->totals.as<unsigned long long>() + s->n_chunks + 1;
+        { LqProfScope ps("sketch", st, 1, (s1 - s0) * (LQ_SLOT_W2 + LQ_SLOT_WN) * 4 + (uint64_t)((double)bases * 2.0 / (s->w + 1)) * 12);
+          if (s->w == 5) lq_sketch_roll_k<5><<<nblk, RK_THREADS, 0, st>>>(a); else lq_sketch_roll_k<10><<<nblk, RK_THREADS, 0, st>>>(a); }
+        LQ_CUDA_OK(cudaGetLastError());
+        s->chunk_state_off.push_back(s->state_used); s->chunk_tiles.push_back(nblk);
+        s->state_used += nblk + 2;
+    } else {
+        LQ_CUDA_OK(cudaEventRecord(s->ev_packed[ring], st));
+        LQ_CUDA_OK(cudaMemcpyAsync(s->totals.as<unsigned long long>() + s->n_chunks + 1, s->totals.as<unsigned long long>() + s->n_chunks, 8, cudaMemcpyDeviceToDevice, st));
+        s->chunk_state_off.push_back(s->state_used); s->chunk_tiles.push_back(0);
+    }
+    d->n_reads = r1; d->n_slots = s1; d->n_bases += bases;
+    ++s->n_chunks;
+    return 0;
+}
+
+int lq_stream_end(LqPartStream *s, LqDevBuf &ws)
+{
+    LqReadsDev *d = s->d; LqMinimizers *out = s->out; cudaStream_t st = s->st;
+    s->open = false;
+    if (s->n_chunks == 0) { out->n = 0; LQ_CUDA_OK(cudaStreamSynchronize(st)); return 0; }
+    unsigned long long total = 0;
+    std::vector<unsigned long long> h_state(s->state_used);
+    LQ_CUDA_OK(cudaMemcpyAsync(&total, s->totals.as<unsigned long long>() + s->n_chunks, 8, cudaMemcpyDeviceToHost, st));
+    if (s->state_used) LQ_CUDA_OK(cudaMemcpyAsync(h_state.data(), s->state.p, s->state_used * 8, cudaMemcpyDeviceToHost, st));
+    lq_prof_d2h(8 + s->state_used * 8);
+    LQ_CUDA_OK(cudaStreamSynchronize(st));
+    for (size_t c = 0; c < s->chunk_tiles.size(); ++c)
+        if (s->chunk_tiles[c] && ((const uint32_t*)(h_state.data() + s->chunk_state_off[c] + s->chunk_tiles[c]))[1]) { fprintf(stderr, "[lqcov] sketch: look-back timed out\n"); return -1; }
+    if (total > s->cap_rec) return lq_sketch_run(d, s->w, s->k, 0, s->rid_base, out, ws, st);   /* low-complexity input: the bases are packed, sketch again with room */
+    out->n = total;
+    return 0;
+}
