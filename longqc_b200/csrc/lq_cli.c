@@ -107,20 +107,30 @@ static struct argp the_argp = { opts, on_opt, "reference reads",
     "minimap2-coverage computes, for every query read, the overlaps with all target reads and prints a coverage table "
     "(LongQC's overlap/coverage pass); this build runs the pass on an NVIDIA B200.\v " };
 
+static double wall(void);
+static double g_t0;
+#define TL(what) fprintf(stderr, "[T::%.3f] %s\n", wall() - g_t0, (what))
 static double wall(void) { struct timeval t; gettimeofday(&t, 0); return t.tv_sec + t.tv_usec * 1e-6; }
 static double cpu(void) { struct rusage r; getrusage(RUSAGE_SELF, &r); return r.ru_utime.tv_sec + r.ru_stime.tv_sec + 1e-6 * (r.ru_utime.tv_usec + r.ru_stime.tv_usec); }
 
 /* ---- the part loop: index parts arrive in chunks of consecutive reads (lq_ingest.c), the device copies, packs and sketches chunk i
  *      while the reader threads fill chunk i+1 (replaces kt_pipeline's read -> sketch -> dispatch stages, index.c:238-309) ---- */
 #define CLI_NSTAGE 4
-#define CLI_STAGE_BYTES ((size_t)32 << 20)
+#define CLI_STAGE_BYTES ((size_t)16 << 20)
 
 struct init_job { const lqcov_opt_t *o; lqcov_ctx *c; char *stage[CLI_NSTAGE]; int rc; };
-static void *init_thread(void *p)
+static void *init_thread(void *p)       /* the CUDA context: hundreds of ms, during which the reader threads already parse */
 {
     struct init_job *j = (struct init_job*)p;
     j->c = lqcov_create(j->o);
-    j->rc = j->c ? lqcov_stage(j->c, CLI_NSTAGE, CLI_STAGE_BYTES, j->stage) : -1;
+    TL("CUDA context + stream created");
+    return 0;
+}
+static void *stage_thread(void *p)      /* page-locking the staging buffers runs beside the query sketch */
+{
+    struct init_job *j = (struct init_job*)p;
+    j->rc = lqcov_stage(j->c, CLI_NSTAGE, CLI_STAGE_BYTES, j->stage);
+    TL("pinned staging buffers allocated");
     return 0;
 }
 
@@ -155,7 +165,8 @@ static int run_parts(lqcov_ctx *c, lqi_reader *tr, const lqcov_opt_t *o, char **
     while (rc == 0 && !eof) {
         uint64_t expect = lqi_bases_left_bound(tr);           /* first sizing of the device arrays; they grow if the part turns out larger */
         if (expect > o->batch_size + 2 * (uint64_t)o->mini_batch_size) expect = o->batch_size + 2 * (uint64_t)o->mini_batch_size;
-        const int streamed = lqcov_part_begin(c, expect, 0);  /* 1: no chunked form for this configuration (-H): whole part at once */
+        const int streamed = lqcov_part_begin(c, expect, 0);
+        TL("part begun (device arrays sized)");  /* 1: no chunked form for this configuration (-H): whole part at once */
         char *whole = 0; size_t whole_cap = 0, whole_n = 0;
         int i = 0, part_end = 0;
         if (streamed < 0) { rc = 1; break; }
@@ -198,7 +209,10 @@ static int run_parts(lqcov_ctx *c, lqi_reader *tr, const lqcov_opt_t *o, char **
             lqcov_reads_t part; memset(&part, 0, sizeof part);
             part.n = (uint32_t)pm.n; part.seq_off = pm.seq_off; part.names = pm.names; part.name_off = pm.name_off;
             if (streamed == 0) {
-                if (lqcov_part_end(c) != 0 || lqcov_part_finish(c, &part) != 0) rc = 1;
+                TL("part parsed, all chunks queued");
+                if (lqcov_part_end(c) != 0) rc = 1;
+                TL("part sketched + counted");
+                if (rc == 0 && lqcov_part_finish(c, &part) != 0) rc = 1;
                 fprintf(stderr, "[M::%s::%.3f*%.2f] indexed %u target sequence(s)\n", __func__, wall() - t0, cpu() / (wall() - t0), part.n);
                 if (rc == 0 && lqcov_map_part(c) != 0) rc = 1;
             } else {
@@ -220,6 +234,7 @@ int lqcov_main(int argc, char **argv)
     struct cli a;
     lqcov_opt_t o;
     const double t0 = wall();
+    g_t0 = t0;
     argp_parse(&the_argp, argc, argv, 0, 0, &a);
     lqcov_opt_init(&o);
     o.verbose = 3;
@@ -265,13 +280,18 @@ int lqcov_main(int argc, char **argv)
     lqcov_reader *qr = tr ? lqcov_reader_open(a.args[1]) : 0;
     lqcov_reads_t q; memset(&q, 0, sizeof q);
     if (qr) lqcov_reader_next(qr, 0, &q);                     /* one kseq_read loop over the query file (minimap2-coverage.c:418) */
+    TL("queries parsed");
     pthread_join(ith, 0);
     lqcov_ctx *c = ij.c;
     if (!tr) fprintf(stderr, "ERROR: failed to open file '%s'\n", a.args[0]);
     else if (!qr) fprintf(stderr, "ERROR: failed to open file '%s'\n", a.args[1]);
-    if (!tr || !qr || !c || ij.rc != 0) { if (tr) lqi_close(tr); if (qr) lqcov_reader_close(qr); if (c) lqcov_destroy(c); return 1; }
+    if (!tr || !qr || !c) { if (tr) lqi_close(tr); if (qr) lqcov_reader_close(qr); if (c) lqcov_destroy(c); return 1; }
     int rc = 0;
+    pthread_create(&ith, 0, stage_thread, &ij);
     if (lqcov_set_queries(c, &q) != 0) rc = 1;
+    pthread_join(ith, 0);
+    if (ij.rc != 0) rc = 1;
+    TL("queries sketched");
     fprintf(stderr, "[M::%s::%.3f*%.2f] loaded %u sequence(s).\n", __func__, wall() - t0, cpu() / (wall() - t0), q.n);
     lqcov_reader_close(qr);
     if (rc == 0) rc = run_parts(c, tr, &o, ij.stage, t0);
@@ -281,6 +301,7 @@ int lqcov_main(int argc, char **argv)
         if (lqcov_table(c, &tab, &len) != 0) rc = 1;
         else { fwrite(tab, 1, len, stdout); fflush(stdout); lqcov_free(tab); }
     }
+    TL("table written");
     if (!getenv("LQCOV_FAST_EXIT")) lqcov_destroy(c);
     fprintf(stderr, "\n[M::%s] Real time: %.3f sec; CPU: %.3f sec\n", __func__, wall() - t0, cpu());
     return rc;
