@@ -394,6 +394,10 @@ def run_ours(a):
 
     # ---- parity spot-check of the benchmarked configuration (not timed) ----
     parity = runner.parity_note()
+    if world > 1:   # the merged N-GPU table against ONE GPU running the same global workload alone
+        same = runner.verify_against_one_gpu()
+        if rank == 0:
+            parity["vs_1gpu_same_global_workload"] = same
 
     if rank != 0:
         if world > 1:

@@ -82,6 +82,7 @@ typedef struct {
 } lqcov_stats_t;
 
 int  lqcov_abi_version(void);
+int  lqcov_device_count(void);                               /* CUDA devices visible to this process */
 void lqcov_opt_init(lqcov_opt_t *o);                       /* the defaults listed above, with -Y semantics */
 
 /* minimap2-coverage.c:217-621 as a library ---------------------------------------------------- */
@@ -96,8 +97,9 @@ int  lqcov_add_part(lqcov_ctx *c, const lqcov_reads_t *part);
 /* the same in phases, so that several GPUs can share one part (one process per GPU; the collectives between
  * the phases are issued by the caller, see longqc_b200/dist.py and INTEGRATION.md):
  *   lqcov_part_sketch        sketch THIS rank's contiguous shard of the part's reads (rid = rid_base + i), count minimizers
- *   lqcov_part_device_views  device pointers of the count table (u32[4^k]: all-reduce SUM) and of the local records
- *   lqcov_part_gather_buffers device buffers for the records of ALL ranks, concatenated in rank order (all-gather target)
+ *   lqcov_part_device_views  device pointers of the count table (u32[4^k]) and of the local records (diagnostics)
+ *   lqcov_part_gather_buffers device buffers for the records of ALL ranks, concatenated in rank order (a caller-driven all-gather;
+ *                            superseded by lqcov_part_exchange, kept for callers that bring their own collectives)
  *   lqcov_part_finish        offsets + stable sort + mid_occ + name tables; `part` describes the WHOLE part
  *                            (n, seq_off for the lengths, names; seq may be NULL)
  *   lqcov_map_part           map this context's queries against the finished part */
@@ -120,6 +122,22 @@ int  lqcov_part_device_views(lqcov_ctx *c, void **counts, uint64_t *n_counts, vo
 int  lqcov_part_gather_buffers(lqcov_ctx *c, uint64_t n_total, void **key, void **y);
 int  lqcov_part_finish(lqcov_ctx *c, const lqcov_reads_t *part);
 int  lqcov_map_part(lqcov_ctx *c);
+/* Several GPUs on one index part (one context per GPU; NCCL over NVLink is loaded on demand, see lq_comm.cu).  The part's reads are
+ * owned by the ranks in contiguous, rank-ordered ranges; every rank sketches its range (lqcov_part_sketch / _begin.._end with
+ * rid_base = position of its first read in the part), then ALL ranks call lqcov_part_exchange: all-reduce of the minimizer counts,
+ * every rank sorts only its own records, the sorted shards are exchanged and placed into the replicated index.  Then
+ * lqcov_part_finish (whole-part metadata) and lqcov_map_part (this rank's queries) as on one GPU.
+ *   lqcov_comm_unique_id   128 opaque bytes made by one rank and handed to the others by the launcher (torchrun: a broadcast)
+ *   lqcov_comm_init_rank   one process per GPU
+ *   lqcov_comm_init_all    one process driving n contexts (the drop-in executable); rank = index in ctxs
+ *   lqcov_comm_gather_rows table rows of all ranks on rank 0, in rank order (*all malloc'ed on rank 0, NULL elsewhere) */
+int  lqcov_comm_unique_id(void *id128);
+int  lqcov_comm_init_rank(lqcov_ctx *c, const void *id128, int nranks, int rank);
+int  lqcov_comm_init_all(lqcov_ctx **ctxs, int n);
+int  lqcov_comm_size(const lqcov_ctx *c);
+int  lqcov_comm_rank(const lqcov_ctx *c);
+int  lqcov_part_exchange(lqcov_ctx *c);
+int  lqcov_comm_gather_rows(lqcov_ctx *c, const char *mine, size_t len, char **all, size_t *all_len);
 /* whole target set in memory: cut into parts exactly as index.c:238-330 does (mini-batch rule) and add each */
 int  lqcov_add_targets(lqcov_ctx *c, const lqcov_reads_t *targets);
 /* the stdout table of minimap2-coverage.c:545-617, one row per query; *buf is malloc'ed (lqcov_free) */

@@ -62,10 +62,11 @@ class Stats(C.Structure):
 
 _lib = None
 
-SYMBOLS = ["lqcov_abi_version", "lqcov_opt_init", "lqcov_create", "lqcov_destroy", "lqcov_reset", "lqcov_part_sketch", "lqcov_part_device_views", "lqcov_part_gather_buffers", "lqcov_part_finish", "lqcov_map_part", "lqcov_profile_enable", "lqcov_profile_reset", "lqcov_profile_json", "lqcov_set_queries", "lqcov_add_part",
+SYMBOLS = ["lqcov_abi_version", "lqcov_device_count", "lqcov_opt_init", "lqcov_create", "lqcov_destroy", "lqcov_reset", "lqcov_part_sketch", "lqcov_part_device_views", "lqcov_part_gather_buffers", "lqcov_part_finish", "lqcov_map_part", "lqcov_profile_enable", "lqcov_profile_reset", "lqcov_profile_json", "lqcov_set_queries", "lqcov_add_part",
            "lqcov_add_targets", "lqcov_table", "lqcov_get_stats", "lqcov_free", "lqcov_sdust_table", "lqcov_sketch",
            "lqcov_debug_seeds", "lqcov_index_part", "lqcov_reader_open", "lqcov_reader_next", "lqcov_reader_next_part",
-           "lqcov_reader_close", "lqcov_main", "lqcov_sdust_main"]
+           "lqcov_reader_close", "lqcov_main", "lqcov_sdust_main", "lqcov_part_begin", "lqcov_stage", "lqcov_part_chunk", "lqcov_stage_wait", "lqcov_part_end",
+           "lqcov_comm_unique_id", "lqcov_comm_init_rank", "lqcov_comm_init_all", "lqcov_comm_size", "lqcov_comm_rank", "lqcov_part_exchange", "lqcov_comm_gather_rows"]
 
 
 def load() -> C.CDLL:

@@ -52,30 +52,13 @@ template <class F> static void parallel_chunks(uint32_t n, unsigned n_chunks, F 
 
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-struct lqcov_ctx {
-    lqcov_opt_t opt;
-    cudaStream_t st;
-    /* queries, host side */
-    uint32_t nq;
-    std::vector<std::string> qname;
-    std::vector<int> qlen;
-    std::vector<double> qsum_p; bool q_has_qual;   /* ordered error-probability sums of the query qualities (device) */
-    /* query names -> query indices: open-address table over (pointer, length) keys, chained for duplicate names */
-    std::vector<int32_t> qn_slot, qn_next; uint32_t qn_mask;
-    std::vector<uint64_t> qfirst;
-    std::vector<lqh_sub_v> ovlp;        /* ovlp_coords (minimap2-coverage.c:438-444) */
-    std::vector<float> avg_k;           /* avg_ks */
-    /* device */
-    LqQueryDev qd; LqIndexDev ix; LqMapScratch sc; LqReadsDev treads; LqMinimizers tmins, full; LqDevBuf ws, qual_dev, qsum_dev; bool use_full;
-    LqPartStream stream; std::vector<char*> stage; size_t stage_bytes; std::vector<cudaEvent_t> stage_ev; double t_part0;
-    /* current part */
-    std::vector<uint32_t> self_off, self_list, qrank, trank;
-    bool part_ready;
-    int32_t mid_occ;
-    lqcov_stats_t stats;
-};
+#include "lq_ctx.h"
+#include "lq_comm.h"
 
 extern "C" int lqcov_abi_version(void) { return LQCOV_ABI_VERSION; }
+extern "C" int lqcov_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
+/* contexts created with an explicit device may be driven from any host thread: every entry point selects the device first */
+#define LQ_USE_DEV(c) do { if ((c)->opt.device >= 0 && cudaSetDevice((c)->opt.device) != cudaSuccess) { fprintf(stderr, "[lqcov] ERROR: cannot select CUDA device %d\n", (c)->opt.device); return -1; } } while (0)
 
 extern "C" void lqcov_opt_init(lqcov_opt_t *o)
 {
@@ -102,7 +85,7 @@ extern "C" lqcov_ctx *lqcov_create(const lqcov_opt_t *o)
     if (o->w < 1 || o->w > LQ_MAX_W) { fprintf(stderr, "[lqcov] ERROR: -w %d outside 1..%d supported by the GPU path\n", o->w, LQ_MAX_W); return 0; }
     if (o->k < 1 || o->k > LQ_MAX_K_DIRECT) { fprintf(stderr, "[lqcov] ERROR: -k %d outside 1..%d supported by the direct-address index of this build\n", o->k, LQ_MAX_K_DIRECT); return 0; }
     lqcov_ctx *c = new lqcov_ctx();
-    c->opt = *o; c->stage_bytes = 0; c->nq = 0; c->q_has_qual = false; c->part_ready = false; c->use_full = false; c->mid_occ = 0;
+    c->opt = *o; c->stage_bytes = 0; c->comm = 0; c->placed = false; c->nq = 0; c->q_has_qual = false; c->part_ready = false; c->use_full = false; c->mid_occ = 0;
     memset(&c->stats, 0, sizeof(c->stats));
     if (cudaStreamCreate(&c->st) != cudaSuccess) { fprintf(stderr, "[lqcov] ERROR: cudaStreamCreate failed\n"); delete c; return 0; }
     return c;
@@ -111,6 +94,7 @@ extern "C" lqcov_ctx *lqcov_create(const lqcov_opt_t *o)
 /* forget everything learnt from previous parts (mid_occ, accumulators); buffers stay allocated */
 extern "C" int lqcov_reset(lqcov_ctx *c)
 {
+    LQ_USE_DEV(c);
     c->mid_occ = 0; c->part_ready = false; c->use_full = false;
     memset(&c->stats, 0, sizeof(c->stats));
     for (size_t i = 0; i < c->ovlp.size(); ++i) { free(c->ovlp[i].a); c->ovlp[i].a = 0; c->ovlp[i].n = c->ovlp[i].m = 0; }
@@ -120,7 +104,9 @@ extern "C" int lqcov_reset(lqcov_ctx *c)
 extern "C" void lqcov_destroy(lqcov_ctx *c)
 {
     if (!c) return;
+    if (c->opt.device >= 0) cudaSetDevice(c->opt.device);
     cudaStreamSynchronize(c->st);
+    lq_comm_release(c);
     for (size_t i = 0; i < c->ovlp.size(); ++i) free(c->ovlp[i].a);
     c->stream.release(); for (size_t i = 0; i < c->stage.size(); ++i) cudaFreeHost(c->stage[i]);
     c->qd.release(); c->ix.release(); c->sc.release(); c->treads.release(); c->tmins.release(); c->full.release(); c->ws.release(); c->qual_dev.release(); c->qsum_dev.release();
@@ -158,6 +144,7 @@ static inline int32_t qnames_find(const lqcov_ctx *c, const char *s, size_t n)
 
 extern "C" int lqcov_set_queries(lqcov_ctx *c, const lqcov_reads_t *q)
 {
+    LQ_USE_DEV(c);
     const double t0 = now_ms();
     c->nq = q->n;
     c->qname.resize(q->n); c->qlen.resize(q->n);
@@ -210,9 +197,10 @@ extern "C" int lqcov_set_queries(lqcov_ctx *c, const lqcov_reads_t *q)
  * lqcov_index_part() is the single-GPU composition. */
 extern "C" int lqcov_part_sketch(lqcov_ctx *c, const lqcov_reads_t *shard, uint32_t rid_base)
 {
+    LQ_USE_DEV(c);
     double t0 = now_ms();
     LqIndexDev *ix = &c->ix;
-    c->part_ready = false; c->use_full = false;
+    c->part_ready = false; c->use_full = false; c->placed = false;
     int piped = 1;
     if (!shard->seq_on_device) {   /* host bases: copy, pack and sketch overlap chunk by chunk where the rolling kernel applies */
         piped = lq_upload_sketch_pipelined(&c->treads, (const uint8_t*)shard->seq, shard->seq_off, shard->n, c->opt.w, c->opt.k, c->opt.is_hpc, rid_base, &ix->rec, c->ws, c->st);
@@ -237,15 +225,17 @@ extern "C" int lqcov_part_sketch(lqcov_ctx *c, const lqcov_reads_t *shard, uint3
 /* ---- the same, with the shard arriving in chunks from pinned staging buffers while the caller's reader threads parse the file ---- */
 extern "C" int lqcov_part_begin(lqcov_ctx *c, uint64_t expect_bases, uint32_t rid_base)
 {
+    LQ_USE_DEV(c);
     if (!lq_stream_ok(c->opt.w, c->opt.k, c->opt.is_hpc)) return 1;   /* not applicable: hand the whole part to lqcov_part_sketch */
     c->t_part0 = now_ms();
-    c->part_ready = false; c->use_full = false;
+    c->part_ready = false; c->use_full = false; c->placed = false;
     LQ_TRY(lq_stream_begin(&c->stream, &c->treads, &c->ix.rec, c->opt.w, c->opt.k, rid_base, expect_bases, c->st));
     return 0;
 }
 
 extern "C" int lqcov_stage(lqcov_ctx *c, int n, size_t bytes, char **bufs)
 {
+    LQ_USE_DEV(c);
     if ((int)c->stage.size() != n || c->stage_bytes != bytes) {
         for (size_t i = 0; i < c->stage.size(); ++i) cudaFreeHost(c->stage[i]);
         c->stage.assign((size_t)n, (char*)0); c->stage_ev.assign((size_t)n, (cudaEvent_t)0); c->stage_bytes = bytes;
@@ -257,6 +247,7 @@ extern "C" int lqcov_stage(lqcov_ctx *c, int n, size_t bytes, char **bufs)
 
 extern "C" int lqcov_part_chunk(lqcov_ctx *c, const lqcov_reads_t *chunk, int stage_index)
 {
+    LQ_USE_DEV(c);
     cudaEvent_t ev = 0;
     LQ_TRY(lq_stream_push(&c->stream, (const uint8_t*)chunk->seq, chunk->seq_off, chunk->n, &ev));
     if (stage_index >= 0 && stage_index < (int)c->stage_ev.size()) c->stage_ev[stage_index] = ev;
@@ -265,6 +256,7 @@ extern "C" int lqcov_part_chunk(lqcov_ctx *c, const lqcov_reads_t *chunk, int st
 
 extern "C" int lqcov_stage_wait(lqcov_ctx *c, int stage_index)
 {
+    LQ_USE_DEV(c);
     if (stage_index >= 0 && stage_index < (int)c->stage_ev.size() && c->stage_ev[stage_index]) {
         LQ_CUDA_OK(cudaEventSynchronize(c->stage_ev[stage_index]));   /* the event may have been re-recorded by a later chunk: waiting longer is harmless */
         c->stage_ev[stage_index] = 0;
@@ -274,6 +266,7 @@ extern "C" int lqcov_stage_wait(lqcov_ctx *c, int stage_index)
 
 extern "C" int lqcov_part_end(lqcov_ctx *c)
 {
+    LQ_USE_DEV(c);
     LqIndexDev *ix = &c->ix;
     LQ_TRY(lq_stream_end(&c->stream, c->ws));
     c->stats.t_sketch_ms += now_ms() - c->t_part0;
@@ -337,7 +330,8 @@ static int part_finish_device(lqcov_ctx *c, const lqcov_reads_t *part)
 {
     LqIndexDev *ix = &c->ix;
     if (c->use_full) { std::swap(ix->rec.key, c->full.key); std::swap(ix->rec.y, c->full.y); ix->rec.n = c->full.n; ix->rec.has_span = 0; c->use_full = false; }
-    LQ_TRY(lq_index_finish(ix, &ix->rec, c->ws, c->st));
+    if (c->placed) c->placed = false;                      /* lqcov_part_exchange left offsets and positions of the replicated index in place */
+    else LQ_TRY(lq_index_finish(ix, &ix->rec, c->ws, c->st));
     ix->n_seq = part->n;
     LQ_TRY(ix->tlen.ensure(((size_t)part->n + 1) * 4));
     {
@@ -358,6 +352,7 @@ static int part_finish_device(lqcov_ctx *c, const lqcov_reads_t *part)
 
 extern "C" int lqcov_part_finish(lqcov_ctx *c, const lqcov_reads_t *part)
 {
+    LQ_USE_DEV(c);
     const double t0 = now_ms();
     /* the name tables are host-only work: built on a second thread while the device sorts the records */
     std::future<void> names = std::async(std::launch::async, build_name_tables, c, part);
@@ -391,6 +386,7 @@ static void map_opt_of(const lqcov_opt_t *o, LqMapOpt *m)
 
 extern "C" int lqcov_map_part(lqcov_ctx *c)
 {
+    LQ_USE_DEV(c);
     if (!c->part_ready) { fprintf(stderr, "[lqcov] ERROR: lqcov_map_part without an index part\n"); return -1; }
     if (c->nq == 0) return 0;
     double t0 = now_ms();
@@ -452,6 +448,7 @@ extern "C" int lqcov_add_targets(lqcov_ctx *c, const lqcov_reads_t *t)
 
 extern "C" int lqcov_table(lqcov_ctx *c, char **buf, size_t *len)
 {
+    LQ_USE_DEV(c);
     const double t0 = now_ms();
     std::vector<uint32_t> n_match; std::vector<uint64_t> lam(c->nq), lam2(c->nq);
     LQ_TRY(lq_map_nmatch(&c->qd, &n_match, c->st));
@@ -516,6 +513,7 @@ extern "C" int lqcov_sketch(const lqcov_opt_t *o, const lqcov_reads_t *reads, ui
 
 extern "C" int lqcov_debug_seeds(lqcov_ctx *c, uint32_t q, uint64_t **ux, uint64_t **uy, uint64_t **sx, uint64_t **sy, uint64_t *n)
 {
+    LQ_USE_DEV(c);
     if (!c->part_ready || q >= c->nq) return -1;
     LqMapOpt mo; map_opt_of(&c->opt, &mo);
     std::vector<lq_mm128> u, s;

@@ -113,25 +113,71 @@ static double g_t0;
 static double wall(void) { struct timeval t; gettimeofday(&t, 0); return t.tv_sec + t.tv_usec * 1e-6; }
 static double cpu(void) { struct rusage r; getrusage(RUSAGE_SELF, &r); return r.ru_utime.tv_sec + r.ru_stime.tv_sec + 1e-6 * (r.ru_utime.tv_usec + r.ru_stime.tv_usec); }
 
-/* ---- the part loop: index parts arrive in chunks of consecutive reads (lq_ingest.c), the device copies, packs and sketches chunk i
- *      while the reader threads fill chunk i+1 (replaces kt_pipeline's read -> sketch -> dispatch stages, index.c:238-309) ---- */
+/* ---- the part loop: index parts arrive in chunks of consecutive reads (lq_ingest.c); the device copies, packs and sketches chunk i
+ *      while the reader threads fill chunk i+1 (replaces kt_pipeline's read -> sketch -> dispatch stages, index.c:238-309).
+ *      With several visible GPUs the executable drives them all from this one process (one context and one host thread per GPU,
+ *      NCCL communicator inside the library): a part's reads go to the GPUs in contiguous ranges, the queries are split, every GPU
+ *      maps its share against the replicated index and the rows are concatenated in GPU order. ---- */
 #define CLI_NSTAGE 4
 #define CLI_STAGE_BYTES ((size_t)16 << 20)
+#define CLI_MAX_DEV 16
 
-struct init_job { const lqcov_opt_t *o; lqcov_ctx *c; char *stage[CLI_NSTAGE]; int rc; };
-static void *init_thread(void *p)       /* the CUDA context: hundreds of ms, during which the reader threads already parse */
+typedef struct {
+    int dev, n_dev, rc;
+    lqcov_opt_t o; lqcov_ctx *c; char *stage[CLI_NSTAGE];
+    lqcov_reads_t q;                     /* this GPU's share of the queries */
+    const lqcov_reads_t *part;           /* whole-part metadata for the finish step */
+    int chunks, begun;
+    char *tab; size_t tab_len;
+    double t0;
+} cli_dev;
+
+static void *dev_create(void *p)         /* the CUDA context: hundreds of ms, during which the reader threads already parse */
 {
-    struct init_job *j = (struct init_job*)p;
-    j->c = lqcov_create(j->o);
+    cli_dev *d = (cli_dev*)p;
+    d->c = lqcov_create(&d->o);
+    d->rc = d->c ? 0 : 1;
     TL("CUDA context + stream created");
     return 0;
 }
-static void *stage_thread(void *p)      /* page-locking the staging buffers runs beside the query sketch */
+static void *dev_stage(void *p)          /* page-locking the staging buffers runs beside the query sketch */
 {
-    struct init_job *j = (struct init_job*)p;
-    j->rc = lqcov_stage(j->c, CLI_NSTAGE, CLI_STAGE_BYTES, j->stage);
-    TL("pinned staging buffers allocated");
+    cli_dev *d = (cli_dev*)p;
+    if (lqcov_stage(d->c, CLI_NSTAGE, CLI_STAGE_BYTES, d->stage) != 0) d->rc = 1;
     return 0;
+}
+static void *dev_queries(void *p)
+{
+    cli_dev *d = (cli_dev*)p;
+    if (lqcov_set_queries(d->c, &d->q) != 0) d->rc = 1;
+    return 0;
+}
+static void *dev_finish_part(void *p)    /* everything behind the last chunk: count, exchange, replicated index, mapping */
+{
+    cli_dev *d = (cli_dev*)p;
+    if (lqcov_part_end(d->c) != 0) { d->rc = 1; return 0; }
+    if (d->dev == 0) TL("part sketched + counted");
+    if (d->n_dev > 1 && lqcov_part_exchange(d->c) != 0) { d->rc = 1; return 0; }
+    if (d->part->n == 0) return 0;       /* an empty part (a rejected record closed it): nothing to map against */
+    if (lqcov_part_finish(d->c, d->part) != 0) { d->rc = 1; return 0; }
+    if (d->dev == 0) fprintf(stderr, "[M::%s::%.3f*%.2f] indexed %u target sequence(s)\n", __func__, wall() - d->t0, cpu() / (wall() - d->t0), d->part->n);
+    if (lqcov_map_part(d->c) != 0) d->rc = 1;
+    return 0;
+}
+static void *dev_table(void *p)
+{
+    cli_dev *d = (cli_dev*)p;
+    if (lqcov_table(d->c, &d->tab, &d->tab_len) != 0) d->rc = 1;
+    return 0;
+}
+/* fn on every device, one thread each; returns non-zero when any failed */
+static int on_all(cli_dev *dv, int n, void *(*fn)(void*))
+{
+    pthread_t th[CLI_MAX_DEV]; int rc = 0;
+    if (n == 1) { fn(&dv[0]); return dv[0].rc; }
+    for (int i = 0; i < n; ++i) pthread_create(&th[i], 0, fn, &dv[i]);
+    for (int i = 0; i < n; ++i) { pthread_join(th[i], 0); rc |= dv[i].rc; }
+    return rc;
 }
 
 static int reader_threads(int t_opt)
@@ -157,39 +203,66 @@ static void meta_add(part_meta *pm, const lqi_chunk *ch)
     pm->n += ch->n; pm->nn += ch->name_off[ch->n];
 }
 
-static int run_parts(lqcov_ctx *c, lqi_reader *tr, const lqcov_opt_t *o, char **stage, double t0)
+/* configurations without a chunked form (-H: the spike-in run, a 4 kb target): one GPU, whole parts */
+static int run_parts_whole(cli_dev *d, lqi_reader *tr, const lqcov_opt_t *o, double t0)
+{
+    part_meta pm; memset(&pm, 0, sizeof pm);
+    int rc = 0, eof = 0;
+    char *whole = 0; size_t whole_cap = 0;
+    lqi_part_rule(tr, o->batch_size, o->mini_batch_size);
+    while (rc == 0 && !eof) {
+        size_t whole_n = 0; int part_end = 0;
+        pm.n = 0; pm.nn = 0;
+        while (!part_end && !eof) {
+            lqi_chunk ch; int r;
+            if (whole_cap - whole_n < CLI_STAGE_BYTES) { whole_cap = whole_cap ? whole_cap * 2 : 4 * CLI_STAGE_BYTES; whole = (char*)realloc(whole, whole_cap); }
+            r = lqi_next_chunk(tr, whole_cap - whole_n, whole + whole_n, 0, &ch);
+            if (r == -2) { whole_cap = whole_n + ch.need + CLI_STAGE_BYTES; whole = (char*)realloc(whole, whole_cap); continue; }
+            part_end = ch.part_end; eof = ch.eof;
+            if (r <= 0) continue;
+            meta_add(&pm, &ch);
+            whole_n += ch.n_bases;
+        }
+        if (pm.n > 0) {
+            lqcov_reads_t part; memset(&part, 0, sizeof part);
+            part.n = (uint32_t)pm.n; part.seq = whole; part.seq_off = pm.seq_off; part.names = pm.names; part.name_off = pm.name_off;
+            if (lqcov_add_part(d->c, &part) != 0) rc = 1;
+            fprintf(stderr, "[M::%s::%.3f*%.2f] mapped against part of %u sequence(s)\n", __func__, wall() - t0, cpu() / (wall() - t0), part.n);
+        }
+    }
+    free(whole); free(pm.seq_off); free(pm.name_off); free(pm.names);
+    return rc;
+}
+
+static int run_parts(cli_dev *dv, int n_dev, lqi_reader *tr, const lqcov_opt_t *o, double t0)
 {
     part_meta pm; memset(&pm, 0, sizeof pm);
     int rc = 0, eof = 0;
     lqi_part_rule(tr, o->batch_size, o->mini_batch_size);
     while (rc == 0 && !eof) {
         uint64_t expect = lqi_bases_left_bound(tr);           /* first sizing of the device arrays; they grow if the part turns out larger */
+        int cur = 0, part_end = 0; uint64_t pb = 0;
+        lqcov_reads_t part;
         if (expect > o->batch_size + 2 * (uint64_t)o->mini_batch_size) expect = o->batch_size + 2 * (uint64_t)o->mini_batch_size;
-        const int streamed = lqcov_part_begin(c, expect, 0);
-        TL("part begun (device arrays sized)");  /* 1: no chunked form for this configuration (-H): whole part at once */
-        char *whole = 0; size_t whole_cap = 0, whole_n = 0;
-        int i = 0, part_end = 0;
-        if (streamed < 0) { rc = 1; break; }
         pm.n = 0; pm.nn = 0;
+        for (int i = 0; i < n_dev; ++i) { dv[i].begun = 0; dv[i].chunks = 0; }
         while (rc == 0 && !part_end && !eof) {
-            lqi_chunk ch; int r;
-            char *dst; size_t cap;
-            if (streamed == 0) { lqcov_stage_wait(c, i % CLI_NSTAGE); dst = stage[i % CLI_NSTAGE]; cap = CLI_STAGE_BYTES; }
-            else {
-                if (whole_cap - whole_n < CLI_STAGE_BYTES) { whole_cap = whole_cap ? whole_cap * 2 : 4 * CLI_STAGE_BYTES; whole = (char*)realloc(whole, whole_cap); }
-                dst = whole + whole_n; cap = whole_cap - whole_n;
-            }
-            r = lqi_next_chunk(tr, cap, dst, 0, &ch);
-            if (r == -2) {                                    /* a read longer than a staging buffer */
-                if (streamed != 0) { whole_cap = whole_n + ch.need + CLI_STAGE_BYTES; whole = (char*)realloc(whole, whole_cap); continue; }
-                /* through pageable memory: cudaMemcpyAsync returns once a pageable source has been staged, so `big` can be freed at once */
-                char *big = (char*)malloc(ch.need + 1);
+            lqi_chunk ch; int r; cli_dev *d;
+            lqcov_reads_t cr;
+            /* GPU `cur` owns the reads until the part's bases pass its share of the expected total */
+            while (cur < n_dev - 1 && expect && pb >= expect / (uint64_t)n_dev * (uint64_t)(cur + 1)) ++cur;
+            d = &dv[cur];
+            if (!d->begun) { if (lqcov_part_begin(d->c, expect / (uint64_t)n_dev + (expect >> 4), (uint32_t)pm.n) != 0) { rc = 1; break; } d->begun = 1; if (cur == 0) TL("part begun (device arrays sized)"); }
+            lqcov_stage_wait(d->c, d->chunks % CLI_NSTAGE);
+            r = lqi_next_chunk(tr, CLI_STAGE_BYTES, d->stage[d->chunks % CLI_NSTAGE], 0, &ch);
+            memset(&cr, 0, sizeof cr);
+            if (r == -2) {                                    /* a read longer than a staging buffer: through pageable memory */
+                char *big = (char*)malloc(ch.need + 1);       /* (cudaMemcpyAsync returns once a pageable source has been staged: freed at once) */
                 r = lqi_next_chunk(tr, ch.need, big, 0, &ch);
                 if (r == 1) {
-                    lqcov_reads_t cr; memset(&cr, 0, sizeof cr);
                     cr.n = ch.n; cr.seq = big; cr.seq_off = ch.seq_off; cr.names = ch.names; cr.name_off = ch.name_off;
-                    meta_add(&pm, &ch);
-                    if (lqcov_part_chunk(c, &cr, -1) != 0) rc = 1;
+                    meta_add(&pm, &ch); pb += ch.n_bases;
+                    if (lqcov_part_chunk(d->c, &cr, -1) != 0) rc = 1;
                 }
                 free(big);
                 part_end = ch.part_end; eof = ch.eof;
@@ -197,36 +270,35 @@ static int run_parts(lqcov_ctx *c, lqi_reader *tr, const lqcov_opt_t *o, char **
             }
             part_end = ch.part_end; eof = ch.eof;
             if (r <= 0) continue;
-            meta_add(&pm, &ch);
-            if (streamed == 0) {
-                lqcov_reads_t cr; memset(&cr, 0, sizeof cr);
-                cr.n = ch.n; cr.seq = dst; cr.seq_off = ch.seq_off; cr.names = ch.names; cr.name_off = ch.name_off;
-                if (lqcov_part_chunk(c, &cr, i % CLI_NSTAGE) != 0) rc = 1;
-                ++i;
-            } else whole_n += ch.n_bases;
+            meta_add(&pm, &ch); pb += ch.n_bases;
+            cr.n = ch.n; cr.seq = d->stage[d->chunks % CLI_NSTAGE]; cr.seq_off = ch.seq_off; cr.names = ch.names; cr.name_off = ch.name_off;
+            if (lqcov_part_chunk(d->c, &cr, d->chunks % CLI_NSTAGE) != 0) rc = 1;
+            ++d->chunks;
         }
-        if (rc == 0 && pm.n > 0) {
-            lqcov_reads_t part; memset(&part, 0, sizeof part);
-            part.n = (uint32_t)pm.n; part.seq_off = pm.seq_off; part.names = pm.names; part.name_off = pm.name_off;
-            if (streamed == 0) {
-                TL("part parsed, all chunks queued");
-                if (lqcov_part_end(c) != 0) rc = 1;
-                TL("part sketched + counted");
-                if (rc == 0 && lqcov_part_finish(c, &part) != 0) rc = 1;
-                fprintf(stderr, "[M::%s::%.3f*%.2f] indexed %u target sequence(s)\n", __func__, wall() - t0, cpu() / (wall() - t0), part.n);
-                if (rc == 0 && lqcov_map_part(c) != 0) rc = 1;
-            } else {
-                part.seq = whole;
-                if (lqcov_add_part(c, &part) != 0) rc = 1;
-            }
-            fprintf(stderr, "[M::%s::%.3f*%.2f] mapped against part of %u sequence(s)\n", __func__, wall() - t0, cpu() / (wall() - t0), part.n);
-        } else if (rc == 0 && streamed == 0) {
-            if (lqcov_part_end(c) != 0) rc = 1;               /* an empty part (a rejected record closed it): nothing to map against */
-        }
-        free(whole);
+        if (rc != 0) break;
+        TL("part parsed, all chunks queued");
+        for (int i = 0; i < n_dev; ++i)                        /* GPUs that got nothing of this part still take part in the exchange */
+            if (!dv[i].begun) { if (lqcov_part_begin(dv[i].c, 0, (uint32_t)pm.n) != 0) rc = 1; dv[i].begun = 1; }
+        memset(&part, 0, sizeof part);
+        if (pm.n == 0) { pm.m = pm.m ? pm.m : 4; if (!pm.seq_off) { pm.seq_off = (uint64_t*)calloc(pm.m, 8); pm.name_off = (uint64_t*)calloc(pm.m, 8); pm.names = (char*)calloc(4, 1); pm.nm = 4; } pm.seq_off[0] = pm.name_off[0] = 0; }
+        part.n = (uint32_t)pm.n; part.seq_off = pm.seq_off; part.names = pm.names; part.name_off = pm.name_off;
+        for (int i = 0; i < n_dev; ++i) { dv[i].part = &part; dv[i].t0 = t0; }
+        if (rc == 0 && on_all(dv, n_dev, dev_finish_part) != 0) rc = 1;
+        if (pm.n > 0) fprintf(stderr, "[M::%s::%.3f*%.2f] mapped against part of %u sequence(s)\n", __func__, wall() - t0, cpu() / (wall() - t0), part.n);
     }
     free(pm.seq_off); free(pm.name_off); free(pm.names);
     return rc;
+}
+
+/* GPUs this run drives: all visible ones (LQCOV_GPUS limits), one for jobs that do not shard (-H) */
+static int pick_devices(const lqcov_opt_t *o)
+{
+    int n = lqcov_device_count();
+    const char *e = getenv("LQCOV_GPUS");
+    if (e && atoi(e) > 0 && atoi(e) < n) n = atoi(e);
+    if (n > CLI_MAX_DEV) n = CLI_MAX_DEV;
+    if (o->is_hpc || n < 1) n = 1;
+    return n;
 }
 
 int lqcov_main(int argc, char **argv)
@@ -271,38 +343,46 @@ int lqcov_main(int argc, char **argv)
     fprintf(stderr, "max-overhang %d, min-overlaplen %d, min-overapratio %.2f\n", o.max_overhang, o.min_ovlp, o.min_ratio);
     fprintf(stderr, "num of threads %d, num of query seqs %d\n===\n", o.n_threads, a.n_subset);
 
-    /* The CUDA context (a few hundred ms) is created on a second thread while the reader threads already parse the inputs. */
-    struct init_job ij; pthread_t ith;
-    memset(&ij, 0, sizeof ij); ij.o = &o;
-    pthread_create(&ith, 0, init_thread, &ij);
+    /* The CUDA contexts (hundreds of ms each) are created on their own threads while the reader threads already parse the inputs. */
+    cli_dev dv[CLI_MAX_DEV]; pthread_t cth[CLI_MAX_DEV];
+    const int n_dev = pick_devices(&o);
+    memset(dv, 0, sizeof dv);
+    for (int i = 0; i < n_dev; ++i) { dv[i].dev = i; dv[i].n_dev = n_dev; dv[i].o = o; dv[i].o.device = n_dev > 1 ? i : -1; pthread_create(&cth[i], 0, dev_create, &dv[i]); }
     const int n_rd = reader_threads(o.n_threads);
     lqi_reader *tr = lqi_open(a.args[0], n_rd);
     lqcov_reader *qr = tr ? lqcov_reader_open(a.args[1]) : 0;
     lqcov_reads_t q; memset(&q, 0, sizeof q);
     if (qr) lqcov_reader_next(qr, 0, &q);                     /* one kseq_read loop over the query file (minimap2-coverage.c:418) */
     TL("queries parsed");
-    pthread_join(ith, 0);
-    lqcov_ctx *c = ij.c;
+    int rc = 0;
+    for (int i = 0; i < n_dev; ++i) { pthread_join(cth[i], 0); rc |= dv[i].rc; }
     if (!tr) fprintf(stderr, "ERROR: failed to open file '%s'\n", a.args[0]);
     else if (!qr) fprintf(stderr, "ERROR: failed to open file '%s'\n", a.args[1]);
-    if (!tr || !qr || !c) { if (tr) lqi_close(tr); if (qr) lqcov_reader_close(qr); if (c) lqcov_destroy(c); return 1; }
-    int rc = 0;
-    pthread_create(&ith, 0, stage_thread, &ij);
-    if (lqcov_set_queries(c, &q) != 0) rc = 1;
-    pthread_join(ith, 0);
-    if (ij.rc != 0) rc = 1;
-    TL("queries sketched");
-    fprintf(stderr, "[M::%s::%.3f*%.2f] loaded %u sequence(s).\n", __func__, wall() - t0, cpu() / (wall() - t0), q.n);
-    lqcov_reader_close(qr);
-    if (rc == 0) rc = run_parts(c, tr, &o, ij.stage, t0);
-    lqi_close(tr);
-    if (rc == 0) {
-        char *tab = 0; size_t len = 0;
-        if (lqcov_table(c, &tab, &len) != 0) rc = 1;
-        else { fwrite(tab, 1, len, stdout); fflush(stdout); lqcov_free(tab); }
+    if (!tr || !qr || rc) { if (tr) lqi_close(tr); if (qr) lqcov_reader_close(qr); for (int i = 0; i < n_dev; ++i) if (dv[i].c) lqcov_destroy(dv[i].c); return 1; }
+    if (n_dev > 1) {
+        lqcov_ctx *cs[CLI_MAX_DEV];
+        for (int i = 0; i < n_dev; ++i) cs[i] = dv[i].c;
+        if (lqcov_comm_init_all(cs, n_dev) != 0) rc = 1;
+        fprintf(stderr, "[M::%s] %d GPUs: targets sharded for sketching, minimizer counts all-reduced, index replicated, queries split\n", __func__, n_dev);
     }
+    /* staging buffers are page-locked beside the query sketch; GPU i takes queries [nq*i/n, nq*(i+1)/n) */
+    for (int i = 0; i < n_dev; ++i) pthread_create(&cth[i], 0, dev_stage, &dv[i]);
+    for (int i = 0; i < n_dev; ++i) {
+        const uint32_t lo = (uint32_t)((uint64_t)q.n * i / n_dev), hi = (uint32_t)((uint64_t)q.n * (i + 1) / n_dev);
+        dv[i].q = q; dv[i].q.n = hi - lo; dv[i].q.seq_off = q.seq_off + lo; dv[i].q.name_off = q.name_off + lo;
+    }
+    { cli_dev qd[CLI_MAX_DEV]; for (int i = 0; i < n_dev; ++i) { qd[i] = dv[i]; qd[i].rc = 0; } if (rc == 0 && on_all(qd, n_dev, dev_queries) != 0) rc = 1; }
+    for (int i = 0; i < n_dev; ++i) { pthread_join(cth[i], 0); rc |= dv[i].rc; }
+    TL("queries sketched, staging buffers allocated");
+    fprintf(stderr, "[M::%s::%.3f*%.2f] loaded %u sequence(s).\n", __func__, wall() - t0, cpu() / (wall() - t0), q.n);
+    if (rc == 0) rc = lqcov_part_begin(dv[0].c, 0, 0) == 1 ? run_parts_whole(&dv[0], tr, &o, t0) : run_parts(dv, n_dev, tr, &o, t0);
+    lqi_close(tr);
+    if (rc == 0 && on_all(dv, n_dev, dev_table) != 0) rc = 1;
+    if (rc == 0) for (int i = 0; i < n_dev; ++i) { fwrite(dv[i].tab, 1, dv[i].tab_len, stdout); lqcov_free(dv[i].tab); }
+    fflush(stdout);
+    lqcov_reader_close(qr);
     TL("table written");
-    if (!getenv("LQCOV_FAST_EXIT")) lqcov_destroy(c);
+    if (!getenv("LQCOV_FAST_EXIT")) for (int i = 0; i < n_dev; ++i) lqcov_destroy(dv[i].c);
     fprintf(stderr, "\n[M::%s] Real time: %.3f sec; CPU: %.3f sec\n", __func__, wall() - t0, cpu());
     return rc;
 }

@@ -1,13 +1,13 @@
-"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink) for the exchange step.
+"""Multi-GPU plumbing: one process per GPU; torch.distributed only hands the NCCL id around, the exchange step runs in liblqcov.so.
 
 How one index part is shared by N GPUs:
   * the part's reads are owned by the ranks in contiguous, rank-ordered ranges, so rid == position in
     the part and the concatenation of the ranks' minimizer records is already ordered by y;
   * every rank packs + sketches its own reads and counts its minimizers (lqcov_part_sketch);
-  * ALL-REDUCE (sum) of the per-minimizer count table -- the one collective the method needs: the
-    counts decide mid_occ (index.c:123-144) and the high-frequency filter (lqmap.c:159,166);
-  * the (key, y) records are replicated in rank order (N broadcasts into one buffer = an all-gather
-    with uneven shards) and every rank builds the same index (lqcov_part_finish);
+  * lqcov_part_exchange (lq_comm.cu, NCCL inside the C library): ALL-REDUCE (sum) of the per-minimizer
+    count table -- the counts decide mid_occ (index.c:123-144) and the high-frequency filter
+    (lqmap.c:159,166) --, every rank sorts only its own records by key, the sorted shards are exchanged
+    and placed into the replicated index (slot = global offset + occurrences on lower ranks + own rank);
   * the queries are split across the ranks, each rank maps its share against every part
     (lqcov_map_part) and rank 0 concatenates the rows in query order.
 Parts follow the reference's mini-batch rule on the GLOBAL read list (index.c:238-246).
@@ -94,15 +94,38 @@ def _sub_struct(keep, a: int, b: int, seq_ptr, on_device: int):
     return st
 
 
+def comm_init(cov, rank: int, world: int):
+    """NCCL communicator of the C library (lq_comm.cu) for this rank's context: rank 0 makes the 128-byte id, the launcher's
+    process group (torch.distributed: plumbing only) hands it to the other ranks.  All data-path collectives then run inside
+    liblqcov.so (lqcov_part_exchange, lqcov_comm_gather_rows)."""
+    if world == 1:
+        return
+    import torch
+    import torch.distributed as dist
+    lib = _lib.load()
+    lib.lqcov_comm_unique_id.argtypes = [C.c_void_p]
+    lib.lqcov_comm_init_rank.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    buf = C.create_string_buffer(128)
+    if rank == 0 and lib.lqcov_comm_unique_id(buf) != 0:
+        raise _lib.LqcovError("lqcov_comm_unique_id failed")
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0)
+    ident = bytes(t.cpu().tolist())
+    if lib.lqcov_comm_init_rank(cov._h, ident, world, rank) != 0:
+        raise _lib.LqcovError("lqcov_comm_init_rank failed")
+
+
 def run_job(cov, t_keep, n_my_targets, my_lo, parts, part_meta, q_keep, n_my_queries, tptr, qptr, on_device, rank, world, exchange=None):
     """One coverage job of this rank: its queries against every index part; targets [my_lo, my_lo+n_my_targets) of the global
-    read list are this rank's to sketch.  Returns the table (all ranks' rows on rank 0 when world > 1)."""
+    read list are this rank's to sketch.  Returns the table (all ranks' rows on rank 0 when world > 1).  The context must have a
+    communicator (comm_init) when world > 1."""
     lib = _lib.load()
     lib.lqcov_part_sketch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     lib.lqcov_part_finish.argtypes = [C.c_void_p, C.c_void_p]
     lib.lqcov_map_part.argtypes = [C.c_void_p]
-    lib.lqcov_part_device_views.argtypes = [C.c_void_p] + [C.c_void_p] * 5
-    lib.lqcov_part_gather_buffers.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.lqcov_part_exchange.argtypes = [C.c_void_p]
+    lib.lqcov_comm_gather_rows.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     h = cov._h
     lib.lqcov_reset(h)
     qs = _sub_struct(q_keep, 0, n_my_queries, qptr, on_device)
@@ -117,48 +140,22 @@ def run_job(cov, t_keep, n_my_targets, my_lo, parts, part_meta, q_keep, n_my_que
         sub = _sub_struct(t_keep, a - my_lo, b - my_lo, tptr, on_device)
         if lib.lqcov_part_sketch(h, C.byref(sub), a - s if b > a else 0) != 0:
             raise _lib.LqcovError("lqcov_part_sketch failed")
-        if world > 1:
-            exchange(lib, h)
+        if world > 1 and lib.lqcov_part_exchange(h) != 0:   # all-reduce of the counts, own shard sorted, shards exchanged + placed
+            raise _lib.LqcovError("lqcov_part_exchange failed")
         if lib.lqcov_part_finish(h, C.byref(meta.st)) != 0:
             raise _lib.LqcovError("lqcov_part_finish failed")
         if lib.lqcov_map_part(h) != 0:
             raise _lib.LqcovError("lqcov_map_part failed")
     table = cov.table()
     if world > 1:
-        import torch.distributed as dist
-        rows = [None] * world if rank == 0 else None
-        dist.gather_object(table, rows, dst=0)
+        out, n = C.c_void_p(), C.c_size_t()
+        if lib.lqcov_comm_gather_rows(h, table, len(table), C.byref(out), C.byref(n)) != 0:
+            raise _lib.LqcovError("lqcov_comm_gather_rows failed")
         if rank == 0:
-            table = b"".join(rows)
+            table = C.string_at(out.value, n.value)
+        if out.value:
+            lib.lqcov_free(out)
     return table
-
-
-def exchange_part(lib, h, rank, world):
-    """all-reduce of the minimizer counts + rank-ordered replication of the records (see module docstring)"""
-    import torch
-    import torch.distributed as dist
-    counts, nc, key, y, n = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_void_p(), C.c_uint64()
-    lib.lqcov_part_device_views(h, C.byref(counts), C.byref(nc), C.byref(key), C.byref(y), C.byref(n))
-    tc = _view(counts.value, nc.value, "<i4")
-    dist.all_reduce(tc)                                   # the minimizer-count all-reduce
-    sizes = torch.zeros(world, dtype=torch.int64, device="cuda")
-    sizes[rank] = n.value
-    dist.all_reduce(sizes)
-    sizes = sizes.tolist()
-    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-    fk, fy = C.c_void_p(), C.c_void_p()
-    if lib.lqcov_part_gather_buffers(h, int(offs[-1]), C.byref(fk), C.byref(fy)) != 0:
-        raise _lib.LqcovError("lqcov_part_gather_buffers failed")
-    full_k = _view(fk.value, max(int(offs[-1]), 1), "<i4")
-    full_y = _view(fy.value, max(int(offs[-1]), 1), "<i8")
-    if n.value:
-        full_k[offs[rank]:offs[rank + 1]].copy_(_view(key.value, n.value, "<i4"))
-        full_y[offs[rank]:offs[rank + 1]].copy_(_view(y.value, n.value, "<i8"))
-    for r in range(world):                                # index replication: rank-ordered all-gather
-        if sizes[r]:
-            dist.broadcast(full_k[offs[r]:offs[r + 1]], src=r)
-            dist.broadcast(full_y[offs[r]:offs[r + 1]], src=r)
-    torch.cuda.synchronize()
 
 
 def rank_inputs(a, rank: int, world: int):
@@ -217,6 +214,7 @@ class Runner:
         self.q_dev = self.q_pin.cuda()
         torch.cuda.synchronize()
         self.cov = _lib.Coverage(self.opt)
+        comm_init(self.cov, rank, world)
         return self.targets, self.queries
 
     def job_bases(self):
@@ -225,19 +223,64 @@ class Runner:
     def parallelism(self):
         if self.world == 1:
             return "1 GPU"
-        return "%d GPUs: targets sharded for sketch+count, NCCL all-reduce of the 4^k count table, index replicated (records broadcast in rank order), queries sharded" % self.world
-
-    def _exchange(self, lib, h):
-        exchange_part(lib, h, self.rank, self.world)
+        return ("%d GPUs: targets sharded for sketch + count + sort, NCCL all-reduce of the 4^k count table, key-sorted shards exchanged and placed into "
+                "the replicated index (lqcov_part_exchange, NCCL inside liblqcov.so), queries sharded" % self.world)
 
     def step(self, resident: bool):
         tptr = self.t_dev.data_ptr() if resident else self.t_pin.data_ptr()
         qptr = self.q_dev.data_ptr() if resident else self.q_pin.data_ptr()
         table = run_job(self.cov, self.t_keep, self.targets.n, self.rank * self.a.reads, self.parts, self.part_meta, self.q_keep, self.queries.n,
-                        tptr, qptr, 1 if resident else 0, self.rank, self.world, exchange=self._exchange)
+                        tptr, qptr, 1 if resident else 0, self.rank, self.world)
         self.last_stats = self.cov.stats()
         self.last_table = table
         return table
+
+    def verify_against_one_gpu(self):
+        """N > 1: rank 0 runs the WHOLE job (every rank's targets in one index, all queries) on its own GPU alone and compares the
+        table with the merged table of the N-GPU job.  Untimed.  The other ranks only ship their reads (a padded gather)."""
+        import torch
+        import torch.distributed as dist
+        world, rank = self.world, self.rank
+        if world == 1:
+            return None
+
+        def gather_bytes(arr):
+            n = torch.tensor([arr.size], dtype=torch.int64, device="cuda")
+            sizes = [torch.zeros_like(n) for _ in range(world)]
+            dist.all_gather(sizes, n)
+            sizes = [int(x.item()) for x in sizes]
+            pad = torch.zeros(max(sizes), dtype=torch.uint8, device="cuda")
+            pad[:arr.size] = torch.from_numpy(arr).cuda()
+            out = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+            dist.gather(pad, out, dst=0)
+            return [o[:sz].cpu().numpy() for o, sz in zip(out, sizes)] if rank == 0 else None
+
+        def gather_set(rs):
+            seqs = gather_bytes(np.ascontiguousarray(rs.seq))
+            quals = gather_bytes(np.ascontiguousarray(rs.qual)) if rs.qual is not None else None
+            lens = gather_bytes(np.ascontiguousarray(rs.lengths().astype(np.int64)).view(np.uint8))
+            names = [None] * world if rank == 0 else None
+            dist.gather_object(rs.names, names, dst=0)
+            if rank != 0:
+                return None
+            sets = []
+            for r in range(world):
+                ln = lens[r].view(np.int64)
+                off = np.zeros(len(ln) + 1, dtype=np.int64)
+                np.cumsum(ln, out=off[1:])
+                sets.append(synth.ReadSet(seqs[r], off, None if quals is None else quals[r], names[r]))
+            return synth.ReadSet.concat(sets)
+
+        T, Q = gather_set(self.targets), gather_set(self.queries)
+        res = None
+        if rank == 0:
+            with _lib.Coverage(self.opt) as cov:            # a fresh context without a communicator: the plain 1-GPU path
+                cov.set_queries(Q)
+                cov.add_targets(T)
+                one = cov.table()
+            res = "identical (%d rows, byte for byte)" % one.count(b"\n") if one == self.last_table else "DIFFERS"
+        dist.barrier()
+        return res
 
     def parity_note(self):
         """md5 / row count of the benchmarked table (rank 0) -- the exact check lives in tests/ (oracle at small sizes)."""

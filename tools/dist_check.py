@@ -36,8 +36,8 @@ def main():
         myT, myQ = T.subset(range(lo, hi)), Q.subset(range(qlo, qhi))
         tk, qk = _lib.reads_struct(myT), _lib.reads_struct(myQ)
         with L.Coverage(opt) as cov:
-            table = lqd.run_job(cov, tk, myT.n, lo, parts, metas, qk, myQ.n, tk.st.seq, qk.st.seq, 0, rank, world,
-                                exchange=lambda lib, h: lqd.exchange_part(lib, h, rank, world))
+            lqd.comm_init(cov, rank, world)
+            table = lqd.run_job(cov, tk, myT.n, lo, parts, metas, qk, myQ.n, tk.st.seq, qk.st.seq, 0, rank, world)
         if rank == 0:
             want = open(os.path.join(ROOT, "tests", "golden", name + ".tsv"), "rb").read()
             same = table == want
