@@ -187,7 +187,7 @@ LQ_HD int lq_afp_run(lq_afp_walk *s, uint32_t n, const uint32_t *start, lq_afp_s
 /* refill rule of one region (host form; the device loads the bytes with two aligned 16-byte loads): a region that moved since its
  * last refill gets the LQ_AFP_DIG digits from its position on.  Digits past the region's end are cached too (the next region's, or
  * padding): the walk never reads them, because a region is picked from exactly as often as it has elements. */
-LQ_HD void lq_afp_refill_host(const uint8_t *dig, const uint32_t *start, lq_afp_st *st, uint32_t r)
+LQ_HD void lq_afp_refill_host(const uint8_t *dig, const uint32_t *start, lq_afp_st *st, uint32_t r)   /* st: the states with stride 1; st + r * (stride - 1) for strided ones */
 {
     lq_afp_st S = st[r];
     const uint32_t n = start[256];
@@ -198,6 +198,146 @@ LQ_HD void lq_afp_refill_host(const uint8_t *dig, const uint32_t *start, lq_afp_
     S.z = (uint32_t)b[4] | (uint32_t)b[5] << 8 | (uint32_t)b[6] << 16 | (uint32_t)b[7] << 24;
     S.w = (uint32_t)b[8] | (uint32_t)b[9] << 8 | (uint32_t)b[10] << 16 | (uint32_t)LQ_AFP_DIG << 24;
     st[r] = S;
+}
+
+/* ---- the walk reduced to what only it can compute: the pick-up DIGIT stream (what lq_af_walk3_k / lq_af_walkf_k run) ----
+ * Everything else about a level follows from that stream in parallel (lq_afq_expand, on the device lq_af_place_k):
+ *   - the t-th pick-up, of digit d, lands at slot start[d] + (number of digit-d pick-ups before t): a stable partition by digit;
+ *   - it is taken from the slot the pick-up before it was dropped at (in-place exchange), one further when that one closed a cycle
+ *     of the outer-loop region k (the hole k left open lags its pick-ups by one), or from the recorded position when step t opens
+ *     a new outer-loop region.
+ * So the sequential part writes ONE BYTE per element (four pick-ups per 32-bit store) and no positions at all; the phase list
+ * (when each outer-loop region opened, and where) has at most 256 entries per bucket. */
+typedef struct { uint32_t t, p; } lq_afq_phase;          /* region k became the outer-loop region at pick-up t, its next unread position was p; t = ~0: never */
+typedef struct { uint32_t k, c, step, end_k, acc; } lq_afq_walk;
+
+LQ_HD void lq_afq_init(lq_afq_walk *s, const uint32_t *start, lq_afq_phase *ph /* [256], all t = ~0 on entry */)
+{
+    uint32_t k = 0;
+    while (k < 256 && start[k + 1] == start[k]) ++k;
+    s->k = k; s->c = k < 256 ? k : 0; s->step = 0; s->acc = 0; s->end_k = k < 256 ? start[k + 1] : 0;
+    if (k < 256) { ph[k].t = 0; ph[k].p = start[k]; }
+}
+
+/* st[r * stride]: packed state of region r as in lq_afp_st (x = next unread position, then up to 11 digits and their number).
+ * seq32: the digit stream, four pick-ups per word (little endian).  Returns 1 when all n elements are picked, 0 when region s->c
+ * has no cached digit left (refill, call again). */
+LQ_HD int lq_afq_run(lq_afq_walk *s, uint32_t n, const uint32_t *start, lq_afp_st *st, uint32_t stride, uint32_t *seq32, lq_afq_phase *ph)
+{
+    uint32_t k = s->k, c = s->c, step = s->step, end_k = s->end_k, acc = s->acc;
+    int done = 1;
+    if (step < n) {
+        lq_afp_st S = st[c * stride];
+        for (;;) {
+            const uint32_t left = S.w >> 24;
+            if (left == 0) { done = 0; break; }
+            const uint32_t d = S.y & 255u;
+            const lq_afp_st Sn = st[d * stride];                  /* the digit's region, loaded as soon as the digit is known */
+            S.x += 1; S.y = LQ_FUNNEL_R8(S.y, S.z); S.z = LQ_FUNNEL_R8(S.z, S.w); S.w = ((S.w >> 8) & 0xffffu) | (left - 1) << 24;
+            st[c * stride] = S;
+            acc |= d << (8 * (step & 3u));
+            if ((step & 3u) == 3u) { seq32[step >> 2] = acc; acc = 0; }
+            if (d != c) S = Sn;                                   /* Sn is stale only when the digit names the region just read */
+            c = d;
+            if (d == k && S.x == end_k) {                         /* region k complete: open the next non-exhausted region */
+                do { ++k; } while (k < 256 && st[k * stride].x == start[k + 1]);
+                if (k < 256) { c = k; end_k = start[k + 1]; S = st[c * stride]; ph[k].t = step + 1; ph[k].p = S.x; }
+                else { c = 0; S = st[0]; }
+            }
+            if (++step >= n) break;
+        }
+        if (step >= n && (step & 3u)) seq32[step >> 2] = acc;     /* the last, partial word */
+    }
+    s->k = k; s->c = c; s->step = step; s->end_k = end_k; s->acc = acc;
+    return done;
+}
+
+/* ord[t] / slot[t] of every pick-up from the digit stream (host reference of lq_af_place_k); run[256] scratch */
+LQ_HD void lq_afq_expand(const uint8_t *seq, uint32_t n, const uint32_t *start, const lq_afq_phase *ph, uint32_t *run, uint32_t *ord, uint32_t *slot)
+{
+    uint32_t t, k = 0, kn, prev_slot = 0, prev_d = 0, prev_k = 0;
+    for (t = 0; t < 256; ++t) run[t] = 0;
+    while (k < 256 && ph[k].t != 0) ++k;                           /* the region the walk starts in */
+    kn = k + 1; while (kn < 256 && ph[kn].t == 0xffffffffu) ++kn;   /* the next region that ever opens (they open in ascending order) */
+    for (t = 0; t < n; ++t) {
+        const uint32_t d = seq[t];
+        if (kn < 256 && ph[kn].t == t) { k = kn; ord[t] = ph[k].p; ++kn; while (kn < 256 && ph[kn].t == 0xffffffffu) ++kn; }
+        else if (t == 0) ord[t] = ph[k].p;
+        else ord[t] = prev_slot + (prev_d == prev_k ? 1u : 0u);
+        slot[t] = start[d] + run[d]++;
+        prev_slot = slot[t]; prev_d = d; prev_k = k;
+    }
+}
+
+/* ---- the same walk for levels with FEW regions (all digits < 16: the rid >> 16 byte once a part holds more than 131 072 reads).
+ * With 11 cached digits per region a 4-region walk runs dry every ~40 pick-ups; here a region caches LQ_AFR_CAP digits
+ * (cache[(r * LQ_AFR_WORDS + w) * stride], four digits per word) and its read offset inside that stretch is one BYTE of four
+ * registers, so a step is: pick the byte (prmt), one 32-bit load, shift -- no per-region state is written back. */
+#define LQ_AFR_CAP 240
+#define LQ_AFR_WORDS (LQ_AFR_CAP / 4)
+#define LQ_AFR_R 16
+typedef struct { uint32_t k, c, step, acc, rem_k; uint32_t off[4]; } lq_afr_walk;
+
+LQ_HD uint32_t lq_afr_off(const lq_afr_walk *s, uint32_t r) { return (s->off[r >> 2] >> (8 * (r & 3u))) & 255u; }
+
+/* base[r * bstride]: bucket-relative position of the first cached digit of region r (== next unread position - offset) */
+LQ_HD void lq_afr_init(lq_afr_walk *s, const uint32_t *start, lq_afq_phase *ph)
+{
+    uint32_t k = 0;
+    while (k < LQ_AFR_R && start[k + 1] == start[k]) ++k;
+    s->k = k; s->c = k < LQ_AFR_R ? k : 0; s->step = 0; s->acc = 0; s->rem_k = k < LQ_AFR_R ? start[k + 1] - start[k] : 0;
+    s->off[0] = s->off[1] = s->off[2] = s->off[3] = 0;
+    if (k < LQ_AFR_R) { ph[k].t = 0; ph[k].p = start[k]; }
+}
+
+LQ_HD int lq_afr_run(lq_afr_walk *s, uint32_t n, const uint32_t *start, const uint32_t *cache, uint32_t stride, const uint32_t *base, uint32_t bstride,
+                     uint32_t *seq32, lq_afq_phase *ph)
+{
+    uint32_t k = s->k, c = s->c, step = s->step, acc = s->acc, rem_k = s->rem_k;
+    uint32_t o0 = s->off[0], o1 = s->off[1], o2 = s->off[2], o3 = s->off[3];
+    int done = 1;
+    while (step < n) {
+        const uint32_t ow = (c >> 2) == 0 ? o0 : (c >> 2) == 1 ? o1 : (c >> 2) == 2 ? o2 : o3;
+        const uint32_t sh = 8 * (c & 3u), off = (ow >> sh) & 255u;
+        if (off >= LQ_AFR_CAP) { done = 0; break; }
+        const uint32_t w = cache[(c * LQ_AFR_WORDS + (off >> 2)) * stride];
+        const uint32_t d = (w >> (8 * (off & 3u))) & 255u;
+        const uint32_t inc = 1u << sh;
+        if ((c >> 2) == 0) o0 += inc; else if ((c >> 2) == 1) o1 += inc; else if ((c >> 2) == 2) o2 += inc; else o3 += inc;
+        if (c == k) --rem_k;
+        acc |= d << (8 * (step & 3u));
+        if ((step & 3u) == 3u) { seq32[step >> 2] = acc; acc = 0; }
+        c = d;
+        if (d == k && rem_k == 0) {                               /* region k complete: open the next non-exhausted region */
+            for (;;) {
+                ++k;
+                if (k >= LQ_AFR_R) break;
+                const uint32_t okw = (k >> 2) == 0 ? o0 : (k >> 2) == 1 ? o1 : (k >> 2) == 2 ? o2 : o3;
+                const uint32_t nxt = base[k * bstride] + ((okw >> (8 * (k & 3u))) & 255u);   /* next unread position of region k */
+                if (nxt != start[k + 1]) { c = k; rem_k = start[k + 1] - nxt; ph[k].t = step + 1; ph[k].p = nxt; break; }
+            }
+            if (k >= LQ_AFR_R) c = 0;
+        }
+        ++step;
+    }
+    if (done && (step & 3u)) seq32[step >> 2] = acc;
+    s->k = k; s->c = c; s->step = step; s->acc = acc; s->rem_k = rem_k; s->off[0] = o0; s->off[1] = o1; s->off[2] = o2; s->off[3] = o3;
+    return done;
+}
+
+/* host form of the few-region refill: every region's cached stretch restarts at its next unread position */
+LQ_HD void lq_afr_refill_host(const uint8_t *dig, uint32_t n, lq_afr_walk *s, uint32_t *cache, uint32_t *base)
+{
+    for (uint32_t r = 0; r < LQ_AFR_R; ++r) {
+        const uint32_t p = base[r] + lq_afr_off(s, r);
+        base[r] = p;
+        for (uint32_t w = 0; w < LQ_AFR_WORDS; ++w) {
+            uint32_t v = 0;
+            for (uint32_t j = 0; j < 4; ++j) { const uint32_t q = p + 4 * w + j; v |= (uint32_t)(q < n ? dig[q] : 0) << (8 * j); }
+            cache[r * LQ_AFR_WORDS + w] = v;
+        }
+    }
+    s->off[0] = s->off[1] = s->off[2] = s->off[3] = 0;
 }
 
 /* Closed form for exactly two non-empty digits d0 < d1 (regions [0,n0) and [n0,n)).

@@ -135,6 +135,7 @@ extern "C" int lqhc_sketch_lanes(const char *seq, int len, int w, int k, uint32_
 #include "lq_afsort_core.h"
 namespace {
 struct Bkt { uint32_t beg, end; };
+static int cnt_above_15(const uint32_t *cnt) { int n = 0; for (int d = 16; d < 256; ++d) n += cnt[d] != 0; return n; }
 // same orchestration as the device: level by level, buckets > 64 keep going, 2..64 get the stable insertion sort
 void afsort_levels(const uint64_t *key, uint32_t n, uint32_t *idx, int use_two)
 {
@@ -164,6 +165,32 @@ void afsort_levels(const uint64_t *key, uint32_t n, uint32_t *idx, int use_two)
                     }
                     for (uint32_t p = 0; p < m; ++p)
                         dest[beg + p] = lq_af_two_dest(p, n0, fr[p], rk[p], (uint32_t)P.size(), P.data(), Z.data());
+                } else if ((use_two & 16) && cnt_above_15(cnt) == 0) { // few regions: cached stretches + byte offsets in registers, digit stream out
+                    uint32_t st257[257], base[LQ_AFR_R]; std::vector<uint32_t> cache(LQ_AFR_R * LQ_AFR_WORDS); lq_afr_walk ws; lq_afq_phase ph[256];
+                    for (int d = 0; d < 256; ++d) { st257[d] = start[d]; ph[d].t = 0xffffffffu; ph[d].p = 0; }
+                    st257[256] = m;
+                    for (int r = 0; r < LQ_AFR_R; ++r) base[r] = start[r];
+                    lq_afr_init(&ws, st257, ph);
+                    std::vector<uint32_t> seq32(m / 4 + 2), ord(m), slot(m); uint32_t run[256];
+                    for (;;) {
+                        lq_afr_refill_host(dig.data() + beg, m, &ws, cache.data(), base);
+                        if (lq_afr_run(&ws, m, st257, cache.data(), 1, base, 1, seq32.data(), ph)) break;
+                    }
+                    lq_afq_expand((const uint8_t*)seq32.data(), m, st257, ph, run, ord.data(), slot.data());
+                    for (uint32_t t = 0; t < m; ++t) dest[beg + ord[t]] = slot[t];
+                } else if (use_two & 8) { // the digit-stream walk (strided packed states) + parallel-form expansion
+                    const uint32_t stride = 3;
+                    uint32_t st257[257]; std::vector<lq_afp_st> pst(256 * stride); lq_afq_walk ws; lq_afq_phase ph[256];
+                    for (int d = 0; d < 256; ++d) { st257[d] = start[d]; pst[d * stride].x = start[d]; pst[d * stride].y = pst[d * stride].z = pst[d * stride].w = 0; ph[d].t = 0xffffffffu; ph[d].p = 0; }
+                    st257[256] = m;
+                    lq_afq_init(&ws, st257, ph);
+                    std::vector<uint32_t> seq32(m / 4 + 2), ord(m), slot(m); uint32_t run[256];
+                    for (;;) {
+                        for (uint32_t r = 0; r < 256; ++r) { lq_afp_st tmp[256]; tmp[r] = pst[r * stride]; lq_afp_refill_host(dig.data() + beg, st257, tmp, r); pst[r * stride] = tmp[r]; }
+                        if (lq_afq_run(&ws, m, st257, pst.data(), stride, seq32.data(), ph)) break;
+                    }
+                    lq_afq_expand((const uint8_t*)seq32.data(), m, st257, ph, run, ord.data(), slot.data());
+                    for (uint32_t t = 0; t < m; ++t) dest[beg + ord[t]] = slot[t];
                 } else if (use_two & 4) { // the packed one-load-per-step form (what the device runs, one lane per bucket)
                     uint32_t st257[257]; lq_afp_st pst[256]; lq_afp_walk ws;
                     for (int d = 0; d < 256; ++d) { st257[d] = start[d]; pst[d].x = start[d]; pst[d].y = pst[d].z = pst[d].w = 0; }

@@ -311,6 +311,9 @@ struct AfArgs {
     const AfBkt *cur; const uint32_t *n_cur; AfBkt *nxt; uint32_t *n_nxt; uint32_t *cursor; uint32_t *n_walk;
     AfBkt *wlist; uint32_t *n_wlist; uint32_t *wcursor, *wcursor_f;   /* tied buckets with > 2 digits: walked by lq_af_walk_k (>= AFW_SMALL elements) ... */
     AfBkt *wlist_s; uint32_t *n_wlist_s; uint32_t *wcursor_s;   /* ... or by lq_af_walk_small_k (a warp per bucket) */
+    AfBkt *wlist_w; uint32_t *n_wlist_w; uint32_t *wcursor_w;   /* ... or, all digits < 16 (few regions), by lq_af_walkf_k */
+    lq_afq_phase *wph;            /* 256 phase entries per bucket of wlist, then of wlist_w (capacity wph_cap each) */
+    uint32_t wph_cap;
     unsigned long long *n_elem;   /* elements this launch handled (profiling: algorithmic bytes of the launch) */
     const AfBkt *curb; const uint32_t *n_curb; AfBkt *nxtb; uint32_t *n_nxtb; uint32_t *cursorb;   /* buckets of >= AFB_MIN elements: a CTA each (lq_af_big_k) */
     int shift;
@@ -350,9 +353,10 @@ __device__ __forceinline__ void af_append(const AfArgs &a, uint32_t beg, uint32_
 }
 
 /* a tied bucket with more than two digits goes to one of the two walk kernels (called by one thread) */
-__device__ __forceinline__ void af_push_walk(const AfArgs &a, uint32_t beg, uint32_t n)
+__device__ __forceinline__ void af_push_walk(const AfArgs &a, uint32_t beg, uint32_t n, bool few /* no digit above 15 */)
 {
     if (n < AFW_SMALL) { const uint32_t at = atomicAdd(a.n_wlist_s, 1u); a.wlist_s[at].beg = beg; a.wlist_s[at].end = beg + n; }
+    else if (few) { const uint32_t at = atomicAdd(a.n_wlist_w, 1u); a.wlist_w[at].beg = beg; a.wlist_w[at].end = beg + n; }
     else { const uint32_t at = atomicAdd(a.n_wlist, 1u); a.wlist[at].beg = beg; a.wlist[at].end = beg + n; }
 }
 
@@ -613,7 +617,13 @@ __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
             __syncwarp();
         } else if (nb > 2) {
             /* tied keys and more than two digits: the sequential walk, done by lq_af_walk_k with a digit cache */
-            if (lane == 0) af_push_walk(a, beg, n);
+            uint32_t hi = 0;                                     /* any element with a digit above 15? */
+            if (lane >= 2) {
+                #pragma unroll
+                for (int j = 0; j < 8; ++j) hi |= cnt[8 * lane + j];
+            }
+            hi = __any_sync(0xffffffffu, hi != 0);
+            if (lane == 0) af_push_walk(a, beg, n, !hi);
             __syncwarp();
             continue;
         }
@@ -628,17 +638,41 @@ __global__ void __launch_bounds__(AF_WARPS * 32) lq_af_level_k(AfArgs a)
  *        tied keys, more digits       handed to lq_af_walk_k (wlist), which also finishes the bucket ---- */
 #define AFB_THREADS 512
 #define AFB_V 4
-template <bool WALKED>   /* WALKED: the buckets of the long-walk list, whose dest[] lq_af_walk_k has just computed: permute + sub-buckets only */
+/* sub-buckets of a finished level (ksort.h:124-133), in the destination buffer; what is finished here must end in the primary one */
+__device__ __forceinline__ void afb_subbuckets(const AfArgs &a, uint32_t beg, uint32_t n, const uint32_t *s_cnt, const uint32_t *s_start)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint64_t *kx2 = a.kx2 + beg, *kp = a.kxp + beg; uint32_t *idx2 = a.idx2 + beg, *ip = a.idxp + beg;
+    if (a.shift > 0) {
+        if (tid < 256) {
+            const uint32_t c = s_cnt[tid], s0 = s_start[tid];
+            const bool big_ = c > LQ_RS_MIN;
+            af_append(a, beg + s0, c, big_);
+            if (c >= 1 && c <= 8) {
+                if (c > 1) lq_af_insertion_kv(kx2 + s0, idx2 + s0, c);
+                if (!a.dst_primary) for (uint32_t x = 0; x < c; ++x) { kp[s0 + x] = kx2[s0 + x]; ip[s0 + x] = idx2[s0 + x]; }
+            }
+        }
+        for (uint32_t d = wid; d < 256; d += AFB_THREADS / 32) {   /* 9..64: a warp each, so that no thread sorts alone while 511 wait */
+            const uint32_t c = s_cnt[d], s0 = s_start[d];
+            if (c > 8 && c <= LQ_RS_MIN) af_warp_ranksort(kx2 + s0, idx2 + s0, c, lane, a.dst_primary ? (uint64_t*)0 : kp + s0, a.dst_primary ? (uint32_t*)0 : ip + s0);
+        }
+    } else if (!a.dst_primary) {
+        #pragma unroll 4
+        for (uint32_t p = tid; p < n; p += AFB_THREADS) { ip[p] = idx2[p]; kp[p] = kx2[p]; }
+    }
+}
+
 __global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
 {
     __shared__ uint32_t s_cnt[256], s_start[257], s_head[256], scan_sm[33];
-    __shared__ uint32_t s_b, s_tied, s_nb, s_d0, s_d1;
+    __shared__ uint32_t s_b, s_tied, s_nb, s_d0, s_d1, s_few;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, lt = (1u << lane) - 1;
-    const uint32_t nbig = WALKED ? *a.n_wlist : *a.n_curb;
-    const AfBkt *list = WALKED ? a.wlist : a.curb;
+    const uint32_t nbig = *a.n_curb;
+    const AfBkt *list = a.curb;
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_b = atomicAdd(WALKED ? a.wcursor_f : a.cursorb, 1u);
+        if (tid == 0) s_b = atomicAdd(a.cursorb, 1u);
         __syncthreads();
         const uint32_t b = s_b;
         if (b >= nbig) break;
@@ -647,23 +681,10 @@ __global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
         uint64_t *kx = a.kx + beg, *kx2 = a.kx2 + beg;
         uint8_t *dig = a.dig + beg;
         if (tid < 256) { s_cnt[tid] = 0; s_head[tid] = 0; }
-        if (tid == 0) { s_tied = 0; if (!WALKED) atomicAdd(a.n_elem, (unsigned long long)n); }
+        if (tid == 0) { s_tied = 0; atomicAdd(a.n_elem, (unsigned long long)n); }
         __syncthreads();
         /* 1. digits + histogram (warp-aggregated shared-memory atomics: a level may have only two digits) */
         uint32_t tied = 0;
-        if (WALKED) {   /* the digits are there already */
-            for (uint32_t r0 = 0; r0 < n; r0 += AFB_THREADS * AFB_V) {
-                uint32_t dv[AFB_V];
-                #pragma unroll
-                for (int u = 0; u < AFB_V; ++u) { const uint32_t p = r0 + u * AFB_THREADS + tid; dv[u] = p < n ? dig[p] : 0; }
-                #pragma unroll
-                for (int u = 0; u < AFB_V; ++u) {
-                    const uint32_t p = r0 + u * AFB_THREADS + tid; const bool ok = p < n;
-                    const uint32_t act = __ballot_sync(0xffffffffu, ok);
-                    if (ok) { const uint32_t peers = __match_any_sync(act, dv[u]); if ((peers & lt) == 0) atomicAdd(&s_cnt[dv[u]], (uint32_t)__popc(peers)); }
-                }
-            }
-        } else
         for (uint32_t r0 = 0; r0 < n; r0 += AFB_THREADS * AFB_V) {
             uint32_t dv[AFB_V]; uint64_t kk[AFB_V];
             #pragma unroll
@@ -685,27 +706,27 @@ __global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
         __syncthreads();
         /* 2. region starts */
         if (wid == 0) {
-            uint32_t loc = 0, ne = 0, d0 = 256, d1 = 0;
+            uint32_t loc = 0, ne = 0, d0 = 256, d1 = 0, hi = 0;
             #pragma unroll
-            for (int j = 0; j < 8; ++j) { const uint32_t c = s_cnt[8 * lane + j]; loc += c; if (c) { ++ne; d0 = min(d0, 8 * lane + j); d1 = max(d1, 8 * lane + j); } }
+            for (int j = 0; j < 8; ++j) { const uint32_t c = s_cnt[8 * lane + j]; loc += c; if (c) { ++ne; d0 = min(d0, 8 * lane + j); d1 = max(d1, 8 * lane + j); if (lane >= 2) hi = 1; } }
             const uint32_t inc = lq_warp_incl_scan(loc);
             uint32_t run = inc - loc;
             #pragma unroll
             for (int j = 0; j < 8; ++j) { s_start[8 * lane + j] = run; run += s_cnt[8 * lane + j]; }
             ne = lq_warp_sum(ne);
+            hi = __any_sync(0xffffffffu, hi != 0);
             #pragma unroll
             for (int o = 16; o > 0; o >>= 1) { d0 = min(d0, __shfl_xor_sync(0xffffffffu, d0, o)); d1 = max(d1, __shfl_xor_sync(0xffffffffu, d1, o)); }
-            if (lane == 0) { s_start[256] = n; s_nb = ne; s_d0 = d0; s_d1 = d1; }
+            if (lane == 0) { s_start[256] = n; s_nb = ne; s_d0 = d0; s_d1 = d1; s_few = !hi; }
         }
         __syncthreads();
         const uint32_t nb = s_nb; const bool tiedb = s_tied != 0;
-        if (!WALKED && nb > 2 && tiedb) {   /* the sequential walk */
-            if (tid == 0) af_push_walk(a, beg, n);
+        if (nb > 2 && tiedb) {   /* the sequential walk: lq_af_walk3_k / lq_af_walkf_k, then lq_af_place_k */
+            if (tid == 0) af_push_walk(a, beg, n, s_few != 0);
             continue;
         }
         if (nb > 1) {
-            if (WALKED) {
-            } else if (tiedb) {
+            if (tiedb) {
                 /* 3a. two digits d0 < d1, tied keys: closed form.  rk = foreign positions before p in p's own region */
                 const uint32_t d0 = s_d0, d1 = s_d1, n0 = s_cnt[d0];
                 uint32_t *P = idx2, *Z = idx2 + n0;
@@ -761,59 +782,36 @@ __global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
                 }
                 __syncthreads();
             }
-            /* 4. permute the payload.  A walked bucket comes as (ord[t], dest[t]) in pick-up order: consecutive t read and write
-             * consecutive positions inside each region, so the sectors of both sides are used whole. */
-            if (WALKED) {
-                const uint32_t *ord = a.ord + beg;
-                #pragma unroll 4
-                for (uint32_t t = tid; t < n; t += AFB_THREADS) { const uint32_t p = ord[t], d = dest[t]; idx2[d] = idx[p]; kx2[d] = kx[p]; }
-            } else {
-                #pragma unroll 4
-                for (uint32_t p = tid; p < n; p += AFB_THREADS) { const uint32_t d = dest[p]; idx2[d] = idx[p]; kx2[d] = kx[p]; }
-            }
+            /* 4. permute the payload */
+            #pragma unroll 4
+            for (uint32_t p = tid; p < n; p += AFB_THREADS) { const uint32_t d = dest[p]; idx2[d] = idx[p]; kx2[d] = kx[p]; }
             __syncthreads();
         } else {   /* one digit: nothing moves, but the bucket changes buffers like every other */
             #pragma unroll 4
             for (uint32_t p = tid; p < n; p += AFB_THREADS) { idx2[p] = idx[p]; kx2[p] = kx[p]; }
             __syncthreads();
         }
-        /* 5. sub-buckets (ksort.h:124-133), in the destination buffer; what is finished here must end in the primary one */
-        uint64_t *kp = a.kxp + beg; uint32_t *ip = a.idxp + beg;
-        if (a.shift > 0) {
-            if (tid < 256) {
-                const uint32_t c = s_cnt[tid], s0 = s_start[tid];
-                const bool big_ = c > LQ_RS_MIN;
-                af_append(a, beg + s0, c, big_);
-                if (c >= 1 && c <= 8) {
-                    if (c > 1) lq_af_insertion_kv(kx2 + s0, idx2 + s0, c);
-                    if (!a.dst_primary) for (uint32_t x = 0; x < c; ++x) { kp[s0 + x] = kx2[s0 + x]; ip[s0 + x] = idx2[s0 + x]; }
-                }
-            }
-            for (uint32_t d = wid; d < 256; d += AFB_THREADS / 32) {   /* 9..64: a warp each, so that no thread sorts alone while 511 wait */
-                const uint32_t c = s_cnt[d], s0 = s_start[d];
-                if (c > 8 && c <= LQ_RS_MIN) af_warp_ranksort(kx2 + s0, idx2 + s0, c, lane, a.dst_primary ? (uint64_t*)0 : kp + s0, a.dst_primary ? (uint32_t*)0 : ip + s0);
-            }
-        } else if (!a.dst_primary) {
-            #pragma unroll 4
-            for (uint32_t p = tid; p < n; p += AFB_THREADS) { ip[p] = idx2[p]; kp[p] = kx2[p]; }
-        }
+        /* 5. sub-buckets */
+        afb_subbuckets(a, beg, n, s_cnt, s_start);
     }
 }
 
-/* The walk of lq_afsort_core.h, one LANE per bucket (lq_afp_run): a single thread chases a pointer through 256 queues, so a warp
- * with one active lane wastes 31/32 of its issue slots and the SM ends up issue-bound.  Here a CTA takes up to AFS_WALKERS buckets at
- * a time ("generation"):
- *   setup   the whole CTA builds the digit histograms (shared-memory atomics), then a warp per bucket turns them into region starts
- *           (kept in a global scratch row) and empty per-region states
+/* ---- the sequential walk of long tied buckets (>= AFW_SMALL elements, more than two digits), one LANE per bucket ----
+ * lq_afsort_core.h: the only thing the walk must compute sequentially is the pick-up DIGIT stream; slots, source positions and the
+ * payload permutation follow from it in parallel (lq_af_place_k).  A lane therefore writes one byte per pick-up (a 32-bit store
+ * every four) plus a phase entry whenever the outer-loop region changes -- no positions, no per-step global traffic.
+ * lq_af_walk3_k (any digits): a CTA takes up to AFS_WALKERS buckets at a time ("generation"):
+ *   setup   the whole CTA builds the digit histograms (shared-memory atomics), a warp per bucket turns them into region starts (kept
+ *           in a global scratch row) and empty per-region states
  *   rounds  all threads refill the 16-byte region states (position + next 11 digits) of every bucket, then the walker warps walk,
- *           lane = bucket, until every lane is done or out of digits somewhere; one step = one LDS.128, an AND and the next address
- *   finish  the whole CTA permutes the payload, then a warp per bucket hands the sub-buckets on (af_finish_bucket)
- * 4 KB of shared memory per bucket (256 states), reused for the histogram before and for start/cnt/staging after the walk. */
+ *           lane = bucket, until every lane is done or out of digits somewhere (lq_afq_run: one LDS.128 per step on the critical path)
+ * The states are laid out REGION-MAJOR, st[region][lane]: the lanes of a walker warp, each somewhere else in its own bucket, then read
+ * consecutive 16-byte words.  (Bucket-major -- 4 KB between lanes -- put all 28 lanes on the same banks: every step of the warp was
+ * 28 serialised shared-memory transactions.) */
 #define AFS_WPW 28                 /* walker lanes per walker warp */
 #define AFS_WW 2                   /* walker warps: they interleave on the SM, hiding each other's load latency */
 #define AFS_WALKERS (AFS_WPW * AFS_WW)
 #define AFS_THREADS 512
-#define AFS_SN 160                 /* staging capacity in the finish phase: start 1040 + cnt 1024 + keys 1280 + indices 640 < 4096 */
 #define AFS_GRID 148               /* one CTA per SM (224 KB of shared memory each) */
 #define AFS_ROW 260                /* u32 per bucket in the global scratch: 257 region starts */
 __device__ __forceinline__ uint4 afw_load16(const uint8_t *addr)   /* 16 bytes from an arbitrary address (reads up to 31 bytes past it: the arena is padded) */
@@ -828,13 +826,13 @@ __device__ __forceinline__ uint4 afw_load16(const uint8_t *addr)   /* 16 bytes f
     return make_uint4(__funnelshift_r(t0, t1, sh), __funnelshift_r(t1, t2, sh), __funnelshift_r(t2, t3, sh), __funnelshift_r(t3, t4, sh));
 }
 
-struct AfsMeta { uint32_t beg, n, nb; };
+struct AfsMeta { uint32_t beg, n; };
 
 extern __shared__ __align__(16) uint8_t afs_smem[];
 
-__global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk_k(AfArgs a, uint32_t *gstart /* gridDim.x * AFS_WALKERS * AFS_ROW */)
+__global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk3_k(AfArgs a, uint32_t *gstart /* gridDim.x * AFS_WALKERS * AFS_ROW */)
 {
-    lq_afp_st *state = (lq_afp_st*)afs_smem;                      /* [AFS_WALKERS][256] */
+    lq_afp_st *state = (lq_afp_st*)afs_smem;                      /* [256][AFS_WALKERS] */
     __shared__ AfsMeta meta[AFS_WALKERS];
     __shared__ uint32_t s_base, s_alive[AFS_WW];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -849,14 +847,19 @@ __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk_k(AfArgs a, uint32_
         const uint32_t base = s_base;
         if (base >= nw) break;
         const uint32_t nbk = nw - base < gsize ? nw - base : gsize;
-        /* ---- setup: histograms by the whole CTA ---- */
+        /* ---- setup: histograms by the whole CTA (bucket w counts in the first KB-s of the state area, bucket-major) ---- */
+        uint32_t *cnts = (uint32_t*)afs_smem;
         for (uint32_t w = tid; w < nbk; w += AFS_THREADS) { const AfBkt b = a.wlist[base + w]; meta[w].beg = b.beg; meta[w].n = b.end - b.beg; }
-        for (uint32_t e = tid; e < nbk * 256; e += AFS_THREADS) ((uint32_t*)(state + (e >> 8) * 256))[e & 255] = 0;   /* cnt = first 1 KB of a bucket's area */
+        for (uint32_t e = tid; e < nbk * 256; e += AFS_THREADS) cnts[e] = 0;
+        for (uint32_t e = tid; e < nbk * 256; e += AFS_THREADS) {   /* phase rows of these buckets: "never opened" */
+            lq_afq_phase ph; ph.t = 0xffffffffu; ph.p = 0;
+            a.wph[(size_t)(base + (e >> 8)) * 256 + (e & 255)] = ph;
+        }
         __syncthreads();
         for (uint32_t w = 0; w < nbk; ++w) {
             const uint32_t n = meta[w].n;
             const uint8_t *dig = a.dig + meta[w].beg;
-            uint32_t *cnt = (uint32_t*)(state + w * 256);
+            uint32_t *cnt = cnts + w * 256;
             uint32_t head = (uint32_t)((16 - ((uintptr_t)dig & 15)) & 15);
             if (head > n) head = n;
             const uint32_t nch = (n - head) >> 4, tail0 = head + (nch << 4);
@@ -875,44 +878,52 @@ __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk_k(AfArgs a, uint32_
             }
         }
         __syncthreads();
-        /* ---- setup: region starts and empty states, a warp per bucket ---- */
-        for (uint32_t w = wid; w < nbk; w += AFS_THREADS / 32) {
-            const uint32_t *cnt = (const uint32_t*)(state + w * 256);
-            uint32_t loc = 0, ne = 0, cc[8];
-            #pragma unroll
-            for (int j = 0; j < 8; ++j) { cc[j] = cnt[8 * lane + j]; loc += cc[j]; if (cc[j]) ++ne; }
-            const uint32_t inc = lq_warp_incl_scan(loc);
-            uint32_t run = inc - loc;
-            const uint32_t nb = lq_warp_sum(ne);
-            __syncwarp();                                          /* every lane holds its counts: the states may overwrite them */
-            #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t r = 8 * lane + j;
-                gs[w * AFS_ROW + r] = run;
-                lq_afp_st e; e.x = run; e.y = e.z = e.w = 0;
-                state[w * 256 + r] = e;
-                run += cc[j];
+        /* ---- setup: region starts (a warp per bucket, up to four buckets per warp) -> registers; then, behind a barrier (the states
+         *      overwrite the counts of OTHER buckets), the empty states ---- */
+        uint32_t st0[4][8];
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t w = wid + q * (AFS_THREADS / 32);
+            if (w < nbk) {
+                const uint32_t *cnt = cnts + w * 256;
+                uint32_t loc = 0, cc[8];
+                #pragma unroll
+                for (int j = 0; j < 8; ++j) { cc[j] = cnt[8 * lane + j]; loc += cc[j]; }
+                uint32_t run = lq_warp_incl_scan(loc) - loc;
+                #pragma unroll
+                for (int j = 0; j < 8; ++j) { st0[q][j] = run; gs[w * AFS_ROW + 8 * lane + j] = run; run += cc[j]; }
+                if (lane == 31) gs[w * AFS_ROW + 256] = meta[w].n;
             }
-            if (lane == 31) gs[w * AFS_ROW + 256] = meta[w].n;
-            if (lane == 0) meta[w].nb = nb;
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t w = wid + q * (AFS_THREADS / 32);
+            if (w < nbk) {
+                #pragma unroll
+                for (int j = 0; j < 8; ++j) { lq_afp_st e; e.x = st0[q][j]; e.y = e.z = e.w = 0; state[(8 * lane + j) * AFS_WALKERS + w] = e; }
+            }
         }
         __syncthreads();
         /* ---- rounds: everybody refills the regions that moved, then the walker warps walk until every lane is done or out of digits ---- */
         const uint32_t wl = wid * AFS_WPW + lane;                 /* this thread's bucket when it is a walker lane */
         const bool walker = wid < AFS_WW && lane < AFS_WPW && wl < nbk;
-        lq_afp_walk ws; bool fin = true; uint32_t my_n = 0; uint32_t *my_dest = 0, *my_ord = 0; const uint32_t *my_start = gs;
-        if (walker) { my_start = gs + wl * AFS_ROW; lq_afp_init(&ws, my_start); fin = false; my_n = meta[wl].n; my_dest = a.dest + meta[wl].beg; my_ord = a.ord + meta[wl].beg; }
+        lq_afq_walk ws; bool fin = true; uint32_t my_n = 0; uint32_t *my_seq = 0; const uint32_t *my_start = gs; lq_afq_phase *my_ph = a.wph;
+        if (walker) {
+            my_start = gs + wl * AFS_ROW; my_ph = a.wph + (size_t)(base + wl) * 256;
+            lq_afq_init(&ws, my_start, my_ph); fin = false; my_n = meta[wl].n; my_seq = a.ord + meta[wl].beg;
+        }
         for (;;) {
-            for (uint32_t e0 = tid; e0 < nbk * 256; e0 += 4 * AFS_THREADS) {   /* refill: consecutive threads, consecutive regions of a bucket; 4 loads in flight */
+            for (uint32_t e0 = tid; e0 < AFS_WALKERS * 256; e0 += 4 * AFS_THREADS) {   /* refill: consecutive threads, consecutive words; 4 loads in flight */
                 lq_afp_st S[4]; bool need[4]; uint4 v[4];
                 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const uint32_t e = e0 + u * AFS_THREADS;
                     need[u] = false;
-                    if (e < nbk * 256) { S[u] = state[e]; need[u] = (S[u].w >> 24) < LQ_AFP_DIG; }   /* the region moved since its last refill */
+                    if (e < AFS_WALKERS * 256 && e % AFS_WALKERS < nbk) { S[u] = state[e]; need[u] = (S[u].w >> 24) < LQ_AFP_DIG; }   /* the region moved since its last refill */
                 }
                 #pragma unroll
-                for (int u = 0; u < 4; ++u) if (need[u]) v[u] = afw_load16(a.dig + meta[(e0 + u * AFS_THREADS) >> 8].beg + S[u].x);
+                for (int u = 0; u < 4; ++u) if (need[u]) v[u] = afw_load16(a.dig + meta[(e0 + u * AFS_THREADS) % AFS_WALKERS].beg + S[u].x);
                 #pragma unroll
                 for (int u = 0; u < 4; ++u) if (need[u]) {
                     S[u].y = v[u].x; S[u].z = v[u].y; S[u].w = (v[u].z & 0x00ffffffu) | (uint32_t)LQ_AFP_DIG << 24;
@@ -921,7 +932,7 @@ __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk_k(AfArgs a, uint32_
             }
             __syncthreads();
             if (wid < AFS_WW) {
-                if (!fin) fin = lq_afp_run(&ws, my_n, my_start, state + wl * 256, my_ord, my_dest) != 0;
+                if (!fin) fin = lq_afq_run(&ws, my_n, my_start, state + wl, AFS_WALKERS, my_seq, my_ph) != 0;
                 const uint32_t alive = __ballot_sync(0xffffffffu, !fin);
                 if (lane == 0) s_alive[wid] = alive;
             }
@@ -936,7 +947,257 @@ __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk_k(AfArgs a, uint32_
             for (uint32_t w = 0; w < nbk; ++w) tot += meta[w].n;
             atomicAdd(a.n_walk, nbk); atomicAdd(a.n_elem, tot);
         }
-        /* the payload is permuted and the sub-buckets handed on by lq_af_big_k<true> (full occupancy, a CTA per bucket) */
+    }
+}
+
+/* lq_af_walkf_k: the same for buckets all of whose digits are below 16 (lq_afr_*: the rid >> 16 byte once a part holds more than
+ * 131 072 reads -- every multi-GPU run, and every 4 G-base part of reads shorter than 30 kb).  Such walks are few (one per tied query and
+ * strand) and long (10^5..10^6 pick-ups), so they are spread thinly: AFF_LANES buckets per CTA, three CTAs per SM.  A region caches
+ * 240 digits in shared memory ([region][word][lane]); its read offset is a byte of four registers. */
+#define AFF_LANES 16
+#define AFF_THREADS 256
+#define AFF_GRID (148 * 3)
+struct AffSmem { uint32_t cache[LQ_AFR_R * LQ_AFR_WORDS][AFF_LANES]; uint32_t base[LQ_AFR_R][AFF_LANES]; uint32_t start[LQ_AFR_R + 1][AFF_LANES]; uint32_t off[4][AFF_LANES]; };
+
+__global__ void __launch_bounds__(AFF_THREADS) lq_af_walkf_k(AfArgs a)
+{
+    extern __shared__ __align__(16) uint8_t aff_raw[];
+    AffSmem &S = *(AffSmem*)aff_raw;
+    __shared__ AfsMeta meta[AFF_LANES];
+    __shared__ uint32_t s_base, s_alive, s_cnt[AFF_LANES][LQ_AFR_R];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t nw = *a.n_wlist_w;
+    uint32_t gsize = (nw + gridDim.x - 1) / gridDim.x;
+    gsize = gsize < 1 ? 1 : gsize > AFF_LANES ? AFF_LANES : gsize;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_base = atomicAdd(a.wcursor_w, gsize);
+        __syncthreads();
+        const uint32_t base = s_base;
+        if (base >= nw) break;
+        const uint32_t nbk = nw - base < gsize ? nw - base : gsize;
+        if (tid < nbk) { const AfBkt b = a.wlist_w[base + tid]; meta[tid].beg = b.beg; meta[tid].n = b.end - b.beg; }
+        for (uint32_t e = tid; e < AFF_LANES * LQ_AFR_R; e += AFF_THREADS) s_cnt[e / LQ_AFR_R][e % LQ_AFR_R] = 0;
+        for (uint32_t e = tid; e < nbk * 256; e += AFF_THREADS) {
+            lq_afq_phase ph; ph.t = 0xffffffffu; ph.p = 0;
+            a.wph[(size_t)(a.wph_cap + base + (e >> 8)) * 256 + (e & 255)] = ph;
+        }
+        __syncthreads();
+        /* histograms: 16 counters per bucket, private per thread, then merged */
+        for (uint32_t w = 0; w < nbk; ++w) {
+            const uint32_t n = meta[w].n; const uint8_t *dig = a.dig + meta[w].beg;
+            uint32_t c[LQ_AFR_R];
+            #pragma unroll
+            for (int r = 0; r < LQ_AFR_R; ++r) c[r] = 0;
+            for (uint32_t p = tid; p < n; p += AFF_THREADS) {
+                const uint32_t d = dig[p] & 15u;
+                #pragma unroll
+                for (int r = 0; r < LQ_AFR_R; ++r) c[r] += d == (uint32_t)r;
+            }
+            #pragma unroll
+            for (int r = 0; r < LQ_AFR_R; ++r) { const uint32_t v = lq_warp_sum(c[r]); if (lane == 0 && v) atomicAdd(&s_cnt[w][r], v); }
+        }
+        __syncthreads();
+        if (tid < nbk) {
+            uint32_t run = 0;
+            for (int r = 0; r < LQ_AFR_R; ++r) { S.start[r][tid] = run; S.base[r][tid] = run; run += s_cnt[tid][r]; }
+            S.start[LQ_AFR_R][tid] = run;
+            S.off[0][tid] = S.off[1][tid] = S.off[2][tid] = S.off[3][tid] = 0;
+        }
+        __syncthreads();
+        const bool walker = wid == 0 && lane < nbk;
+        lq_afr_walk ws; bool fin = true; uint32_t my_n = 0; uint32_t *my_seq = 0; lq_afq_phase *my_ph = a.wph; uint32_t my_start[LQ_AFR_R + 1];
+        #pragma unroll
+        for (int r = 0; r <= LQ_AFR_R; ++r) my_start[r] = 0;
+        if (walker) {
+            #pragma unroll
+            for (int r = 0; r <= LQ_AFR_R; ++r) my_start[r] = S.start[r][lane];
+            my_ph = a.wph + (size_t)(a.wph_cap + base + lane) * 256;
+            lq_afr_init(&ws, my_start, my_ph); fin = false; my_n = meta[lane].n; my_seq = a.ord + meta[lane].beg;
+        }
+        for (;;) {
+            /* refill: every region's cached stretch restarts at its next unread position (base += offset, offset = 0) */
+            for (uint32_t e = tid; e < nbk * LQ_AFR_R; e += AFF_THREADS) {
+                const uint32_t w = e % nbk, r = e / nbk;
+                const uint32_t o = (S.off[r >> 2][w] >> (8 * (r & 3u))) & 255u;
+                S.base[r][w] += o;
+            }
+            __syncthreads();
+            if (tid < nbk) S.off[0][tid] = S.off[1][tid] = S.off[2][tid] = S.off[3][tid] = 0;
+            for (uint32_t e = tid; e < nbk * LQ_AFR_R * LQ_AFR_WORDS; e += AFF_THREADS) {
+                const uint32_t w = e % nbk, rw = e / nbk, r = rw / LQ_AFR_WORDS, j = rw % LQ_AFR_WORDS;
+                const uint32_t n = meta[w].n, p = S.base[r][w] + 4 * j;
+                const uint8_t *dig = a.dig + meta[w].beg;
+                uint32_t v = 0;
+                if (p + 4 <= n) {
+                    const uintptr_t A = (uintptr_t)(dig + p) & ~(uintptr_t)3; const uint32_t sh = (uint32_t)((uintptr_t)(dig + p) & 3) * 8;
+                    const uint32_t lo = *(const uint32_t*)A, hi = sh ? *(const uint32_t*)(A + 4) : 0;   /* the arena is padded: A + 4 stays inside it */
+                    v = __funnelshift_r(lo, hi, sh);
+                } else {
+                    #pragma unroll
+                    for (int q = 0; q < 4; ++q) if (p + q < n) v |= (uint32_t)dig[p + q] << (8 * q);
+                }
+                S.cache[rw][w] = v;
+            }
+            __syncthreads();
+            if (wid == 0) {
+                if (!fin) {
+                    fin = lq_afr_run(&ws, my_n, my_start, &S.cache[0][lane], AFF_LANES, &S.base[0][lane], AFF_LANES, my_seq, my_ph) != 0;
+                    S.off[0][lane] = ws.off[0]; S.off[1][lane] = ws.off[1]; S.off[2][lane] = ws.off[2]; S.off[3][lane] = ws.off[3];
+                    ws.off[0] = ws.off[1] = ws.off[2] = ws.off[3] = 0;   /* the refill above rebases every region */
+                }
+                const uint32_t alive = __ballot_sync(0xffffffffu, !fin);
+                if (lane == 0) s_alive = alive;
+            }
+            __syncthreads();
+            if (!s_alive) break;
+        }
+        if (tid == 0) {
+            unsigned long long tot = 0;
+            for (uint32_t w = 0; w < nbk; ++w) tot += meta[w].n;
+            atomicAdd(a.n_walk, nbk); atomicAdd(a.n_elem, tot);
+        }
+    }
+}
+
+/* lq_af_place_k: everything about a walked bucket that is NOT sequential (lq_afq_expand), a CTA per bucket at full occupancy:
+ *   slot[t] = start[d_t] + (digit-d_t pick-ups before t)        stable ranking of the digit stream, tiles of 4096 pick-ups
+ *   ord[t]  = slot[t-1] (+1 behind a pick-up that closed a cycle of the outer-loop region), or the recorded position of a phase
+ *   payload[slot[t]] = payload[ord[t]]                          in pick-up order: both sides advance sequentially inside each region
+ * then the sub-buckets are handed on like after any other level. */
+#define AFP_TILE 4096
+#define AFP_ROWS (AFP_TILE / AFB_THREADS)          /* 8 rows of 32 per warp */
+__global__ void __launch_bounds__(AFB_THREADS) lq_af_place_k(AfArgs a)
+{
+    __shared__ uint32_t s_cnt[256], s_start[257], s_run[256], s_slot[AFP_TILE];
+    __shared__ uint32_t s_w[AFB_THREADS / 32][256];
+    __shared__ uint32_t s_pt[256], s_pp[256], s_pk[256], s_scan[8];
+    __shared__ uint32_t s_b, s_np, s_carry_slot, s_carry_d;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, lt = (1u << lane) - 1;
+    const uint32_t n1 = *a.n_wlist, n2 = *a.n_wlist_w;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_b = atomicAdd(a.wcursor_f, 1u);
+        __syncthreads();
+        const uint32_t b = s_b;
+        if (b >= n1 + n2) break;
+        const AfBkt bk = b < n1 ? a.wlist[b] : a.wlist_w[b - n1];
+        const lq_afq_phase *ph = a.wph + (size_t)(b < n1 ? b : a.wph_cap + (b - n1)) * 256;
+        const uint32_t beg = bk.beg, n = bk.end - beg;
+        const uint32_t *idx = a.idx + beg; uint32_t *idx2 = a.idx2 + beg;
+        const uint64_t *kx = a.kx + beg; uint64_t *kx2 = a.kx2 + beg;
+        const uint8_t *seq = (const uint8_t*)(a.ord + beg);
+        if (tid < 256) { s_cnt[tid] = 0; s_run[tid] = 0; }
+        __syncthreads();
+        /* region sizes: histogram of the digit stream (the same multiset as the bucket's digits) */
+        for (uint32_t r0 = 0; r0 < n; r0 += AFB_THREADS * AFB_V) {
+            uint32_t dv[AFB_V];
+            #pragma unroll
+            for (int u = 0; u < AFB_V; ++u) { const uint32_t p = r0 + u * AFB_THREADS + tid; dv[u] = p < n ? seq[p] : 0; }
+            #pragma unroll
+            for (int u = 0; u < AFB_V; ++u) {
+                const uint32_t p = r0 + u * AFB_THREADS + tid; const bool ok = p < n;
+                const uint32_t act = __ballot_sync(0xffffffffu, ok);
+                if (ok) { const uint32_t peers = __match_any_sync(act, dv[u]); if ((peers & lt) == 0) atomicAdd(&s_cnt[dv[u]], (uint32_t)__popc(peers)); }
+            }
+        }
+        /* the phases that happened, in time order (== ascending region) */
+        if (tid < 256) {
+            const lq_afq_phase p = ph[tid];
+            const bool ok = p.t != 0xffffffffu;
+            const uint32_t m = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0) s_scan[wid] = __popc(m);
+            __syncwarp();
+            /* finished below, behind the barrier */
+            if (ok) { s_pk[tid] = __popc(m & lt); s_pt[tid] = p.t; s_pp[tid] = p.p; } else s_pk[tid] = 0xffffffffu;
+        }
+        __syncthreads();
+        uint32_t my_pt = 0, my_pp = 0, my_at = 0xffffffffu;
+        if (tid < 256 && s_pk[tid] != 0xffffffffu) {
+            uint32_t basew = 0;
+            for (uint32_t w = 0; w < wid; ++w) basew += s_scan[w];
+            my_at = basew + s_pk[tid]; my_pt = s_pt[tid]; my_pp = s_pp[tid];
+        }
+        if (wid == 0) {
+            uint32_t loc = 0;
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) loc += s_cnt[8 * lane + j];
+            uint32_t run = lq_warp_incl_scan(loc) - loc;
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) { s_start[8 * lane + j] = run; run += s_cnt[8 * lane + j]; }
+            if (lane == 31) s_start[256] = n;
+        }
+        __syncthreads();
+        if (tid == 0) { uint32_t np = 0; for (uint32_t w = 0; w < 8; ++w) np += s_scan[w]; s_np = np; s_carry_slot = 0; s_carry_d = 0; }
+        if (my_at != 0xffffffffu) { s_pt[my_at] = my_pt; s_pp[my_at] = my_pp; s_pk[my_at] = tid; }
+        __syncthreads();
+        const uint32_t np = s_np;
+        for (uint32_t t0 = 0; t0 < n; t0 += AFP_TILE) {
+            const uint32_t wbase = t0 + wid * (AFP_ROWS * 32);
+            /* a. digit counts of every warp's stretch */
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) s_w[wid][lane + 32 * j] = 0;
+            __syncwarp();
+            uint32_t dv[AFP_ROWS];
+            #pragma unroll
+            for (int r = 0; r < AFP_ROWS; ++r) { const uint32_t t = wbase + r * 32 + lane; dv[r] = t < n ? seq[t] : 0; }
+            #pragma unroll
+            for (int r = 0; r < AFP_ROWS; ++r) {
+                const uint32_t t = wbase + r * 32 + lane; const bool ok = t < n;
+                const uint32_t act = __ballot_sync(0xffffffffu, ok);
+                if (ok) { const uint32_t peers = __match_any_sync(act, dv[r]); if ((peers & lt) == 0) s_w[wid][dv[r]] += __popc(peers); }
+                __syncwarp();
+            }
+            __syncthreads();
+            /* b. digit d: exclusive prefix over the warps; the tile's total is added to the running count afterwards */
+            uint32_t tot_d = 0;
+            if (tid < 256) {
+                #pragma unroll
+                for (int w = 0; w < AFB_THREADS / 32; ++w) { const uint32_t c = s_w[w][tid]; s_w[w][tid] = tot_d; tot_d += c; }
+            }
+            __syncthreads();
+            /* c. slots */
+            #pragma unroll
+            for (int r = 0; r < AFP_ROWS; ++r) {
+                const uint32_t t = wbase + r * 32 + lane; const bool ok = t < n;
+                const uint32_t act = __ballot_sync(0xffffffffu, ok);
+                uint32_t peers = 0;
+                if (ok) {
+                    peers = __match_any_sync(act, dv[r]);
+                    s_slot[t - t0] = s_start[dv[r]] + s_run[dv[r]] + s_w[wid][dv[r]] + __popc(peers & lt);
+                }
+                __syncwarp();
+                if (ok && (peers & lt) == 0) s_w[wid][dv[r]] += __popc(peers);
+                __syncwarp();
+            }
+            __syncthreads();
+            /* d. source positions, payload */
+            #pragma unroll
+            for (int r = 0; r < AFP_ROWS; ++r) {
+                const uint32_t t = wbase + r * 32 + lane;
+                if (t < n) {
+                    /* phase in force at t: the last one with start <= t */
+                    uint32_t lo = 0, hi = np;
+                    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_pt[mid] <= t) lo = mid; else hi = mid; }
+                    uint32_t ord;
+                    if (s_pt[lo] == t) ord = s_pp[lo];
+                    else {
+                        const uint32_t ps = t == t0 ? s_carry_slot : s_slot[t - 1 - t0];
+                        const uint32_t pdd = t == t0 ? s_carry_d : (uint32_t)seq[t - 1];
+                        /* the phase in force at t-1 is `lo` as well: a phase that opens at t is the case above */
+                        ord = ps + (pdd == s_pk[lo] ? 1u : 0u);
+                    }
+                    const uint32_t sl = s_slot[t - t0];
+                    idx2[sl] = idx[ord]; kx2[sl] = kx[ord];
+                }
+            }
+            __syncthreads();
+            if (tid < 256) s_run[tid] += tot_d;
+            if (tid == 0) { const uint32_t last = (t0 + AFP_TILE <= n ? AFP_TILE : n - t0) - 1; s_carry_slot = s_slot[last]; s_carry_d = seq[t0 + last]; }
+            __syncthreads();
+        }
+        /* sub-buckets */
+        afb_subbuckets(a, beg, n, s_cnt, s_start);
     }
 }
 
@@ -1521,13 +1782,17 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     }
     /* bucket lists: at most nb/65 + nqb live buckets per level */
     const size_t bcap = (size_t)(nb / (LQ_RS_MIN + 1)) + nqb + 16, bcapb = (size_t)(nb / AFB_MIN) + nqb + 16;
-    LQ_TRY(sc->bkt.ensure((4 * bcap + 2 * bcapb) * sizeof(AfBkt)));
+    const size_t bcapw = (size_t)(nb / AFW_SMALL) + nqb + 16;   /* long walks: buckets of >= AFW_SMALL elements */
+    LQ_TRY(sc->bkt.ensure((4 * bcap + 2 * bcapb + bcapw) * sizeof(AfBkt)));
+    LQ_TRY(sc->wph.ensure(2 * bcapw * 256 * sizeof(lq_afq_phase)));
     LQ_TRY(sc->wst.ensure((size_t)AFS_GRID * AFS_WALKERS * AFS_ROW * 4));
-    LQ_CUDA_OK(cudaFuncSetAttribute(lq_af_walk_k, cudaFuncAttributeMaxDynamicSharedMemorySize, AFS_WALKERS * 4096));
+    LQ_CUDA_OK(cudaFuncSetAttribute(lq_af_walk3_k, cudaFuncAttributeMaxDynamicSharedMemorySize, AFS_WALKERS * 4096));
+    LQ_CUDA_OK(cudaFuncSetAttribute(lq_af_walkf_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AffSmem)));
     AfBkt *bk[2] = { sc->bkt.as<AfBkt>(), sc->bkt.as<AfBkt>() + bcap };
     AfBkt *wl = sc->bkt.as<AfBkt>() + 2 * bcap;
     AfBkt *wls = sc->bkt.as<AfBkt>() + 3 * bcap;                                                     /* short walks: ctr[14] = count, ctr[15] = cursor */
     AfBkt *bkb[2] = { sc->bkt.as<AfBkt>() + 4 * bcap, sc->bkt.as<AfBkt>() + 4 * bcap + bcapb };   /* long buckets: ctr[11], ctr[12] = counts, ctr[13] = cursor */
+    AfBkt *wlw = sc->bkt.as<AfBkt>() + 4 * bcap + 2 * bcapb;                                         /* few-region walks: ctr[52] = count, ctr[53] = cursor */
     /* counters: ctr[0],ctr[1] = bucket counts of the two lists, ctr[2] = cursor, ctr[3] = walks */
     lq_prof_count_launch(1);
     lq_af_init_k<<<lq_grid(nqb, 128), 128, 0, st>>>(nqb, d_qoff, b->ax, b->idx, bk[0], ctr + 0, bkb[0], ctr + 11);
@@ -1544,8 +1809,10 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         a.cur = bk[cur]; a.n_cur = ctr + cur; a.nxt = bk[cur ^ 1]; a.n_nxt = ctr + (cur ^ 1); a.cursor = ctr + 2; a.n_walk = ctr + 3; a.shift = shift;
         a.wlist = wl; a.n_wlist = ctr + 9; a.wcursor = ctr + 10;
         a.wlist_s = wls; a.n_wlist_s = ctr + 14; a.wcursor_s = ctr + 15; a.wcursor_f = ctr + 48;
+        a.wlist_w = wlw; a.n_wlist_w = ctr + 52; a.wcursor_w = ctr + 53; a.wph = sc->wph.as<lq_afq_phase>(); a.wph_cap = (uint32_t)bcapw;
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 14, 0, 8, st));
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 48, 0, 4, st));
+        LQ_CUDA_OK(cudaMemsetAsync(ctr + 52, 0, 8, st));
         a.curb = bkb[cur]; a.n_curb = ctr + 11 + cur; a.nxtb = bkb[cur ^ 1]; a.n_nxtb = ctr + 11 + (cur ^ 1); a.cursorb = ctr + 13;
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 11 + (cur ^ 1), 0, 4, st));
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 13, 0, 4, st));
@@ -1555,12 +1822,13 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         unsigned long long *n_elem = (unsigned long long*)(ctr + 16);
         a.n_elem = n_elem + (shift >> 3);
         { LqProfScope ps(lvl_name[shift >> 3], st, 2, 0);
-          lq_af_big_k<false><<<148 * 4, AFB_THREADS, 0, st>>>(a);
+          lq_af_big_k<<<148 * 4, AFB_THREADS, 0, st>>>(a);
           lq_af_level_k<<<148 * 16, AF_WARPS * 32, 0, st>>>(a); }
         a.n_elem = n_elem + 8 + (shift >> 3);
-        { LqProfScope ps(wlk_name[shift >> 3], st, 3, 0);
-          lq_af_walk_k<<<AFS_GRID, AFS_THREADS, AFS_WALKERS * 4096, st>>>(a, sc->wst.as<uint32_t>());
-          lq_af_big_k<true><<<148 * 4, AFB_THREADS, 0, st>>>(a);
+        { LqProfScope ps(wlk_name[shift >> 3], st, 4, 0);
+          lq_af_walk3_k<<<AFS_GRID, AFS_THREADS, AFS_WALKERS * 4096, st>>>(a, sc->wst.as<uint32_t>());
+          lq_af_walkf_k<<<AFF_GRID, AFF_THREADS, sizeof(AffSmem), st>>>(a);
+          lq_af_place_k<<<148 * 3, AFB_THREADS, 0, st>>>(a);
           lq_af_walk_small_k<<<148 * 16, AFW_WARPS * 32, 0, st>>>(a); }
         LQ_CUDA_OK(cudaGetLastError());
         cur ^= 1;

@@ -39,8 +39,8 @@ struct LqQueryDev {
 struct LqQStat { uint32_t n_kept; uint32_t sum_span_kept; uint64_t n_seeds; uint64_t sum_span_seeds; uint32_t gate_closed; float avg_span; uint64_t n_sorted; };
 
 struct LqMapScratch {
-    LqDevBuf arena1, arena2, bkt, grp, misc, ovl, ws, wst;   /* wst: region starts of the buckets being walked (lq_af_walk_k) */
-    void release() { arena1.release(); arena2.release(); bkt.release(); grp.release(); misc.release(); ovl.release(); ws.release(); wst.release(); }
+    LqDevBuf arena1, arena2, bkt, grp, misc, ovl, ws, wst, wph;   /* wst: region starts of the buckets being walked (lq_af_walk3_k); wph: their phase rows */
+    void release() { arena1.release(); arena2.release(); bkt.release(); grp.release(); misc.release(); ovl.release(); ws.release(); wst.release(); wph.release(); }
 };
 
 struct LqMapStats { uint64_t n_seeds, n_groups, n_chains, n_ovl, n_batches, n_walk_buckets, n_seeds_all; };

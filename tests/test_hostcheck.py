@@ -80,11 +80,16 @@ def _keys(rng, n, mode):
         return (rng.integers(0, 2, n).astype(u) << u(63)) | (rng.integers(0, 1 << 25, n).astype(u) << u(32)) | rng.integers(0, 50, n).astype(u)
     if mode == 3:
         return rng.integers(0, 5, n).astype(u) * u(0x0101010101010101)
+    if mode == 5:   # few regions with small digit values on several levels (rid >> 16 in 0..5, rid & 255 in 0..11, rpos >> 8 in 0..9): many ties
+        return ((rng.integers(0, 2, n).astype(u) << u(63)) | (rng.integers(0, 6, n).astype(u) << u(48)) | (rng.integers(0, 12, n).astype(u) << u(32))
+                | rng.integers(0, 2560, n).astype(u))
     return ((rng.integers(0, 2, n).astype(u) << u(63)) | (rng.integers(0, 2, n).astype(u) << u(48)) | (rng.integers(0, 2, n).astype(u) << u(33))
             | rng.integers(0, 70000, n).astype(u))
 
 
-@pytest.mark.parametrize("use_two", [0, 1, 2, 3, 4, 5])   # bit 0: two-region closed form, bit 1: cached-digit walk, bit 2: packed one-load-per-step walk (device)
+# bit 0: two-region closed form, bit 1: cached-digit walk, bit 2: packed one-load-per-step walk, bit 3: digit-stream walk + expansion (device, long
+# buckets), bit 4: few-region digit-stream walk (device, all digits < 16)
+@pytest.mark.parametrize("use_two", [0, 1, 2, 3, 4, 5, 8, 9, 24, 25])
 def test_seed_sort_walk_and_closed_form(use_two):
     """the queue-walk formulation (and the two-region closed form) reproduce ksort.h's permutation, ties included"""
     hc, o = liblq.hostcheck(), liblq.oracle()
@@ -92,7 +97,7 @@ def test_seed_sort_walk_and_closed_form(use_two):
     rng = np.random.default_rng(30 + use_two)
     for trial in range(250):
         n = int(rng.integers(1, 5000)) if trial % 10 else int(rng.integers(1, 130))
-        x = _keys(rng, n, trial % 5)
+        x = _keys(rng, n, trial % 6)
         a = np.zeros(n, dtype=liblq.mm128_dtype)
         a["x"] = x
         a["y"] = np.arange(n, dtype=np.uint64)
