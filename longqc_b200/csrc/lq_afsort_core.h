@@ -228,24 +228,37 @@ LQ_HD int lq_afq_run(lq_afq_walk *s, uint32_t n, const uint32_t *start, lq_afp_s
     int done = 1;
     if (step < n) {
         lq_afp_st S = st[c * stride];
+        /* one pick-up; J = its byte in the current word of the digit stream (static in the unrolled loop below).  The updated state
+         * is stored BEFORE the state of the digit's region is loaded, so a digit that names the region just read sees the update. */
+#define LQ_AFQ_STEP(J) { \
+            const uint32_t left = S.w >> 24; \
+            if (left == 0) { done = 0; break; } \
+            const uint32_t d = S.y & 255u; \
+            S.x += 1; S.y = LQ_FUNNEL_R8(S.y, S.z); S.z = LQ_FUNNEL_R8(S.z, S.w); S.w = ((S.w >> 8) & 0xffffu) | (left - 1) << 24; \
+            st[c * stride] = S; \
+            acc |= d << (8 * (J)); \
+            if ((J) == 3) { seq32[step >> 2] = acc; acc = 0; } \
+            c = d; \
+            S = st[c * stride]; \
+            if (d == k && S.x == end_k) {                         /* region k complete: open the next non-exhausted region */ \
+                do { ++k; } while (k < 256 && st[k * stride].x == start[k + 1]); \
+                if (k < 256) { c = k; end_k = start[k + 1]; S = st[c * stride]; ph[k].t = step + 1; ph[k].p = S.x; } \
+                else { c = 0; S = st[0]; } \
+            } \
+            if (++step >= n) break; }
         for (;;) {
-            const uint32_t left = S.w >> 24;
-            if (left == 0) { done = 0; break; }
-            const uint32_t d = S.y & 255u;
-            const lq_afp_st Sn = st[d * stride];                  /* the digit's region, loaded as soon as the digit is known */
-            S.x += 1; S.y = LQ_FUNNEL_R8(S.y, S.z); S.z = LQ_FUNNEL_R8(S.z, S.w); S.w = ((S.w >> 8) & 0xffffu) | (left - 1) << 24;
-            st[c * stride] = S;
-            acc |= d << (8 * (step & 3u));
-            if ((step & 3u) == 3u) { seq32[step >> 2] = acc; acc = 0; }
-            if (d != c) S = Sn;                                   /* Sn is stale only when the digit names the region just read */
-            c = d;
-            if (d == k && S.x == end_k) {                         /* region k complete: open the next non-exhausted region */
-                do { ++k; } while (k < 256 && st[k * stride].x == start[k + 1]);
-                if (k < 256) { c = k; end_k = start[k + 1]; S = st[c * stride]; ph[k].t = step + 1; ph[k].p = S.x; }
-                else { c = 0; S = st[0]; }
+            switch (step & 3u) {      /* resume in the middle of a word after a refill */
+            case 0: LQ_AFQ_STEP(0)
+            /* fall through */
+            case 1: LQ_AFQ_STEP(1)
+            /* fall through */
+            case 2: LQ_AFQ_STEP(2)
+            /* fall through */
+            default: LQ_AFQ_STEP(3)
             }
-            if (++step >= n) break;
+            if (!done || step >= n) break;
         }
+#undef LQ_AFQ_STEP
         if (step >= n && (step & 3u)) seq32[step >> 2] = acc;     /* the last, partial word */
     }
     s->k = k; s->c = c; s->step = step; s->end_k = end_k; s->acc = acc;

@@ -12,6 +12,7 @@
 #include <sys/time.h>
 #include <sys/resource.h>
 #include <pthread.h>
+#include <unistd.h>
 #include "lqcov.h"
 #include "lq_ingest.h"
 
@@ -310,6 +311,11 @@ int lqcov_main(int argc, char **argv)
     argp_parse(&the_argp, argc, argv, 0, 0, &a);
     lqcov_opt_init(&o);
     o.verbose = 3;
+    /* stdout carries the table and nothing else (lq_coverage.py parses it): whatever a library prints there (NCCL's version banner
+     * under NCCL_DEBUG, for one) is sent to stderr instead, and the table goes to the saved descriptor at the end */
+    fflush(stdout);
+    const int out_fd = dup(STDOUT_FILENO);
+    dup2(STDERR_FILENO, STDOUT_FILENO);
 
     if (a.ava && a.avs) { fprintf(stderr, "Error: -X and -Y are mutually exclusive\n"); return 1; }
     if (!a.ava && !a.avs && !a.dump) { fprintf(stderr, "Error: Choose either -X (all-vs-all) or -Y (all-vs-sub)\n"); return 1; }
@@ -378,8 +384,11 @@ int lqcov_main(int argc, char **argv)
     if (rc == 0) rc = lqcov_part_begin(dv[0].c, 0, 0) == 1 ? run_parts_whole(&dv[0], tr, &o, t0) : run_parts(dv, n_dev, tr, &o, t0);
     lqi_close(tr);
     if (rc == 0 && on_all(dv, n_dev, dev_table) != 0) rc = 1;
-    if (rc == 0) for (int i = 0; i < n_dev; ++i) { fwrite(dv[i].tab, 1, dv[i].tab_len, stdout); lqcov_free(dv[i].tab); }
-    fflush(stdout);
+    if (rc == 0) {
+        FILE *out = fdopen(out_fd, "w");
+        for (int i = 0; i < n_dev; ++i) { fwrite(dv[i].tab, 1, dv[i].tab_len, out); lqcov_free(dv[i].tab); }
+        fclose(out);
+    }
     lqcov_reader_close(qr);
     TL("table written");
     if (!getenv("LQCOV_FAST_EXIT")) for (int i = 0; i < n_dev; ++i) lqcov_destroy(dv[i].c);

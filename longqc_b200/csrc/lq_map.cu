@@ -814,6 +814,7 @@ __global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
 #define AFS_THREADS 512
 #define AFS_GRID 148               /* one CTA per SM (224 KB of shared memory each) */
 #define AFS_ROW 260                /* u32 per bucket in the global scratch: 257 region starts */
+#define AFS_LOW 5                  /* regions holding more cached digits than this are not refilled */
 __device__ __forceinline__ uint4 afw_load16(const uint8_t *addr)   /* 16 bytes from an arbitrary address (reads up to 31 bytes past it: the arena is padded) */
 {
     const uintptr_t A = (uintptr_t)addr & ~(uintptr_t)15; const uint32_t o = (uint32_t)((uintptr_t)addr & 15), q = o >> 2, sh = (o & 3) * 8;
@@ -914,19 +915,30 @@ __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk3_k(AfArgs a, uint32
             lq_afq_init(&ws, my_start, my_ph); fin = false; my_n = meta[wl].n; my_seq = a.ord + meta[wl].beg;
         }
         for (;;) {
-            for (uint32_t e0 = tid; e0 < AFS_WALKERS * 256; e0 += 4 * AFS_THREADS) {   /* refill: consecutive threads, consecutive words; 4 loads in flight */
-                lq_afp_st S[4]; bool need[4]; uint4 v[4];
+            /* refill: consecutive threads, consecutive state words.  Only regions that are running low are topped up (a region that
+             * still holds more than AFS_LOW digits would fetch the same sector again a round later: measured 10.5 GB of DRAM reads
+             * for 0.32 GB of digits when every region that had moved was refilled).  All 16 word loads of a thread are issued before
+             * the first is used. */
+            for (uint32_t e0 = tid; e0 < AFS_WALKERS * 256; e0 += 4 * AFS_THREADS) {
+                lq_afp_st S[4]; bool need[4]; uint32_t wv[4][4], sh[4];
                 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const uint32_t e = e0 + u * AFS_THREADS;
                     need[u] = false;
-                    if (e < AFS_WALKERS * 256 && e % AFS_WALKERS < nbk) { S[u] = state[e]; need[u] = (S[u].w >> 24) < LQ_AFP_DIG; }   /* the region moved since its last refill */
+                    if (e < AFS_WALKERS * 256 && e % AFS_WALKERS < nbk) { S[u] = state[e]; need[u] = (S[u].w >> 24) <= AFS_LOW; }
                 }
                 #pragma unroll
-                for (int u = 0; u < 4; ++u) if (need[u]) v[u] = afw_load16(a.dig + meta[(e0 + u * AFS_THREADS) % AFS_WALKERS].beg + S[u].x);
+                for (int u = 0; u < 4; ++u) {
+                    const uint8_t *p = a.dig + meta[need[u] ? (e0 + u * AFS_THREADS) % AFS_WALKERS : 0].beg + (need[u] ? S[u].x : 0);
+                    const uint32_t *q = (const uint32_t*)((uintptr_t)p & ~(uintptr_t)3);
+                    sh[u] = (uint32_t)((uintptr_t)p & 3) * 8;
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) wv[u][j] = need[u] ? __ldg(q + j) : 0;   /* the arena is padded: 16 bytes from q stay inside it */
+                }
                 #pragma unroll
                 for (int u = 0; u < 4; ++u) if (need[u]) {
-                    S[u].y = v[u].x; S[u].z = v[u].y; S[u].w = (v[u].z & 0x00ffffffu) | (uint32_t)LQ_AFP_DIG << 24;
+                    S[u].y = __funnelshift_r(wv[u][0], wv[u][1], sh[u]); S[u].z = __funnelshift_r(wv[u][1], wv[u][2], sh[u]);
+                    S[u].w = (__funnelshift_r(wv[u][2], wv[u][3], sh[u]) & 0x00ffffffu) | (uint32_t)LQ_AFP_DIG << 24;
                     state[e0 + u * AFS_THREADS] = S[u];
                 }
             }
@@ -1134,18 +1146,21 @@ __global__ void __launch_bounds__(AFB_THREADS) lq_af_place_k(AfArgs a)
         const uint32_t np = s_np;
         for (uint32_t t0 = 0; t0 < n; t0 += AFP_TILE) {
             const uint32_t wbase = t0 + wid * (AFP_ROWS * 32);
-            /* a. digit counts of every warp's stretch */
+            /* a. rank of every pick-up among the equal digits of its warp's stretch (rows in order), and the stretch's digit counts */
             #pragma unroll
             for (int j = 0; j < 8; ++j) s_w[wid][lane + 32 * j] = 0;
             __syncwarp();
-            uint32_t dv[AFP_ROWS];
+            uint32_t dv[AFP_ROWS], lr[AFP_ROWS];
             #pragma unroll
             for (int r = 0; r < AFP_ROWS; ++r) { const uint32_t t = wbase + r * 32 + lane; dv[r] = t < n ? seq[t] : 0; }
             #pragma unroll
             for (int r = 0; r < AFP_ROWS; ++r) {
                 const uint32_t t = wbase + r * 32 + lane; const bool ok = t < n;
                 const uint32_t act = __ballot_sync(0xffffffffu, ok);
-                if (ok) { const uint32_t peers = __match_any_sync(act, dv[r]); if ((peers & lt) == 0) s_w[wid][dv[r]] += __popc(peers); }
+                uint32_t peers = 0; lr[r] = 0;
+                if (ok) { peers = __match_any_sync(act, dv[r]); lr[r] = s_w[wid][dv[r]] + __popc(peers & lt); }
+                __syncwarp();
+                if (ok && (peers & lt) == 0) s_w[wid][dv[r]] += __popc(peers);
                 __syncwarp();
             }
             __syncthreads();
@@ -1159,16 +1174,8 @@ __global__ void __launch_bounds__(AFB_THREADS) lq_af_place_k(AfArgs a)
             /* c. slots */
             #pragma unroll
             for (int r = 0; r < AFP_ROWS; ++r) {
-                const uint32_t t = wbase + r * 32 + lane; const bool ok = t < n;
-                const uint32_t act = __ballot_sync(0xffffffffu, ok);
-                uint32_t peers = 0;
-                if (ok) {
-                    peers = __match_any_sync(act, dv[r]);
-                    s_slot[t - t0] = s_start[dv[r]] + s_run[dv[r]] + s_w[wid][dv[r]] + __popc(peers & lt);
-                }
-                __syncwarp();
-                if (ok && (peers & lt) == 0) s_w[wid][dv[r]] += __popc(peers);
-                __syncwarp();
+                const uint32_t t = wbase + r * 32 + lane;
+                if (t < n) s_slot[t - t0] = s_start[dv[r]] + s_run[dv[r]] + s_w[wid][dv[r]] + lr[r];
             }
             __syncthreads();
             /* d. source positions, payload */
@@ -1755,11 +1762,11 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     const uint32_t nqb = q1 - q0;
     LQ_TRY(carve(sc, nb, b));
     /* misc: qoff (nqb+1 u64) | counters (16 u32) */
-    LQ_TRY(sc->misc.ensure(al((size_t)(nqb + 2) * 8) + 256));
+    LQ_TRY(sc->misc.ensure(al((size_t)(nqb + 2) * 8) + 512));
     uint64_t *d_qoff = sc->misc.as<uint64_t>();
     uint32_t *ctr = (uint32_t*)((char*)sc->misc.p + al((size_t)(nqb + 2) * 8));
     LQ_CUDA_OK(cudaMemcpyAsync(d_qoff, h_qoff.data(), (size_t)(nqb + 1) * 8, cudaMemcpyHostToDevice, st));
-    LQ_CUDA_OK(cudaMemsetAsync(ctr, 0, 256, st));   /* ctr[0..15]: u32 counters; ctr[16..47]: 16 u64 element counters (8 levels, 8 walks) */
+    LQ_CUDA_OK(cudaMemsetAsync(ctr, 0, 512, st));   /* ctr[0..15], ctr[48..55]: u32 counters; ctr[16..47]: 16 u64 element counters (8 levels, 8 long walks); ctr[64..79]: 8 more (short walks) */
     *d_qoff_out = d_qoff;
     if (nb == 0) return 0;
     if (nb >= (1ULL << 31)) { fprintf(stderr, "[lqcov] a batch of %llu seeds exceeds the 31-bit seed numbers of the sort\n", (unsigned long long)nb); return -1; }
@@ -1798,6 +1805,8 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     lq_af_init_k<<<lq_grid(nqb, 128), 128, 0, st>>>(nqb, d_qoff, b->ax, b->idx, bk[0], ctr + 0, bkb[0], ctr + 11);
     LQ_CUDA_OK(cudaGetLastError());
     static const char *lvl_name[8] = { "seed_sort_s0", "seed_sort_s8", "seed_sort_s16", "seed_sort_s24", "seed_sort_s32", "seed_sort_s40", "seed_sort_s48", "seed_sort_s56" };
+    static const char *plc_name[8] = { "seed_place_s0", "seed_place_s8", "seed_place_s16", "seed_place_s24", "seed_place_s32", "seed_place_s40", "seed_place_s48", "seed_place_s56" };
+    static const char *wls_name[8] = { "seed_walksmall_s0", "seed_walksmall_s8", "seed_walksmall_s16", "seed_walksmall_s24", "seed_walksmall_s32", "seed_walksmall_s40", "seed_walksmall_s48", "seed_walksmall_s56" };
     static const char *wlk_name[8] = { "seed_walk_s0", "seed_walk_s8", "seed_walk_s16", "seed_walk_s24", "seed_walk_s32", "seed_walk_s40", "seed_walk_s48", "seed_walk_s56" };
     int cur = 0;
     for (int shift = 56; shift >= 0; shift -= 8) {
@@ -1825,10 +1834,13 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
           lq_af_big_k<<<148 * 4, AFB_THREADS, 0, st>>>(a);
           lq_af_level_k<<<148 * 16, AF_WARPS * 32, 0, st>>>(a); }
         a.n_elem = n_elem + 8 + (shift >> 3);
-        { LqProfScope ps(wlk_name[shift >> 3], st, 4, 0);
+        { LqProfScope ps(wlk_name[shift >> 3], st, 2, 0);
           lq_af_walk3_k<<<AFS_GRID, AFS_THREADS, AFS_WALKERS * 4096, st>>>(a, sc->wst.as<uint32_t>());
-          lq_af_walkf_k<<<AFF_GRID, AFF_THREADS, sizeof(AffSmem), st>>>(a);
-          lq_af_place_k<<<148 * 3, AFB_THREADS, 0, st>>>(a);
+          lq_af_walkf_k<<<AFF_GRID, AFF_THREADS, sizeof(AffSmem), st>>>(a); }
+        { LqProfScope ps(plc_name[shift >> 3], st, 1, 0);
+          lq_af_place_k<<<148 * 3, AFB_THREADS, 0, st>>>(a); }
+        a.n_elem = (unsigned long long*)(ctr + 64) + (shift >> 3);
+        { LqProfScope ps(wls_name[shift >> 3], st, 1, 0);
           lq_af_walk_small_k<<<148 * 16, AFW_WARPS * 32, 0, st>>>(a); }
         LQ_CUDA_OK(cudaGetLastError());
         cur ^= 1;
@@ -1837,15 +1849,21 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     lq_gather_k<<<lq_grid(nb, 256), 256, 0, st>>>(nb, b->idx, b->s, b->aq, b->am);
     LQ_CUDA_OK(cudaGetLastError());
     if (stats) {
-        uint32_t w = 0; unsigned long long ne[16];
+        uint32_t w = 0; unsigned long long ne[16], nes[8];
         LQ_CUDA_OK(cudaMemcpyAsync(&w, ctr + 3, 4, cudaMemcpyDeviceToHost, st));
         LQ_CUDA_OK(cudaMemcpyAsync(ne, ctr + 16, sizeof ne, cudaMemcpyDeviceToHost, st));
+        LQ_CUDA_OK(cudaMemcpyAsync(nes, ctr + 64, sizeof nes, cudaMemcpyDeviceToHost, st));
         LQ_CUDA_OK(cudaStreamSynchronize(st));
         stats->n_walk_buckets += w;
         if (lq_prof_on()) {
             /* algorithmic bytes per element and level: the 12-byte (key, seed number) pair read once and written once.
              * Digits, destinations and pick-up lists are this implementation's own traffic and are not counted. */
-            for (int l = 0; l < 8; ++l) { lq_prof_add_bytes(lvl_name[l], ne[l] * 24ULL); lq_prof_add_bytes(wlk_name[l], ne[8 + l] * 24ULL); }
+            for (int l = 0; l < 8; ++l) {
+                lq_prof_add_bytes(lvl_name[l], ne[l] * 24ULL);
+                lq_prof_add_bytes(wlk_name[l], ne[8 + l] * 2ULL);      /* the sequential part: one digit byte in, one out */
+                lq_prof_add_bytes(plc_name[l], ne[8 + l] * 24ULL);
+                lq_prof_add_bytes(wls_name[l], nes[l] * 24ULL);
+            }
         }
     }
     return 0;
