@@ -283,15 +283,14 @@ LQ_HD void lq_afq_expand(const uint8_t *seq, uint32_t n, const uint32_t *start, 
 }
 
 /* ---- the same walk for levels with FEW regions (all digits < 16: the rid >> 16 byte once a part holds more than 131 072 reads).
- * With 11 cached digits per region a 4-region walk runs dry every ~40 pick-ups; here a region caches LQ_AFR_CAP digits
- * (cache[(r * LQ_AFR_WORDS + w) * stride], four digits per word) and its read offset inside that stretch is one BYTE of four
- * registers, so a step is: pick the byte (prmt), one 32-bit load, shift -- no per-region state is written back. */
-#define LQ_AFR_CAP 240
+ * With 11 cached digits per region a 4-region walk runs dry every ~40 pick-ups; here a region caches LQ_AFR_CAP digits, four per
+ * word: blk[(r * LQ_AFR_BLK + 1 + w) * stride], and word 0 of the block is the region's read offset inside that stretch.  A step is
+ * two dependent 32-bit loads (offset, digit word) and a handful of ALU operations; the offset is stored back off the critical path. */
+#define LQ_AFR_CAP 236
 #define LQ_AFR_WORDS (LQ_AFR_CAP / 4)
+#define LQ_AFR_BLK (LQ_AFR_WORDS + 1)
 #define LQ_AFR_R 16
-typedef struct { uint32_t k, c, step, acc, rem_k; uint32_t off[4]; } lq_afr_walk;
-
-LQ_HD uint32_t lq_afr_off(const lq_afr_walk *s, uint32_t r) { return (s->off[r >> 2] >> (8 * (r & 3u))) & 255u; }
+typedef struct { uint32_t k, c, step, acc, rem_k; } lq_afr_walk;
 
 /* base[r * bstride]: bucket-relative position of the first cached digit of region r (== next unread position - offset) */
 LQ_HD void lq_afr_init(lq_afr_walk *s, const uint32_t *start, lq_afq_phase *ph)
@@ -299,58 +298,67 @@ LQ_HD void lq_afr_init(lq_afr_walk *s, const uint32_t *start, lq_afq_phase *ph)
     uint32_t k = 0;
     while (k < LQ_AFR_R && start[k + 1] == start[k]) ++k;
     s->k = k; s->c = k < LQ_AFR_R ? k : 0; s->step = 0; s->acc = 0; s->rem_k = k < LQ_AFR_R ? start[k + 1] - start[k] : 0;
-    s->off[0] = s->off[1] = s->off[2] = s->off[3] = 0;
     if (k < LQ_AFR_R) { ph[k].t = 0; ph[k].p = start[k]; }
 }
 
-LQ_HD int lq_afr_run(lq_afr_walk *s, uint32_t n, const uint32_t *start, const uint32_t *cache, uint32_t stride, const uint32_t *base, uint32_t bstride,
+LQ_HD int lq_afr_run(lq_afr_walk *s, uint32_t n, const uint32_t *start, uint32_t *blk, uint32_t stride, const uint32_t *base, uint32_t bstride,
                      uint32_t *seq32, lq_afq_phase *ph)
 {
     uint32_t k = s->k, c = s->c, step = s->step, acc = s->acc, rem_k = s->rem_k;
-    uint32_t o0 = s->off[0], o1 = s->off[1], o2 = s->off[2], o3 = s->off[3];
     int done = 1;
-    while (step < n) {
-        const uint32_t ow = (c >> 2) == 0 ? o0 : (c >> 2) == 1 ? o1 : (c >> 2) == 2 ? o2 : o3;
-        const uint32_t sh = 8 * (c & 3u), off = (ow >> sh) & 255u;
-        if (off >= LQ_AFR_CAP) { done = 0; break; }
-        const uint32_t w = cache[(c * LQ_AFR_WORDS + (off >> 2)) * stride];
-        const uint32_t d = (w >> (8 * (off & 3u))) & 255u;
-        const uint32_t inc = 1u << sh;
-        if ((c >> 2) == 0) o0 += inc; else if ((c >> 2) == 1) o1 += inc; else if ((c >> 2) == 2) o2 += inc; else o3 += inc;
-        if (c == k) --rem_k;
-        acc |= d << (8 * (step & 3u));
-        if ((step & 3u) == 3u) { seq32[step >> 2] = acc; acc = 0; }
-        c = d;
-        if (d == k && rem_k == 0) {                               /* region k complete: open the next non-exhausted region */
-            for (;;) {
-                ++k;
-                if (k >= LQ_AFR_R) break;
-                const uint32_t okw = (k >> 2) == 0 ? o0 : (k >> 2) == 1 ? o1 : (k >> 2) == 2 ? o2 : o3;
-                const uint32_t nxt = base[k * bstride] + ((okw >> (8 * (k & 3u))) & 255u);   /* next unread position of region k */
-                if (nxt != start[k + 1]) { c = k; rem_k = start[k + 1] - nxt; ph[k].t = step + 1; ph[k].p = nxt; break; }
+    if (step < n) {
+#define LQ_AFR_STEP(J) { \
+            uint32_t *rb = blk + c * (LQ_AFR_BLK * stride); \
+            const uint32_t off = rb[0]; \
+            if (off >= LQ_AFR_CAP) { done = 0; break; } \
+            const uint32_t w = rb[(1 + (off >> 2)) * stride]; \
+            const uint32_t d = (w >> (8 * (off & 3u))) & 255u; \
+            rb[0] = off + 1; \
+            if (c == k) --rem_k; \
+            acc |= d << (8 * (J)); \
+            if ((J) == 3) { seq32[step >> 2] = acc; acc = 0; } \
+            c = d; \
+            if (d == k && rem_k == 0) {                           /* region k complete: open the next non-exhausted region */ \
+                for (;;) { \
+                    ++k; \
+                    if (k >= LQ_AFR_R) break; \
+                    const uint32_t nxt = base[k * bstride] + blk[k * (LQ_AFR_BLK * stride)];   /* next unread position of region k */ \
+                    if (nxt != start[k + 1]) { c = k; rem_k = start[k + 1] - nxt; ph[k].t = step + 1; ph[k].p = nxt; break; } \
+                } \
+                if (k >= LQ_AFR_R) c = 0; \
+            } \
+            if (++step >= n) break; }
+        for (;;) {
+            switch (step & 3u) {
+            case 0: LQ_AFR_STEP(0)
+            /* fall through */
+            case 1: LQ_AFR_STEP(1)
+            /* fall through */
+            case 2: LQ_AFR_STEP(2)
+            /* fall through */
+            default: LQ_AFR_STEP(3)
             }
-            if (k >= LQ_AFR_R) c = 0;
+            if (!done || step >= n) break;
         }
-        ++step;
+#undef LQ_AFR_STEP
+        if (step >= n && (step & 3u)) seq32[step >> 2] = acc;
     }
-    if (done && (step & 3u)) seq32[step >> 2] = acc;
-    s->k = k; s->c = c; s->step = step; s->acc = acc; s->rem_k = rem_k; s->off[0] = o0; s->off[1] = o1; s->off[2] = o2; s->off[3] = o3;
+    s->k = k; s->c = c; s->step = step; s->acc = acc; s->rem_k = rem_k;
     return done;
 }
 
 /* host form of the few-region refill: every region's cached stretch restarts at its next unread position */
-LQ_HD void lq_afr_refill_host(const uint8_t *dig, uint32_t n, lq_afr_walk *s, uint32_t *cache, uint32_t *base)
+LQ_HD void lq_afr_refill_host(const uint8_t *dig, uint32_t n, uint32_t *blk, uint32_t *base)
 {
     for (uint32_t r = 0; r < LQ_AFR_R; ++r) {
-        const uint32_t p = base[r] + lq_afr_off(s, r);
-        base[r] = p;
+        const uint32_t p = base[r] + blk[r * LQ_AFR_BLK];
+        base[r] = p; blk[r * LQ_AFR_BLK] = 0;
         for (uint32_t w = 0; w < LQ_AFR_WORDS; ++w) {
             uint32_t v = 0;
             for (uint32_t j = 0; j < 4; ++j) { const uint32_t q = p + 4 * w + j; v |= (uint32_t)(q < n ? dig[q] : 0) << (8 * j); }
-            cache[r * LQ_AFR_WORDS + w] = v;
+            blk[r * LQ_AFR_BLK + 1 + w] = v;
         }
     }
-    s->off[0] = s->off[1] = s->off[2] = s->off[3] = 0;
 }
 
 /* Closed form for exactly two non-empty digits d0 < d1 (regions [0,n0) and [n0,n)).

@@ -814,7 +814,7 @@ __global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
 #define AFS_THREADS 512
 #define AFS_GRID 148               /* one CTA per SM (224 KB of shared memory each) */
 #define AFS_ROW 260                /* u32 per bucket in the global scratch: 257 region starts */
-#define AFS_LOW 5                  /* regions holding more cached digits than this are not refilled */
+#define AFS_LOW 10                 /* regions holding more cached digits than this are not refilled (5: twice the rounds, measured slower) */
 __device__ __forceinline__ uint4 afw_load16(const uint8_t *addr)   /* 16 bytes from an arbitrary address (reads up to 31 bytes past it: the arena is padded) */
 {
     const uintptr_t A = (uintptr_t)addr & ~(uintptr_t)15; const uint32_t o = (uint32_t)((uintptr_t)addr & 15), q = o >> 2, sh = (o & 3) * 8;
@@ -969,7 +969,7 @@ __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk3_k(AfArgs a, uint32
 #define AFF_LANES 16
 #define AFF_THREADS 256
 #define AFF_GRID (148 * 3)
-struct AffSmem { uint32_t cache[LQ_AFR_R * LQ_AFR_WORDS][AFF_LANES]; uint32_t base[LQ_AFR_R][AFF_LANES]; uint32_t start[LQ_AFR_R + 1][AFF_LANES]; uint32_t off[4][AFF_LANES]; };
+struct AffSmem { uint32_t blk[LQ_AFR_R * LQ_AFR_BLK][AFF_LANES]; uint32_t base[LQ_AFR_R][AFF_LANES]; uint32_t start[LQ_AFR_R + 1][AFF_LANES]; };   /* blk: per region the read offset, then 59 digit words */
 
 __global__ void __launch_bounds__(AFF_THREADS) lq_af_walkf_k(AfArgs a)
 {
@@ -1014,7 +1014,7 @@ __global__ void __launch_bounds__(AFF_THREADS) lq_af_walkf_k(AfArgs a)
             uint32_t run = 0;
             for (int r = 0; r < LQ_AFR_R; ++r) { S.start[r][tid] = run; S.base[r][tid] = run; run += s_cnt[tid][r]; }
             S.start[LQ_AFR_R][tid] = run;
-            S.off[0][tid] = S.off[1][tid] = S.off[2][tid] = S.off[3][tid] = 0;
+            for (int r = 0; r < LQ_AFR_R; ++r) S.blk[r * LQ_AFR_BLK][tid] = 0;
         }
         __syncthreads();
         const bool walker = wid == 0 && lane < nbk;
@@ -1031,33 +1031,42 @@ __global__ void __launch_bounds__(AFF_THREADS) lq_af_walkf_k(AfArgs a)
             /* refill: every region's cached stretch restarts at its next unread position (base += offset, offset = 0) */
             for (uint32_t e = tid; e < nbk * LQ_AFR_R; e += AFF_THREADS) {
                 const uint32_t w = e % nbk, r = e / nbk;
-                const uint32_t o = (S.off[r >> 2][w] >> (8 * (r & 3u))) & 255u;
-                S.base[r][w] += o;
+                S.base[r][w] += S.blk[r * LQ_AFR_BLK][w];
+                S.blk[r * LQ_AFR_BLK][w] = 0;
             }
             __syncthreads();
-            if (tid < nbk) S.off[0][tid] = S.off[1][tid] = S.off[2][tid] = S.off[3][tid] = 0;
-            for (uint32_t e = tid; e < nbk * LQ_AFR_R * LQ_AFR_WORDS; e += AFF_THREADS) {
-                const uint32_t w = e % nbk, rw = e / nbk, r = rw / LQ_AFR_WORDS, j = rw % LQ_AFR_WORDS;
-                const uint32_t n = meta[w].n, p = S.base[r][w] + 4 * j;
-                const uint8_t *dig = a.dig + meta[w].beg;
-                uint32_t v = 0;
-                if (p + 4 <= n) {
-                    const uintptr_t A = (uintptr_t)(dig + p) & ~(uintptr_t)3; const uint32_t sh = (uint32_t)((uintptr_t)(dig + p) & 3) * 8;
-                    const uint32_t lo = *(const uint32_t*)A, hi = sh ? *(const uint32_t*)(A + 4) : 0;   /* the arena is padded: A + 4 stays inside it */
-                    v = __funnelshift_r(lo, hi, sh);
-                } else {
-                    #pragma unroll
-                    for (int q = 0; q < 4; ++q) if (p + q < n) v |= (uint32_t)dig[p + q] << (8 * q);
+            for (uint32_t e0 = tid; e0 < nbk * LQ_AFR_R * LQ_AFR_WORDS; e0 += 4 * AFF_THREADS) {   /* 8 word loads in flight per thread */
+                uint32_t lo[4], hi[4], sh[4], v[4]; bool fast[4];
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t e = e0 + u * AFF_THREADS;
+                    fast[u] = false; lo[u] = hi[u] = sh[u] = v[u] = 0;
+                    if (e < nbk * LQ_AFR_R * LQ_AFR_WORDS) {
+                        const uint32_t w = e % nbk, rw = e / nbk, r = rw / LQ_AFR_WORDS, j = rw % LQ_AFR_WORDS;
+                        const uint32_t n = meta[w].n, p = S.base[r][w] + 4 * j;
+                        const uint8_t *dig = a.dig + meta[w].beg;
+                        if (p + 4 <= n) {
+                            const uint32_t *q = (const uint32_t*)((uintptr_t)(dig + p) & ~(uintptr_t)3);
+                            sh[u] = (uint32_t)((uintptr_t)(dig + p) & 3) * 8; fast[u] = true;
+                            lo[u] = __ldg(q); hi[u] = __ldg(q + 1);                    /* the arena is padded: q + 1 stays inside it */
+                        } else {
+                            #pragma unroll
+                            for (int b = 0; b < 4; ++b) if (p + b < n) v[u] |= (uint32_t)dig[p + b] << (8 * b);
+                        }
+                    }
                 }
-                S.cache[rw][w] = v;
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t e = e0 + u * AFF_THREADS;
+                    if (e < nbk * LQ_AFR_R * LQ_AFR_WORDS) {
+                        const uint32_t w = e % nbk, rw = e / nbk, r = rw / LQ_AFR_WORDS, j = rw % LQ_AFR_WORDS;
+                        S.blk[r * LQ_AFR_BLK + 1 + j][w] = fast[u] ? __funnelshift_r(lo[u], hi[u], sh[u]) : v[u];
+                    }
+                }
             }
             __syncthreads();
             if (wid == 0) {
-                if (!fin) {
-                    fin = lq_afr_run(&ws, my_n, my_start, &S.cache[0][lane], AFF_LANES, &S.base[0][lane], AFF_LANES, my_seq, my_ph) != 0;
-                    S.off[0][lane] = ws.off[0]; S.off[1][lane] = ws.off[1]; S.off[2][lane] = ws.off[2]; S.off[3][lane] = ws.off[3];
-                    ws.off[0] = ws.off[1] = ws.off[2] = ws.off[3] = 0;   /* the refill above rebases every region */
-                }
+                if (!fin) fin = lq_afr_run(&ws, my_n, my_start, &S.blk[0][lane], AFF_LANES, &S.base[0][lane], AFF_LANES, my_seq, my_ph) != 0;
                 const uint32_t alive = __ballot_sync(0xffffffffu, !fin);
                 if (lane == 0) s_alive = alive;
             }
