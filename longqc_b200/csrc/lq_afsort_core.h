@@ -301,51 +301,94 @@ LQ_HD void lq_afr_init(lq_afr_walk *s, const uint32_t *start, lq_afq_phase *ph)
     if (k < LQ_AFR_R) { ph[k].t = 0; ph[k].p = start[k]; }
 }
 
-LQ_HD int lq_afr_run(lq_afr_walk *s, uint32_t n, const uint32_t *start, uint32_t *blk, uint32_t stride, const uint32_t *base, uint32_t bstride,
+/* M: word access to the walk's cache, M::ld(i) / M::st(i, v) with i = (r * LQ_AFR_BLK + j) * stride -- on the device explicit
+ * shared-space loads and stores (LqSmemWords in lq_map.cu), on the host a plain array.  The walk runs in SAFE STRETCHES: m = the
+ * fewest cached digits any region has left, so the next m pick-ups need neither a "cache empty" nor an "end of bucket" test; a
+ * stretch shorter than LQ_AFR_MINRUN asks for a refill instead.  One pick-up is then ~17 instructions: a lone walker warp issues
+ * them back to back at ~5 cycles each, so the instruction count IS the step time. */
+#define LQ_AFR_MINRUN 16
+template <class M>
+LQ_HD int lq_afr_run(lq_afr_walk *s, uint32_t n, const uint32_t *start, M mem, uint32_t stride, const uint32_t *base, uint32_t bstride,
                      uint32_t *seq32, lq_afq_phase *ph)
 {
     uint32_t k = s->k, c = s->c, step = s->step, acc = s->acc, rem_k = s->rem_k;
+    const uint32_t RB = LQ_AFR_BLK * stride;
     int done = 1;
-    if (step < n) {
 #define LQ_AFR_STEP(J) { \
-            uint32_t *rb = blk + c * (LQ_AFR_BLK * stride); \
-            const uint32_t off = rb[0]; \
-            if (off >= LQ_AFR_CAP) { done = 0; break; } \
-            const uint32_t w = rb[(1 + (off >> 2)) * stride]; \
-            const uint32_t d = (w >> (8 * (off & 3u))) & 255u; \
-            rb[0] = off + 1; \
-            if (c == k) --rem_k; \
-            acc |= d << (8 * (J)); \
-            if ((J) == 3) { seq32[step >> 2] = acc; acc = 0; } \
-            c = d; \
-            if (d == k && rem_k == 0) {                           /* region k complete: open the next non-exhausted region */ \
-                for (;;) { \
-                    ++k; \
-                    if (k >= LQ_AFR_R) break; \
-                    const uint32_t nxt = base[k * bstride] + blk[k * (LQ_AFR_BLK * stride)];   /* next unread position of region k */ \
-                    if (nxt != start[k + 1]) { c = k; rem_k = start[k + 1] - nxt; ph[k].t = step + 1; ph[k].p = nxt; break; } \
-                } \
-                if (k >= LQ_AFR_R) c = 0; \
+        const uint32_t ob = c * RB; \
+        const uint32_t off = mem.ld(ob); \
+        const uint32_t w = mem.ld(ob + (1 + (off >> 2)) * stride); \
+        const uint32_t d = (w >> (8 * (off & 3u))) & 255u; \
+        mem.st(ob, off + 1); \
+        rem_k -= (c == k); \
+        acc |= d << (8 * (J)); \
+        c = d; \
+        if (d == k && rem_k == 0) {                               /* region k complete: open the next non-exhausted region */ \
+            for (;;) { \
+                ++k; \
+                if (k >= LQ_AFR_R) break; \
+                const uint32_t nxt = base[k * bstride] + mem.ld(k * RB);   /* next unread position of region k */ \
+                if (nxt != start[k + 1]) { c = k; rem_k = start[k + 1] - nxt; ph[k].t = step + (J) + 1; ph[k].p = nxt; break; } \
             } \
-            if (++step >= n) break; }
-        for (;;) {
-            switch (step & 3u) {
-            case 0: LQ_AFR_STEP(0)
-            /* fall through */
-            case 1: LQ_AFR_STEP(1)
-            /* fall through */
-            case 2: LQ_AFR_STEP(2)
-            /* fall through */
-            default: LQ_AFR_STEP(3)
+            if (k >= LQ_AFR_R) c = 0; \
+        } }
+    while (step < n) {
+        uint32_t m = n - step;
+        for (uint32_t r = 0; r < LQ_AFR_R; ++r) { const uint32_t left = LQ_AFR_CAP - mem.ld(r * RB); m = left < m ? left : m; }
+        if (m < LQ_AFR_MINRUN && m < n - step) { done = 0; break; }
+        const uint32_t stop = step + m;
+        while (step < stop && (step & 3u)) {                      /* up to a word boundary of the digit stream */
+            const uint32_t J = step & 3u;
+            const uint32_t ob = c * RB, off = mem.ld(ob), w = mem.ld(ob + (1 + (off >> 2)) * stride), d = (w >> (8 * (off & 3u))) & 255u;
+            mem.st(ob, off + 1);
+            rem_k -= (c == k);
+            acc |= d << (8 * J);
+            c = d;
+            if (d == k && rem_k == 0) {
+                for (;;) {
+                    ++k;
+                    if (k >= LQ_AFR_R) break;
+                    const uint32_t nxt = base[k * bstride] + mem.ld(k * RB);
+                    if (nxt != start[k + 1]) { c = k; rem_k = start[k + 1] - nxt; ph[k].t = step + 1; ph[k].p = nxt; break; }
+                }
+                if (k >= LQ_AFR_R) c = 0;
             }
-            if (!done || step >= n) break;
+            ++step;
+            if ((step & 3u) == 0) { seq32[(step - 1) >> 2] = acc; acc = 0; }
         }
-#undef LQ_AFR_STEP
-        if (step >= n && (step & 3u)) seq32[step >> 2] = acc;
+        while (step + 4 <= stop) {                                /* whole words: static byte lanes */
+            LQ_AFR_STEP(0) LQ_AFR_STEP(1) LQ_AFR_STEP(2) LQ_AFR_STEP(3)
+            seq32[step >> 2] = acc; acc = 0;
+            step += 4;
+        }
+        while (step < stop) {                                     /* the rest of the stretch */
+            const uint32_t J = step & 3u;
+            const uint32_t ob = c * RB, off = mem.ld(ob), w = mem.ld(ob + (1 + (off >> 2)) * stride), d = (w >> (8 * (off & 3u))) & 255u;
+            mem.st(ob, off + 1);
+            rem_k -= (c == k);
+            acc |= d << (8 * J);
+            c = d;
+            if (d == k && rem_k == 0) {
+                for (;;) {
+                    ++k;
+                    if (k >= LQ_AFR_R) break;
+                    const uint32_t nxt = base[k * bstride] + mem.ld(k * RB);
+                    if (nxt != start[k + 1]) { c = k; rem_k = start[k + 1] - nxt; ph[k].t = step + 1; ph[k].p = nxt; break; }
+                }
+                if (k >= LQ_AFR_R) c = 0;
+            }
+            ++step;
+            if ((step & 3u) == 0) { seq32[(step - 1) >> 2] = acc; acc = 0; }
+        }
     }
+#undef LQ_AFR_STEP
+    if (done && (step & 3u)) seq32[step >> 2] = acc;
     s->k = k; s->c = c; s->step = step; s->acc = acc; s->rem_k = rem_k;
     return done;
 }
+
+/* plain-array word access (host check) */
+struct lq_afr_host_words { uint32_t *a; LQ_HD uint32_t ld(uint32_t i) const { return a[i]; } LQ_HD void st(uint32_t i, uint32_t v) const { a[i] = v; } };
 
 /* host form of the few-region refill: every region's cached stretch restarts at its next unread position */
 LQ_HD void lq_afr_refill_host(const uint8_t *dig, uint32_t n, uint32_t *blk, uint32_t *base)

@@ -174,7 +174,7 @@ void afsort_levels(const uint64_t *key, uint32_t n, uint32_t *idx, int use_two)
                     std::vector<uint32_t> seq32(m / 4 + 2), ord(m), slot(m); uint32_t run[256];
                     for (;;) {
                         lq_afr_refill_host(dig.data() + beg, m, cache.data(), base);
-                        if (lq_afr_run(&ws, m, st257, cache.data(), 1, base, 1, seq32.data(), ph)) break;
+                        { lq_afr_host_words hw; hw.a = cache.data(); if (lq_afr_run(&ws, m, st257, hw, 1, base, 1, seq32.data(), ph)) break; }
                     }
                     lq_afq_expand((const uint8_t*)seq32.data(), m, st257, ph, run, ord.data(), slot.data());
                     for (uint32_t t = 0; t < m; ++t) dest[beg + ord[t]] = slot[t];

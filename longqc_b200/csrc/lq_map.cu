@@ -969,6 +969,12 @@ __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk3_k(AfArgs a, uint32
 #define AFF_LANES 16
 #define AFF_THREADS 256
 #define AFF_GRID (148 * 3)
+/* explicit shared-space word access for lq_afr_run: no generic-address conversion inside the walk loop */
+struct LqSmemWords {
+    uint32_t base;   /* shared-space byte address of this lane's word 0 */
+    __device__ __forceinline__ uint32_t ld(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + 4u * i) : "memory"); return v; }
+    __device__ __forceinline__ void st(uint32_t i, uint32_t v) const { asm volatile("st.shared.u32 [%0], %1;" :: "r"(base + 4u * i), "r"(v) : "memory"); }
+};
 struct AffSmem { uint32_t blk[LQ_AFR_R * LQ_AFR_BLK][AFF_LANES]; uint32_t base[LQ_AFR_R][AFF_LANES]; uint32_t start[LQ_AFR_R + 1][AFF_LANES]; };   /* blk: per region the read offset, then 59 digit words */
 
 __global__ void __launch_bounds__(AFF_THREADS) lq_af_walkf_k(AfArgs a)
@@ -1066,7 +1072,7 @@ __global__ void __launch_bounds__(AFF_THREADS) lq_af_walkf_k(AfArgs a)
             }
             __syncthreads();
             if (wid == 0) {
-                if (!fin) fin = lq_afr_run(&ws, my_n, my_start, &S.blk[0][lane], AFF_LANES, &S.base[0][lane], AFF_LANES, my_seq, my_ph) != 0;
+                if (!fin) { LqSmemWords mw; mw.base = (uint32_t)__cvta_generic_to_shared(&S.blk[0][lane]); fin = lq_afr_run(&ws, my_n, my_start, mw, AFF_LANES, &S.base[0][lane], AFF_LANES, my_seq, my_ph) != 0; }
                 const uint32_t alive = __ballot_sync(0xffffffffu, !fin);
                 if (lane == 0) s_alive = alive;
             }
