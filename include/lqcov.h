@@ -140,6 +140,17 @@ int  lqcov_part_exchange(lqcov_ctx *c);
 int  lqcov_comm_gather_rows(lqcov_ctx *c, const char *mine, size_t len, char **all, size_t *all_len);
 /* whole target set in memory: cut into parts exactly as index.c:238-330 does (mini-batch rule) and add each */
 int  lqcov_add_targets(lqcov_ctx *c, const lqcov_reads_t *targets);
+/* `-d FILE` and prebuilt indexes (index.c:390-479: the "MMI\2" image of the reference's index, byte for byte, khash slot order
+ * included; longQC.py --db writes one with `-d` and maps against it later):
+ *   lqcov_index_dump        append the part just indexed (lqcov_index_part / lqcov_add_part; `part` with its bases in host memory) to `file` (a FILE*)
+ *   lqcov_index_peek        1 when `path` is such a file: k, w, -H of its first part (they override the command line's: index.c:524-526)
+ *   lqcov_load_part         the next part of an index file becomes the current part (then lqcov_map_part); 1 = loaded, 0 = end of file
+ *   lqcov_set_prepass_counts  the row's minimizer count `n` is the COMMAND LINE's k / w (minimap2-coverage.c:418-427) even when an index
+ *                           built with other parameters is mapped against: records those counts (call after lqcov_set_queries) */
+int  lqcov_index_dump(lqcov_ctx *c, const lqcov_reads_t *part, void *file);
+int  lqcov_index_peek(const char *path, int *k, int *w, int *is_hpc);
+int  lqcov_load_part(lqcov_ctx *c, void *file);
+int  lqcov_set_prepass_counts(lqcov_ctx *c, const lqcov_reads_t *queries, int k, int w, int is_hpc);
 /* the stdout table of minimap2-coverage.c:545-617, one row per query; *buf is malloc'ed (lqcov_free) */
 int  lqcov_table(lqcov_ctx *c, char **buf, size_t *len);
 int  lqcov_get_stats(const lqcov_ctx *c, lqcov_stats_t *s);

@@ -54,6 +54,7 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 
 #include "lq_ctx.h"
 #include "lq_comm.h"
+#include "lq_mmi.h"
 
 extern "C" int lqcov_abi_version(void) { return LQCOV_ABI_VERSION; }
 extern "C" int lqcov_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
@@ -146,7 +147,7 @@ extern "C" int lqcov_set_queries(lqcov_ctx *c, const lqcov_reads_t *q)
 {
     LQ_USE_DEV(c);
     const double t0 = now_ms();
-    c->nq = q->n;
+    c->nq = q->n; c->n_prepass.clear();
     c->qname.resize(q->n); c->qlen.resize(q->n);
     for (uint32_t i = 0; i < q->n; ++i) {
         c->qname[i] = name_of(q, i);
@@ -421,6 +422,86 @@ extern "C" int lqcov_map_part(lqcov_ctx *c)
     return 0;
 }
 
+/* ---- `-d FILE` and index files as the target argument (index.c:390-479, lq_mmi.cpp) ---- */
+extern "C" int lqcov_index_dump(lqcov_ctx *c, const lqcov_reads_t *part, void *file)
+{
+    LQ_USE_DEV(c);
+    if (!c->part_ready || !part->seq || part->seq_on_device) { fprintf(stderr, "[lqcov] ERROR: lqcov_index_dump needs the part just indexed, with its bases in host memory\n"); return -1; }
+    LqIndexDev *ix = &c->ix;
+    std::vector<uint32_t> counts((size_t)ix->n_keyspace); std::vector<uint64_t> offs((size_t)ix->n_keyspace + 1), pos((size_t)ix->n_rec + 1);
+    LQ_CUDA_OK(cudaMemcpyAsync(counts.data(), ix->counts.p, counts.size() * 4, cudaMemcpyDeviceToHost, c->st));
+    LQ_CUDA_OK(cudaMemcpyAsync(offs.data(), ix->offs.p, offs.size() * 8, cudaMemcpyDeviceToHost, c->st));
+    if (ix->n_rec) LQ_CUDA_OK(cudaMemcpyAsync(pos.data(), ix->rec.y.p, (size_t)ix->n_rec * 8, cudaMemcpyDeviceToHost, c->st));
+    LQ_CUDA_OK(cudaStreamSynchronize(c->st));
+    return lq_mmi_dump_part((FILE*)file, c->opt.w, c->opt.k, c->opt.is_hpc, part, counts.data(), offs.data(), pos.data());
+}
+
+extern "C" int lqcov_index_peek(const char *path, int *k, int *w, int *is_hpc)
+{
+    const int is = lq_mmi_is_index(path);
+    if (is <= 0) return is;
+    FILE *fp = fopen(path, "rb");
+    uint32_t x[6];
+    if (!fp || fread(x, 4, 6, fp) != 6) { if (fp) fclose(fp); return -1; }
+    fclose(fp);
+    *w = (int)x[1]; *k = (int)x[2]; *is_hpc = (int)(x[5] & 1u);
+    return 1;
+}
+
+/* the next part of an index file becomes the current part: 1 = loaded, 0 = end of file */
+extern "C" int lqcov_load_part(lqcov_ctx *c, void *file)
+{
+    LQ_USE_DEV(c);
+    LqMmiPart mp;
+    const int rc = lq_mmi_load_part((FILE*)file, &mp);
+    if (rc <= 0) { if (rc < 0) fprintf(stderr, "[lqcov] ERROR: damaged index file\n"); return rc; }
+    if (mp.k != c->opt.k || mp.w != c->opt.w || (int)(mp.flag & 1u) != (c->opt.is_hpc ? 1 : 0)) {
+        fprintf(stderr, "[lqcov] ERROR: the index part was built with -k %d -w %d%s, the context with -k %d -w %d%s (lqcov_index_peek tells before lqcov_create)\n",
+                mp.k, mp.w, mp.flag & 1 ? " -H" : "", c->opt.k, c->opt.w, c->opt.is_hpc ? " -H" : "");
+        return -1;
+    }
+    const double t0 = now_ms();
+    LqIndexDev *ix = &c->ix;
+    c->part_ready = false; c->use_full = false; c->placed = false;
+    const uint64_t n = mp.key.size();
+    LQ_TRY(ix->rec.key.ensure((size_t)(n + 1) * 4)); LQ_TRY(ix->rec.y.ensure((size_t)(n + 1) * 8));
+    ix->rec.n = n; ix->rec.has_span = 0;
+    if (n) {
+        LQ_CUDA_OK(cudaMemcpyAsync(ix->rec.key.p, mp.key.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+        LQ_CUDA_OK(cudaMemcpyAsync(ix->rec.y.p, mp.y.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->st));
+    }
+    LQ_TRY(lq_index_alloc(ix, c->opt.k, c->st));
+    LQ_TRY(lq_index_count(ix, &ix->rec, c->st));
+    LQ_CUDA_OK(cudaStreamSynchronize(c->st));
+    c->stats.t_index_ms += now_ms() - t0;
+    lqcov_reads_t part; memset(&part, 0, sizeof part);
+    part.n = mp.n_seq; part.seq_off = mp.seq_off.data(); part.names = mp.names.data(); part.name_off = mp.name_off.data();
+    c->stats.target_bases += mp.seq_off[mp.n_seq];
+    LQ_TRY(lqcov_part_finish(c, &part));
+    return 1;
+}
+
+/* minimap2-coverage.c:418-427 sketches the queries with the COMMAND LINE's k / w only to size the per-minimizer counters; mapping
+ * uses the index's own k / w (index.c:468-470).  When an index file built with other parameters is mapped against, the row's
+ * `n` (minimap2-coverage.c:552-563) is still the command line's: this call records those counts. */
+extern "C" int lqcov_set_prepass_counts(lqcov_ctx *c, const lqcov_reads_t *q, int k, int w, int is_hpc)
+{
+    LQ_USE_DEV(c);
+    if (q->n != c->nq) return -1;
+    LqReadsDev rd; LqMinimizers m; LqDevBuf first; int rc = -1;
+    std::vector<uint64_t> hf((size_t)q->n + 1);
+    if (lq_reads_upload(&rd, (const uint8_t*)q->seq, q->seq_off, q->n, q->seq_on_device, 0, c->st) == 0 &&
+        lq_sketch_run(&rd, w, k, is_hpc, 0, &m, c->ws, c->st) == 0 && lq_read_first(&m, 0, q->n, first, c->st) == 0 &&
+        cudaMemcpyAsync(hf.data(), first.p, ((size_t)q->n + 1) * 8, cudaMemcpyDeviceToHost, c->st) == cudaSuccess &&
+        cudaStreamSynchronize(c->st) == cudaSuccess) {
+        c->n_prepass.resize(q->n);
+        for (uint32_t i = 0; i < q->n; ++i) c->n_prepass[i] = (uint32_t)(hf[i + 1] - hf[i]);
+        rc = 0;
+    }
+    rd.release(); m.release(); first.release();
+    return rc;
+}
+
 extern "C" int lqcov_add_part(lqcov_ctx *c, const lqcov_reads_t *part)
 {
     LQ_TRY(lqcov_index_part(c, part));
@@ -451,7 +532,8 @@ extern "C" int lqcov_table(lqcov_ctx *c, char **buf, size_t *len)
     LQ_USE_DEV(c);
     const double t0 = now_ms();
     std::vector<uint32_t> n_match; std::vector<uint64_t> lam(c->nq), lam2(c->nq);
-    LQ_TRY(lq_map_nmatch(&c->qd, &n_match, c->st));
+    const bool pre = c->n_prepass.size() == c->nq && c->nq > 0;
+    LQ_TRY(lq_map_nmatch(&c->qd, pre ? c->n_prepass.data() : (const uint32_t*)0, &n_match, c->st));
     if (c->nq) {
         LQ_CUDA_OK(cudaMemcpyAsync(lam.data(), c->qd.lambda.p, (size_t)c->nq * 8, cudaMemcpyDeviceToHost, c->st));
         LQ_CUDA_OK(cudaMemcpyAsync(lam2.data(), c->qd.lambda2.p, (size_t)c->nq * 8, cudaMemcpyDeviceToHost, c->st));
@@ -459,7 +541,7 @@ extern "C" int lqcov_table(lqcov_ctx *c, char **buf, size_t *len)
     }
     lq_prof_d2h((uint64_t)c->nq * 16); lq_prof_collect();
     for (uint32_t q = 0; q < c->nq; ++q)
-        if (c->qfirst[q + 1] == c->qfirst[q]) { /* the reference divides by zero here (minimap2-coverage.c:558, SIGFPE) */
+        if (pre ? c->n_prepass[q] == 0 : c->qfirst[q + 1] == c->qfirst[q]) { /* the reference divides by zero here (minimap2-coverage.c:558, SIGFPE) */
             fprintf(stderr, "[lqcov] ERROR: query '%s' yields no minimizer; the reference binary crashes on such input\n", c->qname[q].c_str());
             return -1;
         }
@@ -471,7 +553,7 @@ extern "C" int lqcov_table(lqcov_ctx *c, char **buf, size_t *len)
     parallel_chunks(c->nq, nt, [&](uint32_t lo, uint32_t hi, unsigned t) {
         for (uint32_t q = lo; q < hi; ++q)
             lqh_format_row(&piece[t], c->qname[q].data(), c->qname[q].size(), c->qlen[q], c->q_has_qual, c->qsum_p[q], lam[q], lam2[q],
-                           (uint32_t)(c->qfirst[q + 1] - c->qfirst[q]), n_match[q], c->avg_k[q], &c->ovlp[q], c->opt.min_coverage, c->opt.filter);
+                           pre ? c->n_prepass[q] : (uint32_t)(c->qfirst[q + 1] - c->qfirst[q]), n_match[q], c->avg_k[q], &c->ovlp[q], c->opt.min_coverage, c->opt.filter);
     });
     lqh_str out; out.l = 0; out.m = 1; out.s = 0;
     for (unsigned t = 0; t < nt; ++t) out.m += piece[t].l;

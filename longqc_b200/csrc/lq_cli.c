@@ -2,7 +2,7 @@
  *
  * Command line == the reference's (minimap2-coverage.c:63-197): same option letters, long names,
  * argument kinds, "0 / -1 means default" sentinels (:252-388), the same fatal checks, stdout carries
- * only the table, everything else goes to stderr.  Not supported by this build: -d (index dump).
+ * only the table, everything else goes to stderr.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -81,7 +81,7 @@ static struct argp_option opts[] = {
     { "k-mer",             'k', "INT",    0, "k-mer size" },
     { "window",            'w', "INT",    0, "minimizer window size" },
     { "index-size",        'I', "STRING", 0, "start a new index part every ~NUM target bases (K/M/G suffix)" },
-    { "dump-index",        'd', "FILE",   0, "dump the index to FILE (not supported by this build)" },
+    { "dump-index",        'd', "FILE",   0, "dump the index to FILE (the reference's MMI format)" },
     { 0, 0, 0, 0, "Mapping options", 2 },
     { "max-gap-length",    'g', "INT",    0, "maximum distance between chained minimizers" },
     { "min-cnt",           'n', "INT",    0, "minimum number of minimizers on a chain" },
@@ -302,6 +302,56 @@ static int pick_devices(const lqcov_opt_t *o)
     return n;
 }
 
+/* `-d FILE` (write every part's index as the reference's "MMI\2" image, index.c:390-426) and index files as the target argument
+ * (longQC.py --db): one GPU, a part at a time in host memory -- the dump needs the bases for the packed-sequence block. */
+static int run_dump_or_indexfile(cli_dev *d, const char *target, int is_idx, const char *dump_path, lqi_reader *tr, const lqcov_opt_t *o, int have_q, double t0)
+{
+    int rc = 0;
+    if (is_idx) {
+        FILE *fp = fopen(target, "rb");
+        int r;
+        if (!fp) { fprintf(stderr, "ERROR: failed to open file '%s'\n", target); return 1; }
+        while ((r = lqcov_load_part(d->c, fp)) == 1) {
+            fprintf(stderr, "[M::%s::%.3f*%.2f] loaded/built the index for target sequence(s)\n", __func__, wall() - t0, cpu() / (wall() - t0));
+            if (have_q && lqcov_map_part(d->c) != 0) { rc = 1; break; }
+        }
+        if (r < 0) rc = 1;
+        fclose(fp);
+        return rc;
+    }
+    FILE *fd = dump_path ? fopen(dump_path, "wb") : 0;
+    if (dump_path && !fd) { fprintf(stderr, "ERROR: failed to open file '%s' for writing\n", dump_path); return 1; }
+    part_meta pm; memset(&pm, 0, sizeof pm);
+    int eof = 0;
+    char *whole = 0; size_t whole_cap = 0;
+    lqi_part_rule(tr, o->batch_size, o->mini_batch_size);
+    while (rc == 0 && !eof) {
+        size_t whole_n = 0; int part_end = 0;
+        pm.n = 0; pm.nn = 0;
+        while (!part_end && !eof) {
+            lqi_chunk ch; int r;
+            if (whole_cap - whole_n < CLI_STAGE_BYTES) { whole_cap = whole_cap ? whole_cap * 2 : 4 * CLI_STAGE_BYTES; whole = (char*)realloc(whole, whole_cap); }
+            r = lqi_next_chunk(tr, whole_cap - whole_n, whole + whole_n, 0, &ch);
+            if (r == -2) { whole_cap = whole_n + ch.need + CLI_STAGE_BYTES; whole = (char*)realloc(whole, whole_cap); continue; }
+            part_end = ch.part_end; eof = ch.eof;
+            if (r <= 0) continue;
+            meta_add(&pm, &ch);
+            whole_n += ch.n_bases;
+        }
+        if (pm.n > 0) {
+            lqcov_reads_t part; memset(&part, 0, sizeof part);
+            part.n = (uint32_t)pm.n; part.seq = whole; part.seq_off = pm.seq_off; part.names = pm.names; part.name_off = pm.name_off;
+            if (lqcov_index_part(d->c, &part) != 0) rc = 1;
+            fprintf(stderr, "[M::%s::%.3f*%.2f] loaded/built the index for %u target sequence(s)\n", __func__, wall() - t0, cpu() / (wall() - t0), part.n);
+            if (rc == 0 && fd && lqcov_index_dump(d->c, &part, fd) != 0) rc = 1;
+            if (rc == 0 && have_q && lqcov_map_part(d->c) != 0) rc = 1;
+        }
+    }
+    if (fd) fclose(fd);
+    free(whole); free(pm.seq_off); free(pm.name_off); free(pm.names);
+    return rc;
+}
+
 int lqcov_main(int argc, char **argv)
 {
     struct cli a;
@@ -324,7 +374,6 @@ int lqcov_main(int argc, char **argv)
     if (a.k == 0) { fprintf(stderr, "Warning: Apply default k=12 instead. \n"); o.k = 12; } else o.k = a.k;
     if (a.w == 0) { fprintf(stderr, "Warning: Apply default w=5 instead. \n"); o.w = 5; } else o.w = a.w;
     if (a.batch == 0) fprintf(stderr, "Warning: Apply default I=4G instead. \n"); else o.batch_size = a.batch;
-    if (a.dump) { fprintf(stderr, "ERROR: -d (index dump) is not supported by this build\n"); return 1; }
     if (a.min_cov == -1) { fprintf(stderr, "Warning: Apply default c=3 instead. \n"); o.min_coverage = 3; } else o.min_coverage = a.min_cov;
     if (a.n_subset == -1) { fprintf(stderr, "Warning: -s shouldn't be zero. Apply default s=100000 instead.\n"); a.n_subset = 100000; }
     if (a.max_gap == 0) { fprintf(stderr, "Warning: Apply default g=10000 instead.\n"); o.max_gap = 10000; } else o.max_gap = a.max_gap;
@@ -349,22 +398,34 @@ int lqcov_main(int argc, char **argv)
     fprintf(stderr, "max-overhang %d, min-overlaplen %d, min-overapratio %.2f\n", o.max_overhang, o.min_ovlp, o.min_ratio);
     fprintf(stderr, "num of threads %d, num of query seqs %d\n===\n", o.n_threads, a.n_subset);
 
+    /* an index file as the target (index.c:481-498): its k / w / -H replace the command line's for the mapping, not for the rows' `n` */
+    int idx_k = 0, idx_w = 0, idx_hpc = 0;
+    const int is_idx = lqcov_index_peek(a.args[0], &idx_k, &idx_w, &idx_hpc);
+    const int cl_k = o.k, cl_w = o.w, cl_hpc = o.is_hpc, have_q = a.args[1] != 0;
+    if (is_idx < 0) { fprintf(stderr, "ERROR: failed to open file '%s'\n", a.args[0]); return 1; }
+    if (is_idx == 1) {
+        if (idx_k != o.k || idx_w != o.w || idx_hpc != o.is_hpc)
+            fprintf(stderr, "[WARNING]\033[1;31m Indexing parameters (-k, -w or -H) overridden by parameters used in the prebuilt index.\033[0m\n");
+        o.k = idx_k; o.w = idx_w; o.is_hpc = idx_hpc;
+    }
     /* The CUDA contexts (hundreds of ms each) are created on their own threads while the reader threads already parse the inputs. */
     cli_dev dv[CLI_MAX_DEV]; pthread_t cth[CLI_MAX_DEV];
-    const int n_dev = pick_devices(&o);
+    const int n_dev = (is_idx == 1 || a.dump) ? 1 : pick_devices(&o);
     memset(dv, 0, sizeof dv);
     for (int i = 0; i < n_dev; ++i) { dv[i].dev = i; dv[i].n_dev = n_dev; dv[i].o = o; dv[i].o.device = n_dev > 1 ? i : -1; pthread_create(&cth[i], 0, dev_create, &dv[i]); }
     const int n_rd = reader_threads(o.n_threads);
-    lqi_reader *tr = lqi_open(a.args[0], n_rd);
-    lqcov_reader *qr = tr ? lqcov_reader_open(a.args[1]) : 0;
+    lqi_reader *tr = is_idx == 1 ? 0 : lqi_open(a.args[0], n_rd);
+    lqcov_reader *qr = (tr || is_idx == 1) && have_q ? lqcov_reader_open(a.args[1]) : 0;
     lqcov_reads_t q; memset(&q, 0, sizeof q);
+    static const uint64_t zero_off[1] = { 0 };
+    q.seq_off = zero_off; q.name_off = zero_off; q.seq = ""; q.names = "";
     if (qr) lqcov_reader_next(qr, 0, &q);                     /* one kseq_read loop over the query file (minimap2-coverage.c:418) */
     TL("queries parsed");
     int rc = 0;
     for (int i = 0; i < n_dev; ++i) { pthread_join(cth[i], 0); rc |= dv[i].rc; }
-    if (!tr) fprintf(stderr, "ERROR: failed to open file '%s'\n", a.args[0]);
-    else if (!qr) fprintf(stderr, "ERROR: failed to open file '%s'\n", a.args[1]);
-    if (!tr || !qr || rc) { if (tr) lqi_close(tr); if (qr) lqcov_reader_close(qr); for (int i = 0; i < n_dev; ++i) if (dv[i].c) lqcov_destroy(dv[i].c); return 1; }
+    if (!tr && is_idx != 1) fprintf(stderr, "ERROR: failed to open file '%s'\n", a.args[0]);
+    else if (!qr && have_q) fprintf(stderr, "ERROR: failed to open file '%s'\n", a.args[1]);
+    if ((!tr && is_idx != 1) || (!qr && have_q) || rc) { if (tr) lqi_close(tr); if (qr) lqcov_reader_close(qr); for (int i = 0; i < n_dev; ++i) if (dv[i].c) lqcov_destroy(dv[i].c); return 1; }
     if (n_dev > 1) {
         lqcov_ctx *cs[CLI_MAX_DEV];
         for (int i = 0; i < n_dev; ++i) cs[i] = dv[i].c;
@@ -381,15 +442,25 @@ int lqcov_main(int argc, char **argv)
     for (int i = 0; i < n_dev; ++i) { pthread_join(cth[i], 0); rc |= dv[i].rc; }
     TL("queries sketched, staging buffers allocated");
     fprintf(stderr, "[M::%s::%.3f*%.2f] loaded %u sequence(s).\n", __func__, wall() - t0, cpu() / (wall() - t0), q.n);
-    if (rc == 0) rc = lqcov_part_begin(dv[0].c, 0, 0) == 1 ? run_parts_whole(&dv[0], tr, &o, t0) : run_parts(dv, n_dev, tr, &o, t0);
-    lqi_close(tr);
+    if (rc == 0 && is_idx == 1 && have_q && (cl_k != o.k || cl_w != o.w || cl_hpc != o.is_hpc) && lqcov_set_prepass_counts(dv[0].c, &q, cl_k, cl_w, cl_hpc) != 0) rc = 1;
+    if (rc == 0) {
+        if (is_idx == 1 || a.dump) rc = run_dump_or_indexfile(&dv[0], a.args[0], is_idx == 1, a.dump, tr, &o, have_q, t0);
+        else rc = lqcov_part_begin(dv[0].c, 0, 0) == 1 ? run_parts_whole(&dv[0], tr, &o, t0) : run_parts(dv, n_dev, tr, &o, t0);
+    }
+    if (tr) lqi_close(tr);
+    if (!have_q) {                       /* -d without a query file: the index is written, nothing is mapped (minimap2-coverage.c:460-468) */
+        for (int i = 0; i < n_dev; ++i) lqcov_destroy(dv[i].c);
+        close(out_fd);
+        fprintf(stderr, "\n[M::%s] Real time: %.3f sec; CPU: %.3f sec\n", __func__, wall() - t0, cpu());
+        return rc;
+    }
     if (rc == 0 && on_all(dv, n_dev, dev_table) != 0) rc = 1;
     if (rc == 0) {
         FILE *out = fdopen(out_fd, "w");
         for (int i = 0; i < n_dev; ++i) { fwrite(dv[i].tab, 1, dv[i].tab_len, out); lqcov_free(dv[i].tab); }
         fclose(out);
     }
-    lqcov_reader_close(qr);
+    if (qr) lqcov_reader_close(qr);
     TL("table written");
     if (!getenv("LQCOV_FAST_EXIT")) for (int i = 0; i < n_dev; ++i) lqcov_destroy(dv[i].c);
     fprintf(stderr, "\n[M::%s] Real time: %.3f sec; CPU: %.3f sec\n", __func__, wall() - t0, cpu());

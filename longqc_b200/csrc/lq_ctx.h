@@ -33,6 +33,7 @@ struct lqcov_ctx {
     bool part_ready;
     int32_t mid_occ;
     lqcov_stats_t stats;
+    std::vector<uint32_t> n_prepass;     /* per query: minimizers under the command line's k / w when an index file with other parameters is mapped against */
     LqComm *comm;                        /* multi-GPU: NULL for a single context (lq_comm.cu) */
     bool placed;                         /* the part's records were merged and placed by lqcov_part_exchange: lqcov_part_finish must not sort them again */
 };

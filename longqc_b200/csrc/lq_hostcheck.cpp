@@ -308,3 +308,32 @@ extern "C" long lqhc_sdust_masked(const char *seq, int len, int T, int W)
 // ---------------------------------------------------------------- host table code (lq_table.c is plain C: linked in for its self-test)
 extern "C" double lqh_q2p(int q);
 extern "C" double lqhc_q2p(int q) { return lqh_q2p(q); }
+
+// ---------------------------------------------------------------- index dump (lq_mmi.cpp is plain C++: linked in for the format check)
+#include <algorithm>
+#include "lq_mmi.h"
+// records (key, y) of one part in y order -> the index arrays of lq_index.cu built on the host -> the reference's file image
+extern "C" int lqhc_mmi_dump(const char *path, int append, int w, int k, int is_hpc, const lqcov_reads_t *part, const uint32_t *key, const uint64_t *y, uint64_t n)
+{
+    const uint64_t nk = 1ULL << (2 * k);
+    std::vector<uint32_t> counts(nk, 0); std::vector<uint64_t> offs(nk + 1, 0), pos(n + 1), fill;
+    for (uint64_t i = 0; i < n; ++i) ++counts[key[i]];
+    for (uint64_t q = 0; q < nk; ++q) offs[q + 1] = offs[q] + counts[q];
+    fill.assign(offs.begin(), offs.end() - 1);
+    for (uint64_t i = 0; i < n; ++i) pos[fill[key[i]]++] = y[i];          // stable: y ascending inside a key
+    FILE *fp = fopen(path, append ? "ab" : "wb");
+    if (!fp) return -1;
+    const int rc = lq_mmi_dump_part(fp, w, k, is_hpc, part, counts.data(), offs.data(), pos.data());
+    fclose(fp);
+    return rc;
+}
+// an index file -> number of parts, records and sequences (checks the reader)
+extern "C" long lqhc_mmi_load_count(const char *path, long *n_rec, long *n_seq)
+{
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return -1;
+    LqMmiPart mp; long parts = 0; *n_rec = 0; *n_seq = 0; int r;
+    while ((r = lq_mmi_load_part(fp, &mp)) == 1) { ++parts; *n_rec += (long)mp.key.size(); *n_seq += mp.n_seq; }
+    fclose(fp);
+    return r < 0 ? -1 : parts;
+}

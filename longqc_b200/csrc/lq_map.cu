@@ -1698,17 +1698,21 @@ __global__ void lq_dupflag_k(uint64_t n, const uint32_t *__restrict__ skey, cons
 __global__ void lq_iota64_k(uint64_t *a, uint64_t n) { const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }
 
 /* minimap2-coverage.c:552-562 */
-__global__ void lq_nmatch_k(uint32_t nq, const uint64_t *__restrict__ first, const uint32_t *__restrict__ mcnt, uint32_t *__restrict__ n_match, uint32_t *__restrict__ sat)
+__global__ void lq_nmatch_k(uint32_t nq, const uint64_t *__restrict__ first, const uint32_t *__restrict__ mcnt, const uint32_t *__restrict__ npre,
+                            uint32_t *__restrict__ n_match, uint32_t *__restrict__ sat)
 {
     const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (q >= nq) return;
-    const uint64_t b = first[q], e = first[q + 1];
+    const uint64_t b = first[q];
+    uint64_t e = first[q + 1];
+    uint32_t n_div = (uint32_t)(e - b);
+    if (npre) { n_div = npre[q]; if (b + n_div < e) e = b + n_div; }   /* the reference sums its first n counters, n from the command line's k / w */
     uint32_t sum = 0, big = 0;
     for (uint64_t i = b + lane; i < e; i += 32) { sum += mcnt[i]; big |= mcnt[i] >= 65535u; }
     sum = lq_warp_sum(sum); big = __any_sync(0xffffffffu, big);
     uint32_t nm = 0;
-    if (e > b) {
-        const uint32_t mean = sum / (uint32_t)(e - b);
+    if (n_div > 0) {
+        const uint32_t mean = sum / n_div;
         for (uint64_t i = b + lane; i < e; i += 32) nm += mcnt[i] > mean;
         nm = lq_warp_sum(nm);
     }
@@ -2059,15 +2063,17 @@ int lq_map_flag_dups(LqQueryDev *qd, int key_bits, LqDevBuf &ws, cudaStream_t st
     return rc;
 }
 
-int lq_map_nmatch(LqQueryDev *qd, std::vector<uint32_t> *n_match, cudaStream_t st)
+int lq_map_nmatch(LqQueryDev *qd, const uint32_t *h_npre, std::vector<uint32_t> *n_match, cudaStream_t st)
 {
     const uint32_t nq = qd->nq;
     n_match->assign(nq, 0);
     if (nq == 0) return 0;
-    LqDevBuf &out = qd->nmatch_buf; LQ_TRY(out.ensure(((size_t)nq + 2) * 4));
+    LqDevBuf &out = qd->nmatch_buf; LQ_TRY(out.ensure(((size_t)nq + 2) * 4 + (h_npre ? (size_t)nq * 4 : 0)));
     LQ_CUDA_OK(cudaMemsetAsync(out.p, 0, ((size_t)nq + 2) * 4, st));
+    uint32_t *d_npre = 0;
+    if (h_npre) { d_npre = out.as<uint32_t>() + nq + 2; LQ_CUDA_OK(cudaMemcpyAsync(d_npre, h_npre, (size_t)nq * 4, cudaMemcpyHostToDevice, st)); }
     lq_prof_count_launch(1); lq_prof_d2h((uint64_t)nq * 4);
-    lq_nmatch_k<<<lq_grid((size_t)nq * 32, 256), 256, 0, st>>>(nq, qd->first.as<uint64_t>(), qd->mcnt.as<uint32_t>(), out.as<uint32_t>(), out.as<uint32_t>() + nq);
+    lq_nmatch_k<<<lq_grid((size_t)nq * 32, 256), 256, 0, st>>>(nq, qd->first.as<uint64_t>(), qd->mcnt.as<uint32_t>(), d_npre, out.as<uint32_t>(), out.as<uint32_t>() + nq);
     LQ_CUDA_OK(cudaGetLastError());
     uint32_t sat = 0;
     LQ_CUDA_OK(cudaMemcpyAsync(n_match->data(), out.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));

@@ -54,7 +54,9 @@ int lq_map_part(LqQueryDev *qd, const LqIndexDev *ix, const LqMapOpt *opt, int m
                 LqMapStats *stats, cudaStream_t st);
 
 /* final per-query reduction of the match counters (minimap2-coverage.c:552-562): n_match[q] */
-int lq_map_nmatch(LqQueryDev *qd, std::vector<uint32_t> *n_match, cudaStream_t st);
+/* h_npre (may be NULL): per query the minimizer count of the command line's k / w -- the `n` of minimap2-coverage.c:552-563 when it differs
+ * from the mapping sketch (index files built with other parameters) */
+int lq_map_nmatch(LqQueryDev *qd, const uint32_t *h_npre, std::vector<uint32_t> *n_match, cudaStream_t st);
 
 /* once per query set: flag the minimizers whose (key, strand) occurs more than once in their query */
 int lq_map_flag_dups(LqQueryDev *qd, int key_bits, LqDevBuf &ws, cudaStream_t st);
