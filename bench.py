@@ -296,11 +296,19 @@ def sdust_line(a, L, reads):
     t0 = time.perf_counter()
     tab = L.sdust_table(reads)
     torch.cuda.synchronize()
+    lib = L.load()
+    lib.lqcov_profile_reset(); lib.lqcov_profile_enable(1)
     t1 = time.perf_counter()
     tab = L.sdust_table(reads)
     dt = time.perf_counter() - t1
+    prof = profile_json(L)
+    lib.lqcov_profile_enable(0)
+    kms = sum(k["ms"] for k in prof["kernels"] if k["name"] == "sdust")
+    peak, _ = load_peaks()
     out = {"value": reads.n_bases / dt / 1e9, "unit": "Gbases/s", "seconds": dt, "first_call_seconds": t1 - t0, "reads": reads.n, "rows": tab.count(b"\n"),
-           "what": "lqcov_sdust_table on all target reads (host buffers in, table out)"}
+           "kernel_ms": kms, "kernel_gbs": (2 * reads.n_bases / (kms * 1e-3) / 1e9) if kms > 0 else None, "kernel_frac_of_hbm_peak": (2 * reads.n_bases / (kms * 1e-3) / 1e9 / peak) if kms > 0 else None,
+           "what": "lqcov_sdust_table on all target reads (pageable host buffers in, table out; chunks of 48 MB: copy of chunk c+1 beside the kernel of chunk c); "
+                   "kernel_*: lq_sdust_k alone (CUDA events), 2 bytes per base (base + quality)"}
     ref = os.path.join(ROOT, "oracle", "_ref", "sdust")
     if os.path.exists(ref):   # the reference's sdust on a bounded sample (one thread, as lq_mask.py runs it per chunk)
         n = min(reads.n, 4000)

@@ -158,6 +158,15 @@ void lqcov_free(void *p);
 
 /* sdust.c:187-223 as a library: the stdout table of `sdust <reads>` */
 int  lqcov_sdust_table(const lqcov_opt_t *o, const lqcov_reads_t *reads, int W, int T, char **buf, size_t *len);
+/* the same, chunk by chunk (the executable: reader threads fill pinned staging buffers while the device works on the chunk before):
+ *   lqcov_sdust_begin  stage_bytes > 0: two pinned (sequence, quality) buffer pairs of that size are handed out in stage_seq[2] / stage_qual[2]
+ *   lqcov_sdust_chunk  queue copy + kernel of a chunk of whole reads; *rows (malloc'ed) = the rows of the chunk BEFORE it, possibly empty.
+ *                      The chunk's host buffers may be overwritten once the next lqcov_sdust_chunk / _end has returned
+ *   lqcov_sdust_end    the remaining rows; frees the state */
+typedef struct lqcov_sdust lqcov_sdust;
+lqcov_sdust *lqcov_sdust_begin(const lqcov_opt_t *o, int W, int T, size_t stage_bytes, char **stage_seq, char **stage_qual);
+int  lqcov_sdust_chunk(lqcov_sdust *s, const lqcov_reads_t *reads, char **rows, size_t *rows_len);
+int  lqcov_sdust_end(lqcov_sdust *s, char **rows, size_t *rows_len);
 
 /* stage-level entry points (parity tests against the oracle) --------------------------------- */
 /* mm_sketch (sketch.c:76-142) of every read; records in (read, position) order.  x[i] = hash<<8|span,

@@ -66,7 +66,7 @@ SYMBOLS = ["lqcov_abi_version", "lqcov_device_count", "lqcov_opt_init", "lqcov_c
            "lqcov_add_targets", "lqcov_table", "lqcov_get_stats", "lqcov_free", "lqcov_sdust_table", "lqcov_sketch",
            "lqcov_debug_seeds", "lqcov_index_part", "lqcov_reader_open", "lqcov_reader_next", "lqcov_reader_next_part",
            "lqcov_reader_close", "lqcov_main", "lqcov_sdust_main", "lqcov_part_begin", "lqcov_stage", "lqcov_part_chunk", "lqcov_stage_wait", "lqcov_part_end",
-           "lqcov_comm_unique_id", "lqcov_comm_init_rank", "lqcov_comm_init_all", "lqcov_comm_size", "lqcov_comm_rank", "lqcov_part_exchange", "lqcov_comm_gather_rows", "lqcov_index_dump", "lqcov_index_peek", "lqcov_load_part", "lqcov_set_prepass_counts"]
+           "lqcov_comm_unique_id", "lqcov_comm_init_rank", "lqcov_comm_init_all", "lqcov_comm_size", "lqcov_comm_rank", "lqcov_part_exchange", "lqcov_comm_gather_rows", "lqcov_sdust_begin", "lqcov_sdust_chunk", "lqcov_sdust_end", "lqcov_index_dump", "lqcov_index_peek", "lqcov_load_part", "lqcov_set_prepass_counts"]
 
 
 def load() -> C.CDLL:
