@@ -305,6 +305,25 @@ extern "C" long lqhc_sdust_masked(const char *seq, int len, int T, int W)
     return ov ? -1 : m;
 }
 
+// segment form: every segment of S steps scanned on its own after its warm-up, the merged runs of all segments folded in order (what
+// lq_sdust_seg_k + lq_sdust_merge_k do); cap_runs small on purpose: -2 = a segment had more runs than fit (the device falls back)
+extern "C" long lqhc_sdust_segments(const char *seq, int len, int T, int W, int S, int capP, int cap_runs)
+{
+    std::vector<int> pbuf(4 * (size_t)capP);
+    std::vector<lq_sd_run> runs((size_t)cap_runs);
+    lq_sd_merge_sink all; all.init();
+    for (int lo = 0; lo <= len; lo += S) {
+        int ov = 0;
+        const bool last = lo + S > len;
+        const int n = lq_sdust_segment((const uint8_t*)seq, len, T, W, lo, last ? 0x7fffffff : lo + S, pbuf.data(), capP, runs.data(), cap_runs, &ov);
+        if (ov) return -1;
+        if (n > cap_runs) return -2;
+        for (int j = 0; j < n; ++j) all.add(runs[j].s, runs[j].f);
+        if (last) break;
+    }
+    return (long)all.total();
+}
+
 // ---------------------------------------------------------------- host table code (lq_table.c is plain C: linked in for its self-test)
 extern "C" double lqh_q2p(int q);
 extern "C" double lqhc_q2p(int q) { return lqh_q2p(q); }

@@ -176,3 +176,19 @@ def test_sdust_table():
     assert L.sdust_table(rs2) == liblq.oracle_sdust_table(rs2)
     rs3 = liblq.reads_from_seqs(liblq.sdust_stale_seqs(rng), qual=True, rng=rng)   # repeats interrupted by N: the interval list at its bound
     assert L.sdust_table(rs3) == liblq.oracle_sdust_table(rs3)
+    # long reads cut into segments by the kernel: random stretches, long repeats (the whole-read fallback) and stale-N repeats joined
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    stale = liblq.sdust_stale_seqs(rng)
+    long_reads = []
+    for i in range(60):
+        parts = []
+        for _ in range(int(rng.integers(2, 9))):
+            kind = int(rng.integers(0, 4))
+            if kind == 0: parts.append(acgt[rng.integers(0, 4, int(rng.integers(100, 3000)))].tobytes())
+            elif kind == 1: parts.append(stale[int(rng.integers(0, len(stale)))])
+            elif kind == 2: parts.append(np.tile(acgt[rng.integers(0, 4, int(rng.integers(1, 5)))], 2000)[: int(rng.integers(300, 4000))].tobytes())
+            else: parts.append(b"N" * int(rng.integers(1, 70)))
+        long_reads.append(b"".join(parts))
+    long_reads += [b"A" * 511, b"A" * 512, b"A" * 513, b"ACGT" * 128, b"ACGT" * 256 + b"N", b"A" * 1024 + b"N" + b"A" * 1023]
+    rs4 = liblq.reads_from_seqs(long_reads, qual=True, rng=rng)
+    assert L.sdust_table(rs4) == liblq.oracle_sdust_table(rs4)

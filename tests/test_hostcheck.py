@@ -145,3 +145,8 @@ def test_sdust_core():
     want = [int(ln.split(b"\t")[1]) for ln in liblq.oracle_sdust_table(rs).strip().split(b"\n")]
     got = [hc.lqhc_sdust_masked(s, len(s), 20, 64) for s in seqs]
     assert got == want
+    # the segment form of the device kernel: every 96 / 256 / 1000 bases scanned on their own after 3 W bases of warm-up
+    hc.lqhc_sdust_segments.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    hc.lqhc_sdust_segments.restype = C.c_long
+    for S in (64, 96, 256, 1000):
+        assert [hc.lqhc_sdust_segments(s, len(s), 20, 64, S, 4096, 512) for s in seqs] == want, S
