@@ -84,7 +84,7 @@ extern "C" lqcov_ctx *lqcov_create(const lqcov_opt_t *o)
     }
     if (o->device >= 0) { if (cudaSetDevice(o->device) != cudaSuccess) { fprintf(stderr, "[lqcov] ERROR: cannot select CUDA device %d\n", o->device); return 0; } }
     if (o->w < 1 || o->w > LQ_MAX_W) { fprintf(stderr, "[lqcov] ERROR: -w %d outside 1..%d supported by the GPU path\n", o->w, LQ_MAX_W); return 0; }
-    if (o->k < 1 || o->k > LQ_MAX_K_DIRECT) { fprintf(stderr, "[lqcov] ERROR: -k %d outside 1..%d supported by the direct-address index of this build\n", o->k, LQ_MAX_K_DIRECT); return 0; }
+    if (o->k < 1 || o->k > LQ_MAX_K) { fprintf(stderr, "[lqcov] ERROR: -k %d outside 1..%d\n", o->k, LQ_MAX_K); return 0; }   /* minimap2-coverage.c:171 */
     lqcov_ctx *c = new lqcov_ctx();
     c->opt = *o; c->stage_bytes = 0; c->comm = 0; c->placed = false; c->nq = 0; c->q_has_qual = false; c->part_ready = false; c->use_full = false; c->mid_occ = 0;
     memset(&c->stats, 0, sizeof(c->stats));
@@ -166,7 +166,14 @@ extern "C" int lqcov_set_queries(lqcov_ctx *c, const lqcov_reads_t *q)
     LQ_TRY(lq_sketch_run(&qd->reads, c->opt.w, c->opt.k, c->opt.is_hpc, 0, &qd->mins, c->ws, c->st));
     qd->n_min = qd->mins.n;
     LQ_TRY(lq_read_first(&qd->mins, 0, q->n, qd->first, c->st));
-    LQ_TRY(lq_map_flag_dups(qd, 2 * c->opt.k, c->ws, c->st));
+    if (qd->mins.wide) {   /* k > 15: equal keys <=> equal ids of a table over the query set's own keys; per part the ids are the part's (lqcov_map_part) */
+        LqWideTable qt; int kb = 1;
+        int rc = lq_wide_build(&qt, qd->mins.key64.as<uint64_t>(), qd->n_min, qd->mins.key.as<uint32_t>(), c->st);
+        while (kb < 32 && ((uint64_t)qt.n_ids >> kb)) ++kb;
+        if (rc == 0) rc = lq_map_flag_dups(qd, kb, c->ws, c->st);
+        qt.release();
+        if (rc != 0) return -1;
+    } else LQ_TRY(lq_map_flag_dups(qd, 2 * c->opt.k, c->ws, c->st));
     if (q->qual && q->n) { /* meanQ of the table rows (lqutils.c:51-58): the additions must happen in read order, one thread per read */
         const uint64_t nbq = q->seq_off[q->n] - q->seq_off[0];
         LQ_TRY(c->qual_dev.ensure(nbq + 16)); LQ_TRY(c->qsum_dev.ensure(((size_t)q->n + 1) * 8));
@@ -215,7 +222,12 @@ extern "C" int lqcov_part_sketch(lqcov_ctx *c, const lqcov_reads_t *shard, uint3
     }
     LQ_CUDA_OK(cudaStreamSynchronize(c->st));
     c->stats.t_sketch_ms += now_ms() - t0; t0 = now_ms();
-    LQ_TRY(lq_index_alloc(ix, c->opt.k, c->st));
+    uint64_t n_addr = 0;
+    if (ix->rec.wide) {    /* k > 15: dense addresses for the part's distinct keys, one more for "not in this part" */
+        LQ_TRY(lq_wide_build(&ix->wide, ix->rec.key64.as<uint64_t>(), ix->rec.n, ix->rec.key.as<uint32_t>(), c->st));
+        n_addr = (uint64_t)ix->wide.n_ids + 1;
+    }
+    LQ_TRY(lq_index_alloc(ix, c->opt.k, n_addr, c->st));
     LQ_TRY(lq_index_count(ix, &ix->rec, c->st));
     LQ_CUDA_OK(cudaStreamSynchronize(c->st));
     c->stats.t_index_ms += now_ms() - t0;
@@ -272,7 +284,7 @@ extern "C" int lqcov_part_end(lqcov_ctx *c)
     LQ_TRY(lq_stream_end(&c->stream, c->ws));
     c->stats.t_sketch_ms += now_ms() - c->t_part0;
     const double t0 = now_ms();
-    LQ_TRY(lq_index_alloc(ix, c->opt.k, c->st));
+    LQ_TRY(lq_index_alloc(ix, c->opt.k, 0, c->st));
     LQ_TRY(lq_index_count(ix, &ix->rec, c->st));
     LQ_CUDA_OK(cudaStreamSynchronize(c->st));
     c->stats.t_index_ms += now_ms() - t0;
@@ -394,6 +406,8 @@ extern "C" int lqcov_map_part(lqcov_ctx *c)
     LqMapOpt mo; map_opt_of(&c->opt, &mo);
     std::vector<LqOvl> ovl; std::vector<LqQStat> hs; LqMapStats ms; memset(&ms, 0, sizeof(ms));
     const uint64_t cap = c->opt.seed_budget ? c->opt.seed_budget : 1000000000ULL;
+    if (c->qd.mins.wide)   /* k > 15: the query minimizers take the addresses this part gave their keys */
+        LQ_TRY(lq_wide_translate(&c->ix.wide, c->qd.mins.key64.as<uint64_t>(), c->qd.n_min, c->qd.mins.key.as<uint32_t>(), c->st));
     LQ_TRY(lq_map_part(&c->qd, &c->ix, &mo, c->mid_occ, c->self_off.data(), c->self_list.data(), c->qrank.data(), c->trank.data(), cap, &c->sc, &ovl, &hs, &ms, c->st));
     lq_prof_collect();
     c->stats.t_map_ms += now_ms() - t0; t0 = now_ms();
@@ -428,6 +442,7 @@ extern "C" int lqcov_index_dump(lqcov_ctx *c, const lqcov_reads_t *part, void *f
     LQ_USE_DEV(c);
     if (!c->part_ready || !part->seq || part->seq_on_device) { fprintf(stderr, "[lqcov] ERROR: lqcov_index_dump needs the part just indexed, with its bases in host memory\n"); return -1; }
     LqIndexDev *ix = &c->ix;
+    if (ix->rec.wide) { fprintf(stderr, "[lqcov] ERROR: -d with k > 15 is not supported by this build (index files: k <= 15)\n"); return -1; }
     std::vector<uint32_t> counts((size_t)ix->n_keyspace); std::vector<uint64_t> offs((size_t)ix->n_keyspace + 1), pos((size_t)ix->n_rec + 1);
     LQ_CUDA_OK(cudaMemcpyAsync(counts.data(), ix->counts.p, counts.size() * 4, cudaMemcpyDeviceToHost, c->st));
     LQ_CUDA_OK(cudaMemcpyAsync(offs.data(), ix->offs.p, offs.size() * 8, cudaMemcpyDeviceToHost, c->st));
@@ -465,12 +480,12 @@ extern "C" int lqcov_load_part(lqcov_ctx *c, void *file)
     c->part_ready = false; c->use_full = false; c->placed = false;
     const uint64_t n = mp.key.size();
     LQ_TRY(ix->rec.key.ensure((size_t)(n + 1) * 4)); LQ_TRY(ix->rec.y.ensure((size_t)(n + 1) * 8));
-    ix->rec.n = n; ix->rec.has_span = 0;
+    ix->rec.n = n; ix->rec.has_span = 0; ix->rec.wide = 0;
     if (n) {
         LQ_CUDA_OK(cudaMemcpyAsync(ix->rec.key.p, mp.key.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
         LQ_CUDA_OK(cudaMemcpyAsync(ix->rec.y.p, mp.y.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->st));
     }
-    LQ_TRY(lq_index_alloc(ix, c->opt.k, c->st));
+    LQ_TRY(lq_index_alloc(ix, c->opt.k, 0, c->st));
     LQ_TRY(lq_index_count(ix, &ix->rec, c->st));
     LQ_CUDA_OK(cudaStreamSynchronize(c->st));
     c->stats.t_index_ms += now_ms() - t0;
@@ -576,16 +591,16 @@ extern "C" int lqcov_sketch(const lqcov_opt_t *o, const lqcov_reads_t *reads, ui
     if (o->device >= 0 && cudaSetDevice(o->device) != cudaSuccess) { fprintf(stderr, "[lqcov] ERROR: cannot select CUDA device %d\n", o->device); return -1; }
     if (lq_reads_upload(&rd, (const uint8_t*)reads->seq, reads->seq_off, reads->n, reads->seq_on_device, 0, st) == 0 &&
         lq_sketch_run(&rd, o->w, o->k, o->is_hpc, rid_base, &m, ws, st) == 0) {
-        std::vector<uint32_t> key(m.n); std::vector<uint8_t> sp(m.n);
+        std::vector<uint32_t> key(m.wide ? 0 : m.n); std::vector<uint64_t> key64(m.wide ? m.n : 0); std::vector<uint8_t> sp(m.n);
         uint64_t *hy = (uint64_t*)malloc((m.n + 1) * 8), *hx = (uint64_t*)malloc((m.n + 1) * 8);
         bool ok = true;
         if (m.n) {
-            ok = cudaMemcpy(key.data(), m.key.p, m.n * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
+            ok = (m.wide ? cudaMemcpy(key64.data(), m.key64.p, m.n * 8, cudaMemcpyDeviceToHost) : cudaMemcpy(key.data(), m.key.p, m.n * 4, cudaMemcpyDeviceToHost)) == cudaSuccess &&
                  cudaMemcpy(hy, m.y.p, m.n * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
             if (ok && m.has_span) ok = cudaMemcpy(sp.data(), m.span.p, m.n, cudaMemcpyDeviceToHost) == cudaSuccess;
         }
         if (ok && cudaDeviceSynchronize() == cudaSuccess) {
-            for (uint64_t i = 0; i < m.n; ++i) hx[i] = (uint64_t)key[i] << 8 | (uint64_t)(m.has_span ? sp[i] : o->k);
+            for (uint64_t i = 0; i < m.n; ++i) hx[i] = (m.wide ? key64[i] : (uint64_t)key[i]) << 8 | (uint64_t)(m.has_span ? sp[i] : o->k);
             *x = hx; *y = hy; *n = m.n; rc = 0;
         } else { fprintf(stderr, "[lqcov] CUDA error in lqcov_sketch: %s\n", cudaGetErrorString(cudaGetLastError())); free(hx); free(hy); }
     }

@@ -291,14 +291,15 @@ static int run_parts(cli_dev *dv, int n_dev, lqi_reader *tr, const lqcov_opt_t *
     return rc;
 }
 
-/* GPUs this run drives: all visible ones (LQCOV_GPUS limits), one for jobs that do not shard (-H) */
+/* GPUs this run drives: all visible ones (LQCOV_GPUS limits), one for jobs that do not shard (-H; k > 15, whose index addresses are
+ * numbered per GPU: lq_widx.cu) */
 static int pick_devices(const lqcov_opt_t *o)
 {
     int n = lqcov_device_count();
     const char *e = getenv("LQCOV_GPUS");
     if (e && atoi(e) > 0 && atoi(e) < n) n = atoi(e);
     if (n > CLI_MAX_DEV) n = CLI_MAX_DEV;
-    if (o->is_hpc || n < 1) n = 1;
+    if (o->is_hpc || o->k > 15 || n < 1) n = 1;
     return n;
 }
 

@@ -153,6 +153,7 @@ extern "C" int lqcov_part_exchange(lqcov_ctx *c)
     LqComm *m = c->comm;
     if (!m || m->n == 1) return 0;
     if (c->opt.is_hpc) { fprintf(stderr, "[lqcov] ERROR: -H (spike-in run, a 4 kb target) is a single-GPU job: do not share it between GPUs\n"); return -1; }
+    if (c->ix.rec.wide) { fprintf(stderr, "[lqcov] ERROR: k > 15 is a single-GPU job in this build (the index addresses of wide keys are numbered per GPU)\n"); return -1; }
     if (m->n > PL_MAX_RANKS) { fprintf(stderr, "[lqcov] ERROR: more than %d ranks\n", PL_MAX_RANKS); return -1; }
     LqIndexDev *ix = &c->ix; cudaStream_t st = c->st;
     const int n = m->n, me = m->rank; const uint64_t nkeys = ix->n_keyspace;

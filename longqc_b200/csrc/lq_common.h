@@ -26,6 +26,7 @@
 
 #define LQ_MAX_W 32    /* window sizes the GPU path accepts (LongQC uses 5 and 10) */
 #define LQ_MAX_K_DIRECT 15 /* direct-address minimizer table: 4^k counters (k=15 -> 4 GiB) */
+#define LQ_MAX_K 28        /* as the reference (minimap2-coverage.c:171); 16..28 through the open-address table of lq_widx.cu */
 
 #define LQ_U64MAX 0xffffffffffffffffULL
 

@@ -18,9 +18,10 @@ struct LqReadsDev {
  * y = rid<<32 | lastPos<<1 | strand (minimap.h:42 / sketch.c:70-72); span only in HPC mode (else == k) */
 struct LqMinimizers {
     uint64_t n; int has_span;
-    LqDevBuf key, y, span, blk;
-    LqMinimizers() : n(0), has_span(0) {}
-    void release() { key.release(); y.release(); span.release(); blk.release(); }
+    int wide;              /* k > 15: key64 holds the 2k-bit hashes, key the dense ids lq_widx.cu gives them */
+    LqDevBuf key, y, span, blk, key64;
+    LqMinimizers() : n(0), has_span(0), wide(0) {}
+    void release() { key.release(); y.release(); span.release(); blk.release(); key64.release(); }
 };
 
 int lq_reads_upload(LqReadsDev *d, const uint8_t *h_seq, const uint64_t *h_off, uint32_t n_reads, int seq_on_device, int sdust_tbl, cudaStream_t st);

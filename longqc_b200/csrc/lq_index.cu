@@ -244,13 +244,15 @@ int lq_index_mid_occ(const LqIndexDev *ix, float frac, int32_t *mid_occ, uint64_
 
 /* ------------------------------------------------------------------ part build */
 
-int lq_index_alloc(LqIndexDev *ix, int k, cudaStream_t st)
+int lq_index_alloc(LqIndexDev *ix, int k, uint64_t n_ids, cudaStream_t st)
 {
-    if (k < 1 || k > LQ_MAX_K_DIRECT) {
-        fprintf(stderr, "[lqcov] k=%d: the direct-address minimizer table supports k <= %d in this build\n", k, LQ_MAX_K_DIRECT);
+    if (k < 1 || k > LQ_MAX_K || (k > LQ_MAX_K_DIRECT) != (n_ids != 0)) {
+        fprintf(stderr, "[lqcov] k=%d: unsupported by the index of this build (1..%d)\n", k, LQ_MAX_K);
         return -1;
     }
-    ix->k = k; ix->n_keyspace = 1ULL << (2 * k);
+    ix->k = k;
+    if (n_ids) { ix->n_keyspace = n_ids; ix->key_bits = 1; while (ix->key_bits < 32 && (n_ids >> ix->key_bits)) ++ix->key_bits; }
+    else { ix->n_keyspace = 1ULL << (2 * k); ix->key_bits = 2 * k; }
     LQ_TRY(ix->counts.ensure((size_t)(ix->n_keyspace + 1) * 4));
     LQ_TRY(ix->offs.ensure((size_t)(ix->n_keyspace + 2) * 8));
     LQ_CUDA_OK(cudaMemsetAsync(ix->counts.p, 0, (size_t)(ix->n_keyspace + 1) * 4, st));
@@ -272,7 +274,7 @@ int lq_index_finish(LqIndexDev *ix, LqMinimizers *m, LqDevBuf &ws, cudaStream_t 
     /* counts are final (all-reduced when several GPUs share the part); m holds ALL records of the part in y order */
     { LqProfScope ps("offs_scan", st, 0, ix->n_keyspace * 16);
       LQ_TRY((lq_exclusive_scan<uint32_t, uint64_t>(ix->counts.as<uint32_t>(), ix->offs.as<uint64_t>(), (size_t)ix->n_keyspace, 1, ws, st))); }
-    LQ_TRY(lq_sort_by_key(m, 2 * ix->k, ix->tmp_key, ix->tmp_y, ix->tmp_sp, ix->hist, ws, st, 0));
+    LQ_TRY(lq_sort_by_key(m, ix->key_bits, ix->tmp_key, ix->tmp_y, ix->tmp_sp, ix->hist, ws, st, 0));
     ix->n_rec = m->n;
     return 0;
 }

@@ -146,7 +146,7 @@ static int sd_setup(lqcov_sdust *s)
     double h_q2p[127];
     for (int q = 0; q < 127; ++q) h_q2p[q] = lqh_q2p(q); /* lqutils.c:26-49 */
     LQ_CUDA_OK(cudaMemcpyToSymbol(c_q2p, h_q2p, sizeof(h_q2p)));
-    s->capP = LQ_SD_PCAP(s->W); s->threads = 64; s->blocks = 148;   /* the redo kernel: 64 threads x 61 KB of interval scratch each (0.6 GB) */
+    s->capP = LQ_SD_PCAP(s->W); s->threads = 64; s->blocks = 148 * 8;   /* the redo kernel: 64 threads x 61 KB of interval scratch each (4.7 GB) */
     LQ_TRY(s->d_p.ensure((size_t)s->blocks * s->threads * 4 * s->capP * sizeof(int)));
     LQ_TRY(s->d_cur.ensure(64));
     LQ_CUDA_OK(cudaStreamCreate(&s->st));

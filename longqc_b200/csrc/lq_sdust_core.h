@@ -74,27 +74,42 @@ LQ_HD void lq_sdust_scan(const uint8_t *seq, int l_seq, int T, int W, int from, 
                 if (s.cv[t] * 10 > T << 1) {
                     do { x = s.win[(s.w_front + s.w_n - s.L) & 63]; s.rv -= --s.cv[x]; --s.L; } while (x != (int)t);
                 }
-                if (s.rw * 10 > s.L * T) { /* find_perfect (sdust.c:110-134) */
-                    uint8_t c[64]; int r = s.rv, ii, max_r = 0, max_l = 0, q;
+                if (s.rw * 10 > s.L * T) {
+                    /* find_perfect (sdust.c:110-134), with its two inner loops made linear.  The reference, for every suffix ii of the
+                     * window (longest last), rescans the list from the top down to the first entry starting before ii + start, folding
+                     * the best score ratio seen, and memmoves the tail to insert.  The bound ii + start only falls and every entry
+                     * inserted on the way starts at or above the next bound, so (1) the scan can go on where the previous suffix's
+                     * stopped -- folding an entry twice changes nothing, and the inserted entries carry the running best itself --
+                     * and (2) the insertion points are non-decreasing in the ORIGINAL list: they are collected (at most W-2 per call)
+                     * and merged in with one backward pass.  Same list, O(|P| + W) instead of O(W |P|) steps per base. */
+                    uint8_t c[64]; int r = s.rv, ii, max_r = 0, max_l = 0, q, j = 0, nnew = 0;
+                    uint16_t nat[64]; uint32_t nrl[64];
                     for (q = 0; q < 64; ++q) c[q] = s.cv[q];
                     for (ii = s.w_n - s.L - 1; ii >= 0; --ii) {
                         const int tt = s.win[(s.w_front + ii) & 63];
-                        int j, new_r, new_l;
+                        int new_r, new_l;
                         r += c[tt]++;
                         new_r = r; new_l = s.w_n - ii - 1;
                         if (new_r * 10 > T * new_l) {
-                            for (j = 0; j < s.nP && s.Ps[j] >= ii + start; ++j)
+                            for (; j < s.nP && s.Ps[j] >= ii + start; ++j)
                                 if (max_r == 0 || s.Pr[j] * max_l > max_r * s.Pl[j]) { max_r = s.Pr[j]; max_l = s.Pl[j]; }
                             if (max_r == 0 || new_r * max_l >= max_r * new_l) {
                                 max_r = new_r; max_l = new_l;
-                                if (s.nP >= s.capP) { s.overflow = 1; }
-                                else {
-                                    for (q = s.nP; q > j; --q) { s.Ps[q] = s.Ps[q-1]; s.Pf[q] = s.Pf[q-1]; s.Pr[q] = s.Pr[q-1]; s.Pl[q] = s.Pl[q-1]; }
-                                    ++s.nP;
-                                    s.Ps[j] = ii + start; s.Pf[j] = s.w_n + 2 + start; s.Pr[j] = new_r; s.Pl[j] = new_l;
-                                }
+                                nat[nnew] = (uint16_t)j; nrl[nnew] = (uint32_t)new_r << 8 | (uint32_t)new_l; ++nnew;
                             }
                         }
+                    }
+                    if (s.nP + nnew > s.capP) s.overflow = 1;
+                    else if (nnew) {
+                        int dst = s.nP + nnew - 1, src = s.nP - 1, m;
+                        const int fin = s.w_n + 2 + start;
+                        for (m = nnew - 1; m >= 0; --m) {
+                            const int at = (int)nat[m], nl = (int)(nrl[m] & 255u);
+                            for (; src >= at; --src, --dst) { s.Ps[dst] = s.Ps[src]; s.Pf[dst] = s.Pf[src]; s.Pr[dst] = s.Pr[src]; s.Pl[dst] = s.Pl[src]; }
+                            s.Ps[dst] = s.w_n - 1 - nl + start; s.Pf[dst] = fin; s.Pr[dst] = (int)(nrl[m] >> 8); s.Pl[dst] = nl;
+                            --dst;
+                        }
+                        s.nP += nnew;
                     }
                 }
             }

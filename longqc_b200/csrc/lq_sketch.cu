@@ -651,12 +651,16 @@ __global__ void __launch_bounds__(RL_THREADS) lq_sketch_lane_k(SkArgs a)
 /* ------------------------------------------------------------------ HPC sketch: one thread per read (spike-in run, reference sketch.c:93-104) */
 
 struct SkWriteSpan {
-    uint32_t *key; uint64_t *yy; uint8_t *span; uint64_t at;
-    __device__ __forceinline__ void operator()(uint64_t x_, uint64_t y_) { key[at] = (uint32_t)(x_ >> 8); yy[at] = y_; span[at] = (uint8_t)x_; ++at; }
+    uint32_t *key; uint64_t *key64; uint64_t *yy; uint8_t *span; uint64_t at;
+    __device__ __forceinline__ void operator()(uint64_t x_, uint64_t y_)
+    {
+        if (key64) key64[at] = x_ >> 8; else key[at] = (uint32_t)(x_ >> 8);
+        yy[at] = y_; if (span) span[at] = (uint8_t)x_; ++at;
+    }
 };
 
 template <int WRITE>
-__global__ void lq_sketch_seq_k(SkArgs a, uint32_t n_reads, int is_hpc, uint32_t *read_count, const uint64_t *read_base, uint8_t *out_span)
+__global__ void lq_sketch_seq_k(SkArgs a, uint32_t n_reads, int is_hpc, uint32_t *read_count, const uint64_t *read_base, uint8_t *out_span, uint64_t *out_key64)
 {
     const uint32_t rd = blockIdx.x * blockDim.x + threadIdx.x;
     if (rd >= n_reads) return;
@@ -667,7 +671,7 @@ __global__ void lq_sketch_seq_k(SkArgs a, uint32_t n_reads, int is_hpc, uint32_t
         if (L > 0) lq_sketch_replay(a.b2, a.nm, g0, L, a.w, a.k, a.rid_base + rd, is_hpc, 0, 1, L - 1, 0, L, (int*)0, c);
         read_count[rd] = (uint32_t)c.n;
     } else {
-        SkWriteSpan wr; wr.key = a.out_key; wr.yy = a.out_y; wr.span = out_span; wr.at = read_base[rd];
+        SkWriteSpan wr; wr.key = a.out_key; wr.key64 = out_key64; wr.yy = a.out_y; wr.span = out_span; wr.at = read_base[rd];
         if (L > 0) lq_sketch_replay(a.b2, a.nm, g0, L, a.w, a.k, a.rid_base + rd, is_hpc, 0, 1, L - 1, 0, L, (int*)0, wr);
     }
 }
@@ -855,7 +859,8 @@ int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_b
     a.slot0 = rd->slot0.as<uint64_t>(); a.n_slots = rd->n_slots; a.w = w; a.k = k; a.rid_base = rid_base;
     a.ticket = 0; a.state = 0; a.cap = 0; a.err = 0; a.out_key = 0; a.out_y = 0; a.g_begin = 0; a.base_in = 0; a.base_out = 0;
     uint64_t total = 0;
-    if (!is_hpc) {
+    out->wide = k > LQ_MAX_K_DIRECT;   /* 2k-bit hashes in key64; one thread per read, as in HPC mode (the general state machine) */
+    if (!is_hpc && !out->wide) {
         const bool roll = (w == 5 || w == 10) && k <= 15 && !g_sketch_tiled;
         const bool lanes = roll && g_sketch_lanes;
         const unsigned nblk = lanes ? (unsigned)((rd->n_slots * (LQ_SLOT / LQ_RL_SEG) + RL_TILE_SEGS - 1) / RL_TILE_SEGS)
@@ -903,19 +908,20 @@ int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_b
         uint32_t *cnt = out->blk.as<uint32_t>();
         uint64_t *base = (uint64_t*)((char*)out->blk.p + (((size_t)(n + 1) * 4 + 7) & ~(size_t)7));
         lq_prof_count_launch(2);
-        lq_sketch_seq_k<0><<<lq_grid(n, 64), 64, 0, st>>>(a, n, 1, cnt, 0, 0);
+        lq_sketch_seq_k<0><<<lq_grid(n, 64), 64, 0, st>>>(a, n, is_hpc, cnt, 0, 0, 0);
         LQ_CUDA_OK(cudaGetLastError());
         LQ_TRY((lq_exclusive_scan<uint32_t, uint64_t>(cnt, base, n, 1, ws, st)));
         LQ_CUDA_OK(cudaMemcpyAsync(&total, base + n, 8, cudaMemcpyDeviceToHost, st));
         LQ_CUDA_OK(cudaStreamSynchronize(st));
         LQ_TRY(out->key.ensure((size_t)(total + 1) * 4));
         LQ_TRY(out->y.ensure((size_t)(total + 1) * 8));
-        LQ_TRY(out->span.ensure((size_t)(total + 1)));
+        if (is_hpc) LQ_TRY(out->span.ensure((size_t)(total + 1)));
+        if (k > LQ_MAX_K_DIRECT) LQ_TRY(out->key64.ensure((size_t)(total + 1) * 8));
         a.out_key = out->key.as<uint32_t>(); a.out_y = out->y.as<uint64_t>();
-        lq_sketch_seq_k<1><<<lq_grid(n, 64), 64, 0, st>>>(a, n, 1, 0, base, out->span.as<uint8_t>());
+        lq_sketch_seq_k<1><<<lq_grid(n, 64), 64, 0, st>>>(a, n, is_hpc, 0, base, is_hpc ? out->span.as<uint8_t>() : 0, k > LQ_MAX_K_DIRECT ? out->key64.as<uint64_t>() : 0);
         LQ_CUDA_OK(cudaGetLastError());
     }
-    out->n = total;
+    out->n = total; out->has_span = is_hpc;
     return 0;
 }
 

@@ -3,7 +3,7 @@
 /root/reference by oracle/Makefile) on the seeded cases of tests/cases.py.  Run in the build container
 (the reference sources are not available on the GPU box); the outputs are committed.
 
-    python oracle/make_golden.py
+    python oracle/make_golden.py [case ...]
 """
 import json
 import os
@@ -24,8 +24,12 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 def main():
     assert os.path.exists(REF), "build oracle/_ref first: make -C oracle ref"
     os.makedirs(GOLD, exist_ok=True)
-    manifest = {}
+    only = set(sys.argv[1:])   # case names: regenerate just those (the manifest keeps the others)
+    mf = os.path.join(GOLD, "manifest.json")
+    manifest = json.load(open(mf)) if only and os.path.exists(mf) else {}
     for name in sorted(cases.CASES):
+        if only and name not in only:
+            continue
         T, Q = cases.make_case(name)
         flags = cases.CASES[name][2]
         with tempfile.TemporaryDirectory() as d:
@@ -43,7 +47,8 @@ def main():
                           "rows": out.stdout.count(b"\n"), "mid_occ_line": mid[0].split("] ")[-1] if mid else None}
         print(name, manifest[name])
     json.dump(manifest, open(os.path.join(GOLD, "manifest.json"), "w"), indent=1, sort_keys=True)
-    make_dump_goldens()
+    if not only:
+        make_dump_goldens()
 
 
 def make_dump_goldens():

@@ -22,6 +22,11 @@ CASES = {
     # BASELINE configs[3] flavour: ONT ultra-long 50 kb reads, -x ont-rapid (-p 160): long chains, thousands of anchors per target
     "ultralong": (("std", 60, 50000, 0.15, 31, 12), dict(min_score_med=160, min_score_good=160), "-Y -l 0 -q 160 -k 12 -w 5 -I 4G -p 160"),
     # BASELINE configs[4] reduced: mixed-GC genome, 10 % iid junk + 10 % adapter/low-complexity reads, several index parts, -x pb-sequel
+    # k > 15: the open-address index (lq_widx.cu).  longQC.py:222-226: `-x pb-hifi --fast` runs -k 19 -w 10; then other widths / several parts
+    "hifi_fast_k19": (("std", 250, 8000, 0.01, 112, 30), dict(k=19, w=10, min_score_med=80, min_score_good=160), "-Y -l 0 -q 160 -k 19 -w 10 -I 4G -p 80"),
+    "wide_k17_parts": (("std", 300, 6000, 0.04, 113, 40), dict(k=17, min_score_med=80, min_score_good=160, batch_size=400000), "-Y -l 0 -q 160 -k 17 -w 5 -I 400K -p 80"),
+    "wide_k28_tandem": (("tandem", 114, 200, 5000, 30), dict(k=28, w=10, min_score_med=80, min_score_good=160), "-Y -l 0 -q 160 -k 28 -w 10 -I 4G -p 80"),
+    "wide_k16_nfasta": (("nfasta", 115, 200, 5000, 30), dict(k=16, min_score_med=80, min_score_good=160), "-Y -l 0 -q 160 -k 16 -w 5 -p 80"),
     "c5_small": (("junk", 111, 1500, 6000, 400), dict(min_score_med=80, min_score_good=160, batch_size=2000000), "-Y -l 0 -q 160 -k 12 -w 5 -I 2M -p 80"),
 }
 

@@ -14,7 +14,7 @@ def _L():
     return L
 
 
-@pytest.mark.parametrize("w,k", [(5, 12), (10, 15), (5, 15), (3, 4), (7, 11), (32, 9)])
+@pytest.mark.parametrize("w,k", [(5, 12), (10, 15), (5, 15), (3, 4), (7, 11), (32, 9), (10, 19), (5, 16), (11, 28)])
 def test_sketch_adversarial(w, k):
     L = _L()
     rng = np.random.default_rng(100 + w * 31 + k)
