@@ -852,7 +852,7 @@ int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_b
 {
     out->n = 0; out->has_span = is_hpc;
     if (w < 1 || w > LQ_MAX_W) { fprintf(stderr, "[lqcov] window size %d not supported on the GPU path (1..%d)\n", w, LQ_MAX_W); return -1; }
-    if (k < 1 || k > 16) { fprintf(stderr, "[lqcov] k-mer size %d not supported on the GPU path (1..16 sketch, <=%d indexed)\n", k, LQ_MAX_K_DIRECT); return -1; }
+    if (k < 1 || k > LQ_MAX_K) { fprintf(stderr, "[lqcov] k-mer size %d outside 1..%d\n", k, LQ_MAX_K); return -1; }
     if (rd->n_reads == 0 || rd->n_slots == 0) return 0;
     SkArgs a;
     a.b2 = rd->b2.as<uint32_t>(); a.nm = rd->nm.as<uint32_t>(); a.slot_read = rd->slot_read.as<uint32_t>(); a.len = rd->len.as<uint32_t>();

@@ -30,7 +30,8 @@ def test_abi_sdust_equals_reference_golden(name):
     assert L.sdust_table(Q) == open(os.path.join(GOLD, name + ".sdust.tsv"), "rb").read()
 
 
-@pytest.mark.parametrize("name,gz", [("plain_pb", False), ("tandem_parts", True), ("spike_hpc_filter", False), ("ambiguous_fasta", True), ("ava_X", False)])
+@pytest.mark.parametrize("name,gz", [("plain_pb", False), ("tandem_parts", True), ("spike_hpc_filter", False), ("ambiguous_fasta", True), ("ava_X", False), ("hifi_fast_k19", False),
+                                     ("wide_k17_parts", False)])
 def test_dropin_executables_like_longqc(name, gz, tmp_path):
     """argv + stdout bytes + exit status: exactly what longQC.py:438-445 / lq_mask.py:17-23 rely on"""
     import longqc_b200 as L

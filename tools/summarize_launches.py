@@ -52,12 +52,16 @@ def main():
         a = agg.setdefault(nm, [0, 0.0, 0.0, 0.0])
         a[0] += 1; a[1] += t; a[2] += x.get("dram__bytes_read.sum", 0.0); a[3] += x.get("dram__bytes_write.sum", 0.0)
         sc = SCOPE_OF.get(nm)
-        if nm == "lq_af_big_k<0>":
+        if nm in ("lq_af_big_k<0>", "lq_af_big_k"):
             level += 1                                           # first launch of a sort level (shift 56, 48, ...)
-        if nm in ("lq_af_big_k<0>", "lq_af_level_k"):
+        if nm in ("lq_af_big_k<0>", "lq_af_big_k", "lq_af_level_k"):
             sc = "seed_sort_s%d" % (56 - 8 * (level % 8))
-        if nm in ("lq_af_walk_k", "lq_af_big_k<1>", "lq_af_walk_small_k"):
+        if nm in ("lq_af_walk_k", "lq_af_big_k<1>", "lq_af_walk3_k", "lq_af_walkf_k"):
             sc = "seed_walk_s%d" % (56 - 8 * (level % 8))
+        if nm == "lq_af_place_k":
+            sc = "seed_place_s%d" % (56 - 8 * (level % 8))
+        if nm == "lq_af_walk_small_k":
+            sc = "seed_walksmall_s%d" % (56 - 8 * (level % 8))
         if sc:
             s = scope[sc]; s[0] += t; s[1] += b; s[2] += 1
     tot = sum(a[1] for a in agg.values())
