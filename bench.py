@@ -50,12 +50,18 @@ def parse():
     ap.add_argument("--ref-full", action="store_true", help="--impl reference at N > 1: time the whole N-GPU workload (N x 25 s per step)")
     ap.add_argument("--no-cli", action="store_true", help="skip the drop-in executable's end-to-end run (cli_e2e)")
     ap.add_argument("--no-sdust", action="store_true", help="skip the sdust line")
-    return ap.parse_args()
+    ap.add_argument("--preset", default="ont-ligation", choices=["ont-ligation", "ont-rapid", "pb-sequel"],
+                    help="LongQC preset whose native flags are used (longQC.py:171-231); the default is BASELINE configs[1]'s")
+    a = ap.parse_args()
+    global FLAGS
+    if a.preset == "pb-sequel":      # minimap2_med_score_threshold = 80
+        FLAGS = "-Y -l 0 -q 160 -k 12 -w 5 -I 4G -p 80"
+    return a
 
 
 def workload_name(a, world=1):
-    s = "%dk synthetic ONT %d kb reads (%.0f%% error), -x ont-ligation (%s), %d sampled queries" % (
-        a.reads // 1000, a.read_len // 1000, a.err * 100, FLAGS, a.queries)
+    s = "%dk synthetic %s %d kb reads (%.0f%% error), -x %s (%s), %d sampled queries" % (
+        a.reads // 1000, "Sequel" if a.preset == "pb-sequel" else "ONT", a.read_len // 1000, a.err * 100, a.preset, FLAGS, a.queries)
     if world > 1:   # weak scaling: every rank brings its own reads of one shared genome, the queries are split
         s += "; x%d GPUs = %dk target reads in one replicated index, %d queries per GPU" % (world, a.reads * world // 1000, a.queries // world)
     return s
@@ -308,7 +314,7 @@ def sdust_line(a, L, reads):
     out = {"value": reads.n_bases / dt / 1e9, "unit": "Gbases/s", "seconds": dt, "first_call_seconds": t1 - t0, "reads": reads.n, "rows": tab.count(b"\n"),
            "kernel_ms": kms, "kernel_gbs": (2 * reads.n_bases / (kms * 1e-3) / 1e9) if kms > 0 else None, "kernel_frac_of_hbm_peak": (2 * reads.n_bases / (kms * 1e-3) / 1e9 / peak) if kms > 0 else None,
            "what": "lqcov_sdust_table on all target reads (pageable host buffers in, table out; chunks of 48 MB: copy of chunk c+1 beside the kernel of chunk c); "
-                   "kernel_*: lq_sdust_k alone (CUDA events), 2 bytes per base (base + quality)"}
+                   "kernel_*: the sdust kernels alone (segment scan, redo of segments with long interval lists, per-read fold, quality sums; CUDA events), 2 bytes per base (base + quality)"}
     ref = os.path.join(ROOT, "oracle", "_ref", "sdust")
     if os.path.exists(ref):   # the reference's sdust on a bounded sample (one thread, as lq_mask.py runs it per chunk)
         n = min(reads.n, 4000)
@@ -340,7 +346,7 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from longqc_b200 import dist as lqdist
 
-    opt = L.Opt(min_score_med=160, min_score_good=160, device=local)
+    opt = L.Opt(min_score_med=80 if a.preset == "pb-sequel" else 160, min_score_good=160, device=local)
     runner = lqdist.Runner(a, opt, rank, world, local)
     targets, queries = runner.make_inputs()        # this rank's shard of the workload (weak scaling)
     n_bases_job = runner.job_bases()                # all ranks together

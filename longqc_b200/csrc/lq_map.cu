@@ -663,6 +663,9 @@ __device__ __forceinline__ void afb_subbuckets(const AfArgs &a, uint32_t beg, ui
     }
 }
 
+/* CTAs per SM working on big buckets at a time: the passes over a bucket re-read it, so the buckets in flight should fit the L2 */
+static unsigned g_afb_ctas = getenv("LQCOV_AFB_CTAS") && atoi(getenv("LQCOV_AFB_CTAS")) > 0 ? (unsigned)atoi(getenv("LQCOV_AFB_CTAS")) : 4u;
+
 __global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
 {
     __shared__ uint32_t s_cnt[256], s_start[257], s_head[256], scan_sm[33];
@@ -1850,7 +1853,7 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         unsigned long long *n_elem = (unsigned long long*)(ctr + 16);
         a.n_elem = n_elem + (shift >> 3);
         { LqProfScope ps(lvl_name[shift >> 3], st, 2, 0);
-          lq_af_big_k<<<148 * 4, AFB_THREADS, 0, st>>>(a);
+          lq_af_big_k<<<148 * g_afb_ctas, AFB_THREADS, 0, st>>>(a);
           lq_af_level_k<<<148 * 16, AF_WARPS * 32, 0, st>>>(a); }
         a.n_elem = n_elem + 8 + (shift >> 3);
         { LqProfScope ps(wlk_name[shift >> 3], st, 2, 0);

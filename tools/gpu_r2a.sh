@@ -15,3 +15,7 @@ for k in b['kernels'][:24]: print("  %-22s %8.3f ms  %5.1f%%  %7.1f GB/s" % (k['
 print({k: (round(v,1) if isinstance(v,float) else v) for k,v in b['stats'].items()})
 PY
 tail -3 gpurun_out/bench.err
+( time timeout 600 python bench.py --impl reference --steps 1 --warmup 3 ) > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err
+cut -c1-600 gpurun_out/bench_ref.log
+( timeout 300 python -c 'import __graft_entry__ as g; g.smoke(); print("smoke ok")' ) 2>&1 | tail -2
+bash tools/gpu_launches.sh
