@@ -283,16 +283,39 @@ LQ_HD void lq_afq_expand(const uint8_t *seq, uint32_t n, const uint32_t *start, 
 }
 
 /* ---- the same walk for levels with FEW regions (all digits < 16: the rid >> 16 byte once a part holds more than 131 072 reads).
- * With 11 cached digits per region a 4-region walk runs dry every ~40 pick-ups; here a region caches LQ_AFR_CAP digits, four per
- * word: blk[(r * LQ_AFR_BLK + 1 + w) * stride], and word 0 of the block is the region's read offset inside that stretch.  A step is
- * two dependent 32-bit loads (offset, digit word) and a handful of ALU operations; the offset is stored back off the critical path. */
-#define LQ_AFR_CAP 236
-#define LQ_AFR_WORDS (LQ_AFR_CAP / 4)
-#define LQ_AFR_BLK (LQ_AFR_WORDS + 1)
+ * Such walks are long (a whole (query, strand) bucket: 10^5..10^6 pick-ups) and nothing hides the latency of a lone walker, so the
+ * step is cut down to ONE load on the critical path.  Per region, in the walker's cache (words, interleaved by `stride`):
+ *   word 0   the WINDOW: the region's next (up to) 7 digits, 4 bits each, lowest first, under a marker bit -- 1 = empty
+ *   word 1   how many queue words have been moved into the window
+ *   word 2   bucket-relative position of the first digit of queue word 0
+ *   word 3.. the QUEUE: LQ_AFR_QW words in window format, then a sentinel: 0 = "more digits in global memory", 1 = "region ends here"
+ * A pick-up is: load the window of region c, d = w & 15, store w >> 4 -- or, when that leaves the window empty, the next queue word
+ * (eagerly: the next visit again finds its digit with one load).  A sentinel 0 ends the round: every region's queue is then rebuilt
+ * from its next unread position (lq_afr_refill_*).  Digits cached beyond a region's end are never consumed: a region is visited
+ * exactly as often as it has elements. */
 #define LQ_AFR_R 16
+#define LQ_AFR_BLK 60
+#define LQ_AFR_QW (LQ_AFR_BLK - 4)          /* 56 queue words = 392 digits per region and round */
 typedef struct { uint32_t k, c, step, acc, rem_k; } lq_afr_walk;
 
-/* base[r * bstride]: bucket-relative position of the first cached digit of region r (== next unread position - offset) */
+LQ_HD uint32_t lq_afr_digits_left(uint32_t win)   /* digits under the marker bit (win >= 1) */
+{
+#ifdef __CUDA_ARCH__
+    return (31u - (uint32_t)__clz((int)win)) >> 2;
+#else
+    uint32_t n = 0; while (win > 15u) { win >>= 4; ++n; } return n;
+#endif
+}
+
+/* next unread position of region r (whose elements end at `end`) from its three state words */
+LQ_HD uint32_t lq_afr_next(uint32_t win, uint32_t q, uint32_t qbase, uint32_t end)
+{
+    if (win == 0u) return qbase + 7u * q;                         /* the whole queue has been consumed */
+    const uint32_t wstart = qbase + 7u * (q - 1u);                /* first digit of the word now in the window */
+    const uint32_t cntw = wstart < end ? (end - wstart < 7u ? end - wstart : 7u) : 0u;
+    return wstart + cntw - lq_afr_digits_left(win);
+}
+
 LQ_HD void lq_afr_init(lq_afr_walk *s, const uint32_t *start, lq_afq_phase *ph)
 {
     uint32_t k = 0;
@@ -301,87 +324,74 @@ LQ_HD void lq_afr_init(lq_afr_walk *s, const uint32_t *start, lq_afq_phase *ph)
     if (k < LQ_AFR_R) { ph[k].t = 0; ph[k].p = start[k]; }
 }
 
+/* queue word j (0..LQ_AFR_QW) of a region whose next unread position is nxt and whose elements end at `end` */
+LQ_HD uint32_t lq_afr_queue_word(const uint8_t *dig, uint32_t nxt, uint32_t end, uint32_t j)
+{
+    const uint32_t p = nxt + 7u * j;
+    if (j == LQ_AFR_QW) return p < end ? 0u : 1u;
+    const uint32_t cnt = p < end ? (end - p < 7u ? end - p : 7u) : 0u;
+    uint32_t v = 1u << (4u * cnt);
+    for (uint32_t b = 0; b < cnt; ++b) v |= (uint32_t)(dig[p + b] & 15u) << (4u * b);
+    return v;
+}
+
 /* M: word access to the walk's cache, M::ld(i) / M::st(i, v) with i = (r * LQ_AFR_BLK + j) * stride -- on the device explicit
- * shared-space loads and stores (LqSmemWords in lq_map.cu), on the host a plain array.  The walk runs in SAFE STRETCHES: m = the
- * fewest cached digits any region has left, so the next m pick-ups need neither a "cache empty" nor an "end of bucket" test; a
- * stretch shorter than LQ_AFR_MINRUN asks for a refill instead.  One pick-up is then ~17 instructions: a lone walker warp issues
- * them back to back at ~5 cycles each, so the instruction count IS the step time. */
-#define LQ_AFR_MINRUN 16
+ * shared-space loads and stores (LqSmemWords in lq_map.cu), on the host a plain array.  Returns 1 when the bucket is finished,
+ * 0 when a queue ran dry (refill every region and call again). */
 template <class M>
-LQ_HD int lq_afr_run(lq_afr_walk *s, uint32_t n, const uint32_t *start, M mem, uint32_t stride, const uint32_t *base, uint32_t bstride,
-                     uint32_t *seq32, lq_afq_phase *ph)
+LQ_HD int lq_afr_run(lq_afr_walk *s, uint32_t n, const uint32_t *start, M mem, uint32_t stride, uint32_t *seq32, lq_afq_phase *ph)
 {
     uint32_t k = s->k, c = s->c, step = s->step, acc = s->acc, rem_k = s->rem_k;
     const uint32_t RB = LQ_AFR_BLK * stride;
-    int done = 1;
-#define LQ_AFR_STEP(J) { \
+    uint32_t need = 0;
+#define LQ_AFR_STEP(J, T) { \
         const uint32_t ob = c * RB; \
-        const uint32_t off = mem.ld(ob); \
-        const uint32_t w = mem.ld(ob + (1 + (off >> 2)) * stride); \
-        const uint32_t d = (w >> (8 * (off & 3u))) & 255u; \
-        mem.st(ob, off + 1); \
+        const uint32_t w = mem.ld(ob); \
+        const uint32_t d = w & 15u; \
+        uint32_t wn = w >> 4; \
         rem_k -= (c == k); \
         acc |= d << (8 * (J)); \
+        if (wn == 1u) {                                           /* window empty: the next queue word, now */ \
+            const uint32_t q = mem.ld(ob + stride); \
+            wn = mem.ld(ob + (3u + q) * stride); \
+            if (wn != 0u) mem.st(ob + stride, q + 1u); else need = 1u; \
+        } \
+        mem.st(ob, wn); \
         c = d; \
-        if (d == k && rem_k == 0) {                               /* region k complete: open the next non-exhausted region */ \
+        if (rem_k == 0u && d == k) {                              /* region k complete: open the next non-exhausted region */ \
             for (;;) { \
                 ++k; \
                 if (k >= LQ_AFR_R) break; \
-                const uint32_t nxt = base[k * bstride] + mem.ld(k * RB);   /* next unread position of region k */ \
-                if (nxt != start[k + 1]) { c = k; rem_k = start[k + 1] - nxt; ph[k].t = step + (J) + 1; ph[k].p = nxt; break; } \
+                const uint32_t kb = k * RB; \
+                const uint32_t nxt = lq_afr_next(mem.ld(kb), mem.ld(kb + stride), mem.ld(kb + 2u * stride), start[k + 1]); \
+                if (nxt < start[k + 1]) { c = k; rem_k = start[k + 1] - nxt; ph[k].t = (T) + 1; ph[k].p = nxt; break; } \
             } \
             if (k >= LQ_AFR_R) c = 0; \
         } }
-    while (step < n) {
-        uint32_t m = n - step;
-        for (uint32_t r = 0; r < LQ_AFR_R; ++r) { const uint32_t left = LQ_AFR_CAP - mem.ld(r * RB); m = left < m ? left : m; }
-        if (m < LQ_AFR_MINRUN && m < n - step) { done = 0; break; }
-        const uint32_t stop = step + m;
-        while (step < stop && (step & 3u)) {                      /* up to a word boundary of the digit stream */
-            const uint32_t J = step & 3u;
-            const uint32_t ob = c * RB, off = mem.ld(ob), w = mem.ld(ob + (1 + (off >> 2)) * stride), d = (w >> (8 * (off & 3u))) & 255u;
-            mem.st(ob, off + 1);
-            rem_k -= (c == k);
-            acc |= d << (8 * J);
-            c = d;
-            if (d == k && rem_k == 0) {
-                for (;;) {
-                    ++k;
-                    if (k >= LQ_AFR_R) break;
-                    const uint32_t nxt = base[k * bstride] + mem.ld(k * RB);
-                    if (nxt != start[k + 1]) { c = k; rem_k = start[k + 1] - nxt; ph[k].t = step + 1; ph[k].p = nxt; break; }
-                }
-                if (k >= LQ_AFR_R) c = 0;
-            }
-            ++step;
-            if ((step & 3u) == 0) { seq32[(step - 1) >> 2] = acc; acc = 0; }
-        }
-        while (step + 4 <= stop) {                                /* whole words: static byte lanes */
-            LQ_AFR_STEP(0) LQ_AFR_STEP(1) LQ_AFR_STEP(2) LQ_AFR_STEP(3)
+    while (step < n && !need) {
+        if ((step & 3u) == 0u && step + 4 <= n) {                 /* whole words of the digit stream: static byte lanes */
+            LQ_AFR_STEP(0, step)
+            if (need) { step += 1; break; }
+            LQ_AFR_STEP(1, step + 1)
+            if (need) { step += 2; break; }
+            LQ_AFR_STEP(2, step + 2)
+            if (need) { step += 3; break; }
+            LQ_AFR_STEP(3, step + 3)
             seq32[step >> 2] = acc; acc = 0;
             step += 4;
-        }
-        while (step < stop) {                                     /* the rest of the stretch */
-            const uint32_t J = step & 3u;
-            const uint32_t ob = c * RB, off = mem.ld(ob), w = mem.ld(ob + (1 + (off >> 2)) * stride), d = (w >> (8 * (off & 3u))) & 255u;
-            mem.st(ob, off + 1);
-            rem_k -= (c == k);
-            acc |= d << (8 * J);
-            c = d;
-            if (d == k && rem_k == 0) {
-                for (;;) {
-                    ++k;
-                    if (k >= LQ_AFR_R) break;
-                    const uint32_t nxt = base[k * bstride] + mem.ld(k * RB);
-                    if (nxt != start[k + 1]) { c = k; rem_k = start[k + 1] - nxt; ph[k].t = step + 1; ph[k].p = nxt; break; }
-                }
-                if (k >= LQ_AFR_R) c = 0;
+        } else {
+            switch (step & 3u) {
+                case 0: LQ_AFR_STEP(0, step) break;
+                case 1: LQ_AFR_STEP(1, step) break;
+                case 2: LQ_AFR_STEP(2, step) break;
+                default: LQ_AFR_STEP(3, step) break;
             }
             ++step;
-            if ((step & 3u) == 0) { seq32[(step - 1) >> 2] = acc; acc = 0; }
+            if ((step & 3u) == 0u) { seq32[(step - 1) >> 2] = acc; acc = 0; }
         }
     }
 #undef LQ_AFR_STEP
+    const int done = step >= n;
     if (done && (step & 3u)) seq32[step >> 2] = acc;
     s->k = k; s->c = c; s->step = step; s->acc = acc; s->rem_k = rem_k;
     return done;
@@ -390,17 +400,20 @@ LQ_HD int lq_afr_run(lq_afr_walk *s, uint32_t n, const uint32_t *start, M mem, u
 /* plain-array word access (host check) */
 struct lq_afr_host_words { uint32_t *a; LQ_HD uint32_t ld(uint32_t i) const { return a[i]; } LQ_HD void st(uint32_t i, uint32_t v) const { a[i] = v; } };
 
-/* host form of the few-region refill: every region's cached stretch restarts at its next unread position */
-LQ_HD void lq_afr_refill_host(const uint8_t *dig, uint32_t n, uint32_t *blk, uint32_t *base)
+/* the cache before the first refill: nothing consumed, queues empty */
+LQ_HD void lq_afr_cache_init_host(uint32_t *blk, const uint32_t *start)
+{
+    for (uint32_t r = 0; r < LQ_AFR_R; ++r) { blk[r * LQ_AFR_BLK] = 0; blk[r * LQ_AFR_BLK + 1] = 0; blk[r * LQ_AFR_BLK + 2] = start[r]; }
+}
+
+/* host form of the few-region refill: every region's queue restarts at its next unread position */
+LQ_HD void lq_afr_refill_host(const uint8_t *dig, const uint32_t *start, uint32_t *blk)
 {
     for (uint32_t r = 0; r < LQ_AFR_R; ++r) {
-        const uint32_t p = base[r] + blk[r * LQ_AFR_BLK];
-        base[r] = p; blk[r * LQ_AFR_BLK] = 0;
-        for (uint32_t w = 0; w < LQ_AFR_WORDS; ++w) {
-            uint32_t v = 0;
-            for (uint32_t j = 0; j < 4; ++j) { const uint32_t q = p + 4 * w + j; v |= (uint32_t)(q < n ? dig[q] : 0) << (8 * j); }
-            blk[r * LQ_AFR_BLK + 1 + w] = v;
-        }
+        uint32_t *b = blk + r * LQ_AFR_BLK;
+        const uint32_t end = start[r + 1], nxt = lq_afr_next(b[0], b[1], b[2], end);
+        for (uint32_t j = 0; j <= LQ_AFR_QW; ++j) b[3 + j] = lq_afr_queue_word(dig, nxt, end, j);
+        b[2] = nxt; b[1] = 1; b[0] = b[3];
     }
 }
 

@@ -166,15 +166,15 @@ void afsort_levels(const uint64_t *key, uint32_t n, uint32_t *idx, int use_two)
                     for (uint32_t p = 0; p < m; ++p)
                         dest[beg + p] = lq_af_two_dest(p, n0, fr[p], rk[p], (uint32_t)P.size(), P.data(), Z.data());
                 } else if ((use_two & 16) && cnt_above_15(cnt) == 0) { // few regions: cached stretches + byte offsets in registers, digit stream out
-                    uint32_t st257[257], base[LQ_AFR_R]; std::vector<uint32_t> cache(LQ_AFR_R * LQ_AFR_BLK, 0u); lq_afr_walk ws; lq_afq_phase ph[256];
+                    uint32_t st257[257]; std::vector<uint32_t> cache(LQ_AFR_R * LQ_AFR_BLK, 0u); lq_afr_walk ws; lq_afq_phase ph[256];
                     for (int d = 0; d < 256; ++d) { st257[d] = start[d]; ph[d].t = 0xffffffffu; ph[d].p = 0; }
                     st257[256] = m;
-                    for (int r = 0; r < LQ_AFR_R; ++r) base[r] = start[r];
+                    lq_afr_cache_init_host(cache.data(), st257);
                     lq_afr_init(&ws, st257, ph);
                     std::vector<uint32_t> seq32(m / 4 + 2), ord(m), slot(m); uint32_t run[256];
                     for (;;) {
-                        lq_afr_refill_host(dig.data() + beg, m, cache.data(), base);
-                        { lq_afr_host_words hw; hw.a = cache.data(); if (lq_afr_run(&ws, m, st257, hw, 1, base, 1, seq32.data(), ph)) break; }
+                        lq_afr_refill_host(dig.data() + beg, st257, cache.data());
+                        { lq_afr_host_words hw; hw.a = cache.data(); if (lq_afr_run(&ws, m, st257, hw, 1, seq32.data(), ph)) break; }
                     }
                     lq_afq_expand((const uint8_t*)seq32.data(), m, st257, ph, run, ord.data(), slot.data());
                     for (uint32_t t = 0; t < m; ++t) dest[beg + ord[t]] = slot[t];

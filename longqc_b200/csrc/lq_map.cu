@@ -968,7 +968,8 @@ __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk3_k(AfArgs a, uint32
 /* lq_af_walkf_k: the same for buckets all of whose digits are below 16 (lq_afr_*: the rid >> 16 byte once a part holds more than
  * 131 072 reads -- every multi-GPU run, and every 4 G-base part of reads shorter than 30 kb).  Such walks are few (one per tied query and
  * strand) and long (10^5..10^6 pick-ups), so they are spread thinly: AFF_LANES buckets per CTA, three CTAs per SM.  A region caches
- * 240 digits in shared memory ([region][word][lane]); its read offset is a byte of four registers. */
+ * 392 digits in shared memory ([region][word][lane]: window, queue cursor, queue origin, 57 queue words of 7 four-bit digits); a
+ * pick-up is one shared-memory load on the critical path (lq_afsort_core.h, lq_afr_run). */
 #define AFF_LANES 16
 #define AFF_THREADS 256
 #define AFF_GRID (148 * 3)
@@ -978,7 +979,7 @@ struct LqSmemWords {
     __device__ __forceinline__ uint32_t ld(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + 4u * i) : "memory"); return v; }
     __device__ __forceinline__ void st(uint32_t i, uint32_t v) const { asm volatile("st.shared.u32 [%0], %1;" :: "r"(base + 4u * i), "r"(v) : "memory"); }
 };
-struct AffSmem { uint32_t blk[LQ_AFR_R * LQ_AFR_BLK][AFF_LANES]; uint32_t base[LQ_AFR_R][AFF_LANES]; uint32_t start[LQ_AFR_R + 1][AFF_LANES]; };   /* blk: per region the read offset, then 59 digit words */
+struct AffSmem { uint32_t blk[LQ_AFR_R * LQ_AFR_BLK][AFF_LANES]; uint32_t start[LQ_AFR_R + 1][AFF_LANES]; };   /* blk: per region window, queue cursor, queue origin, 57 queue words */
 
 __global__ void __launch_bounds__(AFF_THREADS) lq_af_walkf_k(AfArgs a)
 {
@@ -1021,9 +1022,11 @@ __global__ void __launch_bounds__(AFF_THREADS) lq_af_walkf_k(AfArgs a)
         __syncthreads();
         if (tid < nbk) {
             uint32_t run = 0;
-            for (int r = 0; r < LQ_AFR_R; ++r) { S.start[r][tid] = run; S.base[r][tid] = run; run += s_cnt[tid][r]; }
+            for (int r = 0; r < LQ_AFR_R; ++r) {   /* nothing consumed, queues empty (lq_afr_cache_init_host) */
+                S.start[r][tid] = run; S.blk[r * LQ_AFR_BLK][tid] = 0; S.blk[r * LQ_AFR_BLK + 1][tid] = 0; S.blk[r * LQ_AFR_BLK + 2][tid] = run;
+                run += s_cnt[tid][r];
+            }
             S.start[LQ_AFR_R][tid] = run;
-            for (int r = 0; r < LQ_AFR_R; ++r) S.blk[r * LQ_AFR_BLK][tid] = 0;
         }
         __syncthreads();
         const bool walker = wid == 0 && lane < nbk;
@@ -1037,45 +1040,52 @@ __global__ void __launch_bounds__(AFF_THREADS) lq_af_walkf_k(AfArgs a)
             lq_afr_init(&ws, my_start, my_ph); fin = false; my_n = meta[lane].n; my_seq = a.ord + meta[lane].beg;
         }
         for (;;) {
-            /* refill: every region's cached stretch restarts at its next unread position (base += offset, offset = 0) */
+            /* refill (lq_afr_refill_host): every region's queue restarts at its next unread position */
             for (uint32_t e = tid; e < nbk * LQ_AFR_R; e += AFF_THREADS) {
                 const uint32_t w = e % nbk, r = e / nbk;
-                S.base[r][w] += S.blk[r * LQ_AFR_BLK][w];
-                S.blk[r * LQ_AFR_BLK][w] = 0;
+                S.blk[r * LQ_AFR_BLK + 2][w] = lq_afr_next(S.blk[r * LQ_AFR_BLK][w], S.blk[r * LQ_AFR_BLK + 1][w], S.blk[r * LQ_AFR_BLK + 2][w], S.start[r + 1][w]);
             }
             __syncthreads();
-            for (uint32_t e0 = tid; e0 < nbk * LQ_AFR_R * LQ_AFR_WORDS; e0 += 4 * AFF_THREADS) {   /* 8 word loads in flight per thread */
-                uint32_t lo[4], hi[4], sh[4], v[4]; bool fast[4];
+            for (uint32_t e0 = tid; e0 < nbk * LQ_AFR_R * (LQ_AFR_QW + 1); e0 += 4 * AFF_THREADS) {   /* 8 word loads in flight per thread */
+                uint32_t lo[4], hi[4], th[4], sh[4]; bool fast[4];
                 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const uint32_t e = e0 + u * AFF_THREADS;
-                    fast[u] = false; lo[u] = hi[u] = sh[u] = v[u] = 0;
-                    if (e < nbk * LQ_AFR_R * LQ_AFR_WORDS) {
-                        const uint32_t w = e % nbk, rw = e / nbk, r = rw / LQ_AFR_WORDS, j = rw % LQ_AFR_WORDS;
-                        const uint32_t n = meta[w].n, p = S.base[r][w] + 4 * j;
+                    fast[u] = false; lo[u] = hi[u] = th[u] = sh[u] = 0;
+                    if (e < nbk * LQ_AFR_R * (LQ_AFR_QW + 1)) {
+                        const uint32_t w = e % nbk, rw = e / nbk, r = rw / (LQ_AFR_QW + 1), j = rw % (LQ_AFR_QW + 1);
+                        const uint32_t end = S.start[r + 1][w], p = S.blk[r * LQ_AFR_BLK + 2][w] + 7 * j;
                         const uint8_t *dig = a.dig + meta[w].beg;
-                        if (p + 4 <= n) {
+                        if (j < LQ_AFR_QW && p + 7 <= end) {
                             const uint32_t *q = (const uint32_t*)((uintptr_t)(dig + p) & ~(uintptr_t)3);
                             sh[u] = (uint32_t)((uintptr_t)(dig + p) & 3) * 8; fast[u] = true;
-                            lo[u] = __ldg(q); hi[u] = __ldg(q + 1);                    /* the arena is padded: q + 1 stays inside it */
-                        } else {
-                            #pragma unroll
-                            for (int b = 0; b < 4; ++b) if (p + b < n) v[u] |= (uint32_t)dig[p + b] << (8 * b);
+                            lo[u] = __ldg(q); hi[u] = __ldg(q + 1); th[u] = __ldg(q + 2);   /* seven bytes from offset 0..3: three aligned words (the arena is padded) */
                         }
                     }
                 }
                 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const uint32_t e = e0 + u * AFF_THREADS;
-                    if (e < nbk * LQ_AFR_R * LQ_AFR_WORDS) {
-                        const uint32_t w = e % nbk, rw = e / nbk, r = rw / LQ_AFR_WORDS, j = rw % LQ_AFR_WORDS;
-                        S.blk[r * LQ_AFR_BLK + 1 + j][w] = fast[u] ? __funnelshift_r(lo[u], hi[u], sh[u]) : v[u];
+                    if (e < nbk * LQ_AFR_R * (LQ_AFR_QW + 1)) {
+                        const uint32_t w = e % nbk, rw = e / nbk, r = rw / (LQ_AFR_QW + 1), j = rw % (LQ_AFR_QW + 1);
+                        uint32_t v;
+                        if (fast[u]) {   /* seven bytes from an arbitrary address -> seven nibbles under the marker */
+                            const uint32_t b0 = __funnelshift_r(lo[u], hi[u], sh[u]), b1 = __funnelshift_r(hi[u], th[u], sh[u]);
+                            v = (b0 & 15u) | ((b0 >> 4) & 0xf0u) | ((b0 >> 8) & 0xf00u) | ((b0 >> 12) & 0xf000u)
+                              | ((b1 & 15u) << 16) | (((b1 >> 8) & 15u) << 20) | (((b1 >> 16) & 15u) << 24) | (1u << 28);
+                        } else v = lq_afr_queue_word(a.dig + meta[w].beg, S.blk[r * LQ_AFR_BLK + 2][w], S.start[r + 1][w], j);
+                        S.blk[r * LQ_AFR_BLK + 3 + j][w] = v;
                     }
                 }
             }
             __syncthreads();
+            for (uint32_t e = tid; e < nbk * LQ_AFR_R; e += AFF_THREADS) {
+                const uint32_t w = e % nbk, r = e / nbk;
+                S.blk[r * LQ_AFR_BLK][w] = S.blk[r * LQ_AFR_BLK + 3][w]; S.blk[r * LQ_AFR_BLK + 1][w] = 1;
+            }
+            __syncthreads();
             if (wid == 0) {
-                if (!fin) { LqSmemWords mw; mw.base = (uint32_t)__cvta_generic_to_shared(&S.blk[0][lane]); fin = lq_afr_run(&ws, my_n, my_start, mw, AFF_LANES, &S.base[0][lane], AFF_LANES, my_seq, my_ph) != 0; }
+                if (!fin) { LqSmemWords mw; mw.base = (uint32_t)__cvta_generic_to_shared(&S.blk[0][lane]); fin = lq_afr_run(&ws, my_n, my_start, mw, AFF_LANES, my_seq, my_ph) != 0; }
                 const uint32_t alive = __ballot_sync(0xffffffffu, !fin);
                 if (lane == 0) s_alive = alive;
             }
