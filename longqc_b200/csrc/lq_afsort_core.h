@@ -25,6 +25,7 @@
 #define LQ_AFSORT_CORE_H
 
 #include "lq_common.h"
+#define LQ_UNLIKELY(x) __builtin_expect(!!(x), 0)   /* rare blocks out of line: the walk's common path then has no taken branch */
 
 #define LQ_RS_MIN 64
 
@@ -196,7 +197,8 @@ LQ_HD void lq_afp_refill_host(const uint8_t *dig, const uint32_t *start, lq_afp_
     for (j = 0; j < 12; ++j) b[j] = j < LQ_AFP_DIG && S.x + j < n ? dig[S.x + j] : 0;
     S.y = (uint32_t)b[0] | (uint32_t)b[1] << 8 | (uint32_t)b[2] << 16 | (uint32_t)b[3] << 24;
     S.z = (uint32_t)b[4] | (uint32_t)b[5] << 8 | (uint32_t)b[6] << 16 | (uint32_t)b[7] << 24;
-    S.w = (uint32_t)b[8] | (uint32_t)b[9] << 8 | (uint32_t)b[10] << 16 | (uint32_t)LQ_AFP_DIG << 24;
+    /* bit 7 of the count: the cached digits reach the region's end -- it never needs another refill (and never counts down to 0) */
+    S.w = (uint32_t)b[8] | (uint32_t)b[9] << 8 | (uint32_t)b[10] << 16 | (uint32_t)(LQ_AFP_DIG | (S.x + LQ_AFP_DIG >= start[r + 1] ? 0x80u : 0u)) << 24;
     st[r] = S;
 }
 
@@ -209,43 +211,48 @@ LQ_HD void lq_afp_refill_host(const uint8_t *dig, const uint32_t *start, lq_afp_
  * So the sequential part writes ONE BYTE per element (four pick-ups per 32-bit store) and no positions at all; the phase list
  * (when each outer-loop region opened, and where) has at most 256 entries per bucket. */
 typedef struct { uint32_t t, p; } lq_afq_phase;          /* region k became the outer-loop region at pick-up t, its next unread position was p; t = ~0: never */
-typedef struct { uint32_t k, c, step, end_k, acc; } lq_afq_walk;
+typedef struct { uint32_t k, c, step, rem_k, acc; } lq_afq_walk;   /* rem_k: elements of the outer-loop region k still to be picked up */
 
 LQ_HD void lq_afq_init(lq_afq_walk *s, const uint32_t *start, lq_afq_phase *ph /* [256], all t = ~0 on entry */)
 {
     uint32_t k = 0;
     while (k < 256 && start[k + 1] == start[k]) ++k;
-    s->k = k; s->c = k < 256 ? k : 0; s->step = 0; s->acc = 0; s->end_k = k < 256 ? start[k + 1] : 0;
+    s->k = k; s->c = k < 256 ? k : 0; s->step = 0; s->acc = 0; s->rem_k = k < 256 ? start[k + 1] - start[k] : 0;
     if (k < 256) { ph[k].t = 0; ph[k].p = start[k]; }
 }
 
-/* st[r * stride]: packed state of region r as in lq_afp_st (x = next unread position, then up to 11 digits and their number).
- * seq32: the digit stream, four pick-ups per word (little endian).  Returns 1 when all n elements are picked, 0 when region s->c
- * has no cached digit left (refill, call again). */
+/* st[r * stride]: packed state of region r as in lq_afp_st (x = next unread position, then up to 11 digits and their number; bit 7
+ * of the number: the cached digits reach the region's end).  Every region with elements left holds at least one digit when this is
+ * called (the refill tops up every region that is running low).  seq32: the digit stream, four pick-ups per word (little endian).
+ * Returns 1 when all n elements are picked, 0 when a region has just used its last cached digit (refill, call again).
+ * The critical path of a pick-up is ONE 16-byte load: the state of the digit's region is requested as soon as the digit is known,
+ * before the state just read is shifted, stored and checked (a digit naming the region just read takes the shifted copy instead);
+ * "region k complete" is a counter, not a comparison on the freshly loaded state. */
 LQ_HD int lq_afq_run(lq_afq_walk *s, uint32_t n, const uint32_t *start, lq_afp_st *st, uint32_t stride, uint32_t *seq32, lq_afq_phase *ph)
 {
-    uint32_t k = s->k, c = s->c, step = s->step, end_k = s->end_k, acc = s->acc;
-    int done = 1;
+    uint32_t k = s->k, c = s->c, step = s->step, rem_k = s->rem_k, acc = s->acc;
+    uint32_t need = 0;
     if (step < n) {
         lq_afp_st S = st[c * stride];
-        /* one pick-up; J = its byte in the current word of the digit stream (static in the unrolled loop below).  The updated state
-         * is stored BEFORE the state of the digit's region is loaded, so a digit that names the region just read sees the update. */
 #define LQ_AFQ_STEP(J) { \
-            const uint32_t left = S.w >> 24; \
-            if (left == 0) { done = 0; break; } \
             const uint32_t d = S.y & 255u; \
-            S.x += 1; S.y = LQ_FUNNEL_R8(S.y, S.z); S.z = LQ_FUNNEL_R8(S.z, S.w); S.w = ((S.w >> 8) & 0xffffu) | (left - 1) << 24; \
+            lq_afp_st Sn = st[d * stride]; \
+            const uint32_t left = (S.w >> 24) - 1u; \
+            S.x += 1; S.y = LQ_FUNNEL_R8(S.y, S.z); S.z = LQ_FUNNEL_R8(S.z, S.w); S.w = ((S.w >> 8) & 0xffffu) | left << 24; \
             st[c * stride] = S; \
+            need |= (uint32_t)(left == 0u); \
+            rem_k -= (uint32_t)(c == k); \
             acc |= d << (8 * (J)); \
             if ((J) == 3) { seq32[step >> 2] = acc; acc = 0; } \
-            c = d; \
-            S = st[c * stride]; \
-            if (d == k && S.x == end_k) {                         /* region k complete: open the next non-exhausted region */ \
+            if (d == c) Sn = S; \
+            c = d; S = Sn; \
+            if (LQ_UNLIKELY(rem_k == 0u && d == k)) {             /* region k complete: open the next non-exhausted region */ \
                 do { ++k; } while (k < 256 && st[k * stride].x == start[k + 1]); \
-                if (k < 256) { c = k; end_k = start[k + 1]; S = st[c * stride]; ph[k].t = step + 1; ph[k].p = S.x; } \
+                if (k < 256) { c = k; S = st[c * stride]; rem_k = start[k + 1] - S.x; ph[k].t = step + 1; ph[k].p = S.x; } \
                 else { c = 0; S = st[0]; } \
             } \
-            if (++step >= n) break; }
+            ++step; \
+            if (LQ_UNLIKELY(need || step >= n)) break; }
         for (;;) {
             switch (step & 3u) {      /* resume in the middle of a word after a refill */
             case 0: LQ_AFQ_STEP(0)
@@ -256,13 +263,13 @@ LQ_HD int lq_afq_run(lq_afq_walk *s, uint32_t n, const uint32_t *start, lq_afp_s
             /* fall through */
             default: LQ_AFQ_STEP(3)
             }
-            if (!done || step >= n) break;
+            if (need || step >= n) break;
         }
 #undef LQ_AFQ_STEP
         if (step >= n && (step & 3u)) seq32[step >> 2] = acc;     /* the last, partial word */
     }
-    s->k = k; s->c = c; s->step = step; s->end_k = end_k; s->acc = acc;
-    return done;
+    s->k = k; s->c = c; s->step = step; s->rem_k = rem_k; s->acc = acc;
+    return step >= n;
 }
 
 /* ord[t] / slot[t] of every pick-up from the digit stream (host reference of lq_af_place_k); run[256] scratch */
@@ -351,14 +358,14 @@ LQ_HD int lq_afr_run(lq_afr_walk *s, uint32_t n, const uint32_t *start, M mem, u
         uint32_t wn = w >> 4; \
         rem_k -= (c == k); \
         acc |= d << (8 * (J)); \
-        if (wn == 1u) {                                           /* window empty: the next queue word, now */ \
+        if (LQ_UNLIKELY(wn == 1u)) {                              /* window empty: the next queue word, now */ \
             const uint32_t q = mem.ld(ob + stride); \
             wn = mem.ld(ob + (3u + q) * stride); \
             if (wn != 0u) mem.st(ob + stride, q + 1u); else need = 1u; \
         } \
         mem.st(ob, wn); \
         c = d; \
-        if (rem_k == 0u && d == k) {                              /* region k complete: open the next non-exhausted region */ \
+        if (LQ_UNLIKELY(rem_k == 0u && d == k)) {                 /* region k complete: open the next non-exhausted region */ \
             for (;;) { \
                 ++k; \
                 if (k >= LQ_AFR_R) break; \
@@ -371,11 +378,11 @@ LQ_HD int lq_afr_run(lq_afr_walk *s, uint32_t n, const uint32_t *start, M mem, u
     while (step < n && !need) {
         if ((step & 3u) == 0u && step + 4 <= n) {                 /* whole words of the digit stream: static byte lanes */
             LQ_AFR_STEP(0, step)
-            if (need) { step += 1; break; }
+            if (LQ_UNLIKELY(need)) { step += 1; break; }
             LQ_AFR_STEP(1, step + 1)
-            if (need) { step += 2; break; }
+            if (LQ_UNLIKELY(need)) { step += 2; break; }
             LQ_AFR_STEP(2, step + 2)
-            if (need) { step += 3; break; }
+            if (LQ_UNLIKELY(need)) { step += 3; break; }
             LQ_AFR_STEP(3, step + 3)
             seq32[step >> 2] = acc; acc = 0;
             step += 4;

@@ -663,6 +663,7 @@ __device__ __forceinline__ void afb_subbuckets(const AfArgs &a, uint32_t beg, ui
     }
 }
 
+static int g_walk_stats = getenv("LQCOV_WALK_STATS") ? atoi(getenv("LQCOV_WALK_STATS")) : 0;
 /* CTAs per SM working on big buckets at a time: the passes over a bucket re-read it, so the buckets in flight should fit the L2 */
 static unsigned g_afb_ctas = getenv("LQCOV_AFB_CTAS") && atoi(getenv("LQCOV_AFB_CTAS")) > 0 ? (unsigned)atoi(getenv("LQCOV_AFB_CTAS")) : 4u;
 
@@ -941,8 +942,10 @@ __global__ void __launch_bounds__(AFS_THREADS, 1) lq_af_walk3_k(AfArgs a, uint32
                 #pragma unroll
                 for (int u = 0; u < 4; ++u) if (need[u]) {
                     S[u].y = __funnelshift_r(wv[u][0], wv[u][1], sh[u]); S[u].z = __funnelshift_r(wv[u][1], wv[u][2], sh[u]);
-                    S[u].w = (__funnelshift_r(wv[u][2], wv[u][3], sh[u]) & 0x00ffffffu) | (uint32_t)LQ_AFP_DIG << 24;
-                    state[e0 + u * AFS_THREADS] = S[u];
+                    /* bit 7 of the count: the cached digits reach the region's end (lq_afp_refill_host) */
+                    const uint32_t e = e0 + u * AFS_THREADS, end = gs[(e % AFS_WALKERS) * AFS_ROW + e / AFS_WALKERS + 1];
+                    S[u].w = (__funnelshift_r(wv[u][2], wv[u][3], sh[u]) & 0x00ffffffu) | (uint32_t)(LQ_AFP_DIG | (S[u].x + LQ_AFP_DIG >= end ? 0x80u : 0u)) << 24;
+                    state[e] = S[u];
                 }
             }
             __syncthreads();
@@ -1869,6 +1872,19 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         { LqProfScope ps(wlk_name[shift >> 3], st, 2, 0);
           lq_af_walk3_k<<<AFS_GRID, AFS_THREADS, AFS_WALKERS * 4096, st>>>(a, sc->wst.as<uint32_t>());
           lq_af_walkf_k<<<AFF_GRID, AFF_THREADS, sizeof(AffSmem), st>>>(a); }
+        if (g_walk_stats) {   /* LQCOV_WALK_STATS=1: the walks of this level (count, elements, longest) on stderr -- the longest one is the critical path */
+            uint32_t cnt[2] = { 0, 0 };
+            cudaStreamSynchronize(st);
+            cudaMemcpy(&cnt[0], ctr + 9, 4, cudaMemcpyDeviceToHost); cudaMemcpy(&cnt[1], ctr + 52, 4, cudaMemcpyDeviceToHost);
+            const AfBkt *lists[2] = { a.wlist, a.wlist_w };
+            for (int f = 0; f < 2; ++f) {
+                std::vector<AfBkt> h(cnt[f]);
+                if (cnt[f]) cudaMemcpy(h.data(), lists[f], (size_t)cnt[f] * sizeof(AfBkt), cudaMemcpyDeviceToHost);
+                uint64_t tot = 0; uint32_t mx = 0;
+                for (size_t i = 0; i < h.size(); ++i) { const uint32_t n = h[i].end - h[i].beg; tot += n; if (n > mx) mx = n; }
+                if (cnt[f]) fprintf(stderr, "[lqcov] walk stats: shift %d %s walks %u elements %llu longest %u\n", shift, f ? "few-region" : "256-region", cnt[f], (unsigned long long)tot, mx);
+            }
+        }
         { LqProfScope ps(plc_name[shift >> 3], st, 1, 0);
           lq_af_place_k<<<148 * 3, AFB_THREADS, 0, st>>>(a); }
         a.n_elem = (unsigned long long*)(ctr + 64) + (shift >> 3);
