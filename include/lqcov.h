@@ -175,8 +175,9 @@ int  lqcov_sketch(const lqcov_opt_t *o, const lqcov_reads_t *reads, uint32_t rid
 /* seeds of query q against the CURRENT part, before and after the reference-exact sort (lqmap.c:237-238):
  * x/y as the reference lays mm128_t seeds out (y without the tandem flag).  Arrays malloc'ed, n each. */
 int  lqcov_debug_seeds(lqcov_ctx *c, uint32_t q, uint64_t **ux, uint64_t **uy, uint64_t **sx, uint64_t **sy, uint64_t *n);
-/* test switch for the sketch where the rolling kernel is the default (w = 5/10, k <= 15): 1 = the tiled position-parallel kernel,
- * 2 = the 16-bases-per-lane kernel, 0 = default */
+/* test switch for the sketch (w = 5/10, k <= 15): 0 = the defaults (packed-key kernel fed by bulk copies for w = 5, k = 12 / 15,
+ * rolling kernel otherwise), 1 = the tiled position-parallel kernel, 2 = the packed-key kernel fed by plain loads,
+ * 3 = the rolling kernel everywhere */
 void lqcov_debug_sketch_tiled(int on);
 /* index one part WITHOUT mapping (used with lqcov_debug_seeds) */
 int  lqcov_index_part(lqcov_ctx *c, const lqcov_reads_t *part);

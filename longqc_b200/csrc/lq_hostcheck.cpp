@@ -78,57 +78,6 @@ uint64_t lqhc_hash64(uint64_t key, uint64_t mask) { return lq_hash64(key, mask);
 
 } // extern "C"
 
-// the 16-bases-per-lane form (lq_sketch_lane_core.h): every segment that may start from a handed-over state does, the others
-// take the per-position path; *n_inj counts the segments that did
-#include "lq_sketch_lane_core.h"
-namespace {
-struct LaneSink {
-    std::vector<lq_mm128> *v; uint32_t rid; int k;
-    void operator()(uint32_t h, uint32_t p) { lq_mm128 e; e.x = (uint64_t)h << 8 | (uint64_t)k; e.y = (uint64_t)rid << 32 | p; v->push_back(e); }
-};
-template <int W>
-int sketch_lanes(const char *seq, int len, int k, uint32_t rid, lq_mm128 *out, int cap, int *n_inj)
-{
-    std::vector<uint32_t> b2, nm; std::vector<lq_mm128> v; VecSink s; s.v = &v; LaneSink ls; ls.v = &v; ls.rid = rid; ls.k = k;
-    pack_read(seq, len, 0, b2, nm);
-    const int nseg = (len + LQ_RL_SEG - 1) / LQ_RL_SEG;
-    int inj = 0;
-    for (int sg = 0; sg < nseg; ++sg) {
-        const int i0 = sg * LQ_RL_SEG, nb = len - i0 < LQ_RL_SEG ? len - i0 : LQ_RL_SEG;
-        uint32_t cx[3][LQ_RL_SEG], zm[3] = {0, 0, 0}, ok[3] = {0, 0, 0};
-        for (int b = 0; b < 3; ++b) {          // this segment and the two before it
-            const int t = sg - b;
-            if (t < 0 || k > 15) continue;
-            lq_rl_cands(t > 0 ? b2[t - 1] : 0u, b2[t], k, cx[b], &zm[b], &ok[b]);
-        }
-        if (nb < LQ_RL_SEG) ok[0] &= (1u << nb) - 1;
-        if (lq_rl_inject_ok(nm.data(), (uint64_t)i0, i0, nb, ok[1], ok[2], W, k)) {
-            uint32_t wx[W], wp[W];
-            lq_rl_tail<W>(cx[1], zm[1], ok[1], i0 - LQ_RL_SEG, wx, wp);
-            lq_rl_steady<W>(cx[0], 1, zm[0], ok[0], i0, wx, wp, i0 + nb == len, ls);
-            ++inj;
-        } else {
-            for (int i = i0; i < i0 + nb; ++i) lq_sketch_at(b2.data(), nm.data(), 0, len, W, k, rid, i, s);
-        }
-    }
-    if (n_inj) *n_inj = inj;
-    int n = (int)v.size();
-    for (int i = 0; i < n && i < cap; ++i) out[i] = v[i];
-    return n;
-}
-}
-extern "C" int lqhc_sketch_lanes(const char *seq, int len, int w, int k, uint32_t rid, int *n_inj, lq_mm128 *out, int cap)
-{
-    switch (w) {
-    case 1: return sketch_lanes<1>(seq, len, k, rid, out, cap, n_inj);
-    case 3: return sketch_lanes<3>(seq, len, k, rid, out, cap, n_inj);
-    case 5: return sketch_lanes<5>(seq, len, k, rid, out, cap, n_inj);
-    case 7: return sketch_lanes<7>(seq, len, k, rid, out, cap, n_inj);
-    case 10: return sketch_lanes<10>(seq, len, k, rid, out, cap, n_inj);
-    case 16: return sketch_lanes<16>(seq, len, k, rid, out, cap, n_inj);
-    }
-    return -1;
-}
 
 
 // ---------------------------------------------------------------- seed sort (lq_afsort_core.h)
@@ -355,4 +304,59 @@ extern "C" long lqhc_mmi_load_count(const char *path, long *n_rec, long *n_seq)
     while ((r = lq_mmi_load_part(fp, &mp)) == 1) { ++parts; *n_rec += (long)mp.key.size(); *n_seq += mp.n_seq; }
     fclose(fp);
     return r < 0 ? -1 : parts;
+}
+
+// the 64-bases-per-thread packed-key form (lq_sketch_pk_core.h): every segment it accepts comes from it, the others from the
+// general state machine; *n_lean counts the segments it accepted.  The words before a read's first segment are garbage on purpose.
+#include "lq_sketch_pk_core.h"
+namespace {
+template <int W, int K>
+int sketch_pk(const char *seq, int len, uint32_t rid, lq_mm128 *out, int cap, int *n_lean)
+{
+    typedef lq_pk_tr<(K > 12)> T;
+    std::vector<uint32_t> b2, nm; std::vector<lq_mm128> v; VecSink s; s.v = &v;
+    pack_read(seq, len, 0, b2, nm);
+    b2.resize(b2.size() + 8, 0u); nm.resize(nm.size() + 4, 0xffffffffu);
+    int lean = 0;
+    for (int i0 = 0; i0 < len; i0 += LQ_PK_SEG) {
+        const int nseg = len - i0 < LQ_PK_SEG ? len - i0 : LQ_PK_SEG;
+        const bool is_last = i0 + nseg == len;
+        uint32_t lw8[8], nw4[4];
+        for (int j = 0; j < 8; ++j) lw8[j] = i0 ? b2[(i0 >> 4) - 4 + j] : (j < 4 ? 0xdeadbeefu * (j + 1) : b2[j - 4]);
+        for (int j = 0; j < 4; ++j) nw4[j] = i0 ? nm[(i0 >> 5) - 2 + j] : (j < 2 ? 0x5a5a5a5au : nm[j - 2]);
+        struct KeySink {
+            typedef size_t mark_t;
+            std::vector<lq_mm128> *v; uint32_t rid; int i0;
+            void push(typename T::key kk) { lq_mm128 e; e.x = (uint64_t)T::hash(kk) << 8 | (uint64_t)K; e.y = (uint64_t)rid << 32 | lq_pk_p2z(i0, T::code(kk)); v->push_back(e); }
+            void put(typename T::key kk, bool yes) { if (yes) push(kk); }
+            int room() const { return 1 << 20; }
+            mark_t mark() const { return v->size(); }
+            void rewind(mark_t m) { v->resize(m); }
+        } ks; ks.v = &v; ks.rid = rid; ks.i0 = i0;
+        const size_t mark = v.size();
+        if (lq_pk_segment<W, K>(lw8, nw4, i0, nseg, is_last, ks) == 0) ++lean;
+        else {
+            v.resize(mark);
+            lq_sketch_replay(b2.data(), nm.data(), 0, len, W, K, rid, 0, 0, 1, i0 + nseg - 1, i0, is_last ? len : i0 + nseg - 1, (int*)0, s);
+        }
+    }
+    if (n_lean) *n_lean = lean;
+    int n = (int)v.size();
+    for (int i = 0; i < n && i < cap; ++i) out[i] = v[i];
+    return n;
+}
+}
+extern "C" int lqhc_sketch_pk(const char *seq, int len, int w, int k, uint32_t rid, int *n_lean, lq_mm128 *out, int cap)
+{
+    switch (w * 100 + k) {
+    case 512: return sketch_pk<5, 12>(seq, len, rid, out, cap, n_lean);
+    case 515: return sketch_pk<5, 15>(seq, len, rid, out, cap, n_lean);
+    case 511: return sketch_pk<5, 11>(seq, len, rid, out, cap, n_lean);
+    case 1015: return sketch_pk<10, 15>(seq, len, rid, out, cap, n_lean);
+    case 1012: return sketch_pk<10, 12>(seq, len, rid, out, cap, n_lean);
+    case 308: return sketch_pk<3, 8>(seq, len, rid, out, cap, n_lean);
+    case 204: return sketch_pk<2, 4>(seq, len, rid, out, cap, n_lean);
+    case 713: return sketch_pk<7, 13>(seq, len, rid, out, cap, n_lean);
+    }
+    return -1;
 }

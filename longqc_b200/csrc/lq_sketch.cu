@@ -17,7 +17,7 @@
  */
 #include "lq_cuda.cuh"
 #include "lq_sketch_core.h"
-#include "lq_sketch_lane_core.h"
+#include "lq_sketch_pk_core.h"
 #include "lq_device.h"
 
 #define SK_THREADS 256
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
 #define RK_CAP 32
 #define RK_TILE (RK_SEG * RK_THREADS)
 
-template <int W, int MODE /* 0: buffer in smem, 1: write directly at `wat` */, int THREADS = RK_THREADS, int CAP = RK_CAP /* staging geometry of the calling kernel */>
+template <int W, int MODE /* 0: buffer in smem, 1: write directly at `wat` */, int THREADS = RK_THREADS, int CAP = RK_CAP /* staging geometry of the calling kernel */, bool INL = false /* the replay inline: no call in the kernel */>
 __device__ __forceinline__ int rk_scan(const SkArgs &a, uint32_t rd, uint64_t g0, int L, int i0, int i1 /* segment [i0,i1) */,
                                        uint2 *s_rec, int tid, uint64_t wat)
 {
@@ -405,7 +405,8 @@ __device__ __forceinline__ int rk_scan(const SkArgs &a, uint32_t rd, uint64_t g0
         const bool use_slow = out && !cert;
         if (i == i1 - 1) last_slow = use_slow;
         if (use_slow) {                    /* not certified yet: this base's records come from the bounded replay */
-            sk_slow(a.b2, a.nm, g0, L, w, k, rid, i, &sbuf);
+            if (INL) { sbuf.n = 0; lq_sketch_slow_at(a.b2, a.nm, g0, L, w, k, rid, i, sbuf); }
+            else sk_slow(a.b2, a.nm, g0, L, w, k, rid, i, &sbuf);
             for (int j = 0; j < sbuf.n; ++j) RK_EMIT((uint32_t)(sbuf.x[j] >> 8), (uint32_t)sbuf.y[j]);
         }
         uint32_t cx = MAXH, cp = MAXH;
@@ -463,33 +464,12 @@ __device__ __forceinline__ int rk_scan(const SkArgs &a, uint32_t rd, uint64_t g0
     return n;
 }
 
-template <int W>
-__global__ void __launch_bounds__(RK_THREADS) lq_sketch_roll_k(SkArgs a)
+/* decoupled look-back over the tiles (called by warp 0 of the CTA): publishes this tile's record count, returns through *s_base
+ * the number of records before it (those of the launches before this one included) */
+__device__ __forceinline__ void sk_tile_base(const SkArgs &a, const uint32_t tile, const uint64_t tot, const int tid, uint64_t *s_base_p)
 {
-    __shared__ uint2 s_rec[RK_CAP * RK_THREADS];       /* 32 KB */
-    __shared__ uint64_t scan_sm[33];
-    __shared__ uint32_t s_tile; __shared__ uint64_t s_base; __shared__ int s_over;
-    const int tid = threadIdx.x;
-    if (tid == 0) { s_tile = atomicAdd(a.ticket, 1u); s_over = 0; }
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint64_t g = a.g_begin + ((uint64_t)tile * RK_THREADS + tid) * RK_SEG;   /* global base index of the segment */
-    const uint64_t slot = g >> 7;
-    uint32_t rd = 0; uint64_t g0 = 0; int L = 0, i0 = 0, i1 = 0;
-    if (slot < a.n_slots) {
-        rd = a.slot_read[slot];
-        const uint64_t s0 = a.slot0[rd];
-        L = (int)a.len[rd]; g0 = s0 * LQ_SLOT;
-        i0 = (int)(slot - s0) * LQ_SLOT + (int)(g & 127);
-        i1 = i0 + RK_SEG < L ? i0 + RK_SEG : L;
-    }
-    int n = 0;
-    if (i0 < i1) n = rk_scan<W, 0>(a, rd, g0, L, i0, i1, s_rec, tid, 0);
-    if (n > RK_CAP) s_over = 1;
-    uint64_t tot;
-    const uint64_t ex = lq_block_excl_scan((uint64_t)n, scan_sm, &tot);
-    /* decoupled look-back (warp 0) */
-    if (tid < 32) {
+    uint64_t &s_base = *s_base_p;
+    {
         const unsigned long long FLAG_AGG = 1ULL << 62, FLAG_PRE = 2ULL << 62, VMASK = (1ULL << 62) - 1;
         uint64_t base = 0;
         if (tile == 0) { if (tid == 0) atomicExch(&a.state[0], FLAG_PRE | tot); }
@@ -520,6 +500,34 @@ __global__ void __launch_bounds__(RK_THREADS) lq_sketch_roll_k(SkArgs a)
             if (a.base_out && tile == gridDim.x - 1) *a.base_out = cb + base + tot;
         }
     }
+}
+
+template <int W>
+__global__ void __launch_bounds__(RK_THREADS) lq_sketch_roll_k(SkArgs a)
+{
+    __shared__ uint2 s_rec[RK_CAP * RK_THREADS];       /* 32 KB */
+    __shared__ uint64_t scan_sm[33];
+    __shared__ uint32_t s_tile; __shared__ uint64_t s_base; __shared__ int s_over;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_tile = atomicAdd(a.ticket, 1u); s_over = 0; }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t g = a.g_begin + ((uint64_t)tile * RK_THREADS + tid) * RK_SEG;   /* global base index of the segment */
+    const uint64_t slot = g >> 7;
+    uint32_t rd = 0; uint64_t g0 = 0; int L = 0, i0 = 0, i1 = 0;
+    if (slot < a.n_slots) {
+        rd = a.slot_read[slot];
+        const uint64_t s0 = a.slot0[rd];
+        L = (int)a.len[rd]; g0 = s0 * LQ_SLOT;
+        i0 = (int)(slot - s0) * LQ_SLOT + (int)(g & 127);
+        i1 = i0 + RK_SEG < L ? i0 + RK_SEG : L;
+    }
+    int n = 0;
+    if (i0 < i1) n = rk_scan<W, 0>(a, rd, g0, L, i0, i1, s_rec, tid, 0);
+    if (n > RK_CAP) s_over = 1;
+    uint64_t tot;
+    const uint64_t ex = lq_block_excl_scan((uint64_t)n, scan_sm, &tot);
+    if (tid < 32) sk_tile_base(a, tile, tot, tid, &s_base);   /* decoupled look-back (warp 0) */
     __syncthreads();
     const uint64_t at = s_base + ex;
     if (s_base + tot > a.cap || n == 0) return;
@@ -528,124 +536,166 @@ __global__ void __launch_bounds__(RK_THREADS) lq_sketch_roll_k(SkArgs a)
     } else rk_scan<W, 1>(a, rd, g0, L, i0, i1, s_rec, tid, at);   /* low-complexity tile: scan again, writing in place */
 }
 
-/* ------------------------------------------------------------------ K1, lane form (w = 5 or 10, k <= 15): 16 bases per thread
+/* ------------------------------------------------------------------ K1, packed-key form (w = 5, k <= 15): the default
  *
- * lq_sketch_lane_core.h: a thread owns one packed word, computes the candidates of its 16 bases, hands the tail of them to the
- * next lane by shuffle and starts the reference's steady state from the tail it receives -- no warm-up.  Lanes 0 and 1 of a warp
- * are halo lanes (they redo the two segments before the warp's first one and emit nothing), so a warp emits 30 segments = 480
- * bases and a CTA of 4 warps 1920.  A segment that may not start from a handed-over state (read start, ambiguous bases,
- * palindromic runs) runs rk_scan with its certified warm-up.  Output staging, look-back and overflow handling as in
- * lq_sketch_roll_k. */
-#define RL_THREADS 512             /* 16 warps: 7680 bases per tile, so that the look-back is paid once per ~2600 records */
-#define RL_CAP 16                  /* staged records per thread (16 bases emit ~5); more: the tile is scanned again writing in place */
-#define RL_SMEM (RL_CAP * RL_THREADS * 8 + LQ_RL_SEG * RL_THREADS * 4)
-#define RL_EMIT 30
-#define RL_TILE_SEGS (RL_EMIT * (RL_THREADS / 32))
+ * lq_sketch_pk_core.h: a thread scans 64 bases of a read out of two 16-byte shared-memory loads, its candidates are single
+ * integers (hash | inverted position), the window minimum two 3-input minima, the look-back 25-28 bases of which 8 are hashed.
+ * The tile's packed words (64 slots and the one before: 2 KB + 1 KB) are brought into shared memory by two bulk asynchronous
+ * copies (cp.async.bulk, completion on an mbarrier) issued by one thread while the others fetch their read's geometry.
+ * Records wait in shared memory as keys, a row per thread (odd row stride: no bank conflicts when the lanes of a warp write
+ * their rows, none when the warp later reads ONE row); after the look-back has given the tile its place, each warp writes the
+ * rows of its threads one after the other, lanes along the row: runs of ~21 consecutive records per store.
+ * Segments the form declines (ambiguous bases, palindrome-rich look-back, equal k-mers inside a read's first window) run
+ * rk_scan into a small pool; a tile with more of those than the pool holds, or with a row that overflows, runs rk_scan
+ * everywhere, writing in place. */
+#define PK_CAP 48                        /* records a thread can stage (64 bases write ~21) */
+#define PK_STRIDE (PK_CAP + 1)
+#define PK_FB 6
+#define PK_SLOTS (RK_TILE / LQ_SLOT)     /* 64 slots per tile */
+#define PK_OFF_NM ((PK_SLOTS + 1) * LQ_SLOT_W2 * 4)
+#define PK_OFF_STAGE (PK_OFF_NM + (PK_SLOTS + 1) * LQ_SLOT_WN * 4)
+#define PK_SMEM(KEYBYTES) (PK_OFF_STAGE + RK_THREADS * PK_STRIDE * (KEYBYTES) + PK_FB * PK_CAP * 8)
 
-struct RlStage {
-    uint2 *rec; int tid; int n;
-    __device__ __forceinline__ void operator()(uint32_t h, uint32_t p) { if (n < RL_CAP) rec[n * RL_THREADS + tid] = make_uint2(h, p); ++n; }
-};
-struct RlWrite {
-    uint32_t *key; uint64_t *yy; uint64_t at; uint64_t ridhi;
-    __device__ __forceinline__ void operator()(uint32_t h, uint32_t p) { key[at] = h; yy[at] = ridhi | p; ++at; }
-};
-
-template <int W>
-__global__ void __launch_bounds__(RL_THREADS) lq_sketch_lane_k(SkArgs a)
+__device__ __forceinline__ uint32_t lq_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lq_mbar_init(uint32_t bar, uint32_t count)
 {
-    extern __shared__ __align__(16) uint8_t rl_smem[];
-    uint2 *s_rec = (uint2*)rl_smem;                                   /* RL_CAP x RL_THREADS staged records (64 KB) */
-    uint32_t *s_cx = (uint32_t*)(s_rec + RL_CAP * RL_THREADS);        /* candidate j of thread t at [j * RL_THREADS + t] (32 KB) */
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void lq_mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+/* global -> shared bulk copy (TMA engine, no tensor map): 16-byte aligned on both sides, bytes a multiple of 16 */
+__device__ __forceinline__ void lq_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t lq_mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+
+/* a thread's row of staged keys, addressed in the shared window (32-bit arithmetic): put() is the unrolled blocks'
+ * store-always / keep-if, push() checks */
+__device__ __forceinline__ void lq_sts(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void lq_sts(uint32_t addr, uint64_t v) { asm volatile("st.shared.b64 [%0], %1;" :: "r"(addr), "l"(v) : "memory"); }
+template <class KEY> struct PkStage {
+    typedef uint32_t mark_t;
+    uint32_t w, row;                   /* shared-window byte addresses */
+    __device__ __forceinline__ void put(KEY kk, bool yes) { lq_sts(w, kk); w += yes ? (uint32_t)sizeof(KEY) : 0u; }
+    __device__ __forceinline__ void push(KEY kk) { if (w - row < PK_CAP * sizeof(KEY)) lq_sts(w, kk); w += (uint32_t)sizeof(KEY); }
+    __device__ __forceinline__ int count() const { return (int)((w - row) / (uint32_t)sizeof(KEY)); }
+    __device__ __forceinline__ int room() const { return PK_CAP - count(); }
+    __device__ __forceinline__ mark_t mark() const { return w; }
+    __device__ __forceinline__ void rewind(mark_t m) { w = m; }
+};
+/* the general state machine for one segment (inline, replay included: a call in this kernel costs the common path spills) */
+template <int W>
+__device__ __forceinline__ int pk_general(const SkArgs &a, uint32_t rd, uint64_t g0, int L, int i0, int i1, uint2 *rec)
+{
+    return rk_scan<W, 0, 1, PK_CAP, true>(a, rd, g0, L, i0, i1, rec, 0, 0);
+}
+template <int W>
+__device__ __forceinline__ void pk_general_inplace(const SkArgs &a, uint32_t rd, uint64_t g0, int L, int i0, int i1, uint64_t at)
+{
+    rk_scan<W, 1, RK_THREADS, RK_CAP, true>(a, rd, g0, L, i0, i1, (uint2*)0, 0, at);
+}
+
+extern __shared__ __align__(16) unsigned char pk_smem[];
+
+template <int W, int K>
+__global__ void __launch_bounds__(RK_THREADS) lq_sketch_pk_k(SkArgs a, int use_bulk)
+{
+    typedef lq_pk_tr<(K > 12)> T;
+    typedef typename T::key key;
+    uint32_t *s_b2 = (uint32_t*)pk_smem;                                    /* the slot before the tile, then the tile */
+    uint32_t *s_nm = (uint32_t*)(pk_smem + PK_OFF_NM);
+    key *s_stage = (key*)(pk_smem + PK_OFF_STAGE);
+    uint2 *s_fb = (uint2*)(pk_smem + PK_OFF_STAGE + RK_THREADS * PK_STRIDE * sizeof(key));
+    __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint64_t scan_sm[33];
-    __shared__ uint32_t s_tile; __shared__ uint64_t s_base; __shared__ int s_over;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) { s_tile = atomicAdd(a.ticket, 1u); s_over = 0; }
+    __shared__ uint32_t s_tile, s_nfb; __shared__ uint64_t s_base; __shared__ int s_over;
+    const int tid = threadIdx.x;
+    const uint32_t bar = lq_smem_u32(&s_bar);
+    if (tid == 0) { s_tile = atomicAdd(a.ticket, 1u); s_over = 0; s_nfb = 0; if (use_bulk) lq_mbar_init(bar, 1); }
     __syncthreads();
     const uint32_t tile = s_tile;
-    /* this lane's segment (index in units of 16 bases of the packed stream; negative: before the data) */
-    const int64_t seg = ((int64_t)tile * (RL_THREADS / 32) + wid) * RL_EMIT + (lane - 2);
-    const bool halo = lane < 2;
-    bool live = seg >= 0 && (uint64_t)(seg >> 3) < a.n_slots;
-    uint32_t rd = 0; uint64_t g0 = 0, g = 0; int L = 0, i0 = 0, i1 = 0;
-    if (live) {
-        g = (uint64_t)seg * LQ_RL_SEG;
-        const uint64_t slot = g >> 7;
+    {
+        const uint64_t t0 = (a.g_begin >> 7) + (uint64_t)tile * PK_SLOTS;              /* first slot of the tile */
+        const uint64_t c0 = t0 ? t0 - 1 : 0, c1 = t0 + PK_SLOTS < a.n_slots ? t0 + PK_SLOTS : a.n_slots;
+        const uint32_t off = t0 ? 0u : 1u, ns = (uint32_t)(c1 - c0);                    /* slots copied, and where the first one lands */
+        if (use_bulk) {
+            if (tid == 0) {
+                lq_mbar_expect_tx(bar, ns * (LQ_SLOT_W2 + LQ_SLOT_WN) * 4);
+                lq_bulk_g2s(lq_smem_u32(s_b2 + off * LQ_SLOT_W2), a.b2 + c0 * LQ_SLOT_W2, ns * LQ_SLOT_W2 * 4, bar);
+                lq_bulk_g2s(lq_smem_u32(s_nm + off * LQ_SLOT_WN), a.nm + c0 * LQ_SLOT_WN, ns * LQ_SLOT_WN * 4, bar);
+            }
+        } else {
+            const uint4 *gb = (const uint4*)(a.b2 + c0 * LQ_SLOT_W2), *gn = (const uint4*)(a.nm + c0 * LQ_SLOT_WN);
+            uint4 *sb = (uint4*)(s_b2 + off * LQ_SLOT_W2), *sn = (uint4*)(s_nm + off * LQ_SLOT_WN);
+            for (uint32_t i = tid; i < ns * 2; i += RK_THREADS) sb[i] = gb[i];
+            for (uint32_t i = tid; i < ns; i += RK_THREADS) sn[i] = gn[i];
+        }
+    }
+    const uint64_t g = a.g_begin + ((uint64_t)tile * RK_THREADS + tid) * RK_SEG;   /* global base index of the segment */
+    const uint64_t slot = g >> 7;
+    uint32_t rd = 0; uint64_t g0 = 0; int L = 0, i0 = 0, i1 = 0;
+    if (slot < a.n_slots) {
         rd = a.slot_read[slot];
         const uint64_t s0 = a.slot0[rd];
         L = (int)a.len[rd]; g0 = s0 * LQ_SLOT;
         i0 = (int)(slot - s0) * LQ_SLOT + (int)(g & 127);
-        i1 = i0 + LQ_RL_SEG < L ? i0 + LQ_RL_SEG : L;
-        if (i0 >= L) live = false;                     /* padding after the read's last base */
+        i1 = i0 + RK_SEG < L ? i0 + RK_SEG : L;
     }
-    /* candidates of the segment, the tail for the next lane, the tail of the previous one */
-    uint32_t cx[LQ_RL_SEG], zmask = 0, okmask = 0, tx[W], tp[W];
-    if (live) {
-        lq_rl_cands(seg > 0 ? a.b2[seg - 1] : 0u, a.b2[seg], a.k, cx, &zmask, &okmask);
-        if (i1 - i0 < LQ_RL_SEG) okmask &= (1u << (i1 - i0)) - 1;
-    } else {
-        #pragma unroll
-        for (int j = 0; j < LQ_RL_SEG; ++j) cx[j] = 0;
-    }
-    lq_rl_tail<W>(cx, zmask, okmask, i0, tx, tp);
-    #pragma unroll
-    for (int j = 0; j < LQ_RL_SEG; ++j) s_cx[j * RL_THREADS + tid] = cx[j];   /* read back by this thread only */
-    const uint32_t ok1 = __shfl_up_sync(0xffffffffu, okmask, 1), ok2 = __shfl_up_sync(0xffffffffu, okmask, 2);
-    uint32_t wx[W], wp[W];
-    #pragma unroll
-    for (int t = 0; t < W; ++t) { wx[t] = __shfl_up_sync(0xffffffffu, tx[t], 1); wp[t] = __shfl_up_sync(0xffffffffu, tp[t], 1); }
-    const bool emit = live && !halo;
-    const bool inj = emit && lq_rl_inject_ok(a.nm, g, i0, i1 - i0, ok1, ok2, W, a.k);
-    int n = 0;
-    if (inj) {
-        RlStage st; st.rec = s_rec; st.tid = tid; st.n = 0;
-        uint32_t rx[W], rp[W];                          /* the ring is consumed: keep the received tail for a possible second run */
-        #pragma unroll
-        for (int t = 0; t < W; ++t) { rx[t] = wx[t]; rp[t] = wp[t]; }
-        lq_rl_steady<W>(s_cx + tid, RL_THREADS, zmask, okmask, i0, rx, rp, i1 == L, st);
-        n = st.n;
-    } else if (emit) n = rk_scan<W, 0, RL_THREADS, RL_CAP>(a, rd, g0, L, i0, i1, s_rec, tid, 0);
-    if (n > RL_CAP) s_over = 1;
-    uint64_t tot;
-    const uint64_t ex = lq_block_excl_scan((uint64_t)n, scan_sm, &tot);
-    /* decoupled look-back (warp 0) */
-    if (tid < 32) {
-        const unsigned long long FLAG_AGG = 1ULL << 62, FLAG_PRE = 2ULL << 62, VMASK = (1ULL << 62) - 1;
-        uint64_t base = 0;
-        if (tile == 0) { if (tid == 0) atomicExch(&a.state[0], FLAG_PRE | tot); }
+    if (use_bulk) {
+        uint32_t spins = 0;
+        while (!lq_mbar_try_wait(bar, 0)) { if (++spins > (1u << 22)) { atomicOr(a.err, 2u); break; } }
+    } else __syncthreads();
+    int n = 0, fbi = -1;
+    if (i0 < i1) {
+        PkStage<key> sink; sink.row = sink.w = lq_smem_u32(s_stage + tid * PK_STRIDE);
+        const int r = lq_pk_segment<W, K>(s_b2 + 4 + tid * 4, s_nm + 2 + tid * 2, i0, i1 - i0, i1 == L, sink);
+        if (r == 0) n = sink.count();
         else {
-            if (tid == 0) atomicExch(&a.state[tile], FLAG_AGG | tot);
-            int64_t hi = (int64_t)tile - 1; uint32_t spins = 0;
-            for (;;) {
-                const int64_t j = hi - tid;
-                unsigned long long sv = FLAG_PRE;
-                if (j >= 0) sv = *(volatile unsigned long long*)&a.state[j];
-                const uint32_t ready = __ballot_sync(0xffffffffu, (sv >> 62) != 0);
-                const uint32_t pre = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
-                const int stop = pre ? __ffs(pre) - 1 : 31;
-                const uint32_t need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1);
-                if ((ready & need) != need) { __nanosleep(64); if (++spins > (1u << 24)) { if (tid == 0) atomicOr(a.err, 1u); break; } continue; }
-                uint64_t v = (tid <= stop) ? (sv & VMASK) : 0;
-                #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                base += v;
-                if (pre) break;
-                hi -= 32;
-            }
-            if (tid == 0) atomicExch(&a.state[tile], FLAG_PRE | (base + tot));
+            fbi = (int)atomicAdd(&s_nfb, 1u);
+            if (fbi >= PK_FB || r == 2) s_over = 1;
         }
-        if (tid == 0) s_base = base;
     }
     __syncthreads();
+    if (s_nfb) {                                              /* rare: some segments of the tile take the general state machine */
+        if (fbi >= 0) {
+            n = pk_general<W>(a, rd, g0, L, i0, i1, s_fb + (fbi < PK_FB ? fbi : 0) * PK_CAP);   /* past the pool: only the count matters */
+            if (n > PK_CAP) s_over = 1;
+        }
+    }
+    uint64_t tot;
+    const uint64_t ex = lq_block_excl_scan((uint64_t)n, scan_sm, &tot);
+    if (tid < 32) sk_tile_base(a, tile, tot, tid, &s_base);   /* decoupled look-back (warp 0) */
+    __syncthreads();
+    if (s_base + tot > a.cap) return;
     const uint64_t at = s_base + ex;
-    if (s_base + tot > a.cap || n == 0) return;
-    const uint64_t ridhi = (uint64_t)(a.rid_base + rd) << 32;
-    if (!s_over) {
-        for (int j = 0; j < n; ++j) { const uint2 r = s_rec[j * RL_THREADS + tid]; a.out_key[at + j] = r.x; a.out_y[at + j] = ridhi | r.y; }
-    } else if (inj) {                                    /* low-complexity tile: scan again, writing in place */
-        RlWrite wr; wr.key = a.out_key; wr.yy = a.out_y; wr.at = at; wr.ridhi = ridhi;
-        lq_rl_steady<W>(s_cx + tid, RL_THREADS, zmask, okmask, i0, wx, wp, i1 == L, wr);
-    } else rk_scan<W, 1, RL_THREADS, RL_CAP>(a, rd, g0, L, i0, i1, s_rec, tid, at);
+    if (s_over) { if (n) pk_general_inplace<W>(a, rd, g0, L, i0, i1, at); return; }   /* low-complexity tile */
+    const uint32_t lane = tid & 31, wb = tid & ~31u;
+    const uint32_t rid = a.rid_base + rd, t127 = (uint32_t)(2 * i0 + 127);
+    #pragma unroll 1
+    for (int t = 0; t < 32; ++t) {
+        const int nt = __shfl_sync(0xffffffffu, n, t);
+        if (nt == 0) continue;
+        const uint64_t at_t = __shfl_sync(0xffffffffu, at, t);
+        const uint32_t rid_t = __shfl_sync(0xffffffffu, rid, t), t127_t = __shfl_sync(0xffffffffu, t127, t);
+        const int fb_t = __shfl_sync(0xffffffffu, fbi, t);
+        for (int j = lane; j < nt; j += 32) {
+            uint32_t h, p;
+            if (fb_t < 0) { const key kk = s_stage[(wb + t) * PK_STRIDE + j]; h = T::hash(kk); p = t127_t - T::code(kk); }
+            else { const uint2 r = s_fb[fb_t * PK_CAP + j]; h = r.x; p = r.y; }
+            a.out_key[at_t + j] = h; a.out_y[at_t + j] = (uint64_t)rid_t << 32 | p;
+        }
+    }
 }
 
 /* ------------------------------------------------------------------ HPC sketch: one thread per read (spike-in run, reference sketch.c:93-104) */
@@ -690,11 +740,20 @@ __global__ void lq_read_first_k(const uint64_t *__restrict__ y, uint64_t n, uint
 
 /* test switch: force the tiled position-parallel kernel even where the rolling kernel applies (LQCOV_SKETCH_TILED=1) */
 static int g_sketch_tiled = getenv("LQCOV_SKETCH_TILED") ? atoi(getenv("LQCOV_SKETCH_TILED")) : 0;
-/* on = 1: tiled kernel; on = 2: lane kernel (16 bases per thread, lq_sketch_lane_core.h); 0: the default (rolling kernel where it
- * applies).  The lane kernel is exact and tested, but measured slower on B200 (14.9 ms vs 12.0 ms for 840 Mbases): with 16 bases
- * per thread the dependent slot -> read -> length loads and the per-tile look-back are paid four times as often. */
-static int g_sketch_lanes = getenv("LQCOV_SKETCH_LANES") ? atoi(getenv("LQCOV_SKETCH_LANES")) : 0;
-extern "C" void lqcov_debug_sketch_tiled(int on) { g_sketch_tiled = on == 1; g_sketch_lanes = on == 2; }
+/* LQCOV_SKETCH_PK: 1 (default) packed-key kernel fed by bulk asynchronous copies, 2 the same fed by plain loads, 0 the rolling kernel */
+static int g_sketch_pk = getenv("LQCOV_SKETCH_PK") ? atoi(getenv("LQCOV_SKETCH_PK")) : 1;
+/* test switch: 0 the defaults; 1 tiled kernel; 2 packed-key kernel fed by plain loads; 3 rolling kernel where the packed-key one is the default */
+extern "C" void lqcov_debug_sketch_tiled(int on) { g_sketch_tiled = on == 1; g_sketch_pk = on == 2 ? 2 : on == 3 ? 0 : 1; }
+/* the 64-bases-per-thread kernels share the tile geometry (RK_TILE bases per CTA) */
+static void sk_launch_seg64(const SkArgs &a, unsigned nblk, cudaStream_t st)
+{
+    static int once = (cudaFuncSetAttribute(lq_sketch_pk_k<5, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM(8)), 0);
+    (void)once;
+    if (a.w == 5 && a.k == 12 && g_sketch_pk) lq_sketch_pk_k<5, 12><<<nblk, RK_THREADS, PK_SMEM(4), st>>>(a, g_sketch_pk == 1);          /* LongQC's overlap runs */
+    else if (a.w == 5 && a.k == 15 && g_sketch_pk) lq_sketch_pk_k<5, 15><<<nblk, RK_THREADS, PK_SMEM(8), st>>>(a, g_sketch_pk == 1);     /* --fast */
+    else if (a.w == 5) lq_sketch_roll_k<5><<<nblk, RK_THREADS, 0, st>>>(a);
+    else lq_sketch_roll_k<10><<<nblk, RK_THREADS, 0, st>>>(a);
+}
 
 int lq_reads_upload(LqReadsDev *d, const uint8_t *h_seq, const uint64_t *h_off, uint32_t n_reads, int seq_on_device, int sdust_tbl, cudaStream_t st)
 {
@@ -756,7 +815,7 @@ static int g_pipeline = getenv("LQCOV_NO_PIPELINE") ? 0 : 1;
 int lq_upload_sketch_pipelined(LqReadsDev *d, const uint8_t *h_seq, const uint64_t *h_off, uint32_t n_reads, int w, int k, int is_hpc, uint32_t rid_base,
                                LqMinimizers *out, LqDevBuf &ws, cudaStream_t st)
 {
-    const bool roll = !is_hpc && (w == 5 || w == 10) && k <= 15 && !g_sketch_tiled && !g_sketch_lanes;
+    const bool roll = !is_hpc && (w == 5 || w == 10) && k <= 15 && !g_sketch_tiled;
     if (!g_pipeline || !roll || n_reads == 0 || h_off[n_reads] - h_off[0] < 2 * PL_CHUNK) return 1;
     static cudaStream_t st_copy = 0;
     if (!st_copy) LQ_CUDA_OK(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
@@ -828,7 +887,7 @@ int lq_upload_sketch_pipelined(LqReadsDev *d, const uint8_t *h_seq, const uint64
         a.state = state + soff[c]; a.ticket = (uint32_t*)(a.state + nblk); a.err = a.ticket + 1;
         a.base_in = totals + c; a.base_out = totals + c + 1;
         { LqProfScope ps("sketch", st, 1, (s1 - s0) * (LQ_SLOT_W2 + LQ_SLOT_WN) * 4 + (uint64_t)((double)bases * 2.0 / (w + 1)) * 12);
-          if (w == 5) lq_sketch_roll_k<5><<<nblk, RK_THREADS, 0, st>>>(a); else lq_sketch_roll_k<10><<<nblk, RK_THREADS, 0, st>>>(a); }
+          sk_launch_seg64(a, nblk, st); }
         LQ_CUDA_OK(cudaGetLastError());
     }
     unsigned long long total = 0;
@@ -841,7 +900,7 @@ int lq_upload_sketch_pipelined(LqReadsDev *d, const uint8_t *h_seq, const uint64
     for (size_t c = 0; c < nc; ++c) {                      /* the err word of every chunk */
         const uint64_t ns = d->h_slot0[cut[c + 1]] - d->h_slot0[cut[c]];
         const size_t nblk = (size_t)((ns * LQ_SLOT + RK_TILE - 1) / RK_TILE);
-        if (((const uint32_t*)(h_state.data() + soff[c] + nblk))[1]) { fprintf(stderr, "[lqcov] sketch: look-back timed out\n"); return -1; }
+        if (((const uint32_t*)(h_state.data() + soff[c] + nblk))[1]) { fprintf(stderr, "[lqcov] sketch: look-back or bulk copy timed out\n"); return -1; }
     }
     if (total > cap) return lq_sketch_run(d, w, k, is_hpc, rid_base, out, ws, st);   /* low-complexity input: the bases are packed, sketch again with room */
     out->n = total;
@@ -862,9 +921,7 @@ int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_b
     out->wide = k > LQ_MAX_K_DIRECT;   /* 2k-bit hashes in key64; one thread per read, as in HPC mode (the general state machine) */
     if (!is_hpc && !out->wide) {
         const bool roll = (w == 5 || w == 10) && k <= 15 && !g_sketch_tiled;
-        const bool lanes = roll && g_sketch_lanes;
-        const unsigned nblk = lanes ? (unsigned)((rd->n_slots * (LQ_SLOT / LQ_RL_SEG) + RL_TILE_SEGS - 1) / RL_TILE_SEGS)
-                            : roll ? (unsigned)((rd->n_slots * LQ_SLOT + RK_TILE - 1) / RK_TILE) : (unsigned)((rd->n_slots * LQ_SLOT + SK_TILE - 1) / SK_TILE);
+        const unsigned nblk = roll ? (unsigned)((rd->n_slots * LQ_SLOT + RK_TILE - 1) / RK_TILE) : (unsigned)((rd->n_slots * LQ_SLOT + SK_TILE - 1) / SK_TILE);
         LQ_TRY(out->blk.ensure((size_t)(nblk + 2) * 8 + 64));
         unsigned long long *state = out->blk.as<unsigned long long>();
         uint32_t *ticket = (uint32_t*)(state + nblk + 1), *err = ticket + 1;
@@ -877,16 +934,9 @@ int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_b
             LQ_CUDA_OK(cudaMemsetAsync(state, 0, (size_t)(nblk + 2) * 8 + 16, st));
             a.ticket = ticket; a.state = state; a.cap = cap; a.err = err;
             a.out_key = out->key.as<uint32_t>(); a.out_y = out->y.as<uint64_t>();
-            if (lanes) {
-                LQ_CUDA_OK(cudaFuncSetAttribute(lq_sketch_lane_k<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM));
-                LQ_CUDA_OK(cudaFuncSetAttribute(lq_sketch_lane_k<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM));
-            }
             {
                 LqProfScope ps("sketch", st, 1, rd->n_slots * (LQ_SLOT_W2 + LQ_SLOT_WN) * 4 + (uint64_t)((double)rd->n_bases * 2.0 / (w + 1)) * 12);
-                if (lanes && w == 5) lq_sketch_lane_k<5><<<nblk, RL_THREADS, RL_SMEM, st>>>(a);                              /* LongQC's overlap runs */
-                else if (lanes && w == 10) lq_sketch_lane_k<10><<<nblk, RL_THREADS, RL_SMEM, st>>>(a);                       /* LongQC's spike-in run */
-                else if (w == 5 && k <= 15 && !g_sketch_tiled) lq_sketch_roll_k<5><<<nblk, RK_THREADS, 0, st>>>(a);
-                else if (w == 10 && k <= 15 && !g_sketch_tiled) lq_sketch_roll_k<10><<<nblk, RK_THREADS, 0, st>>>(a); /* LongQC's spike-in run */
+                if (roll) sk_launch_seg64(a, nblk, st);
                 else if (w == 5) lq_sketch_k<5, 5><<<nblk, SK_THREADS, 0, st>>>(a);
                 else if (w == 10) lq_sketch_k<10, 10><<<nblk, SK_THREADS, 0, st>>>(a);
                 else lq_sketch_k<LQ_MAX_W, 0><<<nblk, SK_THREADS, 0, st>>>(a);
@@ -896,7 +946,7 @@ int lq_sketch_run(const LqReadsDev *rd, int w, int k, int is_hpc, uint32_t rid_b
             LQ_CUDA_OK(cudaMemcpyAsync(&last, state + (nblk - 1), 8, cudaMemcpyDeviceToHost, st));
             LQ_CUDA_OK(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, st)); lq_prof_d2h(12);
             LQ_CUDA_OK(cudaStreamSynchronize(st));
-            if (h_err) { fprintf(stderr, "[lqcov] sketch: look-back timed out\n"); return -1; }
+            if (h_err) { fprintf(stderr, "[lqcov] sketch: look-back or bulk copy timed out\n"); return -1; }
             total = last & ((1ULL << 62) - 1);
             if (total <= cap) break;
             if (attempt == 1) { fprintf(stderr, "[lqcov] sketch: output overflow after resize\n"); return -1; }
@@ -950,7 +1000,7 @@ void LqPartStream::release()
     for (int i = 0; i < LQ_STREAM_RING; ++i) { if (h_meta[i]) cudaFreeHost(h_meta[i]); h_meta[i] = 0; h_meta_cap[i] = 0; }
 }
 
-bool lq_stream_ok(int w, int k, int is_hpc) { return !is_hpc && (w == 5 || w == 10) && k <= 15 && !g_sketch_tiled && !g_sketch_lanes; }
+bool lq_stream_ok(int w, int k, int is_hpc) { return !is_hpc && (w == 5 || w == 10) && k <= 15 && !g_sketch_tiled; }
 
 #define ST_MAX_CHUNKS 65536
 int lq_stream_begin(LqPartStream *s, LqReadsDev *d, LqMinimizers *out, int w, int k, uint32_t rid_base, uint64_t expect_bases, cudaStream_t st)
@@ -1054,7 +1104,7 @@ int lq_stream_push(LqPartStream *s, const uint8_t *h_seq, const uint64_t *h_off,
         a.state = state; a.ticket = (uint32_t*)(state + nblk); a.err = a.ticket + 1;
         a.base_in = s->totals.as<unsigned long long>() + s->n_chunks; a.base_out = s->totals.as<unsigned long long>() + s->n_chunks + 1;
         { LqProfScope ps("sketch", st, 1, (s1 - s0) * (LQ_SLOT_W2 + LQ_SLOT_WN) * 4 + (uint64_t)((double)bases * 2.0 / (s->w + 1)) * 12);
-          if (s->w == 5) lq_sketch_roll_k<5><<<nblk, RK_THREADS, 0, st>>>(a); else lq_sketch_roll_k<10><<<nblk, RK_THREADS, 0, st>>>(a); }
+          sk_launch_seg64(a, nblk, st); }
         LQ_CUDA_OK(cudaGetLastError());
         s->chunk_state_off.push_back(s->state_used); s->chunk_tiles.push_back(nblk);
         s->state_used += nblk + 2;
@@ -1080,7 +1130,7 @@ int lq_stream_end(LqPartStream *s, LqDevBuf &ws)
     lq_prof_d2h(8 + s->state_used * 8);
     LQ_CUDA_OK(cudaStreamSynchronize(st));
     for (size_t c = 0; c < s->chunk_tiles.size(); ++c)
-        if (s->chunk_tiles[c] && ((const uint32_t*)(h_state.data() + s->chunk_state_off[c] + s->chunk_tiles[c]))[1]) { fprintf(stderr, "[lqcov] sketch: look-back timed out\n"); return -1; }
+        if (s->chunk_tiles[c] && ((const uint32_t*)(h_state.data() + s->chunk_state_off[c] + s->chunk_tiles[c]))[1]) { fprintf(stderr, "[lqcov] sketch: look-back or bulk copy timed out\n"); return -1; }
     if (total > s->cap_rec) return lq_sketch_run(d, s->w, s->k, 0, s->rid_base, out, ws, st);   /* low-complexity input: the bases are packed, sketch again with room */
     out->n = total;
     return 0;

@@ -96,8 +96,8 @@ def hostcheck():
             f.restype = C.c_int
         lib.lqhc_sketch_replay.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_int]
         lib.lqhc_sketch_replay.restype = C.c_int
-        lib.lqhc_sketch_lanes.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
-        lib.lqhc_sketch_lanes.restype = C.c_int
+        lib.lqhc_sketch_pk.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        lib.lqhc_sketch_pk.restype = C.c_int
         lib.lqhc_hash32.argtypes = [C.c_uint32, C.c_uint32]
         lib.lqhc_hash32.restype = C.c_uint32
         lib.lqhc_hash64.argtypes = [C.c_uint64, C.c_uint64]

@@ -41,22 +41,31 @@ def test_sketch_tiled_kernel_where_rolling_is_default(w, k):
     assert np.array_equal(x, want["x"]) and np.array_equal(y, want["y"])
 
 
-@pytest.mark.parametrize("w,k", [(5, 12), (10, 15), (5, 15)])
-def test_sketch_lane_kernel(w, k):
-    """the 16-bases-per-lane kernel (state handed over by warp shuffle, lq_sketch_lane_core.h) is exact as well; long clean reads
-    so that nearly every segment starts from a handed-over state, plus the adversarial set for the fall-backs"""
+@pytest.mark.parametrize("w,k,mode", [(5, 12, 0), (5, 15, 0), (5, 12, 2), (5, 15, 2), (5, 12, 3), (5, 15, 3)])
+def test_sketch_packed_key_kernel(w, k, mode):
+    """the 64-bases-per-thread packed-key kernel (lq_sketch_pk_core.h), fed by bulk copies (0) or plain loads (2), and the rolling
+    kernel it replaced (3): long clean reads so that nearly every segment takes the unrolled blocks, repeat-rich reads for the
+    twin records, the adversarial set for the segments the form declines, N-rich reads for tiles that run the general machine"""
     L = _L()
     rng = np.random.default_rng(300 + w + k)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
     seqs = liblq.adversarial_seqs(rng, 120, 2500)
     for _ in range(40):
-        seqs.append(bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(rng.integers(500, 20000))).tobytes()))
+        seqs.append(bytes(rng.choice(acgt, size=int(rng.integers(500, 20000))).tobytes()))
+    for _ in range(20):
+        unit = bytes(rng.choice(acgt, size=int(rng.integers(1, 9))).tobytes())
+        body = bytearray(rng.choice(acgt, size=6000).tobytes())
+        for _ in range(12):
+            p0 = int(rng.integers(0, 5800)); rep = unit * int(rng.integers(3, 40)); body[p0:p0 + len(rep)] = rep[:max(0, 6000 - p0)]
+        seqs.append(bytes(body))
     rs = liblq.reads_from_seqs(seqs)
-    L.load().lqcov_debug_sketch_tiled(2)
+    L.load().lqcov_debug_sketch_tiled(mode)
     try:
         x, y = L.sketch(rs, L.Opt(w=w, k=k), rid_base=3)
     finally:
         L.load().lqcov_debug_sketch_tiled(0)
     want = liblq.oracle_sketch_set(rs, w, k, 0, rid_base=3)
+    assert len(x) == len(want)
     assert np.array_equal(x, want["x"]) and np.array_equal(y, want["y"])
 
 
