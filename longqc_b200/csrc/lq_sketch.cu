@@ -608,7 +608,7 @@ __device__ __forceinline__ void pk_general_inplace(const SkArgs &a, uint32_t rd,
 
 extern __shared__ __align__(16) unsigned char pk_smem[];
 
-template <int W, int K>
+template <int W, int K, bool ROT>
 __global__ void __launch_bounds__(RK_THREADS) lq_sketch_pk_k(SkArgs a, int use_bulk)
 {
     typedef lq_pk_tr<(K > 12)> T;
@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(RK_THREADS) lq_sketch_pk_k(SkArgs a, int use_b
     int n = 0, fbi = -1;
     if (i0 < i1) {
         PkStage<key> sink; sink.row = sink.w = lq_smem_u32(s_stage + tid * PK_STRIDE);
-        const int r = lq_pk_segment<W, K>(s_b2 + 4 + tid * 4, s_nm + 2 + tid * 2, i0, i1 - i0, i1 == L, sink);
+        const int r = lq_pk_segment<W, K, ROT>(s_b2 + 4 + tid * 4, s_nm + 2 + tid * 2, i0, i1 - i0, i1 == L, sink);
         if (r == 0) n = sink.count();
         else {
             fbi = (int)atomicAdd(&s_nfb, 1u);
@@ -740,17 +740,23 @@ __global__ void lq_read_first_k(const uint64_t *__restrict__ y, uint64_t n, uint
 
 /* test switch: force the tiled position-parallel kernel even where the rolling kernel applies (LQCOV_SKETCH_TILED=1) */
 static int g_sketch_tiled = getenv("LQCOV_SKETCH_TILED") ? atoi(getenv("LQCOV_SKETCH_TILED")) : 0;
-/* LQCOV_SKETCH_PK: 1 (default) packed-key kernel fed by bulk asynchronous copies, 2 the same fed by plain loads, 0 the rolling kernel */
+/* LQCOV_SKETCH_PK: 1 (default) packed-key kernel, one copy of the unrolled block (moving frame), fed by bulk asynchronous copies;
+ * 2 the same fed by plain loads; 3 four copies of the block (fixed frame), bulk copies; 0 the rolling kernel */
 static int g_sketch_pk = getenv("LQCOV_SKETCH_PK") ? atoi(getenv("LQCOV_SKETCH_PK")) : 1;
-/* test switch: 0 the defaults; 1 tiled kernel; 2 packed-key kernel fed by plain loads; 3 rolling kernel where the packed-key one is the default */
-extern "C" void lqcov_debug_sketch_tiled(int on) { g_sketch_tiled = on == 1; g_sketch_pk = on == 2 ? 2 : on == 3 ? 0 : 1; }
+/* test switch: 0 the defaults; 1 tiled kernel; 2 / 4 packed-key kernel fed by plain loads / with the fixed frame; 3 rolling kernel where
+ * the packed-key one is the default */
+extern "C" void lqcov_debug_sketch_tiled(int on) { g_sketch_tiled = on == 1; g_sketch_pk = on == 2 ? 2 : on == 4 ? 3 : on == 3 ? 0 : 1; }
 /* the 64-bases-per-thread kernels share the tile geometry (RK_TILE bases per CTA) */
 static void sk_launch_seg64(const SkArgs &a, unsigned nblk, cudaStream_t st)
 {
-    static int once = (cudaFuncSetAttribute(lq_sketch_pk_k<5, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM(8)), 0);
+    static int once = (cudaFuncSetAttribute(lq_sketch_pk_k<5, 15, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM(8)),
+                       cudaFuncSetAttribute(lq_sketch_pk_k<5, 15, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM(8)), 0);
     (void)once;
-    if (a.w == 5 && a.k == 12 && g_sketch_pk) lq_sketch_pk_k<5, 12><<<nblk, RK_THREADS, PK_SMEM(4), st>>>(a, g_sketch_pk == 1);          /* LongQC's overlap runs */
-    else if (a.w == 5 && a.k == 15 && g_sketch_pk) lq_sketch_pk_k<5, 15><<<nblk, RK_THREADS, PK_SMEM(8), st>>>(a, g_sketch_pk == 1);     /* --fast */
+    const int bulk = g_sketch_pk != 2;
+    if (a.w == 5 && a.k == 12 && g_sketch_pk == 3) lq_sketch_pk_k<5, 12, false><<<nblk, RK_THREADS, PK_SMEM(4), st>>>(a, bulk);
+    else if (a.w == 5 && a.k == 15 && g_sketch_pk == 3) lq_sketch_pk_k<5, 15, false><<<nblk, RK_THREADS, PK_SMEM(8), st>>>(a, bulk);
+    else if (a.w == 5 && a.k == 12 && g_sketch_pk) lq_sketch_pk_k<5, 12, true><<<nblk, RK_THREADS, PK_SMEM(4), st>>>(a, bulk);          /* LongQC's overlap runs */
+    else if (a.w == 5 && a.k == 15 && g_sketch_pk) lq_sketch_pk_k<5, 15, true><<<nblk, RK_THREADS, PK_SMEM(8), st>>>(a, bulk);     /* --fast */
     else if (a.w == 5) lq_sketch_roll_k<5><<<nblk, RK_THREADS, 0, st>>>(a);
     else lq_sketch_roll_k<10><<<nblk, RK_THREADS, 0, st>>>(a);
 }

@@ -113,7 +113,7 @@ LQ_HD void lq_pk_window(const typename lq_pk_tr<WIDE>::key kk, lq_pk_state<W, WI
  * constant after unrolling.  sink.put(key, yes) stores unconditionally and keeps the record only if `yes`.  A palindromic
  * k-mer (no push) leaves the state alone; its key still enters s.d, which is harmless: it cannot equal a pushed k-mer. */
 template <int W, int K, bool EMIT, class Sink>
-LQ_HD void lq_pk_fast(const uint32_t *Lw, const uint32_t *Rw, const int P, lq_pk_state<W, (K > 12)> &s, Sink &sink)
+LQ_HD void lq_pk_fast(const uint32_t *Lw, const uint32_t *Rw, const int P, lq_pk_state<W, (K > 12)> &s, Sink &sink, const uint32_t rb = 0)
 {
     typedef lq_pk_tr<(K > 12)> T;
     typedef typename T::key key;
@@ -125,7 +125,7 @@ LQ_HD void lq_pk_fast(const uint32_t *Lw, const uint32_t *Rw, const int P, lq_pk
     const key kk = T::mk(lq_hash32(z ? rv : fw, mask), 255u - 2u * (uint32_t)P) - z;   /* the code is odd: no borrow */
     key nm;
     lq_pk_window<W, (K > 12)>(kk, s, &nm);
-    if (EMIT) sink.put(s.om, push && nm != s.om);
+    if (EMIT) sink.put(s.om - rb, push && nm != s.om);
     s.om = push ? nm : s.om;
     for (int j = 0; j + 1 < W; ++j) s.r[j] = push ? s.r[j + 1] : s.r[j];
     s.r[W - 1] = push ? kk : s.r[W - 1];
@@ -135,7 +135,8 @@ LQ_HD void lq_pk_fast(const uint32_t *Lw, const uint32_t *Rw, const int P, lq_pk
  * honours lo <= P < hi (bases that exist and, at a read start, have seen k bases), writes only from P >= efrom on
  * (sketch.c:123, :126: l >= w+k at a read start), and writes the twins of a minimum that took over by age (sketch.c:131-136). */
 template <int W, int K, class Sink>
-LQ_HD void lq_pk_slow(const uint32_t *lw8, const int P, lq_pk_state<W, (K > 12)> &s, const int lo, const int hi, const int efrom, Sink &sink)
+LQ_HD void lq_pk_slow(const uint32_t *lw8, const int P, lq_pk_state<W, (K > 12)> &s, const int lo, const int hi, const int efrom, Sink &sink,
+                       const int Pc /* the position the code is made of: P, or P in the frame of the block */, const uint32_t rb = 0)
 {
     typedef lq_pk_tr<(K > 12)> T;
     typedef typename T::key key;
@@ -146,15 +147,15 @@ LQ_HD void lq_pk_slow(const uint32_t *lw8, const int P, lq_pk_state<W, (K > 12)>
     const uint32_t rv = ~le & mask, fw = lq_pk_rev2(le) >> (32 - 2 * K);
     if (fw == rv) { if (P < efrom) s.bad = 1; return; }          /* a palindrome before a read's first full window: l is no longer the position */
     const uint32_t z = fw < rv ? 0u : 1u;
-    const key kk = T::mk(lq_hash32(z ? rv : fw, mask), (255u - 2u * (uint32_t)P) - z);
+    const key kk = T::mk(lq_hash32(z ? rv : fw, mask), (255u - 2u * (uint32_t)Pc) - z);
     key nm;
     lq_pk_window<W, (K > 12)>(kk, s, &nm);
     if (T::same(s.d) && P < efrom) s.bad = 1;                    /* sketch.c:116-121 is not restated */
     if (nm != s.om) {
         if (P >= efrom) {
-            sink.push(s.om);
+            sink.push(s.om - rb);
             if (s.om == s.r[0] && T::hash(kk) > T::hash(s.om)) {
-                for (int j = 1; j < W; ++j) if (s.r[j] != nm && s.r[j] != T::none() && T::same(s.r[j] ^ nm)) sink.push(s.r[j]);
+                for (int j = 1; j < W; ++j) if (s.r[j] != nm && s.r[j] != T::none() && T::same(s.r[j] ^ nm)) sink.push(s.r[j] - rb);
             }
         }
         s.om = nm;
@@ -170,7 +171,7 @@ LQ_HD void lq_pk_slow(const uint32_t *lw8, const int P, lq_pk_state<W, (K > 12)>
  * (in both cases whatever the sink holds is to be dropped). */
 LQ_HD uint32_t lq_pk_p2z(int i0, uint32_t code) { return (uint32_t)(2 * i0 + 127) - code; }
 
-template <int W, int K, class Sink>
+template <int W, int K, bool ROT, class Sink>
 LQ_HD int lq_pk_segment(const uint32_t *lw8, const uint32_t *nw4, const int i0, const int nseg, const bool is_last, Sink &sink)
 {
     typedef lq_pk_tr<(K > 12)> T;
@@ -218,6 +219,42 @@ LQ_HD int lq_pk_segment(const uint32_t *lw8, const uint32_t *nw4, const int i0, 
         lo = 64 + K - 1; efrom = 64 + W + K - 1;
     }
     bool dup = T::same(s.d);                               /* an equal pair in the block before: this block looks for twins */
+    uint32_t rb = 0;
+    if (ROT) {
+        /* One copy of the unrolled block: the frame moves with the block (its 16 bases are always positions 64..79, the words it
+         * needs always Lw[3], Lw[4] and their reversals), the codes of the keys in flight grow by 32 per block (they are
+         * positions relative to the frame) and a record leaves with its code taken back to the segment's frame (- rb). */
+#ifdef __CUDA_ARCH__
+        #pragma unroll 1
+#endif
+        for (int B = 0; B * 16 < nseg; ++B) {
+            if (B) {
+                for (int j = 0; j < W; ++j) if (s.r[j] != T::none()) { if (T::code(s.r[j]) > 223u) return 1; s.r[j] += 32u; }   /* older than the frame: not here */
+                if (s.om != T::none()) s.om += 32u;
+                rb += 32u;
+                Lw[3] = Lw[4]; Lw[4] = lw8[4 + B]; Rw[4] = Rw[3]; Rw[3] = lq_pk_rev2(Lw[4]);
+            }
+            bool slow = dup || (i0 == 0 && B * 16 < W + K - 1) || nseg < (B + 1) * 16;
+            if (sink.room() < 17) return 2;
+            s.d = T::none();
+            if (!slow) {
+                const lq_pk_state<W, (K > 12)> keep = s;
+                const typename Sink::mark_t m = sink.mark();
+#ifdef __CUDA_ARCH__
+                #pragma unroll
+#endif
+                for (int j = 0; j < 16; ++j) lq_pk_fast<W, K, true>(Lw, Rw, 64 + j, s, sink, rb);
+                if (T::same(s.d)) { s = keep; s.d = T::none(); sink.rewind(m); slow = true; }
+            }
+            if (slow) {
+#ifdef __CUDA_ARCH__
+                #pragma unroll 1
+#endif
+                for (int j = 0; j < 16; ++j) lq_pk_slow<W, K>(lw8, 64 + B * 16 + j, s, lo, hi, efrom, sink, 64 + j, rb);
+            }
+            dup = T::same(s.d);
+        }
+    } else {
 #ifdef __CUDA_ARCH__
     #pragma unroll
 #endif
@@ -239,13 +276,14 @@ LQ_HD int lq_pk_segment(const uint32_t *lw8, const uint32_t *nw4, const int i0, 
 #ifdef __CUDA_ARCH__
                 #pragma unroll 1
 #endif
-                for (int j = 0; j < 16; ++j) lq_pk_slow<W, K>(lw8, 64 + B * 16 + j, s, lo, hi, efrom, sink);
+                for (int j = 0; j < 16; ++j) lq_pk_slow<W, K>(lw8, 64 + B * 16 + j, s, lo, hi, efrom, sink, 64 + B * 16 + j);
             }
             dup = T::same(s.d);
         }
     }
+    }
     if (s.bad) return 1;
-    if (is_last && s.om != T::none()) sink.push(s.om);     /* sketch.c:140-141 */
+    if (is_last && s.om != T::none()) sink.push(s.om - rb);     /* sketch.c:140-141 */
     return sink.room() < 0 ? 2 : 0;
 }
 
