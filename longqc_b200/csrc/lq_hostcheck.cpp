@@ -310,7 +310,7 @@ extern "C" long lqhc_mmi_load_count(const char *path, long *n_rec, long *n_seq)
 // general state machine; *n_lean counts the segments it accepted.  The words before a read's first segment are garbage on purpose.
 #include "lq_sketch_pk_core.h"
 namespace {
-template <int W, int K, bool ROT>
+template <int W, int K>
 int sketch_pk(const char *seq, int len, uint32_t rid, lq_mm128 *out, int cap, int *n_lean)
 {
     typedef lq_pk_tr<(K > 12)> T;
@@ -334,7 +334,7 @@ int sketch_pk(const char *seq, int len, uint32_t rid, lq_mm128 *out, int cap, in
             void rewind(mark_t m) { v->resize(m); }
         } ks; ks.v = &v; ks.rid = rid; ks.i0 = i0;
         const size_t mark = v.size();
-        if (lq_pk_segment<W, K, ROT>(lw8, nw4, i0, nseg, is_last, ks) == 0) ++lean;
+        if (lq_pk_segment<W, K>(lw8, nw4, i0, nseg, is_last, ks) == 0) ++lean;
         else {
             v.resize(mark);
             lq_sketch_replay(b2.data(), nm.data(), 0, len, W, K, rid, 0, 0, 1, i0 + nseg - 1, i0, is_last ? len : i0 + nseg - 1, (int*)0, s);
@@ -348,17 +348,15 @@ int sketch_pk(const char *seq, int len, uint32_t rid, lq_mm128 *out, int cap, in
 }
 extern "C" int lqhc_sketch_pk(const char *seq, int len, int w, int k, uint32_t rid, int *n_lean, lq_mm128 *out, int cap)
 {
-    const int rot = w >= 100;    // w + 100: the form with one copy of the unrolled block (moving frame)
-    if (rot) w -= 100;
     switch (w * 100 + k) {
-    case 512: return rot ? sketch_pk<5, 12, true>(seq, len, rid, out, cap, n_lean) : sketch_pk<5, 12, false>(seq, len, rid, out, cap, n_lean);
-    case 515: return rot ? sketch_pk<5, 15, true>(seq, len, rid, out, cap, n_lean) : sketch_pk<5, 15, false>(seq, len, rid, out, cap, n_lean);
-    case 511: return rot ? sketch_pk<5, 11, true>(seq, len, rid, out, cap, n_lean) : sketch_pk<5, 11, false>(seq, len, rid, out, cap, n_lean);
-    case 1015: return rot ? sketch_pk<10, 15, true>(seq, len, rid, out, cap, n_lean) : sketch_pk<10, 15, false>(seq, len, rid, out, cap, n_lean);
-    case 1012: return rot ? sketch_pk<10, 12, true>(seq, len, rid, out, cap, n_lean) : sketch_pk<10, 12, false>(seq, len, rid, out, cap, n_lean);
-    case 308: return rot ? sketch_pk<3, 8, true>(seq, len, rid, out, cap, n_lean) : sketch_pk<3, 8, false>(seq, len, rid, out, cap, n_lean);
-    case 204: return rot ? sketch_pk<2, 4, true>(seq, len, rid, out, cap, n_lean) : sketch_pk<2, 4, false>(seq, len, rid, out, cap, n_lean);
-    case 713: return rot ? sketch_pk<7, 13, true>(seq, len, rid, out, cap, n_lean) : sketch_pk<7, 13, false>(seq, len, rid, out, cap, n_lean);
+    case 512: return sketch_pk<5, 12>(seq, len, rid, out, cap, n_lean);
+    case 515: return sketch_pk<5, 15>(seq, len, rid, out, cap, n_lean);
+    case 511: return sketch_pk<5, 11>(seq, len, rid, out, cap, n_lean);
+    case 1015: return sketch_pk<10, 15>(seq, len, rid, out, cap, n_lean);
+    case 1012: return sketch_pk<10, 12>(seq, len, rid, out, cap, n_lean);
+    case 308: return sketch_pk<3, 8>(seq, len, rid, out, cap, n_lean);
+    case 204: return sketch_pk<2, 4>(seq, len, rid, out, cap, n_lean);
+    case 713: return sketch_pk<7, 13>(seq, len, rid, out, cap, n_lean);
     }
     return -1;
 }

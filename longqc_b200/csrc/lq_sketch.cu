@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(SK_THREADS) lq_sketch_k(SkArgs a)
                 /* usable lanes: 0 .. first PREFIX lane, all of which must be ready */
                 const int stop = pre ? __ffs(pre) - 1 : 31;
                 const uint32_t need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1);
-                if ((ready & need) != need) { __nanosleep(64); if (++spins > (1u << 24)) { if (tid == 0) atomicOr(a.err, 1u); break; } continue; }
+                if ((ready & need) != need) { __nanosleep(spins < 5 ? 32u << spins : 1024u); if (++spins > (1u << 22)) { if (tid == 0) atomicOr(a.err, 1u); break; } continue; }
                 uint64_t v = (tid <= stop) ? (sv & VMASK) : 0;
                 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -476,7 +476,8 @@ __device__ __forceinline__ void sk_tile_base(const SkArgs &a, const uint32_t til
         else {
             if (tid == 0) atomicExch(&a.state[tile], FLAG_AGG | tot);
             int64_t hi = (int64_t)tile - 1; uint32_t spins = 0;
-            for (;;) {
+            for (;;) {   /* lanes look at tiles hi, hi-1, ..., hi-31 (rounds of 128 were measured: no faster -- the wait is for the
+                          * predecessors to finish, not for the walk) */
                 const int64_t j = hi - tid;
                 unsigned long long sv = FLAG_PRE;
                 if (j >= 0) sv = *(volatile unsigned long long*)&a.state[j];
@@ -484,7 +485,7 @@ __device__ __forceinline__ void sk_tile_base(const SkArgs &a, const uint32_t til
                 const uint32_t pre = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
                 const int stop = pre ? __ffs(pre) - 1 : 31;
                 const uint32_t need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1);
-                if ((ready & need) != need) { __nanosleep(64); if (++spins > (1u << 24)) { if (tid == 0) atomicOr(a.err, 1u); break; } continue; }
+                if ((ready & need) != need) { __nanosleep(spins < 5 ? 32u << spins : 1024u); if (++spins > (1u << 22)) { if (tid == 0) atomicOr(a.err, 1u); break; } continue; }
                 uint64_t v = (tid <= stop) ? (sv & VMASK) : 0;
                 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -608,7 +609,7 @@ __device__ __forceinline__ void pk_general_inplace(const SkArgs &a, uint32_t rd,
 
 extern __shared__ __align__(16) unsigned char pk_smem[];
 
-template <int W, int K, bool ROT>
+template <int W, int K>
 __global__ void __launch_bounds__(RK_THREADS) lq_sketch_pk_k(SkArgs a, int use_bulk)
 {
     typedef lq_pk_tr<(K > 12)> T;
@@ -659,7 +660,7 @@ __global__ void __launch_bounds__(RK_THREADS) lq_sketch_pk_k(SkArgs a, int use_b
     int n = 0, fbi = -1;
     if (i0 < i1) {
         PkStage<key> sink; sink.row = sink.w = lq_smem_u32(s_stage + tid * PK_STRIDE);
-        const int r = lq_pk_segment<W, K, ROT>(s_b2 + 4 + tid * 4, s_nm + 2 + tid * 2, i0, i1 - i0, i1 == L, sink);
+        const int r = lq_pk_segment<W, K>(s_b2 + 4 + tid * 4, s_nm + 2 + tid * 2, i0, i1 - i0, i1 == L, sink);
         if (r == 0) n = sink.count();
         else {
             fbi = (int)atomicAdd(&s_nfb, 1u);
@@ -680,21 +681,26 @@ __global__ void __launch_bounds__(RK_THREADS) lq_sketch_pk_k(SkArgs a, int use_b
     if (s_base + tot > a.cap) return;
     const uint64_t at = s_base + ex;
     if (s_over) { if (n) pk_general_inplace<W>(a, rd, g0, L, i0, i1, at); return; }   /* low-complexity tile */
+    /* A warp's records are one stretch of the output.  Every thread leaves what a writer needs to know about its row where the
+     * packed words were (all warps are past them); then lane l of round i writes record 32 i + l of the stretch: it finds the
+     * row by bisection over the rows' first records (5 shared loads), and the warp's stores are whole sectors. */
     const uint32_t lane = tid & 31, wb = tid & ~31u;
-    const uint32_t rid = a.rid_base + rd, t127 = (uint32_t)(2 * i0 + 127);
+    const uint32_t wex0 = __shfl_sync(0xffffffffu, (uint32_t)ex, 0), wtot = __shfl_sync(0xffffffffu, (uint32_t)ex + (uint32_t)n, 31) - wex0;
+    uint4 *s_meta = (uint4*)pk_smem + wb;
+    s_meta[lane] = make_uint4((uint32_t)ex - wex0, (uint32_t)(fbi + 1), (uint32_t)(2 * i0 + 127), a.rid_base + rd);
+    __syncwarp();
+    uint32_t *const ok = a.out_key + (s_base + wex0); uint64_t *const oy = a.out_y + (s_base + wex0);
     #pragma unroll 1
-    for (int t = 0; t < 32; ++t) {
-        const int nt = __shfl_sync(0xffffffffu, n, t);
-        if (nt == 0) continue;
-        const uint64_t at_t = __shfl_sync(0xffffffffu, at, t);
-        const uint32_t rid_t = __shfl_sync(0xffffffffu, rid, t), t127_t = __shfl_sync(0xffffffffu, t127, t);
-        const int fb_t = __shfl_sync(0xffffffffu, fbi, t);
-        for (int j = lane; j < nt; j += 32) {
-            uint32_t h, p;
-            if (fb_t < 0) { const key kk = s_stage[(wb + t) * PK_STRIDE + j]; h = T::hash(kk); p = t127_t - T::code(kk); }
-            else { const uint2 r = s_fb[fb_t * PK_CAP + j]; h = r.x; p = r.y; }
-            a.out_key[at_t + j] = h; a.out_y[at_t + j] = (uint64_t)rid_t << 32 | p;
-        }
+    for (uint32_t o = lane; o < wtot; o += 32) {
+        uint32_t t = 0;
+        #pragma unroll
+        for (uint32_t st = 16; st > 0; st >>= 1) if (s_meta[t + st].x <= o) t += st;
+        const uint4 m = s_meta[t];
+        const uint32_t j = o - m.x;
+        uint32_t h, p;
+        if (m.y == 0) { const key kk = s_stage[(wb + t) * PK_STRIDE + j]; h = T::hash(kk); p = m.z - T::code(kk); }
+        else { const uint2 r = s_fb[(m.y - 1) * PK_CAP + j]; h = r.x; p = r.y; }
+        ok[o] = h; oy[o] = (uint64_t)m.w << 32 | p;
     }
 }
 
@@ -740,23 +746,17 @@ __global__ void lq_read_first_k(const uint64_t *__restrict__ y, uint64_t n, uint
 
 /* test switch: force the tiled position-parallel kernel even where the rolling kernel applies (LQCOV_SKETCH_TILED=1) */
 static int g_sketch_tiled = getenv("LQCOV_SKETCH_TILED") ? atoi(getenv("LQCOV_SKETCH_TILED")) : 0;
-/* LQCOV_SKETCH_PK: 1 (default) packed-key kernel, one copy of the unrolled block (moving frame), fed by bulk asynchronous copies;
- * 2 the same fed by plain loads; 3 four copies of the block (fixed frame), bulk copies; 0 the rolling kernel */
+/* LQCOV_SKETCH_PK: 1 (default) packed-key kernel fed by bulk asynchronous copies; 2 the same fed by plain loads; 0 the rolling kernel */
 static int g_sketch_pk = getenv("LQCOV_SKETCH_PK") ? atoi(getenv("LQCOV_SKETCH_PK")) : 1;
-/* test switch: 0 the defaults; 1 tiled kernel; 2 / 4 packed-key kernel fed by plain loads / with the fixed frame; 3 rolling kernel where
- * the packed-key one is the default */
-extern "C" void lqcov_debug_sketch_tiled(int on) { g_sketch_tiled = on == 1; g_sketch_pk = on == 2 ? 2 : on == 4 ? 3 : on == 3 ? 0 : 1; }
+/* test switch: 0 the defaults; 1 tiled kernel; 2 packed-key kernel fed by plain loads; 3 rolling kernel where the packed-key one is the default */
+extern "C" void lqcov_debug_sketch_tiled(int on) { g_sketch_tiled = on == 1; g_sketch_pk = on == 2 ? 2 : on == 3 ? 0 : 1; }
 /* the 64-bases-per-thread kernels share the tile geometry (RK_TILE bases per CTA) */
 static void sk_launch_seg64(const SkArgs &a, unsigned nblk, cudaStream_t st)
 {
-    static int once = (cudaFuncSetAttribute(lq_sketch_pk_k<5, 15, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM(8)),
-                       cudaFuncSetAttribute(lq_sketch_pk_k<5, 15, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM(8)), 0);
+    static int once = (cudaFuncSetAttribute(lq_sketch_pk_k<5, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM(8)), 0);
     (void)once;
-    const int bulk = g_sketch_pk != 2;
-    if (a.w == 5 && a.k == 12 && g_sketch_pk == 3) lq_sketch_pk_k<5, 12, false><<<nblk, RK_THREADS, PK_SMEM(4), st>>>(a, bulk);
-    else if (a.w == 5 && a.k == 15 && g_sketch_pk == 3) lq_sketch_pk_k<5, 15, false><<<nblk, RK_THREADS, PK_SMEM(8), st>>>(a, bulk);
-    else if (a.w == 5 && a.k == 12 && g_sketch_pk) lq_sketch_pk_k<5, 12, true><<<nblk, RK_THREADS, PK_SMEM(4), st>>>(a, bulk);          /* LongQC's overlap runs */
-    else if (a.w == 5 && a.k == 15 && g_sketch_pk) lq_sketch_pk_k<5, 15, true><<<nblk, RK_THREADS, PK_SMEM(8), st>>>(a, bulk);     /* --fast */
+    if (a.w == 5 && a.k == 12 && g_sketch_pk) lq_sketch_pk_k<5, 12><<<nblk, RK_THREADS, PK_SMEM(4), st>>>(a, g_sketch_pk != 2);          /* LongQC's overlap runs */
+    else if (a.w == 5 && a.k == 15 && g_sketch_pk) lq_sketch_pk_k<5, 15><<<nblk, RK_THREADS, PK_SMEM(8), st>>>(a, g_sketch_pk != 2);     /* --fast */
     else if (a.w == 5) lq_sketch_roll_k<5><<<nblk, RK_THREADS, 0, st>>>(a);
     else lq_sketch_roll_k<10><<<nblk, RK_THREADS, 0, st>>>(a);
 }

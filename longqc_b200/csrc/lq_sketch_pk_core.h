@@ -35,11 +35,12 @@
 template <bool WIDE> struct lq_pk_tr;
 template <> struct lq_pk_tr<false> {          /* 2k <= 24: hash and code share 32 bits */
     typedef uint32_t key;
-    static LQ_HD key mk(uint32_t h, uint32_t code) { return h << 8 | code; }
+    static LQ_HD key mk(uint32_t h, uint32_t code) { return (h << 8) + code; }   /* code < 256; a sum folds into the hash's last multiply-add */
     static LQ_HD bool same(key d /* a ^ b */) { return d < 256u; }
     static LQ_HD uint32_t hash(key a) { return a >> 8; }
     static LQ_HD uint32_t code(key a) { return a & 255u; }
     static LQ_HD key none() { return 0xffffffffu; }
+    static LQ_HD key fill() { return 0xfffffeffu; }      /* neither an entry nor the twin of one (nor of none()) */
     static LQ_HD key min2(key a, key b) { return a < b ? a : b; }
 #ifdef __CUDA_ARCH__
     static LQ_HD key min3(key a, key b, key c) { return __vimin3_u32(a, b, c); }
@@ -49,11 +50,12 @@ template <> struct lq_pk_tr<false> {          /* 2k <= 24: hash and code share 3
 };
 template <> struct lq_pk_tr<true> {           /* 2k <= 32: hash in the high word */
     typedef uint64_t key;
-    static LQ_HD key mk(uint32_t h, uint32_t code) { return (uint64_t)h << 32 | code; }
+    static LQ_HD key mk(uint32_t h, uint32_t code) { return ((uint64_t)h << 32) + code; }
     static LQ_HD bool same(key d) { return (d >> 32) == 0; }
     static LQ_HD uint32_t hash(key a) { return (uint32_t)(a >> 32); }
     static LQ_HD uint32_t code(key a) { return (uint32_t)a & 255u; }
     static LQ_HD key none() { return LQ_U64MAX; }
+    static LQ_HD key fill() { return 0xfffffffeffffffffULL; }
     static LQ_HD key min2(key a, key b) { return a < b ? a : b; }
     static LQ_HD key min3(key a, key b, key c) { return min2(min2(a, b), c); }
 };
@@ -113,7 +115,7 @@ LQ_HD void lq_pk_window(const typename lq_pk_tr<WIDE>::key kk, lq_pk_state<W, WI
  * constant after unrolling.  sink.put(key, yes) stores unconditionally and keeps the record only if `yes`.  A palindromic
  * k-mer (no push) leaves the state alone; its key still enters s.d, which is harmless: it cannot equal a pushed k-mer. */
 template <int W, int K, bool EMIT, class Sink>
-LQ_HD void lq_pk_fast(const uint32_t *Lw, const uint32_t *Rw, const int P, lq_pk_state<W, (K > 12)> &s, Sink &sink, const uint32_t rb = 0)
+LQ_HD void lq_pk_fast(const uint32_t *Lw, const uint32_t *Rw, const int P, lq_pk_state<W, (K > 12)> &s, Sink &sink, const uint32_t cb = 255u /* 255 - 32 * block: the code is made of the position in the SEGMENT's frame */)
 {
     typedef lq_pk_tr<(K > 12)> T;
     typedef typename T::key key;
@@ -122,10 +124,35 @@ LQ_HD void lq_pk_fast(const uint32_t *Lw, const uint32_t *Rw, const int P, lq_pk
     lq_pk_regs<K>(Lw, Rw, P, &fw, &rv);
     const bool push = fw != rv;
     const uint32_t z = fw < rv ? 0u : 1u;
-    const key kk = T::mk(lq_hash32(z ? rv : fw, mask), 255u - 2u * (uint32_t)P) - z;   /* the code is odd: no borrow */
+    const key kk = T::mk(lq_hash32(z ? rv : fw, mask), cb - 2u * (uint32_t)P - z);
     key nm;
     lq_pk_window<W, (K > 12)>(kk, s, &nm);
-    if (EMIT) sink.put(s.om - rb, push && nm != s.om);
+    if (EMIT) sink.put(s.om, push && nm != s.om);
+    s.om = push ? nm : s.om;
+    for (int j = 0; j + 1 < W; ++j) s.r[j] = push ? s.r[j + 1] : s.r[j];
+    s.r[W - 1] = push ? kk : s.r[W - 1];
+}
+
+/* the same with the gates of a read's first and last blocks: a base counts from plo on (at a read start: once k bases have
+ * been seen) and below phi (the read's end), records leave from pef on (sketch.c:123, :126: l >= w+k at a read start).  A
+ * palindromic k-mer before pef makes the segment one for the general state machine (l is no longer the position there). */
+template <int W, int K, class Sink>
+LQ_HD void lq_pk_fast_g(const uint32_t *Lw, const uint32_t *Rw, const int P, lq_pk_state<W, (K > 12)> &s, Sink &sink, const uint32_t cb,
+                        const int plo, const int phi, const int pef)
+{
+    typedef lq_pk_tr<(K > 12)> T;
+    typedef typename T::key key;
+    const uint32_t mask = (1u << 2 * K) - 1;
+    uint32_t fw, rv;
+    lq_pk_regs<K>(Lw, Rw, P, &fw, &rv);
+    const bool live = P >= plo && P < phi;
+    const bool push = live && fw != rv;
+    if (live && fw == rv && P < pef) s.bad = 1;
+    const uint32_t z = fw < rv ? 0u : 1u;
+    const key kk = live ? T::mk(lq_hash32(z ? rv : fw, mask), cb - 2u * (uint32_t)P - z) : T::fill();   /* padding must not look like an equal pair */
+    key nm;
+    lq_pk_window<W, (K > 12)>(kk, s, &nm);
+    sink.put(s.om, push && nm != s.om && P >= pef);
     s.om = push ? nm : s.om;
     for (int j = 0; j + 1 < W; ++j) s.r[j] = push ? s.r[j + 1] : s.r[j];
     s.r[W - 1] = push ? kk : s.r[W - 1];
@@ -135,8 +162,7 @@ LQ_HD void lq_pk_fast(const uint32_t *Lw, const uint32_t *Rw, const int P, lq_pk
  * honours lo <= P < hi (bases that exist and, at a read start, have seen k bases), writes only from P >= efrom on
  * (sketch.c:123, :126: l >= w+k at a read start), and writes the twins of a minimum that took over by age (sketch.c:131-136). */
 template <int W, int K, class Sink>
-LQ_HD void lq_pk_slow(const uint32_t *lw8, const int P, lq_pk_state<W, (K > 12)> &s, const int lo, const int hi, const int efrom, Sink &sink,
-                       const int Pc /* the position the code is made of: P, or P in the frame of the block */, const uint32_t rb = 0)
+LQ_HD void lq_pk_slow(const uint32_t *lw8, const int P, lq_pk_state<W, (K > 12)> &s, const int lo, const int hi, const int efrom, Sink &sink)
 {
     typedef lq_pk_tr<(K > 12)> T;
     typedef typename T::key key;
@@ -147,15 +173,15 @@ LQ_HD void lq_pk_slow(const uint32_t *lw8, const int P, lq_pk_state<W, (K > 12)>
     const uint32_t rv = ~le & mask, fw = lq_pk_rev2(le) >> (32 - 2 * K);
     if (fw == rv) { if (P < efrom) s.bad = 1; return; }          /* a palindrome before a read's first full window: l is no longer the position */
     const uint32_t z = fw < rv ? 0u : 1u;
-    const key kk = T::mk(lq_hash32(z ? rv : fw, mask), (255u - 2u * (uint32_t)Pc) - z);
+    const key kk = T::mk(lq_hash32(z ? rv : fw, mask), (255u - 2u * (uint32_t)P) - z);
     key nm;
     lq_pk_window<W, (K > 12)>(kk, s, &nm);
     if (T::same(s.d) && P < efrom) s.bad = 1;                    /* sketch.c:116-121 is not restated */
     if (nm != s.om) {
         if (P >= efrom) {
-            sink.push(s.om - rb);
+            sink.push(s.om);
             if (s.om == s.r[0] && T::hash(kk) > T::hash(s.om)) {
-                for (int j = 1; j < W; ++j) if (s.r[j] != nm && s.r[j] != T::none() && T::same(s.r[j] ^ nm)) sink.push(s.r[j] - rb);
+                for (int j = 1; j < W; ++j) if (s.r[j] != nm && s.r[j] != T::none() && T::same(s.r[j] ^ nm)) sink.push(s.r[j]);
             }
         }
         s.om = nm;
@@ -171,7 +197,7 @@ LQ_HD void lq_pk_slow(const uint32_t *lw8, const int P, lq_pk_state<W, (K > 12)>
  * (in both cases whatever the sink holds is to be dropped). */
 LQ_HD uint32_t lq_pk_p2z(int i0, uint32_t code) { return (uint32_t)(2 * i0 + 127) - code; }
 
-template <int W, int K, bool ROT, class Sink>
+template <int W, int K, class Sink>
 LQ_HD int lq_pk_segment(const uint32_t *lw8, const uint32_t *nw4, const int i0, const int nseg, const bool is_last, Sink &sink)
 {
     typedef lq_pk_tr<(K > 12)> T;
@@ -219,71 +245,50 @@ LQ_HD int lq_pk_segment(const uint32_t *lw8, const uint32_t *nw4, const int i0, 
         lo = 64 + K - 1; efrom = 64 + W + K - 1;
     }
     bool dup = T::same(s.d);                               /* an equal pair in the block before: this block looks for twins */
-    uint32_t rb = 0;
-    if (ROT) {
-        /* One copy of the unrolled block: the frame moves with the block (its 16 bases are always positions 64..79, the words it
-         * needs always Lw[3], Lw[4] and their reversals), the codes of the keys in flight grow by 32 per block (they are
-         * positions relative to the frame) and a record leaves with its code taken back to the segment's frame (- rb). */
+    {
+        /* One copy of the unrolled block: the frame of the WORDS moves with the block (its 16 bases are always bit positions
+         * 64..79, the words it needs always Lw[3], Lw[4] and their reversals); the codes stay positions in the segment's frame. */
 #ifdef __CUDA_ARCH__
         #pragma unroll 1
 #endif
         for (int B = 0; B * 16 < nseg; ++B) {
-            if (B) {
-                for (int j = 0; j < W; ++j) if (s.r[j] != T::none()) { if (T::code(s.r[j]) > 223u) return 1; s.r[j] += 32u; }   /* older than the frame: not here */
-                if (s.om != T::none()) s.om += 32u;
-                rb += 32u;
-                Lw[3] = Lw[4]; Lw[4] = lw8[4 + B]; Rw[4] = Rw[3]; Rw[3] = lq_pk_rev2(Lw[4]);
-            }
-            bool slow = dup || (i0 == 0 && B * 16 < W + K - 1) || nseg < (B + 1) * 16;
+            if (B) { Lw[3] = Lw[4]; Lw[4] = lw8[4 + B]; Rw[4] = Rw[3]; Rw[3] = lq_pk_rev2(Lw[4]); }
+            const uint32_t cb = 255u - 32u * (uint32_t)B;
+            const bool first = i0 == 0 && B * 16 < W + K - 1, gated = first || nseg < (B + 1) * 16;
+            bool slow = dup;
             if (sink.room() < 17) return 2;
             s.d = T::none();
             if (!slow) {
                 const lq_pk_state<W, (K > 12)> keep = s;
                 const typename Sink::mark_t m = sink.mark();
+                if (!gated) {
 #ifdef __CUDA_ARCH__
-                #pragma unroll
+                    #pragma unroll
 #endif
-                for (int j = 0; j < 16; ++j) lq_pk_fast<W, K, true>(Lw, Rw, 64 + j, s, sink, rb);
-                if (T::same(s.d)) { s = keep; s.d = T::none(); sink.rewind(m); slow = true; }
+                    for (int j = 0; j < 16; ++j) lq_pk_fast<W, K, true>(Lw, Rw, 64 + j, s, sink, cb);
+                } else {
+                    const int plo = lo - 16 * B, phi = hi - 16 * B, pef = efrom - 16 * B;
+#ifdef __CUDA_ARCH__
+                    #pragma unroll
+#endif
+                    for (int j = 0; j < 16; ++j) lq_pk_fast_g<W, K>(Lw, Rw, 64 + j, s, sink, cb, plo, phi, pef);
+                }
+                if (T::same(s.d)) {
+                    if (first) return 1;                         /* an equal pair around a read's first window (sketch.c:116-121 is not restated) */
+                    s = keep; s.d = T::none(); sink.rewind(m); slow = true;
+                }
             }
             if (slow) {
 #ifdef __CUDA_ARCH__
                 #pragma unroll 1
 #endif
-                for (int j = 0; j < 16; ++j) lq_pk_slow<W, K>(lw8, 64 + B * 16 + j, s, lo, hi, efrom, sink, 64 + j, rb);
+                for (int j = 0; j < 16; ++j) lq_pk_slow<W, K>(lw8, 64 + B * 16 + j, s, lo, hi, efrom, sink);
             }
             dup = T::same(s.d);
         }
-    } else {
-#ifdef __CUDA_ARCH__
-    #pragma unroll
-#endif
-    for (int B = 0; B < 4; ++B) {
-        if (B * 16 < nseg) {
-            bool slow = dup || (i0 == 0 && B * 16 < W + K - 1) || nseg < (B + 1) * 16;
-            if (sink.room() < 17) return 2;
-            s.d = T::none();
-            if (!slow) {
-                const lq_pk_state<W, (K > 12)> keep = s;
-                const typename Sink::mark_t m = sink.mark();
-#ifdef __CUDA_ARCH__
-                #pragma unroll
-#endif
-                for (int j = 0; j < 16; ++j) lq_pk_fast<W, K, true>(Lw, Rw, 64 + B * 16 + j, s, sink);
-                if (T::same(s.d)) { s = keep; s.d = T::none(); sink.rewind(m); slow = true; }
-            }
-            if (slow) {
-#ifdef __CUDA_ARCH__
-                #pragma unroll 1
-#endif
-                for (int j = 0; j < 16; ++j) lq_pk_slow<W, K>(lw8, 64 + B * 16 + j, s, lo, hi, efrom, sink, 64 + B * 16 + j);
-            }
-            dup = T::same(s.d);
-        }
-    }
     }
     if (s.bad) return 1;
-    if (is_last && s.om != T::none()) sink.push(s.om - rb);     /* sketch.c:140-141 */
+    if (is_last && s.om != T::none()) sink.push(s.om);     /* sketch.c:140-141 */
     return sink.room() < 0 ? 2 : 0;
 }
 

@@ -38,7 +38,7 @@ def test_packed_key_sketch(w, k):
         seqs.append(bytes(body))
     hc = liblq.hostcheck()
     lean_total = seg_total = 0
-    for s in seqs:
+    for i, s in enumerate(seqs):
         want = liblq.oracle_sketch(s, w, k, 3)
         cap = 2 * len(s) + 64
         out = np.zeros(cap, dtype=liblq.mm128_dtype)
@@ -47,6 +47,8 @@ def test_packed_key_sketch(w, k):
         assert 0 <= n <= cap
         assert np.array_equal(out[:n], want)
         lean_total += n_lean.value; seg_total += (len(s) + 63) // 64
+        if 210 <= i < 222 and k >= 11:   # plain random reads: the general state machine is for the odd segment (on the GPU it costs a warp ~4x)
+            assert n_lean.value >= (len(s) + 63) // 64 - 1
     assert lean_total > 0.7 * seg_total   # the form itself is what is being tested
 
 
