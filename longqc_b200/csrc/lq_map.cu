@@ -317,6 +317,8 @@ struct AfArgs {
     unsigned long long *n_elem;   /* elements this launch handled (profiling: algorithmic bytes of the launch) */
     const AfBkt *curb; const uint32_t *n_curb; AfBkt *nxtb; uint32_t *n_nxtb; uint32_t *cursorb;   /* buckets of >= AFB_MIN elements: a CTA each (lq_af_big_k) */
     int shift;
+    int two;                      /* this level's digit takes at most two values in every bucket (strand; rid >> 16 of a part of <= 131072 reads) */
+    uint32_t bitw;                /* 32-bit words of lq_af_big_k's shared-memory digit bitmap */
 };
 
 #define AFB_MIN 4096               /* buckets at least this long are sorted by a whole CTA (lq_af_big_k), shorter ones by a warp (lq_af_level_k) */
@@ -665,11 +667,15 @@ __device__ __forceinline__ void afb_subbuckets(const AfArgs &a, uint32_t beg, ui
 
 static int g_walk_stats = getenv("LQCOV_WALK_STATS") ? atoi(getenv("LQCOV_WALK_STATS")) : 0;
 /* CTAs per SM working on big buckets at a time: the passes over a bucket re-read it, so the buckets in flight should fit the L2 */
+/* words of the two-digit levels' shared-memory bitmap (LQCOV_AFB_BITW=0: the levels go through the digit and destination arrays) */
+static unsigned g_afb_bitw = getenv("LQCOV_AFB_BITW") ? (unsigned)atoi(getenv("LQCOV_AFB_BITW")) : 24576u;
 static unsigned g_afb_ctas = getenv("LQCOV_AFB_CTAS") && atoi(getenv("LQCOV_AFB_CTAS")) > 0 ? (unsigned)atoi(getenv("LQCOV_AFB_CTAS")) : 4u;
+
+extern __shared__ uint32_t afb_bits[];   /* a.bitw words: one bit per element of a two-digit bucket ("its digit is not the first element's") */
 
 __global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
 {
-    __shared__ uint32_t s_cnt[256], s_start[257], s_head[256], scan_sm[33];
+    __shared__ uint32_t s_cnt[256], s_start[257], s_head[256], scan_sm[33], s_wt[2][AFB_THREADS / 32];
     __shared__ uint32_t s_b, s_tied, s_nb, s_d0, s_d1, s_few;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, lt = (1u << lane) - 1;
     const uint32_t nbig = *a.n_curb;
@@ -687,20 +693,26 @@ __global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
         if (tid < 256) { s_cnt[tid] = 0; s_head[tid] = 0; }
         if (tid == 0) { s_tied = 0; atomicAdd(a.n_elem, (unsigned long long)n); }
         __syncthreads();
-        /* 1. digits + histogram (warp-aggregated shared-memory atomics: a level may have only two digits) */
+        /* 1. digits + histogram (warp-aggregated shared-memory atomics: a level may have only two digits).
+         * On a two-digit level (a.two) the digits of a bucket that fits stay in shared memory as ONE BIT each and nothing else is
+         * written: the bucket is then read once more and permuted by the closed form, whose ranks come straight from the bits
+         * (keys 8 B + pairs 12 B in, 12 B out, instead of 13 + 14 + 28 through the digit and destination arrays). */
+        const bool fused = a.two && n <= a.bitw * 32u;
+        const uint32_t dA = fused ? (uint32_t)(kx[0] >> a.shift) & 255u : 0u;
         uint32_t tied = 0;
         for (uint32_t r0 = 0; r0 < n; r0 += AFB_THREADS * AFB_V) {
             uint32_t dv[AFB_V]; uint64_t kk[AFB_V];
             #pragma unroll
-            for (int u = 0; u < AFB_V; ++u) { const uint32_t p = r0 + u * AFB_THREADS + tid; kk[u] = p < n ? kx[p] : 0; if (p < n) tied |= idx[p] >> 31; }
+            for (int u = 0; u < AFB_V; ++u) { const uint32_t p = r0 + u * AFB_THREADS + tid; kk[u] = p < n ? kx[p] : 0; if (!fused && p < n) tied |= idx[p] >> 31; }
             #pragma unroll
             for (int u = 0; u < AFB_V; ++u) dv[u] = (uint32_t)(kk[u] >> a.shift) & 255u;
             #pragma unroll
             for (int u = 0; u < AFB_V; ++u) {
                 const uint32_t p = r0 + u * AFB_THREADS + tid; const bool ok = p < n;
                 const uint32_t act = __ballot_sync(0xffffffffu, ok);
+                if (fused) { const uint32_t bits = __ballot_sync(0xffffffffu, ok && dv[u] != dA); if (lane == 0 && (p >> 5) < a.bitw) afb_bits[p >> 5] = bits; }
                 if (ok) {
-                    dig[p] = (uint8_t)dv[u];
+                    if (!fused) dig[p] = (uint8_t)dv[u];
                     const uint32_t peers = __match_any_sync(act, dv[u]);
                     if ((peers & lt) == 0) atomicAdd(&s_cnt[dv[u]], (uint32_t)__popc(peers));
                 }
@@ -724,7 +736,77 @@ __global__ void __launch_bounds__(AFB_THREADS) lq_af_big_k(AfArgs a)
             if (lane == 0) { s_start[256] = n; s_nb = ne; s_d0 = d0; s_d1 = d1; s_few = !hi; }
         }
         __syncthreads();
-        const uint32_t nb = s_nb; const bool tiedb = s_tied != 0;
+        const uint32_t nb = s_nb;
+        if (fused && nb > 2) {   /* the level was not a two-digit one for this bucket after all: what the general forms need */
+            for (uint32_t p = tid; p < n; p += AFB_THREADS) { dig[p] = (uint8_t)((uint32_t)(kx[p] >> a.shift) & 255u); tied |= idx[p] >> 31; }
+            if (tied) s_tied = 1;
+            __syncthreads();
+        }
+        const bool tiedb = s_tied != 0;
+        if (fused && nb == 2) {
+            /* 3f. two digits d0 < d1, closed form (lq_af_two_dest) for tied and untied buckets alike (any partition by digit serves
+             * the latter).  b1 = "digit is d1"; foreign = b1 below n0, !b1 from n0 on.  P / Z = the foreign positions of the two regions. */
+            const uint32_t d0 = s_d0, n0 = s_cnt[d0], inv = dA == d0 ? 0u : 0xffffffffu, nw = (n + 31) >> 5;
+            uint32_t *P = dest, *Z = dest + n0;
+            uint32_t runP = 0, runZ = 0;
+            for (uint32_t w0 = 0; w0 < nw; w0 += AFB_THREADS) {                      /* the lists, from the bits alone */
+                const uint32_t w = w0 + tid, pw = w << 5;
+                uint32_t f0 = 0, f1 = 0;
+                if (w < nw) {
+                    const uint32_t b1 = afb_bits[w] ^ inv;
+                    const uint32_t vm = n - pw >= 32 ? 0xffffffffu : (1u << (n - pw)) - 1u;              /* positions below n */
+                    const uint32_t lo = pw >= n0 ? 0u : n0 - pw >= 32 ? 0xffffffffu : (1u << (n0 - pw)) - 1u;   /* positions below n0 */
+                    f0 = b1 & lo & vm; f1 = ~b1 & ~lo & vm;
+                }
+                uint32_t tot;
+                const uint32_t ex = lq_block_excl_scan<uint32_t>(__popc(f0) | __popc(f1) << 16, scan_sm, &tot);
+                uint32_t r0 = runP + (ex & 0xffffu), r1 = runZ + (ex >> 16);
+                while (f0) { P[r0++] = pw + (__ffs(f0) - 1); f0 &= f0 - 1; }
+                while (f1) { Z[r1++] = pw + (__ffs(f1) - 1); f1 &= f1 - 1; }
+                runP += tot & 0xffffu; runZ += tot >> 16;
+            }
+            __syncthreads();
+            /* the permutation: a warp takes 32 AFB_V consecutive elements, 32 at a time (one word of the bitmap each) */
+            uint32_t cumP = 0, cumZ = 0; int par = 0;
+            for (uint32_t t0 = 0; t0 < n; t0 += AFB_THREADS * AFB_V, par ^= 1) {
+                const uint32_t wbase = t0 + wid * 32 * AFB_V;
+                uint32_t f0[AFB_V], f1[AFB_V], c0 = 0, c1 = 0; uint64_t kk[AFB_V]; uint32_t ii[AFB_V];
+                #pragma unroll
+                for (int u = 0; u < AFB_V; ++u) {
+                    const uint32_t pw = wbase + u * 32, p = pw + lane;
+                    f0[u] = 0; f1[u] = 0;
+                    if (pw < n) {
+                        const uint32_t b1 = afb_bits[pw >> 5] ^ inv;
+                        const uint32_t vm = n - pw >= 32 ? 0xffffffffu : (1u << (n - pw)) - 1u;
+                        const uint32_t lo = pw >= n0 ? 0u : n0 - pw >= 32 ? 0xffffffffu : (1u << (n0 - pw)) - 1u;
+                        f0[u] = b1 & lo & vm; f1[u] = ~b1 & ~lo & vm;
+                    }
+                    if (p < n) { kk[u] = kx[p]; ii[u] = idx[p]; }
+                    c0 += __popc(f0[u]); c1 += __popc(f1[u]);
+                }
+                if (lane == 0) s_wt[par][wid] = c0 | c1 << 16;
+                __syncthreads();
+                const uint32_t wv = lane < AFB_THREADS / 32 ? s_wt[par][lane] : 0u;
+                const uint32_t before = lq_warp_sum(lane < wid ? wv : 0u), all = lq_warp_sum(wv);
+                uint32_t r0 = cumP + (before & 0xffffu), r1 = cumZ + (before >> 16);
+                #pragma unroll
+                for (int u = 0; u < AFB_V; ++u) {
+                    const uint32_t p = wbase + u * 32 + lane;
+                    if (p < n) {
+                        const bool low = p < n0;
+                        const uint32_t fm = low ? f0[u] : f1[u];
+                        const uint32_t rk = (low ? r0 : r1) + __popc(fm & lt);
+                        const uint32_t d = lq_af_two_dest(p, n0, (fm >> lane) & 1u, rk, runP, P, Z);
+                        idx2[d] = ii[u]; kx2[d] = kk[u];
+                    }
+                    r0 += __popc(f0[u]); r1 += __popc(f1[u]);
+                }
+                cumP += all & 0xffffu; cumZ += all >> 16;
+            }
+            __syncthreads();
+            afb_subbuckets(a, beg, n, s_cnt, s_start);
+            continue;
+        }
         if (nb > 2 && tiedb) {   /* the sequential walk: lq_af_walk3_k / lq_af_walkf_k, then lq_af_place_k */
             if (tid == 0) af_push_walk(a, beg, n, s_few != 0);
             continue;
@@ -1830,6 +1912,7 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
     LQ_TRY(sc->wst.ensure((size_t)AFS_GRID * AFS_WALKERS * AFS_ROW * 4));
     LQ_CUDA_OK(cudaFuncSetAttribute(lq_af_walk3_k, cudaFuncAttributeMaxDynamicSharedMemorySize, AFS_WALKERS * 4096));
     LQ_CUDA_OK(cudaFuncSetAttribute(lq_af_walkf_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AffSmem)));
+    LQ_CUDA_OK(cudaFuncSetAttribute(lq_af_big_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(g_afb_bitw * 4)));
     AfBkt *bk[2] = { sc->bkt.as<AfBkt>(), sc->bkt.as<AfBkt>() + bcap };
     AfBkt *wl = sc->bkt.as<AfBkt>() + 2 * bcap;
     AfBkt *wls = sc->bkt.as<AfBkt>() + 3 * bcap;                                                     /* short walks: ctr[14] = count, ctr[15] = cursor */
@@ -1854,6 +1937,7 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         a.wlist = wl; a.n_wlist = ctr + 9; a.wcursor = ctr + 10;
         a.wlist_s = wls; a.n_wlist_s = ctr + 14; a.wcursor_s = ctr + 15; a.wcursor_f = ctr + 48;
         a.wlist_w = wlw; a.n_wlist_w = ctr + 52; a.wcursor_w = ctr + 53; a.wph = sc->wph.as<lq_afq_phase>(); a.wph_cap = (uint32_t)bcapw;
+        a.bitw = g_afb_bitw; a.two = g_afb_bitw && ((shift == 56 && ix->n_seq <= (1u << 24)) || (shift == 48 && ix->n_seq <= (1u << 17)));
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 14, 0, 8, st));
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 48, 0, 4, st));
         LQ_CUDA_OK(cudaMemsetAsync(ctr + 52, 0, 8, st));
@@ -1866,7 +1950,7 @@ static int seed_and_sort(LqQueryDev *qd, const LqIndexDev *ix, const MapTables &
         unsigned long long *n_elem = (unsigned long long*)(ctr + 16);
         a.n_elem = n_elem + (shift >> 3);
         { LqProfScope ps(lvl_name[shift >> 3], st, 2, 0);
-          lq_af_big_k<<<148 * g_afb_ctas, AFB_THREADS, 0, st>>>(a);
+          lq_af_big_k<<<148 * g_afb_ctas, AFB_THREADS, g_afb_bitw * 4, st>>>(a);
           lq_af_level_k<<<148 * 16, AF_WARPS * 32, 0, st>>>(a); }
         a.n_elem = n_elem + 8 + (shift >> 3);
         { LqProfScope ps(wlk_name[shift >> 3], st, 2, 0);
