@@ -357,6 +357,7 @@ __device__ __forceinline__ void af_append(const AfArgs &a, uint32_t beg, uint32_
 /* a tied bucket with more than two digits goes to one of the two walk kernels (called by one thread) */
 __device__ __forceinline__ void af_push_walk(const AfArgs &a, uint32_t beg, uint32_t n, bool few /* no digit above 15 */)
 {
+    atomicAdd(a.n_elem, 0ULL - (unsigned long long)n);    /* profiling: the level only looked at these elements, the walk's place kernel moves them */
     if (n < AFW_SMALL) { const uint32_t at = atomicAdd(a.n_wlist_s, 1u); a.wlist_s[at].beg = beg; a.wlist_s[at].end = beg + n; }
     else if (few) { const uint32_t at = atomicAdd(a.n_wlist_w, 1u); a.wlist_w[at].beg = beg; a.wlist_w[at].end = beg + n; }
     else { const uint32_t at = atomicAdd(a.n_wlist, 1u); a.wlist[at].beg = beg; a.wlist[at].end = beg + n; }

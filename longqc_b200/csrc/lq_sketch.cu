@@ -549,8 +549,13 @@ __global__ void __launch_bounds__(RK_THREADS) lq_sketch_roll_k(SkArgs a)
  * Segments the form declines (ambiguous bases, palindrome-rich look-back, equal k-mers inside a read's first window) run
  * rk_scan into a small pool; a tile with more of those than the pool holds, or with a row that overflows, runs rk_scan
  * everywhere, writing in place. */
-#define PK_CAP 48                        /* records a thread can stage (64 bases write ~21) */
+#define PK_CAP 32                        /* records a thread can stage: 64 bases write 21.5 on average, more than 30 with probability 1e-5.
+                                          * The unrolled blocks store unchecked: a row that overflows runs into the next one (into the
+                                          * pool behind the last one), which only ever happens in a tile that is then scanned again in place */
 #define PK_STRIDE (PK_CAP + 1)
+#ifndef PK_MIN_CTAS
+#define PK_MIN_CTAS 8                    /* 64 registers: with 23 KB of shared memory per CTA, 8 to 9 CTAs per SM */
+#endif
 #define PK_FB 6
 #define PK_SLOTS (RK_TILE / LQ_SLOT)     /* 64 slots per tile */
 #define PK_OFF_NM ((PK_SLOTS + 1) * LQ_SLOT_W2 * 4)
@@ -609,8 +614,8 @@ __device__ __forceinline__ void pk_general_inplace(const SkArgs &a, uint32_t rd,
 
 extern __shared__ __align__(16) unsigned char pk_smem[];
 
-template <int W, int K>
-__global__ void __launch_bounds__(RK_THREADS) lq_sketch_pk_k(SkArgs a, int use_bulk)
+template <int W, int K, int MINB>
+__global__ void __launch_bounds__(RK_THREADS, MINB) lq_sketch_pk_k(SkArgs a, int use_bulk)
 {
     typedef lq_pk_tr<(K > 12)> T;
     typedef typename T::key key;
@@ -753,10 +758,16 @@ extern "C" void lqcov_debug_sketch_tiled(int on) { g_sketch_tiled = on == 1; g_s
 /* the 64-bases-per-thread kernels share the tile geometry (RK_TILE bases per CTA) */
 static void sk_launch_seg64(const SkArgs &a, unsigned nblk, cudaStream_t st)
 {
-    static int once = (cudaFuncSetAttribute(lq_sketch_pk_k<5, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM(8)), 0);
+    static int once = (cudaFuncSetAttribute(lq_sketch_pk_k<5, 15, PK_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM(8)), 0);
+    static int minb = getenv("LQCOV_SKETCH_MINB") ? atoi(getenv("LQCOV_SKETCH_MINB")) : PK_MIN_CTAS;   /* tuning: registers per thread through the CTAs-per-SM bound */
     (void)once;
-    if (a.w == 5 && a.k == 12 && g_sketch_pk) lq_sketch_pk_k<5, 12><<<nblk, RK_THREADS, PK_SMEM(4), st>>>(a, g_sketch_pk != 2);          /* LongQC's overlap runs */
-    else if (a.w == 5 && a.k == 15 && g_sketch_pk) lq_sketch_pk_k<5, 15><<<nblk, RK_THREADS, PK_SMEM(8), st>>>(a, g_sketch_pk != 2);     /* --fast */
+    const int bulk = g_sketch_pk != 2;
+    if (a.w == 5 && a.k == 12 && g_sketch_pk) {                                                         /* LongQC's overlap runs */
+        if (minb == 7) lq_sketch_pk_k<5, 12, 7><<<nblk, RK_THREADS, PK_SMEM(4), st>>>(a, bulk);
+        else if (minb == 9) lq_sketch_pk_k<5, 12, 9><<<nblk, RK_THREADS, PK_SMEM(4), st>>>(a, bulk);
+        else lq_sketch_pk_k<5, 12, PK_MIN_CTAS><<<nblk, RK_THREADS, PK_SMEM(4), st>>>(a, bulk);
+    }
+    else if (a.w == 5 && a.k == 15 && g_sketch_pk) lq_sketch_pk_k<5, 15, PK_MIN_CTAS><<<nblk, RK_THREADS, PK_SMEM(8), st>>>(a, bulk);     /* --fast */
     else if (a.w == 5) lq_sketch_roll_k<5><<<nblk, RK_THREADS, 0, st>>>(a);
     else lq_sketch_roll_k<10><<<nblk, RK_THREADS, 0, st>>>(a);
 }

@@ -192,8 +192,8 @@ LQ_HD void lq_pk_slow(const uint32_t *lw8, const int P, lq_pk_state<W, (K > 12)>
 
 /* lw8: the packed words of the 64 bases before the segment and of the segment; nw4: their ambiguity bits; i0: the segment's
  * first base in its read (a multiple of 64); nseg: its bases (1..64); is_last: the read ends with it.  The sink receives the
- * records in the reference's order as keys (put: at most one per base from an unrolled block, at most 16 between two calls of
- * room(); push: checked); lq_pk_p2z() turns a key's code into pos<<1|strand.  Returns 0; 1 = not here; 2 = the sink is full
+ * records in the reference's order as keys (put: at most one per base from an unrolled block, NOT checked -- a sink of fixed
+ * size must have 64 entries of slack behind it and is full when room() < 0 at the end; push: checked); lq_pk_p2z() turns a key's code into pos<<1|strand.  Returns 0; 1 = not here; 2 = the sink is full
  * (in both cases whatever the sink holds is to be dropped). */
 LQ_HD uint32_t lq_pk_p2z(int i0, uint32_t code) { return (uint32_t)(2 * i0 + 127) - code; }
 
@@ -256,7 +256,6 @@ LQ_HD int lq_pk_segment(const uint32_t *lw8, const uint32_t *nw4, const int i0, 
             const uint32_t cb = 255u - 32u * (uint32_t)B;
             const bool first = i0 == 0 && B * 16 < W + K - 1, gated = first || nseg < (B + 1) * 16;
             bool slow = dup;
-            if (sink.room() < 17) return 2;
             s.d = T::none();
             if (!slow) {
                 const lq_pk_state<W, (K > 12)> keep = s;
