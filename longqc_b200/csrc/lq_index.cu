@@ -73,8 +73,10 @@ __global__ void __launch_bounds__(RS_THREADS, 3) lq_rs_scatter_k(const uint32_t 
     const uint32_t lt = (1u << lane) - 1;
     for (int d = lane; d < 256; d += 32) wbase[wid][d] = 0;
     __syncwarp();
-    /* 1. per-warp digit counts */
-    uint32_t kv[RS_ROWS]; uint64_t yv[RS_ROWS];   /* the payload is fetched up front too: the ordering loop below is a chain of warp syncs, no load may wait inside it */
+    /* 1. per-warp digit counts, and for every record its rank among the warp's records of the same digit (rows in order, lanes in
+     *    order inside a row): the only sequential chain of the kernel -- one match + one counter update per row */
+    uint32_t kv[RS_ROWS]; uint64_t yv[RS_ROWS];   /* the payload is fetched up front too: the chain below is a chain of warp syncs, no load may wait inside it */
+    uint16_t rk[RS_ROWS];
     #pragma unroll
     for (int r = 0; r < RS_ROWS; ++r) { const uint64_t i = base + (uint64_t)r * 32 + lane; kv[r] = i < n ? key_in[i] : 0; yv[r] = i < n ? y_in[i] : 0; }
     #pragma unroll
@@ -82,11 +84,14 @@ __global__ void __launch_bounds__(RS_THREADS, 3) lq_rs_scatter_k(const uint32_t 
         const uint64_t i = base + (uint64_t)r * 32 + lane;
         const bool ok = i < n;
         const uint32_t act = __ballot_sync(0xffffffffu, ok);
+        uint32_t d = 0, peers = 0;
         if (ok) {
-            const uint32_t d = (kv[r] >> shift) & 255u;
-            const uint32_t peers = __match_any_sync(act, d);
-            if ((peers & lt) == 0) wbase[wid][d] += __popc(peers);
+            d = (kv[r] >> shift) & 255u;
+            peers = __match_any_sync(act, d);
+            rk[r] = (uint16_t)(wbase[wid][d] + __popc(peers & lt));
         }
+        __syncwarp();
+        if (ok && (peers & lt) == 0) wbase[wid][d] += __popc(peers);
         __syncwarp();
     }
     __syncthreads();
@@ -102,25 +107,16 @@ __global__ void __launch_bounds__(RS_THREADS, 3) lq_rs_scatter_k(const uint32_t 
         s_gb[d] = gbase[(uint64_t)d * nblk + blockIdx.x] - ds;
     }
     __syncthreads();
-    /* 3. order the CTA's records by digit in shared memory, rows in order */
+    /* 3. order the CTA's records by digit in shared memory: every destination is known, nothing waits on anything */
     #pragma unroll
     for (int r = 0; r < RS_ROWS; ++r) {
         const uint64_t i = base + (uint64_t)r * 32 + lane;
-        const bool ok = i < n;
-        const uint32_t act = __ballot_sync(0xffffffffu, ok);
-        uint32_t d = 0, peers = 0, dst = 0;
-        if (ok) {
-            d = (kv[r] >> shift) & 255u;
-            peers = __match_any_sync(act, d);
-            dst = s_dstart[d] + wbase[wid][d] + __popc(peers & lt);
-        }
-        __syncwarp();
-        if (ok) {
-            if ((peers & lt) == 0) wbase[wid][d] += __popc(peers);
+        if (i < n) {
+            const uint32_t d = (kv[r] >> shift) & 255u;
+            const uint32_t dst = s_dstart[d] + wbase[wid][d] + rk[r];
             s_key[dst] = kv[r]; s_y[dst] = yv[r];
             if (sp_in) s_sp[dst] = sp_in[i];
         }
-        __syncwarp();
     }
     __syncthreads();
     /* 4. write out: record j of the CTA goes to (global base of its digit) + j */
