@@ -31,7 +31,7 @@ def short(n):
 
 
 SCOPE_OF = {  # kernels that are a profiling scope of their own
-    "lq_pack_k": "pack", "lq_sketch_lane_k<5>": "sketch", "lq_sketch_lane_k<10>": "sketch", "lq_sketch_roll_k<5>": "sketch", "lq_sketch_roll_k<10>": "sketch",
+    "lq_pack_k": "pack", "lq_sketch_pk_k<5, 12, 8>": "sketch", "lq_sketch_pk_k<5, 15, 8>": "sketch", "lq_sketch_roll_k<5>": "sketch", "lq_sketch_roll_k<10>": "sketch",
     "lq_count_k": "idx_count", "lq_rs_hist_k": "radix_hist", "lq_rs_scatter_k": "radix_scatter", "lq_lookup_k": "seed_lookup",
     "lq_filter_count_k": "seed_filter", "lq_fill_k": "seed_fill", "lq_fill_masked_k": "seed_fill_filtered", "lq_gather_k": "seed_gather",
     "lq_runs_k": "runs", "lq_runs_emit_k": "runs", "lq_runs_q_k": "runs", "lq_chain_small_k": "chain_small", "lq_chain_k": "chain",
