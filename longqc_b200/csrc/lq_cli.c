@@ -463,7 +463,7 @@ int lqcov_main(int argc, char **argv)
     }
     if (qr) lqcov_reader_close(qr);
     TL("table written");
-    if (!getenv("LQCOV_FAST_EXIT")) for (int i = 0; i < n_dev; ++i) lqcov_destroy(dv[i].c);
+    { const char *fe = getenv("LQCOV_FAST_EXIT"); if (!fe || fe[0] == '0') for (int i = 0; i < n_dev; ++i) lqcov_destroy(dv[i].c); }   /* set (by lq_main_cov.c): the process is about to _exit */
     fprintf(stderr, "\n[M::%s] Real time: %.3f sec; CPU: %.3f sec\n", __func__, wall() - t0, cpu());
     return rc;
 }

@@ -758,12 +758,13 @@ extern "C" void lqcov_debug_sketch_tiled(int on) { g_sketch_tiled = on == 1; g_s
 /* the 64-bases-per-thread kernels share the tile geometry (RK_TILE bases per CTA) */
 static void sk_launch_seg64(const SkArgs &a, unsigned nblk, cudaStream_t st)
 {
-    static int once = (cudaFuncSetAttribute(lq_sketch_pk_k<5, 15, PK_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM(8)), 0);
-    (void)once;
     const int bulk = g_sketch_pk != 2;
     /* 7 / 8 / 9 CTAs per SM (72 / 64 / 56 registers) were measured: 3.71 / 3.64 / 3.76 ms -- occupancy is not what limits the kernel */
     if (a.w == 5 && a.k == 12 && g_sketch_pk) lq_sketch_pk_k<5, 12, PK_MIN_CTAS><<<nblk, RK_THREADS, PK_SMEM(4), st>>>(a, bulk);          /* LongQC's overlap runs */
-    else if (a.w == 5 && a.k == 15 && g_sketch_pk) lq_sketch_pk_k<5, 15, PK_MIN_CTAS><<<nblk, RK_THREADS, PK_SMEM(8), st>>>(a, bulk);     /* --fast */
+    else if (a.w == 5 && a.k == 15 && g_sketch_pk) {                                                                                   /* --fast */
+        cudaFuncSetAttribute(lq_sketch_pk_k<5, 15, PK_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM(8));   /* per device: every launch, the executable drives several GPUs from one process */
+        lq_sketch_pk_k<5, 15, PK_MIN_CTAS><<<nblk, RK_THREADS, PK_SMEM(8), st>>>(a, bulk);
+    }
     else if (a.w == 5) lq_sketch_roll_k<5><<<nblk, RK_THREADS, 0, st>>>(a);
     else lq_sketch_roll_k<10><<<nblk, RK_THREADS, 0, st>>>(a);
 }

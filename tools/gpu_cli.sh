@@ -14,11 +14,11 @@ print("files ready %.1fs" % (time.time()-t0), f.tf)
 open('gpurun_out/cli_files.txt','w').write(f.tf+"\n"+f.qf+"\n")
 PY
 TF=$(sed -n 1p gpurun_out/cli_files.txt); QF=$(sed -n 2p gpurun_out/cli_files.txt)
-for v in "" "LQCOV_FAST_EXIT=1" "LQCOV_READER_THREADS=8" "LQCOV_READER_THREADS=32"; do
+for v in "" "LQCOV_FAST_EXIT=0" ""; do
   for i in 1 2 3; do
     echo "== $v run $i" >> gpurun_out/cli_timeline.log
     ( time env $v longqc_b200/bin/minimap2-coverage -Y -l 0 -q 160 -k 12 -w 5 -I 4G -p 160 -t 16 $TF $QF > /dev/shm/out.tsv ) 2>> gpurun_out/cli_timeline.log
   done
 done
 md5sum /dev/shm/out.tsv >> gpurun_out/cli_timeline.log
-grep -E "^\[T::|^== |real" gpurun_out/cli_timeline.log | tail -120
+grep -E "table written|Real time|^== |real" gpurun_out/cli_timeline.log | tail -60; tail -1 gpurun_out/cli_timeline.log
