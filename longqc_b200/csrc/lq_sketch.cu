@@ -1,19 +1,20 @@
-/* lq_sketch.cu -- K0 (ASCII -> 2-bit + ambiguity planes) and K1 (position-parallel (w,k)-minimizer sketch).
+/* lq_sketch.cu -- K0 (ASCII -> 2-bit + ambiguity planes) and K1 ((w,k)-minimizer sketch).
  *
  * Replaces, on the device, mm_sketch() as called for every target read (reference index.c:291-302)
- * and every query read (minimap2-coverage.c:419, lqmap.c:131).  See lq_sketch_core.h for why the
- * position-parallel form is exact.
- *
- * K1 launch shape: one CTA per tile of 1024 bases (8 slots), 256 threads, 4 bases per thread.
- *   stage 0  the tile's 2-bit words (+256-base halo) and ambiguity words go to shared memory
- *   stage A  every base of tile+128-base halo gets its candidate: 2k-bit hash of min(fw,rv), strand bit,
- *            and an "ok" bit (pushes into the reference's ring: unambiguous and not palindromic)
- *   stage B  every base of the tile evaluates what the reference scan pushes while processing it:
- *            closed form over the candidates at i-w..i when the last w+k bases are all ok (fast path),
- *            else a bounded replay of the reference state machine (lq_sketch_slow_at)
- *   output   records are written in base order: block scan of the per-thread record counts + the CTA's
- *            base offset (from the count pass, see lq_sketch_run()).
- * Output is therefore globally ordered by (read, position) == ascending y, which the index build needs.
+ * and every query read (minimap2-coverage.c:419, lqmap.c:131).  Four exact forms of K1, by (w, k):
+ *   lq_sketch_pk_k    w = 5, k = 12 / 15 (LongQC's overlap runs): 64 bases per thread in registers, candidates as single
+ *                     integers, tile words by cp.async.bulk -- lq_sketch_pk_core.h.  The default and the fast one.
+ *   lq_sketch_roll_k  w = 5 / 10, other k <= 15: a thread runs the reference scan over 64 bases after a certified warm-up
+ *                     (rk_scan, also the general state machine the packed-key kernel falls back on for the segments it declines)
+ *   lq_sketch_k       any other (w, k <= 15): position-parallel closed form over a tile of 1024 bases (lq_sketch_core.h):
+ *                       stage 0  the tile's 2-bit words (+256-base halo) and ambiguity words go to shared memory
+ *                       stage A  every base of tile+128-base halo gets its candidate: 2k-bit hash of min(fw,rv), strand bit,
+ *                                and an "ok" bit (pushes into the reference's ring: unambiguous and not palindromic)
+ *                       stage B  every base evaluates what the reference scan pushes while processing it: closed form over
+ *                                the candidates at i-w..i when the last w+k bases are all ok, else a bounded replay
+ *   lq_sketch_seq_k   HPC mode (-H) and k > 15: the restartable state machine itself, one thread per read
+ * All of them write their records in base order (block scan of the per-thread counts + the tile's place from a decoupled
+ * look-back over the tiles): the output is globally ordered by (read, position) == ascending y, which the index build needs.
  */
 #include "lq_cuda.cuh"
 #include "lq_sketch_core.h"

@@ -15,6 +15,12 @@
  * minimum, and the position of the minimum comes back out of the key: a step is two 3-input minima and one comparison.
  * k-mers come out of the packed words by funnel shifts with compile-time amounts (a segment starts on a word boundary):
  * the forward k-mer from the 2-bit-group-reversed words, the complement one from the words as they are.
+ * The segment is scanned in four blocks of 16 bases by ONE unrolled copy of the step (lq_pk_fast): the frame of the words moves
+ * with the block, the codes stay positions in the segment's frame.  The unrolled step is straight-line and knows neither twins
+ * (fact 4, second case) nor gates; it only records the smallest XOR between a candidate and the entries of its window, and a block
+ * that saw one below 256 (two equal k-mers in one window, fact 3) is undone and scanned again by the general step (lq_pk_slow,
+ * run-time position, writes the twins), as is the block after it.  A read's first and last blocks run a gated copy of the unrolled
+ * step (lq_pk_fast_g).
  *
  * A thread may start in the middle of a read ("case A") when the look-back is free of ambiguous bases and holds >= w+k pushes
  * (counted: palindromic k-mers do not push), the last w of them inside the part that is hashed -- then l >= w+k, the ring is
