@@ -21,7 +21,7 @@
 
 #define RS_WARPS 8
 #define RS_THREADS (RS_WARPS * 32)
-#define RS_ROWS 12
+#define RS_ROWS 8
 #define RS_CHUNK (RS_THREADS * RS_ROWS) /* records per CTA */
 
 /* ------------------------------------------------------------------ counts */
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(RS_THREADS) lq_rs_hist_k(const uint32_t *__res
  * "CTA order" == "warp, row, lane" order == input order.  The CTA's 4096 records are first ordered by digit in shared
  * memory (stable), then written out run by run, so that consecutive threads store to consecutive addresses. */
 #define RS_SMEM_BYTES (RS_CHUNK * (4 + 8 + 1) + RS_WARPS * 256 * 4 + 256 * 4 + 256 * 8 + 33 * 4 + 64)
-__global__ void __launch_bounds__(RS_THREADS, 4) lq_rs_scatter_k(const uint32_t *__restrict__ key_in, const uint64_t *__restrict__ y_in, const uint8_t *__restrict__ sp_in,
+__global__ void __launch_bounds__(RS_THREADS, 5) lq_rs_scatter_k(const uint32_t *__restrict__ key_in, const uint64_t *__restrict__ y_in, const uint8_t *__restrict__ sp_in,
                                                                uint64_t n, int shift, uint32_t nblk, const uint64_t *__restrict__ gbase,
                                                                uint32_t *__restrict__ key_out, uint64_t *__restrict__ y_out, uint8_t *__restrict__ sp_out)
 {
